@@ -1,0 +1,23 @@
+"""CPU oracle for the MKID SDR hot path -- TEST INFRASTRUCTURE ONLY.
+
+Every module here is a plain NumPy / pure-Python / C restatement of the
+reference's algorithm (creanero/MKIDS_SDR), each function citing the
+reference file:line it follows.  Nothing under ``mkids_sdr_b200/`` may import
+this package: only ``tests/``, ``__graft_entry__.smoke()`` and the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` do, and there only
+as the checker / reported CPU baseline, never as the product path.
+
+Pinned against the reference's own fixtures (see tests/golden/make_golden.py):
+  * lut.py        <- ChannelizerControls/dac.npy.npz  (bit-exact)
+  * fixed.py      <- castBin call sites in lib/set_alpha.py, set_base_thresh.py,
+                     set_svf.py (known answers), Utils/bin.py run under py3 for
+                     the py3-safe functions
+  * control.py    <- LUT/*.txt FIR tap files (quantised taps), ch_snap_0.txt
+  * trigger.py    <- ch_snap_0.txt
+  * decode.py     <- oracle/_ref/packetmaster_ref (the reference's own
+                     PacketMaster.c inner loop is not compilable: needs hdf5.h)
+                     -> restated in packetmaster_core.c; the bitfield layout is
+                     pinned by ROACH_Pulses.py:805-811 and PacketMaster.c:306.
+  * channelizer.py: PARITY UNPINNED -- the firmware data plane is absent from
+                     the reference; this float64 model is the parity definition.
+"""

@@ -1,0 +1,259 @@
+"""Pin the oracle against the reference's own fixtures / known answers (CPU only).
+
+Fixtures under tests/golden/ were condensed from /root/reference by
+tests/golden/make_golden.py."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from oracle import control, decode, fixed, lut, trigger
+
+
+# ------------------------------------------------------------------ LUT (a1,a2,a4,a5)
+def test_dac_golden_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'dac_golden.npz'))
+    I, Q, scale, ph = lut.freq_comb_lut('yes', [412e6], 512e6, 7812.5, [1.0])
+    assert ph[0] == 4.106624480316831
+    assert abs(scale - 1.1) < 1e-3
+    assert np.array_equal(I, g['I_dac'].astype(np.int64))
+    assert np.array_equal(Q, g['Q_dac'].astype(np.int64))
+    assert hashlib.sha256(I.astype('<i2').tobytes()).hexdigest() == str(g['I_dac_sha256'])
+    assert str(g['I_dac_sha256']).startswith('c449906788665797857b3b505edc5ebc')
+    assert str(g['Q_dac_sha256']).startswith('bbb728b827f6d4043cca562c646323c2')
+
+
+def test_dac_golden_through_define_dac_lut(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'dac_golden.npz'))
+    f = lut.dac_freqs_single(4.75e9, 4.65e9, 512e6, 7812.5)      # LO 4.65 GHz, tone 4.75 GHz
+    assert f == [412e6]
+    I, Q, _, _ = lut.freq_comb_lut('yes', f, 512e6, 7812.5, lut.dac_amplitudes([5.0]))
+    assert np.array_equal(I, g['I_dac'].astype(np.int64))
+
+
+def test_dds_golden_and_dram_image(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'dac_golden.npz'))
+    freqs_dds = lut.dds_freqs([4.75e9], 4.65e9, 512e6, 7812.5)
+    bins, resid = lut.select_bins(freqs_dds, 512e6, 7812.5)
+    assert bins[0] == 100 and resid[0] == 0.0
+    I_dds, Q_dds, _ = lut.define_dds_lut(resid, 512e6, 7812.5)
+    assert np.array_equal(I_dds, g['I_dds'].astype(np.int64))
+    assert np.array_equal(Q_dds, g['Q_dds'].astype(np.int64))
+    img = lut.pack_dram(g['I_dac'], g['Q_dac'], g['I_dds'], g['Q_dds'])
+    assert len(img) == 524288
+    assert img[:16].hex() == '000000001e28a0557fff7fff8f9abdbd'
+    assert hashlib.sha256(img).hexdigest() == \
+        '44b66622c49f414ceeae34d9011391c081bdf1ab06902a14de6243df3ff270d1'
+    assert lut.pack_dram_literal(g['I_dac'][:64], g['Q_dac'][:64], g['I_dds'][:64], g['Q_dds'][:64]) == img[:512]
+
+
+def test_literal_vs_vectorised_comb():
+    f = [k * 512e6 / 1024 for k in (3, 700, 129, 513)]
+    a = [1.0, 0.5, 0.25, 0.8]
+    I0, Q0, s0 = lut.freq_comb_lut_literal('yes', f, 512e6, 512e6 / 1024, a)
+    I1, Q1, s1, _ = lut.freq_comb_lut('yes', f, 512e6, 512e6 / 1024, a)
+    assert s0 == s1 and np.array_equal(I0, I1) and np.array_equal(Q0, Q1)
+
+
+def test_dds_known_answer():
+    # N=2^16 -> size 256, residual 3*7812.5, phase 0.3, echo='no'
+    I, Q, sc, _ = lut.freq_comb_lut('no', [23437.5], 2e6, 7812.5, [1.], [0.3], 'no')
+    assert sc == 0.9999850084539461
+    assert list(I[:6]) == [31303, 30506, 29544, 28421, 27145, 25721]
+    assert list(Q[:6]) == [9683, 11960, 14171, 16306, 18353, 20300]
+
+
+def test_select_bins_known_answers():
+    bins, res = lut.select_bins([412e6, 100023437.5, 255.5e6, 0], 512e6, 7812.5)
+    assert bins == [412, 100, 256, 0]
+    assert res == [0.0, 23437.5, -500000.0, 0.0]
+
+
+def test_seed_1000_phases():
+    ph = lut.random_phases(4)
+    assert list(ph) == [4.106624480316831, 0.7226099352629045, 5.9708033309423225, 3.029697928700732]
+
+
+# ------------------------------------------------------------------ fixed point (a15)
+def test_fixed_against_reference_py3_outputs(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'utils_bin_py3.npz'))
+    v = g['values']
+    for nb, bp, key in ((12, 9, 'reinterpret_12_9'), (16, 13, 'reinterpret_16_13'), (18, 16, 'reinterpret_18_16')):
+        assert np.array_equal(fixed.reinterpretBin(v, nb, bp), g[key])
+        # scalar extractBin (py2 semantics) agrees with the reference's vectorised routine
+        for x, want in zip(v[:300].tolist() + v[-50:].tolist(), list(g[key][:300]) + list(g[key][-50:])):
+            assert fixed.extractBin(x, nb, bp) == want
+    assert np.array_equal([fixed.bin12_9ToRad(x) for x in range(4096)], g['bin12_9ToRad'])
+    assert np.array_equal([fixed.bin12_9ToDeg(x) for x in range(4096)], g['bin12_9ToDeg'])
+    assert [fixed.binMask(n) for n in range(1, 33)] == g['binMask'].tolist()
+    assert [fixed.castBin(x) for x in g['castBin_in']] == g['castBin_trunc_12_9'].tolist()
+    assert [fixed.castBin(x, quantization='Round') for x in g['castBin_in']] == g['castBin_round_12_9'].tolist()
+    assert [fixed.peakfit(1, 3, 2), fixed.peakfit(1, 2, 3), fixed.peakfit(-5., -9., -6.)] == g['peakfit'].tolist()
+
+
+def test_fixed_known_answers():
+    # SURVEY App. C; call sites lib/set_alpha.py:11, set_base_thresh.py:10, set_svf.py:24-25
+    ka = {0x000: 0.0, 0x001: 0.001953125, 0x7FF: 3.998046875, 0x800: -4.0,
+          0x801: -3.998046875, 0xFFF: -0.001953125, 0x923: -3.431640625}
+    for k, v in ka.items():
+        assert fixed.extractBin(k) == v
+        assert fixed.bin12_9ToRad(k) == fixed.extractBin(k ^ 0x800)
+    assert fixed.castBin(0.08) == 40
+    assert fixed.castBin(0.08, quantization='Round') == 41
+    assert fixed.castBin(-0.08) == 4056
+    assert fixed.castBin(1., quantization='Round', nBits=16, binaryPoint=13) == 8192
+    assert fixed.castBin(2 * np.sin(np.pi * 200 / 1e6), quantization='Round', nBits=18, binaryPoint=16) == 82
+    assert fixed.castBin(1 / 0.7, quantization='Round', nBits=18, binaryPoint=16) == 93623
+    assert fixed.castBin(1.5 / 512, quantization='Round') == 2
+    assert fixed.castBin(2.5 / 512, quantization='Round') == 3      # py2 half away from zero
+    assert fixed.peakfit(1, 3, 2) == 3.0416666666666665
+    assert fixed.peakfit(1, 2, 3) == 2
+
+
+# ------------------------------------------------------------------ control plane (a6,a7,a10)
+def test_fir_quantisation_known_answers(golden_dir):
+    t = np.load(os.path.join(golden_dir, 'fir_taps.npz'))
+    assert control.fir_quantise(t['matched_30us']) == [160, 155, 150, 144, 140, 135, 130, 126, 122, 118, 115,
+                                                        111, 107, 104, 101, 97, 94, 90, 88, 84, 82, 79, 77, 74, 72, 69]
+    regs = [r[1] for r in control.fir_registers(t['matched_30us'])]
+    assert regs == [0x9B0A0, 0x90096, 0x8708C, 0x7E082, 0x7607A, 0x6F073, 0x6806B, 0x61065, 0x5A05E,
+                    0x54058, 0x4F052, 0x4A04D, 0x45048]
+    assert control.fir_quantise(t['BlackmanFilter_250kHz']) == [0, 0, 3, 8, 17, 32, 53, 80, 111, 142, 172, 194, 206,
+                                                                 206, 194, 172, 142, 111, 80, 53, 32, 17, 8, 3, 0, 0]
+
+
+def _snap_raw(golden_dir):
+    deg = np.load(os.path.join(golden_dir, 'ch_snap_0.npy'))
+    raw = deg / control.SCALE_TO_ANGLE
+    assert np.max(np.abs(raw - np.round(raw))) < 1e-6
+    return deg, np.round(raw).astype(np.int64)
+
+
+def test_snapshot_scaling_and_threshold(golden_dir):
+    deg, raw = _snap_raw(golden_dir)
+    assert len(raw) == 2048 and list(raw[:4]) == [18480, 18640, 19056, 18976]
+    thr, med, p5 = control.threshold_from_phase(raw)
+    assert thr == -5913
+    assert abs(med - 18961.6) < 1e-6 and abs(p5 - 16596.16) < 1e-6
+    assert abs(control.SCALE_TO_ANGLE * thr - (-41.356194)) < 1e-5
+    assert abs(control.SCALE_TO_ANGLE * med - 132.619587) < 1e-5
+
+
+def test_iq_snapshot_decode_matches_literal():
+    rng = np.random.default_rng(3)
+    buf = rng.integers(0, 256, 16 * 200, dtype=np.uint8).tobytes()
+    I0, Q0 = control.decode_iq_snapshot_literal(buf)
+    I1, Q1 = control.decode_iq_snapshot(buf)
+    assert np.array_equal(I0, I1) and np.array_equal(Q0, Q1)
+
+
+# ------------------------------------------------------------------ triggers (a11,a12)
+def test_trigger_known_answers(golden_dir):
+    deg, _ = _snap_raw(golden_dir)
+    assert trigger.trigger_rolling_literal(deg, 20, 1000, 10.) == [153]
+    assert trigger.trigger_rolling_literal(deg, 20, 1000, 15.) == [237]
+    assert trigger.trigger_rolling_literal(deg, 20, 1000, 20.) == []
+    assert trigger.trigger_block_literal(deg, 128, 10.) == [100, 309, 512, 731, 970, 1170, 1405, 1625]
+    assert trigger.trigger_block_literal(deg, 128, 15.) == [237, 440, 662, 912, 1112, 1708]
+    assert trigger.trigger_block_literal(deg, 128, 20.) == [239]
+
+
+def test_trigger_fast_form_equals_literal(golden_dir):
+    deg, _ = _snap_raw(golden_dir)
+    rng = np.random.default_rng(0)
+    x = np.concatenate([deg, deg[::-1] + rng.normal(0, 3, deg.size)])
+    for thr in (8., 12., 15.):
+        for L in (50, 300, 1000):
+            lit = trigger.trigger_rolling_literal(x, 20, L, thr)
+            d = trigger.rolling_candidates(x, 20)
+            fast = trigger.greedy_holdoff(d > thr, 120, L, len(x), L)
+            assert lit == fast
+
+
+# ------------------------------------------------------------------ decode (a14,a16)
+def test_word_layout_known_answer():
+    w = decode.pack_word(37, 0x5A3, 0x5A1, 0x7F0, 123456)
+    assert int(w) == 0x255A35A17F01E240
+    ch, ts, base, peak, p1 = decode.unpack_fields([w])
+    assert (ch[0], ts[0], base[0], peak[0], p1[0]) == (37, 123456, 0x7F0, 0x5A3, 0x5A1)
+    wire = decode.words_to_wire(np.full(8192, w, dtype=np.uint64))
+    assert wire[:4].hex() == '7f01e240' and wire[32768:32772].hex() == '255a35a1'
+    assert np.array_equal(decode.wire_to_words(wire), np.full(8192, w, dtype=np.uint64))
+
+
+def _mini_streams(seed=5, R=3, npix=7, secs=4, per_sec=300, cap=20):
+    rng = np.random.default_rng(seed)
+    streams = []
+    for r in range(R):
+        parts = []
+        for s in range(secs + 1):                      # one second more than exptime -> ignored tail
+            n = per_sec + int(rng.integers(0, 50))
+            ch = rng.integers(0, npix + 2, n)          # some non-pixel addresses
+            ch[rng.random(n) < 0.3] = 2                # hot pixel -> exceeds cap
+            ts = np.sort(rng.integers(0, 10 ** 6, n))
+            w = decode.pack_word(ch, rng.integers(0, 4096, n), rng.integers(0, 4096, n),
+                                 rng.integers(0, 4096, n), ts)
+            eos = np.array([0xFFFFFFFFFFFFFFFF if (s != 1 or r != 0) else 0xFF00000000000001], dtype=np.uint64)
+            parts += [w, eos]
+        streams.append(np.concatenate(parts))
+    return streams, npix, secs, cap
+
+
+def test_packetmaster_vectorised_equals_literal():
+    streams, npix, secs, cap = _mini_streams()
+    lit = decode.packetmaster_bin_literal(streams, npix, secs, cap)
+    vec = decode.packetmaster_bin(streams, npix, secs, cap, want_lists=True)
+    assert np.array_equal(lit['counts'], vec['counts'])
+    for k in ('n_eos', 'n_corrupt_eos', 'n_nonpixel', 'n_ignored'):
+        assert lit[k] == vec[k], k
+    assert lit['n_corrupt_eos'] == 1 and lit['n_nonpixel'] > 0 and lit['n_ignored'] > 0
+    assert vec['counts'].max() == cap - 1               # cap quirk: max_events-1 counted
+    off = vec['list_offsets']
+    npt = len(streams) * npix
+    for (sec, pix), words in lit['lists'].items():
+        k = sec * npt + pix
+        assert list(vec['list_words'][off[k]:off[k + 1]]) == words
+
+
+def test_packetmaster_c_core_equals_numpy():
+    import ctypes
+    so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_build', 'libpm_core.so')
+    if not os.path.exists(so):
+        import subprocess
+        subprocess.check_call(['make', '-C', os.path.dirname(os.path.dirname(so))])
+    lib = ctypes.CDLL(so)
+    streams, npix, secs, cap = _mini_streams(seed=9)
+    R = len(streams)
+    counts = np.zeros((secs, R * npix), dtype=np.int32)
+    hist = np.zeros((R * npix, 4096), dtype=np.uint32)
+    st = (ctypes.c_int64 * 5)()
+    for r, w in enumerate(streams):
+        w = np.ascontiguousarray(w)
+        rc = lib.pm_core_words(w.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(w.size), r, npix, R * npix, secs, cap,
+                               counts.ctypes.data_as(ctypes.c_void_p), None, hist.ctypes.data_as(ctypes.c_void_p),
+                               4096, 44, None, st)
+        assert rc == 0
+    vec = decode.packetmaster_bin(streams, npix, secs, cap)
+    assert np.array_equal(counts, vec['counts'])
+    assert (st[0], st[1], st[2], st[3]) == (vec['n_eos'], vec['n_corrupt_eos'], vec['n_nonpixel'], vec['n_ignored'])
+    assert np.array_equal(hist, decode.pixel_field_hist(streams, npix, secs, 'peak'))
+
+
+def test_read_pulses_wrap_and_hist():
+    rng = np.random.default_rng(11)
+    n = 2 ** 14
+    ch = rng.integers(0, 256, n)
+    w = decode.pack_word(ch, rng.integers(0, 4096, n), rng.integers(0, 4096, n), rng.integers(0, 4096, n),
+                         rng.integers(0, 2 ** 20, n))
+    b0 = (w & np.uint64(0xFFFFFFFF)).astype('>u4').tobytes()
+    b1 = (w >> np.uint64(32)).astype('>u4').tobytes()
+    out = decode.read_pulses([b0, b0], [b1, b1], [(100, 5000), (16000, 300)], sel_ch=3)
+    assert out['total_counts'] == [4900, 684]
+    idx = list(range(100, 5000)) + list(range(16000, n)) + list(range(0, 300))
+    assert np.array_equal(out['channel_count'], np.bincount(ch[idx], minlength=256))
+    lutb, edges = decode.deg_bin_lut()
+    sel = [i for i in idx if ch[i] == 3]
+    base_raw = ((w[sel] >> np.uint64(20)) & np.uint64(0xFFF)).astype(np.int64)
+    h = np.bincount(lutb[base_raw][lutb[base_raw] < 40], minlength=40)
+    assert np.array_equal(h, out['hgBase'])
