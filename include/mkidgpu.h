@@ -1,0 +1,133 @@
+/* mkidgpu.h -- C ABI of the B200-native (sm_100a) hot path of the ARCONS/MKID SDR readout.
+ *
+ * Plain C: pointers + sizes, no torch / C++ types.  Every entry point names the
+ * reference interface it replaces (paths relative to creanero/MKIDS_SDR).
+ *
+ * Conventions
+ *   - return 0 on success, a negative MKID_E* code on failure; the message is in
+ *     mkid_last_error(ctx).  The library never calls exit() (contrast
+ *     DataReadout/ReadoutControls/lib/PacketMaster.c:517-522 error()).
+ *   - there is NO CPU fallback: without an sm_100 device mkid_init returns MKID_ENODEV.
+ *   - data pointers may be host or device memory (detected with
+ *     cudaPointerGetAttributes); host buffers are staged through the context's stream,
+ *     pinned host memory (mkid_host_alloc) makes those copies asynchronous.
+ *   - the caller owns every buffer; the context owns only scratch memory.
+ *   - one context = one GPU + one CUDA stream; a context is not thread-safe, distinct
+ *     contexts are independent (mirrors "one GUI process per roach",
+ *     DataReadout/ChannelizerControls/ROACH_Setup.py:35-47).
+ *   - calls are asynchronous on the context stream unless they return host scalars;
+ *     mkid_sync() waits for the stream.
+ */
+#ifndef MKIDGPU_H
+#define MKIDGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MKID_OK        0
+#define MKID_ENODEV   -1   /* no sm_100 CUDA device */
+#define MKID_EINVAL   -2   /* bad argument */
+#define MKID_ENOMEM   -3   /* allocation failed */
+#define MKID_ECUDA    -4   /* CUDA runtime error (see mkid_last_error) */
+#define MKID_ENCCL    -5   /* NCCL error */
+
+typedef struct mkid_ctx mkid_ctx;
+
+/* ------------------------------------------------------------------ context */
+int  mkid_init(int device, mkid_ctx **out);
+void mkid_destroy(mkid_ctx *ctx);
+const char *mkid_last_error(mkid_ctx *ctx);     /* ctx may be NULL: last init error */
+int  mkid_sync(mkid_ctx *ctx);
+/* the CUDA stream of the context as an opaque handle (cudaStream_t) */
+void *mkid_stream(mkid_ctx *ctx);
+/* number of kernels this context has launched since creation (bench "gpu_launches") */
+int64_t mkid_launch_count(mkid_ctx *ctx);
+/* device timing on the context stream: record returns an event slot id (0..63) */
+int  mkid_event_record(mkid_ctx *ctx, int slot);
+int  mkid_event_elapsed_ms(mkid_ctx *ctx, int slot_start, int slot_stop, float *ms);
+/* pinned host / device memory helpers for callers without torch */
+int  mkid_host_alloc(mkid_ctx *ctx, size_t bytes, void **out);
+int  mkid_host_free(mkid_ctx *ctx, void *p);
+int  mkid_dev_alloc(mkid_ctx *ctx, size_t bytes, void **out);
+int  mkid_dev_free(mkid_ctx *ctx, void *p);
+int  mkid_memcpy(mkid_ctx *ctx, void *dst, const void *src, size_t bytes);   /* async on the stream */
+int  mkid_memset(mkid_ctx *ctx, void *dst, int value, size_t bytes);
+/* writes > L2-size scratch so the next timed kernel starts with a cold L2 */
+int  mkid_flush_l2(mkid_ctx *ctx);
+const char *mkid_version(void);
+
+/* ------------------------------------------------------------------ photon-word decode (K6)
+ * Replaces the receive/bin loop of DataReadout/ReadoutControls/lib/PacketMaster.c:286-397
+ * and the per-word unpack of DataReadout/ChannelizerControls/ROACH_Pulses.py:795-832.
+ *
+ * A "segment" is a contiguous run of one roach's word stream: words
+ * [seg_offset[i], seg_offset[i+1]) of the input belong to roach seg_roach[i] and start
+ * with seg_sec[i] seconds already closed (number of end-of-second words seen before).
+ * On return seg_sec_out[i] (if not NULL) holds the seconds closed at the end of the
+ * segment, so a stream can be decoded in pieces (per bundle, per file chunk, per GPU).
+ */
+typedef struct {
+    int32_t n_roaches;          /* NROACHES                               PacketMaster.c:50   */
+    int32_t npix_per_roach;     /* NPIXELS_PER_ROACH                      PacketMaster.c:52   */
+    int32_t exptime;            /* seconds kept; later words are ignored  PacketMaster.c:327  */
+    int32_t max_events;         /* MAX_EVENTS_PER_SEC (2500)              PacketMaster.c:55   */
+    int32_t hist_field_shift;   /* 44 = peak, 32 = p1, 20 = base; < 0: no pulse-height histogram */
+    int32_t n_bins;             /* bins per pixel of the pulse-height histogram */
+    const uint16_t *bin_lut;    /* 4096 entries raw-field -> bin (>= n_bins: dropped); NULL = identity */
+} mkid_decode_cfg;
+
+typedef struct {
+    int64_t n_eos;              /* end-of-second words seen while sec < exptime        (:329) */
+    int64_t n_corrupt_eos;      /* adr==255 but word != all ones, "Corrupted EOS!"     (:331) */
+    int64_t n_nonpixel;         /* adr >= npix_per_roach, "Photon from non-pixel"      (:382) */
+    int64_t n_ignored;          /* words after sec == exptime                          (:327) */
+    int64_t n_valid;            /* photon words binned (before the 2500 cap)                  */
+} mkid_decode_stats;
+
+/* Flat little-endian u64 words.  counts_raw [exptime][n_roaches*npix_per_roach] u32 and
+ * hist [n_roaches*npix_per_roach][n_bins] u32 are ACCUMULATED into (caller zeroes them):
+ * counts_raw holds uncapped per-(second,pixel) counts so that partial results from
+ * several segments/GPUs can be summed; mkid_counts_cap() then applies PacketMaster's
+ * cap quirk (min(count, max_events-1), PacketMaster.c:373-380).  stats is accumulated too
+ * (device or host pointer; host pointer => the call synchronises). */
+int mkid_decode_words(mkid_ctx *ctx, const uint64_t *words, int64_t n_words,
+                      const int64_t *seg_offset, const int32_t *seg_roach,
+                      const int32_t *seg_sec, int32_t *seg_sec_out, int32_t n_segments,
+                      const mkid_decode_cfg *cfg, uint32_t *counts_raw, uint32_t *hist,
+                      mkid_decode_stats *stats);
+
+/* Wire format of DataReadout/ReadoutControls/lib/PulseServer.c:318-352 as received by
+ * PacketMaster.c:286-287: per bundle 8192 big-endian u32 low halves then 8192 big-endian
+ * u32 high halves.  Segment offsets are in BUNDLES. */
+int mkid_decode_wire(mkid_ctx *ctx, const uint32_t *wire, int64_t n_bundles,
+                     const int64_t *seg_offset, const int32_t *seg_roach,
+                     const int32_t *seg_sec, int32_t *seg_sec_out, int32_t n_segments,
+                     const mkid_decode_cfg *cfg, uint32_t *counts_raw, uint32_t *hist,
+                     mkid_decode_stats *stats);
+
+/* counts[i] = min(counts_raw[i], max_events-1)   (PacketMaster.c:373-380), in place or not */
+int mkid_counts_cap(mkid_ctx *ctx, const uint32_t *counts_raw, uint32_t *counts, int64_t n,
+                    int32_t max_events);
+
+/* Field unpack of ROACH_Pulses.py:805-811 into structure-of-arrays (any output may be NULL):
+ * ch = w>>56, peak = (w>>44)&0xfff, p1 = (w>>32)&0xfff, base = (w>>20)&0xfff, ts = w&0xfffff */
+int mkid_unpack_fields(mkid_ctx *ctx, const uint64_t *words, int64_t n_words, uint8_t *ch,
+                       uint32_t *ts, uint16_t *base, uint16_t *peak, uint16_t *p1);
+
+/* Utils/binTools.py:50-64 reinterpretBin: two's-complement field of nBits with binaryPoint
+ * fractional bits, u64 -> f64.  (Utils/bin.py:18-29 extractBin is its scalar form.) */
+int mkid_reinterpret_bin(mkid_ctx *ctx, const uint64_t *values, int64_t n, int32_t n_bits,
+                         int32_t binary_point, int32_t n_bits_after_end, double *out);
+
+/* quick-look image of PacketMaster.c:1029-1045: image[i] = (uint16) counts_sec[pixel_adr[i]] */
+int mkid_quicklook_image(mkid_ctx *ctx, const uint32_t *counts_sec, const int32_t *pixel_adr,
+                         int32_t n_image_pixels, uint16_t *image);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MKIDGPU_H */

@@ -1,0 +1,152 @@
+"""Host side of the photon-word decode / binning path (K6).
+
+Mirrors, on the GPU, the receive/bin loop of the reference's native receiver
+(DataReadout/ReadoutControls/lib/PacketMaster.c:245-405) and the photon read-out of the
+channelizer GUI (DataReadout/ChannelizerControls/ROACH_Pulses.py:782-889).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+
+BUFSIZE = 32768                # PacketMaster.c:42
+BUFSIZE_INTS = 8192            # PacketMaster.c:44
+MAX_EVENTS_PER_SEC = 2500      # PacketMaster.c:55
+FIELD_SHIFT = {'peak': 44, 'p1': 32, 'base': 20, None: -1}
+
+
+def _seg_arrays(seg_offset, seg_roach, seg_sec):
+    off = np.ascontiguousarray(seg_offset, dtype=np.int64)
+    roach = np.ascontiguousarray(seg_roach, dtype=np.int32)
+    sec = np.ascontiguousarray(seg_sec if seg_sec is not None else np.zeros(len(roach)), dtype=np.int32)
+    assert off.size == roach.size + 1 == sec.size + 1
+    return off, roach, sec
+
+
+class PhotonDecoder:
+    """Per-(second,pixel) counts + per-pixel pulse-height histogram accumulator.
+
+    counts_raw / hist live in HBM (u32) and are accumulated across calls, so a stream can
+    be fed bundle by bundle, file chunk by file chunk, or sharded across GPUs and summed
+    (`counts_raw`/`hist` are plain sums; the 2500-event cap quirk of PacketMaster.c:373-380
+    is applied by `counts()` after any reduction)."""
+
+    def __init__(self, n_roaches, npix_per_roach, exptime, max_events=MAX_EVENTS_PER_SEC, hist_field='peak',
+                 n_bins=4096, bin_lut=None, ctx=None):
+        self.ctx = ctx or _lib.default_context()
+        self.n_roaches, self.npix_per_roach, self.exptime = int(n_roaches), int(npix_per_roach), int(exptime)
+        self.max_events = int(max_events)
+        self.n_pix = self.n_roaches * self.npix_per_roach
+        self.hist_field = hist_field
+        self.n_bins = int(n_bins) if hist_field else 0
+        self._lut_dev = None
+        if hist_field and bin_lut is not None:
+            lut = np.ascontiguousarray(np.minimum(np.asarray(bin_lut), 65535), dtype=np.uint16)
+            assert lut.size == 4096
+            self._lut_dev = self.ctx.to_device(lut)
+        self.cfg = _lib.DecodeCfg(self.n_roaches, self.npix_per_roach, self.exptime, self.max_events,
+                                  FIELD_SHIFT[hist_field], self.n_bins,
+                                  self._lut_dev.ptr if self._lut_dev else None)
+        self.counts_dev = self.ctx.alloc(self.exptime * self.n_pix * 4).zero()
+        self.hist_dev = self.ctx.alloc(self.n_pix * self.n_bins * 4).zero() if hist_field else None
+        self.stats = _lib.DecodeStats()
+        self.sec = np.zeros(self.n_roaches, dtype=np.int32)     # seconds closed per roach stream
+
+    def reset(self):
+        self.counts_dev.zero()
+        if self.hist_dev:
+            self.hist_dev.zero()
+        self.stats = _lib.DecodeStats()
+        self.sec[:] = 0
+
+    # ------------------------------------------------------------------ feeding
+    def decode_words(self, words, seg_offset, seg_roach, seg_sec=None, n_words=None, want_stats=True):
+        """words: u64 array (host numpy, torch tensor or DeviceBuffer).  Returns seg_sec_out."""
+        off, roach, sec = _seg_arrays(seg_offset, seg_roach, seg_sec)
+        if n_words is None:
+            n_words = int(off[-1])
+        sec_out = np.zeros(roach.size, dtype=np.int32)
+        c = self.ctx
+        c._check(c.lib.mkid_decode_words(c.h, _lib.ptr(words), n_words, _lib.ptr(off), _lib.ptr(roach), _lib.ptr(sec),
+                                         _lib.ptr(sec_out), roach.size, ctypes.byref(self.cfg),
+                                         _lib.ptr(self.counts_dev), _lib.ptr(self.hist_dev),
+                                         ctypes.addressof(self.stats) if want_stats else None))
+        return sec_out
+
+    def decode_wire(self, wire, seg_offset, seg_roach, seg_sec=None, n_bundles=None, want_stats=True):
+        """wire: PulseServer bundles (bytes / u8 / u32 array, host or device)."""
+        if isinstance(wire, (bytes, bytearray, memoryview)):
+            wire = np.frombuffer(wire, dtype=np.uint8)
+        off, roach, sec = _seg_arrays(seg_offset, seg_roach, seg_sec)
+        if n_bundles is None:
+            n_bundles = int(off[-1])
+        sec_out = np.zeros(roach.size, dtype=np.int32)
+        c = self.ctx
+        c._check(c.lib.mkid_decode_wire(c.h, _lib.ptr(wire), n_bundles, _lib.ptr(off), _lib.ptr(roach), _lib.ptr(sec),
+                                        _lib.ptr(sec_out), roach.size, ctypes.byref(self.cfg),
+                                        _lib.ptr(self.counts_dev), _lib.ptr(self.hist_dev),
+                                        ctypes.addressof(self.stats) if want_stats else None))
+        return sec_out
+
+    def feed_bundles(self, roach, wire):
+        """One or more whole bundles from one roach, in arrival order (the body of the
+        PacketMaster main loop, PacketMaster.c:286-397, for `ready_roach = roach`)."""
+        if isinstance(wire, (bytes, bytearray, memoryview)):
+            wire = np.frombuffer(wire, dtype=np.uint8)
+        nb = wire.nbytes // (2 * BUFSIZE)
+        assert nb * 2 * BUFSIZE == wire.nbytes, 'whole 64 KiB bundles only'
+        out = self.decode_wire(wire, [0, nb], [roach], [self.sec[roach]])
+        self.sec[roach] = out[0]
+
+    def feed_streams(self, streams):
+        """streams: list (one per roach) of u64 word arrays in arrival order."""
+        lens = [len(s) for s in streams]
+        off = np.concatenate([[0], np.cumsum(lens)])
+        words = np.ascontiguousarray(np.concatenate(streams), dtype=np.uint64) if streams else np.zeros(0, np.uint64)
+        out = self.decode_words(words, off, np.arange(len(streams)), self.sec[:len(streams)].copy())
+        self.sec[:len(streams)] = out
+
+    # ------------------------------------------------------------------ results
+    def counts_raw(self):
+        return self.counts_dev.download(np.uint32).reshape(self.exptime, self.n_pix)
+
+    def counts(self):
+        """photon_counts[sec][pixel] with the cap quirk applied (PacketMaster.c:373-380)."""
+        c = self.ctx
+        out = np.empty(self.exptime * self.n_pix, dtype=np.uint32)
+        c._check(c.lib.mkid_counts_cap(c.h, _lib.ptr(self.counts_dev), _lib.ptr(out), out.size, self.max_events))
+        return out.reshape(self.exptime, self.n_pix)
+
+    def hist(self):
+        return self.hist_dev.download(np.uint32).reshape(self.n_pix, self.n_bins)
+
+    def stats_dict(self):
+        s = self.stats
+        return dict(n_eos=s.n_eos, n_corrupt_eos=s.n_corrupt_eos, n_nonpixel=s.n_nonpixel, n_ignored=s.n_ignored,
+                    n_valid=s.n_valid)
+
+    def quicklook_image(self, sec, pixel_adr):
+        """write_sec_data quick-look (PacketMaster.c:1029-1045): capped counts of second
+        `sec` gathered through the beammap `pixel_adr[rows][cols]` as uint16."""
+        c = self.ctx
+        capped = c.alloc(self.n_pix * 4)
+        c._check(c.lib.mkid_counts_cap(c.h, ctypes.c_void_p(self.counts_dev.ptr + sec * self.n_pix * 4),
+                                       _lib.ptr(capped), self.n_pix, self.max_events))
+        adr = np.ascontiguousarray(pixel_adr, dtype=np.int32)
+        img = np.empty(adr.shape, dtype=np.uint16)
+        c._check(c.lib.mkid_quicklook_image(c.h, _lib.ptr(capped), _lib.ptr(adr), adr.size, _lib.ptr(img)))
+        capped.free()
+        return img
+
+
+def unpack_fields(words, ctx=None):
+    """ROACH_Pulses.py:805-811 on the GPU -> (ch u8, ts u32, base u16, peak u16, p1 u16)."""
+    ctx = ctx or _lib.default_context()
+    w = np.ascontiguousarray(words, dtype=np.uint64)
+    n = w.size
+    ch = np.empty(n, np.uint8); ts = np.empty(n, np.uint32)
+    base = np.empty(n, np.uint16); peak = np.empty(n, np.uint16); p1 = np.empty(n, np.uint16)
+    ctx._check(ctx.lib.mkid_unpack_fields(ctx.h, _lib.ptr(w), n, _lib.ptr(ch), _lib.ptr(ts), _lib.ptr(base),
+                                          _lib.ptr(peak), _lib.ptr(p1)))
+    return ch, ts, base, peak, p1

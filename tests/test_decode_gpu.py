@@ -1,0 +1,158 @@
+"""GPU parity: K6 decode / binning / histogram through the C ABI vs the oracle (bit-exact)."""
+import numpy as np
+import pytest
+
+from oracle import decode as odec
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    from mkids_sdr_b200 import _lib
+    return _lib.default_context(0)
+
+
+def _check(dec, streams, npix, exptime, cap, field='peak', bin_lut=None, n_bins=4096):
+    ref = odec.packetmaster_bin(streams, npix, exptime, cap)
+    assert np.array_equal(dec.counts_raw(), ref['raw_counts'])
+    assert np.array_equal(dec.counts(), ref['counts'])
+    st = dec.stats_dict()
+    for k in ('n_eos', 'n_corrupt_eos', 'n_nonpixel', 'n_ignored'):
+        assert st[k] == ref[k], k
+    if field:
+        h = odec.pixel_field_hist(streams, npix, exptime, field, bin_lut, n_bins)
+        assert np.array_equal(dec.hist(), h)
+
+
+def _ragged_streams(seed, R, npix, secs, per_sec, hot=True):
+    rng = np.random.default_rng(seed)
+    streams = []
+    for r in range(R):
+        parts = []
+        for s in range(secs + 1):
+            n = int(per_sec * (0.5 + rng.random()))
+            ch = rng.integers(0, npix + 2, n)
+            if hot:
+                ch[rng.random(n) < 0.2] = 1
+            w = odec.pack_word(ch, rng.integers(0, 4096, n), rng.integers(0, 4096, n), rng.integers(0, 4096, n),
+                               np.sort(rng.integers(0, 10 ** 6, n)))
+            eos = np.array([0xFFFFFFFFFFFFFFFF if (s != 1 or r != 0) else 0xFF00000000000001], dtype=np.uint64)
+            parts += [w, eos]
+        streams.append(np.concatenate(parts))
+    return streams
+
+
+@pytest.mark.parametrize('field,n_bins', [('peak', 4096), ('base', 4096), ('p1', 10), (None, 0)])
+def test_decode_words_ragged(ctx, field, n_bins):
+    from mkids_sdr_b200.decode import PhotonDecoder
+    R, npix, secs, cap = 3, 37, 4, 300
+    streams = _ragged_streams(21, R, npix, secs, 30000)
+    lut = None
+    if field == 'p1':
+        lut = (np.arange(4096) * 11 // 4096)          # 11 classes, class 10 is out of range for n_bins=10
+    dec = PhotonDecoder(R, npix, secs, cap, field, n_bins, lut, ctx=ctx)
+    dec.feed_streams(streams)
+    _check(dec, streams, npix, secs, cap, field, lut, n_bins)
+    assert dec.counts().max() == cap - 1
+    assert list(dec.sec) == [secs + 1] * R
+
+
+def test_decode_many_eos_and_empty(ctx):
+    from mkids_sdr_b200.decode import PhotonDecoder
+    R, npix, secs, cap = 2, 5, 50, 2500
+    rng = np.random.default_rng(2)
+    # dense EOS: a second is closed every ~7 words, several per 2-word load group
+    st0 = odec.pack_word(rng.integers(0, npix, 20000), 1, 2, 3, 4)
+    st0[rng.random(st0.size) < 0.15] = np.uint64(0xFFFFFFFFFFFFFFFF)
+    st1 = np.zeros(0, dtype=np.uint64)                # empty stream
+    streams = [st0, st1]
+    dec = PhotonDecoder(R, npix, secs, cap, 'peak', 16, ctx=ctx)
+    dec.feed_streams(streams)
+    _check(dec, streams, npix, secs, cap, 'peak', None, 16)
+
+
+def test_decode_piecewise_equals_whole(ctx):
+    """Feeding a stream in arbitrary (odd-sized, unaligned) pieces with carried seconds gives the same sums."""
+    from mkids_sdr_b200.decode import PhotonDecoder
+    R, npix, secs, cap = 2, 253, 6, 2500
+    streams = _ragged_streams(5, R, npix, secs, 20000, hot=False)
+    dec = PhotonDecoder(R, npix, secs, cap, 'peak', 4096, ctx=ctx)
+    rng = np.random.default_rng(0)
+    for r, st in enumerate(streams):
+        cuts = np.sort(rng.choice(np.arange(1, st.size), 9, replace=False))
+        pieces = np.split(st, cuts)
+        sec = 0
+        for pc in pieces:
+            words = np.concatenate([np.zeros(1, np.uint64), pc])      # force odd alignment of the segment
+            out = dec.decode_words(words, [1, 1 + pc.size], [r], [sec], n_words=words.size)
+            sec = int(out[0])
+    _check(dec, streams, npix, secs, cap)
+
+
+def test_decode_wire_bundles(ctx):
+    from mkids_sdr_b200 import synth
+    from mkids_sdr_b200.decode import PhotonDecoder
+    R, npix, secs, cap = 4, 253, 3, 2500
+    streams, _ = synth.photon_streams(400000, R, npix, secs, seed=77, n_hot=2, hot_rate=3000)
+    wire = synth.streams_to_wire(streams)
+    dec = PhotonDecoder(R, npix, secs, cap, 'peak', 4096, ctx=ctx)
+    for r in range(R):           # bundle by bundle, as PacketMaster receives them (interleaved roaches)
+        pass
+    nb = [w.size // 65536 for w in wire]
+    for b in range(max(nb)):
+        for r in range(R):
+            if b < nb[r]:
+                dec.feed_bundles(r, wire[r][b * 65536:(b + 1) * 65536])
+    _check(dec, streams, npix, secs, cap)
+    assert dec.counts().max() == cap - 1            # hot pixels exceed the 2500 cap
+    # all bundles in one call
+    dec2 = PhotonDecoder(R, npix, secs, cap, 'peak', 4096, ctx=ctx)
+    allw = np.concatenate(wire)
+    off = np.concatenate([[0], np.cumsum(nb)])
+    dec2.decode_wire(allw, off, np.arange(R))
+    _check(dec2, streams, npix, secs, cap)
+    # wire -> words oracle agrees with the synth packer
+    assert np.array_equal(odec.wire_to_words(wire[0].tobytes()), streams[0])
+
+
+def test_quicklook_and_unpack_and_reinterpret(ctx, golden_dir):
+    import os
+    from mkids_sdr_b200 import synth
+    from mkids_sdr_b200.decode import PhotonDecoder, unpack_fields
+    from mkids_sdr_b200.Utils import binTools
+    R, npix, secs = 8, 253, 2
+    streams, _ = synth.photon_streams(300000, R, npix, secs, seed=3)
+    dec = PhotonDecoder(R, npix, secs, ctx=ctx)
+    dec.feed_streams(streams)
+    rng = np.random.default_rng(1)
+    pixel_adr = rng.permutation(R * npix).reshape(46, 44)
+    img = dec.quicklook_image(1, pixel_adr)
+    assert np.array_equal(img, odec.quicklook_image(dec.counts()[1], pixel_adr))
+    f = unpack_fields(streams[2])
+    for a, b in zip(f, odec.unpack_fields(streams[2])):
+        assert np.array_equal(a, b)
+    g = np.load(os.path.join(golden_dir, 'utils_bin_py3.npz'))
+    for nb, bp, key in ((12, 9, 'reinterpret_12_9'), (16, 13, 'reinterpret_16_13'), (18, 16, 'reinterpret_18_16')):
+        assert np.array_equal(binTools.reinterpretBin(g['values'], nb, bp), g[key])
+
+
+def test_full_size_config1_properties(ctx):
+    """BASELINE config 0 at full size (1e7 words, 2024 pixels): checked through size-independent
+    properties and against the oracle's vectorised counts."""
+    from mkids_sdr_b200 import synth
+    from mkids_sdr_b200.decode import PhotonDecoder
+    R, npix, secs = 8, 253, 10
+    streams, eos = synth.photon_streams(10 ** 7, R, npix, secs, seed=1234)
+    dec = PhotonDecoder(R, npix, secs, 2500, 'peak', 4096, ctx=ctx)
+    dec.feed_streams(streams)
+    raw = dec.counts_raw()
+    st = dec.stats_dict()
+    assert st['n_eos'] == R * secs and st['n_corrupt_eos'] == 0
+    assert int(raw.sum()) == st['n_valid'] == 10 ** 7
+    assert int(dec.hist().sum()) == 10 ** 7
+    assert np.array_equal(dec.hist().sum(axis=1), raw.sum(axis=0))       # checksum of checksums
+    assert dec.counts().max() == 2499
+    ref = odec.packetmaster_bin(streams, npix, secs)
+    assert np.array_equal(raw, ref['raw_counts'])
+    assert st['n_nonpixel'] == ref['n_nonpixel']
