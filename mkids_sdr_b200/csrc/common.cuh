@@ -22,6 +22,9 @@ struct mkid_ctx {
     void *scratch[16] = {};
     size_t scratch_bytes[16] = {};
     void *l2_flush = nullptr;
+    // last segment table uploaded by the decode path (skips re-upload when unchanged)
+    std::vector<char> dec_meta_host;
+    void *dec_meta_dev = nullptr;
     size_t l2_flush_bytes = 0;
 };
 

@@ -12,8 +12,9 @@
 
 namespace {
 
-constexpr int DEC_THREADS = 1024;
-constexpr int DEC_CHUNK = 8192;
+constexpr int DEC_THREADS = 512;
+constexpr int DEC_CHUNK = 4096;                    // words per chunk (wire: half a bundle)
+constexpr int DEC_BUNDLE = 8192;                   // PacketMaster.c:44 BUFSIZE_INTS
 constexpr int DEC_WPT = DEC_CHUNK / DEC_THREADS;   // 8 words per thread
 constexpr int DEC_ITERS = DEC_WPT / 2;             // 4 iterations of 2 words (one uint4)
 constexpr int DEC_WARPS = DEC_THREADS / 32;
@@ -42,7 +43,7 @@ struct DecParams {
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
 
 template <bool WIRE, bool SMEM_HIST>
-__global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(DecParams p) {
+__global__ void __launch_bounds__(DEC_THREADS, 2) decode_kernel(DecParams p) {
     __shared__ uint32_t s_cnt[256];
     __shared__ uint32_t s_hist[SMEM_HIST ? DEC_SMEM_HIST : 1];
     __shared__ uint16_t s_lut[4096];
@@ -88,8 +89,9 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(DecParams p) {
         int n_here;   // valid words in this chunk
         if (WIRE) {
             n_here = DEC_CHUNK;
-            const uint32_t *lo_blk = p.wire + (size_t)(p.seg_offset[g] + lc) * (2 * DEC_CHUNK);
-            const uint32_t *hi_blk = lo_blk + DEC_CHUNK;
+            // chunk lc of a segment = half (lc & 1) of bundle lc >> 1: 4096 low halves + 4096 high halves
+            const uint32_t *lo_blk = p.wire + (size_t)(p.seg_offset[g] + (lc >> 1)) * (2 * DEC_BUNDLE) + (lc & 1) * DEC_CHUNK;
+            const uint32_t *hi_blk = lo_blk + DEC_BUNDLE;
 #pragma unroll
             for (int i = 0; i < DEC_ITERS / 2; ++i) {     // 2 iterations of 4 words
                 uint4 l = ld_stream_u4(reinterpret_cast<const uint4 *>(lo_blk) + i * DEC_THREADS + tid);
@@ -164,29 +166,46 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(DecParams p) {
             total_eos = run;
         }
 
-        // ---- decoupled look-back: seconds closed before this chunk
-        if (tid == 0) {
-            int base_sec;
+        // ---- decoupled look-back (warp-parallel): seconds closed before this chunk
+        if (warp == 0) {
+            int base_sec = 0;
             if (lc == 0) {
                 base_sec = p.seg_sec[g];
             } else {
-                // publish aggregate first so successors can make progress past us
-                atomicExch(&p.state[c], (1ull << 32) | (unsigned)total_eos);
-                int acc = 0;
+                // publish the aggregate first so successors never wait on our own look-back
+                if (lane == 0) atomicExch(&p.state[c], (1ull << 32) | (unsigned)total_eos);
+                const long long first = c - lc;       // first chunk of the segment: always inclusive
                 long long q = c - 1;
+                int acc = 0;
                 for (;;) {
-                    unsigned long long st;
-                    do { st = *reinterpret_cast<volatile unsigned long long *>(&p.state[q]); } while ((st >> 32) == 0);
-                    if ((st >> 32) == 2) { base_sec = (int)(unsigned)st + acc; break; }
-                    acc += (int)(unsigned)st;
-                    --q;   // aggregate only: keep walking (q never passes the segment's first chunk,
-                           // which always publishes an inclusive prefix)
+                    const long long idx = q - lane;
+                    const bool valid = idx >= first;
+                    unsigned long long st = 0;
+                    if (valid) {
+                        do { st = *reinterpret_cast<volatile unsigned long long *>(&p.state[idx]); } while ((st >> 32) == 0);
+                    }
+                    const unsigned incl = __ballot_sync(0xffffffffu, valid && (st >> 32) == 2);
+                    int v;
+                    if (incl) {
+                        const int stop = __ffs(incl) - 1;           // nearest predecessor holding a prefix
+                        v = (lane <= stop) ? (int)(unsigned)st : 0;
+                    } else {
+                        v = valid ? (int)(unsigned)st : 0;
+                    }
+#pragma unroll
+                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                    acc += v;
+                    if (incl) break;
+                    q -= 32;
                 }
+                base_sec = acc;
             }
-            __threadfence();
-            atomicExch(&p.state[c], (2ull << 32) | (unsigned)(base_sec + total_eos));
-            s_secbase = base_sec;
-            if (last_chunk && p.seg_sec_out) p.seg_sec_out[g] = base_sec + total_eos;
+            if (lane == 0) {
+                // the record is self-contained (flag and value in one 64-bit word): no fence needed
+                atomicExch(&p.state[c], (2ull << 32) | (unsigned)(base_sec + total_eos));
+                s_secbase = base_sec;
+                if (last_chunk && p.seg_sec_out) p.seg_sec_out[g] = base_sec + total_eos;
+            }
         }
         __syncthreads();
         const int sec_base = s_secbase;
@@ -313,13 +332,13 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
         int64_t len = seg_offset[i + 1] - seg_offset[i];
         MKID_REQUIRE(ctx, len >= 0 && seg_offset[i + 1] <= n_units, "segment offsets out of range");
         MKID_REQUIRE(ctx, seg_roach[i] >= 0 && seg_roach[i] < cfg->n_roaches, "segment roach out of range");
-        first_chunk[i + 1] = first_chunk[i] + (wire_fmt ? len : (len + DEC_CHUNK - 1) / DEC_CHUNK);
+        first_chunk[i + 1] = first_chunk[i] + (wire_fmt ? 2 * len : (len + DEC_CHUNK - 1) / DEC_CHUNK);
     }
     const int64_t n_chunks = first_chunk[n_seg];
     std::vector<int32_t> sec0(n_seg, 0);
     if (seg_sec) for (int i = 0; i < n_seg; ++i) sec0[i] = seg_sec[i];
 
-    // meta buffer: first_chunk | seg_offset | roach | sec | sec_out | stats(5 u64) | ticket
+    // meta buffer: first_chunk | seg_offset | stats(5 u64) | roach | sec | sec_out | ticket
     const size_t meta_bytes = (size_t)(n_seg + 1) * 16 + (size_t)n_seg * 12 + 5 * 8 + 16;
     char *meta = nullptr;
     int rc = mkid_scratch(ctx, SCR_META, meta_bytes, (void **)&meta);
@@ -331,15 +350,22 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
     int32_t *d_sec = d_roach + n_seg;
     int32_t *d_sec_out = d_sec + n_seg;
     unsigned int *d_ticket = (unsigned int *)(d_sec_out + n_seg);
-    MKID_CUDA(ctx, cudaMemcpyAsync(d_first, first_chunk.data(), (n_seg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    MKID_CUDA(ctx, cudaMemcpyAsync(d_off, seg_offset, (n_seg + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
-    MKID_CUDA(ctx, cudaMemcpyAsync(d_roach, seg_roach, n_seg * 4, cudaMemcpyHostToDevice, ctx->stream));
-    MKID_CUDA(ctx, cudaMemcpyAsync(d_sec, sec0.data(), n_seg * 4, cudaMemcpyHostToDevice, ctx->stream));
-    MKID_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 5 * 8, ctx->stream));
-    MKID_CUDA(ctx, cudaMemsetAsync(d_sec_out, 0, n_seg * 4 + 16, ctx->stream));
-    // the host vectors must outlive the async copies (pageable memcpyAsync stages synchronously,
-    // but be explicit)
-    MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    {   // upload the segment table only when it changed since the last call on this context
+        std::vector<char> blob(meta_bytes, 0);
+        memcpy(blob.data() + ((char *)d_first - meta), first_chunk.data(), (n_seg + 1) * 8);
+        memcpy(blob.data() + ((char *)d_off - meta), seg_offset, (n_seg + 1) * 8);
+        memcpy(blob.data() + ((char *)d_roach - meta), seg_roach, n_seg * 4);
+        memcpy(blob.data() + ((char *)d_sec - meta), sec0.data(), n_seg * 4);
+        if (ctx->dec_meta_dev != meta || ctx->dec_meta_host != blob) {
+            MKID_CUDA(ctx, cudaMemcpyAsync(meta, blob.data(), meta_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // blob is pageable and about to be moved
+            ctx->dec_meta_host.swap(blob);
+            ctx->dec_meta_dev = meta;
+        } else {
+            MKID_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 5 * 8, ctx->stream));
+            MKID_CUDA(ctx, cudaMemsetAsync(d_sec_out, 0, n_seg * 4 + 16, ctx->stream));
+        }
+    }
 
     unsigned long long *d_state = nullptr;
     rc = mkid_scratch(ctx, SCR_STATE, (size_t)(n_chunks + 1) * 8, (void **)&d_state);
@@ -347,7 +373,7 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
     MKID_CUDA(ctx, cudaMemsetAsync(d_state, 0, (size_t)(n_chunks + 1) * 8, ctx->stream));
 
     const void *d_in = nullptr;
-    const size_t in_bytes = wire_fmt ? (size_t)n_units * 2 * DEC_CHUNK * 4 : (size_t)n_units * 8;
+    const size_t in_bytes = wire_fmt ? (size_t)n_units * 2 * DEC_BUNDLE * 4 : (size_t)n_units * 8;
     rc = mkid_stage_in(ctx, wire_fmt ? (const void *)wire : (const void *)words, in_bytes, SCR_IN, &d_in);
     if (rc) return rc;
     const void *d_lut = nullptr;
@@ -377,7 +403,7 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
 
     if (n_chunks > 0) {
         const bool smem_hist = want_hist && (int64_t)cfg->npix_per_roach * cfg->n_bins <= DEC_SMEM_HIST;
-        int grid = (int)std::min<int64_t>(n_chunks, (int64_t)ctx->num_sms * 2);   // 2 CTAs of 1024 threads per SM when registers allow
+        int grid = (int)std::min<int64_t>(n_chunks, (int64_t)ctx->num_sms * 2);   // persistent, 2 CTAs of 512 threads per SM
         if (wire_fmt) {
             if (smem_hist) decode_kernel<true, true><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
             else decode_kernel<true, false><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
