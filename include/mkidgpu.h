@@ -127,6 +127,80 @@ int mkid_reinterpret_bin(mkid_ctx *ctx, const uint64_t *values, int64_t n, int32
 int mkid_quicklook_image(mkid_ctx *ctx, const uint32_t *counts_sec, const int32_t *pixel_adr,
                          int32_t n_image_pixels, uint16_t *image);
 
+/* ------------------------------------------------------------------ channelizer + pulse detection (K4, K5)
+ * Software model of the firmware channelizer that the reference only parameterises
+ * (the .bof/.mdl files are absent): 512-branch 2x-oversampled polyphase filter bank + FFT-512
+ * -> bin select (select_bins, ROACH_Setup.py:534-550) -> DDS mix with the LUT of
+ * define_DDS_LUT (ROACH_Setup.py:506-532, layout [j][(m+154)%256][s]) -> 26-tap FIR with the
+ * 12-bit taps of loadFIRcoeffs (ROACH_Pulses.py:59-111) and decimation by 2 -> centre subtract
+ * (loadIQcenters, ROACH_Pulses.py:948-956) -> atan2 phase in Fix16_13 (ROACH_Pulses.py:374-378)
+ * -> rolling-mean threshold trigger with hold-off (pulse_triggering_v2.py:104-174, thresholds of
+ * loadThresholds ROACH_Pulses.py:259-288) -> 64-bit photon words (layout ROACH_Pulses.py:805-811)
+ * with one all-ones word per second boundary (PacketMaster.c:329-333).
+ * The exact arithmetic is defined by oracle/channelizer.py (parity definition of the unpinned stages).
+ *
+ * One mkid_chan holds n_boards independent boards (feedlines) of 256 channels each and their
+ * streaming state (input history, hold-off, time).  Streams are processed in calls of n samples
+ * per board (n multiple of 512); results do not depend on how a stream is cut into calls.
+ */
+typedef struct mkid_chan mkid_chan;
+
+typedef struct {
+    int32_t n_boards;      /* boards (ROACH streams) processed together                         */
+    int32_t n_lut;         /* DDS/DAC LUT length N = sampleRate/freqRes (ROACH_Setup.py:83-84)  */
+    int32_t mean_len;      /* M: baseline = mean of the previous M phase samples (meanlength)   */
+    int32_t holdoff;       /* L: dead time after a trigger in us (pulselength), >= 32           */
+    int32_t peak_win;      /* W: peak search window in us, <= 60                                */
+    int32_t reserved;
+} mkid_chan_params;
+
+int  mkid_chan_create(mkid_ctx *ctx, const mkid_chan_params *prm, mkid_chan **out);
+void mkid_chan_destroy(mkid_ctx *ctx, mkid_chan *ch);
+/* FIR taps shared by all channels: c[k] = int(tap*2047) (ROACH_Pulses.py:69,88-89), 26 ints */
+int  mkid_chan_set_fir(mkid_ctx *ctx, mkid_chan *ch, const int32_t *fir_int);
+/* PFB prototype window, 2048 floats (default: Hamming-windowed sinc, sum = 1) */
+int  mkid_chan_set_window(mkid_ctx *ctx, mkid_chan *ch, const float *h);
+/* per board: fft bins [256] (select_bins), DDS LUT I/Q int16 [n_lut] in the define_DDS_LUT
+ * layout, zero_ch [256] (FIR zeroed: deleted / inactive channels, ROACH_Pulses.py:65-67,99-108),
+ * centres I_c,Q_c = int(c/8) [256] (ROACH_Pulses.py:949-951), raw Fix16_13 thresholds [256]
+ * (capture_threshold, ROACH_Pulses.py:286).  Host pointers. */
+int  mkid_chan_set_board(mkid_ctx *ctx, mkid_chan *ch, int32_t board, const int32_t *bins,
+                         const int16_t *I_dds, const int16_t *Q_dds, const uint8_t *zero_ch,
+                         const int32_t *centers_i, const int32_t *centers_q, const int32_t *thresholds);
+int  mkid_chan_set_thresholds(mkid_ctx *ctx, mkid_chan *ch, int32_t board, const int32_t *thresholds);
+/* test hook: when set (device pointer, float [n_boards][n/512][256]) the next mkid_chan_process calls
+ * also store the unquantised phase in radians of the new outputs; NULL switches it off */
+int  mkid_chan_set_f32_phase_out(mkid_ctx *ctx, mkid_chan *ch, float *dev);
+/* restart every stream at time 0 with empty history */
+int  mkid_chan_reset(mkid_ctx *ctx, mkid_chan *ch);
+/* iq: int16 [n_boards][n][2] (I,Q) host or device.  words: u64 [n_boards][words_cap];
+ * n_words: int32 [n_boards] (host).  phase_out (optional): int16 [n_boards][n/512][256] Fix16_13
+ * phase of the n/512 new output samples.  detect = 0 skips K5 (no words). */
+int  mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq, int64_t n, int32_t detect,
+                       uint64_t *words, int64_t words_cap, int32_t *n_words, int16_t *phase_out);
+/* K5 alone on a caller-supplied phase stream (bit-exact seam test and phase-snapshot triggering):
+ * phase int16 [n_boards][rows][256]; row r is absolute time t_abs0 + r; triggers are resolved for
+ * rows [mean_len, rows - peak_win - 1) ; t_next int64 [n_boards][256] in/out (host). */
+int  mkid_chan_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase, int64_t rows, int64_t t_abs0,
+                      int64_t *t_next, uint64_t *words, int64_t words_cap, int32_t *n_words);
+/* synthetic ADC stream for tests and benchmarks (replaces the ROACH ADC): per board a comb of
+ * n_tones tones at fine bins tone_bin[] (f = bin*fs/n_lut), amplitude tone_amp[], phase tone_phase[],
+ * each phase-modulated by exponential pulses (rate per second, decay tau_us, depth uniform in
+ * [deg_lo,deg_hi] degrees), plus white Gaussian noise, clipped to 12 bits.
+ * out: int16 [n_boards][n][2] device or host. */
+typedef struct {
+    int32_t n_tones;
+    int32_t n_lut;
+    float   full_scale;     /* peak amplitude of the comb in ADC counts (<= 2047)  */
+    float   noise_lsb;
+    float   pulse_rate;     /* per second per tone                                  */
+    float   tau_us;
+    float   deg_lo, deg_hi;
+    uint64_t seed;
+} mkid_synth_params;
+int  mkid_synth_adc(mkid_ctx *ctx, const mkid_synth_params *prm, int32_t n_boards, const int32_t *tone_bin,
+                    const float *tone_amp, const float *tone_phase, int64_t n, int64_t t_abs0_us, int16_t *out);
+
 #ifdef __cplusplus
 }
 #endif

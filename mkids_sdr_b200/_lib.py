@@ -27,6 +27,17 @@ class DecodeCfg(Structure):
                 ('bin_lut', c_void_p)]
 
 
+class ChanParams(Structure):
+    _fields_ = [('n_boards', c_int32), ('n_lut', c_int32), ('mean_len', c_int32), ('holdoff', c_int32),
+                ('peak_win', c_int32), ('reserved', c_int32)]
+
+
+class SynthParams(Structure):
+    _fields_ = [('n_tones', c_int32), ('n_lut', c_int32), ('full_scale', c_float), ('noise_lsb', c_float),
+                ('pulse_rate', c_float), ('tau_us', c_float), ('deg_lo', c_float), ('deg_hi', c_float),
+                ('seed', ctypes.c_uint64)]
+
+
 class DecodeStats(Structure):
     _fields_ = [('n_eos', c_int64), ('n_corrupt_eos', c_int64), ('n_nonpixel', c_int64),
                 ('n_ignored', c_int64), ('n_valid', c_int64)]
@@ -59,6 +70,21 @@ _SIGNATURES = {
     'mkid_unpack_fields': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'mkid_reinterpret_bin': (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_void_p]),
     'mkid_quicklook_image': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
+    'mkid_chan_create': (c_int32, [c_void_p, POINTER(ChanParams), POINTER(c_void_p)]),
+    'mkid_chan_destroy': (None, [c_void_p, c_void_p]),
+    'mkid_chan_set_fir': (c_int32, [c_void_p, c_void_p, c_void_p]),
+    'mkid_chan_set_window': (c_int32, [c_void_p, c_void_p, c_void_p]),
+    'mkid_chan_set_board': (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
+    'mkid_chan_set_thresholds': (c_int32, [c_void_p, c_void_p, c_int32, c_void_p]),
+    'mkid_chan_reset': (c_int32, [c_void_p, c_void_p]),
+    'mkid_chan_set_f32_phase_out': (c_int32, [c_void_p, c_void_p, c_void_p]),
+    'mkid_chan_process': (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p,
+                                    c_void_p]),
+    'mkid_chan_detect': (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+                                   c_void_p]),
+    'mkid_synth_adc': (c_int32, [c_void_p, POINTER(SynthParams), c_int32, c_void_p, c_void_p, c_void_p, c_int64,
+                                 c_int64, c_void_p]),
 }
 
 _lib = None

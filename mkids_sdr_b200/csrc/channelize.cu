@@ -1,0 +1,905 @@
+// K4: streaming software channelizer (PFB + FFT-512 + bin select + DDS mix + 26-tap FIR /2 +
+//     centre subtract + atan2 -> Fix16_13 phase), and K5: pulse detection -> 64-bit photon words.
+//
+// The arithmetic is the model defined in oracle/channelizer.py (the firmware data plane is absent
+// from the reference; see include/mkidgpu.h for the control-plane interfaces each stage follows).
+//
+// K4 layout: one CTA = (board, chunk of output rows); 256 threads.  Work proceeds in blocks of
+// 8 frames (hop 256 samples, 2x oversampled):
+//   PFB    thread k owns branches k and k+256; an 8-deep sliding register window means every
+//          ADC sample is loaded from HBM exactly once per chunk (4 B coalesced per lane per frame);
+//          the first radix-2 DIF stage of the 512-point FFT is done in registers.
+//   FFT    16 FFTs of 256 points per block (8 frames x even/odd bins), 16 threads each, two radix-16
+//          passes in registers with one padded shared-memory exchange; the 16 threads of one FFT sit
+//          in one warp, so the exchange needs only __syncwarp.
+//   CHAN   thread c = channel c: gather its bin, DDS mix (packed LUT read through L2), append to a
+//          32-frame shared-memory ring (private column per thread, no block barrier), 26-tap FIR
+//          for 4 outputs at once from a register window, centre subtract, atan2, Fix16_13 store.
+// FP32-issue-bound, not HBM-bound (about 150 instructions per ADC sample against 4 B read).
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int NCH = 256;
+constexpr int NFFT = 512;
+constexpr int HOP = 256;
+constexpr int PTAPS = 4;
+constexpr int WIN = NFFT * PTAPS;        // 2048-sample prototype window
+constexpr int FIRT = 26;
+constexpr int FB = 8;                    // frames per block
+constexpr int RING = 32;                 // frames kept per channel for the FIR
+constexpr int PRE_ROWS = 96;             // output rows recomputed in front of each call (32 baseline + 64 look-ahead)
+constexpr int RES_LO = 32;               // first resolved row of the phase buffer in mkid_chan_process
+constexpr int T_START = 64;              // first absolute output index that may trigger
+constexpr int FFT_STRIDE = 272;          // 16 x 17 padded float2 per 256-point FFT
+constexpr int CAND_ROWS = 1024;          // rows per CTA of the candidate kernel
+constexpr int64_t SEC_US = 1000000;
+
+struct ChanDev {                         // device-resident configuration + state of one mkid_chan
+    int n_boards, n_lut, Ld, M, L, W, Lw;
+    float *window;        // [2048]
+    float2 *tw512;        // [256]  W512^k
+    float2 *tw256;        // [16][16] W256^(j*q) stored [q][j]
+    float fir[FIRT];      // c_k / (2047*32767)
+    int16_t *bins;        // [B][256]
+    uint32_t *dds;        // [B][Ld][256]  I | Q<<16
+    float *gain;          // [B][256] 0 (zeroed FIR) or 1
+    float *cen_i, *cen_q; // [B][256] 8*I_c, 8*Q_c
+    int32_t *thr;         // [B][256]
+    uint32_t *hist;       // [B][H] input history (packed int16 I,Q)
+    int64_t *t_next;      // [B][256]
+    int H;
+};
+
+}  // namespace
+
+struct mkid_chan {
+    ChanDev d;
+    int64_t t_consumed = 0;              // output samples (us) produced so far per board
+    // scratch owned by the object
+    int16_t *phase_buf = nullptr; size_t phase_rows = 0;
+    uint32_t *mask = nullptr; size_t mask_bytes = 0;
+    uint32_t *acc = nullptr; size_t acc_bytes = 0;
+    uint32_t *win_cnt = nullptr; size_t win_bytes = 0;    // [B][n_win] counts then offsets
+    int32_t *n_words_dev = nullptr;
+    uint64_t *words_dev = nullptr; size_t words_bytes = 0;
+    uint32_t *in_dev = nullptr; size_t in_bytes = 0;
+    bool board_set[64] = {};
+    bool fir_set = false;
+    float *f32_out = nullptr;            // set by mkid_chan_set_f32_phase_out (device pointer)
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------
+// small complex helpers
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
+
+// forward 4-point DFT in place: (a0,a1,a2,a3) -> (X0,X1,X2,X3)
+__device__ __forceinline__ void fft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3) {
+    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_mi(csub(a1, a3));
+    a0 = cadd(t0, t2); a2 = csub(t0, t2); a1 = cadd(t1, t3); a3 = csub(t1, t3);
+}
+
+// forward 16-point DFT; on return X[4*k1 + k2] is in v[4*k2 + k1]
+__device__ __forceinline__ void fft16(float2 (&v)[16]) {
+#pragma unroll
+    for (int n1 = 0; n1 < 4; ++n1) fft4(v[n1], v[n1 + 4], v[n1 + 8], v[n1 + 12]);
+    // twiddle v[n1 + 4*k2] *= W16^(n1*k2)
+    const float c1 = 0.92387953251128674f, s1 = 0.38268343236508977f, r2 = 0.70710678118654752f;
+    v[5] = cmul(v[5], make_float2(c1, -s1));                       // W16^1
+    v[9] = make_float2((v[9].x + v[9].y) * r2, (v[9].y - v[9].x) * r2);   // W16^2 = (1-i)/sqrt2
+    v[13] = cmul(v[13], make_float2(s1, -c1));                     // W16^3
+    v[6] = make_float2((v[6].x + v[6].y) * r2, (v[6].y - v[6].x) * r2);   // W16^2
+    v[10] = mul_mi(v[10]);                                         // W16^4 = -i
+    v[14] = make_float2((v[14].y - v[14].x) * r2, -(v[14].x + v[14].y) * r2);  // W16^6 = (-1-i)/sqrt2
+    v[7] = cmul(v[7], make_float2(s1, -c1));                       // W16^3
+    v[11] = make_float2((v[11].y - v[11].x) * r2, -(v[11].x + v[11].y) * r2);  // W16^6
+    v[15] = cmul(v[15], make_float2(-c1, s1));                     // W16^9
+#pragma unroll
+    for (int k2 = 0; k2 < 4; ++k2) fft4(v[4 * k2], v[4 * k2 + 1], v[4 * k2 + 2], v[4 * k2 + 3]);
+}
+
+struct K4Params {
+    ChanDev d;
+    const uint32_t *in;      // [B][n] packed samples of this call
+    int64_t n;               // samples per board in this call
+    int64_t f0_abs;          // absolute frame index of local frame 0
+    int16_t *phase;          // [B][rows][256]
+    float *phase_f32;        // optional [B][n/512][256] unquantised phase (rad) of the new outputs (tests)
+    int64_t rows;            // PRE_ROWS + n/512
+    int rows_per_chunk;      // multiple of 4
+    int chunks_per_board;
+};
+
+__global__ void __launch_bounds__(256, 2) channelize_kernel(K4Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *s_fft = reinterpret_cast<float2 *>(smem_raw);                 // [16][FFT_STRIDE]
+    float2 *s_ring = s_fft + 16 * FFT_STRIDE;                             // [RING][256]
+    float2 *s_tw = s_ring + RING * NCH;                                   // [16][16]
+
+    const int tid = threadIdx.x;
+    const int board = blockIdx.y;
+    const int chunk = blockIdx.x;
+    const ChanDev &d = p.d;
+
+    // ---- per-thread constants
+    float hA[PTAPS], hB[PTAPS];
+#pragma unroll
+    for (int q = 0; q < PTAPS; ++q) {
+        hA[q] = d.window[NFFT * q + tid];
+        hB[q] = d.window[NFFT * q + HOP + tid];
+    }
+    const float2 w512 = d.tw512[tid];
+    s_tw[tid] = d.tw256[tid];
+    const int bin = d.bins[board * NCH + tid];
+    const float gain = d.gain[board * NCH + tid];
+    const float cen_i = d.cen_i[board * NCH + tid], cen_q = d.cen_q[board * NCH + tid];
+    const uint32_t *dds = d.dds + (size_t)board * d.Ld * NCH;
+    const uint32_t *in = p.in + (size_t)board * p.n;
+    const uint32_t *hist = d.hist + (size_t)board * d.H;
+    int16_t *phase = p.phase + (size_t)board * p.rows * NCH;
+
+    // output rows [row0,row1) of the phase buffer; row r is local output t = r - PRE_ROWS
+    const int64_t row0 = (int64_t)chunk * p.rows_per_chunk;
+    const int64_t row1 = min(row0 + (int64_t)p.rows_per_chunk, p.rows);
+    if (row0 >= row1) return;
+    const int64_t tl0 = row0 - PRE_ROWS, tl1 = row1 - PRE_ROWS;
+    // first frame block: the FIR of output tl0 needs frames 2*tl0 - 24 .. 2*tl0 + 1
+    const int64_t fb_first = ((2 * tl0 - 24) >> 3) << 3;       // floor to a multiple of 8 (arithmetic shift)
+    const int64_t fb_last = 2 * tl1;                           // exclusive
+
+    auto load_sample = [&](int64_t nidx) -> uint32_t {
+        if (nidx >= 0) return in[nidx];
+        const int64_t h = (int64_t)d.H + nidx;
+        return h >= 0 ? hist[h] : 0u;
+    };
+    auto unpack = [](uint32_t v) -> float2 {
+        return make_float2((float)(int16_t)(v & 0xFFFF), (float)(int16_t)(v >> 16));
+    };
+
+    // ---- PFB warm-up: s[j] = x[256*(f+1) - 2048 + k + 256*j], j = 0..6 for f = fb_first
+    float2 sw[8];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) sw[j] = unpack(load_sample(HOP * (fb_first + 1) - WIN + tid + HOP * j));
+    sw[7] = make_float2(0.f, 0.f);
+    // zero the ring (frames before the first computed one are never read with non-zero weight, but keep it clean)
+    for (int i = tid; i < RING * NCH; i += 256) s_ring[i] = make_float2(0.f, 0.f);
+    uint32_t pre[FB];
+#pragma unroll
+    for (int i = 0; i < FB; ++i) pre[i] = load_sample(HOP * (fb_first + i) + tid);
+    __syncthreads();
+
+    for (int64_t fb = fb_first; fb < fb_last; fb += FB) {
+        // ================= PFB + first radix-2 stage for 8 frames =================
+#pragma unroll
+        for (int i = 0; i < FB; ++i) {
+            sw[(i + 7) & 7] = unpack(pre[i]);
+            float2 u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < PTAPS; ++q) {
+                const float2 a = sw[(2 * q + i) & 7], b = sw[(2 * q + 1 + i) & 7];
+                u0.x = fmaf(hA[q], a.x, u0.x); u0.y = fmaf(hA[q], a.y, u0.y);
+                u1.x = fmaf(hB[q], b.x, u1.x); u1.y = fmaf(hB[q], b.y, u1.y);
+            }
+            s_fft[(2 * i) * FFT_STRIDE + tid] = cadd(u0, u1);                      // even bins
+            s_fft[(2 * i + 1) * FFT_STRIDE + tid] = cmul(csub(u0, u1), w512);      // odd bins
+        }
+        // prefetch the next block's samples while the FFT runs
+        if (fb + FB < fb_last) {
+#pragma unroll
+            for (int i = 0; i < FB; ++i) pre[i] = load_sample(HOP * (fb + FB + i) + tid);
+        }
+        __syncthreads();
+        // ================= 16 x FFT-256: two radix-16 passes =================
+        {
+            float2 *reg = s_fft + (tid >> 4) * FFT_STRIDE;
+            const int j = tid & 15;
+            float2 v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = reg[j + 16 * i];
+            fft16(v);
+            __syncwarp();
+            // B_j[q] = A_j[q] * W256^(j*q) -> reg[q*17 + j];  A_j[q], q = 4*k1+k2, sits in v[4*k2+k1]
+#pragma unroll
+            for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+                for (int k2 = 0; k2 < 4; ++k2) {
+                    const int q = 4 * k1 + k2;
+                    float2 x = v[4 * k2 + k1];
+                    if (q != 0) x = cmul(x, s_tw[q * 16 + j]);
+                    reg[q * 17 + j] = x;
+                }
+            __syncwarp();
+            // pass 2: thread q = j reads B_i[q] over i
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = reg[j * 17 + i];
+            fft16(v);
+            __syncwarp();
+            // X[q + 16*r], r = 4*k1+k2 in v[4*k2+k1]
+#pragma unroll
+            for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+                for (int k2 = 0; k2 < 4; ++k2) reg[j + 16 * (4 * k1 + k2)] = v[4 * k2 + k1];
+        }
+        __syncthreads();
+        // ================= channel stage: thread = channel =================
+        {
+            const int par = bin & 1, m = bin >> 1;
+#pragma unroll
+            for (int i = 0; i < FB; ++i) {
+                const int64_t f_abs = p.f0_abs + fb + i;
+                float2 z = s_fft[(2 * i + par) * FFT_STRIDE + m];
+                if (par && ((f_abs + 1) & 1)) { z.x = -z.x; z.y = -z.y; }
+                float2 y = make_float2(0.f, 0.f);
+                if (f_abs >= 0) {
+                    const uint32_t dv = dds[(size_t)(f_abs % d.Ld) * NCH + tid];
+                    const float dr = (float)(int16_t)(dv & 0xFFFF), di = (float)(int16_t)(dv >> 16);
+                    y.x = z.x * dr + z.y * di;          // z * conj(d)
+                    y.y = z.y * dr - z.x * di;
+                }
+                s_ring[((fb + i) & (RING - 1)) * NCH + tid] = y;
+            }
+            // every thread has gathered its bins: the next block's PFB may overwrite s_fft.  From
+            // here on a thread touches only its own ring column.
+            __syncthreads();
+            // FIR for the 4 outputs t = fb/2 + jj: frames fb + 2*jj - 24 + k, k = 0..25
+            const int64_t t_first = fb >> 1;
+            if (t_first + 3 >= tl0 && t_first < tl1) {
+                float2 yw[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) yw[i] = s_ring[((fb - 24 + i) & (RING - 1)) * NCH + tid];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    float ar = 0.f, ai = 0.f;
+#pragma unroll
+                    for (int k = 0; k < FIRT; ++k) {
+                        ar = fmaf(d.fir[k], yw[2 * jj + k].x, ar);
+                        ai = fmaf(d.fir[k], yw[2 * jj + k].y, ai);
+                    }
+                    const int64_t t = t_first + jj;
+                    if (t >= tl0 && t < tl1) {
+                        // zeroed FIR (deleted / inactive channel): w = +0 exactly, as in the model
+                        const float a = (gain != 0.f ? ar : 0.f) - cen_i, b = (gain != 0.f ? ai : 0.f) - cen_q;
+                        const float ph = atan2f(b, a);
+                        phase[(t + PRE_ROWS) * NCH + tid] = (int16_t)__float2int_rn(ph * 8192.0f);
+                        if (p.phase_f32 && t >= 0)
+                            p.phase_f32[((size_t)board * (p.rows - PRE_ROWS) + t) * NCH + tid] = ph;
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K5c: candidate mask from the phase rows.  bit (r & 31) of mask[b][r >> 5][c] is set iff
+//      M*raw[r] - sum_{k=1..M} raw[r-k] < M*thr[c]   (rows r >= M)
+__global__ void __launch_bounds__(256) candidates_kernel(const int16_t *__restrict__ phase, int64_t rows, int M,
+                                                         const int32_t *__restrict__ thr, uint32_t *mask) {
+    const int c = threadIdx.x, board = blockIdx.y;
+    const int64_t r0 = (int64_t)blockIdx.x * CAND_ROWS;
+    const int64_t r1 = min(r0 + CAND_ROWS, rows);
+    const int16_t *ph = phase + (size_t)board * rows * NCH;
+    const int64_t n_groups = (rows + 31) >> 5;
+    uint32_t *mk = mask + (size_t)board * n_groups * NCH;
+    const int th = M * thr[board * NCH + c];
+    int S = 0;
+    for (int k = 1; k <= M; ++k) {
+        const int64_t r = r0 - k;
+        if (r >= 0) S += ph[r * NCH + c];
+    }
+    for (int64_t rg = r0; rg < r1; rg += 32) {
+        uint32_t bits = 0;
+#pragma unroll 8
+        for (int b = 0; b < 32; ++b) {
+            const int64_t r = rg + b;
+            if (r < r1) {
+                const int v = ph[r * NCH + c];
+                if (r >= M && (M * v - S) < th) bits |= 1u << b;
+                S += v;
+                if (r >= M) S -= ph[(r - M) * NCH + c];
+            }
+        }
+        mk[(rg >> 5) * NCH + c] = bits;
+    }
+}
+
+// K5a: greedy hold-off per channel (sequential in time, one thread per channel).
+__global__ void __launch_bounds__(32) resolve_kernel(const uint32_t *__restrict__ mask, int64_t rows, int64_t r_lo,
+                                                     int64_t r_hi, int64_t t_abs0, int L, int Lw, int n_win,
+                                                     int64_t *t_next, uint32_t *acc, uint32_t *win_cnt) {
+    const int board = blockIdx.y;
+    const int c = blockIdx.x * 32 + threadIdx.x;
+    const int64_t n_groups = (rows + 31) >> 5;
+    const uint32_t *mk = mask + (size_t)board * n_groups * NCH;
+    int64_t tn = t_next[board * NCH + c];
+    uint32_t *ac = acc + (size_t)board * n_win * NCH;
+    uint32_t *wc = win_cnt + (size_t)board * (n_win + 1);
+    const int64_t g_lo = r_lo >> 5, g_hi = (r_hi + 31) >> 5;
+    for (int64_t g0 = g_lo; g0 < g_hi; g0 += 8) {
+        uint32_t wv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) wv[u] = (g0 + u < g_hi) ? mk[(g0 + u) * NCH + c] : 0u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            uint32_t w = wv[u];
+            while (w) {
+                const int b = __ffs(w) - 1;
+                w &= w - 1;
+                const int64_t r = ((g0 + u) << 5) + b;
+                if (r < r_lo || r >= r_hi) continue;
+                const int64_t t = t_abs0 + r;
+                if (t < T_START || t < tn) continue;
+                tn = t + L;
+                const int wi = (int)((r - r_lo) / Lw);
+                ac[(size_t)wi * NCH + c] = (uint32_t)(r + 1);
+                atomicAdd(&wc[wi], 1u);
+            }
+        }
+    }
+    t_next[board * NCH + c] = tn;
+}
+
+// K5s: per board, add the end-of-second events and turn per-window counts into offsets.
+__global__ void __launch_bounds__(256) scan_kernel(uint32_t *win_cnt, int n_win, int64_t r_lo, int64_t r_hi,
+                                                   int64_t t_abs0, int Lw, int32_t *n_words) {
+    __shared__ uint32_t s_part[256];
+    const int board = blockIdx.x, tid = threadIdx.x;
+    uint32_t *wc = win_cnt + (size_t)board * (n_win + 1);
+    // second boundaries B (multiples of 1e6, B > 0) with t_abs0 + r_lo <= B < t_abs0 + r_hi
+    if (tid == 0) {
+        const int64_t ta = t_abs0 + r_lo, tb = t_abs0 + r_hi;
+        int64_t B = ((ta + SEC_US - 1) / SEC_US) * SEC_US;
+        if (ta < 0) B = 0;
+        for (; B < tb; B += SEC_US)
+            if (B > 0) wc[(B - ta) / Lw] += 1;
+    }
+    __syncthreads();
+    const int per = (n_win + 255) / 256;
+    uint32_t sum = 0;
+    for (int i = 0; i < per; ++i) {
+        const int w = tid * per + i;
+        if (w < n_win) sum += wc[w];
+    }
+    s_part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (int i = 0; i < 256; ++i) { uint32_t v = s_part[i]; s_part[i] = run; run += v; }
+        n_words[board] = (int32_t)run;
+    }
+    __syncthreads();
+    uint32_t run = s_part[tid];
+    for (int i = 0; i < per; ++i) {
+        const int w = tid * per + i;
+        if (w < n_win) { uint32_t v = wc[w]; wc[w] = run; run += v; }
+    }
+}
+
+// K5b: build the photon words of one window and write them in (time, channel) order.
+__global__ void __launch_bounds__(256) emit_kernel(const int16_t *__restrict__ phase, int64_t rows,
+                                                   const uint32_t *__restrict__ acc, const uint32_t *__restrict__ win_off,
+                                                   int n_win, int64_t r_lo, int64_t r_hi, int64_t t_abs0, int M, int W,
+                                                   int Lw, uint64_t *words, int64_t words_cap) {
+    __shared__ uint32_t s_keys[NCH + 2];
+    __shared__ int s_n;
+    const int board = blockIdx.y, wi = blockIdx.x, c = threadIdx.x;
+    const int16_t *ph = phase + (size_t)board * rows * NCH;
+    const uint32_t a = acc[((size_t)board * n_win + wi) * NCH + c];
+    const int64_t w_lo = r_lo + (int64_t)wi * Lw;          // first row of the window
+    if (c == 0) s_n = 0;
+    __syncthreads();
+    uint32_t key = 0xFFFFFFFFu;
+    uint64_t word = 0;
+    if (a) {
+        const int64_t r = (int64_t)a - 1;
+        int S = 0;
+        for (int k = 1; k <= M; ++k) S += ph[(r - k) * NCH + c];
+        int vmin = ph[r * NCH + c];
+        int64_t tp = r;
+        for (int j = 1; j < W; ++j) {
+            const int v = ph[(r + j) * NCH + c];
+            if (v < vmin) { vmin = v; tp = r + j; }
+        }
+        const double y1 = (double)ph[(tp - 1) * NCH + c], y2 = (double)vmin, y3 = (double)ph[(tp + 1) * NCH + c];
+        const double den = __dsub_rn(__dadd_rn(y3, y1), __dmul_rn(2.0, y2));
+        double y4 = y2;
+        if (den != 0.0) {
+            const double dy = __dsub_rn(y3, y1);
+            y4 = __dsub_rn(y2, __ddiv_rn(__dmul_rn(0.125, __dmul_rn(dy, dy)), den));
+        }
+        const int peak = (__double2int_rz(__dmul_rn(y4, 0.0625)) + 2048) & 0xFFF;
+        const int p1 = (vmin / 16 + 2048) & 0xFFF;
+        const int base = (S / (16 * M) + 2048) & 0xFFF;
+        const int64_t t = t_abs0 + r;
+        const uint32_t ts = (uint32_t)(t % SEC_US);
+        word = ((uint64_t)c << 56) | ((uint64_t)peak << 44) | ((uint64_t)p1 << 32) | ((uint64_t)base << 20) | ts;
+        key = ((uint32_t)(r - w_lo) << 9) | (uint32_t)(c + 1);
+        s_keys[atomicAdd(&s_n, 1)] = key;
+    }
+    // end-of-second event inside this window?
+    if (c == 0) {
+        const int64_t ta = t_abs0 + w_lo;
+        const int64_t tb = min(t_abs0 + w_lo + Lw, t_abs0 + r_hi);
+        int64_t B = ta <= 0 ? SEC_US : ((ta + SEC_US - 1) / SEC_US) * SEC_US;
+        if (B < tb) s_keys[atomicAdd(&s_n, 1)] = ((uint32_t)(B - ta) << 9);          // channel field 0: before all channels
+    }
+    __syncthreads();
+    const int n = s_n;
+    const uint32_t off = win_off[(size_t)board * (n_win + 1) + wi];
+    uint64_t *out = words + (size_t)board * words_cap;
+    if (a) {
+        int rank = 0;
+        for (int i = 0; i < n; ++i) rank += s_keys[i] < key;
+        if ((int64_t)off + rank < words_cap) out[off + rank] = word;
+    }
+    if (c == 0) {   // the EOS word, if any
+        const int64_t ta = t_abs0 + w_lo;
+        const int64_t tb = min(t_abs0 + w_lo + Lw, t_abs0 + r_hi);
+        int64_t B = ta <= 0 ? SEC_US : ((ta + SEC_US - 1) / SEC_US) * SEC_US;
+        if (B < tb) {
+            const uint32_t k = ((uint32_t)(B - ta) << 9);
+            int rank = 0;
+            for (int i = 0; i < n; ++i) rank += s_keys[i] < k;
+            if ((int64_t)off + rank < words_cap) out[off + rank] = ~0ull;
+        }
+    }
+}
+
+// history <- last H samples of [history | new input]
+__global__ void update_history_kernel(uint32_t *hist, int H, const uint32_t *in, int64_t n, int n_boards) {
+    const int board = blockIdx.y;
+    uint32_t *h = hist + (size_t)board * H;
+    const uint32_t *x = in + (size_t)board * n;
+    // out-of-place is required when n < H (shift): use a two-phase grid-stride that reads before writing
+    // only when n >= H (pure copy); the n < H case is handled on the host by a staging buffer.
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < H; i += (int64_t)gridDim.x * blockDim.x)
+        h[i] = x[n - H + i];
+}
+
+__global__ void pack_dds_kernel(const int16_t *I, const int16_t *Q, int n_lut, uint32_t *out) {
+    // out[t][m] = lut[(t/2)*512 + 2*((m+154)%256) + (t&1)]   (define_DDS_LUT layout, ROACH_Setup.py:526-530)
+    const int Ld = n_lut / 256;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= Ld * NCH) return;
+    const int t = idx / NCH, m = idx % NCH;
+    const int src = (t >> 1) * 512 + 2 * ((m + 154) & 255) + (t & 1);
+    out[idx] = (uint32_t)(uint16_t)I[src] | ((uint32_t)(uint16_t)Q[src] << 16);
+}
+
+// ------------------------------------------------------------------------------------------
+// synthetic ADC stream
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+    return x;
+}
+__device__ __forceinline__ float u01(uint64_t h) { return ((h >> 40) + 0.5f) * (1.0f / 16777216.0f); }
+
+// theta[u][i]: phase excursion of tone i at microsecond u (recursive exponential decay of hashed pulses)
+__global__ void synth_theta_kernel(float *theta, int n_tones, int64_t n_us, int64_t u_abs0, int board_id,
+                                   mkid_synth_params prm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tones) return;
+    const float decay = expf(-1.0f / prm.tau_us);
+    const float p = prm.pulse_rate * 1e-6f;
+    const int64_t warm = 512;
+    float acc = 0.f;
+    for (int64_t u = u_abs0 - warm; u < u_abs0 + n_us; ++u) {
+        acc *= decay;
+        if (u >= 0) {
+            const uint64_t h = mix64(prm.seed ^ mix64(((uint64_t)board_id << 48) ^ ((uint64_t)i << 32) ^ (uint64_t)u));
+            if (u01(h) < p) {
+                const float depth = prm.deg_lo + (prm.deg_hi - prm.deg_lo) * u01(mix64(h + 1));
+                acc -= depth * 0.017453292519943295f;
+            }
+        }
+        if (u >= u_abs0) theta[(u - u_abs0) * n_tones + i] = acc;
+    }
+}
+
+__global__ void __launch_bounds__(256) synth_adc_kernel(uint32_t *out, int64_t n, int64_t n_abs0, const float *theta,
+                                                        const int32_t *tone_bin, const float *tone_amp,
+                                                        const float *tone_phase, int board_id, float scale,
+                                                        mkid_synth_params prm) {
+    extern __shared__ float s_syn[];     // theta row | bins | amp | phase
+    float *s_theta = s_syn;
+    int *s_bin = reinterpret_cast<int *>(s_syn + prm.n_tones);
+    float *s_amp = s_syn + 2 * prm.n_tones;
+    float *s_ph = s_syn + 3 * prm.n_tones;
+    const int64_t u = blockIdx.x;                  // one microsecond (512 samples) per CTA
+    for (int i = threadIdx.x; i < prm.n_tones; i += blockDim.x) {
+        s_theta[i] = theta[u * prm.n_tones + i] + tone_phase[i];
+        s_bin[i] = tone_bin[i];
+        s_amp[i] = tone_amp[i];
+    }
+    __syncthreads();
+    const uint64_t mask = (uint64_t)prm.n_lut - 1;
+    const float inv = 6.283185307179586f / (float)prm.n_lut;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+        const int64_t nl = u * 512 + s * 256 + threadIdx.x;
+        if (nl >= n) continue;
+        const uint64_t na = (uint64_t)(n_abs0 + nl);
+        float xr = 0.f, xi = 0.f;
+        for (int i = 0; i < prm.n_tones; ++i) {
+            const uint32_t frac = (uint32_t)(((uint64_t)(uint32_t)s_bin[i] * na) & mask);
+            float sn, cs;
+            __sincosf(fmaf((float)frac, inv, s_theta[i]), &sn, &cs);
+            xr = fmaf(s_amp[i], cs, xr);
+            xi = fmaf(s_amp[i], sn, xi);
+        }
+        const uint64_t h = mix64(prm.seed ^ mix64(0x9e3779b97f4a7c15ull + ((uint64_t)board_id << 56) + na));
+        const float u1 = u01(h), u2 = u01(mix64(h ^ 0xabcdef12345ull));
+        const float rad = sqrtf(-2.0f * __logf(u1)) * prm.noise_lsb;
+        float sn, cs;
+        __sincosf(6.283185307179586f * u2, &sn, &cs);
+        int vi = __float2int_rn(fmaf(xr, scale, rad * cs)), vq = __float2int_rn(fmaf(xi, scale, rad * sn));
+        vi = max(-2047, min(2047, vi));
+        vq = max(-2047, min(2047, vq));
+        out[nl] = (uint32_t)(uint16_t)(int16_t)vi | ((uint32_t)(uint16_t)(int16_t)vq << 16);
+    }
+}
+
+int ensure(mkid_ctx *ctx, void **p, size_t *cap, size_t bytes) {
+    if (*cap >= bytes && *p) return MKID_OK;
+    if (*p) { MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); MKID_CUDA(ctx, cudaFree(*p)); *p = nullptr; *cap = 0; }
+    const size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(p, want);
+    if (e != cudaSuccess) return mkid_fail(ctx, MKID_ENOMEM, "device allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+    *cap = want;
+    return MKID_OK;
+}
+
+// K5 driver shared by mkid_chan_process and mkid_chan_detect
+int run_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase_dev, int64_t rows, int64_t r_lo, int64_t r_hi,
+               int64_t t_abs0, uint64_t *words_dev, int64_t words_cap) {
+    const ChanDev &d = ch->d;
+    const int B = d.n_boards;
+    const int64_t n_groups = (rows + 31) >> 5;
+    int rc;
+    size_t cap;
+    cap = ch->mask_bytes;
+    if ((rc = ensure(ctx, (void **)&ch->mask, &cap, (size_t)B * n_groups * NCH * 4))) return rc;
+    ch->mask_bytes = cap;
+    const int n_win = (int)((r_hi - r_lo + d.Lw - 1) / d.Lw);
+    cap = ch->acc_bytes;
+    if ((rc = ensure(ctx, (void **)&ch->acc, &cap, (size_t)B * n_win * NCH * 4))) return rc;
+    ch->acc_bytes = cap;
+    cap = ch->win_bytes;
+    if ((rc = ensure(ctx, (void **)&ch->win_cnt, &cap, (size_t)B * (n_win + 1) * 4))) return rc;
+    ch->win_bytes = cap;
+    MKID_CUDA(ctx, cudaMemsetAsync(ch->acc, 0, (size_t)B * n_win * NCH * 4, ctx->stream));
+    MKID_CUDA(ctx, cudaMemsetAsync(ch->win_cnt, 0, (size_t)B * (n_win + 1) * 4, ctx->stream));
+    dim3 gc((unsigned)((rows + CAND_ROWS - 1) / CAND_ROWS), B);
+    candidates_kernel<<<gc, 256, 0, ctx->stream>>>(phase_dev, rows, d.M, d.thr, ch->mask);
+    MKID_CHECK_LAUNCH(ctx);
+    resolve_kernel<<<dim3(NCH / 32, B), 32, 0, ctx->stream>>>(ch->mask, rows, r_lo, r_hi, t_abs0, d.L, d.Lw, n_win,
+                                                             d.t_next, ch->acc, ch->win_cnt);
+    MKID_CHECK_LAUNCH(ctx);
+    scan_kernel<<<B, 256, 0, ctx->stream>>>(ch->win_cnt, n_win, r_lo, r_hi, t_abs0, d.Lw, ch->n_words_dev);
+    MKID_CHECK_LAUNCH(ctx);
+    emit_kernel<<<dim3(n_win, B), 256, 0, ctx->stream>>>(phase_dev, rows, ch->acc, ch->win_cnt, n_win, r_lo, r_hi, t_abs0,
+                                                         d.M, d.W, d.Lw, words_dev, words_cap);
+    MKID_CHECK_LAUNCH(ctx);
+    return MKID_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" int mkid_chan_create(mkid_ctx *ctx, const mkid_chan_params *prm, mkid_chan **out) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, prm && out, "chan_create: NULL argument");
+    MKID_REQUIRE(ctx, prm->n_boards >= 1 && prm->n_boards <= 64, "n_boards must be 1..64");
+    MKID_REQUIRE(ctx, prm->n_lut >= 512 && (prm->n_lut & (prm->n_lut - 1)) == 0, "n_lut must be a power of two >= 512");
+    MKID_REQUIRE(ctx, prm->mean_len >= 1 && prm->mean_len <= 32, "mean_len must be 1..32");
+    MKID_REQUIRE(ctx, prm->holdoff >= 32, "holdoff must be >= 32");
+    MKID_REQUIRE(ctx, prm->peak_win >= 1 && prm->peak_win <= 60, "peak_win must be 1..60");
+    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
+    mkid_chan *ch = new mkid_chan();
+    ChanDev &d = ch->d;
+    const int B = prm->n_boards;
+    d.n_boards = B; d.n_lut = prm->n_lut; d.Ld = prm->n_lut / 256;
+    d.M = prm->mean_len; d.L = prm->holdoff; d.W = prm->peak_win;
+    int lw = 32;
+    while (lw * 2 <= d.L && lw * 2 <= 512) lw *= 2;
+    d.Lw = lw;
+    // history: earliest sample read = 256*(fb_first+1) - 2048 with fb_first >= 2*(-PRE_ROWS) - 24 - 7
+    d.H = HOP * (2 * PRE_ROWS + 24 + 8) + WIN;
+    auto A = [&](void **p, size_t bytes) -> int {
+        cudaError_t e = cudaMalloc(p, bytes);
+        return e == cudaSuccess ? 0 : 1;
+    };
+    int bad = 0;
+    bad |= A((void **)&d.window, WIN * 4);
+    bad |= A((void **)&d.tw512, 256 * 8);
+    bad |= A((void **)&d.tw256, 256 * 8);
+    bad |= A((void **)&d.bins, (size_t)B * NCH * 2);
+    bad |= A((void **)&d.dds, (size_t)B * d.Ld * NCH * 4);
+    bad |= A((void **)&d.gain, (size_t)B * NCH * 4);
+    bad |= A((void **)&d.cen_i, (size_t)B * NCH * 4);
+    bad |= A((void **)&d.cen_q, (size_t)B * NCH * 4);
+    bad |= A((void **)&d.thr, (size_t)B * NCH * 4);
+    bad |= A((void **)&d.hist, (size_t)B * d.H * 4);
+    bad |= A((void **)&d.t_next, (size_t)B * NCH * 8);
+    bad |= A((void **)&ch->n_words_dev, (size_t)B * 4);
+    if (bad) { mkid_chan_destroy(ctx, ch); return mkid_fail(ctx, MKID_ENOMEM, "chan_create: device allocation failed"); }
+    // default window (Hamming-windowed sinc, sum 1, float32) and twiddles, computed in double on the host
+    std::vector<float> h(WIN);
+    {
+        std::vector<double> hd(WIN);
+        double sum = 0;
+        for (int m = 0; m < WIN; ++m) {
+            const double x = (m - (WIN - 1) / 2.0) / NFFT;
+            const double sinc = x == 0 ? 1.0 : sin(M_PI * x) / (M_PI * x);
+            const double ham = 0.54 - 0.46 * cos(2.0 * M_PI * m / (WIN - 1));
+            hd[m] = sinc * ham; sum += hd[m];
+        }
+        for (int m = 0; m < WIN; ++m) h[m] = (float)(hd[m] / sum);
+    }
+    std::vector<float2> t512(256), t256(256);
+    for (int k = 0; k < 256; ++k) t512[k] = make_float2((float)cos(-2.0 * M_PI * k / 512.0), (float)sin(-2.0 * M_PI * k / 512.0));
+    for (int q = 0; q < 16; ++q)
+        for (int j = 0; j < 16; ++j) {
+            const double a = -2.0 * M_PI * ((j * q) % 256) / 256.0;
+            t256[q * 16 + j] = make_float2((float)cos(a), (float)sin(a));
+        }
+    MKID_CUDA(ctx, cudaMemcpy(d.window, h.data(), WIN * 4, cudaMemcpyHostToDevice));
+    MKID_CUDA(ctx, cudaMemcpy(d.tw512, t512.data(), 256 * 8, cudaMemcpyHostToDevice));
+    MKID_CUDA(ctx, cudaMemcpy(d.tw256, t256.data(), 256 * 8, cudaMemcpyHostToDevice));
+    for (int k = 0; k < FIRT; ++k) d.fir[k] = 0.f;
+    *out = ch;
+    return mkid_chan_reset(ctx, ch);
+}
+
+extern "C" void mkid_chan_destroy(mkid_ctx *ctx, mkid_chan *ch) {
+    if (!ch) return;
+    if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+    ChanDev &d = ch->d;
+    void *ps[] = {d.window, d.tw512, d.tw256, d.bins, d.dds, d.gain, d.cen_i, d.cen_q, d.thr, d.hist, d.t_next,
+                  ch->n_words_dev, ch->phase_buf, ch->mask, ch->acc, ch->win_cnt, ch->words_dev, ch->in_dev};
+    for (void *p : ps) if (p) cudaFree(p);
+    delete ch;
+}
+
+extern "C" int mkid_chan_set_fir(mkid_ctx *ctx, mkid_chan *ch, const int32_t *fir_int) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, ch && fir_int, "chan_set_fir: NULL argument");
+    for (int k = 0; k < FIRT; ++k) {
+        MKID_REQUIRE(ctx, fir_int[k] >= -2048 && fir_int[k] <= 2047, "FIR taps are 12-bit two's complement");
+        ch->d.fir[k] = (float)((double)fir_int[k] / (2047.0 * 32767.0));
+    }
+    ch->fir_set = true;
+    return MKID_OK;
+}
+
+extern "C" int mkid_chan_set_window(mkid_ctx *ctx, mkid_chan *ch, const float *h) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, ch && h, "chan_set_window: NULL argument");
+    MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MKID_CUDA(ctx, cudaMemcpy(ch->d.window, h, WIN * 4, cudaMemcpyDefault));
+    return MKID_OK;
+}
+
+extern "C" int mkid_chan_set_thresholds(mkid_ctx *ctx, mkid_chan *ch, int32_t board, const int32_t *thresholds) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, ch && thresholds && board >= 0 && board < ch->d.n_boards, "chan_set_thresholds: bad argument");
+    MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MKID_CUDA(ctx, cudaMemcpy(ch->d.thr + (size_t)board * NCH, thresholds, NCH * 4, cudaMemcpyDefault));
+    return MKID_OK;
+}
+
+extern "C" int mkid_chan_set_board(mkid_ctx *ctx, mkid_chan *ch, int32_t board, const int32_t *bins,
+                                   const int16_t *I_dds, const int16_t *Q_dds, const uint8_t *zero_ch,
+                                   const int32_t *centers_i, const int32_t *centers_q, const int32_t *thresholds) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, ch && bins && I_dds && Q_dds, "chan_set_board: NULL argument");
+    MKID_REQUIRE(ctx, board >= 0 && board < ch->d.n_boards, "chan_set_board: board out of range");
+    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
+    ChanDev &d = ch->d;
+    std::vector<int16_t> b16(NCH);
+    std::vector<float> g(NCH), ci(NCH), cq(NCH);
+    std::vector<int32_t> th(NCH);
+    for (int c = 0; c < NCH; ++c) {
+        b16[c] = (int16_t)(((bins[c] % NFFT) + NFFT) % NFFT);
+        g[c] = (zero_ch && zero_ch[c]) ? 0.f : 1.f;
+        ci[c] = centers_i ? 8.0f * (float)centers_i[c] : 0.f;
+        cq[c] = centers_q ? 8.0f * (float)centers_q[c] : 0.f;
+        th[c] = thresholds ? thresholds[c] : -25736;
+    }
+    MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    MKID_CUDA(ctx, cudaMemcpy(d.bins + (size_t)board * NCH, b16.data(), NCH * 2, cudaMemcpyHostToDevice));
+    MKID_CUDA(ctx, cudaMemcpy(d.gain + (size_t)board * NCH, g.data(), NCH * 4, cudaMemcpyHostToDevice));
+    MKID_CUDA(ctx, cudaMemcpy(d.cen_i + (size_t)board * NCH, ci.data(), NCH * 4, cudaMemcpyHostToDevice));
+    MKID_CUDA(ctx, cudaMemcpy(d.cen_q + (size_t)board * NCH, cq.data(), NCH * 4, cudaMemcpyHostToDevice));
+    MKID_CUDA(ctx, cudaMemcpy(d.thr + (size_t)board * NCH, th.data(), NCH * 4, cudaMemcpyHostToDevice));
+    // DDS LUT: upload in the reference layout, repack on the device to [t][channel] (I | Q<<16)
+    int16_t *tmp = nullptr;
+    int rc = mkid_scratch(ctx, SCR_AUX1, (size_t)d.n_lut * 4, (void **)&tmp);
+    if (rc) return rc;
+    MKID_CUDA(ctx, cudaMemcpyAsync(tmp, I_dds, (size_t)d.n_lut * 2, cudaMemcpyDefault, ctx->stream));
+    MKID_CUDA(ctx, cudaMemcpyAsync(tmp + d.n_lut, Q_dds, (size_t)d.n_lut * 2, cudaMemcpyDefault, ctx->stream));
+    const int total = d.Ld * NCH;
+    pack_dds_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(tmp, tmp + d.n_lut, d.n_lut,
+                                                                 d.dds + (size_t)board * d.Ld * NCH);
+    MKID_CHECK_LAUNCH(ctx);
+    MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ch->board_set[board] = true;
+    return MKID_OK;
+}
+
+extern "C" int mkid_chan_set_f32_phase_out(mkid_ctx *ctx, mkid_chan *ch, float *dev) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, ch, "chan_set_f32_phase_out: NULL");
+    MKID_REQUIRE(ctx, dev == nullptr || mkid_is_device_ptr(dev), "f32 phase output must be device memory");
+    ch->f32_out = dev;
+    return MKID_OK;
+}
+
+extern "C" int mkid_chan_reset(mkid_ctx *ctx, mkid_chan *ch) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, ch, "chan_reset: NULL");
+    ChanDev &d = ch->d;
+    MKID_CUDA(ctx, cudaMemsetAsync(d.hist, 0, (size_t)d.n_boards * d.H * 4, ctx->stream));
+    MKID_CUDA(ctx, cudaMemsetAsync(d.t_next, 0, (size_t)d.n_boards * NCH * 8, ctx->stream));
+    ch->t_consumed = 0;
+    return MKID_OK;
+}
+
+extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq, int64_t n, int32_t detect,
+                                 uint64_t *words, int64_t words_cap, int32_t *n_words, int16_t *phase_out) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, ch && iq, "chan_process: NULL argument");
+    ChanDev &d = ch->d;
+    MKID_REQUIRE(ctx, n > 0 && n % 512 == 0, "n must be a positive multiple of 512");
+    MKID_REQUIRE(ctx, n >= d.H, "n must be at least the history length (59392 samples) per call");
+    MKID_REQUIRE(ctx, ch->fir_set, "FIR taps not set (mkid_chan_set_fir)");
+    for (int b = 0; b < d.n_boards; ++b) MKID_REQUIRE(ctx, ch->board_set[b], "a board is not configured (mkid_chan_set_board)");
+    if (detect) MKID_REQUIRE(ctx, words && n_words && words_cap > 0, "detect requested but no word buffer");
+    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int B = d.n_boards;
+    const int64_t T = n / 512, rows = PRE_ROWS + T;
+    int rc;
+    size_t cap;
+    // input
+    const uint32_t *in_dev;
+    if (mkid_is_device_ptr(iq)) in_dev = (const uint32_t *)iq;
+    else {
+        cap = ch->in_bytes;
+        if ((rc = ensure(ctx, (void **)&ch->in_dev, &cap, (size_t)B * n * 4))) return rc;
+        ch->in_bytes = cap;
+        MKID_CUDA(ctx, cudaMemcpyAsync(ch->in_dev, iq, (size_t)B * n * 4, cudaMemcpyHostToDevice, ctx->stream));
+        in_dev = ch->in_dev;
+    }
+    cap = ch->phase_rows * NCH * 2 * B;
+    if (ch->phase_rows < (size_t)rows) {
+        if ((rc = ensure(ctx, (void **)&ch->phase_buf, &cap, (size_t)B * rows * NCH * 2))) return rc;
+        ch->phase_rows = (size_t)rows;
+    }
+    // K4
+    K4Params p;
+    p.d = d; p.in = in_dev; p.n = n; p.f0_abs = 2 * ch->t_consumed; p.phase = ch->phase_buf; p.rows = rows; p.phase_f32 = ch->f32_out;
+    {   // chunk the rows so that the grid is close to a multiple of 2 CTAs/SM, chunks of >= 256 rows
+        const int64_t target = std::max<int64_t>(1, (int64_t)ctx->num_sms * 2 / B);
+        int64_t k = std::max<int64_t>(1, (rows / 512 + target - 1) / target);     // waves
+        int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(k * target, rows / 256));
+        int64_t rpc = (rows + chunks - 1) / chunks;
+        rpc = (rpc + 3) / 4 * 4;
+        p.rows_per_chunk = (int)rpc;
+        p.chunks_per_board = (int)((rows + rpc - 1) / rpc);
+    }
+    const size_t smem = (size_t)(16 * FFT_STRIDE + RING * NCH + 256) * sizeof(float2);
+    MKID_CUDA(ctx, cudaFuncSetAttribute(channelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    channelize_kernel<<<dim3(p.chunks_per_board, B), 256, smem, ctx->stream>>>(p);
+    MKID_CHECK_LAUNCH(ctx);
+    if (phase_out) {
+        for (int b = 0; b < B; ++b)
+            MKID_CUDA(ctx, cudaMemcpyAsync(phase_out + (size_t)b * T * NCH, ch->phase_buf + ((size_t)b * rows + PRE_ROWS) * NCH,
+                                           (size_t)T * NCH * 2, cudaMemcpyDefault, ctx->stream));
+    }
+    const int64_t t_abs0 = ch->t_consumed - PRE_ROWS;
+    if (detect) {
+        uint64_t *wdev;
+        if (mkid_is_device_ptr(words)) wdev = words;
+        else {
+            cap = ch->words_bytes;
+            if ((rc = ensure(ctx, (void **)&ch->words_dev, &cap, (size_t)B * words_cap * 8))) return rc;
+            ch->words_bytes = cap;
+            wdev = ch->words_dev;
+        }
+        if ((rc = run_detect(ctx, ch, ch->phase_buf, rows, RES_LO, RES_LO + T, t_abs0, wdev, words_cap))) return rc;
+        MKID_CUDA(ctx, cudaMemcpyAsync(n_words, ch->n_words_dev, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int64_t mx = 0;
+        for (int b = 0; b < B; ++b) mx = std::max<int64_t>(mx, n_words[b]);
+        if (wdev != words) {
+            const int64_t ncopy = std::min<int64_t>(mx, words_cap);
+            for (int b = 0; b < B; ++b)
+                if (n_words[b] > 0)
+                    MKID_CUDA(ctx, cudaMemcpyAsync(words + (size_t)b * words_cap, wdev + (size_t)b * words_cap,
+                                                   (size_t)std::min<int64_t>(n_words[b], ncopy) * 8, cudaMemcpyDeviceToHost,
+                                                   ctx->stream));
+            MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        if (mx > words_cap) return mkid_fail(ctx, MKID_EINVAL, "word buffer too small: need %lld per board, have %lld",
+                                             (long long)mx, (long long)words_cap);
+    }
+    // history <- last H samples of this call (n >= H)
+    update_history_kernel<<<dim3(32, B), 256, 0, ctx->stream>>>(d.hist, d.H, in_dev, n, B);
+    MKID_CHECK_LAUNCH(ctx);
+    ch->t_consumed += T;
+    if (!mkid_is_device_ptr(iq) || phase_out) MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MKID_OK;
+}
+
+extern "C" int mkid_chan_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase, int64_t rows, int64_t t_abs0,
+                                int64_t *t_next, uint64_t *words, int64_t words_cap, int32_t *n_words) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, ch && phase && words && n_words && words_cap > 0, "chan_detect: NULL argument");
+    ChanDev &d = ch->d;
+    MKID_REQUIRE(ctx, rows > d.M + d.W + 1, "chan_detect: too few rows");
+    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int B = d.n_boards;
+    int rc;
+    const void *ph_dev;
+    if ((rc = mkid_stage_in(ctx, phase, (size_t)B * rows * NCH * 2, SCR_IN, &ph_dev))) return rc;
+    if (t_next) MKID_CUDA(ctx, cudaMemcpyAsync(d.t_next, t_next, (size_t)B * NCH * 8, cudaMemcpyDefault, ctx->stream));
+    void *w_dev;
+    if ((rc = mkid_stage_out(ctx, words, (size_t)B * words_cap * 8, SCR_OUT0, false, &w_dev))) return rc;
+    if ((rc = run_detect(ctx, ch, (const int16_t *)ph_dev, rows, d.M, rows - d.W - 1, t_abs0, (uint64_t *)w_dev, words_cap))) return rc;
+    MKID_CUDA(ctx, cudaMemcpyAsync(n_words, ch->n_words_dev, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (t_next) MKID_CUDA(ctx, cudaMemcpyAsync(t_next, d.t_next, (size_t)B * NCH * 8, cudaMemcpyDefault, ctx->stream));
+    MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = mkid_stage_out_finish(ctx, words, (size_t)B * words_cap * 8, w_dev))) return rc;
+    for (int b = 0; b < B; ++b)
+        if (n_words[b] > words_cap) return mkid_fail(ctx, MKID_EINVAL, "word buffer too small: need %d", n_words[b]);
+    return MKID_OK;
+}
+
+extern "C" int mkid_synth_adc(mkid_ctx *ctx, const mkid_synth_params *prm, int32_t n_boards, const int32_t *tone_bin,
+                              const float *tone_amp, const float *tone_phase, int64_t n, int64_t t_abs0_us, int16_t *out) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, prm && tone_bin && tone_amp && tone_phase && out, "synth_adc: NULL argument");
+    MKID_REQUIRE(ctx, prm->n_tones >= 1 && prm->n_tones <= 1024 && n > 0 && n % 512 == 0, "synth_adc: bad sizes");
+    MKID_REQUIRE(ctx, prm->n_lut >= 512 && (prm->n_lut & (prm->n_lut - 1)) == 0, "synth_adc: n_lut must be a power of two");
+    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int Tn = prm->n_tones;
+    const int64_t n_us = n / 512;
+    int rc;
+    float *theta; int32_t *d_bin; float *d_amp, *d_ph;
+    if ((rc = mkid_scratch(ctx, SCR_AUX2, (size_t)n_us * Tn * 4, (void **)&theta))) return rc;
+    if ((rc = mkid_scratch(ctx, SCR_AUX3, (size_t)n_boards * Tn * 12, (void **)&d_bin))) return rc;
+    d_amp = (float *)(d_bin + (size_t)n_boards * Tn);
+    d_ph = d_amp + (size_t)n_boards * Tn;
+    MKID_CUDA(ctx, cudaMemcpyAsync(d_bin, tone_bin, (size_t)n_boards * Tn * 4, cudaMemcpyDefault, ctx->stream));
+    MKID_CUDA(ctx, cudaMemcpyAsync(d_amp, tone_amp, (size_t)n_boards * Tn * 4, cudaMemcpyDefault, ctx->stream));
+    MKID_CUDA(ctx, cudaMemcpyAsync(d_ph, tone_phase, (size_t)n_boards * Tn * 4, cudaMemcpyDefault, ctx->stream));
+    void *o_dev;
+    if ((rc = mkid_stage_out(ctx, out, (size_t)n_boards * n * 4, SCR_OUT0, false, &o_dev))) return rc;
+    // amplitude scale: sum of squares -> 4 sigma headroom
+    std::vector<float> amp_h((size_t)n_boards * Tn);
+    MKID_CUDA(ctx, cudaMemcpyAsync(amp_h.data(), d_amp, amp_h.size() * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < n_boards; ++b) {
+        double ss = 0;
+        for (int i = 0; i < Tn; ++i) ss += (double)amp_h[(size_t)b * Tn + i] * amp_h[(size_t)b * Tn + i];
+        const float scale = Tn == 1 ? prm->full_scale / (float)sqrt(ss) : prm->full_scale / (4.0f * (float)sqrt(ss));
+        synth_theta_kernel<<<(Tn + 63) / 64, 64, 0, ctx->stream>>>(theta, Tn, n_us, t_abs0_us, b, *prm);
+        MKID_CHECK_LAUNCH(ctx);
+        synth_adc_kernel<<<(unsigned)n_us, 256, (size_t)Tn * 16, ctx->stream>>>(
+            (uint32_t *)o_dev + (size_t)b * n, n, t_abs0_us * 512, theta, d_bin + (size_t)b * Tn, d_amp + (size_t)b * Tn,
+            d_ph + (size_t)b * Tn, b, scale, *prm);
+        MKID_CHECK_LAUNCH(ctx);
+    }
+    return mkid_stage_out_finish(ctx, out, (size_t)n_boards * n * 4, o_dev);
+}
