@@ -201,6 +201,32 @@ typedef struct {
 int  mkid_synth_adc(mkid_ctx *ctx, const mkid_synth_params *prm, int32_t n_boards, const int32_t *tone_bin,
                     const float *tone_amp, const float *tone_phase, int64_t n, int64_t t_abs0_us, int16_t *out);
 
+/* ------------------------------------------------------------------ LUT synthesis (K1-K3)
+ * mkid_comb_lut replaces AppForm.freqCombLUT (ChannelizerControls/ROACH_Setup.py:416-475; twin with GUI
+ * offset/scale options ROACH_Setup_DAC.py:396-455): I[t] = sum a_n cos(2 pi f_n (t+offset)/fs + phi_n),
+ * Q[t] = sum a_n sin(2 pi f_n t/fs + phi_n), scale = fudge * max(|I|,|Q|) (fudge 1.1 for echo='yes',
+ * 1.0 for 'no'; scale_override > 0 replaces it: keep-old / custom scale, :456-459),
+ * out = int(v*32767/scale) truncated toward zero.  Every f_n must be a multiple of
+ * sample_rate/n_samples (define_DAC_LUT snaps to that grid, :498).  random_phase != 0 draws
+ * phi_n = numpy.random.seed(1000); uniform(0, 2 pi) per tone (:426-429) and returns them in phase.
+ * All arrays are [batch][n_tones] / [batch][n_samples]; freq/amp/phase/scale_out are host pointers. */
+int mkid_random_phases(uint32_t seed, int32_t n, double *out);
+int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double *amp, double *phase, int32_t n_tones,
+                  double sample_rate, int32_t n_samples, int32_t offset, double fudge, int32_t random_phase,
+                  double scale_override, int32_t batch, int16_t *I, int16_t *Q, double *scale_out);
+/* define_DDS_LUT (ROACH_Setup.py:506-532): 256 single-tone tables of n_lut/256 samples at
+ * sample_rate/512*2, each normalised to its own max, scattered to
+ * [j*512 + 2*((m+ch_shift)%256) + s].  offset: the GUI sample offset applied to I only
+ * (ROACH_Setup_DAC.py:397,421).  resid/phase: [batch][256] host or device. */
+int mkid_dds_lut(mkid_ctx *ctx, const double *resid_hz, const double *phase, double sample_rate, int32_t n_lut,
+                 int32_t ch_shift, int32_t offset, int32_t batch, int16_t *I_dds, int16_t *Q_dds, double *scales_out);
+/* write_LUTs (ROACH_Setup.py:560-569): per sample pair 16 bytes, big-endian int16
+ * q_dds[2n+1] q_dds[2n] q_dac[2n+1] q_dac[2n] i_dds[2n+1] i_dds[2n] i_dac[2n+1] i_dac[2n]; out: 8*n bytes */
+int mkid_pack_dram(mkid_ctx *ctx, const int16_t *I_dac, const int16_t *Q_dac, const int16_t *I_dds,
+                   const int16_t *Q_dds, int64_t n, uint8_t *out);
+/* test hook: the correctly rounded double sin/cos the exact LUT paths use */
+int mkid_sincos_cr(mkid_ctx *ctx, const double *x, int64_t n, double *s, double *c);
+
 #ifdef __cplusplus
 }
 #endif

@@ -83,6 +83,13 @@ _SIGNATURES = {
                                     c_void_p]),
     'mkid_chan_detect': (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64,
                                    c_void_p]),
+    'mkid_random_phases': (c_int32, [ctypes.c_uint32, c_int32, c_void_p]),
+    'mkid_comb_lut': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_double, c_int32, c_int32, c_double,
+                                c_int32, c_double, c_int32, c_void_p, c_void_p, c_void_p]),
+    'mkid_dds_lut': (c_int32, [c_void_p, c_void_p, c_void_p, c_double, c_int32, c_int32, c_int32, c_int32, c_void_p,
+                               c_void_p, c_void_p]),
+    'mkid_pack_dram': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    'mkid_sincos_cr': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     'mkid_synth_adc': (c_int32, [c_void_p, POINTER(SynthParams), c_int32, c_void_p, c_void_p, c_void_p, c_int64,
                                  c_int64, c_void_p]),
 }

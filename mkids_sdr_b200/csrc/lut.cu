@@ -1,0 +1,534 @@
+// K1-K3: DAC frequency-comb LUT, DDS LUT and DRAM image synthesis.
+//
+// Replaces AppForm.freqCombLUT / define_DDS_LUT / write_LUTs of
+// DataReadout/ChannelizerControls/ROACH_Setup.py:416-578 (multi-tone twin ROACH_Setup_DAC.py:396-558).
+//
+// K1  every comb frequency is a multiple of fs/N, so I + jQ = N * IDFT(X) with one spectral line
+//     per tone.  Bulk: four-step fp64 IFFT, N = N2 x N1 (N1 a power of four <= 1024): for each
+//     n2 < N2 a shared-memory Stockham radix-4 IFFT of length N1 over the (sparse) lines, fused
+//     with the global max search.  The reference evaluates every sample as a sequential float64 sum of
+//     a*cos(((2*pi*f)*t)/fs + phi); its int() truncation can flip on samples whose scaled value
+//     is within the reference's own rounding error of an integer.  Those samples (and the
+//     candidates for the max that sets the scale) are re-evaluated in the reference's operation
+//     order with correctly rounded double-double sin/cos, so the int16 output is the reference's.
+// K2  DDS tables are small (256 channels x N/256 samples): evaluated directly in reference order.
+// K3  big-endian 8 x int16 DRAM image (ROACH_Setup.py:560-569).
+#include <math.h>
+
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ double-double arithmetic
+struct dd { double hi, lo; };
+__device__ __forceinline__ dd two_sum(double a, double b) {
+    double s = __dadd_rn(a, b), bb = __dsub_rn(s, a);
+    double e = __dadd_rn(__dsub_rn(a, __dsub_rn(s, bb)), __dsub_rn(b, bb));
+    return {s, e};
+}
+__device__ __forceinline__ dd quick_two_sum(double a, double b) {
+    double s = __dadd_rn(a, b);
+    return {s, __dsub_rn(b, __dsub_rn(s, a))};
+}
+__device__ __forceinline__ dd two_prod(double a, double b) {
+    double p = __dmul_rn(a, b);
+    return {p, __fma_rn(a, b, -p)};
+}
+__device__ __forceinline__ dd dd_add(dd a, dd b) {
+    dd s = two_sum(a.hi, b.hi);
+    dd t = two_sum(a.lo, b.lo);
+    s.lo = __dadd_rn(s.lo, t.hi);
+    s = quick_two_sum(s.hi, s.lo);
+    s.lo = __dadd_rn(s.lo, t.lo);
+    return quick_two_sum(s.hi, s.lo);
+}
+__device__ __forceinline__ dd dd_mul(dd a, dd b) {
+    dd p = two_prod(a.hi, b.hi);
+    p.lo = __dadd_rn(p.lo, __dadd_rn(__dmul_rn(a.hi, b.lo), __dmul_rn(a.lo, b.hi)));
+    return quick_two_sum(p.hi, p.lo);
+}
+
+__constant__ double c_S[13][2] = {   // (-1)^i / (2i+3)!  i = 0..12  (sin series after the leading r)
+    {-0.16666666666666666, -9.25185853854297e-18},  {0.008333333333333333, 1.1564823173178714e-19},
+    {-0.0001984126984126984, -1.7209558293420705e-22}, {2.7557319223985893e-06, -1.858393274046472e-22},
+    {-2.505210838544172e-08, 1.448814070935912e-24}, {1.6059043836821613e-10, 1.2585294588752098e-26},
+    {-7.647163731819816e-13, -7.03872877733453e-30}, {2.8114572543455206e-15, 1.6508842730861433e-31},
+    {-8.22063524662433e-18, -2.2141894119604265e-34}, {1.9572941063391263e-20, -1.3643503830087908e-36},
+    {-3.868170170630684e-23, 8.843177655482344e-40}, {6.446950284384474e-26, -1.9330404233703465e-42},
+    {-9.183689863795546e-29, -1.4303150396787322e-45}};
+__constant__ double c_C[13][2] = {   // (-1)^i / (2i)!  i = 1..13  (cos series after the leading 1)
+    {-0.5, 0.0}, {0.041666666666666664, 2.3129646346357427e-18}, {-0.001388888888888889, 5.300543954373577e-20},
+    {2.48015873015873e-05, 2.1511947866775882e-23}, {-2.755731922398589e-07, -2.3767714622250297e-23},
+    {2.08767569878681e-09, -1.20734505911326e-25}, {-1.1470745597729725e-11, -2.0655512752830745e-28},
+    {4.779477332387385e-14, 4.399205485834081e-31}, {-1.5619206968586225e-16, -1.1910679660273754e-32},
+    {4.110317623312165e-19, 1.4412973378659527e-36}, {-8.896791392450574e-22, 7.911402614872376e-38},
+    {1.6117375710961184e-24, -3.6846573564509766e-41}, {-2.4795962632247976e-27, 1.2953730964765229e-43}};
+
+// sin and cos of a double, correctly rounded in all but astronomically rare cases (error < 2^-95
+// relative before the final rounding), |x| < 2^30.
+__device__ void sincos_cr(double x, double *s_out, double *c_out) {
+    const double PIO2_1 = 1.5707963267948966, PIO2_2 = 6.123233995736766e-17, PIO2_3 = -1.4973849048591698e-33;
+    const double k = rint(__dmul_rn(x, 0.6366197723675814));
+    dd p = two_prod(k, PIO2_1);
+    dd r = two_sum(x, -p.hi);
+    r.lo = __dsub_rn(r.lo, p.lo);
+    r = two_sum(r.hi, r.lo);
+    dd q = two_prod(k, PIO2_2);
+    r = dd_add(r, dd{-q.hi, -q.lo});
+    r.lo = __dsub_rn(r.lo, __dmul_rn(k, PIO2_3));
+    r = two_sum(r.hi, r.lo);
+    const dd z = dd_mul(r, r);
+    dd ps = {c_S[12][0], c_S[12][1]}, pc = {c_C[12][0], c_C[12][1]};
+#pragma unroll 1
+    for (int i = 11; i >= 0; --i) {
+        ps = dd_add(dd_mul(ps, z), dd{c_S[i][0], c_S[i][1]});
+        pc = dd_add(dd_mul(pc, z), dd{c_C[i][0], c_C[i][1]});
+    }
+    const dd sn = dd_add(r, dd_mul(dd_mul(r, z), ps));        // r + r^3 * S(z)
+    const dd cs = dd_add(dd{1.0, 0.0}, dd_mul(z, pc));        // 1 + z * C(z)
+    const long long kk = (long long)k;
+    switch ((int)(kk & 3)) {
+    case 0: *s_out = sn.hi; *c_out = cs.hi; break;
+    case 1: *s_out = cs.hi; *c_out = -sn.hi; break;
+    case 2: *s_out = -sn.hi; *c_out = -cs.hi; break;
+    default: *s_out = -cs.hi; *c_out = sn.hi; break;
+    }
+}
+
+// argument of the reference: ((2*pi*f)*(t+offset))/fs + phi, evaluated left to right in float64
+// (ROACH_Setup.py:439-440)
+__device__ __forceinline__ double ref_arg(double f, double t, double fs, double phi) {
+    const double w = __dmul_rn(6.283185307179586, f);
+    return __dadd_rn(__ddiv_rn(__dmul_rn(w, t), fs), phi);
+}
+
+struct CombParams {
+    const double *freq, *amp, *phase;    // [batch][T]
+    const long long *kbin;               // [batch][T] spectral line index in [0, N)
+    int T, N, N1, N2, offset;
+    double fs;
+    double2 *x;                          // [batch][N] bulk result
+    unsigned long long *maxbits;         // [batch] bits of the bulk max(|I|,|Q|)
+    double *scale;                       // [batch]
+    unsigned long long *exact_max;       // [batch] bits of the exact max
+    unsigned int *list;                  // [batch][cap] flagged samples: t | (isQ << 31)
+    unsigned int *count;                 // [batch]
+    unsigned int cap;
+    double fudge, scale_override;
+    int16_t *I, *Q;                      // [batch][N]
+};
+
+// ---- K1a: per (n2, batch) a length-N1 Stockham radix-4 IFFT in shared memory
+template <int N1>
+__global__ void __launch_bounds__(N1 / 4) comb_ifft_kernel(CombParams p) {
+    __shared__ double2 bufA[N1], bufB[N1];
+    __shared__ double s_red[32];
+    const int n2 = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    constexpr int NT = N1 / 4;
+    for (int i = tid; i < N1; i += NT) bufA[i] = make_double2(0.0, 0.0);
+    __syncthreads();
+    // sparse fill: G[k mod N1] += a e^{j phi} e^{2 pi j k n2 / N}
+    for (int i = tid; i < p.T; i += NT) {
+        const long long k = p.kbin[(size_t)b * p.T + i];
+        const long long m = (k * (long long)n2) % p.N;
+        double s, c, sp, cp;
+        sincospi(2.0 * (double)m / (double)p.N, &s, &c);
+        sincos(p.phase[(size_t)b * p.T + i], &sp, &cp);
+        const double a = p.amp[(size_t)b * p.T + i];
+        const double re = a * (c * cp - s * sp), im = a * (s * cp + c * sp);
+        const int k1 = (int)(k % N1);
+        atomicAdd(&bufA[k1].x, re);
+        atomicAdd(&bufA[k1].y, im);
+    }
+    __syncthreads();
+    double2 *in = bufA, *out = bufB;
+#pragma unroll 1
+    for (int Ns = 1; Ns < N1; Ns *= 4) {
+        const int j = tid, k = j % Ns;
+        double2 v[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) v[r] = in[j + r * NT];
+        if (Ns > 1) {
+#pragma unroll
+            for (int r = 1; r < 4; ++r) {
+                double s, c;
+                sincospi(2.0 * (double)(r * k) / (double)(Ns * 4), &s, &c);     // e^{+2 pi j r k/(4 Ns)}
+                v[r] = make_double2(v[r].x * c - v[r].y * s, v[r].x * s + v[r].y * c);
+            }
+        }
+        // inverse radix-4 butterfly (twiddle +j)
+        const double2 t0 = make_double2(v[0].x + v[2].x, v[0].y + v[2].y), t1 = make_double2(v[0].x - v[2].x, v[0].y - v[2].y);
+        const double2 t2 = make_double2(v[1].x + v[3].x, v[1].y + v[3].y);
+        const double2 t3 = make_double2(-(v[1].y - v[3].y), v[1].x - v[3].x);       // (v1 - v3) * (+j)
+        const int j0 = (j - k) * 4 + k;
+        out[j0] = make_double2(t0.x + t2.x, t0.y + t2.y);
+        out[j0 + Ns] = make_double2(t1.x + t3.x, t1.y + t3.y);
+        out[j0 + 2 * Ns] = make_double2(t0.x - t2.x, t0.y - t2.y);
+        out[j0 + 3 * Ns] = make_double2(t1.x - t3.x, t1.y - t3.y);
+        __syncthreads();
+        double2 *tmp = in; in = out; out = tmp;
+    }
+    // x[n2 + N2 * n1] = in[n1]
+    double mx = 0.0;
+    double2 *x = p.x + (size_t)b * p.N;
+    for (int n1 = tid; n1 < N1; n1 += NT) {
+        const double2 v = in[n1];
+        x[n2 + p.N2 * n1] = v;
+        mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
+    }
+    for (int d = 16; d > 0; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+    __syncthreads();
+    if (tid == 0) {
+        for (int i = 1; i < (NT + 31) / 32; ++i) mx = fmax(mx, s_red[i]);
+        atomicMax(&p.maxbits[b], (unsigned long long)__double_as_longlong(mx));
+    }
+}
+
+// bulk value of I (uses t+offset) or Q at sample t
+__device__ __forceinline__ double bulk_value(const CombParams &p, int b, int t, int isQ) {
+    const double2 *x = p.x + (size_t)b * p.N;
+    if (isQ) return x[t].y;
+    return x[(t + p.offset) & (p.N - 1)].x;      // N is a power of two; offset may be negative
+}
+
+// ---- K1b: samples that can hold the max -> list
+__global__ void comb_max_candidates_kernel(CombParams p) {
+    const int b = blockIdx.y;
+    const double mx = __longlong_as_double((long long)p.maxbits[b]);
+    const double lim = mx * (1.0 - 1e-8);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * p.N; i += gridDim.x * blockDim.x) {
+        const int t = i >> 1, isQ = i & 1;
+        if (fabs(bulk_value(p, b, t, isQ)) >= lim) {
+            const unsigned pos = atomicAdd(&p.count[b], 1u);
+            if (pos < p.cap) p.list[(size_t)b * p.cap + pos] = (unsigned)t | ((unsigned)isQ << 31);
+        }
+    }
+}
+
+// reference-order evaluation of one sample by one warp: terms in parallel, sum sequentially
+__device__ double exact_sample(const CombParams &p, int b, int t, int isQ, double *s_terms) {
+    const int lane = threadIdx.x & 31;
+    const double tt = isQ ? (double)t : (double)(t + p.offset);
+    for (int i = lane; i < p.T; i += 32) {
+        const double arg = ref_arg(p.freq[(size_t)b * p.T + i], tt, p.fs, p.phase[(size_t)b * p.T + i]);
+        double s, c;
+        sincos_cr(arg, &s, &c);
+        s_terms[i] = __dmul_rn(p.amp[(size_t)b * p.T + i], isQ ? s : c);
+    }
+    __syncwarp();
+    double acc = 0.0;
+    if (lane == 0)
+        for (int i = 0; i < p.T; ++i) acc = __dadd_rn(acc, s_terms[i]);
+    acc = __shfl_sync(0xffffffffu, acc, 0);
+    __syncwarp();
+    return acc;
+}
+
+// ---- K1c: exact max over the candidates (one warp per candidate), then the scale
+__global__ void __launch_bounds__(128) comb_exact_max_kernel(CombParams p) {
+    extern __shared__ double s_dyn[];
+    const int b = blockIdx.y, warp = threadIdx.x >> 5;
+    double *terms = s_dyn + (size_t)warp * p.T;
+    const unsigned n = min(p.count[b], p.cap);
+    for (unsigned c = blockIdx.x * 4 + warp; c < n; c += gridDim.x * 4) {
+        const unsigned e = p.list[(size_t)b * p.cap + c];
+        const double v = fabs(exact_sample(p, b, (int)(e & 0x7fffffffu), (int)(e >> 31), terms));
+        if ((threadIdx.x & 31) == 0) atomicMax(&p.exact_max[b], (unsigned long long)__double_as_longlong(v));
+    }
+}
+
+__global__ void comb_scale_kernel(CombParams p, int batch) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= batch) return;
+    const double a = __longlong_as_double((long long)p.exact_max[b]);
+    double sc = a;                                             // scale_factor = a.max()        (:448-449)
+    if (p.fudge != 1.0) sc = __dmul_rn(p.fudge, sc);           // scaleFudgeFactor*scale_factor (:453-455)
+    if (p.scale_override > 0.0) sc = p.scale_override;         // keep-old / custom scale       (:456-459)
+    p.scale[b] = sc;
+    p.count[b] = 0;                                            // the list is reused by the quantiser
+}
+
+// ---- K1d: quantise; flag samples within eps of an integer for exact re-evaluation
+__global__ void comb_quantise_kernel(CombParams p, double eps) {
+    const int b = blockIdx.y;
+    const double sc = p.scale[b];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * p.N; i += gridDim.x * blockDim.x) {
+        const int t = i >> 1, isQ = i & 1;
+        const double v = __ddiv_rn(__dmul_rn(bulk_value(p, b, t, isQ), 32767.0), sc);
+        if (fabs(v - rint(v)) < eps) {
+            const unsigned pos = atomicAdd(&p.count[b], 1u);
+            if (pos < p.cap) p.list[(size_t)b * p.cap + pos] = (unsigned)t | ((unsigned)isQ << 31);
+        }
+        const int16_t q = (int16_t)max(-32768, min(32767, __double2int_rz(v)));
+        (isQ ? p.Q : p.I)[(size_t)b * p.N + t] = q;
+    }
+}
+
+// ---- K1e: exact re-evaluation of the flagged samples
+__global__ void __launch_bounds__(128) comb_fixup_kernel(CombParams p) {
+    extern __shared__ double s_dyn[];
+    const int b = blockIdx.y, warp = threadIdx.x >> 5;
+    double *terms = s_dyn + (size_t)warp * p.T;
+    const unsigned n = min(p.count[b], p.cap);
+    const double sc = p.scale[b];
+    for (unsigned c = blockIdx.x * 4 + warp; c < n; c += gridDim.x * 4) {
+        const unsigned e = p.list[(size_t)b * p.cap + c];
+        const int t = (int)(e & 0x7fffffffu), isQ = (int)(e >> 31);
+        const double x = exact_sample(p, b, t, isQ, terms);
+        const double v = __ddiv_rn(__dmul_rn(x, 32767.0), sc);           // int(i*amp_full_scale/scale_factor) (:461-462)
+        if ((threadIdx.x & 31) == 0)
+            (isQ ? p.Q : p.I)[(size_t)b * p.N + t] = (int16_t)max(-32768, min(32767, __double2int_rz(v)));
+    }
+}
+
+// ---- K2: DDS tables, one CTA per (channel, batch); direct reference-order evaluation
+__global__ void __launch_bounds__(256) dds_lut_kernel(const double *resid, const double *phase, double fs2, int size,
+                                                      int n_lut, int ch_shift, int offset, int16_t *I_dds,
+                                                      int16_t *Q_dds, double *scales) {
+    extern __shared__ double s_dyn[];            // I[size] | Q[size]
+    __shared__ double s_red[8];
+    double *sI = s_dyn, *sQ = s_dyn + size;
+    const int m = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    const double f = resid[(size_t)b * 256 + m], ph = phase[(size_t)b * 256 + m];
+    double mx = 0.0;
+    for (int t = tid; t < size; t += 256) {
+        double s, c;
+        sincos_cr(ref_arg(f, (double)t, fs2, ph), &s, &c);
+        sQ[t] = s;                                // amplitude 1., accumulated onto 0. : exact
+        if (offset != 0) { double s2; sincos_cr(ref_arg(f, (double)(t + offset), fs2, ph), &s2, &c); }
+        sI[t] = c;
+        mx = fmax(mx, fmax(fabs(c), fabs(s)));
+    }
+    for (int d = 16; d > 0; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+    __syncthreads();
+    mx = s_red[0];
+    for (int i = 1; i < 8; ++i) mx = fmax(mx, s_red[i]);
+    if (tid == 0 && scales) scales[(size_t)b * 256 + m] = mx;
+    const int slot = 2 * ((m + ch_shift) & 255);
+    int16_t *Io = I_dds + (size_t)b * n_lut, *Qo = Q_dds + (size_t)b * n_lut;
+    for (int t = tid; t < size; t += 256) {
+        const int dst = (t >> 1) * 512 + slot + (t & 1);                 // ROACH_Setup.py:526-530
+        Io[dst] = (int16_t)__double2int_rz(__ddiv_rn(__dmul_rn(sI[t], 32767.0), mx));
+        Qo[dst] = (int16_t)__double2int_rz(__ddiv_rn(__dmul_rn(sQ[t], 32767.0), mx));
+    }
+}
+
+// ---- K3: DRAM image, 16 bytes per sample pair: >h of q_dds1 q_dds0 q_dac1 q_dac0 i_dds1 i_dds0 i_dac1 i_dac0
+__device__ __forceinline__ uint32_t be_pair(int16_t first, int16_t second) {
+    // bytes in memory: first.hi first.lo second.hi second.lo  (little-endian u32 store)
+    const uint32_t a = (uint16_t)first, c = (uint16_t)second;
+    return (a >> 8) | ((a & 0xFF) << 8) | ((c >> 8) << 16) | ((c & 0xFF) << 24);
+}
+__global__ void pack_dram_kernel(const int16_t *I_dac, const int16_t *Q_dac, const int16_t *I_dds, const int16_t *Q_dds,
+                                 int64_t n_pairs, uint4 *out) {
+    for (int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; n < n_pairs; n += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t qd = reinterpret_cast<const uint32_t *>(Q_dds)[n], qa = reinterpret_cast<const uint32_t *>(Q_dac)[n];
+        const uint32_t id = reinterpret_cast<const uint32_t *>(I_dds)[n], ia = reinterpret_cast<const uint32_t *>(I_dac)[n];
+        uint4 o;
+        o.x = be_pair((int16_t)(qd >> 16), (int16_t)(qd & 0xFFFF));
+        o.y = be_pair((int16_t)(qa >> 16), (int16_t)(qa & 0xFFFF));
+        o.z = be_pair((int16_t)(id >> 16), (int16_t)(id & 0xFFFF));
+        o.w = be_pair((int16_t)(ia >> 16), (int16_t)(ia & 0xFFFF));
+        out[n] = o;
+    }
+}
+
+__global__ void sincos_cr_test_kernel(const double *x, int64_t n, double *s, double *c) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sincos_cr(x[i], &s[i], &c[i]);
+}
+
+// ------------------------------------------------------------------ MT19937 (numpy.random.seed / uniform)
+struct MT19937 {
+    uint32_t mt[624]; int idx;
+    explicit MT19937(uint32_t seed) {            // init_genrand
+        mt[0] = seed;
+        for (int i = 1; i < 624; ++i) mt[i] = 1812433253u * (mt[i - 1] ^ (mt[i - 1] >> 30)) + (uint32_t)i;
+        idx = 624;
+    }
+    uint32_t next() {
+        if (idx >= 624) {
+            for (int k = 0; k < 624; ++k) {
+                uint32_t y = (mt[k] & 0x80000000u) | (mt[(k + 1) % 624] & 0x7fffffffu);
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+            }
+            idx = 0;
+        }
+        uint32_t y = mt[idx++];
+        y ^= y >> 11; y ^= (y << 7) & 0x9d2c5680u; y ^= (y << 15) & 0xefc60000u; y ^= y >> 18;
+        return y;
+    }
+    double res53() { uint32_t a = next() >> 5, b = next() >> 6; return (a * 67108864.0 + b) / 9007199254740992.0; }
+};
+
+}  // namespace
+
+// numpy.random.seed(1000); phase[n] = numpy.random.uniform(0, 2*numpy.pi)  (ROACH_Setup.py:426-429)
+extern "C" int mkid_random_phases(uint32_t seed, int32_t n, double *out) {
+    if (!out || n < 0) return MKID_EINVAL;
+    MT19937 g(seed);
+    const double two_pi = 2 * 3.141592653589793;
+    for (int i = 0; i < n; ++i) out[i] = 0.0 + (two_pi - 0.0) * g.res53();
+    return MKID_OK;
+}
+
+extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double *amp, double *phase, int32_t n_tones,
+                             double sample_rate, int32_t n_samples, int32_t offset, double fudge, int32_t random_phase,
+                             double scale_override, int32_t batch, int16_t *I, int16_t *Q, double *scale_out) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, freq_hz && amp && phase && I && Q, "comb_lut: NULL argument");
+    MKID_REQUIRE(ctx, n_tones >= 1 && n_tones <= 1024 && batch >= 1, "comb_lut: 1..1024 tones, batch >= 1");
+    const int N = n_samples;
+    MKID_REQUIRE(ctx, N >= 64 && N <= (1 << 24) && (N & (N - 1)) == 0, "comb_lut: n_samples must be a power of two in [64, 2^24]");
+    int N1 = 1024;                         // largest power of four <= min(1024, N/2)
+    while (N1 * 2 > N) N1 /= 4;
+    const int N2 = N / N1;
+    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t TB = (size_t)batch * n_tones;
+    // host: spectral line of every tone; must be on the fs/N grid (define_DAC_LUT snaps to it, :498)
+    std::vector<long long> kbin(TB);
+    std::vector<double> ph(phase, phase + TB);
+    for (int b = 0; b < batch; ++b) {
+        if (random_phase) mkid_random_phases(1000u, n_tones, ph.data() + (size_t)b * n_tones);
+        for (int i = 0; i < n_tones; ++i) {
+            const double k = freq_hz[(size_t)b * n_tones + i] * (double)N / sample_rate;
+            const double kr = nearbyint(k);
+            MKID_REQUIRE(ctx, fabs(k - kr) < 1e-6, "comb_lut: tone frequency is not a multiple of sampleRate/n_samples");
+            long long kk = (long long)kr % N;
+            if (kk < 0) kk += N;
+            kbin[(size_t)b * n_tones + i] = kk;
+        }
+    }
+    if (random_phase) memcpy(phase, ph.data(), TB * 8);
+    // device buffers
+    const unsigned cap = 1u << 17;
+    char *meta; double2 *x; unsigned *list;
+    int rc;
+    const size_t meta_bytes = TB * 32 + (size_t)batch * 48;
+    if ((rc = mkid_scratch(ctx, SCR_META, meta_bytes, (void **)&meta))) return rc;
+    if ((rc = mkid_scratch(ctx, SCR_AUX0, (size_t)batch * N * 16, (void **)&x))) return rc;
+    if ((rc = mkid_scratch(ctx, SCR_AUX1, (size_t)batch * cap * 4, (void **)&list))) return rc;
+    CombParams p;
+    double *d_freq = (double *)meta, *d_amp = d_freq + TB, *d_phase = d_amp + TB;
+    long long *d_k = (long long *)(d_phase + TB);
+    unsigned long long *d_max = (unsigned long long *)(d_k + TB), *d_emax = d_max + batch;
+    double *d_scale = (double *)(d_emax + batch);
+    unsigned *d_count = (unsigned *)(d_scale + batch);
+    MKID_CUDA(ctx, cudaMemcpyAsync(d_freq, freq_hz, TB * 8, cudaMemcpyHostToDevice, ctx->stream));
+    MKID_CUDA(ctx, cudaMemcpyAsync(d_amp, amp, TB * 8, cudaMemcpyHostToDevice, ctx->stream));
+    MKID_CUDA(ctx, cudaMemcpyAsync(d_phase, ph.data(), TB * 8, cudaMemcpyHostToDevice, ctx->stream));
+    MKID_CUDA(ctx, cudaMemcpyAsync(d_k, kbin.data(), TB * 8, cudaMemcpyHostToDevice, ctx->stream));
+    MKID_CUDA(ctx, cudaMemsetAsync(d_max, 0, (size_t)batch * 48 - 0, ctx->stream));
+    void *dI, *dQ;
+    if ((rc = mkid_stage_out(ctx, I, (size_t)batch * N * 2, SCR_OUT0, false, &dI))) return rc;
+    if ((rc = mkid_stage_out(ctx, Q, (size_t)batch * N * 2, SCR_OUT1, false, &dQ))) return rc;
+    p.freq = d_freq; p.amp = d_amp; p.phase = d_phase; p.kbin = d_k; p.T = n_tones; p.N = N; p.N1 = N1; p.N2 = N2; p.offset = offset;
+    p.fs = sample_rate; p.x = x; p.maxbits = d_max; p.scale = d_scale; p.exact_max = d_emax; p.list = list;
+    p.count = d_count; p.cap = cap; p.fudge = fudge; p.scale_override = scale_override; p.I = (int16_t *)dI; p.Q = (int16_t *)dQ;
+    dim3 g1(N2, batch);
+    switch (N1) {
+    case 16: comb_ifft_kernel<16><<<g1, 4, 0, ctx->stream>>>(p); break;
+    case 64: comb_ifft_kernel<64><<<g1, 16, 0, ctx->stream>>>(p); break;
+    case 256: comb_ifft_kernel<256><<<g1, 64, 0, ctx->stream>>>(p); break;
+    default: comb_ifft_kernel<1024><<<g1, 256, 0, ctx->stream>>>(p); break;
+    }
+    MKID_CHECK_LAUNCH(ctx);
+    const int gs = std::min(2 * N / 256, ctx->num_sms * 8);
+    const size_t wsm = (size_t)4 * n_tones * 8;
+    if (scale_override <= 0.0) {
+        comb_max_candidates_kernel<<<dim3(gs, batch), 256, 0, ctx->stream>>>(p);
+        MKID_CHECK_LAUNCH(ctx);
+        comb_exact_max_kernel<<<dim3(64, batch), 128, wsm, ctx->stream>>>(p);
+        MKID_CHECK_LAUNCH(ctx);
+    }
+    comb_scale_kernel<<<(batch + 63) / 64, 64, 0, ctx->stream>>>(p, batch);
+    MKID_CHECK_LAUNCH(ctx);
+    comb_quantise_kernel<<<dim3(gs, batch), 256, 0, ctx->stream>>>(p, 1e-4);
+    MKID_CHECK_LAUNCH(ctx);
+    comb_fixup_kernel<<<dim3(64, batch), 128, wsm, ctx->stream>>>(p);
+    MKID_CHECK_LAUNCH(ctx);
+    // overflow of the candidate / fix-up list would silently skip exact re-evaluation: check
+    std::vector<unsigned> cnt(batch);
+    std::vector<double> sc(batch);
+    MKID_CUDA(ctx, cudaMemcpyAsync(cnt.data(), d_count, (size_t)batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    MKID_CUDA(ctx, cudaMemcpyAsync(sc.data(), d_scale, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < batch; ++b) {
+        if (cnt[b] > cap) return mkid_fail(ctx, MKID_EINVAL, "comb_lut: %u samples need exact re-evaluation (> %u)", cnt[b], cap);
+        if (scale_out) scale_out[b] = sc[b];
+    }
+    if ((rc = mkid_stage_out_finish(ctx, I, (size_t)batch * N * 2, dI))) return rc;
+    return mkid_stage_out_finish(ctx, Q, (size_t)batch * N * 2, dQ);
+}
+
+extern "C" int mkid_dds_lut(mkid_ctx *ctx, const double *resid_hz, const double *phase, double sample_rate, int32_t n_lut,
+                            int32_t ch_shift, int32_t offset, int32_t batch, int16_t *I_dds, int16_t *Q_dds,
+                            double *scales_out) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, resid_hz && phase && I_dds && Q_dds && batch >= 1, "dds_lut: NULL argument");
+    MKID_REQUIRE(ctx, n_lut >= 512 && n_lut % 512 == 0, "dds_lut: n_lut must be a multiple of 512");
+    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
+    const double fs2 = sample_rate / 512.0 * 2.0;              // sampleRate/fft_len*2   (ROACH_Setup.py:525)
+    const double res = sample_rate / (double)n_lut;
+    const int size = (int)(fs2 / res);                          // size = int(sampleRate/resolution) (:422)
+    MKID_REQUIRE(ctx, size * 256 == n_lut, "dds_lut: table size mismatch");
+    int rc;
+    double *meta;
+    if ((rc = mkid_scratch(ctx, SCR_META, (size_t)batch * 256 * 24, (void **)&meta))) return rc;
+    double *d_res = meta, *d_ph = meta + (size_t)batch * 256, *d_sc = d_ph + (size_t)batch * 256;
+    MKID_CUDA(ctx, cudaMemcpyAsync(d_res, resid_hz, (size_t)batch * 256 * 8, cudaMemcpyDefault, ctx->stream));
+    MKID_CUDA(ctx, cudaMemcpyAsync(d_ph, phase, (size_t)batch * 256 * 8, cudaMemcpyDefault, ctx->stream));
+    void *dI, *dQ;
+    if ((rc = mkid_stage_out(ctx, I_dds, (size_t)batch * n_lut * 2, SCR_OUT0, false, &dI))) return rc;
+    if ((rc = mkid_stage_out(ctx, Q_dds, (size_t)batch * n_lut * 2, SCR_OUT1, false, &dQ))) return rc;
+    const size_t smem = (size_t)size * 16;
+    MKID_REQUIRE(ctx, smem <= 200 * 1024, "dds_lut: table too long for shared memory");
+    MKID_CUDA(ctx, cudaFuncSetAttribute(dds_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dds_lut_kernel<<<dim3(256, batch), 256, smem, ctx->stream>>>(d_res, d_ph, fs2, size, n_lut, ch_shift, offset, (int16_t *)dI,
+                                                                 (int16_t *)dQ, d_sc);
+    MKID_CHECK_LAUNCH(ctx);
+    if (scales_out) {
+        MKID_CUDA(ctx, cudaMemcpyAsync(scales_out, d_sc, (size_t)batch * 256 * 8, cudaMemcpyDefault, ctx->stream));
+        MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+    if ((rc = mkid_stage_out_finish(ctx, I_dds, (size_t)batch * n_lut * 2, dI))) return rc;
+    return mkid_stage_out_finish(ctx, Q_dds, (size_t)batch * n_lut * 2, dQ);
+}
+
+extern "C" int mkid_pack_dram(mkid_ctx *ctx, const int16_t *I_dac, const int16_t *Q_dac, const int16_t *I_dds,
+                              const int16_t *Q_dds, int64_t n, uint8_t *out) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, I_dac && Q_dac && I_dds && Q_dds && out && n > 0 && n % 2 == 0, "pack_dram: bad argument");
+    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void *a, *b, *c, *d; void *o; int rc;
+    if ((rc = mkid_stage_in(ctx, I_dac, n * 2, SCR_IN, &a))) return rc;
+    if ((rc = mkid_stage_in(ctx, Q_dac, n * 2, SCR_IN1, &b))) return rc;
+    if ((rc = mkid_stage_in(ctx, I_dds, n * 2, SCR_IN2, &c))) return rc;
+    if ((rc = mkid_stage_in(ctx, Q_dds, n * 2, SCR_IN3, &d))) return rc;
+    if ((rc = mkid_stage_out(ctx, out, n * 8, SCR_OUT2, false, &o))) return rc;
+    const int64_t pairs = n / 2;
+    const int grid = (int)std::min<int64_t>((pairs + 255) / 256, (int64_t)ctx->num_sms * 8);
+    pack_dram_kernel<<<grid, 256, 0, ctx->stream>>>((const int16_t *)a, (const int16_t *)b, (const int16_t *)c,
+                                                    (const int16_t *)d, pairs, (uint4 *)o);
+    MKID_CHECK_LAUNCH(ctx);
+    return mkid_stage_out_finish(ctx, out, n * 8, o);
+}
+
+// test hook: correctly rounded sin/cos used by the exact paths
+extern "C" int mkid_sincos_cr(mkid_ctx *ctx, const double *x, int64_t n, double *s, double *c) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, x && s && c && n > 0, "sincos_cr: bad argument");
+    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
+    const void *dx; void *ds, *dc; int rc;
+    if ((rc = mkid_stage_in(ctx, x, n * 8, SCR_IN, &dx))) return rc;
+    if ((rc = mkid_stage_out(ctx, s, n * 8, SCR_OUT0, false, &ds))) return rc;
+    if ((rc = mkid_stage_out(ctx, c, n * 8, SCR_OUT1, false, &dc))) return rc;
+    sincos_cr_test_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ctx->stream>>>((const double *)dx, n, (double *)ds, (double *)dc);
+    MKID_CHECK_LAUNCH(ctx);
+    if ((rc = mkid_stage_out_finish(ctx, s, n * 8, ds))) return rc;
+    return mkid_stage_out_finish(ctx, c, n * 8, dc);
+}
