@@ -1,0 +1,380 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native MKID readout hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the full chain (channelize -> phase -> detect -> photon words ->
+decode/bin/histogram [-> NCCL sum of the per-pixel histograms when N > 1]) over one batch of
+synthetic ADC samples: 8 boards x 256 channels per GPU (BASELINE config "full ARCONS chain ...
+8 boards x 256 channels", weak scaling: every GPU runs its own 8 boards).
+
+Rank 0 prints ONE JSON line (see the contract in the task statement / DESIGN.md "Measurement").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+FS = 512e6
+N_LUT = 2 ** 19
+BOARDS_PER_GPU = 8
+N_ACTIVE = 253
+METRIC = 'channelized_adc_samples_per_s_full_chain'
+UNIT = 'MS/s'
+BYTES_PER_SAMPLE = 4.0          # algorithmic: one complex int16 ADC sample read
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))['hbm_gbs']), 'measured (MEASURED_PEAKS.json)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([x.strip() for x in out.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith('active'):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons),
+                'samples': len(sm)}
+
+
+# ------------------------------------------------------------------ CPU reference arm (oracle port)
+def _cpu_worker(args):
+    import numpy as np   # noqa
+    from oracle import channelizer as oc
+    from oracle import decode as odec
+    iq, cfgd, slabs = args
+    cfg = oc.ChanConfig(cfgd['bins'], cfgd['I_dds'], cfgd['Q_dds'], cfgd['fir_int'], thresholds=cfgd['thr'],
+                        zero_ch=cfgd['zero_ch'], M=20, L=1000, W=32)
+    n = iq.shape[0]
+    step = n // slabs
+    hist = None
+    raws = []
+    for s in range(slabs):
+        a, b = s * step, (s + 1) * step
+        h = iq[max(0, a - 2 * 8192):a] if a else None
+        _, raw = oc.channelize_phase(iq[a:b], cfg, f0=a // 256, history=h)
+        raws.append(raw)
+    raw = np.concatenate(raws)
+    words = oc.detect_emit(raw, cfg, 0, np.zeros(256, np.int64), raw.shape[0] - 64 - cfg.M)
+    res = odec.packetmaster_bin([np.array(words, dtype=np.uint64)], 253, 4)
+    return len(words), int(res['counts'].sum())
+
+
+def cpu_reference_rate(iq_boards, cfgs, n_samples_each, cores):
+    """Oracle (NumPy float64 port of the model + integer detection + PacketMaster binning) on
+    `cores` processes, one board slice each.  Returns (MS/s, seconds, description)."""
+    import multiprocessing as mp
+    jobs = [(np.ascontiguousarray(iq_boards[i % len(iq_boards)][:n_samples_each]), cfgs[i % len(cfgs)], 2)
+            for i in range(cores)]
+    ctxmp = mp.get_context('spawn')        # the parent holds a CUDA context: never fork it
+    t0 = time.time()
+    with ctxmp.Pool(cores) as pool:
+        pool.map(_cpu_worker, jobs)
+    dt = time.time() - t0
+    total = cores * n_samples_each
+    return total / dt / 1e6, dt, '%d board slices x 2^%d samples, one process per core' % (cores, int(np.log2(n_samples_each)))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--log2-samples', type=int, default=25, help='ADC samples per board per step (log2)')
+    ap.add_argument('--hist-bins', type=int, default=64)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip the decode / LUT side measurements')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    n_gpus = max(args.gpus, 1)
+    if args.impl == 'reference' and rank != 0:
+        return 0
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py needs a CUDA device: the product path has no CPU fallback')
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1 and args.impl == 'b200':
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
+
+    from mkids_sdr_b200 import _lib
+    from mkids_sdr_b200.chain import ReadoutChain
+    from mkids_sdr_b200.channelizer import synth_adc
+    ctx = _lib.default_context(local_rank)
+
+    n = 1 << args.log2_samples
+    B = BOARDS_PER_GPU
+    n_roaches_total = B * world
+    n_pix = n_roaches_total * 253
+    exptime = 64
+    # per-pixel products live in torch tensors so that NCCL can reduce them in place
+    counts_t = torch.zeros(exptime * n_pix, dtype=torch.int32, device='cuda')
+    hist_t = torch.zeros(n_pix * args.hist_bins, dtype=torch.int32, device='cuda')
+    chain, boards = ReadoutChain.synthetic(B, N_LUT, N_ACTIVE, seed0=42 + 8 * rank, ctx=ctx, exptime=exptime,
+                                           n_roaches_total=n_roaches_total, roach0=B * rank, n_bins=args.hist_bins,
+                                           counts_buf=counts_t, hist_buf=hist_t)
+    thr = chain.derive_thresholds(boards)
+    tone_bins = np.stack([bd['tone_bins'] for bd in boards])
+
+    # synthetic ADC streams, generated on the GPU, resident in HBM (1 GiB per GPU at the default size)
+    iq_dev = torch.empty((B, n, 2), dtype=torch.int16, device='cuda')
+    synth_adc(B, n, tone_bins, n_lut=N_LUT, pulse_rate=1000.0, seed=1000 + rank, out=iq_dev, ctx=ctx)
+    ctx.sync()
+
+    cfgs_cpu = [dict(bins=bd['bins'], I_dds=bd['I_dds'], Q_dds=bd['Q_dds'], fir_int=chain.fir_int, thr=thr[b],
+                     zero_ch=bd['zero_ch'].astype(bool)) for b, bd in enumerate(boards)]
+    cores = len(os.sched_getaffinity(0))
+
+    if args.impl == 'reference':
+        n_each = 1 << 21
+        iq_host = [iq_dev[b, :n_each].cpu().numpy() for b in range(min(B, cores))]
+        vals = []
+        for it in range(args.warmup + args.steps):
+            v, dt, desc = cpu_reference_rate(iq_host, cfgs_cpu, n_each, cores)
+            if it >= args.warmup:
+                vals.append((v, dt))
+        v = float(np.mean([x[0] for x in vals]))
+        line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': n_gpus, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': float(np.mean([x[1] for x in vals]) * 1e3), 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+                'config': {'workload': 'full ARCONS chain, 8 boards x 256 channels per GPU (bounded CPU sample)',
+                           'sample': desc},
+                'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
+                'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return 0
+
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def reduce_products():
+        if dist is not None:
+            ctx.sync()
+            dist.all_reduce(hist_t)
+            dist.all_reduce(counts_t)
+
+    def run_steps(k, iq, words_host=None):
+        k4 = 0.0
+        for _ in range(k):
+            chain.process(iq, n=n, words_host=words_host)
+            k4 += chain.chan.last_kernel_ms()
+        return k4
+
+    # ---------------------------------------------------------------- device-resident value
+    run_steps(args.warmup, iq_dev)
+    reduce_products()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = ctx.launches
+    ctx.record(0)
+    t0 = time.time()
+    k4_ms = run_steps(args.steps, iq_dev)
+    reduce_products()
+    ctx.record(1)
+    barrier()
+    wall = time.time() - t0
+    dev_ms = ctx.elapsed_ms(0, 1)
+    launches = ctx.launches - l0
+    el = torch.tensor([max(dev_ms, 0.0), wall * 1e3], dtype=torch.float64, device='cuda')
+    if dist is not None:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    dev_ms, wall_ms = float(el[0]), float(el[1])
+    # the step contains host synchronisations (word counts come back every batch): report the
+    # slower of the device-event time and the wall clock
+    step_ms = max(dev_ms, wall_ms) / args.steps
+    value = world * B * n / (step_ms * 1e-3) / 1e6
+
+    # ---------------------------------------------------------------- end to end with host buffers
+    pin_iq = torch.empty((B, n, 2), dtype=torch.int16).pin_memory()
+    pin_iq.copy_(iq_dev.cpu())
+    cap = chain.chan.words_capacity(n)
+    pin_words = torch.empty((B, cap), dtype=torch.int64).pin_memory()
+    pin_counts = torch.empty(exptime * n_pix, dtype=torch.int32).pin_memory()
+    words_np = pin_words.numpy().view(np.uint64)
+
+    def e2e_steps(k):
+        nw = 0
+        for _ in range(k):
+            nw += int(chain.process(pin_iq, n=n, words_host=words_np).sum())
+            ctx._check(ctx.lib.mkid_memcpy(ctx.h, _lib.ptr(pin_counts), _lib.ptr(counts_t), pin_counts.numel() * 4))
+            ctx.sync()
+        return nw
+    e2e_steps(1)
+    barrier()
+    t0 = time.time()
+    nw = e2e_steps(max(args.steps // 2, 1))
+    reduce_products()
+    barrier()
+    e2e_ms = (time.time() - t0) * 1e3
+    el = torch.tensor([e2e_ms], dtype=torch.float64, device='cuda')
+    if dist is not None:
+        dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    e2e_step_ms = float(el[0]) / max(args.steps // 2, 1)
+    e2e_value = world * B * n / (e2e_step_ms * 1e-3) / 1e6
+    words_per_step = nw / max(args.steps // 2, 1)
+    if rank == 0:
+        sampler.stop_flag = True
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = measured_peaks()
+    k4_avg_ms = k4_ms / args.steps
+    achieved = BYTES_PER_SAMPLE * B * n / (k4_avg_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, 'profiles', 'k4_traffic.json')
+    if os.path.exists(tp):
+        try:
+            traffic = float(json.load(open(tp))['dram_bytes_per_sample']) * B * n
+        except Exception:
+            traffic = None
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': n_gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': 'full ARCONS chain with matched-filter pulse detection: 8 boards x 256 channels per GPU '
+                                   '(253 driven), channelize->phase->detect->photon words->decode/bin/hist',
+                       'boards_per_gpu': B, 'samples_per_board_per_step': n, 'n_lut': N_LUT, 'fir': 'matched_30us',
+                       'pulse_rate_hz': 1000, 'hist_bins': args.hist_bins,
+                       'l2': 'inputs (%.0f MiB per GPU per step) are larger than the 126 MB L2' % (B * n * 4 / 2 ** 20),
+                       'sharding': 'boards per GPU, no data-path collective; one NCCL all-reduce of per-pixel products'},
+            'roofline': {'bound': 'hbm', 'kernel': 'channelize_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                         'kernel_ms_per_launch': k4_avg_ms, 'kernel_share_of_step': k4_avg_ms / step_ms,
+                         'note': 'algorithmic 4 B per complex ADC sample; the kernel is FP32-issue-bound, not HBM-bound '
+                                 '(see DESIGN.md)'},
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(B * n * 4),
+                    'd2h_bytes_per_step': int(words_per_step * 8 + pin_counts.numel() * 4), 'ms_per_step': e2e_step_ms},
+            'gpu_launches': int(launches),
+            'photon_words_per_step': words_per_step,
+            'clocks': sampler.summary()}
+
+    if not args.no_extras:
+        try:
+            line['decode'] = decode_side_bench(ctx, peak)
+        except Exception as e:      # side measurement only
+            line['decode'] = {'error': str(e)}
+        try:
+            line['lut'] = lut_side_bench(ctx)
+        except Exception as e:
+            line['lut'] = {'error': str(e)}
+
+    if not args.no_cpu_baseline:
+        n_each = 1 << 21
+        iq_host = [iq_dev[b, :n_each].cpu().numpy() for b in range(min(B, cores))]
+        v, dt, desc = cpu_reference_rate(iq_host, cfgs_cpu, n_each, cores)
+        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc, 'seconds': dt}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def decode_side_bench(ctx, peak):
+    """BASELINE config 0 on the GPU: decode + per-pixel binning of 1e7-word synthetic photon files
+    (replicated 16x = 1.28 GB so the input exceeds L2), device resident."""
+    from mkids_sdr_b200 import synth
+    from mkids_sdr_b200.decode import PhotonDecoder
+    R, npix, secs = 8, 253, 10
+    streams, _ = synth.photon_streams(10 ** 7, R, npix, secs, seed=1234)
+    lens = [len(s) for s in streams]
+    reps = 16
+    words = np.tile(np.concatenate(streams), reps)
+    offs = np.concatenate([[0], np.cumsum(lens * reps)]).astype(np.int64)
+    roach = np.tile(np.arange(R), reps)
+    dw = ctx.to_device(words)
+    out = {}
+    for name, field, nb in (('counts_only', None, 1), ('counts_hist10', 'p1', 10), ('counts_hist4096', 'peak', 4096)):
+        lut = (np.arange(4096) * 10 // 4096) if nb == 10 else None
+        dec = PhotonDecoder(R, npix, secs, 2500, field, nb, lut, ctx=ctx)
+        for _ in range(3):
+            dec.decode_words(dw, offs, roach, want_stats=False)
+        ctx.sync(); ctx.record(2)
+        k = 10
+        for _ in range(k):
+            dec.decode_words(dw, offs, roach, want_stats=False)
+        ctx.record(3)
+        ms = ctx.elapsed_ms(2, 3) / k
+        gbs = words.size * 8 / ms / 1e6
+        out[name] = {'words_per_s': words.size / ms * 1e3, 'GB/s': gbs, 'frac_hbm': gbs / peak, 'ms': ms}
+    out['workload'] = 'Utils/bin.py-style decode + per-pixel binning, 2024 pixels, 16 x 1e7 photon words resident in HBM'
+    return out
+
+
+def lut_side_bench(ctx):
+    """BASELINE config 1: 256 tones, 2^19-sample int16 I/Q comb + DDS LUT + DRAM image."""
+    from mkids_sdr_b200 import lut
+    N, T = 2 ** 19, 256
+    k = np.sort(np.random.default_rng(0).choice(np.arange(-N // 2 + 1, N // 2), T, replace=False))
+    f = (k % N) * FS / N
+    amps = 10 ** (-(np.random.default_rng(1).integers(0, 20, T)) / 20.)
+    out = {}
+    for batch in (1, 8):
+        ff = np.tile(f, (batch, 1)); aa = np.tile(amps, (batch, 1))
+        lut.comb_lut(ff, FS, N, aa, ctx=ctx)
+        t0 = time.time()
+        reps = 3
+        for _ in range(reps):
+            lut.comb_lut(ff, FS, N, aa, ctx=ctx)
+        dt = (time.time() - t0) / reps
+        out['comb_batch%d' % batch] = {'luts_per_s': batch / dt, 'ms_per_call': dt * 1e3}
+    return out
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -100,6 +100,14 @@ int mkid_decode_words(mkid_ctx *ctx, const uint64_t *words, int64_t n_words,
                       const mkid_decode_cfg *cfg, uint32_t *counts_raw, uint32_t *hist,
                       mkid_decode_stats *stats);
 
+/* Same with explicit (start, length) segments that need not be contiguous, e.g. the per-board
+ * word regions mkid_chan_process fills. */
+int mkid_decode_words_seg(mkid_ctx *ctx, const uint64_t *words, int64_t n_words,
+                          const int64_t *seg_start, const int64_t *seg_len, const int32_t *seg_roach,
+                          const int32_t *seg_sec, int32_t *seg_sec_out, int32_t n_segments,
+                          const mkid_decode_cfg *cfg, uint32_t *counts_raw, uint32_t *hist,
+                          mkid_decode_stats *stats);
+
 /* Wire format of DataReadout/ReadoutControls/lib/PulseServer.c:318-352 as received by
  * PacketMaster.c:286-287: per bundle 8192 big-endian u32 low halves then 8192 big-endian
  * u32 high halves.  Segment offsets are in BUNDLES. */
@@ -181,6 +189,9 @@ int  mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq, int64_t 
 /* K5 alone on a caller-supplied phase stream (bit-exact seam test and phase-snapshot triggering):
  * phase int16 [n_boards][rows][256]; row r is absolute time t_abs0 + r; triggers are resolved for
  * rows [mean_len, rows - peak_win - 1) ; t_next int64 [n_boards][256] in/out (host). */
+/* device time (ms, CUDA events on the context stream) of the channelize kernel of the last
+ * mkid_chan_process call; the call synchronises on that kernel's end event */
+int  mkid_chan_last_kernel_ms(mkid_ctx *ctx, mkid_chan *ch, float *ms);
 int  mkid_chan_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase, int64_t rows, int64_t t_abs0,
                       int64_t *t_next, uint64_t *words, int64_t words_cap, int32_t *n_words);
 /* synthetic ADC stream for tests and benchmarks (replaces the ROACH ADC): per board a comb of

@@ -64,6 +64,8 @@ _SIGNATURES = {
     'mkid_flush_l2': (c_int32, [c_void_p]),
     'mkid_decode_words': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                     POINTER(DecodeCfg), c_void_p, c_void_p, c_void_p]),
+    'mkid_decode_words_seg': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_int32, POINTER(DecodeCfg), c_void_p, c_void_p, c_void_p]),
     'mkid_decode_wire': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                    POINTER(DecodeCfg), c_void_p, c_void_p, c_void_p]),
     'mkid_counts_cap': (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32]),
@@ -81,6 +83,7 @@ _SIGNATURES = {
     'mkid_chan_set_f32_phase_out': (c_int32, [c_void_p, c_void_p, c_void_p]),
     'mkid_chan_process': (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p,
                                     c_void_p]),
+    'mkid_chan_last_kernel_ms': (c_int32, [c_void_p, c_void_p, POINTER(c_float)]),
     'mkid_chan_detect': (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64,
                                    c_void_p]),
     'mkid_random_phases': (c_int32, [ctypes.c_uint32, c_int32, c_void_p]),

@@ -1,0 +1,133 @@
+"""The full software readout chain of one GPU: channelize -> phase -> detect -> photon words ->
+decode / per-pixel binning / histogram (K4 + K5 + K6), configured from the reference's control plane.
+
+This is the public API a user of the reference switches to for the data path:
+
+    chain = ReadoutChain.from_setup(setup_forms, pulses_forms, ...)   # or .synthetic(...)
+    out = chain.process(iq)          # iq: int16 [n_boards][n][2], host or device
+
+Boards (ROACH streams / feedlines) are independent; several GPUs each run their own chain over
+their own boards and sum the per-pixel histograms once (see dist.py).
+"""
+import os
+
+import numpy as np
+
+from . import _lib
+from .channelizer import Channelizer, synth_adc
+from .decode import PhotonDecoder
+from .pulses_form import PulsesForm
+from .setup_form import SetupForm
+
+DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'data')
+FS = 512e6
+
+
+class ReadoutChain:
+    def __init__(self, n_boards, n_lut, fir_int, mean_len=20, holdoff=1000, peak_win=32, npix_per_roach=253,
+                 exptime=64, n_roaches_total=None, roach0=0, hist_field='peak', n_bins=64, bin_lut=None, ctx=None,
+                 counts_buf=None, hist_buf=None):
+        self.ctx = ctx or _lib.default_context()
+        self.n_boards, self.n_lut = n_boards, n_lut
+        self.roach0 = roach0
+        self.chan = Channelizer(n_boards, n_lut, mean_len, holdoff, peak_win, ctx=self.ctx)
+        self.chan.set_fir(fir_int)
+        n_roaches_total = n_roaches_total or n_boards
+        if bin_lut is None and hist_field and n_bins < 4096:
+            bin_lut = np.arange(4096) * n_bins // 4096           # coarse pulse-height spectrum
+        self.dec = PhotonDecoder(n_roaches_total, npix_per_roach, exptime, hist_field=hist_field, n_bins=n_bins,
+                                 bin_lut=bin_lut, ctx=self.ctx, counts_buf=counts_buf, hist_buf=hist_buf)
+        self._words_dev = None
+        self._cap = 0
+        self.sec = np.zeros(n_boards, dtype=np.int32)
+
+    def set_board(self, b, bins, I_dds, Q_dds, zero_ch=None, centers_i=None, centers_q=None, thresholds=None):
+        self.chan.set_board(b, bins, I_dds, Q_dds, zero_ch, centers_i, centers_q, thresholds)
+
+    def reset(self):
+        self.chan.reset()
+        self.dec.reset()
+        self.sec[:] = 0
+
+    def process(self, iq, n=None, words_host=None):
+        """One batch: n samples per board.  Photon words stay in HBM and are decoded/binned in
+        place; if words_host (u64 [n_boards][cap] array, e.g. pinned) is given they are also
+        returned to the host.  Returns n_words per board."""
+        if n is None:
+            n = iq.shape[-2]
+        cap = self.chan.words_capacity(n)
+        if self._words_dev is None or self._cap < cap:
+            self._words_dev = self.ctx.alloc(self.n_boards * cap * 8)
+            self._cap = cap
+        (_, n_words), _ = self.chan.process(iq, n=n, detect=True, words_out=self._words_dev, words_cap=self._cap)
+        start = np.arange(self.n_boards, dtype=np.int64) * self._cap
+        self.sec = self.dec.decode_words_seg(self._words_dev, start, n_words.astype(np.int64),
+                                             self.roach0 + np.arange(self.n_boards), self.sec,
+                                             n_words=self.n_boards * self._cap, want_stats=False)
+        if words_host is not None:
+            c = self.ctx
+            for b in range(self.n_boards):
+                if n_words[b]:
+                    c._check(c.lib.mkid_memcpy(c.h, _lib.ptr(words_host[b]), self._words_dev.ptr + b * self._cap * 8,
+                                               int(n_words[b]) * 8))
+            c.sync()
+        return n_words
+
+    # ------------------------------------------------------------------ synthetic configuration
+    @staticmethod
+    def synthetic_boards(n_boards, n_lut=2 ** 19, n_active=253, seed0=42, lo_freq=5.0e9, ctx=None):
+        """Per board: 256 resonator frequencies on the fs/n_lut grid (n_active of them driven), the
+        DDS LUT from SetupForm.define_DDS_LUT (GPU), bins from select_bins.  Returns a list of dicts."""
+        boards = []
+        for b in range(n_boards):
+            rng = np.random.default_rng(seed0 + b)
+            k = np.sort(rng.choice(np.arange(-n_lut // 2 + 4096, n_lut // 2 - 4096), 256, replace=False))
+            sf = SetupForm(N_lut_entries=n_lut, multi_tone=True, ctx=ctx)
+            sf.save_npz = False
+            sf.lo_freq = lo_freq
+            sf.dac_freqs = [lo_freq + float(v) * FS / n_lut for v in k]
+            sf.attens = np.zeros(256)
+            sf.define_DDS_LUT()
+            zero = np.zeros(256, np.uint8)
+            zero[n_active:] = 1
+            boards.append(dict(tone_bins=(k % n_lut)[:n_active].astype(np.int64), bins=np.array(sf.fft_bins),
+                               I_dds=sf.I_dds.astype(np.int16), Q_dds=sf.Q_dds.astype(np.int16), zero_ch=zero,
+                               residuals=np.array(sf.freq_residuals)))
+        return boards
+
+    @classmethod
+    def synthetic(cls, n_boards, n_lut=2 ** 19, n_active=253, seed0=42, fir='matched_30us', threshold=None,
+                  ctx=None, **kw):
+        """Chain over synthetic boards.  Returns (chain, boards)."""
+        ctx = ctx or _lib.default_context()
+        pf = PulsesForm(N_lut_entries=n_lut, ctx=ctx)
+        pf.importFIRcoeffs(os.path.join(DATA_DIR, fir + '.txt'))
+        pf.dac_freqs = [0.0] * n_active
+        pf.zeroChannels = [0] * 256
+        pf.loadFIRcoeffs()
+        boards = cls.synthetic_boards(n_boards, n_lut, n_active, seed0, ctx=ctx)
+        chain = cls(n_boards, n_lut, pf.fir_int, ctx=ctx, **kw)
+        for b, bd in enumerate(boards):
+            thr = np.full(256, -3000 if threshold is None else threshold, np.int32)
+            chain.set_board(b, bd['bins'], bd['I_dds'], bd['Q_dds'], bd['zero_ch'], None, None, thr)
+        chain.fir_int = pf.fir_int
+        return chain, boards
+
+    def derive_thresholds(self, boards, n=2 ** 22, seed=7):
+        """loadThresholds (ROACH_Pulses.py:259-288) on a pulse-free stretch of the synthetic stream."""
+        tb = np.stack([bd['tone_bins'] for bd in boards])
+        iq = synth_adc(self.n_boards, n, tb, n_lut=self.n_lut, pulse_rate=0.0, seed=seed, ctx=self.ctx)
+        self.chan.reset()
+        _, ph = self.chan.process(iq, detect=False, want_phase=True)
+        self.chan.reset()
+        out = []
+        for b in range(self.n_boards):
+            thr = np.full(256, -25736, np.int32)
+            for c in range(256):
+                if boards[b]['zero_ch'][c]:
+                    continue
+                t, _ = PulsesForm._threshold(ph[b, 64:64 + 20480, c].astype(np.int64))
+                thr[c] = t
+            self.chan.set_thresholds(b, thr)
+            out.append(thr)
+        return out

@@ -95,6 +95,13 @@ class Channelizer:
             words = (words, n_words)
         return words, phase
 
+    def last_kernel_ms(self):
+        """Device time of the channelize kernel (K4) of the last process() call."""
+        ms = ctypes.c_float()
+        c = self.ctx
+        c._check(c.lib.mkid_chan_last_kernel_ms(c.h, self.h, ctypes.byref(ms)))
+        return float(ms.value)
+
     def detect(self, phase, t_abs0=0, t_next=None):
         """K5 alone on int16 phase rows [B][rows][256]; resolves rows [M, rows-W-1)."""
         ph = np.ascontiguousarray(phase, dtype=np.int16)

@@ -71,6 +71,7 @@ struct mkid_chan {
     bool board_set[64] = {};
     bool fir_set = false;
     float *f32_out = nullptr;            // set by mkid_chan_set_f32_phase_out (device pointer)
+    cudaEvent_t ev_k4[2] = {nullptr, nullptr};
 };
 
 namespace {
@@ -325,27 +326,38 @@ __global__ void __launch_bounds__(32) resolve_kernel(const uint32_t *__restrict_
     int64_t tn = t_next[board * NCH + c];
     uint32_t *ac = acc + (size_t)board * n_win * NCH;
     uint32_t *wc = win_cnt + (size_t)board * (n_win + 1);
-    const int64_t g_lo = r_lo >> 5, g_hi = (r_hi + 31) >> 5;
-    for (int64_t g0 = g_lo; g0 < g_hi; g0 += 8) {
+    const int64_t g_hi = (r_hi + 31) >> 5;
+    // first row this channel may trigger on: hold-off from earlier calls and the start-up guard
+    auto first_allowed = [&]() -> int64_t {
+        const int64_t t_min = tn > T_START ? tn : (int64_t)T_START;
+        const int64_t r = t_min - t_abs0;
+        return r > r_lo ? r : r_lo;
+    };
+    int64_t g = first_allowed() >> 5;
+    while (g < g_hi) {
         uint32_t wv[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) wv[u] = (g0 + u < g_hi) ? mk[(g0 + u) * NCH + c] : 0u;
+        for (int u = 0; u < 8; ++u) wv[u] = (g + u < g_hi) ? mk[(g + u) * NCH + c] : 0u;
+        bool jumped = false;
 #pragma unroll
         for (int u = 0; u < 8; ++u) {
             uint32_t w = wv[u];
-            while (w) {
-                const int b = __ffs(w) - 1;
-                w &= w - 1;
-                const int64_t r = ((g0 + u) << 5) + b;
-                if (r < r_lo || r >= r_hi) continue;
-                const int64_t t = t_abs0 + r;
-                if (t < T_START || t < tn) continue;
-                tn = t + L;
-                const int wi = (int)((r - r_lo) / Lw);
-                ac[(size_t)wi * NCH + c] = (uint32_t)(r + 1);
-                atomicAdd(&wc[wi], 1u);
-            }
+            if (!w) continue;
+            const int64_t r_base = (g + u) << 5;
+            const int64_t lo = first_allowed();
+            if (lo > r_base) { const int64_t sh = lo - r_base; w = sh >= 32 ? 0u : (w >> sh) << sh; }
+            if (r_base + 32 > r_hi) { const int64_t keep = r_hi - r_base; w = keep <= 0 ? 0u : (w & (0xFFFFFFFFu >> (32 - keep))); }
+            if (!w) continue;
+            const int64_t r = r_base + (__ffs(w) - 1);
+            tn = t_abs0 + r + L;                         // hold-off: L >= 32, so the next trigger is in a later group
+            const int wi = (int)((r - r_lo) / Lw);
+            ac[(size_t)wi * NCH + c] = (uint32_t)(r + 1);
+            atomicAdd(&wc[wi], 1u);
+            g = first_allowed() >> 5;                   // jump over the dead time
+            jumped = true;
+            break;
         }
+        if (!jumped) g += 8;
     }
     t_next[board * NCH + c] = tn;
 }
@@ -669,6 +681,7 @@ extern "C" void mkid_chan_destroy(mkid_ctx *ctx, mkid_chan *ch) {
     void *ps[] = {d.window, d.tw512, d.tw256, d.bins, d.dds, d.gain, d.cen_i, d.cen_q, d.thr, d.hist, d.t_next,
                   ch->n_words_dev, ch->phase_buf, ch->mask, ch->acc, ch->win_cnt, ch->words_dev, ch->in_dev};
     for (void *p : ps) if (p) cudaFree(p);
+    if (ch->ev_k4[0]) { cudaEventDestroy(ch->ev_k4[0]); cudaEventDestroy(ch->ev_k4[1]); }
     delete ch;
 }
 
@@ -800,8 +813,11 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     }
     const size_t smem = (size_t)(16 * FFT_STRIDE + RING * NCH + 256) * sizeof(float2);
     MKID_CUDA(ctx, cudaFuncSetAttribute(channelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (!ch->ev_k4[0]) { cudaEventCreate(&ch->ev_k4[0]); cudaEventCreate(&ch->ev_k4[1]); }
+    MKID_CUDA(ctx, cudaEventRecord(ch->ev_k4[0], ctx->stream));
     channelize_kernel<<<dim3(p.chunks_per_board, B), 256, smem, ctx->stream>>>(p);
     MKID_CHECK_LAUNCH(ctx);
+    MKID_CUDA(ctx, cudaEventRecord(ch->ev_k4[1], ctx->stream));
     if (phase_out) {
         for (int b = 0; b < B; ++b)
             MKID_CUDA(ctx, cudaMemcpyAsync(phase_out + (size_t)b * T * NCH, ch->phase_buf + ((size_t)b * rows + PRE_ROWS) * NCH,
@@ -839,6 +855,14 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     MKID_CHECK_LAUNCH(ctx);
     ch->t_consumed += T;
     if (!mkid_is_device_ptr(iq) || phase_out) MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MKID_OK;
+}
+
+extern "C" int mkid_chan_last_kernel_ms(mkid_ctx *ctx, mkid_chan *ch, float *ms) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, ch && ms && ch->ev_k4[0], "chan_last_kernel_ms: no process call yet");
+    MKID_CUDA(ctx, cudaEventSynchronize(ch->ev_k4[1]));
+    MKID_CUDA(ctx, cudaEventElapsedTime(ms, ch->ev_k4[0], ch->ev_k4[1]));
     return MKID_OK;
 }
 

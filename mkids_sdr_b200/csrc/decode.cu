@@ -24,7 +24,8 @@ struct DecParams {
     const uint64_t *words;     // flat format (or nullptr)
     const uint32_t *wire;      // wire format (or nullptr)
     const int64_t *seg_first_chunk;   // [n_seg+1]
-    const int64_t *seg_offset;        // [n_seg+1] words (flat) / bundles (wire)
+    const int64_t *seg_offset;        // [n_seg] first word (flat) / bundle (wire) of each segment
+    const int64_t *seg_len;           // [n_seg] words / bundles
     const int32_t *seg_roach;
     const int32_t *seg_sec;
     int32_t *seg_sec_out;
@@ -102,7 +103,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_kernel(DecParams p) {
                 w[4 * i + 3] = ((uint64_t)bswap32(h.w) << 32) | bswap32(l.w);
             }
         } else {
-            const long long seg_n = p.seg_offset[g + 1] - p.seg_offset[g];
+            const long long seg_n = p.seg_len[g];
             const long long rem = seg_n - lc * DEC_CHUNK;
             n_here = rem < DEC_CHUNK ? (int)rem : DEC_CHUNK;
             const uint64_t *base = p.words + p.seg_offset[g] + lc * DEC_CHUNK;
@@ -314,7 +315,7 @@ __global__ void quicklook_kernel(const uint32_t *counts_sec, const int32_t *pixe
 }
 
 int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, int64_t n_units,
-                  const int64_t *seg_offset, const int32_t *seg_roach, const int32_t *seg_sec,
+                  const int64_t *seg_offset, const int64_t *seg_len_in, const int32_t *seg_roach, const int32_t *seg_sec,
                   int32_t *seg_sec_out, int32_t n_seg, const mkid_decode_cfg *cfg, uint32_t *counts_raw,
                   uint32_t *hist, mkid_decode_stats *stats) {
     MKID_REQUIRE(ctx, cfg && seg_offset && seg_roach && n_seg > 0, "decode: missing cfg/segments");
@@ -328,9 +329,11 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
 
     // segment table (host) -> chunk prefix
     std::vector<int64_t> first_chunk(n_seg + 1, 0);
+    std::vector<int64_t> seg_len(n_seg);
     for (int i = 0; i < n_seg; ++i) {
-        int64_t len = seg_offset[i + 1] - seg_offset[i];
-        MKID_REQUIRE(ctx, len >= 0 && seg_offset[i + 1] <= n_units, "segment offsets out of range");
+        int64_t len = seg_len_in ? seg_len_in[i] : seg_offset[i + 1] - seg_offset[i];
+        seg_len[i] = len;
+        MKID_REQUIRE(ctx, len >= 0 && seg_offset[i] >= 0 && seg_offset[i] + len <= n_units, "segment offsets out of range");
         MKID_REQUIRE(ctx, seg_roach[i] >= 0 && seg_roach[i] < cfg->n_roaches, "segment roach out of range");
         first_chunk[i + 1] = first_chunk[i] + (wire_fmt ? 2 * len : (len + DEC_CHUNK - 1) / DEC_CHUNK);
     }
@@ -338,14 +341,15 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
     std::vector<int32_t> sec0(n_seg, 0);
     if (seg_sec) for (int i = 0; i < n_seg; ++i) sec0[i] = seg_sec[i];
 
-    // meta buffer: first_chunk | seg_offset | stats(5 u64) | roach | sec | sec_out | ticket
-    const size_t meta_bytes = (size_t)(n_seg + 1) * 16 + (size_t)n_seg * 12 + 5 * 8 + 16;
+    // meta buffer: first_chunk | seg_offset | seg_len | stats(5 u64) | roach | sec | sec_out | ticket
+    const size_t meta_bytes = (size_t)(n_seg + 1) * 24 + (size_t)n_seg * 12 + 5 * 8 + 16;
     char *meta = nullptr;
     int rc = mkid_scratch(ctx, SCR_META, meta_bytes, (void **)&meta);
     if (rc) return rc;
     int64_t *d_first = (int64_t *)meta;
     int64_t *d_off = d_first + (n_seg + 1);
-    unsigned long long *d_stats = (unsigned long long *)(d_off + (n_seg + 1));
+    int64_t *d_len = d_off + (n_seg + 1);
+    unsigned long long *d_stats = (unsigned long long *)(d_len + (n_seg + 1));
     int32_t *d_roach = (int32_t *)(d_stats + 5);
     int32_t *d_sec = d_roach + n_seg;
     int32_t *d_sec_out = d_sec + n_seg;
@@ -353,7 +357,8 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
     {   // upload the segment table only when it changed since the last call on this context
         std::vector<char> blob(meta_bytes, 0);
         memcpy(blob.data() + ((char *)d_first - meta), first_chunk.data(), (n_seg + 1) * 8);
-        memcpy(blob.data() + ((char *)d_off - meta), seg_offset, (n_seg + 1) * 8);
+        memcpy(blob.data() + ((char *)d_off - meta), seg_offset, n_seg * 8);
+        memcpy(blob.data() + ((char *)d_len - meta), seg_len.data(), n_seg * 8);
         memcpy(blob.data() + ((char *)d_roach - meta), seg_roach, n_seg * 4);
         memcpy(blob.data() + ((char *)d_sec - meta), sec0.data(), n_seg * 4);
         if (ctx->dec_meta_dev != meta || ctx->dec_meta_host != blob) {
@@ -394,7 +399,7 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
     DecParams p;
     p.words = wire_fmt ? nullptr : (const uint64_t *)d_in;
     p.wire = wire_fmt ? (const uint32_t *)d_in : nullptr;
-    p.seg_first_chunk = d_first; p.seg_offset = d_off; p.seg_roach = d_roach; p.seg_sec = d_sec;
+    p.seg_first_chunk = d_first; p.seg_offset = d_off; p.seg_len = d_len; p.seg_roach = d_roach; p.seg_sec = d_sec;
     p.seg_sec_out = d_sec_out; p.n_seg = n_seg; p.n_chunks = n_chunks;
     p.n_roaches = cfg->n_roaches; p.npix_per_roach = cfg->npix_per_roach; p.exptime = cfg->exptime;
     p.field_shift = want_hist ? cfg->hist_field_shift : 0; p.n_bins = want_hist ? cfg->n_bins : 0;
@@ -457,7 +462,17 @@ extern "C" int mkid_decode_words(mkid_ctx *ctx, const uint64_t *words, int64_t n
                                  uint32_t *hist, mkid_decode_stats *stats) {
     if (!ctx) return MKID_EINVAL;
     MKID_REQUIRE(ctx, words || n_words == 0, "words is NULL");
-    return decode_common(ctx, words, nullptr, n_words, seg_offset, seg_roach, seg_sec, seg_sec_out, n_segments, cfg,
+    return decode_common(ctx, words, nullptr, n_words, seg_offset, nullptr, seg_roach, seg_sec, seg_sec_out, n_segments, cfg,
+                         counts_raw, hist, stats);
+}
+
+extern "C" int mkid_decode_words_seg(mkid_ctx *ctx, const uint64_t *words, int64_t n_words, const int64_t *seg_start,
+                                     const int64_t *seg_len, const int32_t *seg_roach, const int32_t *seg_sec,
+                                     int32_t *seg_sec_out, int32_t n_segments, const mkid_decode_cfg *cfg,
+                                     uint32_t *counts_raw, uint32_t *hist, mkid_decode_stats *stats) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, (words || n_words == 0) && seg_len, "words / seg_len is NULL");
+    return decode_common(ctx, words, nullptr, n_words, seg_start, seg_len, seg_roach, seg_sec, seg_sec_out, n_segments, cfg,
                          counts_raw, hist, stats);
 }
 
@@ -467,7 +482,7 @@ extern "C" int mkid_decode_wire(mkid_ctx *ctx, const uint32_t *wire, int64_t n_b
                                 mkid_decode_stats *stats) {
     if (!ctx) return MKID_EINVAL;
     MKID_REQUIRE(ctx, wire, "wire is NULL");
-    return decode_common(ctx, nullptr, wire, n_bundles, seg_offset, seg_roach, seg_sec, seg_sec_out, n_segments, cfg,
+    return decode_common(ctx, nullptr, wire, n_bundles, seg_offset, nullptr, seg_roach, seg_sec, seg_sec_out, n_segments, cfg,
                          counts_raw, hist, stats);
 }
 

@@ -33,7 +33,7 @@ class PhotonDecoder:
     is applied by `counts()` after any reduction)."""
 
     def __init__(self, n_roaches, npix_per_roach, exptime, max_events=MAX_EVENTS_PER_SEC, hist_field='peak',
-                 n_bins=4096, bin_lut=None, ctx=None):
+                 n_bins=4096, bin_lut=None, ctx=None, counts_buf=None, hist_buf=None):
         self.ctx = ctx or _lib.default_context()
         self.n_roaches, self.npix_per_roach, self.exptime = int(n_roaches), int(npix_per_roach), int(exptime)
         self.max_events = int(max_events)
@@ -48,15 +48,20 @@ class PhotonDecoder:
         self.cfg = _lib.DecodeCfg(self.n_roaches, self.npix_per_roach, self.exptime, self.max_events,
                                   FIELD_SHIFT[hist_field], self.n_bins,
                                   self._lut_dev.ptr if self._lut_dev else None)
-        self.counts_dev = self.ctx.alloc(self.exptime * self.n_pix * 4).zero()
-        self.hist_dev = self.ctx.alloc(self.n_pix * self.n_bins * 4).zero() if hist_field else None
+        # counts_buf / hist_buf: caller-owned device buffers (e.g. torch tensors to all-reduce with NCCL)
+        self.counts_dev = counts_buf if counts_buf is not None else self.ctx.alloc(self.exptime * self.n_pix * 4).zero()
+        if hist_field:
+            self.hist_dev = hist_buf if hist_buf is not None else self.ctx.alloc(self.n_pix * self.n_bins * 4).zero()
+        else:
+            self.hist_dev = None
         self.stats = _lib.DecodeStats()
         self.sec = np.zeros(self.n_roaches, dtype=np.int32)     # seconds closed per roach stream
 
     def reset(self):
-        self.counts_dev.zero()
-        if self.hist_dev:
-            self.hist_dev.zero()
+        c = self.ctx
+        c._check(c.lib.mkid_memset(c.h, _lib.ptr(self.counts_dev), 0, self.exptime * self.n_pix * 4))
+        if self.hist_dev is not None:
+            c._check(c.lib.mkid_memset(c.h, _lib.ptr(self.hist_dev), 0, self.n_pix * self.n_bins * 4))
         self.stats = _lib.DecodeStats()
         self.sec[:] = 0
 
@@ -72,6 +77,22 @@ class PhotonDecoder:
                                          _lib.ptr(sec_out), roach.size, ctypes.byref(self.cfg),
                                          _lib.ptr(self.counts_dev), _lib.ptr(self.hist_dev),
                                          ctypes.addressof(self.stats) if want_stats else None))
+        return sec_out
+
+    def decode_words_seg(self, words, seg_start, seg_len, seg_roach, seg_sec=None, n_words=None, want_stats=True):
+        """Explicit (start, length) segments, e.g. the per-board regions Channelizer.process fills."""
+        start = np.ascontiguousarray(seg_start, dtype=np.int64)
+        ln = np.ascontiguousarray(seg_len, dtype=np.int64)
+        roach = np.ascontiguousarray(seg_roach, dtype=np.int32)
+        sec = np.ascontiguousarray(seg_sec if seg_sec is not None else np.zeros(roach.size), dtype=np.int32)
+        if n_words is None:
+            n_words = int((start + ln).max()) if start.size else 0
+        sec_out = np.zeros(roach.size, dtype=np.int32)
+        c = self.ctx
+        c._check(c.lib.mkid_decode_words_seg(c.h, _lib.ptr(words), n_words, _lib.ptr(start), _lib.ptr(ln), _lib.ptr(roach),
+                                             _lib.ptr(sec), _lib.ptr(sec_out), roach.size, ctypes.byref(self.cfg),
+                                             _lib.ptr(self.counts_dev), _lib.ptr(self.hist_dev),
+                                             ctypes.addressof(self.stats) if want_stats else None))
         return sec_out
 
     def decode_wire(self, wire, seg_offset, seg_roach, seg_sec=None, n_bundles=None, want_stats=True):
@@ -108,8 +129,15 @@ class PhotonDecoder:
         self.sec[:len(streams)] = out
 
     # ------------------------------------------------------------------ results
+    def _download(self, buf, count):
+        out = np.empty(count, dtype=np.uint32)
+        c = self.ctx
+        c._check(c.lib.mkid_memcpy(c.h, _lib.ptr(out), _lib.ptr(buf), out.nbytes))
+        c.sync()
+        return out
+
     def counts_raw(self):
-        return self.counts_dev.download(np.uint32).reshape(self.exptime, self.n_pix)
+        return self._download(self.counts_dev, self.exptime * self.n_pix).reshape(self.exptime, self.n_pix)
 
     def counts(self):
         """photon_counts[sec][pixel] with the cap quirk applied (PacketMaster.c:373-380)."""
@@ -119,7 +147,7 @@ class PhotonDecoder:
         return out.reshape(self.exptime, self.n_pix)
 
     def hist(self):
-        return self.hist_dev.download(np.uint32).reshape(self.n_pix, self.n_bins)
+        return self._download(self.hist_dev, self.n_pix * self.n_bins).reshape(self.n_pix, self.n_bins)
 
     def stats_dict(self):
         s = self.stats
@@ -131,7 +159,7 @@ class PhotonDecoder:
         `sec` gathered through the beammap `pixel_adr[rows][cols]` as uint16."""
         c = self.ctx
         capped = c.alloc(self.n_pix * 4)
-        c._check(c.lib.mkid_counts_cap(c.h, ctypes.c_void_p(self.counts_dev.ptr + sec * self.n_pix * 4),
+        c._check(c.lib.mkid_counts_cap(c.h, ctypes.c_void_p(_lib.ptr(self.counts_dev).value + sec * self.n_pix * 4),
                                        _lib.ptr(capped), self.n_pix, self.max_events))
         adr = np.ascontiguousarray(pixel_adr, dtype=np.int32)
         img = np.empty(adr.shape, dtype=np.uint16)

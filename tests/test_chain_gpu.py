@@ -1,0 +1,59 @@
+"""GPU: the full chain (K4 -> K5 -> K6) through the public ReadoutChain API."""
+import numpy as np
+import pytest
+
+from oracle import channelizer as oc
+from oracle import decode as odec
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    from mkids_sdr_b200 import _lib
+    return _lib.default_context(0)
+
+
+def test_chain_counts_and_hist_match_oracle(ctx):
+    from mkids_sdr_b200.chain import ReadoutChain
+    from mkids_sdr_b200.channelizer import synth_adc
+    B, n_lut, n = 2, 2 ** 16, 2 ** 20
+    chain, boards = ReadoutChain.synthetic(B, n_lut, 40, seed0=11, threshold=-2400, holdoff=100, ctx=ctx, exptime=3,
+                                           n_bins=16)
+    tb = np.stack([bd['tone_bins'] for bd in boards])
+    iq = synth_adc(B, n, tb, n_lut=n_lut, pulse_rate=4000., seed=21, ctx=ctx)
+    cap = chain.chan.words_capacity(n)
+    wh = np.zeros((B, cap), dtype=np.uint64)
+    streams = [[] for _ in range(B)]
+    for rep in range(2):                       # two consecutive batches: streaming state is carried
+        nw = chain.process(iq, words_host=wh)
+        for b in range(B):
+            streams[b].append(wh[b, :nw[b]].copy())
+    streams = [np.concatenate(s) for s in streams]
+    assert all(len(s) > 50 for s in streams)
+    ref = odec.packetmaster_bin(streams, 253, 3)
+    assert np.array_equal(chain.dec.counts_raw(), ref['raw_counts'])
+    lut = np.arange(4096) * 16 // 4096
+    assert np.array_equal(chain.dec.hist(), odec.pixel_field_hist(streams, 253, 3, 'peak', lut, 16))
+    # the words themselves: oracle detection on the GPU's own phase rows (both batches in one stream)
+    chain.chan.reset()
+    _, ph = chain.chan.process(np.concatenate([iq, iq], axis=1), detect=False, want_phase=True)
+    for b in range(B):
+        cfg = oc.ChanConfig(boards[b]['bins'], boards[b]['I_dds'], boards[b]['Q_dds'], chain.fir_int,
+                            thresholds=np.full(256, -2400), zero_ch=boards[b]['zero_ch'].astype(bool), M=20, L=100, W=32)
+        want = oc.detect_emit(ph[b], cfg, 0, np.zeros(256, np.int64), 2 * n // 512 - 64 - cfg.M)
+        assert np.array_equal(streams[b], np.array(want, dtype=np.uint64))
+
+
+def test_thresholds_from_noise_and_trigger_rate(ctx):
+    from mkids_sdr_b200.chain import ReadoutChain
+    from mkids_sdr_b200.channelizer import synth_adc
+    chain, boards = ReadoutChain.synthetic(1, 2 ** 16, 24, seed0=5, ctx=ctx, exptime=2, holdoff=1000)
+    thr = chain.derive_thresholds(boards, n=2 ** 24 // 2)
+    act = ~boards[0]['zero_ch'].astype(bool)
+    assert (thr[0][act] < -10).all() and (thr[0][act] > -25736).all()
+    n = 2 ** 23
+    iq = synth_adc(1, n, boards[0]['tone_bins'][None, :], n_lut=2 ** 16, pulse_rate=1000., seed=9, ctx=ctx)
+    nw = chain.process(iq)
+    # 16 ms of data, 24 channels, ~1000 pulses/s (depth 20-120 deg): tens to a few hundred words
+    assert 100 < nw[0] < 24 * 40, nw
