@@ -149,7 +149,7 @@ int mkid_quicklook_image(mkid_ctx *ctx, const uint32_t *counts_sec, const int32_
  *
  * One mkid_chan holds n_boards independent boards (feedlines) of 256 channels each and their
  * streaming state (input history, hold-off, time).  Streams are processed in calls of n samples
- * per board (n multiple of 512); results do not depend on how a stream is cut into calls.
+ * per board (n a multiple of 2048 and >= 59392); results do not depend on how a stream is cut into calls.
  */
 typedef struct mkid_chan mkid_chan;
 

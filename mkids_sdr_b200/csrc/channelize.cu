@@ -46,7 +46,7 @@ struct ChanDev {                         // device-resident configuration + stat
     float2 *tw256;        // [16][16] W256^(j*q) stored [q][j]
     float fir[FIRT];      // c_k / (2047*32767)
     int16_t *bins;        // [B][256]
-    uint32_t *dds;        // [B][Ld][256]  I | Q<<16
+    float2 *ddsf;         // [B][Ld][256]  (I, Q) as float, channel-minor
     float *gain;          // [B][256] 0 (zeroed FIR) or 1
     float *cen_i, *cen_q; // [B][256] 8*I_c, 8*Q_c
     int32_t *thr;         // [B][256]
@@ -114,7 +114,7 @@ struct K4Params {
     ChanDev d;
     const uint32_t *in;      // [B][n] packed samples of this call
     int64_t n;               // samples per board in this call
-    int64_t f0_abs;          // absolute frame index of local frame 0
+    int64_t f0_abs;          // absolute frame index of local frame 0 (always even)
     int16_t *phase;          // [B][rows][256]
     float *phase_f32;        // optional [B][n/512][256] unquantised phase (rad) of the new outputs (tests)
     int64_t rows;            // PRE_ROWS + n/512
@@ -122,17 +122,36 @@ struct K4Params {
     int chunks_per_board;
 };
 
-__global__ void __launch_bounds__(256, 2) channelize_kernel(K4Params p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *s_fft = reinterpret_cast<float2 *>(smem_raw);                 // [16][FFT_STRIDE]
-    float2 *s_ring = s_fft + 16 * FFT_STRIDE;                             // [RING][256]
-    float2 *s_tw = s_ring + RING * NCH;                                   // [16][16]
+// atan2 for the phase stage: branch-free, |error| < 4e-7 rad (minimax degree-8 polynomial in t^2 on
+// [0,1], fast division), exact signed-zero / axis behaviour of atan2f where the model needs it.
+__device__ __forceinline__ float atan2_fast(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    float t = __fdividef(mn, mx);
+    t = mx == 0.f ? 0.f : t;
+    const float s = t * t;
+    float p = 2.4566796610e-03f;
+    p = fmaf(p, s, -1.4401168771e-02f);
+    p = fmaf(p, s, 3.9780896098e-02f);
+    p = fmaf(p, s, -7.2348273357e-02f);
+    p = fmaf(p, s, 1.0498930424e-01f);
+    p = fmaf(p, s, -1.4161224578e-01f);
+    p = fmaf(p, s, 1.9985906047e-01f);
+    p = fmaf(p, s, -3.3332596978e-01f);
+    p = fmaf(p, s, 9.9999988637e-01f);
+    p = p * t;
+    p = ay > ax ? 1.5707963267948966f - p : p;
+    p = x < 0.f ? 3.14159265358979f - p : p;
+    return copysignf(p, y);
+}
 
+// One chunk of output rows of one board.  EDGE = the chunk touches the start of the call (input
+// history) or the start of the stream (frames before time 0 contribute nothing).
+template <bool EDGE>
+__device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_fft, float4 *s_ring, const float2 *s_tw,
+                                                 int board, int64_t tl0, int64_t tl1) {
     const int tid = threadIdx.x;
-    const int board = blockIdx.y;
-    const int chunk = blockIdx.x;
     const ChanDev &d = p.d;
-
     // ---- per-thread constants
     float hA[PTAPS], hB[PTAPS];
 #pragma unroll
@@ -141,25 +160,25 @@ __global__ void __launch_bounds__(256, 2) channelize_kernel(K4Params p) {
         hB[q] = d.window[NFFT * q + HOP + tid];
     }
     const float2 w512 = d.tw512[tid];
-    s_tw[tid] = d.tw256[tid];
     const int bin = d.bins[board * NCH + tid];
-    const float gain = d.gain[board * NCH + tid];
+    const int par = bin & 1;
+    const float2 *zsrc = s_fft + par * FFT_STRIDE + (bin >> 1);      // + 2*i*FFT_STRIDE per frame
+    const bool live = d.gain[board * NCH + tid] != 0.f;
     const float cen_i = d.cen_i[board * NCH + tid], cen_q = d.cen_q[board * NCH + tid];
-    const uint32_t *dds = d.dds + (size_t)board * d.Ld * NCH;
+    const float2 *dds = d.ddsf + (size_t)board * d.Ld * NCH + tid;
     const uint32_t *in = p.in + (size_t)board * p.n;
     const uint32_t *hist = d.hist + (size_t)board * d.H;
-    int16_t *phase = p.phase + (size_t)board * p.rows * NCH;
+    int16_t *phase = p.phase + (size_t)board * p.rows * NCH + tid;
 
-    // output rows [row0,row1) of the phase buffer; row r is local output t = r - PRE_ROWS
-    const int64_t row0 = (int64_t)chunk * p.rows_per_chunk;
-    const int64_t row1 = min(row0 + (int64_t)p.rows_per_chunk, p.rows);
-    if (row0 >= row1) return;
-    const int64_t tl0 = row0 - PRE_ROWS, tl1 = row1 - PRE_ROWS;
     // first frame block: the FIR of output tl0 needs frames 2*tl0 - 24 .. 2*tl0 + 1
-    const int64_t fb_first = ((2 * tl0 - 24) >> 3) << 3;       // floor to a multiple of 8 (arithmetic shift)
-    const int64_t fb_last = 2 * tl1;                           // exclusive
+    const int64_t fb_first = ((2 * tl0 - 24) >> 3) << 3;       // floor to a multiple of 8
+    const int n_blocks = (int)((2 * tl1 - fb_first + FB - 1) / FB);
+    const int ld_mask = d.Ld - 1;                               // Ld is a power of two
+    int dds_row = (int)((p.f0_abs + fb_first) & ld_mask);       // f_abs mod Ld of the block's first frame
+    int ring_base = (int)(fb_first & (RING - 1));               // 0, 8, 16 or 24
+    const uint32_t *src = in + HOP * fb_first + tid;            // sample of frame fb_first handled by this thread
 
-    auto load_sample = [&](int64_t nidx) -> uint32_t {
+    auto load_sample = [&](int64_t nidx) -> uint32_t {          // EDGE only
         if (nidx >= 0) return in[nidx];
         const int64_t h = (int64_t)d.H + nidx;
         return h >= 0 ? hist[h] : 0u;
@@ -171,16 +190,19 @@ __global__ void __launch_bounds__(256, 2) channelize_kernel(K4Params p) {
     // ---- PFB warm-up: s[j] = x[256*(f+1) - 2048 + k + 256*j], j = 0..6 for f = fb_first
     float2 sw[8];
 #pragma unroll
-    for (int j = 0; j < 7; ++j) sw[j] = unpack(load_sample(HOP * (fb_first + 1) - WIN + tid + HOP * j));
+    for (int j = 0; j < 7; ++j) {
+        if (EDGE) sw[j] = unpack(load_sample(HOP * (fb_first + 1) - WIN + tid + HOP * j));
+        else sw[j] = unpack(src[HOP * (j - 7)]);
+    }
     sw[7] = make_float2(0.f, 0.f);
-    // zero the ring (frames before the first computed one are never read with non-zero weight, but keep it clean)
-    for (int i = tid; i < RING * NCH; i += 256) s_ring[i] = make_float2(0.f, 0.f);
     uint32_t pre[FB];
 #pragma unroll
-    for (int i = 0; i < FB; ++i) pre[i] = load_sample(HOP * (fb_first + i) + tid);
-    __syncthreads();
+    for (int i = 0; i < FB; ++i) {
+        if (EDGE) pre[i] = load_sample(HOP * (fb_first + i) + tid);
+        else pre[i] = src[HOP * i];
+    }
 
-    for (int64_t fb = fb_first; fb < fb_last; fb += FB) {
+    for (int blk = 0; blk < n_blocks; ++blk) {
         // ================= PFB + first radix-2 stage for 8 frames =================
 #pragma unroll
         for (int i = 0; i < FB; ++i) {
@@ -195,11 +217,18 @@ __global__ void __launch_bounds__(256, 2) channelize_kernel(K4Params p) {
             s_fft[(2 * i) * FFT_STRIDE + tid] = cadd(u0, u1);                      // even bins
             s_fft[(2 * i + 1) * FFT_STRIDE + tid] = cmul(csub(u0, u1), w512);      // odd bins
         }
-        // prefetch the next block's samples while the FFT runs
-        if (fb + FB < fb_last) {
+        // prefetch: next block's ADC samples and this block's DDS values (consumed after the FFT)
+        src += HOP * FB;
+        if (blk + 1 < n_blocks) {
 #pragma unroll
-            for (int i = 0; i < FB; ++i) pre[i] = load_sample(HOP * (fb + FB + i) + tid);
+            for (int i = 0; i < FB; ++i) {
+                if (EDGE) pre[i] = load_sample(HOP * (fb_first + (int64_t)(blk + 1) * FB + i) + tid);
+                else pre[i] = src[HOP * i];
+            }
         }
+        float2 dv[FB];
+#pragma unroll
+        for (int i = 0; i < FB; ++i) dv[i] = dds[(size_t)((dds_row + i) & ld_mask) * NCH];
         __syncthreads();
         // ================= 16 x FFT-256: two radix-16 passes =================
         {
@@ -221,7 +250,6 @@ __global__ void __launch_bounds__(256, 2) channelize_kernel(K4Params p) {
                     reg[q * 17 + j] = x;
                 }
             __syncwarp();
-            // pass 2: thread q = j reads B_i[q] over i
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = reg[j * 17 + i];
             fft16(v);
@@ -235,51 +263,86 @@ __global__ void __launch_bounds__(256, 2) channelize_kernel(K4Params p) {
         __syncthreads();
         // ================= channel stage: thread = channel =================
         {
-            const int par = bin & 1, m = bin >> 1;
+            // gather the bin, remove the half-frame hop phase of odd bins ((-1)^(bin*(f_abs+1)); f_abs of
+            // frame i has the parity of i because block starts and call starts are even), mix with conj(dds)
 #pragma unroll
-            for (int i = 0; i < FB; ++i) {
-                const int64_t f_abs = p.f0_abs + fb + i;
-                float2 z = s_fft[(2 * i + par) * FFT_STRIDE + m];
-                if (par && ((f_abs + 1) & 1)) { z.x = -z.x; z.y = -z.y; }
-                float2 y = make_float2(0.f, 0.f);
-                if (f_abs >= 0) {
-                    const uint32_t dv = dds[(size_t)(f_abs % d.Ld) * NCH + tid];
-                    const float dr = (float)(int16_t)(dv & 0xFFFF), di = (float)(int16_t)(dv >> 16);
-                    y.x = z.x * dr + z.y * di;          // z * conj(d)
-                    y.y = z.y * dr - z.x * di;
+            for (int i = 0; i < FB; i += 2) {
+                float2 z0 = zsrc[(2 * i) * FFT_STRIDE], z1 = zsrc[(2 * i + 2) * FFT_STRIDE];
+                if (par) { z0.x = -z0.x; z0.y = -z0.y; }                       // even i: f_abs + 1 odd
+                float4 y;
+                y.x = z0.x * dv[i].x + z0.y * dv[i].y;
+                y.y = z0.y * dv[i].x - z0.x * dv[i].y;
+                y.z = z1.x * dv[i + 1].x + z1.y * dv[i + 1].y;
+                y.w = z1.y * dv[i + 1].x - z1.x * dv[i + 1].y;
+                if (EDGE) {
+                    const int64_t f_abs = p.f0_abs + fb_first + (int64_t)blk * FB + i;
+                    if (f_abs < 0) { y.x = 0.f; y.y = 0.f; }
+                    if (f_abs + 1 < 0) { y.z = 0.f; y.w = 0.f; }
                 }
-                s_ring[((fb + i) & (RING - 1)) * NCH + tid] = y;
+                s_ring[(((ring_base + i) & (RING - 1)) >> 1) * NCH + tid] = y;
             }
-            // every thread has gathered its bins: the next block's PFB may overwrite s_fft.  From
-            // here on a thread touches only its own ring column.
-            __syncthreads();
+        }
+        // every thread has gathered its bins: the next block's PFB may overwrite s_fft.  From here on a
+        // thread touches only its own ring column.
+        __syncthreads();
+        {
             // FIR for the 4 outputs t = fb/2 + jj: frames fb + 2*jj - 24 + k, k = 0..25
-            const int64_t t_first = fb >> 1;
+            const int64_t t_first = (fb_first + (int64_t)blk * FB) >> 1;
             if (t_first + 3 >= tl0 && t_first < tl1) {
-                float2 yw[32];
+                float4 yw[16];                                                  // frames fb-24 .. fb+7
 #pragma unroll
-                for (int i = 0; i < 32; ++i) yw[i] = s_ring[((fb - 24 + i) & (RING - 1)) * NCH + tid];
+                for (int i = 0; i < 16; ++i) yw[i] = s_ring[(((ring_base + 8 + 2 * i) & (RING - 1)) >> 1) * NCH + tid];
+                float ar[4] = {0.f, 0.f, 0.f, 0.f}, ai[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int k = 0; k < FIRT; ++k) {
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) {
+                        const int f = 2 * jj + k;                               // frame index in the window
+                        const float yr = (f & 1) ? yw[f >> 1].z : yw[f >> 1].x;
+                        const float yi = (f & 1) ? yw[f >> 1].w : yw[f >> 1].y;
+                        ar[jj] = fmaf(d.fir[k], yr, ar[jj]);
+                        ai[jj] = fmaf(d.fir[k], yi, ai[jj]);
+                    }
+                }
 #pragma unroll
                 for (int jj = 0; jj < 4; ++jj) {
-                    float ar = 0.f, ai = 0.f;
-#pragma unroll
-                    for (int k = 0; k < FIRT; ++k) {
-                        ar = fmaf(d.fir[k], yw[2 * jj + k].x, ar);
-                        ai = fmaf(d.fir[k], yw[2 * jj + k].y, ai);
-                    }
                     const int64_t t = t_first + jj;
                     if (t >= tl0 && t < tl1) {
                         // zeroed FIR (deleted / inactive channel): w = +0 exactly, as in the model
-                        const float a = (gain != 0.f ? ar : 0.f) - cen_i, b = (gain != 0.f ? ai : 0.f) - cen_q;
-                        const float ph = atan2f(b, a);
-                        phase[(t + PRE_ROWS) * NCH + tid] = (int16_t)__float2int_rn(ph * 8192.0f);
+                        const float a = (live ? ar[jj] : 0.f) - cen_i, b = (live ? ai[jj] : 0.f) - cen_q;
+                        const float ph = atan2_fast(b, a);
+                        phase[(t + PRE_ROWS) * NCH] = (int16_t)__float2int_rn(ph * 8192.0f);
                         if (p.phase_f32 && t >= 0)
                             p.phase_f32[((size_t)board * (p.rows - PRE_ROWS) + t) * NCH + tid] = ph;
                     }
                 }
             }
         }
+        dds_row = (dds_row + FB) & ld_mask;
+        ring_base = (ring_base + FB) & (RING - 1);
     }
+}
+
+__global__ void __launch_bounds__(256, 2) channelize_kernel(K4Params p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float4 *s_ring = reinterpret_cast<float4 *>(smem_raw);                        // [RING/2][256] frame pairs
+    float2 *s_fft = reinterpret_cast<float2 *>(s_ring + (RING / 2) * NCH);        // [16][FFT_STRIDE]
+    float2 *s_tw = s_fft + 16 * FFT_STRIDE;                                       // [16][16]
+    const int tid = threadIdx.x;
+    const int board = blockIdx.y;
+    // output rows [row0,row1) of the phase buffer; row r is local output t = r - PRE_ROWS
+    const int64_t row0 = (int64_t)blockIdx.x * p.rows_per_chunk;
+    const int64_t row1 = min(row0 + (int64_t)p.rows_per_chunk, p.rows);
+    if (row0 >= row1) return;
+    s_tw[tid] = p.d.tw256[tid];
+    for (int i = tid; i < (RING / 2) * NCH; i += 256) s_ring[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    const int64_t tl0 = row0 - PRE_ROWS, tl1 = row1 - PRE_ROWS;
+    const int64_t fb_first = ((2 * tl0 - 24) >> 3) << 3;
+    // earliest sample read: 256*(fb_first+1) - 2048; earliest absolute frame: f0_abs + fb_first
+    const bool edge = (HOP * (fb_first + 1) - WIN < 0) || (p.f0_abs + fb_first < 0);
+    if (edge) channelize_chunk<true>(p, s_fft, s_ring, s_tw, board, tl0, tl1);
+    else channelize_chunk<false>(p, s_fft, s_ring, s_tw, board, tl0, tl1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -479,14 +542,14 @@ __global__ void update_history_kernel(uint32_t *hist, int H, const uint32_t *in,
         h[i] = x[n - H + i];
 }
 
-__global__ void pack_dds_kernel(const int16_t *I, const int16_t *Q, int n_lut, uint32_t *out) {
+__global__ void pack_dds_kernel(const int16_t *I, const int16_t *Q, int n_lut, float2 *out) {
     // out[t][m] = lut[(t/2)*512 + 2*((m+154)%256) + (t&1)]   (define_DDS_LUT layout, ROACH_Setup.py:526-530)
     const int Ld = n_lut / 256;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= Ld * NCH) return;
     const int t = idx / NCH, m = idx % NCH;
     const int src = (t >> 1) * 512 + 2 * ((m + 154) & 255) + (t & 1);
-    out[idx] = (uint32_t)(uint16_t)I[src] | ((uint32_t)(uint16_t)Q[src] << 16);
+    out[idx] = make_float2((float)I[src], (float)Q[src]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -637,7 +700,7 @@ extern "C" int mkid_chan_create(mkid_ctx *ctx, const mkid_chan_params *prm, mkid
     bad |= A((void **)&d.tw512, 256 * 8);
     bad |= A((void **)&d.tw256, 256 * 8);
     bad |= A((void **)&d.bins, (size_t)B * NCH * 2);
-    bad |= A((void **)&d.dds, (size_t)B * d.Ld * NCH * 4);
+    bad |= A((void **)&d.ddsf, (size_t)B * d.Ld * NCH * 8);
     bad |= A((void **)&d.gain, (size_t)B * NCH * 4);
     bad |= A((void **)&d.cen_i, (size_t)B * NCH * 4);
     bad |= A((void **)&d.cen_q, (size_t)B * NCH * 4);
@@ -678,7 +741,7 @@ extern "C" void mkid_chan_destroy(mkid_ctx *ctx, mkid_chan *ch) {
     if (!ch) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     ChanDev &d = ch->d;
-    void *ps[] = {d.window, d.tw512, d.tw256, d.bins, d.dds, d.gain, d.cen_i, d.cen_q, d.thr, d.hist, d.t_next,
+    void *ps[] = {d.window, d.tw512, d.tw256, d.bins, d.ddsf, d.gain, d.cen_i, d.cen_q, d.thr, d.hist, d.t_next,
                   ch->n_words_dev, ch->phase_buf, ch->mask, ch->acc, ch->win_cnt, ch->words_dev, ch->in_dev};
     for (void *p : ps) if (p) cudaFree(p);
     if (ch->ev_k4[0]) { cudaEventDestroy(ch->ev_k4[0]); cudaEventDestroy(ch->ev_k4[1]); }
@@ -744,7 +807,7 @@ extern "C" int mkid_chan_set_board(mkid_ctx *ctx, mkid_chan *ch, int32_t board, 
     MKID_CUDA(ctx, cudaMemcpyAsync(tmp + d.n_lut, Q_dds, (size_t)d.n_lut * 2, cudaMemcpyDefault, ctx->stream));
     const int total = d.Ld * NCH;
     pack_dds_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(tmp, tmp + d.n_lut, d.n_lut,
-                                                                 d.dds + (size_t)board * d.Ld * NCH);
+                                                                 d.ddsf + (size_t)board * d.Ld * NCH);
     MKID_CHECK_LAUNCH(ctx);
     MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ch->board_set[board] = true;
@@ -774,7 +837,7 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     if (!ctx) return MKID_EINVAL;
     MKID_REQUIRE(ctx, ch && iq, "chan_process: NULL argument");
     ChanDev &d = ch->d;
-    MKID_REQUIRE(ctx, n > 0 && n % 512 == 0, "n must be a positive multiple of 512");
+    MKID_REQUIRE(ctx, n > 0 && n % 2048 == 0, "n must be a positive multiple of 2048 samples (4 output rows)");
     MKID_REQUIRE(ctx, n >= d.H, "n must be at least the history length (59392 samples) per call");
     MKID_REQUIRE(ctx, ch->fir_set, "FIR taps not set (mkid_chan_set_fir)");
     for (int b = 0; b < d.n_boards; ++b) MKID_REQUIRE(ctx, ch->board_set[b], "a board is not configured (mkid_chan_set_board)");
@@ -811,7 +874,7 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
         p.rows_per_chunk = (int)rpc;
         p.chunks_per_board = (int)((rows + rpc - 1) / rpc);
     }
-    const size_t smem = (size_t)(16 * FFT_STRIDE + RING * NCH + 256) * sizeof(float2);
+    const size_t smem = (size_t)(16 * FFT_STRIDE + RING * NCH + 256) * sizeof(float2);   // ring + fft + twiddles
     MKID_CUDA(ctx, cudaFuncSetAttribute(channelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (!ch->ev_k4[0]) { cudaEventCreate(&ch->ev_k4[0]); cudaEventCreate(&ch->ev_k4[1]); }
     MKID_CUDA(ctx, cudaEventRecord(ch->ev_k4[0], ctx->stream));
