@@ -156,7 +156,7 @@ typedef struct mkid_chan mkid_chan;
 typedef struct {
     int32_t n_boards;      /* boards (ROACH streams) processed together                         */
     int32_t n_lut;         /* DDS/DAC LUT length N = sampleRate/freqRes (ROACH_Setup.py:83-84)  */
-    int32_t mean_len;      /* M: baseline = mean of the previous M phase samples (meanlength)   */
+    int32_t mean_len;      /* M: baseline = mean of the previous M phase samples (meanlength), 4..32 */
     int32_t holdoff;       /* L: dead time after a trigger in us (pulselength), >= 32           */
     int32_t peak_win;      /* W: peak search window in us, <= 60                                */
     int32_t reserved;

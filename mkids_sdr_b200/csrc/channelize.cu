@@ -19,6 +19,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -66,6 +67,7 @@ struct mkid_chan {
     uint32_t *acc = nullptr; size_t acc_bytes = 0;
     uint32_t *win_cnt = nullptr; size_t win_bytes = 0;    // [B][n_win] counts then offsets
     int32_t *n_words_dev = nullptr;
+    int16_t *halo = nullptr; size_t halo_bytes = 0;
     uint64_t *words_dev = nullptr; size_t words_bytes = 0;
     uint32_t *in_dev = nullptr; size_t in_bytes = 0;
     bool board_set[64] = {};
@@ -118,8 +120,10 @@ struct K4Params {
     int16_t *phase;          // [B][rows][256]
     float *phase_f32;        // optional [B][n/512][256] unquantised phase (rad) of the new outputs (tests)
     int64_t rows;            // PRE_ROWS + n/512
-    int rows_per_chunk;      // multiple of 4
+    int rows_per_chunk;      // multiple of 32
     int chunks_per_board;
+    uint32_t *mask;          // [B][ceil(rows/32)][256] candidate bits (fused K5c), or nullptr
+    int16_t *halo;           // [B][chunks][32][256] phase rows recomputed in front of a chunk (baseline history)
 };
 
 // atan2 for the phase stage: branch-free, |error| < 4e-7 rad (minimax degree-8 polynomial in t^2 on
@@ -147,10 +151,15 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
 
 // One chunk of output rows of one board.  EDGE = the chunk touches the start of the call (input
 // history) or the start of the stream (frames before time 0 contribute nothing).
-template <bool EDGE>
+template <bool EDGE, bool F32>
 __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_fft, float4 *s_ring, const float2 *s_tw,
-                                                 int board, int64_t tl0, int64_t tl1) {
+                                                 int board, int64_t row0, int64_t row1) {
     const int tid = threadIdx.x;
+    // rows [row0,row1) are stored; rows from r_start on are computed (the M rows in front of the chunk
+    // feed the rolling baseline of the trigger); row r is local output t = r - PRE_ROWS
+    const int M = p.d.M;
+    const int64_t r_start = p.mask ? (row0 - M > 0 ? row0 - M : 0) : row0;
+    const int64_t tl0 = r_start - PRE_ROWS, tl1 = row1 - PRE_ROWS;
     const ChanDev &d = p.d;
     // ---- per-thread constants
     float hA[PTAPS], hB[PTAPS];
@@ -169,6 +178,13 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
     const uint32_t *in = p.in + (size_t)board * p.n;
     const uint32_t *hist = d.hist + (size_t)board * d.H;
     int16_t *phase = p.phase + (size_t)board * p.rows * NCH + tid;
+    // fused candidate mask (K5c): bit (r & 31) of mask[r >> 5][c] iff M*raw[r] - sum_{k=1..M} raw[r-k] < M*thr
+    const int thM = M * d.thr[board * NCH + tid];
+    const int64_t r_eval0 = row0 > RES_LO ? row0 : RES_LO;
+    int16_t *halo = p.halo ? p.halo + (((size_t)board * p.chunks_per_board + blockIdx.x) * 32) * NCH + tid : nullptr;
+    uint32_t *mk = p.mask ? p.mask + (size_t)board * ((p.rows + 31) >> 5) * NCH + tid : nullptr;
+    int S = 0;
+    uint32_t bits = 0;
 
     // first frame block: the FIR of output tl0 needs frames 2*tl0 - 24 .. 2*tl0 + 1
     const int64_t fb_first = ((2 * tl0 - 24) >> 3) << 3;       // floor to a multiple of 8
@@ -201,6 +217,109 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
         if (EDGE) pre[i] = load_sample(HOP * (fb_first + i) + tid);
         else pre[i] = src[HOP * i];
     }
+
+    // ---- channel-stage state in chunk-relative rows (32-bit): row r = row0 + rl
+    const int n_rows = (int)(row1 - row0);
+    const int rl_start = (int)(r_start - row0);                       // <= 0: first computed row
+    const int rl_eval0 = (int)(r_eval0 - row0);                       // first row whose trigger condition is evaluated
+    int16_t *phase_c = phase + row0 * NCH;                            // this thread's column at the chunk's first row
+    uint32_t *mk_c = mk ? mk + (row0 >> 5) * NCH : nullptr;           // row0 is a multiple of 32
+    float *f32_c = p.phase_f32 ? p.phase_f32 + ((size_t)board * (p.rows - PRE_ROWS) + (row0 - PRE_ROWS)) * NCH + tid : nullptr;
+    int rl = (int)((fb_first >> 1) + PRE_ROWS - row0);                // relative row of the block's first output
+    const int rl_fast = rl_eval0 > M ? rl_eval0 : M;                  // from here on no boundary cases
+
+    auto channel_stage = [&](auto RBc, const float2 (&dv)[FB], int blk) {
+        constexpr int RB = decltype(RBc)::value;
+        // gather the bin, remove the half-frame hop phase of odd bins ((-1)^(bin*(f_abs+1)); f_abs of
+        // frame i has the parity of i because block starts and call starts are even), mix with conj(dds)
+#pragma unroll
+        for (int i = 0; i < FB; i += 2) {
+            float2 z0 = zsrc[(2 * i) * FFT_STRIDE], z1 = zsrc[(2 * i + 2) * FFT_STRIDE];
+            if (par) { z0.x = -z0.x; z0.y = -z0.y; }                       // even i: f_abs + 1 odd
+            float4 y;
+            y.x = z0.x * dv[i].x + z0.y * dv[i].y;
+            y.y = z0.y * dv[i].x - z0.x * dv[i].y;
+            y.z = z1.x * dv[i + 1].x + z1.y * dv[i + 1].y;
+            y.w = z1.y * dv[i + 1].x - z1.x * dv[i + 1].y;
+            if (EDGE) {
+                const int64_t f_abs = p.f0_abs + fb_first + (int64_t)blk * FB + i;
+                if (f_abs < 0) { y.x = 0.f; y.y = 0.f; }
+                if (f_abs + 1 < 0) { y.z = 0.f; y.w = 0.f; }
+            }
+            s_ring[(((RB + i) & (RING - 1)) >> 1) * NCH + tid] = y;
+        }
+        // every thread has gathered its bins: the next block's PFB may overwrite s_fft.  From here on a
+        // thread touches only its own ring column.
+        __syncthreads();
+        if (rl + 3 < rl_start || rl >= n_rows) return;
+        const bool fast = rl >= rl_fast && rl + 3 < n_rows;
+        // rows leaving the rolling baseline while these 4 outputs enter it (M >= 4, so they were stored by
+        // an earlier block): loaded now, used after the FIR arithmetic
+        int old[4] = {0, 0, 0, 0};
+        if (mk) {
+            if (fast) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) old[jj] = phase_c[(rl + jj - M) * NCH];
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int ro = rl + jj - M;
+                    if (ro >= rl_start && rl + jj >= rl_start) old[jj] = ro >= 0 ? phase_c[ro * NCH] : halo[(32 + ro) * NCH];
+                }
+            }
+        }
+        // FIR for the 4 outputs t = fb/2 + jj: frames fb + 2*jj - 24 + k, k = 0..25
+        float4 yw[16];                                                  // frames fb-24 .. fb+7
+#pragma unroll
+        for (int i = 0; i < 16; ++i) yw[i] = s_ring[(((RB + 8 + 2 * i) & (RING - 1)) >> 1) * NCH + tid];
+        float ar[4] = {0.f, 0.f, 0.f, 0.f}, ai[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < FIRT; ++k) {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int f = 2 * jj + k;                               // frame index in the window
+                const float yr = (f & 1) ? yw[f >> 1].z : yw[f >> 1].x;
+                const float yi = (f & 1) ? yw[f >> 1].w : yw[f >> 1].y;
+                ar[jj] = fmaf(d.fir[k], yr, ar[jj]);
+                ai[jj] = fmaf(d.fir[k], yi, ai[jj]);
+            }
+        }
+        int raw[4];
+        float ph[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            // zeroed FIR (deleted / inactive channel): w = +0 exactly, as in the model
+            const float a = (live ? ar[jj] : 0.f) - cen_i, b = (live ? ai[jj] : 0.f) - cen_q;
+            ph[jj] = atan2_fast(b, a);
+            raw[jj] = __float2int_rn(ph[jj] * 8192.0f);
+        }
+        if (fast) {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                phase_c[(rl + jj) * NCH] = (int16_t)raw[jj];
+                if (F32) { if (f32_c && rl + jj + (int)(row0 - PRE_ROWS) >= 0) f32_c[(size_t)(rl + jj) * NCH] = ph[jj]; }
+                if (mk) {
+                    if ((M * raw[jj] - S) < thM) bits |= 1u << ((rl + jj) & 31);
+                    S += raw[jj] - old[jj];
+                }
+            }
+            if (mk && (rl & 31) == 28) { mk_c[(rl >> 5) * NCH] = bits; bits = 0; }
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int r = rl + jj;
+                if (r < rl_start || r >= n_rows) continue;
+                if (r >= 0) phase_c[r * NCH] = (int16_t)raw[jj];
+                else halo[(32 + r) * NCH] = (int16_t)raw[jj];
+                if (F32) { if (f32_c && r >= 0 && r + (int)(row0 - PRE_ROWS) >= 0) f32_c[(size_t)r * NCH] = ph[jj]; }
+                if (mk) {
+                    if (r >= rl_eval0 && (M * raw[jj] - S) < thM) bits |= 1u << (r & 31);
+                    S += raw[jj] - old[jj];
+                    if (r >= 0 && ((r & 31) == 31 || r == n_rows - 1)) { mk_c[(r >> 5) * NCH] = bits; bits = 0; }
+                }
+            }
+        }
+    };
 
     for (int blk = 0; blk < n_blocks; ++blk) {
         // ================= PFB + first radix-2 stage for 8 frames =================
@@ -262,62 +381,14 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
         }
         __syncthreads();
         // ================= channel stage: thread = channel =================
-        {
-            // gather the bin, remove the half-frame hop phase of odd bins ((-1)^(bin*(f_abs+1)); f_abs of
-            // frame i has the parity of i because block starts and call starts are even), mix with conj(dds)
-#pragma unroll
-            for (int i = 0; i < FB; i += 2) {
-                float2 z0 = zsrc[(2 * i) * FFT_STRIDE], z1 = zsrc[(2 * i + 2) * FFT_STRIDE];
-                if (par) { z0.x = -z0.x; z0.y = -z0.y; }                       // even i: f_abs + 1 odd
-                float4 y;
-                y.x = z0.x * dv[i].x + z0.y * dv[i].y;
-                y.y = z0.y * dv[i].x - z0.x * dv[i].y;
-                y.z = z1.x * dv[i + 1].x + z1.y * dv[i + 1].y;
-                y.w = z1.y * dv[i + 1].x - z1.x * dv[i + 1].y;
-                if (EDGE) {
-                    const int64_t f_abs = p.f0_abs + fb_first + (int64_t)blk * FB + i;
-                    if (f_abs < 0) { y.x = 0.f; y.y = 0.f; }
-                    if (f_abs + 1 < 0) { y.z = 0.f; y.w = 0.f; }
-                }
-                s_ring[(((ring_base + i) & (RING - 1)) >> 1) * NCH + tid] = y;
-            }
+        // The ring position of a block takes only 4 values; one statically addressed copy per value.
+        switch (ring_base) {
+        case 0: channel_stage(std::integral_constant<int, 0>{}, dv, blk); break;
+        case 8: channel_stage(std::integral_constant<int, 8>{}, dv, blk); break;
+        case 16: channel_stage(std::integral_constant<int, 16>{}, dv, blk); break;
+        default: channel_stage(std::integral_constant<int, 24>{}, dv, blk); break;
         }
-        // every thread has gathered its bins: the next block's PFB may overwrite s_fft.  From here on a
-        // thread touches only its own ring column.
-        __syncthreads();
-        {
-            // FIR for the 4 outputs t = fb/2 + jj: frames fb + 2*jj - 24 + k, k = 0..25
-            const int64_t t_first = (fb_first + (int64_t)blk * FB) >> 1;
-            if (t_first + 3 >= tl0 && t_first < tl1) {
-                float4 yw[16];                                                  // frames fb-24 .. fb+7
-#pragma unroll
-                for (int i = 0; i < 16; ++i) yw[i] = s_ring[(((ring_base + 8 + 2 * i) & (RING - 1)) >> 1) * NCH + tid];
-                float ar[4] = {0.f, 0.f, 0.f, 0.f}, ai[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int k = 0; k < FIRT; ++k) {
-#pragma unroll
-                    for (int jj = 0; jj < 4; ++jj) {
-                        const int f = 2 * jj + k;                               // frame index in the window
-                        const float yr = (f & 1) ? yw[f >> 1].z : yw[f >> 1].x;
-                        const float yi = (f & 1) ? yw[f >> 1].w : yw[f >> 1].y;
-                        ar[jj] = fmaf(d.fir[k], yr, ar[jj]);
-                        ai[jj] = fmaf(d.fir[k], yi, ai[jj]);
-                    }
-                }
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const int64_t t = t_first + jj;
-                    if (t >= tl0 && t < tl1) {
-                        // zeroed FIR (deleted / inactive channel): w = +0 exactly, as in the model
-                        const float a = (live ? ar[jj] : 0.f) - cen_i, b = (live ? ai[jj] : 0.f) - cen_q;
-                        const float ph = atan2_fast(b, a);
-                        phase[(t + PRE_ROWS) * NCH] = (int16_t)__float2int_rn(ph * 8192.0f);
-                        if (p.phase_f32 && t >= 0)
-                            p.phase_f32[((size_t)board * (p.rows - PRE_ROWS) + t) * NCH + tid] = ph;
-                    }
-                }
-            }
-        }
+        rl += 4;
         dds_row = (dds_row + FB) & ld_mask;
         ring_base = (ring_base + FB) & (RING - 1);
     }
@@ -337,12 +408,13 @@ __global__ void __launch_bounds__(256, 2) channelize_kernel(K4Params p) {
     s_tw[tid] = p.d.tw256[tid];
     for (int i = tid; i < (RING / 2) * NCH; i += 256) s_ring[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    const int64_t tl0 = row0 - PRE_ROWS, tl1 = row1 - PRE_ROWS;
-    const int64_t fb_first = ((2 * tl0 - 24) >> 3) << 3;
+    const int64_t r_start = p.mask ? (row0 - p.d.M > 0 ? row0 - p.d.M : 0) : row0;
+    const int64_t fb_first = ((2 * (r_start - PRE_ROWS) - 24) >> 3) << 3;
     // earliest sample read: 256*(fb_first+1) - 2048; earliest absolute frame: f0_abs + fb_first
     const bool edge = (HOP * (fb_first + 1) - WIN < 0) || (p.f0_abs + fb_first < 0);
-    if (edge) channelize_chunk<true>(p, s_fft, s_ring, s_tw, board, tl0, tl1);
-    else channelize_chunk<false>(p, s_fft, s_ring, s_tw, board, tl0, tl1);
+    if (p.phase_f32) channelize_chunk<true, true>(p, s_fft, s_ring, s_tw, board, row0, row1);     // test hook: slow path
+    else if (edge) channelize_chunk<true, false>(p, s_fft, s_ring, s_tw, board, row0, row1);
+    else channelize_chunk<false, false>(p, s_fft, s_ring, s_tw, board, row0, row1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -637,7 +709,7 @@ int ensure(mkid_ctx *ctx, void **p, size_t *cap, size_t bytes) {
 
 // K5 driver shared by mkid_chan_process and mkid_chan_detect
 int run_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase_dev, int64_t rows, int64_t r_lo, int64_t r_hi,
-               int64_t t_abs0, uint64_t *words_dev, int64_t words_cap) {
+               int64_t t_abs0, uint64_t *words_dev, int64_t words_cap, bool have_mask) {
     const ChanDev &d = ch->d;
     const int B = d.n_boards;
     const int64_t n_groups = (rows + 31) >> 5;
@@ -655,9 +727,11 @@ int run_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase_dev, int64_t r
     ch->win_bytes = cap;
     MKID_CUDA(ctx, cudaMemsetAsync(ch->acc, 0, (size_t)B * n_win * NCH * 4, ctx->stream));
     MKID_CUDA(ctx, cudaMemsetAsync(ch->win_cnt, 0, (size_t)B * (n_win + 1) * 4, ctx->stream));
-    dim3 gc((unsigned)((rows + CAND_ROWS - 1) / CAND_ROWS), B);
-    candidates_kernel<<<gc, 256, 0, ctx->stream>>>(phase_dev, rows, d.M, d.thr, ch->mask);
-    MKID_CHECK_LAUNCH(ctx);
+    if (!have_mask) {
+        dim3 gc((unsigned)((rows + CAND_ROWS - 1) / CAND_ROWS), B);
+        candidates_kernel<<<gc, 256, 0, ctx->stream>>>(phase_dev, rows, d.M, d.thr, ch->mask);
+        MKID_CHECK_LAUNCH(ctx);
+    }
     resolve_kernel<<<dim3(NCH / 32, B), 32, 0, ctx->stream>>>(ch->mask, rows, r_lo, r_hi, t_abs0, d.L, d.Lw, n_win,
                                                              d.t_next, ch->acc, ch->win_cnt);
     MKID_CHECK_LAUNCH(ctx);
@@ -677,7 +751,7 @@ extern "C" int mkid_chan_create(mkid_ctx *ctx, const mkid_chan_params *prm, mkid
     MKID_REQUIRE(ctx, prm && out, "chan_create: NULL argument");
     MKID_REQUIRE(ctx, prm->n_boards >= 1 && prm->n_boards <= 64, "n_boards must be 1..64");
     MKID_REQUIRE(ctx, prm->n_lut >= 512 && (prm->n_lut & (prm->n_lut - 1)) == 0, "n_lut must be a power of two >= 512");
-    MKID_REQUIRE(ctx, prm->mean_len >= 1 && prm->mean_len <= 32, "mean_len must be 1..32");
+    MKID_REQUIRE(ctx, prm->mean_len >= 4 && prm->mean_len <= 32, "mean_len must be 4..32");
     MKID_REQUIRE(ctx, prm->holdoff >= 32, "holdoff must be >= 32");
     MKID_REQUIRE(ctx, prm->peak_win >= 1 && prm->peak_win <= 60, "peak_win must be 1..60");
     MKID_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -742,7 +816,7 @@ extern "C" void mkid_chan_destroy(mkid_ctx *ctx, mkid_chan *ch) {
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     ChanDev &d = ch->d;
     void *ps[] = {d.window, d.tw512, d.tw256, d.bins, d.ddsf, d.gain, d.cen_i, d.cen_q, d.thr, d.hist, d.t_next,
-                  ch->n_words_dev, ch->phase_buf, ch->mask, ch->acc, ch->win_cnt, ch->words_dev, ch->in_dev};
+                  ch->n_words_dev, ch->halo, ch->phase_buf, ch->mask, ch->acc, ch->win_cnt, ch->words_dev, ch->in_dev};
     for (void *p : ps) if (p) cudaFree(p);
     if (ch->ev_k4[0]) { cudaEventDestroy(ch->ev_k4[0]); cudaEventDestroy(ch->ev_k4[1]); }
     delete ch;
@@ -870,9 +944,20 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
         int64_t k = std::max<int64_t>(1, (rows / 512 + target - 1) / target);     // waves
         int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(k * target, rows / 256));
         int64_t rpc = (rows + chunks - 1) / chunks;
-        rpc = (rpc + 3) / 4 * 4;
+        rpc = (rpc + 31) / 32 * 32;
         p.rows_per_chunk = (int)rpc;
         p.chunks_per_board = (int)((rows + rpc - 1) / rpc);
+    }
+    p.mask = nullptr; p.halo = nullptr;
+    if (detect) {       // K5c fused into K4: the candidate mask is produced while the phase is in registers
+        const int64_t n_groups = (rows + 31) >> 5;
+        cap = ch->mask_bytes;
+        if ((rc = ensure(ctx, (void **)&ch->mask, &cap, (size_t)B * n_groups * NCH * 4))) return rc;
+        ch->mask_bytes = cap;
+        cap = ch->halo_bytes;
+        if ((rc = ensure(ctx, (void **)&ch->halo, &cap, (size_t)B * p.chunks_per_board * 32 * NCH * 2))) return rc;
+        ch->halo_bytes = cap;
+        p.mask = ch->mask; p.halo = ch->halo;
     }
     const size_t smem = (size_t)(16 * FFT_STRIDE + RING * NCH + 256) * sizeof(float2);   // ring + fft + twiddles
     MKID_CUDA(ctx, cudaFuncSetAttribute(channelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -896,7 +981,7 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
             ch->words_bytes = cap;
             wdev = ch->words_dev;
         }
-        if ((rc = run_detect(ctx, ch, ch->phase_buf, rows, RES_LO, RES_LO + T, t_abs0, wdev, words_cap))) return rc;
+        if ((rc = run_detect(ctx, ch, ch->phase_buf, rows, RES_LO, RES_LO + T, t_abs0, wdev, words_cap, true))) return rc;
         MKID_CUDA(ctx, cudaMemcpyAsync(n_words, ch->n_words_dev, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
         MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         int64_t mx = 0;
@@ -943,7 +1028,7 @@ extern "C" int mkid_chan_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *pha
     if (t_next) MKID_CUDA(ctx, cudaMemcpyAsync(d.t_next, t_next, (size_t)B * NCH * 8, cudaMemcpyDefault, ctx->stream));
     void *w_dev;
     if ((rc = mkid_stage_out(ctx, words, (size_t)B * words_cap * 8, SCR_OUT0, false, &w_dev))) return rc;
-    if ((rc = run_detect(ctx, ch, (const int16_t *)ph_dev, rows, d.M, rows - d.W - 1, t_abs0, (uint64_t *)w_dev, words_cap))) return rc;
+    if ((rc = run_detect(ctx, ch, (const int16_t *)ph_dev, rows, d.M, rows - d.W - 1, t_abs0, (uint64_t *)w_dev, words_cap, false))) return rc;
     MKID_CUDA(ctx, cudaMemcpyAsync(n_words, ch->n_words_dev, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (t_next) MKID_CUDA(ctx, cudaMemcpyAsync(t_next, d.t_next, (size_t)B * NCH * 8, cudaMemcpyDefault, ctx->stream));
     MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
