@@ -46,6 +46,7 @@ struct ChanDev {                         // device-resident configuration + stat
     float2 *tw512;        // [256]  W512^k
     float2 *tw256;        // [16][16] W256^(j*q) stored [q][j]
     float fir[FIRT];      // c_k / (2047*32767)
+    float2 fir2[FIRT];    // (c_k, c_k) pairs: packed f32x2 FMA operands
     int16_t *bins;        // [B][256]
     float2 *ddsf;         // [B][Ld][256]  (I, Q) as float, channel-minor
     float *gain;          // [B][256] 0 (zeroed FIR) or 1
@@ -162,11 +163,11 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
     const int64_t tl0 = r_start - PRE_ROWS, tl1 = row1 - PRE_ROWS;
     const ChanDev &d = p.d;
     // ---- per-thread constants
-    float hA[PTAPS], hB[PTAPS];
+    float2 hA[PTAPS], hB[PTAPS];           // (h, h) pairs for packed f32x2 FMAs
 #pragma unroll
     for (int q = 0; q < PTAPS; ++q) {
-        hA[q] = d.window[NFFT * q + tid];
-        hB[q] = d.window[NFFT * q + HOP + tid];
+        hA[q] = make_float2(d.window[NFFT * q + tid], d.window[NFFT * q + tid]);
+        hB[q] = make_float2(d.window[NFFT * q + HOP + tid], d.window[NFFT * q + HOP + tid]);
     }
     const float2 w512 = d.tw512[tid];
     const int bin = d.bins[board * NCH + tid];
@@ -272,18 +273,20 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
         float4 yw[16];                                                  // frames fb-24 .. fb+7
 #pragma unroll
         for (int i = 0; i < 16; ++i) yw[i] = s_ring[(((RB + 8 + 2 * i) & (RING - 1)) >> 1) * NCH + tid];
-        float ar[4] = {0.f, 0.f, 0.f, 0.f}, ai[4] = {0.f, 0.f, 0.f, 0.f};
+        // packed FP32x2 FMAs (sm_100 FFMA2): one instruction advances the real and imaginary accumulators
+        float2 acc[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
 #pragma unroll
         for (int k = 0; k < FIRT; ++k) {
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj) {
                 const int f = 2 * jj + k;                               // frame index in the window
-                const float yr = (f & 1) ? yw[f >> 1].z : yw[f >> 1].x;
-                const float yi = (f & 1) ? yw[f >> 1].w : yw[f >> 1].y;
-                ar[jj] = fmaf(d.fir[k], yr, ar[jj]);
-                ai[jj] = fmaf(d.fir[k], yi, ai[jj]);
+                const float2 y2 = (f & 1) ? make_float2(yw[f >> 1].z, yw[f >> 1].w) : make_float2(yw[f >> 1].x, yw[f >> 1].y);
+                acc[jj] = __ffma2_rn(d.fir2[k], y2, acc[jj]);
             }
         }
+        float ar[4], ai[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) { ar[jj] = acc[jj].x; ai[jj] = acc[jj].y; }
         int raw[4];
         float ph[4];
 #pragma unroll
@@ -329,9 +332,8 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
             float2 u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int q = 0; q < PTAPS; ++q) {
-                const float2 a = sw[(2 * q + i) & 7], b = sw[(2 * q + 1 + i) & 7];
-                u0.x = fmaf(hA[q], a.x, u0.x); u0.y = fmaf(hA[q], a.y, u0.y);
-                u1.x = fmaf(hB[q], b.x, u1.x); u1.y = fmaf(hB[q], b.y, u1.y);
+                u0 = __ffma2_rn(hA[q], sw[(2 * q + i) & 7], u0);
+                u1 = __ffma2_rn(hB[q], sw[(2 * q + 1 + i) & 7], u1);
             }
             s_fft[(2 * i) * FFT_STRIDE + tid] = cadd(u0, u1);                      // even bins
             s_fft[(2 * i + 1) * FFT_STRIDE + tid] = cmul(csub(u0, u1), w512);      // odd bins
@@ -806,7 +808,7 @@ extern "C" int mkid_chan_create(mkid_ctx *ctx, const mkid_chan_params *prm, mkid
     MKID_CUDA(ctx, cudaMemcpy(d.window, h.data(), WIN * 4, cudaMemcpyHostToDevice));
     MKID_CUDA(ctx, cudaMemcpy(d.tw512, t512.data(), 256 * 8, cudaMemcpyHostToDevice));
     MKID_CUDA(ctx, cudaMemcpy(d.tw256, t256.data(), 256 * 8, cudaMemcpyHostToDevice));
-    for (int k = 0; k < FIRT; ++k) d.fir[k] = 0.f;
+    for (int k = 0; k < FIRT; ++k) { d.fir[k] = 0.f; d.fir2[k] = make_float2(0.f, 0.f); }
     *out = ch;
     return mkid_chan_reset(ctx, ch);
 }
@@ -828,6 +830,7 @@ extern "C" int mkid_chan_set_fir(mkid_ctx *ctx, mkid_chan *ch, const int32_t *fi
     for (int k = 0; k < FIRT; ++k) {
         MKID_REQUIRE(ctx, fir_int[k] >= -2048 && fir_int[k] <= 2047, "FIR taps are 12-bit two's complement");
         ch->d.fir[k] = (float)((double)fir_int[k] / (2047.0 * 32767.0));
+        ch->d.fir2[k] = make_float2(ch->d.fir[k], ch->d.fir[k]);
     }
     ch->fir_set = true;
     return MKID_OK;
