@@ -942,10 +942,10 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     // K4
     K4Params p;
     p.d = d; p.in = in_dev; p.n = n; p.f0_abs = 2 * ch->t_consumed; p.phase = ch->phase_buf; p.rows = rows; p.phase_f32 = ch->f32_out;
-    {   // chunk the rows so that the grid is close to a multiple of 2 CTAs/SM, chunks of >= 256 rows
+    {   // one wave of equal chunks when they stay >= 512 rows (2 CTAs per SM), else more waves of >= 256 rows
         const int64_t target = std::max<int64_t>(1, (int64_t)ctx->num_sms * 2 / B);
-        int64_t k = std::max<int64_t>(1, (rows / 512 + target - 1) / target);     // waves
-        int64_t chunks = std::max<int64_t>(1, std::min<int64_t>(k * target, rows / 256));
+        int64_t chunks = target;
+        while (chunks > 1 && rows / chunks < 256) chunks = (chunks + 1) / 2;
         int64_t rpc = (rows + chunks - 1) / chunks;
         rpc = (rpc + 31) / 32 * 32;
         p.rows_per_chunk = (int)rpc;
