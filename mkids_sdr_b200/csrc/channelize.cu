@@ -37,6 +37,7 @@ constexpr int PRE_ROWS = 96;             // output rows recomputed in front of e
 constexpr int RES_LO = 32;               // first resolved row of the phase buffer in mkid_chan_process
 constexpr int T_START = 64;              // first absolute output index that may trigger
 constexpr int FFT_STRIDE = 272;          // 16 x 17 padded float2 per 256-point FFT
+constexpr int EDGE_ROWS = 160;            // rows of chunk 0: everything that can touch the input history
 constexpr int CAND_ROWS = 1024;          // rows per CTA of the candidate kernel
 constexpr int64_t SEC_US = 1000000;
 
@@ -153,8 +154,9 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
 // One chunk of output rows of one board.  EDGE = the chunk touches the start of the call (input
 // history) or the start of the stream (frames before time 0 contribute nothing).
 template <bool EDGE, bool F32>
-__device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_fft, float4 *s_ring, const float2 *s_tw,
-                                                 int board, int64_t row0, int64_t row1) {
+__device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_fft, uint32_t *s_adc, float2 *s_dds,
+                                                 uint64_t *s_bar, const float2 *s_tw, int board, int64_t row0,
+                                                 int64_t row1) {
     const int tid = threadIdx.x;
     // rows [row0,row1) are stored; rows from r_start on are computed (the M rows in front of the chunk
     // feed the rolling baseline of the trigger); row r is local output t = r - PRE_ROWS
@@ -175,7 +177,6 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
     const float2 *zsrc = s_fft + par * FFT_STRIDE + (bin >> 1);      // + 2*i*FFT_STRIDE per frame
     const bool live = d.gain[board * NCH + tid] != 0.f;
     const float cen_i = d.cen_i[board * NCH + tid], cen_q = d.cen_q[board * NCH + tid];
-    const float2 *dds = d.ddsf + (size_t)board * d.Ld * NCH + tid;
     const uint32_t *in = p.in + (size_t)board * p.n;
     const uint32_t *hist = d.hist + (size_t)board * d.H;
     int16_t *phase = p.phase + (size_t)board * p.rows * NCH + tid;
@@ -212,11 +213,25 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
         else sw[j] = unpack(src[HOP * (j - 7)]);
     }
     sw[7] = make_float2(0.f, 0.f);
-    uint32_t pre[FB];
+    // staging buffers: the 2048 ADC samples of the next block (8 KiB, contiguous in HBM) and the 8 x 256 DDS
+    // values of the current block (16 KiB, contiguous in the repacked LUT) arrive by 1-D TMA bulk copies issued
+    // by thread 0 and signalled on mbarriers, while the arithmetic runs.  EDGE chunks (input history, time < 0)
+    // fill their own ADC column with plain loads instead.
+    uint32_t *adc_c = s_adc + tid;
+    float2 *dds_c = s_dds + tid;
+    const uint32_t *adc_blk = in + HOP * fb_first;                // first sample of the block being staged
+    const float2 *dds_blk = d.ddsf + (size_t)board * d.Ld * NCH;  // + dds_row * NCH
+    uint32_t par_adc = 0, par_dds = 0;
+    if (EDGE) {
 #pragma unroll
-    for (int i = 0; i < FB; ++i) {
-        if (EDGE) pre[i] = load_sample(HOP * (fb_first + i) + tid);
-        else pre[i] = src[HOP * i];
+        for (int i = 0; i < FB; ++i) adc_c[i * NCH] = load_sample(HOP * (fb_first + i) + tid);
+    } else if (tid == 0) {
+        mk_mbar_expect_tx(&s_bar[0], FB * HOP * 4);
+        mk_bulk_g2s(s_adc, adc_blk, FB * HOP * 4, &s_bar[0]);
+    }
+    if (tid == 0) {
+        mk_mbar_expect_tx(&s_bar[1], FB * NCH * 8);
+        mk_bulk_g2s(s_dds, dds_blk + (size_t)dds_row * NCH, FB * NCH * 8, &s_bar[1]);
     }
 
     // ---- channel-stage state in chunk-relative rows (32-bit): row r = row0 + rl
@@ -229,33 +244,53 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
     int rl = (int)((fb_first >> 1) + PRE_ROWS - row0);                // relative row of the block's first output
     const int rl_fast = rl_eval0 > M ? rl_eval0 : M;                  // from here on no boundary cases
 
-    auto channel_stage = [&](auto RBc, const float2 (&dv)[FB], int blk) {
+    // Transposed-form FIR: every new frame adds its contribution to the 13 outputs it belongs to.
+    // acc[] holds 16 output accumulators (4 completing in this block + 12 pending); the slot of the
+    // output with block-relative index m is (m + 4*block) mod 16, static inside each of the 4 ring
+    // phases RB = 8*(block mod 4).  No shared-memory history of the mixed samples is needed.
+    float2 acc[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) acc[m] = make_float2(0.f, 0.f);
+
+    auto channel_stage = [&](auto RBc, int blk) {
         constexpr int RB = decltype(RBc)::value;
+        constexpr int A0 = RB / 2;                                       // slot of output m = 0
         // gather the bin, remove the half-frame hop phase of odd bins ((-1)^(bin*(f_abs+1)); f_abs of
         // frame i has the parity of i because block starts and call starts are even), mix with conj(dds)
+        float2 y[FB];
 #pragma unroll
-        for (int i = 0; i < FB; i += 2) {
-            float2 z0 = zsrc[(2 * i) * FFT_STRIDE], z1 = zsrc[(2 * i + 2) * FFT_STRIDE];
-            if (par) { z0.x = -z0.x; z0.y = -z0.y; }                       // even i: f_abs + 1 odd
-            float4 y;
-            y.x = z0.x * dv[i].x + z0.y * dv[i].y;
-            y.y = z0.y * dv[i].x - z0.x * dv[i].y;
-            y.z = z1.x * dv[i + 1].x + z1.y * dv[i + 1].y;
-            y.w = z1.y * dv[i + 1].x - z1.x * dv[i + 1].y;
+        for (int i = 0; i < FB; ++i) {
+            float2 z = zsrc[(2 * i) * FFT_STRIDE];
+            const float2 dvi = dds_c[i * NCH];
+            if ((i & 1) == 0 && par) { z.x = -z.x; z.y = -z.y; }           // even i: f_abs + 1 odd
+            y[i].x = z.x * dvi.x + z.y * dvi.y;
+            y[i].y = z.y * dvi.x - z.x * dvi.y;
             if (EDGE) {
                 const int64_t f_abs = p.f0_abs + fb_first + (int64_t)blk * FB + i;
-                if (f_abs < 0) { y.x = 0.f; y.y = 0.f; }
-                if (f_abs + 1 < 0) { y.z = 0.f; y.w = 0.f; }
+                if (f_abs < 0) { y[i].x = 0.f; y[i].y = 0.f; }
             }
-            s_ring[(((RB + i) & (RING - 1)) >> 1) * NCH + tid] = y;
         }
-        // every thread has gathered its bins: the next block's PFB may overwrite s_fft.  From here on a
-        // thread touches only its own ring column.
+        // every thread has gathered its bins: the next block's PFB may overwrite s_fft
         __syncthreads();
+        // output t = fb/2 + m uses frames 2t+1-25+k, k = 0..25: frame fb+i carries tap k = i - 2m + 24
+#pragma unroll
+        for (int k = 0; k < FIRT; ++k) {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const int i = k - 24 + 2 * m;
+                if (i >= 0 && i < FB) acc[(A0 + m) & 15] = __ffma2_rn(d.fir2[k], y[i], acc[(A0 + m) & 15]);
+            }
+        }
+        float ar[4], ai[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            ar[jj] = acc[(A0 + jj) & 15].x; ai[jj] = acc[(A0 + jj) & 15].y;
+            acc[(A0 + jj) & 15] = make_float2(0.f, 0.f);                  // becomes output m = 12 + jj of the next block
+        }
         if (rl + 3 < rl_start || rl >= n_rows) return;
         const bool fast = rl >= rl_fast && rl + 3 < n_rows;
         // rows leaving the rolling baseline while these 4 outputs enter it (M >= 4, so they were stored by
-        // an earlier block): loaded now, used after the FIR arithmetic
+        // an earlier block)
         int old[4] = {0, 0, 0, 0};
         if (mk) {
             if (fast) {
@@ -269,24 +304,6 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
                 }
             }
         }
-        // FIR for the 4 outputs t = fb/2 + jj: frames fb + 2*jj - 24 + k, k = 0..25
-        float4 yw[16];                                                  // frames fb-24 .. fb+7
-#pragma unroll
-        for (int i = 0; i < 16; ++i) yw[i] = s_ring[(((RB + 8 + 2 * i) & (RING - 1)) >> 1) * NCH + tid];
-        // packed FP32x2 FMAs (sm_100 FFMA2): one instruction advances the real and imaginary accumulators
-        float2 acc[4] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};
-#pragma unroll
-        for (int k = 0; k < FIRT; ++k) {
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int f = 2 * jj + k;                               // frame index in the window
-                const float2 y2 = (f & 1) ? make_float2(yw[f >> 1].z, yw[f >> 1].w) : make_float2(yw[f >> 1].x, yw[f >> 1].y);
-                acc[jj] = __ffma2_rn(d.fir2[k], y2, acc[jj]);
-            }
-        }
-        float ar[4], ai[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) { ar[jj] = acc[jj].x; ai[jj] = acc[jj].y; }
         int raw[4];
         float ph[4];
 #pragma unroll
@@ -325,10 +342,11 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
     };
 
     for (int blk = 0; blk < n_blocks; ++blk) {
+        if (!EDGE) { mk_mbar_wait(&s_bar[0], par_adc); par_adc ^= 1; }      // this block's ADC samples have landed
         // ================= PFB + first radix-2 stage for 8 frames =================
 #pragma unroll
         for (int i = 0; i < FB; ++i) {
-            sw[(i + 7) & 7] = unpack(pre[i]);
+            sw[(i + 7) & 7] = unpack(adc_c[i * NCH]);
             float2 u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int q = 0; q < PTAPS; ++q) {
@@ -340,17 +358,16 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
         }
         // prefetch: next block's ADC samples and this block's DDS values (consumed after the FFT)
         src += HOP * FB;
-        if (blk + 1 < n_blocks) {
+        adc_blk += HOP * FB;
+        if (EDGE && blk + 1 < n_blocks) {           // own column: read above by this thread only
 #pragma unroll
-            for (int i = 0; i < FB; ++i) {
-                if (EDGE) pre[i] = load_sample(HOP * (fb_first + (int64_t)(blk + 1) * FB + i) + tid);
-                else pre[i] = src[HOP * i];
-            }
+            for (int i = 0; i < FB; ++i) adc_c[i * NCH] = load_sample(HOP * (fb_first + (int64_t)(blk + 1) * FB + i) + tid);
         }
-        float2 dv[FB];
-#pragma unroll
-        for (int i = 0; i < FB; ++i) dv[i] = dds[(size_t)((dds_row + i) & ld_mask) * NCH];
         __syncthreads();
+        if (!EDGE && tid == 0 && blk + 1 < n_blocks) {   // every thread has consumed the ADC staging buffer
+            mk_mbar_expect_tx(&s_bar[0], FB * HOP * 4);
+            mk_bulk_g2s(s_adc, adc_blk, FB * HOP * 4, &s_bar[0]);
+        }
         // ================= 16 x FFT-256: two radix-16 passes =================
         {
             float2 *reg = s_fft + (tid >> 4) * FFT_STRIDE;
@@ -384,39 +401,51 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
         __syncthreads();
         // ================= channel stage: thread = channel =================
         // The ring position of a block takes only 4 values; one statically addressed copy per value.
+        mk_mbar_wait(&s_bar[1], par_dds); par_dds ^= 1;                   // DDS values of this block have landed
         switch (ring_base) {
-        case 0: channel_stage(std::integral_constant<int, 0>{}, dv, blk); break;
-        case 8: channel_stage(std::integral_constant<int, 8>{}, dv, blk); break;
-        case 16: channel_stage(std::integral_constant<int, 16>{}, dv, blk); break;
-        default: channel_stage(std::integral_constant<int, 24>{}, dv, blk); break;
+        case 0: channel_stage(std::integral_constant<int, 0>{}, blk); break;
+        case 8: channel_stage(std::integral_constant<int, 8>{}, blk); break;
+        case 16: channel_stage(std::integral_constant<int, 16>{}, blk); break;
+        default: channel_stage(std::integral_constant<int, 24>{}, blk); break;
         }
         rl += 4;
         dds_row = (dds_row + FB) & ld_mask;
+        if (tid == 0 && blk + 1 < n_blocks) {            // all threads passed the barrier inside channel_stage
+            mk_mbar_expect_tx(&s_bar[1], FB * NCH * 8);
+            mk_bulk_g2s(s_dds, dds_blk + (size_t)dds_row * NCH, FB * NCH * 8, &s_bar[1]);
+        }
         ring_base = (ring_base + FB) & (RING - 1);
     }
 }
 
 __global__ void __launch_bounds__(256, 2) channelize_kernel(K4Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    float4 *s_ring = reinterpret_cast<float4 *>(smem_raw);                        // [RING/2][256] frame pairs
-    float2 *s_fft = reinterpret_cast<float2 *>(s_ring + (RING / 2) * NCH);        // [16][FFT_STRIDE]
+    float2 *s_fft = reinterpret_cast<float2 *>(smem_raw);                         // [16][FFT_STRIDE]
     float2 *s_tw = s_fft + 16 * FFT_STRIDE;                                       // [16][16]
+    float2 *s_dds = s_tw + 256;                                                    // [8][256] DDS values of the block
+    uint32_t *s_adc = reinterpret_cast<uint32_t *>(s_dds + FB * NCH);             // [8][256] ADC samples of the next block
+    __shared__ __align__(8) uint64_t s_bar[2];                                     // mbarriers: ADC, DDS staging
+    if (threadIdx.x == 0) {
+        mk_mbar_init(&s_bar[0], 1);
+        mk_mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     const int tid = threadIdx.x;
     const int board = blockIdx.y;
     // output rows [row0,row1) of the phase buffer; row r is local output t = r - PRE_ROWS
-    const int64_t row0 = (int64_t)blockIdx.x * p.rows_per_chunk;
-    const int64_t row1 = min(row0 + (int64_t)p.rows_per_chunk, p.rows);
+    // chunk 0 is the short edge chunk (input history / stream start); the others are equal
+    const int64_t row0 = blockIdx.x == 0 ? 0 : EDGE_ROWS + (int64_t)(blockIdx.x - 1) * p.rows_per_chunk;
+    const int64_t row1 = blockIdx.x == 0 ? min((int64_t)EDGE_ROWS, p.rows) : min(row0 + (int64_t)p.rows_per_chunk, p.rows);
     if (row0 >= row1) return;
     s_tw[tid] = p.d.tw256[tid];
-    for (int i = tid; i < (RING / 2) * NCH; i += 256) s_ring[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
     const int64_t r_start = p.mask ? (row0 - p.d.M > 0 ? row0 - p.d.M : 0) : row0;
     const int64_t fb_first = ((2 * (r_start - PRE_ROWS) - 24) >> 3) << 3;
     // earliest sample read: 256*(fb_first+1) - 2048; earliest absolute frame: f0_abs + fb_first
     const bool edge = (HOP * (fb_first + 1) - WIN < 0) || (p.f0_abs + fb_first < 0);
-    if (p.phase_f32) channelize_chunk<true, true>(p, s_fft, s_ring, s_tw, board, row0, row1);     // test hook: slow path
-    else if (edge) channelize_chunk<true, false>(p, s_fft, s_ring, s_tw, board, row0, row1);
-    else channelize_chunk<false, false>(p, s_fft, s_ring, s_tw, board, row0, row1);
+    if (p.phase_f32) channelize_chunk<true, true>(p, s_fft, s_adc, s_dds, s_bar, s_tw, board, row0, row1);     // test hook: slow path
+    else if (edge) channelize_chunk<true, false>(p, s_fft, s_adc, s_dds, s_bar, s_tw, board, row0, row1);
+    else channelize_chunk<false, false>(p, s_fft, s_adc, s_dds, s_bar, s_tw, board, row0, row1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -942,14 +971,15 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     // K4
     K4Params p;
     p.d = d; p.in = in_dev; p.n = n; p.f0_abs = 2 * ch->t_consumed; p.phase = ch->phase_buf; p.rows = rows; p.phase_f32 = ch->f32_out;
-    {   // one wave of equal chunks when they stay >= 512 rows (2 CTAs per SM), else more waves of >= 256 rows
-        const int64_t target = std::max<int64_t>(1, (int64_t)ctx->num_sms * 2 / B);
-        int64_t chunks = target;
-        while (chunks > 1 && rows / chunks < 256) chunks = (chunks + 1) / 2;
-        int64_t rpc = (rows + chunks - 1) / chunks;
-        rpc = (rpc + 31) / 32 * 32;
+    {   // chunk 0 = EDGE_ROWS rows (slow path, small); the rest in equal chunks: one wave of 2 CTAs per SM when
+        // the chunks stay >= 256 rows, else fewer chunks
+        const int64_t rest = std::max<int64_t>(rows - EDGE_ROWS, 0);
+        int64_t chunks = std::max<int64_t>(1, (int64_t)ctx->num_sms * 2 / B - 1);
+        while (chunks > 1 && rest / chunks < 256) chunks = (chunks + 1) / 2;
+        int64_t rpc = (rest + chunks - 1) / chunks;
+        rpc = std::max<int64_t>(32, (rpc + 31) / 32 * 32);
         p.rows_per_chunk = (int)rpc;
-        p.chunks_per_board = (int)((rows + rpc - 1) / rpc);
+        p.chunks_per_board = 1 + (int)((rest + rpc - 1) / rpc);
     }
     p.mask = nullptr; p.halo = nullptr;
     if (detect) {       // K5c fused into K4: the candidate mask is produced while the phase is in registers
@@ -962,7 +992,7 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
         ch->halo_bytes = cap;
         p.mask = ch->mask; p.halo = ch->halo;
     }
-    const size_t smem = (size_t)(16 * FFT_STRIDE + RING * NCH + 256) * sizeof(float2);   // ring + fft + twiddles
+    const size_t smem = (size_t)(16 * FFT_STRIDE + 256 + FB * NCH) * sizeof(float2) + (size_t)FB * NCH * 4;   // fft exchange, twiddles, DDS + ADC staging
     MKID_CUDA(ctx, cudaFuncSetAttribute(channelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (!ch->ev_k4[0]) { cudaEventCreate(&ch->ev_k4[0]); cudaEventCreate(&ch->ev_k4[1]); }
     MKID_CUDA(ctx, cudaEventRecord(ch->ev_k4[0], ctx->stream));

@@ -66,6 +66,31 @@ int mkid_stage_in(mkid_ctx *ctx, const void *p, size_t bytes, int slot, const vo
 int mkid_stage_out(mkid_ctx *ctx, void *p, size_t bytes, int slot, bool accumulate, void **dev);
 int mkid_stage_out_finish(mkid_ctx *ctx, void *p, size_t bytes, void *dev);
 
+// ---- mbarrier + 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) helpers
+__device__ __forceinline__ uint32_t mk_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mk_mbar_init(uint64_t *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mk_smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mk_mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mk_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mk_mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(mk_smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mk_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     mk_smem_u32(dst)), "l"(src), "r"(bytes), "r"(mk_smem_u32(bar))
+                 : "memory");
+}
+
 __device__ __forceinline__ uint4 ld_stream_u4(const uint4 *p) {
     uint4 r;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
