@@ -500,15 +500,16 @@ __global__ void __launch_bounds__(32) resolve_kernel(const uint32_t *__restrict_
         return r > r_lo ? r : r_lo;
     };
     int64_t g = first_allowed() >> 5;
+    constexpr int RB_WORDS = 32;                      // 1024 rows per batch: one batch usually reaches the next trigger
     while (g < g_hi) {
-        uint32_t wv[8];
+        uint32_t wv[RB_WORDS];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) wv[u] = (g + u < g_hi) ? mk[(g + u) * NCH + c] : 0u;
+        for (int u = 0; u < RB_WORDS; ++u) wv[u] = (g + u < g_hi) ? mk[(g + u) * NCH + c] : 0u;
         bool jumped = false;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < RB_WORDS; ++u) {
             uint32_t w = wv[u];
-            if (!w) continue;
+            if (!w || jumped) continue;
             const int64_t r_base = (g + u) << 5;
             const int64_t lo = first_allowed();
             if (lo > r_base) { const int64_t sh = lo - r_base; w = sh >= 32 ? 0u : (w >> sh) << sh; }
@@ -521,9 +522,8 @@ __global__ void __launch_bounds__(32) resolve_kernel(const uint32_t *__restrict_
             atomicAdd(&wc[wi], 1u);
             g = first_allowed() >> 5;                   // jump over the dead time
             jumped = true;
-            break;
         }
-        if (!jumped) g += 8;
+        if (!jumped) g += RB_WORDS;
     }
     t_next[board * NCH + c] = tn;
 }

@@ -4,21 +4,30 @@
 // the per-word unpack of DataReadout/ChannelizerControls/ROACH_Pulses.py:795-832.
 //
 // HBM-bound integer work: every word is read exactly once (8 B/word).  A chunk is 8192 words
-// (= one PulseServer bundle, PacketMaster.c:42-44).  Persistent CTAs take chunks from an
-// ordered ticket; which second a word belongs to is the number of end-of-second words before
-// it in its roach stream, resolved in the same pass with a decoupled look-back over per-chunk
-// EOS counts (chunk c waits only for the published prefix of chunk c-1 of its segment).
+// (64 KiB = one PulseServer bundle, PacketMaster.c:42-44).  One persistent, warp-specialised CTA
+// per SM:
+//   3 scout warps        one per stage of a 3 x 64 KiB shared-memory ring: take a chunk from an ordered
+//                        ticket, stream it in with 1-D TMA bulk copies (mbarrier completion), count its
+//                        end-of-second words as soon as it has landed, publish that count and resolve
+//                        "seconds closed before this chunk" with a decoupled look-back over the published
+//                        counts -- each scout has a full ring revolution to hide its L2 round trips;
+//   16 worker warps      unpack the bitfields from shared memory and bin: per-(second,pixel) counts
+//                        through a per-chunk shared-memory histogram (double buffered, one named
+//                        barrier per chunk), pulse-height histogram through shared memory when it is
+//                        small, else global reductions.
 #include "common.cuh"
 
 namespace {
 
-constexpr int DEC_THREADS = 512;
-constexpr int DEC_CHUNK = 4096;                    // words per chunk (wire: half a bundle)
+constexpr int DEC_WORKERS = 512;                   // worker threads
+constexpr int DEC_THREADS = DEC_WORKERS + 32 * 3;  // + one producer/scout warp per ring stage
+constexpr int DEC_CHUNK = 8192;                    // words per chunk
 constexpr int DEC_BUNDLE = 8192;                   // PacketMaster.c:44 BUFSIZE_INTS
-constexpr int DEC_WPT = DEC_CHUNK / DEC_THREADS;   // 8 words per thread
-constexpr int DEC_ITERS = DEC_WPT / 2;             // 4 iterations of 2 words (one uint4)
-constexpr int DEC_WARPS = DEC_THREADS / 32;
+constexpr int DEC_WPT = DEC_CHUNK / DEC_WORKERS;   // 16 words per worker thread
+constexpr int DEC_STAGES = 3;
+constexpr int DEC_STAGE_BYTES = DEC_CHUNK * 8;
 constexpr int DEC_SMEM_HIST = 4096;                // smem-privatised histogram entries
+constexpr int DEC_MAX_EOS = 64;                    // end-of-second positions kept per chunk (more: slow path)
 
 struct DecParams {
     const uint64_t *words;     // flat format (or nullptr)
@@ -41,157 +50,163 @@ struct DecParams {
     unsigned int *ticket;
 };
 
+struct StageMeta {
+    long long chunk;       // < 0: no more work
+    int roach, base_sec, n_here, n_eos, last_chunk, seg;
+    int eos_pos[DEC_MAX_EOS];
+};
+
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mk_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(DEC_WORKERS) : "memory"); }
 
 template <bool WIRE, bool SMEM_HIST>
-__global__ void __launch_bounds__(DEC_THREADS, 2) decode_kernel(DecParams p) {
-    __shared__ uint32_t s_cnt[256];
+__global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(DecParams p) {
+    extern __shared__ __align__(128) unsigned char s_ring[];      // DEC_STAGES x 64 KiB
+    __shared__ uint32_t s_cnt[2][256];
     __shared__ uint32_t s_hist[SMEM_HIST ? DEC_SMEM_HIST : 1];
     __shared__ uint16_t s_lut[4096];
-    __shared__ int s_eos_iw[DEC_ITERS][DEC_WARPS];
     __shared__ unsigned long long s_stat[5];
-    __shared__ long long s_chunk;
-    __shared__ int s_seg, s_secbase;
+    __shared__ __align__(8) uint64_t s_full[DEC_STAGES], s_ready[DEC_STAGES], s_empty[DEC_STAGES];
+    __shared__ StageMeta s_meta[DEC_STAGES];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool use_lut = p.bin_lut != nullptr;
     if (use_lut)
         for (int i = tid; i < 4096; i += DEC_THREADS) s_lut[i] = p.bin_lut[i];
     if (tid < 5) s_stat[tid] = 0;
+    for (int i = tid; i < 512; i += DEC_THREADS) (&s_cnt[0][0])[i] = 0;
+    if (SMEM_HIST)
+        for (int i = tid; i < DEC_SMEM_HIST; i += DEC_THREADS) s_hist[i] = 0;
+    if (tid == 0) {
+        for (int i = 0; i < DEC_STAGES; ++i) {
+            mk_mbar_init(&s_full[i], 1);
+            mk_mbar_init(&s_ready[i], 1);
+            mk_mbar_init(&s_empty[i], DEC_WORKERS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
     const int n_pix = p.n_roaches * p.npix_per_roach;
 
-    for (;;) {
-        __syncthreads();   // previous iteration's smem fully consumed
-        if (tid == 0) {
-            long long c = (long long)atomicAdd(p.ticket, 1u);
-            s_chunk = c;
-            if (c < p.n_chunks) {   // segment of this chunk: last g with first_chunk[g] <= c
-                int lo = 0, hi = p.n_seg;
+    if (warp >= DEC_WORKERS / 32) {
+        // =========================== producer / scout warps ===========================
+        // scout j owns ring stage j: wait until the workers freed it, take the next ticket, start the bulk
+        // load, scan the chunk when it has landed, resolve its second index, hand it to the workers.
+        const int ss = warp - DEC_WORKERS / 32;
+        StageMeta &m = s_meta[ss];
+        for (int r = 0;; ++r) {                              // r-th use of this stage
+            if (r > 0) mk_mbar_wait(&s_empty[ss], (r - 1) & 1);
+            long long c = 0;
+            if (lane == 0) c = (long long)atomicAdd(p.ticket, 1u);
+            c = __shfl_sync(0xffffffffu, c, 0);
+            if (c >= p.n_chunks) {                           // no more work for this stage, ever (sticky)
+                if (lane == 0) { m.chunk = -1; mbar_arrive(&s_ready[ss]); }
+                break;
+            }
+            {
+                int lo = 0, hi = p.n_seg;       // segment of this chunk: last g with first_chunk[g] <= c
                 while (hi - lo > 1) {
-                    int mid = (lo + hi) >> 1;
+                    const int mid = (lo + hi) >> 1;
                     if (p.seg_first_chunk[mid] <= c) lo = mid; else hi = mid;
                 }
-                s_seg = lo;
-            }
-        }
-        if (tid < 256) s_cnt[tid] = 0;
-        if (SMEM_HIST)
-            for (int i = tid; i < DEC_SMEM_HIST; i += DEC_THREADS) s_hist[i] = 0;
-        __syncthreads();
-        const long long c = s_chunk;
-        if (c >= p.n_chunks) break;
-        const int g = s_seg;
-        const long long lc = c - p.seg_first_chunk[g];
-        const bool last_chunk = (c + 1 == p.seg_first_chunk[g + 1]);
-        const int roach = p.seg_roach[g];
-
-        // ---- load the chunk: each thread 8 x (2 words), coalesced 16 B per lane
-        uint64_t w[DEC_WPT];
-        int n_here;   // valid words in this chunk
-        if (WIRE) {
-            n_here = DEC_CHUNK;
-            // chunk lc of a segment = half (lc & 1) of bundle lc >> 1: 4096 low halves + 4096 high halves
-            const uint32_t *lo_blk = p.wire + (size_t)(p.seg_offset[g] + (lc >> 1)) * (2 * DEC_BUNDLE) + (lc & 1) * DEC_CHUNK;
-            const uint32_t *hi_blk = lo_blk + DEC_BUNDLE;
-#pragma unroll
-            for (int i = 0; i < DEC_ITERS / 2; ++i) {     // 2 iterations of 4 words
-                uint4 l = ld_stream_u4(reinterpret_cast<const uint4 *>(lo_blk) + i * DEC_THREADS + tid);
-                uint4 h = ld_stream_u4(reinterpret_cast<const uint4 *>(hi_blk) + i * DEC_THREADS + tid);
-                w[4 * i + 0] = ((uint64_t)bswap32(h.x) << 32) | bswap32(l.x);
-                w[4 * i + 1] = ((uint64_t)bswap32(h.y) << 32) | bswap32(l.y);
-                w[4 * i + 2] = ((uint64_t)bswap32(h.z) << 32) | bswap32(l.z);
-                w[4 * i + 3] = ((uint64_t)bswap32(h.w) << 32) | bswap32(l.w);
-            }
-        } else {
-            const long long seg_n = p.seg_len[g];
-            const long long rem = seg_n - lc * DEC_CHUNK;
-            n_here = rem < DEC_CHUNK ? (int)rem : DEC_CHUNK;
-            const uint64_t *base = p.words + p.seg_offset[g] + lc * DEC_CHUNK;
-            if (n_here == DEC_CHUNK && ((reinterpret_cast<uintptr_t>(base) & 15) == 0)) {
-#pragma unroll
-                for (int i = 0; i < DEC_ITERS; ++i) {
-                    uint4 v = ld_stream_u4(reinterpret_cast<const uint4 *>(base) + i * DEC_THREADS + tid);
-                    w[2 * i + 0] = ((uint64_t)v.y << 32) | v.x;
-                    w[2 * i + 1] = ((uint64_t)v.w << 32) | v.z;
+                const int g = lo;
+                const long long lc = c - p.seg_first_chunk[g];
+                const unsigned char *src;
+                int n_here = DEC_CHUNK;
+                if (WIRE) {
+                    src = reinterpret_cast<const unsigned char *>(p.wire) + (size_t)(p.seg_offset[g] + lc) * DEC_STAGE_BYTES;
+                } else {
+                    const long long rem = p.seg_len[g] - lc * DEC_CHUNK;
+                    n_here = rem < DEC_CHUNK ? (int)rem : DEC_CHUNK;
+                    src = reinterpret_cast<const unsigned char *>(p.words + p.seg_offset[g] + lc * DEC_CHUNK);
                 }
-            } else {   // ragged tail or odd alignment: scalar loads, same position mapping
+                unsigned char *dst = s_ring + (size_t)ss * DEC_STAGE_BYTES;
+                const bool tma = n_here == DEC_CHUNK && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
+                if (lane == 0) {
+                    m.chunk = c; m.seg = g; m.roach = p.seg_roach[g]; m.n_here = n_here;
+                    m.last_chunk = (c + 1 == p.seg_first_chunk[g + 1]);
+                    if (tma) {
+                        mk_mbar_expect_tx(&s_full[ss], DEC_STAGE_BYTES);
 #pragma unroll
-                for (int i = 0; i < DEC_ITERS; ++i) {
-                    int pos = (i * DEC_THREADS + tid) * 2;
-                    w[2 * i + 0] = pos < n_here ? base[pos] : 0ull;
-                    w[2 * i + 1] = pos + 1 < n_here ? base[pos + 1] : 0ull;
+                        for (int q = 0; q < 4; ++q)
+                            mk_bulk_g2s(dst + q * (DEC_STAGE_BYTES / 4), src + q * (DEC_STAGE_BYTES / 4),
+                                        DEC_STAGE_BYTES / 4, &s_full[ss]);
+                    }
+                }
+                if (!tma) {   // ragged tail / odd alignment (flat format only): the warp copies it, zero padded
+                    const uint64_t *sw = reinterpret_cast<const uint64_t *>(src);
+                    uint64_t *dw = reinterpret_cast<uint64_t *>(dst);
+                    for (int i = lane; i < DEC_CHUNK; i += 32) dw[i] = i < n_here ? sw[i] : 0ull;
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&s_full[ss]);
                 }
             }
-        }
-        // position of w[k] inside the chunk
-        auto pos_of = [&](int k) -> int {
-            if (WIRE) return ((k >> 2) * DEC_THREADS + tid) * 4 + (k & 3);
-            return ((k >> 1) * DEC_THREADS + tid) * 2 + (k & 1);
-        };
-
-        // ---- end-of-second words in this chunk (rare): ordered local rank of every word
-        uint32_t eos_bits = 0;
+            __syncwarp();
+            mk_mbar_wait(&s_full[ss], r & 1);
+            // count end-of-second words (channel field 255) and remember their positions, in order.
+            // Fast path: 8 x 128-bit loads per lane in flight, one ballot per batch; the ordered position
+            // list is only built for batches that contain an end-of-second word (rare).
+            const unsigned char *base = s_ring + (size_t)ss * DEC_STAGE_BYTES;
+            const uint4 *scan = reinterpret_cast<const uint4 *>(WIRE ? base + DEC_STAGE_BYTES / 2 : base);
+            constexpr int SCAN_IT = (WIRE ? DEC_STAGE_BYTES / 2 : DEC_STAGE_BYTES) / 16 / 32;   // uint4 iterations per lane
+            constexpr int POS_PER_IT = WIRE ? 128 : 64;                                       // positions covered by one iteration
+            int n_eos = 0;
+            for (int i0 = 0; i0 < SCAN_IT; i0 += 8) {
+                uint4 v[8];
 #pragma unroll
-        for (int k = 0; k < DEC_WPT; ++k)
-            if ((uint32_t)(w[k] >> 56) == 255u && pos_of(k) < n_here) eos_bits |= 1u << k;
-        const int any_eos = __syncthreads_or(eos_bits != 0);
-        constexpr int G = WIRE ? DEC_ITERS / 2 : DEC_ITERS;    // load groups per thread
-        constexpr int S = WIRE ? 4 : 2;                         // words per group
-        int rbase[G];        // seconds closed inside the chunk before the first word of group gi
-        int total_eos = 0;
+                for (int u = 0; u < 8; ++u) v[u] = scan[(i0 + u) * 32 + lane];
+                bool any = false;
 #pragma unroll
-        for (int gi = 0; gi < G; ++gi) rbase[gi] = 0;
-        if (any_eos) {
-            // positions ascend with (group, tid, sub): per group a warp-ordered exclusive prefix
-#pragma unroll
-            for (int gi = 0; gi < G; ++gi) {
-                const int mine = __popc((eos_bits >> (gi * S)) & ((1u << S) - 1));
-                int incl = mine;
-#pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    int t = __shfl_up_sync(0xffffffffu, incl, d);
-                    if (lane >= d) incl += t;
+                for (int u = 0; u < 8; ++u) {
+                    if (WIRE) any |= ((v[u].x & 0xFFu) == 0xFFu) | ((v[u].y & 0xFFu) == 0xFFu) | ((v[u].z & 0xFFu) == 0xFFu) | ((v[u].w & 0xFFu) == 0xFFu);
+                    else any |= ((v[u].y >> 24) == 0xFFu) | ((v[u].w >> 24) == 0xFFu);
                 }
-                rbase[gi] = incl - mine;
-                if (lane == 31) s_eos_iw[gi][warp] = incl;
-            }
-            __syncthreads();
-            int run = 0;   // every thread scans the (G x WARPS) table (<= 128 entries)
-#pragma unroll
-            for (int gi = 0; gi < G; ++gi) {
-                for (int ww = 0; ww < DEC_WARPS; ++ww) {
-                    if (ww == warp) rbase[gi] += run;
-                    run += s_eos_iw[gi][ww];
+                if (__ballot_sync(0xffffffffu, any)) {
+                    // position-ordered pass over this batch (zero padding beyond n_here is never an EOS word)
+                    const int p0 = i0 * POS_PER_IT, p1 = p0 + 8 * POS_PER_IT;
+                    for (int pb = p0; pb < p1; pb += 32) {
+                        const int pos = pb + lane;
+                        bool is_eos;
+                        if (WIRE) is_eos = (reinterpret_cast<const uint32_t *>(base + DEC_STAGE_BYTES / 2)[pos] & 0xFFu) == 0xFFu;
+                        else is_eos = (reinterpret_cast<const uint32_t *>(base)[2 * pos + 1] >> 24) == 0xFFu;
+                        const unsigned bal = __ballot_sync(0xffffffffu, is_eos);
+                        if (bal) {
+                            const int at = n_eos + __popc(bal & ((1u << lane) - 1));
+                            if (is_eos && at < DEC_MAX_EOS) m.eos_pos[at] = pos;
+                            n_eos += __popc(bal);
+                        }
+                    }
                 }
             }
-            total_eos = run;
-        }
-
-        // ---- decoupled look-back (warp-parallel): seconds closed before this chunk
-        if (warp == 0) {
+            // decoupled look-back: seconds closed before this chunk
+            const int g = m.seg;
+            const long long lc = c - p.seg_first_chunk[g];
             int base_sec = 0;
             if (lc == 0) {
                 base_sec = p.seg_sec[g];
             } else {
-                // publish the aggregate first so successors never wait on our own look-back
-                if (lane == 0) atomicExch(&p.state[c], (1ull << 32) | (unsigned)total_eos);
-                const long long first = c - lc;       // first chunk of the segment: always inclusive
+                // aggregate first (plain 64-bit store: self-contained record, nothing to wait for)
+                if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(&p.state[c]) = (1ull << 32) | (unsigned)n_eos;
+                const long long first = c - lc;
                 long long q = c - 1;
                 int acc = 0;
                 for (;;) {
                     const long long idx = q - lane;
                     const bool valid = idx >= first;
-                    unsigned long long st = 0;
+                    unsigned long long sv = 0;
                     if (valid) {
-                        do { st = *reinterpret_cast<volatile unsigned long long *>(&p.state[idx]); } while ((st >> 32) == 0);
+                        do { sv = *reinterpret_cast<volatile unsigned long long *>(&p.state[idx]); } while ((sv >> 32) == 0);
                     }
-                    const unsigned incl = __ballot_sync(0xffffffffu, valid && (st >> 32) == 2);
+                    const unsigned incl = __ballot_sync(0xffffffffu, valid && (sv >> 32) == 2);
                     int v;
                     if (incl) {
-                        const int stop = __ffs(incl) - 1;           // nearest predecessor holding a prefix
-                        v = (lane <= stop) ? (int)(unsigned)st : 0;
+                        const int stop = __ffs(incl) - 1;
+                        v = (lane <= stop) ? (int)(unsigned)sv : 0;
                     } else {
-                        v = valid ? (int)(unsigned)st : 0;
+                        v = valid ? (int)(unsigned)sv : 0;
                     }
 #pragma unroll
                     for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -202,71 +217,114 @@ __global__ void __launch_bounds__(DEC_THREADS, 2) decode_kernel(DecParams p) {
                 base_sec = acc;
             }
             if (lane == 0) {
-                // the record is self-contained (flag and value in one 64-bit word): no fence needed
-                atomicExch(&p.state[c], (2ull << 32) | (unsigned)(base_sec + total_eos));
-                s_secbase = base_sec;
-                if (last_chunk && p.seg_sec_out) p.seg_sec_out[g] = base_sec + total_eos;
+                *reinterpret_cast<volatile unsigned long long *>(&p.state[c]) = (2ull << 32) | (unsigned)(base_sec + n_eos);
+                m.base_sec = base_sec;
+                m.n_eos = n_eos;
+                if (m.last_chunk && p.seg_sec_out) p.seg_sec_out[g] = base_sec + n_eos;
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_ready[ss]);       // release: meta + data are ready for the workers
         }
-        __syncthreads();
-        const int sec_base = s_secbase;
-
-        // ---- bin
-        unsigned n_eos = 0, n_bad = 0, n_nonpix = 0, n_ign = 0, n_ok = 0;
+    } else {
+        // =========================== worker warps ===========================
+        unsigned n_eos_t = 0, n_bad = 0, n_nonpix = 0, n_ign = 0, n_ok = 0;
+        // stages are visited round-robin; a stage whose scout ran out of tickets is dead for good.  The
+        // scouts may draw their first tickets in any order, so a dead stage does not end the loop: it
+        // ends when all stages are dead.
+        int dead = 0, n_proc = 0;
+        for (int k = 0; dead != (1 << DEC_STAGES) - 1; ++k) {
+            const int st = k % DEC_STAGES;
+            if ((dead >> st) & 1) continue;
+            mk_mbar_wait(&s_ready[st], (k / DEC_STAGES) & 1);
+            const StageMeta &m = s_meta[st];
+            if (m.chunk < 0) { dead |= 1 << st; continue; }
+            const int roach = m.roach, sec_base = m.base_sec, n_here = m.n_here, n_eos = m.n_eos;
+            uint32_t *cnt = s_cnt[n_proc & 1];
+            ++n_proc;
+            const uint4 *sm = reinterpret_cast<const uint4 *>(s_ring + (size_t)st * DEC_STAGE_BYTES);
+            // 16 words per thread, 16 B per lane per access; everything on 32-bit halves
+            const bool f_hi = p.field_shift >= 32;
+            const int f_sh = p.field_shift & 31;
 #pragma unroll
-        for (int k = 0; k < DEC_WPT; ++k) {
-            if (pos_of(k) >= n_here) continue;
-            const uint64_t x = w[k];
-            const int l = rbase[k / S] + __popc((eos_bits >> ((k / S) * S)) & ((1u << (k % S)) - 1));
-            const int sec = sec_base + l;
-            const uint32_t adr = (uint32_t)(x >> 56);
-            if (sec >= p.exptime) { ++n_ign; continue; }
-            if (adr == 255u) {
-                ++n_eos;
-                if (x != ~0ull) ++n_bad;
-                continue;
-            }
-            if ((int)adr >= p.npix_per_roach) { ++n_nonpix; continue; }
-            ++n_ok;
-            if (l == 0) atomicAdd(&s_cnt[adr], 1u);
-            else atomicAdd(&p.counts[(size_t)sec * n_pix + roach * p.npix_per_roach + adr], 1u);
-            if (p.hist) {
-                uint32_t f = (uint32_t)(x >> p.field_shift) & 0xFFFu;
-                uint32_t b = use_lut ? s_lut[f] : f;
-                if ((int)b < p.n_bins) {
-                    if (SMEM_HIST) atomicAdd(&s_hist[adr * p.n_bins + b], 1u);
-                    else atomicAdd(&p.hist[((size_t)(roach * p.npix_per_roach + adr)) * p.n_bins + b], 1u);
+            for (int i = 0; i < (WIRE ? DEC_WPT / 4 : DEC_WPT / 2); ++i) {
+                uint32_t whi[WIRE ? 4 : 2], wlo[WIRE ? 4 : 2];
+                int pos0;
+                if (WIRE) {
+                    const uint4 l = sm[i * DEC_WORKERS + tid], h = sm[DEC_CHUNK / 4 + i * DEC_WORKERS + tid];
+                    whi[0] = bswap32(h.x); whi[1] = bswap32(h.y); whi[2] = bswap32(h.z); whi[3] = bswap32(h.w);
+                    wlo[0] = bswap32(l.x); wlo[1] = bswap32(l.y); wlo[2] = bswap32(l.z); wlo[3] = bswap32(l.w);
+                    pos0 = (i * DEC_WORKERS + tid) * 4;
+                } else {
+                    const uint4 v = sm[i * DEC_WORKERS + tid];
+                    wlo[0] = v.x; whi[0] = v.y; wlo[1] = v.z; whi[1] = v.w;
+                    pos0 = (i * DEC_WORKERS + tid) * 2;
+                }
+#pragma unroll
+                for (int j = 0; j < (WIRE ? 4 : 2); ++j) {
+                    const int pos = pos0 + j;
+                    if (pos >= n_here) continue;
+                    const uint32_t hi = whi[j], lo = wlo[j];
+                    int l = 0;                                   // seconds closed inside the chunk before this word
+                    if (n_eos) {
+                        if (n_eos <= DEC_MAX_EOS) {
+                            for (int e = 0; e < n_eos; ++e) l += m.eos_pos[e] < pos;
+                        } else {                                 // pathological: rescan the chunk prefix
+                            for (int q = 0; q < pos; ++q) {
+                                if (WIRE) l += (reinterpret_cast<const uint32_t *>(sm)[DEC_CHUNK + q] & 0xFFu) == 0xFFu;
+                                else l += (reinterpret_cast<const uint32_t *>(sm)[2 * q + 1] >> 24) == 0xFFu;
+                            }
+                        }
+                    }
+                    const int sec = sec_base + l;
+                    const uint32_t adr = hi >> 24;
+                    if (sec >= p.exptime) { ++n_ign; continue; }
+                    if (adr == 255u) { ++n_eos_t; if ((hi & lo) != 0xFFFFFFFFu) ++n_bad; continue; }
+                    if ((int)adr >= p.npix_per_roach) { ++n_nonpix; continue; }
+                    ++n_ok;
+                    if (l == 0) atomicAdd(&cnt[adr], 1u);
+                    else atomicAdd(&p.counts[(size_t)sec * n_pix + roach * p.npix_per_roach + adr], 1u);
+                    if (p.hist) {
+                        const uint32_t f = ((f_hi ? hi : lo) >> f_sh) & 0xFFFu;
+                        const uint32_t b = use_lut ? s_lut[f] : f;
+                        if ((int)b < p.n_bins) {
+                            if (SMEM_HIST) atomicAdd(&s_hist[adr * p.n_bins + b], 1u);
+                            else atomicAdd(&p.hist[((size_t)(roach * p.npix_per_roach + adr)) * p.n_bins + b], 1u);
+                        }
+                    }
                 }
             }
+            // this thread no longer needs the ring slot
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[st]);
+            workers_sync();                                   // all counts of this chunk are in cnt[]
+            if (sec_base < p.exptime && tid < p.npix_per_roach) {
+                const uint32_t v = cnt[tid];
+                if (v) atomicAdd(&p.counts[(size_t)sec_base * n_pix + roach * p.npix_per_roach + tid], v);
+            }
+            if (tid < 256) cnt[tid] = 0;                      // reused two chunks later (a barrier lies in between)
+            if (SMEM_HIST && p.hist) {
+                const int n = p.npix_per_roach * p.n_bins;
+                for (int i = tid; i < n; i += DEC_WORKERS) {
+                    const uint32_t v = s_hist[i];
+                    if (v) { atomicAdd(&p.hist[(size_t)roach * n + i], v); s_hist[i] = 0; }
+                }
+                workers_sync();                               // s_hist is shared by consecutive chunks
+            }
         }
-        // stats: warp reduce then one smem atomic per warp
 #pragma unroll
         for (int d = 16; d > 0; d >>= 1) {
-            n_eos += __shfl_xor_sync(0xffffffffu, n_eos, d);
+            n_eos_t += __shfl_xor_sync(0xffffffffu, n_eos_t, d);
             n_bad += __shfl_xor_sync(0xffffffffu, n_bad, d);
             n_nonpix += __shfl_xor_sync(0xffffffffu, n_nonpix, d);
             n_ign += __shfl_xor_sync(0xffffffffu, n_ign, d);
             n_ok += __shfl_xor_sync(0xffffffffu, n_ok, d);
         }
         if (lane == 0) {
-            if (n_eos) atomicAdd(&s_stat[0], (unsigned long long)n_eos);
+            if (n_eos_t) atomicAdd(&s_stat[0], (unsigned long long)n_eos_t);
             if (n_bad) atomicAdd(&s_stat[1], (unsigned long long)n_bad);
             if (n_nonpix) atomicAdd(&s_stat[2], (unsigned long long)n_nonpix);
             if (n_ign) atomicAdd(&s_stat[3], (unsigned long long)n_ign);
             if (n_ok) atomicAdd(&s_stat[4], (unsigned long long)n_ok);
-        }
-        __syncthreads();
-        // ---- flush the privatised counters of this chunk
-        if (sec_base < p.exptime && tid < p.npix_per_roach && tid < 256) {
-            uint32_t v = s_cnt[tid];
-            if (v) atomicAdd(&p.counts[(size_t)sec_base * n_pix + roach * p.npix_per_roach + tid], v);
-        }
-        if (SMEM_HIST && p.hist) {
-            const int n = p.npix_per_roach * p.n_bins;
-            for (int i = tid; i < n; i += DEC_THREADS) {
-                uint32_t v = s_hist[i];
-                if (v) atomicAdd(&p.hist[(size_t)roach * n + i], v);
-            }
         }
     }
     __syncthreads();
@@ -335,7 +393,7 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
         seg_len[i] = len;
         MKID_REQUIRE(ctx, len >= 0 && seg_offset[i] >= 0 && seg_offset[i] + len <= n_units, "segment offsets out of range");
         MKID_REQUIRE(ctx, seg_roach[i] >= 0 && seg_roach[i] < cfg->n_roaches, "segment roach out of range");
-        first_chunk[i + 1] = first_chunk[i] + (wire_fmt ? 2 * len : (len + DEC_CHUNK - 1) / DEC_CHUNK);
+        first_chunk[i + 1] = first_chunk[i] + (wire_fmt ? len : (len + DEC_CHUNK - 1) / DEC_CHUNK);
     }
     const int64_t n_chunks = first_chunk[n_seg];
     std::vector<int32_t> sec0(n_seg, 0);
@@ -408,14 +466,18 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
 
     if (n_chunks > 0) {
         const bool smem_hist = want_hist && (int64_t)cfg->npix_per_roach * cfg->n_bins <= DEC_SMEM_HIST;
-        int grid = (int)std::min<int64_t>(n_chunks, (int64_t)ctx->num_sms * 2);   // persistent, 2 CTAs of 512 threads per SM
-        if (wire_fmt) {
-            if (smem_hist) decode_kernel<true, true><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
-            else decode_kernel<true, false><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
-        } else {
-            if (smem_hist) decode_kernel<false, true><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
-            else decode_kernel<false, false><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
-        }
+        int grid = (int)std::min<int64_t>(n_chunks, (int64_t)ctx->num_sms);   // persistent: one CTA per SM
+        const size_t dyn = (size_t)DEC_STAGES * DEC_STAGE_BYTES;
+        auto launch = [&](auto kern) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+            if (e != cudaSuccess) return e;
+            kern<<<grid, DEC_THREADS, dyn, ctx->stream>>>(p);
+            return cudaSuccess;
+        };
+        cudaError_t le;
+        if (wire_fmt) le = smem_hist ? launch(decode_kernel<true, true>) : launch(decode_kernel<true, false>);
+        else le = smem_hist ? launch(decode_kernel<false, true>) : launch(decode_kernel<false, false>);
+        MKID_CUDA(ctx, le);
         MKID_CHECK_LAUNCH(ctx);
     }
     rc = mkid_stage_out_finish(ctx, counts_raw, counts_bytes, d_counts);
