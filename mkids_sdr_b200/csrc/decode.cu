@@ -3,10 +3,10 @@
 // Replaces the receive/bin loop of DataReadout/ReadoutControls/lib/PacketMaster.c:286-397 and
 // the per-word unpack of DataReadout/ChannelizerControls/ROACH_Pulses.py:795-832.
 //
-// HBM-bound integer work: every word is read exactly once (8 B/word).  A chunk is 8192 words
-// (64 KiB = one PulseServer bundle, PacketMaster.c:42-44).  One persistent, warp-specialised CTA
+// HBM-bound integer work: every word is read exactly once (8 B/word).  A chunk is 4096 words
+// (32 KiB = half a PulseServer bundle, PacketMaster.c:42-44).  One persistent, warp-specialised CTA
 // per SM:
-//   3 scout warps        one per stage of a 3 x 64 KiB shared-memory ring: take a chunk from an ordered
+//   6 scout warps        one per stage of a 6 x 32 KiB shared-memory ring: take a chunk from an ordered
 //                        ticket, stream it in with 1-D TMA bulk copies (mbarrier completion), count its
 //                        end-of-second words as soon as it has landed, publish that count and resolve
 //                        "seconds closed before this chunk" with a decoupled look-back over the published
@@ -15,16 +15,18 @@
 //                        through a per-chunk shared-memory histogram (double buffered, one named
 //                        barrier per chunk), pulse-height histogram through shared memory when it is
 //                        small, else global reductions.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace {
 
 constexpr int DEC_WORKERS = 512;                   // worker threads
-constexpr int DEC_THREADS = DEC_WORKERS + 32 * 3;  // + one producer/scout warp per ring stage
-constexpr int DEC_CHUNK = 8192;                    // words per chunk
+constexpr int DEC_THREADS = DEC_WORKERS + 32 * 6;  // + one producer/scout warp per ring stage
+constexpr int DEC_CHUNK = 4096;                    // words per chunk (wire format: half a bundle)
 constexpr int DEC_BUNDLE = 8192;                   // PacketMaster.c:44 BUFSIZE_INTS
-constexpr int DEC_WPT = DEC_CHUNK / DEC_WORKERS;   // 16 words per worker thread
-constexpr int DEC_STAGES = 3;
+constexpr int DEC_WPT = DEC_CHUNK / DEC_WORKERS;   // 8 words per worker thread
+constexpr int DEC_STAGES = 6;
 constexpr int DEC_STAGE_BYTES = DEC_CHUNK * 8;
 constexpr int DEC_SMEM_HIST = 4096;                // smem-privatised histogram entries
 constexpr int DEC_MAX_EOS = 64;                    // end-of-second positions kept per chunk (more: slow path)
@@ -48,6 +50,7 @@ struct DecParams {
     unsigned long long *stats; // 5 x u64
     unsigned long long *state; // [n_chunks] look-back records
     unsigned int *ticket;
+    unsigned long long *prof;  // optional [8] cycle accumulators (MKID_DEC_PROFILE=1): see decode_common
 };
 
 struct StageMeta {
@@ -98,10 +101,15 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(DecParams p) {
         const int ss = warp - DEC_WORKERS / 32;
         StageMeta &m = s_meta[ss];
         for (int r = 0;; ++r) {                              // r-th use of this stage
+            // (the ticket must not be drawn before the stage is free: a held ticket stalls the look-back of
+            // every later chunk)
+            long long t0 = p.prof ? clock64() : 0;
             if (r > 0) mk_mbar_wait(&s_empty[ss], (r - 1) & 1);
+            long long t1 = p.prof ? clock64() : 0;
             long long c = 0;
             if (lane == 0) c = (long long)atomicAdd(p.ticket, 1u);
             c = __shfl_sync(0xffffffffu, c, 0);
+            long long t2 = p.prof ? clock64() : 0;
             if (c >= p.n_chunks) {                           // no more work for this stage, ever (sticky)
                 if (lane == 0) { m.chunk = -1; mbar_arrive(&s_ready[ss]); }
                 break;
@@ -116,8 +124,9 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(DecParams p) {
                 const long long lc = c - p.seg_first_chunk[g];
                 const unsigned char *src;
                 int n_here = DEC_CHUNK;
-                if (WIRE) {
-                    src = reinterpret_cast<const unsigned char *>(p.wire) + (size_t)(p.seg_offset[g] + lc) * DEC_STAGE_BYTES;
+                if (WIRE) {   // chunk lc = half (lc & 1) of bundle lc >> 1: its low halves; the high halves are 32 KiB further
+                    src = reinterpret_cast<const unsigned char *>(p.wire) + (size_t)(p.seg_offset[g] + (lc >> 1)) * (DEC_BUNDLE * 8) +
+                          (size_t)(lc & 1) * (DEC_CHUNK * 4);
                 } else {
                     const long long rem = p.seg_len[g] - lc * DEC_CHUNK;
                     n_here = rem < DEC_CHUNK ? (int)rem : DEC_CHUNK;
@@ -130,10 +139,15 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(DecParams p) {
                     m.last_chunk = (c + 1 == p.seg_first_chunk[g + 1]);
                     if (tma) {
                         mk_mbar_expect_tx(&s_full[ss], DEC_STAGE_BYTES);
+                        if (WIRE) {
+                            mk_bulk_g2s(dst, src, DEC_STAGE_BYTES / 2, &s_full[ss]);
+                            mk_bulk_g2s(dst + DEC_STAGE_BYTES / 2, src + DEC_BUNDLE * 4, DEC_STAGE_BYTES / 2, &s_full[ss]);
+                        } else {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q)
-                            mk_bulk_g2s(dst + q * (DEC_STAGE_BYTES / 4), src + q * (DEC_STAGE_BYTES / 4),
-                                        DEC_STAGE_BYTES / 4, &s_full[ss]);
+                            for (int q = 0; q < 2; ++q)
+                                mk_bulk_g2s(dst + q * (DEC_STAGE_BYTES / 2), src + q * (DEC_STAGE_BYTES / 2),
+                                            DEC_STAGE_BYTES / 2, &s_full[ss]);
+                        }
                     }
                 }
                 if (!tma) {   // ragged tail / odd alignment (flat format only): the warp copies it, zero padded
@@ -146,27 +160,29 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(DecParams p) {
             }
             __syncwarp();
             mk_mbar_wait(&s_full[ss], r & 1);
+            long long t3 = p.prof ? clock64() : 0;
             // count end-of-second words (channel field 255) and remember their positions, in order.
-            // Fast path: 8 x 128-bit loads per lane in flight, one ballot per batch; the ordered position
+            // Fast path: 16 x 128-bit loads per lane in flight, one ballot per batch; the ordered position
             // list is only built for batches that contain an end-of-second word (rare).
             const unsigned char *base = s_ring + (size_t)ss * DEC_STAGE_BYTES;
             const uint4 *scan = reinterpret_cast<const uint4 *>(WIRE ? base + DEC_STAGE_BYTES / 2 : base);
             constexpr int SCAN_IT = (WIRE ? DEC_STAGE_BYTES / 2 : DEC_STAGE_BYTES) / 16 / 32;   // uint4 iterations per lane
             constexpr int POS_PER_IT = WIRE ? 128 : 64;                                       // positions covered by one iteration
             int n_eos = 0;
-            for (int i0 = 0; i0 < SCAN_IT; i0 += 8) {
-                uint4 v[8];
+            constexpr int SB = 16;                           // 128-bit loads in flight per lane
+            for (int i0 = 0; i0 < SCAN_IT; i0 += SB) {
+                uint4 v[SB];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = scan[(i0 + u) * 32 + lane];
+                for (int u = 0; u < SB; ++u) v[u] = scan[(i0 + u) * 32 + lane];
                 bool any = false;
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < SB; ++u) {
                     if (WIRE) any |= ((v[u].x & 0xFFu) == 0xFFu) | ((v[u].y & 0xFFu) == 0xFFu) | ((v[u].z & 0xFFu) == 0xFFu) | ((v[u].w & 0xFFu) == 0xFFu);
                     else any |= ((v[u].y >> 24) == 0xFFu) | ((v[u].w >> 24) == 0xFFu);
                 }
                 if (__ballot_sync(0xffffffffu, any)) {
                     // position-ordered pass over this batch (zero padding beyond n_here is never an EOS word)
-                    const int p0 = i0 * POS_PER_IT, p1 = p0 + 8 * POS_PER_IT;
+                    const int p0 = i0 * POS_PER_IT, p1 = p0 + SB * POS_PER_IT;
                     for (int pb = p0; pb < p1; pb += 32) {
                         const int pos = pb + lane;
                         bool is_eos;
@@ -181,6 +197,7 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(DecParams p) {
                     }
                 }
             }
+            long long t4 = p.prof ? clock64() : 0;
             // decoupled look-back: seconds closed before this chunk
             const int g = m.seg;
             const long long lc = c - p.seg_first_chunk[g];
@@ -194,25 +211,36 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(DecParams p) {
                 long long q = c - 1;
                 int acc = 0;
                 for (;;) {
-                    const long long idx = q - lane;
-                    const bool valid = idx >= first;
-                    unsigned long long sv = 0;
-                    if (valid) {
-                        do { sv = *reinterpret_cast<volatile unsigned long long *>(&p.state[idx]); } while ((sv >> 32) == 0);
-                    }
-                    const unsigned incl = __ballot_sync(0xffffffffu, valid && (sv >> 32) == 2);
-                    int v;
-                    if (incl) {
-                        const int stop = __ffs(incl) - 1;
-                        v = (lane <= stop) ? (int)(unsigned)sv : 0;
-                    } else {
-                        v = valid ? (int)(unsigned)sv : 0;
-                    }
+                    // 128 predecessors per round: lane l looks at q - l - 32*j, j = 0..3 (nearest first)
+                    unsigned long long sv[4];
+                    bool valid[4];
 #pragma unroll
-                    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                    acc += v;
-                    if (incl) break;
-                    q -= 32;
+                    for (int j = 0; j < 4; ++j) {
+                        const long long idx = q - lane - 32 * j;
+                        valid[j] = idx >= first;
+                        sv[j] = valid[j] ? *reinterpret_cast<volatile unsigned long long *>(&p.state[idx]) : 0ull;
+                    }
+                    bool stop_found = false;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (stop_found) break;
+                        const long long idx = q - lane - 32 * j;
+                        while (valid[j] && (sv[j] >> 32) == 0) sv[j] = *reinterpret_cast<volatile unsigned long long *>(&p.state[idx]);
+                        const unsigned incl = __ballot_sync(0xffffffffu, valid[j] && (sv[j] >> 32) == 2);
+                        int v;
+                        if (incl) {
+                            const int stop = __ffs(incl) - 1;           // nearest predecessor holding a prefix
+                            v = (lane <= stop) ? (int)(unsigned)sv[j] : 0;
+                            stop_found = true;
+                        } else {
+                            v = valid[j] ? (int)(unsigned)sv[j] : 0;
+                        }
+#pragma unroll
+                        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+                        acc += v;
+                    }
+                    if (stop_found) break;
+                    q -= 128;
                 }
                 base_sec = acc;
             }
@@ -224,6 +252,15 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(DecParams p) {
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&s_ready[ss]);       // release: meta + data are ready for the workers
+            if (p.prof && lane == 0) {
+                const long long t5 = clock64();
+                atomicAdd(&p.prof[0], (unsigned long long)(t1 - t0));   // scout: wait for a free stage
+                atomicAdd(&p.prof[1], (unsigned long long)(t2 - t1));   // ticket
+                atomicAdd(&p.prof[2], (unsigned long long)(t3 - t2));   // load issue + data arrival
+                atomicAdd(&p.prof[3], (unsigned long long)(t4 - t3));   // EOS scan
+                atomicAdd(&p.prof[4], (unsigned long long)(t5 - t4));   // look-back + publish
+                atomicAdd(&p.prof[7], 1ull);
+            }
         }
     } else {
         // =========================== worker warps ===========================
@@ -235,60 +272,106 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(DecParams p) {
         for (int k = 0; dead != (1 << DEC_STAGES) - 1; ++k) {
             const int st = k % DEC_STAGES;
             if ((dead >> st) & 1) continue;
+            long long w0 = p.prof ? clock64() : 0;
             mk_mbar_wait(&s_ready[st], (k / DEC_STAGES) & 1);
+            long long w1 = p.prof ? clock64() : 0;
             const StageMeta &m = s_meta[st];
             if (m.chunk < 0) { dead |= 1 << st; continue; }
             const int roach = m.roach, sec_base = m.base_sec, n_here = m.n_here, n_eos = m.n_eos;
             uint32_t *cnt = s_cnt[n_proc & 1];
             ++n_proc;
             const uint4 *sm = reinterpret_cast<const uint4 *>(s_ring + (size_t)st * DEC_STAGE_BYTES);
-            // 16 words per thread, 16 B per lane per access; everything on 32-bit halves
-            const bool f_hi = p.field_shift >= 32;
-            const int f_sh = p.field_shift & 31;
+            if (n_here == DEC_CHUNK && n_eos == 0 && sec_base < p.exptime) {
+                // fast path (almost every chunk): full chunk, no second boundary inside, all words live
+                const bool f_hi = p.field_shift >= 32;
+                const int f_sh = p.field_shift & 31;
+                const int npix = p.npix_per_roach;
+                uint32_t *hist_r = p.hist ? p.hist + (size_t)roach * npix * p.n_bins : nullptr;
 #pragma unroll
-            for (int i = 0; i < (WIRE ? DEC_WPT / 4 : DEC_WPT / 2); ++i) {
-                uint32_t whi[WIRE ? 4 : 2], wlo[WIRE ? 4 : 2];
-                int pos0;
-                if (WIRE) {
-                    const uint4 l = sm[i * DEC_WORKERS + tid], h = sm[DEC_CHUNK / 4 + i * DEC_WORKERS + tid];
-                    whi[0] = bswap32(h.x); whi[1] = bswap32(h.y); whi[2] = bswap32(h.z); whi[3] = bswap32(h.w);
-                    wlo[0] = bswap32(l.x); wlo[1] = bswap32(l.y); wlo[2] = bswap32(l.z); wlo[3] = bswap32(l.w);
-                    pos0 = (i * DEC_WORKERS + tid) * 4;
-                } else {
-                    const uint4 v = sm[i * DEC_WORKERS + tid];
-                    wlo[0] = v.x; whi[0] = v.y; wlo[1] = v.z; whi[1] = v.w;
-                    pos0 = (i * DEC_WORKERS + tid) * 2;
-                }
+                for (int i = 0; i < (WIRE ? DEC_WPT / 4 : DEC_WPT / 2); ++i) {
+                    uint32_t whi[WIRE ? 4 : 2], wlo[WIRE ? 4 : 2];
+                    if (WIRE) {
+                        const uint4 l = sm[i * DEC_WORKERS + tid], h = sm[DEC_CHUNK / 4 + i * DEC_WORKERS + tid];
+                        whi[0] = bswap32(h.x); whi[1] = bswap32(h.y); whi[2] = bswap32(h.z); whi[3] = bswap32(h.w);
+                        wlo[0] = bswap32(l.x); wlo[1] = bswap32(l.y); wlo[2] = bswap32(l.z); wlo[3] = bswap32(l.w);
+                    } else {
+                        const uint4 v = sm[i * DEC_WORKERS + tid];
+                        wlo[0] = v.x; whi[0] = v.y; wlo[1] = v.z; whi[1] = v.w;
+                    }
 #pragma unroll
-                for (int j = 0; j < (WIRE ? 4 : 2); ++j) {
-                    const int pos = pos0 + j;
-                    if (pos >= n_here) continue;
-                    const uint32_t hi = whi[j], lo = wlo[j];
-                    int l = 0;                                   // seconds closed inside the chunk before this word
-                    if (n_eos) {
-                        if (n_eos <= DEC_MAX_EOS) {
-                            for (int e = 0; e < n_eos; ++e) l += m.eos_pos[e] < pos;
-                        } else {                                 // pathological: rescan the chunk prefix
-                            for (int q = 0; q < pos; ++q) {
-                                if (WIRE) l += (reinterpret_cast<const uint32_t *>(sm)[DEC_CHUNK + q] & 0xFFu) == 0xFFu;
-                                else l += (reinterpret_cast<const uint32_t *>(sm)[2 * q + 1] >> 24) == 0xFFu;
+                    for (int j = 0; j < (WIRE ? 4 : 2); ++j) {
+                        const uint32_t hi = whi[j], lo = wlo[j];
+                        const uint32_t adr = hi >> 24;
+                        if ((int)adr >= npix) { ++n_nonpix; --n_ok; continue; }   // (adr == 255 cannot occur: n_eos == 0)
+                        if (SMEM_HIST) {
+                            // one shared atomic per word: row adr, column = bin or the overflow column n_bins;
+                            // the per-pixel count is the row sum (taken at the flush)
+                            const uint32_t f = ((f_hi ? hi : lo) >> f_sh) & 0xFFFu;
+                            const uint32_t b = use_lut ? s_lut[f] : f;
+                            atomicAdd(&s_hist[adr * (p.n_bins + 1) + min((int)b, p.n_bins)], 1u);
+                        } else {
+                            atomicAdd(&cnt[adr], 1u);
+                            if (hist_r) {
+                                const uint32_t f = ((f_hi ? hi : lo) >> f_sh) & 0xFFFu;
+                                const uint32_t b = use_lut ? s_lut[f] : f;
+                                if ((int)b < p.n_bins) atomicAdd(&hist_r[adr * p.n_bins + b], 1u);
                             }
                         }
                     }
-                    const int sec = sec_base + l;
-                    const uint32_t adr = hi >> 24;
-                    if (sec >= p.exptime) { ++n_ign; continue; }
-                    if (adr == 255u) { ++n_eos_t; if ((hi & lo) != 0xFFFFFFFFu) ++n_bad; continue; }
-                    if ((int)adr >= p.npix_per_roach) { ++n_nonpix; continue; }
-                    ++n_ok;
-                    if (l == 0) atomicAdd(&cnt[adr], 1u);
-                    else atomicAdd(&p.counts[(size_t)sec * n_pix + roach * p.npix_per_roach + adr], 1u);
-                    if (p.hist) {
-                        const uint32_t f = ((f_hi ? hi : lo) >> f_sh) & 0xFFFu;
-                        const uint32_t b = use_lut ? s_lut[f] : f;
-                        if ((int)b < p.n_bins) {
-                            if (SMEM_HIST) atomicAdd(&s_hist[adr * p.n_bins + b], 1u);
-                            else atomicAdd(&p.hist[((size_t)(roach * p.npix_per_roach + adr)) * p.n_bins + b], 1u);
+                }
+                n_ok += DEC_WPT;          // corrected by the non-pixel words below
+            } else {
+                // 16 words per thread, 16 B per lane per access; everything on 32-bit halves
+                const bool f_hi = p.field_shift >= 32;
+                const int f_sh = p.field_shift & 31;
+    #pragma unroll
+                for (int i = 0; i < (WIRE ? DEC_WPT / 4 : DEC_WPT / 2); ++i) {
+                    uint32_t whi[WIRE ? 4 : 2], wlo[WIRE ? 4 : 2];
+                    int pos0;
+                    if (WIRE) {
+                        const uint4 l = sm[i * DEC_WORKERS + tid], h = sm[DEC_CHUNK / 4 + i * DEC_WORKERS + tid];
+                        whi[0] = bswap32(h.x); whi[1] = bswap32(h.y); whi[2] = bswap32(h.z); whi[3] = bswap32(h.w);
+                        wlo[0] = bswap32(l.x); wlo[1] = bswap32(l.y); wlo[2] = bswap32(l.z); wlo[3] = bswap32(l.w);
+                        pos0 = (i * DEC_WORKERS + tid) * 4;
+                    } else {
+                        const uint4 v = sm[i * DEC_WORKERS + tid];
+                        wlo[0] = v.x; whi[0] = v.y; wlo[1] = v.z; whi[1] = v.w;
+                        pos0 = (i * DEC_WORKERS + tid) * 2;
+                    }
+    #pragma unroll
+                    for (int j = 0; j < (WIRE ? 4 : 2); ++j) {
+                        const int pos = pos0 + j;
+                        if (pos >= n_here) continue;
+                        const uint32_t hi = whi[j], lo = wlo[j];
+                        int l = 0;                                   // seconds closed inside the chunk before this word
+                        if (n_eos) {
+                            if (n_eos <= DEC_MAX_EOS) {
+                                for (int e = 0; e < n_eos; ++e) l += m.eos_pos[e] < pos;
+                            } else {                                 // pathological: rescan the chunk prefix
+                                for (int q = 0; q < pos; ++q) {
+                                    if (WIRE) l += (reinterpret_cast<const uint32_t *>(sm)[DEC_CHUNK + q] & 0xFFu) == 0xFFu;
+                                    else l += (reinterpret_cast<const uint32_t *>(sm)[2 * q + 1] >> 24) == 0xFFu;
+                                }
+                            }
+                        }
+                        const int sec = sec_base + l;
+                        const uint32_t adr = hi >> 24;
+                        if (sec >= p.exptime) { ++n_ign; continue; }
+                        if (adr == 255u) { ++n_eos_t; if ((hi & lo) != 0xFFFFFFFFu) ++n_bad; continue; }
+                        if ((int)adr >= p.npix_per_roach) { ++n_nonpix; continue; }
+                        ++n_ok;
+                        uint32_t b = 0;
+                        if (p.hist) {
+                            const uint32_t f = ((f_hi ? hi : lo) >> f_sh) & 0xFFFu;
+                            b = use_lut ? s_lut[f] : f;
+                        }
+                        if (SMEM_HIST && l == 0) {
+                            atomicAdd(&s_hist[adr * (p.n_bins + 1) + min((int)b, p.n_bins)], 1u);
+                        } else {
+                            if (l == 0) atomicAdd(&cnt[adr], 1u);
+                            else atomicAdd(&p.counts[(size_t)sec * n_pix + roach * p.npix_per_roach + adr], 1u);
+                            if (p.hist && (int)b < p.n_bins)
+                                atomicAdd(&p.hist[((size_t)(roach * p.npix_per_roach + adr)) * p.n_bins + b], 1u);
                         }
                     }
                 }
@@ -303,12 +386,28 @@ __global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(DecParams p) {
             }
             if (tid < 256) cnt[tid] = 0;                      // reused two chunks later (a barrier lies in between)
             if (SMEM_HIST && p.hist) {
-                const int n = p.npix_per_roach * p.n_bins;
+                const int hs = p.n_bins + 1, n = p.npix_per_roach * hs;
+                if (tid < p.npix_per_roach) {                 // per-pixel count of this chunk = row sum (incl. overflow column)
+                    uint32_t sum = 0;
+                    for (int b = 0; b < hs; ++b) sum += s_hist[tid * hs + b];
+                    if (sum && sec_base < p.exptime)
+                        atomicAdd(&p.counts[(size_t)sec_base * n_pix + roach * p.npix_per_roach + tid], sum);
+                }
+                workers_sync();
                 for (int i = tid; i < n; i += DEC_WORKERS) {
                     const uint32_t v = s_hist[i];
-                    if (v) { atomicAdd(&p.hist[(size_t)roach * n + i], v); s_hist[i] = 0; }
+                    if (v) {
+                        const int pix = i / hs, b = i - pix * hs;
+                        if (b < p.n_bins) atomicAdd(&p.hist[((size_t)roach * p.npix_per_roach + pix) * p.n_bins + b], v);
+                        s_hist[i] = 0;
+                    }
                 }
                 workers_sync();                               // s_hist is shared by consecutive chunks
+            }
+            if (p.prof && tid == 0) {
+                const long long w2 = clock64();
+                atomicAdd(&p.prof[5], (unsigned long long)(w1 - w0));   // workers: wait for a ready chunk
+                atomicAdd(&p.prof[6], (unsigned long long)(w2 - w1));   // workers: process + flush
             }
         }
 #pragma unroll
@@ -393,7 +492,7 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
         seg_len[i] = len;
         MKID_REQUIRE(ctx, len >= 0 && seg_offset[i] >= 0 && seg_offset[i] + len <= n_units, "segment offsets out of range");
         MKID_REQUIRE(ctx, seg_roach[i] >= 0 && seg_roach[i] < cfg->n_roaches, "segment roach out of range");
-        first_chunk[i + 1] = first_chunk[i] + (wire_fmt ? len : (len + DEC_CHUNK - 1) / DEC_CHUNK);
+        first_chunk[i + 1] = first_chunk[i] + (wire_fmt ? 2 * len : (len + DEC_CHUNK - 1) / DEC_CHUNK);
     }
     const int64_t n_chunks = first_chunk[n_seg];
     std::vector<int32_t> sec0(n_seg, 0);
@@ -463,9 +562,17 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
     p.field_shift = want_hist ? cfg->hist_field_shift : 0; p.n_bins = want_hist ? cfg->n_bins : 0;
     p.bin_lut = (const uint16_t *)d_lut; p.counts = (uint32_t *)d_counts; p.hist = (uint32_t *)d_hist;
     p.stats = d_stats; p.state = d_state; p.ticket = d_ticket;
+    p.prof = nullptr;
+    static const bool want_prof = getenv("MKID_DEC_PROFILE") != nullptr;
+    if (want_prof) {
+        void *pb = nullptr;
+        if ((rc = mkid_scratch(ctx, SCR_AUX5, 64, &pb))) return rc;
+        MKID_CUDA(ctx, cudaMemsetAsync(pb, 0, 64, ctx->stream));
+        p.prof = (unsigned long long *)pb;
+    }
 
     if (n_chunks > 0) {
-        const bool smem_hist = want_hist && (int64_t)cfg->npix_per_roach * cfg->n_bins <= DEC_SMEM_HIST;
+        const bool smem_hist = want_hist && (int64_t)cfg->npix_per_roach * (cfg->n_bins + 1) <= DEC_SMEM_HIST;
         int grid = (int)std::min<int64_t>(n_chunks, (int64_t)ctx->num_sms);   // persistent: one CTA per SM
         const size_t dyn = (size_t)DEC_STAGES * DEC_STAGE_BYTES;
         auto launch = [&](auto kern) -> cudaError_t {
@@ -479,6 +586,15 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
         else le = smem_hist ? launch(decode_kernel<false, true>) : launch(decode_kernel<false, false>);
         MKID_CUDA(ctx, le);
         MKID_CHECK_LAUNCH(ctx);
+    }
+    if (p.prof) {
+        unsigned long long h[8];
+        MKID_CUDA(ctx, cudaMemcpyAsync(h, p.prof, 64, cudaMemcpyDeviceToHost, ctx->stream));
+        MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        const double n = h[7] ? (double)h[7] : 1.0;
+        fprintf(stderr, "[mkid decode profile] chunks %llu | scout cycles/chunk: wait-free %.0f ticket %.0f load %.0f scan %.0f "
+                        "lookback %.0f | workers cycles/chunk: wait-ready %.0f process %.0f\n", h[7], h[0] / n, h[1] / n,
+                h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n);
     }
     rc = mkid_stage_out_finish(ctx, counts_raw, counts_bytes, d_counts);
     if (rc) return rc;

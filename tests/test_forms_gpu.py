@@ -1,0 +1,117 @@
+"""GPU: the headless GUI twins (SetupForm / PulsesForm) behave like the reference's AppForm methods:
+same register traffic, same files, same numbers (oracle = restated reference lines)."""
+import os
+import struct
+
+import numpy as np
+import pytest
+
+from oracle import control, decode as odec, lut as olut
+
+pytestmark = pytest.mark.gpu
+FS = 512e6
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    from mkids_sdr_b200 import _lib
+    return _lib.default_context(0)
+
+
+def test_multitone_setup_to_pulses_roundtrip(ctx, tmp_path, golden_dir):
+    from mkids_sdr_b200.pulses_form import PulsesForm
+    from mkids_sdr_b200.setup_form import SetupForm
+    N = 2 ** 16
+    rng = np.random.default_rng(4)
+    lo = 5.0e9
+    k = np.sort(rng.choice(np.arange(-N // 2 + 100, N // 2 - 100), 60, replace=False))
+    freqs = [lo + float(v) * FS / N for v in k]
+    sf = SetupForm(N_lut_entries=N, multi_tone=True, ctx=ctx, LUT_saveDir=str(tmp_path))
+    sf.dac_freqs, sf.lo_freq = freqs, lo
+    sf.attens = rng.integers(0, 15, 60).astype(float)
+    sf.iq_centers = np.array([0. + 0j] * 256)
+    sf.iq_centers[:60] = rng.normal(0, 400, 60) + 1j * rng.normal(0, 400, 60)
+    sf.define_DAC_LUT()
+    sf.define_DDS_LUT([0.] * 256)
+    sf.write_LUTs()
+    sf.loadIQcenters()
+    # oracle: the same through the restated reference
+    fd = olut.dac_freqs_multi(freqs, lo, FS / N)
+    Io, Qo, so, _ = olut.freq_comb_lut('yes', fd, FS, FS / N, olut.dac_amplitudes(sf.attens))
+    assert sf.freqs_dac == fd and sf.scale_factor == so
+    assert np.array_equal(sf.I_dac, Io) and np.array_equal(sf.Q_dac, Qo)
+    bins, resid = olut.select_bins(olut.dds_freqs(freqs, lo, FS, FS / N), FS, FS / N)
+    Id, Qd, _ = olut.define_dds_lut(resid, FS, FS / N)
+    assert sf.fft_bins == bins and sf.freq_residuals == resid
+    assert np.array_equal(sf.I_dds, Id) and np.array_equal(sf.Q_dds, Qd)
+    assert sf.binaryData == olut.pack_dram(Io, Qo, Id, Qd)
+    assert sf.roach.writes('bins') == bins
+    assert sf.roach.writes('load_bins')[:4] == [1, 0, 3, 2]
+    # the channelizer GUI reloads the files
+    pf = PulsesForm(N_lut_entries=N, ctx=ctx)
+    pf.dac_freqs, pf.lo_freq, pf.lutDir = freqs, lo, str(tmp_path)
+    pf.loadLUTs()
+    assert pf.roach.mem['dram_memory'] == sf.binaryData
+    assert pf.fft_bins == bins
+    Id2, Qd2 = pf.dds_from_luts()
+    assert np.array_equal(Id2, Id) and np.array_equal(Qd2, Qd)
+    want = [control.iq_center_word(c)[0] for c in sf.iq_centers]
+    assert pf.roach.writes('conv_phase_centers') == want
+    # FIR registers (known answers of the shipped matched filter)
+    pf.importFIRcoeffs(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'mkids_sdr_b200', 'data',
+                                    'matched_30us.txt'))
+    pf.zeroChannels = [0] * 256
+    pf.zeroChannels[3] = 1
+    pf.loadFIRcoeffs()
+    regs = [r[2] for r in control.fir_registers(pf.fir)]
+    log = [(n, v) for op, n, v in pf.roach.log if op == 'write' and n.startswith('FIR_b')]
+    assert len(log) == 256 * 13
+    assert pf.fir_int == control.fir_quantise(pf.fir)
+    assert struct.unpack('>l', regs[0])[0] == 0x9B0A0
+
+
+def test_load_thresholds_golden_snapshot(ctx, golden_dir):
+    from mkids_sdr_b200.pulses_form import PulsesForm
+    deg = np.load(os.path.join(golden_dir, 'ch_snap_0.npy'))
+    raw = np.round(deg / control.SCALE_TO_ANGLE).astype(np.int64)            # 2048 Fix16_13 samples
+    pf = PulsesForm(ctx=ctx)
+    pf.dac_freqs = [1.0]
+    # snapPhase_bram: 1024 words, second sample in bytes [0:2], first in bytes [2:4] (ROACH_Pulses.py:251-253)
+    words = np.empty((1024, 2), dtype='>i2')
+    words[:, 1] = raw[0::2]; words[:, 0] = raw[1::2]
+    pf.roach.mem['snapPhase_bram'] = words.tobytes()
+    pf.loadThresholds(steps=1)
+    assert pf.thresholds_raw[0] == -5913
+    assert abs(pf.thresholds[0] - (-41.356194)) < 1e-5 and abs(pf.medians[0] - 132.619587) < 1e-5
+    assert pf.roach.writes('capture_threshold') == [-5913]
+    assert np.array_equal(control.decode_phase_snapshot(words.tobytes()), raw)
+
+
+def test_read_pulses_matches_reference_loop(ctx):
+    from mkids_sdr_b200.pulses_form import PulsesForm
+    rng = np.random.default_rng(11)
+    n = 2 ** 14
+    ch = rng.integers(0, 256, n)
+    w = odec.pack_word(ch, rng.integers(0, 4096, n), rng.integers(0, 4096, n), rng.integers(0, 4096, n),
+                       rng.integers(0, 2 ** 20, n))
+    b0 = (w & np.uint64(0xFFFFFFFF)).astype('>u4').tobytes()
+    b1 = (w >> np.uint64(32)).astype('>u4').tobytes()
+
+    class Roach:
+        def __init__(self, addrs): self.addrs = list(addrs)
+        def write_int(self, *a): pass
+        def read_int(self, name): return self.addrs.pop(0)
+        def read(self, name, size): return b0 if name == 'pulses_bram0' else b1
+
+    pairs = [(100, 5000), (16000, 300), (7, 7)]
+    pf = PulsesForm(roach=Roach([a for p in pairs for a in p]), ctx=ctx)
+    pf.channel = 3
+    cc = pf.readPulses(steps=3)
+    ref = odec.read_pulses([b0] * 3, [b1] * 3, pairs, sel_ch=3)
+    assert np.array_equal(cc, ref['channel_count'])
+    assert pf.total_counts == ref['total_counts']
+    for c in (0, 3, 77, 255):
+        assert pf.timestamp[c] == ref['timestamp'][c] and pf.baseline[c] == ref['baseline'][c]
+        assert pf.peaks[c] == ref['peaks'][c] and pf.p1[c] == ref['p1'][c]
+    assert np.array_equal(pf.hgBase, ref['hgBase']) and np.array_equal(pf.hgPeak, ref['hgPeak'])
+    assert np.array_equal(pf.hgPeakSubBase, ref['hgPeakSubBase'])
