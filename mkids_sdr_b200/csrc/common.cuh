@@ -25,6 +25,8 @@ struct mkid_ctx {
     // last segment table uploaded by the decode path (skips re-upload when unchanged)
     std::vector<char> dec_meta_host;
     void *dec_meta_dev = nullptr;
+    std::vector<char> dec_ranges_host;
+    void *dec_ranges_dev = nullptr;
     size_t l2_flush_bytes = 0;
 };
 

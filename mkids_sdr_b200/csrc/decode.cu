@@ -3,432 +3,474 @@
 // Replaces the receive/bin loop of DataReadout/ReadoutControls/lib/PacketMaster.c:286-397 and
 // the per-word unpack of DataReadout/ChannelizerControls/ROACH_Pulses.py:795-832.
 //
-// HBM-bound integer work: every word is read exactly once (8 B/word).  A chunk is 4096 words
-// (32 KiB = half a PulseServer bundle, PacketMaster.c:42-44).  One persistent, warp-specialised CTA
-// per SM:
-//   6 scout warps        one per stage of a 6 x 32 KiB shared-memory ring: take a chunk from an ordered
-//                        ticket, stream it in with 1-D TMA bulk copies (mbarrier completion), count its
-//                        end-of-second words as soon as it has landed, publish that count and resolve
-//                        "seconds closed before this chunk" with a decoupled look-back over the published
-//                        counts -- each scout has a full ring revolution to hide its L2 round trips;
-//   16 worker warps      unpack the bitfields from shared memory and bin: per-(second,pixel) counts
-//                        through a per-chunk shared-memory histogram (double buffered, one named
-//                        barrier per chunk), pulse-height histogram through shared memory when it is
-//                        small, else global reductions.
+// HBM-bound integer work: every word is read exactly once (8 B/word).  The only sequential dependency of
+// the reference loop is "seconds closed so far" (the number of end-of-second words earlier in the same
+// roach stream).  It is removed like this:
+//
+//   * the host cuts every segment into contiguous RANGES (whole 4096-word chunks, PacketMaster.c:42-44);
+//     there are about as many ranges as resident warps (148 SMs x 2 CTAs x 16 warps);
+//   * decode_stream_kernel<REL>: ONE WARP streams one range with 128-bit loads (two 2 KiB batches in flight per
+//     warp), bins into its own 256-entry shared-memory row, and counts seconds LOCALLY (0,1,2,... from the start
+//     of its range).  When an end-of-second word closes a local second the row is written to
+//     rows[range][local second] and cleared.  No warp ever waits for another warp or CTA: no barriers, no
+//     look-back, no tickets.
+//   * decode_prefix_kernel (1 CTA): segmented exclusive scan of the ranges' end-of-second totals
+//     -> absolute second at the start of every range (+ seg_sec_out).
+//   * decode_commit_kernel: rows[range][ls] -> counts[base+ls][pixel], statistics; rows that turn out to
+//     lie beyond exptime are dropped and their histogram contribution is taken back.
+//   * decode_stream_kernel<ABS> (gated on a device flag, normally exits at once): ranges with more than
+//     DEC_MAX_LS seconds are finished from the recorded resume point with the now known absolute second.
 #include <stdlib.h>
+
+#include <algorithm>
 
 #include "common.cuh"
 
 namespace {
 
-constexpr int DEC_WORKERS = 512;                   // worker threads
-constexpr int DEC_THREADS = DEC_WORKERS + 32 * 6;  // + one producer/scout warp per ring stage
+constexpr int DEC_WARPS = 16;                      // warps per CTA, each streams its own range
+constexpr int DEC_THREADS = DEC_WARPS * 32;
+constexpr int DEC_CTAS_PER_SM = 2;
 constexpr int DEC_CHUNK = 4096;                    // words per chunk (wire format: half a bundle)
 constexpr int DEC_BUNDLE = 8192;                   // PacketMaster.c:44 BUFSIZE_INTS
-constexpr int DEC_WPT = DEC_CHUNK / DEC_WORKERS;   // 8 words per worker thread
-constexpr int DEC_STAGES = 6;
-constexpr int DEC_STAGE_BYTES = DEC_CHUNK * 8;
-constexpr int DEC_SMEM_HIST = 4096;                // smem-privatised histogram entries
-constexpr int DEC_MAX_EOS = 64;                    // end-of-second positions kept per chunk (more: slow path)
+constexpr int DEC_BATCH = 256;                     // words per warp iteration (2 KiB)
+constexpr int DEC_MAX_LS = 4;                      // local seconds kept per range on the relative pass
+constexpr int DEC_ROW = 264;                       // u32 per row: 256 pixels | non-pixel | corrupt EOS | words | start
+constexpr int DEC_SMEM_HIST = 4096;                // smem-privatised histogram entries per CTA
+
+struct DecRange {
+    long long start;       // flat: first word (relative to words); wire: first half-bundle chunk
+    int n_words;           // words in the range
+    int roach, seg, first_of_seg;
+};
+struct DecRangeOut {
+    int eos_total;         // end-of-second words in the range
+    int n_ls;              // rows written on the relative pass (<= DEC_MAX_LS)
+    int resume;            // < 0: range done; else first word the absolute pass must handle
+    int pad;
+};
 
 struct DecParams {
     const uint64_t *words;     // flat format (or nullptr)
     const uint32_t *wire;      // wire format (or nullptr)
-    const int64_t *seg_first_chunk;   // [n_seg+1]
-    const int64_t *seg_offset;        // [n_seg] first word (flat) / bundle (wire) of each segment
-    const int64_t *seg_len;           // [n_seg] words / bundles
-    const int32_t *seg_roach;
-    const int32_t *seg_sec;
-    int32_t *seg_sec_out;
-    int32_t n_seg;
-    int64_t n_chunks;
-    int32_t n_roaches, npix_per_roach, exptime;
-    int32_t field_shift, n_bins;
+    const DecRange *ranges;
+    DecRangeOut *rout;
+    int n_ranges;
+    uint32_t *rows;            // [n_ranges][DEC_MAX_LS][DEC_ROW]
+    const int32_t *base;       // [n_ranges] absolute second at the start of each range (absolute pass)
+    int *flag;                 // != 0: some range needs the absolute pass
+    int n_pix, npix_per_roach, exptime, n_bins, field_shift;
     const uint16_t *bin_lut;
     uint32_t *counts;          // [exptime][n_pix]
-    uint32_t *hist;            // [n_pix][n_bins]
-    unsigned long long *stats; // 5 x u64
-    unsigned long long *state; // [n_chunks] look-back records
-    unsigned int *ticket;
-    unsigned long long *prof;  // optional [8] cycle accumulators (MKID_DEC_PROFILE=1): see decode_common
-};
-
-struct StageMeta {
-    long long chunk;       // < 0: no more work
-    int roach, base_sec, n_here, n_eos, last_chunk, seg;
-    int eos_pos[DEC_MAX_EOS];
+    uint32_t *hist;            // [n_pix][n_bins] or nullptr
+    unsigned long long *stats; // 5 x u64: eos, corrupt eos, non-pixel, ignored, valid
 };
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mk_smem_u32(bar)) : "memory");
+__device__ __forceinline__ unsigned warp_sum(unsigned v) { return __reduce_add_sync(0xffffffffu, v); }
+__device__ __forceinline__ uint2 ld_stream_u2(const uint64_t *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
 }
-__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(DEC_WORKERS) : "memory"); }
+__device__ __forceinline__ uint32_t ld_stream_u1(const uint32_t *p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
 
-template <bool WIRE, bool SMEM_HIST>
-__global__ void __launch_bounds__(DEC_THREADS, 1) decode_kernel(DecParams p) {
-    extern __shared__ __align__(128) unsigned char s_ring[];      // DEC_STAGES x 64 KiB
-    __shared__ uint32_t s_cnt[2][256];
-    __shared__ uint32_t s_hist[SMEM_HIST ? DEC_SMEM_HIST : 1];
-    __shared__ uint16_t s_lut[4096];
-    __shared__ unsigned long long s_stat[5];
-    __shared__ __align__(8) uint64_t s_full[DEC_STAGES], s_ready[DEC_STAGES], s_empty[DEC_STAGES];
-    __shared__ StageMeta s_meta[DEC_STAGES];
+// One warp, one range.  J = words per lane per 128-bit load group (flat 2, wire 4), U = groups per batch.
+// HIST: 0 = counts only, 1 = pulse-height histogram by global reductions, 2 = through the CTA's shared-memory copy
+template <bool WIRE, int HIST, bool ABS>
+struct RangeDecoder {
+    static constexpr int J = WIRE ? 4 : 2;
+    static constexpr int U = DEC_BATCH / (32 * J);
 
+    const DecParams &p;
+    uint32_t *cnt;             // this warp's shared-memory row [256]
+    uint32_t *s_hist;          // CTA histogram of roach cta_roach (SMEM_HIST)
+    const uint16_t *s_lut;
+    uint32_t *hist_r;          // global histogram of this range's roach
+    int lane, r, roach, npix, n_bins, f_sh;
+    bool f_hi, use_lut, own_roach;
+    int n_words;
+    const uint64_t *w_flat;
+    const uint32_t *w_wire;
+    long long wire_chunk0;
+
+    int sec;                   // REL: local second, ABS: absolute second
+    int row_start;             // position of the first word of the current second
+    int eos_total;
+    bool count_only;           // REL: more than DEC_MAX_LS seconds, only count end-of-second words from here on
+    bool stop;                 // ABS: exptime reached
+    int resume;
+    unsigned n_nonpix, n_bad;                          // per lane, current second
+    unsigned st_eos, st_bad, st_nonpix, st_valid;      // ABS: per lane totals
+    unsigned long long st_ign;
+
+    __device__ __forceinline__ RangeDecoder(const DecParams &p_) : p(p_) {}
+
+    __device__ __forceinline__ void bin(uint32_t hi, uint32_t lo) {
+        const uint32_t adr = hi >> 24;
+        if ((int)adr >= npix) { ++n_nonpix; return; }          // (adr == 255 never gets here)
+        atomicAdd(&cnt[adr], 1u);
+        if (HIST) {
+            const uint32_t f = ((f_hi ? hi : lo) >> f_sh) & 0xFFFu;
+            const uint32_t b = use_lut ? s_lut[f] : f;
+            if ((int)b < n_bins) {
+                if (HIST == 2 && own_roach) atomicAdd(&s_hist[adr * n_bins + b], 1u);
+                else atomicAdd(&hist_r[adr * n_bins + b], 1u);
+            }
+        }
+    }
+
+    // the second that ends with the word at position pe (or with the range: pe = n_words - 1, closed = false)
+    __device__ __forceinline__ void flush(int pe, bool closed) {
+        __syncwarp();
+        const unsigned np = warp_sum(n_nonpix), nb = warp_sum(n_bad);
+        n_nonpix = n_bad = 0;
+        if (!ABS) {
+            uint32_t *row = p.rows + ((size_t)r * DEC_MAX_LS + sec) * DEC_ROW;
+            uint4 a = reinterpret_cast<uint4 *>(cnt)[lane * 2], b = reinterpret_cast<uint4 *>(cnt)[lane * 2 + 1];
+            reinterpret_cast<uint4 *>(row)[lane * 2] = a;
+            reinterpret_cast<uint4 *>(row)[lane * 2 + 1] = b;
+            reinterpret_cast<uint4 *>(cnt)[lane * 2] = make_uint4(0, 0, 0, 0);
+            reinterpret_cast<uint4 *>(cnt)[lane * 2 + 1] = make_uint4(0, 0, 0, 0);
+            if (lane == 0) {
+                row[256] = np; row[257] = nb;
+                row[258] = (unsigned)(pe + 1 - row_start);
+                row[259] = (unsigned)row_start;
+            }
+        } else {
+            uint32_t *dst = p.counts + (size_t)sec * p.n_pix + (size_t)roach * npix;
+            for (int i = lane; i < 256; i += 32) {
+                const uint32_t v = cnt[i];
+                if (v) { atomicAdd(&dst[i], v); cnt[i] = 0; st_valid += v; }
+            }
+            if (lane == 0) { st_nonpix += np; st_bad += nb; st_eos += closed ? 1u : 0u; }
+        }
+        __syncwarp();
+    }
+
+    // an end-of-second word at position pe closes the current second (warp-uniform)
+    __device__ __forceinline__ void close_second(int pe) {
+        ++eos_total;
+        flush(pe, true);
+        ++sec;
+        row_start = pe + 1;
+        if (!ABS) {
+            if (sec == DEC_MAX_LS) { count_only = true; resume = pe + 1; }
+        } else if (sec >= p.exptime) {
+            stop = true;
+            if (lane == 0) st_ign += (unsigned long long)(n_words - (pe + 1));
+        }
+    }
+
+    // ordered path for one load group: lane holds words idx = J*lane + j at positions pos_base + idx;
+    // valid: bit j set if that word exists and is to be handled
+    __device__ __forceinline__ void slow_group(const uint32_t (&hi)[J], const uint32_t (&lo)[J], unsigned valid, int pos_base) {
+        unsigned e = 0;
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+            if (((valid >> j) & 1u) && (hi[j] >> 24) == 255u) e |= 1u << j;
+        int done = 0;
+        for (;;) {
+            if (stop) return;
+            if (count_only) {
+                unsigned c = 0;
+#pragma unroll
+                for (int j = 0; j < J; ++j) c += ((e >> j) & 1u) && (J * lane + j >= done);
+                eos_total += (int)warp_sum(c);
+                return;
+            }
+            int cand = 0x7fffffff;
+#pragma unroll
+            for (int j = J - 1; j >= 0; --j)
+                if (((e >> j) & 1u) && J * lane + j >= done) cand = J * lane + j;
+            const int pe = __reduce_min_sync(0xffffffffu, cand);
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int idx = J * lane + j;
+                if (((valid >> j) & 1u) && idx >= done && idx < pe) bin(hi[j], lo[j]);
+            }
+            if (pe == 0x7fffffff) return;
+#pragma unroll
+            for (int j = 0; j < J; ++j)
+                if (J * lane + j == pe && (hi[j] & lo[j]) != 0xFFFFFFFFu) ++n_bad;      // "Corrupted EOS!" PacketMaster.c:331
+            close_second(pos_base + pe);
+            done = pe + 1;
+        }
+    }
+
+    // batch with per-word guards: words at positions [b0, b0 + DEC_BATCH) restricted to [lo_bound, n_words)
+    __device__ __forceinline__ void guarded_batch(int b0, int lo_bound) {
+#pragma unroll 1
+        for (int u = 0; u < U; ++u) {
+            uint32_t hi[J], lo[J];
+            unsigned valid = 0;
+            const int g0 = b0 + u * 32 * J;
+#pragma unroll
+            for (int j = 0; j < J; ++j) {
+                const int pos = g0 + J * lane + j;
+                hi[j] = lo[j] = 0;
+                if (pos >= lo_bound && pos < n_words && pos >= 0) {
+                    valid |= 1u << j;
+                    if (WIRE) {
+                        const long long hc = wire_chunk0 + (pos >> 12);
+                        const uint32_t *lp = w_wire + (size_t)(hc >> 1) * (2 * DEC_BUNDLE) + (size_t)(hc & 1) * DEC_CHUNK + (pos & 4095);
+                        lo[j] = bswap32(ld_stream_u1(lp));
+                        hi[j] = bswap32(ld_stream_u1(lp + DEC_BUNDLE));
+                    } else {
+                        const uint2 v = ld_stream_u2(w_flat + pos);
+                        lo[j] = v.x; hi[j] = v.y;
+                    }
+                }
+            }
+            if (__any_sync(0xffffffffu, valid != 0)) slow_group(hi, lo, valid, g0);
+        }
+    }
+
+    struct Batch { uint4 v[WIRE ? 2 * U : U]; };
+
+    __device__ __forceinline__ void load_batch(Batch &bt, int b0) const {
+        if (WIRE) {
+            const long long hc = wire_chunk0 + (b0 >> 12);
+            const uint32_t *lp = w_wire + (size_t)(hc >> 1) * (2 * DEC_BUNDLE) + (size_t)(hc & 1) * DEC_CHUNK + (b0 & 4095) + 4 * lane;
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                bt.v[2 * u] = ld_stream_u4(reinterpret_cast<const uint4 *>(lp + u * 128));
+                bt.v[2 * u + 1] = ld_stream_u4(reinterpret_cast<const uint4 *>(lp + u * 128 + DEC_BUNDLE));
+            }
+        } else {
+            const uint4 *q = reinterpret_cast<const uint4 *>(w_flat + b0) + lane;
+#pragma unroll
+            for (int u = 0; u < U; ++u) bt.v[u] = ld_stream_u4(q + u * 32);
+        }
+    }
+
+    // bins a full batch if it holds no end-of-second word (almost always); else returns false, nothing done
+    __device__ __forceinline__ bool fast_batch(const Batch &bt) {
+        bool any = false;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (WIRE) {
+                const uint4 h = bt.v[2 * u + 1];      // big-endian: the channel byte is the low byte
+                any |= ((h.x & 0xFFu) == 0xFFu) | ((h.y & 0xFFu) == 0xFFu) | ((h.z & 0xFFu) == 0xFFu) | ((h.w & 0xFFu) == 0xFFu);
+            } else {
+                any |= ((bt.v[u].y >> 24) == 0xFFu) | ((bt.v[u].w >> 24) == 0xFFu);
+            }
+        }
+        if (__any_sync(0xffffffffu, any)) return false;
+        if (count_only) return true;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (WIRE) {
+                const uint4 l = bt.v[2 * u], h = bt.v[2 * u + 1];
+                bin(bswap32(h.x), bswap32(l.x)); bin(bswap32(h.y), bswap32(l.y));
+                bin(bswap32(h.z), bswap32(l.z)); bin(bswap32(h.w), bswap32(l.w));
+            } else {
+                bin(bt.v[u].y, bt.v[u].x); bin(bt.v[u].w, bt.v[u].z);
+            }
+        }
+        return true;
+    }
+
+    __device__ void run(int r_, const DecRange &rg, int cta_roach) {
+        r = r_;
+        roach = rg.roach; n_words = rg.n_words;
+        own_roach = roach == cta_roach;
+        hist_r = HIST ? p.hist + (size_t)roach * npix * n_bins : nullptr;
+        w_flat = WIRE ? nullptr : p.words + rg.start;
+        w_wire = p.wire; wire_chunk0 = rg.start;
+        sec = 0; row_start = 0; eos_total = 0; count_only = false; stop = false; resume = -1;
+        n_nonpix = n_bad = 0;
+        int lo_bound = 0;
+        if (ABS) {
+            const DecRangeOut ro = p.rout[r];
+            if (ro.resume < 0) return;
+            lo_bound = ro.resume; row_start = lo_bound;
+            sec = p.base[r] + DEC_MAX_LS;
+            if (sec >= p.exptime) {
+                if (lane == 0) st_ign += (unsigned long long)(n_words - lo_bound);
+                return;
+            }
+        }
+        // batches are anchored at a0 so that full batches are 16-byte aligned; the batch before the anchor (one
+        // word), the batch an absolute pass resumes in, the ragged tail and every batch that holds an
+        // end-of-second word go through the guarded, ordered path
+        const int a0 = WIRE ? 0 : (int)((reinterpret_cast<uintptr_t>(w_flat) >> 3) & 1);
+        int b = lo_bound < a0 ? a0 - DEC_BATCH : a0 + (lo_bound - a0) / DEC_BATCH * DEC_BATCH;
+        Batch cur;
+        bool have = false;
+#pragma unroll 1
+        for (; b < n_words && !stop; b += DEC_BATCH) {
+            bool guard = true;
+            if (b >= lo_bound && b + DEC_BATCH <= n_words) {
+                if (!have) load_batch(cur, b);
+                Batch nxt;
+                have = b + 2 * DEC_BATCH <= n_words;
+                if (have) load_batch(nxt, b + DEC_BATCH);
+                guard = !fast_batch(cur);
+                cur = nxt;
+            }
+            if (guard) guarded_batch(b, lo_bound);
+        }
+        if (!ABS) {
+            int n_ls = DEC_MAX_LS;
+            if (!count_only) { flush(n_words - 1, false); n_ls = sec + 1; }
+            if (lane == 0) {
+                p.rout[r] = DecRangeOut{eos_total, n_ls, resume, 0};
+                if (resume >= 0) atomicOr(p.flag, 1);
+            }
+        } else if (!stop) {
+            flush(n_words - 1, false);
+        }
+    }
+};
+
+template <bool WIRE, int HIST, bool ABS>
+__global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_stream_kernel(DecParams p) {
+    __shared__ __align__(16) uint32_t s_cnt[DEC_WARPS][256];
+    __shared__ uint32_t s_hist[HIST == 2 ? DEC_SMEM_HIST : 1];
+    __shared__ uint16_t s_lut[HIST ? 4096 : 1];
+    if (ABS && *p.flag == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const bool use_lut = p.bin_lut != nullptr;
+    const bool use_lut = HIST != 0 && p.bin_lut != nullptr;
     if (use_lut)
         for (int i = tid; i < 4096; i += DEC_THREADS) s_lut[i] = p.bin_lut[i];
-    if (tid < 5) s_stat[tid] = 0;
-    for (int i = tid; i < 512; i += DEC_THREADS) (&s_cnt[0][0])[i] = 0;
-    if (SMEM_HIST)
+    for (int i = tid; i < DEC_WARPS * 256; i += DEC_THREADS) (&s_cnt[0][0])[i] = 0;
+    if (HIST == 2)
         for (int i = tid; i < DEC_SMEM_HIST; i += DEC_THREADS) s_hist[i] = 0;
-    if (tid == 0) {
-        for (int i = 0; i < DEC_STAGES; ++i) {
-            mk_mbar_init(&s_full[i], 1);
-            mk_mbar_init(&s_ready[i], 1);
-            mk_mbar_init(&s_empty[i], DEC_WORKERS / 32);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
     __syncthreads();
-    const int n_pix = p.n_roaches * p.npix_per_roach;
 
-    if (warp >= DEC_WORKERS / 32) {
-        // =========================== producer / scout warps ===========================
-        // scout j owns ring stage j: wait until the workers freed it, take the next ticket, start the bulk
-        // load, scan the chunk when it has landed, resolve its second index, hand it to the workers.
-        const int ss = warp - DEC_WORKERS / 32;
-        StageMeta &m = s_meta[ss];
-        for (int r = 0;; ++r) {                              // r-th use of this stage
-            // (the ticket must not be drawn before the stage is free: a held ticket stalls the look-back of
-            // every later chunk)
-            long long t0 = p.prof ? clock64() : 0;
-            if (r > 0) mk_mbar_wait(&s_empty[ss], (r - 1) & 1);
-            long long t1 = p.prof ? clock64() : 0;
-            long long c = 0;
-            if (lane == 0) c = (long long)atomicAdd(p.ticket, 1u);
-            c = __shfl_sync(0xffffffffu, c, 0);
-            long long t2 = p.prof ? clock64() : 0;
-            if (c >= p.n_chunks) {                           // no more work for this stage, ever (sticky)
-                if (lane == 0) { m.chunk = -1; mbar_arrive(&s_ready[ss]); }
-                break;
-            }
-            {
-                int lo = 0, hi = p.n_seg;       // segment of this chunk: last g with first_chunk[g] <= c
-                while (hi - lo > 1) {
-                    const int mid = (lo + hi) >> 1;
-                    if (p.seg_first_chunk[mid] <= c) lo = mid; else hi = mid;
-                }
-                const int g = lo;
-                const long long lc = c - p.seg_first_chunk[g];
-                const unsigned char *src;
-                int n_here = DEC_CHUNK;
-                if (WIRE) {   // chunk lc = half (lc & 1) of bundle lc >> 1: its low halves; the high halves are 32 KiB further
-                    src = reinterpret_cast<const unsigned char *>(p.wire) + (size_t)(p.seg_offset[g] + (lc >> 1)) * (DEC_BUNDLE * 8) +
-                          (size_t)(lc & 1) * (DEC_CHUNK * 4);
-                } else {
-                    const long long rem = p.seg_len[g] - lc * DEC_CHUNK;
-                    n_here = rem < DEC_CHUNK ? (int)rem : DEC_CHUNK;
-                    src = reinterpret_cast<const unsigned char *>(p.words + p.seg_offset[g] + lc * DEC_CHUNK);
-                }
-                unsigned char *dst = s_ring + (size_t)ss * DEC_STAGE_BYTES;
-                const bool tma = n_here == DEC_CHUNK && (reinterpret_cast<uintptr_t>(src) & 15) == 0;
-                if (lane == 0) {
-                    m.chunk = c; m.seg = g; m.roach = p.seg_roach[g]; m.n_here = n_here;
-                    m.last_chunk = (c + 1 == p.seg_first_chunk[g + 1]);
-                    if (tma) {
-                        mk_mbar_expect_tx(&s_full[ss], DEC_STAGE_BYTES);
-                        if (WIRE) {
-                            mk_bulk_g2s(dst, src, DEC_STAGE_BYTES / 2, &s_full[ss]);
-                            mk_bulk_g2s(dst + DEC_STAGE_BYTES / 2, src + DEC_BUNDLE * 4, DEC_STAGE_BYTES / 2, &s_full[ss]);
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 2; ++q)
-                                mk_bulk_g2s(dst + q * (DEC_STAGE_BYTES / 2), src + q * (DEC_STAGE_BYTES / 2),
-                                            DEC_STAGE_BYTES / 2, &s_full[ss]);
-                        }
-                    }
-                }
-                if (!tma) {   // ragged tail / odd alignment (flat format only): the warp copies it, zero padded
-                    const uint64_t *sw = reinterpret_cast<const uint64_t *>(src);
-                    uint64_t *dw = reinterpret_cast<uint64_t *>(dst);
-                    for (int i = lane; i < DEC_CHUNK; i += 32) dw[i] = i < n_here ? sw[i] : 0ull;
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&s_full[ss]);
-                }
-            }
-            __syncwarp();
-            mk_mbar_wait(&s_full[ss], r & 1);
-            long long t3 = p.prof ? clock64() : 0;
-            // count end-of-second words (channel field 255) and remember their positions, in order.
-            // Fast path: 16 x 128-bit loads per lane in flight, one ballot per batch; the ordered position
-            // list is only built for batches that contain an end-of-second word (rare).
-            const unsigned char *base = s_ring + (size_t)ss * DEC_STAGE_BYTES;
-            const uint4 *scan = reinterpret_cast<const uint4 *>(WIRE ? base + DEC_STAGE_BYTES / 2 : base);
-            constexpr int SCAN_IT = (WIRE ? DEC_STAGE_BYTES / 2 : DEC_STAGE_BYTES) / 16 / 32;   // uint4 iterations per lane
-            constexpr int POS_PER_IT = WIRE ? 128 : 64;                                       // positions covered by one iteration
-            int n_eos = 0;
-            constexpr int SB = 16;                           // 128-bit loads in flight per lane
-            for (int i0 = 0; i0 < SCAN_IT; i0 += SB) {
-                uint4 v[SB];
-#pragma unroll
-                for (int u = 0; u < SB; ++u) v[u] = scan[(i0 + u) * 32 + lane];
-                bool any = false;
-#pragma unroll
-                for (int u = 0; u < SB; ++u) {
-                    if (WIRE) any |= ((v[u].x & 0xFFu) == 0xFFu) | ((v[u].y & 0xFFu) == 0xFFu) | ((v[u].z & 0xFFu) == 0xFFu) | ((v[u].w & 0xFFu) == 0xFFu);
-                    else any |= ((v[u].y >> 24) == 0xFFu) | ((v[u].w >> 24) == 0xFFu);
-                }
-                if (__ballot_sync(0xffffffffu, any)) {
-                    // position-ordered pass over this batch (zero padding beyond n_here is never an EOS word)
-                    const int p0 = i0 * POS_PER_IT, p1 = p0 + SB * POS_PER_IT;
-                    for (int pb = p0; pb < p1; pb += 32) {
-                        const int pos = pb + lane;
-                        bool is_eos;
-                        if (WIRE) is_eos = (reinterpret_cast<const uint32_t *>(base + DEC_STAGE_BYTES / 2)[pos] & 0xFFu) == 0xFFu;
-                        else is_eos = (reinterpret_cast<const uint32_t *>(base)[2 * pos + 1] >> 24) == 0xFFu;
-                        const unsigned bal = __ballot_sync(0xffffffffu, is_eos);
-                        if (bal) {
-                            const int at = n_eos + __popc(bal & ((1u << lane) - 1));
-                            if (is_eos && at < DEC_MAX_EOS) m.eos_pos[at] = pos;
-                            n_eos += __popc(bal);
-                        }
-                    }
-                }
-            }
-            long long t4 = p.prof ? clock64() : 0;
-            // decoupled look-back: seconds closed before this chunk
-            const int g = m.seg;
-            const long long lc = c - p.seg_first_chunk[g];
-            int base_sec = 0;
-            if (lc == 0) {
-                base_sec = p.seg_sec[g];
-            } else {
-                // aggregate first (plain 64-bit store: self-contained record, nothing to wait for)
-                if (lane == 0) *reinterpret_cast<volatile unsigned long long *>(&p.state[c]) = (1ull << 32) | (unsigned)n_eos;
-                const long long first = c - lc;
-                long long q = c - 1;
-                int acc = 0;
-                for (;;) {
-                    // 128 predecessors per round: lane l looks at q - l - 32*j, j = 0..3 (nearest first)
-                    unsigned long long sv[4];
-                    bool valid[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const long long idx = q - lane - 32 * j;
-                        valid[j] = idx >= first;
-                        sv[j] = valid[j] ? *reinterpret_cast<volatile unsigned long long *>(&p.state[idx]) : 0ull;
-                    }
-                    bool stop_found = false;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (stop_found) break;
-                        const long long idx = q - lane - 32 * j;
-                        while (valid[j] && (sv[j] >> 32) == 0) sv[j] = *reinterpret_cast<volatile unsigned long long *>(&p.state[idx]);
-                        const unsigned incl = __ballot_sync(0xffffffffu, valid[j] && (sv[j] >> 32) == 2);
-                        int v;
-                        if (incl) {
-                            const int stop = __ffs(incl) - 1;           // nearest predecessor holding a prefix
-                            v = (lane <= stop) ? (int)(unsigned)sv[j] : 0;
-                            stop_found = true;
-                        } else {
-                            v = valid[j] ? (int)(unsigned)sv[j] : 0;
-                        }
-#pragma unroll
-                        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
-                        acc += v;
-                    }
-                    if (stop_found) break;
-                    q -= 128;
-                }
-                base_sec = acc;
-            }
-            if (lane == 0) {
-                *reinterpret_cast<volatile unsigned long long *>(&p.state[c]) = (2ull << 32) | (unsigned)(base_sec + n_eos);
-                m.base_sec = base_sec;
-                m.n_eos = n_eos;
-                if (m.last_chunk && p.seg_sec_out) p.seg_sec_out[g] = base_sec + n_eos;
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_ready[ss]);       // release: meta + data are ready for the workers
-            if (p.prof && lane == 0) {
-                const long long t5 = clock64();
-                atomicAdd(&p.prof[0], (unsigned long long)(t1 - t0));   // scout: wait for a free stage
-                atomicAdd(&p.prof[1], (unsigned long long)(t2 - t1));   // ticket
-                atomicAdd(&p.prof[2], (unsigned long long)(t3 - t2));   // load issue + data arrival
-                atomicAdd(&p.prof[3], (unsigned long long)(t4 - t3));   // EOS scan
-                atomicAdd(&p.prof[4], (unsigned long long)(t5 - t4));   // look-back + publish
-                atomicAdd(&p.prof[7], 1ull);
-            }
-        }
-    } else {
-        // =========================== worker warps ===========================
-        unsigned n_eos_t = 0, n_bad = 0, n_nonpix = 0, n_ign = 0, n_ok = 0;
-        // stages are visited round-robin; a stage whose scout ran out of tickets is dead for good.  The
-        // scouts may draw their first tickets in any order, so a dead stage does not end the loop: it
-        // ends when all stages are dead.
-        int dead = 0, n_proc = 0;
-        for (int k = 0; dead != (1 << DEC_STAGES) - 1; ++k) {
-            const int st = k % DEC_STAGES;
-            if ((dead >> st) & 1) continue;
-            long long w0 = p.prof ? clock64() : 0;
-            mk_mbar_wait(&s_ready[st], (k / DEC_STAGES) & 1);
-            long long w1 = p.prof ? clock64() : 0;
-            const StageMeta &m = s_meta[st];
-            if (m.chunk < 0) { dead |= 1 << st; continue; }
-            const int roach = m.roach, sec_base = m.base_sec, n_here = m.n_here, n_eos = m.n_eos;
-            uint32_t *cnt = s_cnt[n_proc & 1];
-            ++n_proc;
-            const uint4 *sm = reinterpret_cast<const uint4 *>(s_ring + (size_t)st * DEC_STAGE_BYTES);
-            if (n_here == DEC_CHUNK && n_eos == 0 && sec_base < p.exptime) {
-                // fast path (almost every chunk): full chunk, no second boundary inside, all words live
-                const bool f_hi = p.field_shift >= 32;
-                const int f_sh = p.field_shift & 31;
-                const int npix = p.npix_per_roach;
-                uint32_t *hist_r = p.hist ? p.hist + (size_t)roach * npix * p.n_bins : nullptr;
-#pragma unroll
-                for (int i = 0; i < (WIRE ? DEC_WPT / 4 : DEC_WPT / 2); ++i) {
-                    uint32_t whi[WIRE ? 4 : 2], wlo[WIRE ? 4 : 2];
-                    if (WIRE) {
-                        const uint4 l = sm[i * DEC_WORKERS + tid], h = sm[DEC_CHUNK / 4 + i * DEC_WORKERS + tid];
-                        whi[0] = bswap32(h.x); whi[1] = bswap32(h.y); whi[2] = bswap32(h.z); whi[3] = bswap32(h.w);
-                        wlo[0] = bswap32(l.x); wlo[1] = bswap32(l.y); wlo[2] = bswap32(l.z); wlo[3] = bswap32(l.w);
-                    } else {
-                        const uint4 v = sm[i * DEC_WORKERS + tid];
-                        wlo[0] = v.x; whi[0] = v.y; wlo[1] = v.z; whi[1] = v.w;
-                    }
-#pragma unroll
-                    for (int j = 0; j < (WIRE ? 4 : 2); ++j) {
-                        const uint32_t hi = whi[j], lo = wlo[j];
-                        const uint32_t adr = hi >> 24;
-                        if ((int)adr >= npix) { ++n_nonpix; --n_ok; continue; }   // (adr == 255 cannot occur: n_eos == 0)
-                        if (SMEM_HIST) {
-                            // one shared atomic per word: row adr, column = bin or the overflow column n_bins;
-                            // the per-pixel count is the row sum (taken at the flush)
-                            const uint32_t f = ((f_hi ? hi : lo) >> f_sh) & 0xFFFu;
-                            const uint32_t b = use_lut ? s_lut[f] : f;
-                            atomicAdd(&s_hist[adr * (p.n_bins + 1) + min((int)b, p.n_bins)], 1u);
-                        } else {
-                            atomicAdd(&cnt[adr], 1u);
-                            if (hist_r) {
-                                const uint32_t f = ((f_hi ? hi : lo) >> f_sh) & 0xFFFu;
-                                const uint32_t b = use_lut ? s_lut[f] : f;
-                                if ((int)b < p.n_bins) atomicAdd(&hist_r[adr * p.n_bins + b], 1u);
-                            }
-                        }
-                    }
-                }
-                n_ok += DEC_WPT;          // corrected by the non-pixel words below
-            } else {
-                // 16 words per thread, 16 B per lane per access; everything on 32-bit halves
-                const bool f_hi = p.field_shift >= 32;
-                const int f_sh = p.field_shift & 31;
-    #pragma unroll
-                for (int i = 0; i < (WIRE ? DEC_WPT / 4 : DEC_WPT / 2); ++i) {
-                    uint32_t whi[WIRE ? 4 : 2], wlo[WIRE ? 4 : 2];
-                    int pos0;
-                    if (WIRE) {
-                        const uint4 l = sm[i * DEC_WORKERS + tid], h = sm[DEC_CHUNK / 4 + i * DEC_WORKERS + tid];
-                        whi[0] = bswap32(h.x); whi[1] = bswap32(h.y); whi[2] = bswap32(h.z); whi[3] = bswap32(h.w);
-                        wlo[0] = bswap32(l.x); wlo[1] = bswap32(l.y); wlo[2] = bswap32(l.z); wlo[3] = bswap32(l.w);
-                        pos0 = (i * DEC_WORKERS + tid) * 4;
-                    } else {
-                        const uint4 v = sm[i * DEC_WORKERS + tid];
-                        wlo[0] = v.x; whi[0] = v.y; wlo[1] = v.z; whi[1] = v.w;
-                        pos0 = (i * DEC_WORKERS + tid) * 2;
-                    }
-    #pragma unroll
-                    for (int j = 0; j < (WIRE ? 4 : 2); ++j) {
-                        const int pos = pos0 + j;
-                        if (pos >= n_here) continue;
-                        const uint32_t hi = whi[j], lo = wlo[j];
-                        int l = 0;                                   // seconds closed inside the chunk before this word
-                        if (n_eos) {
-                            if (n_eos <= DEC_MAX_EOS) {
-                                for (int e = 0; e < n_eos; ++e) l += m.eos_pos[e] < pos;
-                            } else {                                 // pathological: rescan the chunk prefix
-                                for (int q = 0; q < pos; ++q) {
-                                    if (WIRE) l += (reinterpret_cast<const uint32_t *>(sm)[DEC_CHUNK + q] & 0xFFu) == 0xFFu;
-                                    else l += (reinterpret_cast<const uint32_t *>(sm)[2 * q + 1] >> 24) == 0xFFu;
-                                }
-                            }
-                        }
-                        const int sec = sec_base + l;
-                        const uint32_t adr = hi >> 24;
-                        if (sec >= p.exptime) { ++n_ign; continue; }
-                        if (adr == 255u) { ++n_eos_t; if ((hi & lo) != 0xFFFFFFFFu) ++n_bad; continue; }
-                        if ((int)adr >= p.npix_per_roach) { ++n_nonpix; continue; }
-                        ++n_ok;
-                        uint32_t b = 0;
-                        if (p.hist) {
-                            const uint32_t f = ((f_hi ? hi : lo) >> f_sh) & 0xFFFu;
-                            b = use_lut ? s_lut[f] : f;
-                        }
-                        if (SMEM_HIST && l == 0) {
-                            atomicAdd(&s_hist[adr * (p.n_bins + 1) + min((int)b, p.n_bins)], 1u);
-                        } else {
-                            if (l == 0) atomicAdd(&cnt[adr], 1u);
-                            else atomicAdd(&p.counts[(size_t)sec * n_pix + roach * p.npix_per_roach + adr], 1u);
-                            if (p.hist && (int)b < p.n_bins)
-                                atomicAdd(&p.hist[((size_t)(roach * p.npix_per_roach + adr)) * p.n_bins + b], 1u);
-                        }
-                    }
-                }
-            }
-            // this thread no longer needs the ring slot
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_empty[st]);
-            workers_sync();                                   // all counts of this chunk are in cnt[]
-            if (sec_base < p.exptime && tid < p.npix_per_roach) {
-                const uint32_t v = cnt[tid];
-                if (v) atomicAdd(&p.counts[(size_t)sec_base * n_pix + roach * p.npix_per_roach + tid], v);
-            }
-            if (tid < 256) cnt[tid] = 0;                      // reused two chunks later (a barrier lies in between)
-            if (SMEM_HIST && p.hist) {
-                const int hs = p.n_bins + 1, n = p.npix_per_roach * hs;
-                if (tid < p.npix_per_roach) {                 // per-pixel count of this chunk = row sum (incl. overflow column)
-                    uint32_t sum = 0;
-                    for (int b = 0; b < hs; ++b) sum += s_hist[tid * hs + b];
-                    if (sum && sec_base < p.exptime)
-                        atomicAdd(&p.counts[(size_t)sec_base * n_pix + roach * p.npix_per_roach + tid], sum);
-                }
-                workers_sync();
-                for (int i = tid; i < n; i += DEC_WORKERS) {
-                    const uint32_t v = s_hist[i];
-                    if (v) {
-                        const int pix = i / hs, b = i - pix * hs;
-                        if (b < p.n_bins) atomicAdd(&p.hist[((size_t)roach * p.npix_per_roach + pix) * p.n_bins + b], v);
-                        s_hist[i] = 0;
-                    }
-                }
-                workers_sync();                               // s_hist is shared by consecutive chunks
-            }
-            if (p.prof && tid == 0) {
-                const long long w2 = clock64();
-                atomicAdd(&p.prof[5], (unsigned long long)(w1 - w0));   // workers: wait for a ready chunk
-                atomicAdd(&p.prof[6], (unsigned long long)(w2 - w1));   // workers: process + flush
-            }
-        }
-#pragma unroll
-        for (int d = 16; d > 0; d >>= 1) {
-            n_eos_t += __shfl_xor_sync(0xffffffffu, n_eos_t, d);
-            n_bad += __shfl_xor_sync(0xffffffffu, n_bad, d);
-            n_nonpix += __shfl_xor_sync(0xffffffffu, n_nonpix, d);
-            n_ign += __shfl_xor_sync(0xffffffffu, n_ign, d);
-            n_ok += __shfl_xor_sync(0xffffffffu, n_ok, d);
-        }
+    int r = blockIdx.x * DEC_WARPS + warp;
+    const int cta_roach = blockIdx.x * DEC_WARPS < p.n_ranges ? p.ranges[blockIdx.x * DEC_WARPS].roach : -1;
+    RangeDecoder<WIRE, HIST, ABS> d(p);
+    d.cnt = s_cnt[warp]; d.s_hist = s_hist; d.s_lut = s_lut; d.lane = lane;
+    d.npix = p.npix_per_roach; d.n_bins = p.n_bins;
+    d.use_lut = use_lut;
+    d.f_hi = p.field_shift >= 32; d.f_sh = p.field_shift & 31;
+    d.st_eos = d.st_bad = d.st_nonpix = d.st_valid = 0; d.st_ign = 0;
+    for (; r < p.n_ranges; r += gridDim.x * DEC_WARPS) d.run(r, p.ranges[r], cta_roach);
+    if (ABS) {
+        const unsigned e = warp_sum(d.st_eos), b = warp_sum(d.st_bad), n = warp_sum(d.st_nonpix), v = warp_sum(d.st_valid);
         if (lane == 0) {
-            if (n_eos_t) atomicAdd(&s_stat[0], (unsigned long long)n_eos_t);
-            if (n_bad) atomicAdd(&s_stat[1], (unsigned long long)n_bad);
-            if (n_nonpix) atomicAdd(&s_stat[2], (unsigned long long)n_nonpix);
-            if (n_ign) atomicAdd(&s_stat[3], (unsigned long long)n_ign);
-            if (n_ok) atomicAdd(&s_stat[4], (unsigned long long)n_ok);
+            if (e) atomicAdd(&p.stats[0], (unsigned long long)e);
+            if (b) atomicAdd(&p.stats[1], (unsigned long long)b);
+            if (n) atomicAdd(&p.stats[2], (unsigned long long)n);
+            if (d.st_ign) atomicAdd(&p.stats[3], d.st_ign);
+            if (v) atomicAdd(&p.stats[4], (unsigned long long)v);
         }
     }
-    __syncthreads();
-    if (tid < 5 && s_stat[tid]) atomicAdd(&p.stats[tid], s_stat[tid]);
+    if (HIST == 2) {
+        __syncthreads();
+        if (cta_roach >= 0) {
+            uint32_t *hist_r = p.hist + (size_t)cta_roach * p.npix_per_roach * p.n_bins;
+            const int n = p.npix_per_roach * p.n_bins;
+            for (int i = tid; i < n; i += DEC_THREADS) {
+                const uint32_t v = s_hist[i];
+                if (v) atomicAdd(&hist_r[i], v);
+            }
+        }
+    }
 }
+
+// segmented exclusive scan of the ranges' end-of-second totals (one CTA)
+__global__ void __launch_bounds__(1024) decode_prefix_kernel(const DecRange *ranges, const DecRangeOut *rout, int n,
+                                                             const int32_t *seg_sec, int32_t *seg_sec_out, int32_t *base) {
+    __shared__ int s_sum[1024];
+    __shared__ int s_head[1024];
+    const int t = threadIdx.x;
+    const int K = (n + 1023) / 1024;
+    const int i0 = min(n, t * K), i1 = min(n, i0 + K);
+    int sum = 0, head = 0;
+    for (int i = i0; i < i1; ++i) {
+        if (ranges[i].first_of_seg) { sum = seg_sec[ranges[i].seg]; head = 1; }
+        sum += rout[i].eos_total;
+    }
+    s_sum[t] = sum; s_head[t] = head;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {          // inclusive scan with (a o b) = (b.head ? b.sum : a.sum + b.sum, a.head | b.head)
+        int a_sum = 0, a_head = 0;
+        if (t >= d) { a_sum = s_sum[t - d]; a_head = s_head[t - d]; }
+        __syncthreads();
+        if (t >= d) {
+            if (!s_head[t]) s_sum[t] += a_sum;
+            s_head[t] |= a_head;
+        }
+        __syncthreads();
+    }
+    int run = t > 0 ? s_sum[t - 1] : 0;
+    for (int i = i0; i < i1; ++i) {
+        if (ranges[i].first_of_seg) run = seg_sec[ranges[i].seg];
+        base[i] = run;
+        run += rout[i].eos_total;
+        if (seg_sec_out && (i + 1 == n || ranges[i + 1].first_of_seg)) seg_sec_out[ranges[i].seg] = run;
+    }
+}
+
+// rows[range][local second] -> counts[second][pixel] + statistics; rows beyond exptime are dropped and their
+// histogram contribution (made before the second was known) is taken back
+template <bool WIRE>
+__global__ void __launch_bounds__(256) decode_commit_kernel(DecParams p) {
+    __shared__ unsigned long long s_st[5];
+    const int tid = threadIdx.x;
+    if (tid < 5) s_st[tid] = 0;
+    __syncthreads();
+    unsigned long long eos = 0, bad = 0, nonpix = 0, ign = 0;
+    unsigned valid = 0;
+    const bool use_lut = p.bin_lut != nullptr;
+    const bool f_hi = p.field_shift >= 32;
+    const int f_sh = p.field_shift & 31;
+    for (int r = blockIdx.x; r < p.n_ranges; r += gridDim.x) {
+        const DecRangeOut ro = p.rout[r];
+        const DecRange rg = p.ranges[r];
+        const int base = p.base[r];
+        for (int ls = 0; ls < ro.n_ls; ++ls) {
+            const int sec = base + ls;
+            const uint32_t *row = p.rows + ((size_t)r * DEC_MAX_LS + ls) * DEC_ROW;
+            if (sec < p.exptime) {
+                if (tid < p.npix_per_roach) {
+                    const uint32_t v = row[tid];
+                    if (v) { atomicAdd(&p.counts[(size_t)sec * p.n_pix + (size_t)rg.roach * p.npix_per_roach + tid], v); valid += v; }
+                }
+                if (tid == 0) { nonpix += row[256]; bad += row[257]; eos += ls < ro.eos_total ? 1 : 0; }
+                continue;
+            }
+            const unsigned n_w = row[258], w0 = row[259];
+            if (tid == 0) ign += n_w;
+            if (!p.hist) continue;
+            for (unsigned w = w0 + tid; w < w0 + n_w; w += blockDim.x) {
+                uint32_t hi, lo;
+                if (WIRE) {
+                    const long long hc = rg.start + (w >> 12);
+                    const uint32_t *lp = p.wire + (size_t)(hc >> 1) * (2 * DEC_BUNDLE) + (size_t)(hc & 1) * DEC_CHUNK + (w & 4095);
+                    lo = bswap32(lp[0]); hi = bswap32(lp[DEC_BUNDLE]);
+                } else {
+                    const uint64_t x = p.words[rg.start + w];
+                    hi = (uint32_t)(x >> 32); lo = (uint32_t)x;
+                }
+                const uint32_t adr = hi >> 24;
+                if ((int)adr >= p.npix_per_roach) continue;
+                const uint32_t f = ((f_hi ? hi : lo) >> f_sh) & 0xFFFu;
+                const uint32_t b = use_lut ? p.bin_lut[f] : f;
+                if ((int)b < p.n_bins)
+                    atomicAdd(&p.hist[((size_t)rg.roach * p.npix_per_roach + adr) * p.n_bins + b], 0xFFFFFFFFu);
+            }
+        }
+    }
+    valid = warp_sum(valid);
+    if ((tid & 31) == 0 && valid) atomicAdd(&s_st[4], (unsigned long long)valid);
+    if (tid == 0) {
+        if (eos) atomicAdd(&s_st[0], eos);
+        if (bad) atomicAdd(&s_st[1], bad);
+        if (nonpix) atomicAdd(&s_st[2], nonpix);
+        if (ign) atomicAdd(&s_st[3], ign);
+    }
+    __syncthreads();
+    if (tid < 5 && s_st[tid]) atomicAdd(&p.stats[tid], s_st[tid]);
+}
+
 
 __global__ void counts_cap_kernel(const uint32_t *in, uint32_t *out, int64_t n, uint32_t cap) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -484,60 +526,69 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
     const bool wire_fmt = wire != nullptr;
     const int64_t n_pix = (int64_t)cfg->n_roaches * cfg->npix_per_roach;
 
-    // segment table (host) -> chunk prefix
-    std::vector<int64_t> first_chunk(n_seg + 1, 0);
-    std::vector<int64_t> seg_len(n_seg);
+    // segments -> chunks -> ranges (about one per resident warp, whole chunks, never across a segment)
+    std::vector<int64_t> seg_chunks(n_seg), seg_len(n_seg);
+    int64_t n_chunks = 0;
     for (int i = 0; i < n_seg; ++i) {
-        int64_t len = seg_len_in ? seg_len_in[i] : seg_offset[i + 1] - seg_offset[i];
+        const int64_t len = seg_len_in ? seg_len_in[i] : seg_offset[i + 1] - seg_offset[i];
         seg_len[i] = len;
         MKID_REQUIRE(ctx, len >= 0 && seg_offset[i] >= 0 && seg_offset[i] + len <= n_units, "segment offsets out of range");
         MKID_REQUIRE(ctx, seg_roach[i] >= 0 && seg_roach[i] < cfg->n_roaches, "segment roach out of range");
-        first_chunk[i + 1] = first_chunk[i] + (wire_fmt ? 2 * len : (len + DEC_CHUNK - 1) / DEC_CHUNK);
+        seg_chunks[i] = wire_fmt ? 2 * len : (len + DEC_CHUNK - 1) / DEC_CHUNK;
+        n_chunks += seg_chunks[i];
     }
-    const int64_t n_chunks = first_chunk[n_seg];
     std::vector<int32_t> sec0(n_seg, 0);
     if (seg_sec) for (int i = 0; i < n_seg; ++i) sec0[i] = seg_sec[i];
 
-    // meta buffer: first_chunk | seg_offset | seg_len | stats(5 u64) | roach | sec | sec_out | ticket
-    const size_t meta_bytes = (size_t)(n_seg + 1) * 24 + (size_t)n_seg * 12 + 5 * 8 + 16;
+    const int64_t warps_total = (int64_t)ctx->num_sms * DEC_CTAS_PER_SM * DEC_WARPS;
+    const int64_t per = std::max<int64_t>(2, (n_chunks + warps_total - 1) / warps_total);
+    std::vector<DecRange> ranges;
+    for (int i = 0; i < n_seg; ++i) {
+        const int64_t nc = seg_chunks[i];
+        const int64_t pieces = (nc + per - 1) / per;
+        bool first = true;
+        for (int64_t q = 0; q < pieces; ++q) {
+            const int64_t c0 = nc * q / pieces, c1 = nc * (q + 1) / pieces;
+            if (c1 <= c0) continue;
+            DecRange r;
+            if (wire_fmt) { r.start = seg_offset[i] * 2 + c0; r.n_words = (int)((c1 - c0) * DEC_CHUNK); }
+            else { r.start = seg_offset[i] + c0 * DEC_CHUNK; r.n_words = (int)std::min<int64_t>((c1 - c0) * DEC_CHUNK, seg_len[i] - c0 * DEC_CHUNK); }
+            r.roach = seg_roach[i]; r.seg = i; r.first_of_seg = first ? 1 : 0;
+            first = false;
+            ranges.push_back(r);
+        }
+    }
+    const int n_ranges = (int)ranges.size();
+    MKID_REQUIRE(ctx, ranges.size() <= (size_t)1 << 18, "decode: too many segments in one call");
+    for (const DecRange &r : ranges) MKID_REQUIRE(ctx, (int64_t)r.n_words <= (int64_t)1 << 30, "decode: range too long");
+
+    // meta: stats (5 u64) | flag, pad | sec_out [n_seg] | sec [n_seg]
+    const size_t meta_bytes = 48 + (size_t)n_seg * 8;
     char *meta = nullptr;
     int rc = mkid_scratch(ctx, SCR_META, meta_bytes, (void **)&meta);
     if (rc) return rc;
-    int64_t *d_first = (int64_t *)meta;
-    int64_t *d_off = d_first + (n_seg + 1);
-    int64_t *d_len = d_off + (n_seg + 1);
-    unsigned long long *d_stats = (unsigned long long *)(d_len + (n_seg + 1));
-    int32_t *d_roach = (int32_t *)(d_stats + 5);
-    int32_t *d_sec = d_roach + n_seg;
-    int32_t *d_sec_out = d_sec + n_seg;
-    unsigned int *d_ticket = (unsigned int *)(d_sec_out + n_seg);
-    {   // upload the segment table only when it changed since the last call on this context
+    unsigned long long *d_stats = (unsigned long long *)meta;
+    int *d_flag = (int *)(meta + 40);
+    int32_t *d_sec_out = (int32_t *)(meta + 48);
+    int32_t *d_sec = d_sec_out + n_seg;
+    {   // upload the segment seconds only when they changed since the last call on this context
         std::vector<char> blob(meta_bytes, 0);
-        memcpy(blob.data() + ((char *)d_first - meta), first_chunk.data(), (n_seg + 1) * 8);
-        memcpy(blob.data() + ((char *)d_off - meta), seg_offset, n_seg * 8);
-        memcpy(blob.data() + ((char *)d_len - meta), seg_len.data(), n_seg * 8);
-        memcpy(blob.data() + ((char *)d_roach - meta), seg_roach, n_seg * 4);
-        memcpy(blob.data() + ((char *)d_sec - meta), sec0.data(), n_seg * 4);
+        memcpy(blob.data() + 48 + (size_t)n_seg * 4, sec0.data(), (size_t)n_seg * 4);
         if (ctx->dec_meta_dev != meta || ctx->dec_meta_host != blob) {
             MKID_CUDA(ctx, cudaMemcpyAsync(meta, blob.data(), meta_bytes, cudaMemcpyHostToDevice, ctx->stream));
             MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // blob is pageable and about to be moved
             ctx->dec_meta_host.swap(blob);
             ctx->dec_meta_dev = meta;
         } else {
-            MKID_CUDA(ctx, cudaMemsetAsync(d_stats, 0, 5 * 8, ctx->stream));
-            MKID_CUDA(ctx, cudaMemsetAsync(d_sec_out, 0, n_seg * 4 + 16, ctx->stream));
+            MKID_CUDA(ctx, cudaMemsetAsync(meta, 0, 48 + (size_t)n_seg * 4, ctx->stream));
         }
     }
-
-    unsigned long long *d_state = nullptr;
-    rc = mkid_scratch(ctx, SCR_STATE, (size_t)(n_chunks + 1) * 8, (void **)&d_state);
-    if (rc) return rc;
-    MKID_CUDA(ctx, cudaMemsetAsync(d_state, 0, (size_t)(n_chunks + 1) * 8, ctx->stream));
 
     const void *d_in = nullptr;
     const size_t in_bytes = wire_fmt ? (size_t)n_units * 2 * DEC_BUNDLE * 4 : (size_t)n_units * 8;
     rc = mkid_stage_in(ctx, wire_fmt ? (const void *)wire : (const void *)words, in_bytes, SCR_IN, &d_in);
     if (rc) return rc;
+    MKID_REQUIRE(ctx, (reinterpret_cast<uintptr_t>(d_in) & (wire_fmt ? 15 : 7)) == 0, "decode: input must be 8-byte (words) / 16-byte (wire) aligned");
     const void *d_lut = nullptr;
     if (want_hist && cfg->bin_lut) {
         rc = mkid_stage_in(ctx, cfg->bin_lut, 4096 * 2, SCR_AUX0, &d_lut);
@@ -553,48 +604,55 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
         if (rc) return rc;
     }
 
-    DecParams p;
-    p.words = wire_fmt ? nullptr : (const uint64_t *)d_in;
-    p.wire = wire_fmt ? (const uint32_t *)d_in : nullptr;
-    p.seg_first_chunk = d_first; p.seg_offset = d_off; p.seg_len = d_len; p.seg_roach = d_roach; p.seg_sec = d_sec;
-    p.seg_sec_out = d_sec_out; p.n_seg = n_seg; p.n_chunks = n_chunks;
-    p.n_roaches = cfg->n_roaches; p.npix_per_roach = cfg->npix_per_roach; p.exptime = cfg->exptime;
-    p.field_shift = want_hist ? cfg->hist_field_shift : 0; p.n_bins = want_hist ? cfg->n_bins : 0;
-    p.bin_lut = (const uint16_t *)d_lut; p.counts = (uint32_t *)d_counts; p.hist = (uint32_t *)d_hist;
-    p.stats = d_stats; p.state = d_state; p.ticket = d_ticket;
-    p.prof = nullptr;
-    static const bool want_prof = getenv("MKID_DEC_PROFILE") != nullptr;
-    if (want_prof) {
-        void *pb = nullptr;
-        if ((rc = mkid_scratch(ctx, SCR_AUX5, 64, &pb))) return rc;
-        MKID_CUDA(ctx, cudaMemsetAsync(pb, 0, 64, ctx->stream));
-        p.prof = (unsigned long long *)pb;
-    }
+    if (n_ranges > 0) {
+        DecRange *d_ranges; DecRangeOut *d_rout; uint32_t *d_rows;
+        if ((rc = mkid_scratch(ctx, SCR_AUX2, (size_t)n_ranges * sizeof(DecRange), (void **)&d_ranges))) return rc;
+        if ((rc = mkid_scratch(ctx, SCR_STATE, (size_t)n_ranges * (sizeof(DecRangeOut) + 4), (void **)&d_rout))) return rc;
+        if ((rc = mkid_scratch(ctx, SCR_AUX4, (size_t)n_ranges * DEC_MAX_LS * DEC_ROW * 4, (void **)&d_rows))) return rc;
+        int32_t *d_base = (int32_t *)(d_rout + n_ranges);
+        {
+            std::vector<char> blob((const char *)ranges.data(), (const char *)ranges.data() + ranges.size() * sizeof(DecRange));
+            if (ctx->dec_ranges_dev != d_ranges || ctx->dec_ranges_host != blob) {
+                MKID_CUDA(ctx, cudaMemcpyAsync(d_ranges, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+                MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+                ctx->dec_ranges_host.swap(blob);
+                ctx->dec_ranges_dev = d_ranges;
+            }
+        }
+        DecParams p;
+        p.words = wire_fmt ? nullptr : (const uint64_t *)d_in;
+        p.wire = wire_fmt ? (const uint32_t *)d_in : nullptr;
+        p.ranges = d_ranges; p.rout = d_rout; p.n_ranges = n_ranges; p.rows = d_rows; p.base = d_base; p.flag = d_flag;
+        p.n_pix = (int)n_pix; p.npix_per_roach = cfg->npix_per_roach; p.exptime = cfg->exptime;
+        p.field_shift = want_hist ? cfg->hist_field_shift : 0; p.n_bins = want_hist ? cfg->n_bins : 0;
+        p.bin_lut = (const uint16_t *)d_lut; p.counts = (uint32_t *)d_counts; p.hist = (uint32_t *)d_hist;
+        p.stats = d_stats;
 
-    if (n_chunks > 0) {
-        const bool smem_hist = want_hist && (int64_t)cfg->npix_per_roach * (cfg->n_bins + 1) <= DEC_SMEM_HIST;
-        int grid = (int)std::min<int64_t>(n_chunks, (int64_t)ctx->num_sms);   // persistent: one CTA per SM
-        const size_t dyn = (size_t)DEC_STAGES * DEC_STAGE_BYTES;
-        auto launch = [&](auto kern) -> cudaError_t {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-            if (e != cudaSuccess) return e;
-            kern<<<grid, DEC_THREADS, dyn, ctx->stream>>>(p);
-            return cudaSuccess;
+        const bool smem_hist = want_hist && (int64_t)cfg->npix_per_roach * cfg->n_bins <= DEC_SMEM_HIST;
+        const int grid = (int)std::min<int64_t>((n_ranges + DEC_WARPS - 1) / DEC_WARPS, (int64_t)ctx->num_sms * DEC_CTAS_PER_SM);
+        const int hist_mode = !want_hist ? 0 : smem_hist ? 2 : 1;
+        auto stream_pass = [&](auto abs_tag) {
+            constexpr bool ABS = decltype(abs_tag)::value;
+            if (wire_fmt) {
+                if (hist_mode == 0) decode_stream_kernel<true, 0, ABS><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
+                else if (hist_mode == 1) decode_stream_kernel<true, 1, ABS><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
+                else decode_stream_kernel<true, 2, ABS><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
+            } else {
+                if (hist_mode == 0) decode_stream_kernel<false, 0, ABS><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
+                else if (hist_mode == 1) decode_stream_kernel<false, 1, ABS><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
+                else decode_stream_kernel<false, 2, ABS><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
+            }
         };
-        cudaError_t le;
-        if (wire_fmt) le = smem_hist ? launch(decode_kernel<true, true>) : launch(decode_kernel<true, false>);
-        else le = smem_hist ? launch(decode_kernel<false, true>) : launch(decode_kernel<false, false>);
-        MKID_CUDA(ctx, le);
+        stream_pass(std::false_type{});                      // relative pass: every word is read here, once
         MKID_CHECK_LAUNCH(ctx);
-    }
-    if (p.prof) {
-        unsigned long long h[8];
-        MKID_CUDA(ctx, cudaMemcpyAsync(h, p.prof, 64, cudaMemcpyDeviceToHost, ctx->stream));
-        MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        const double n = h[7] ? (double)h[7] : 1.0;
-        fprintf(stderr, "[mkid decode profile] chunks %llu | scout cycles/chunk: wait-free %.0f ticket %.0f load %.0f scan %.0f "
-                        "lookback %.0f | workers cycles/chunk: wait-ready %.0f process %.0f\n", h[7], h[0] / n, h[1] / n,
-                h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n);
+        decode_prefix_kernel<<<1, 1024, 0, ctx->stream>>>(d_ranges, d_rout, n_ranges, d_sec, d_sec_out, d_base);
+        MKID_CHECK_LAUNCH(ctx);
+        const int cgrid = std::min(n_ranges, ctx->num_sms * 8);
+        if (wire_fmt) decode_commit_kernel<true><<<cgrid, 256, 0, ctx->stream>>>(p);
+        else decode_commit_kernel<false><<<cgrid, 256, 0, ctx->stream>>>(p);
+        MKID_CHECK_LAUNCH(ctx);
+        stream_pass(std::true_type{});                       // absolute pass: exits at once unless a range overflowed
+        MKID_CHECK_LAUNCH(ctx);
     }
     rc = mkid_stage_out_finish(ctx, counts_raw, counts_bytes, d_counts);
     if (rc) return rc;
@@ -603,28 +661,23 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
         if (rc) return rc;
     }
     if (seg_sec_out) {
-        if (n_chunks == 0) { for (int i = 0; i < n_seg; ++i) seg_sec_out[i] = sec0[i]; }
-        else {
-            std::vector<int32_t> tmp(n_seg);
-            MKID_CUDA(ctx, cudaMemcpyAsync(tmp.data(), d_sec_out, n_seg * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        std::vector<int32_t> tmp(n_seg, 0);
+        if (n_ranges > 0) {
+            MKID_CUDA(ctx, cudaMemcpyAsync(tmp.data(), d_sec_out, (size_t)n_seg * 4, cudaMemcpyDeviceToHost, ctx->stream));
             MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            for (int i = 0; i < n_seg; ++i)
-                seg_sec_out[i] = (first_chunk[i + 1] == first_chunk[i]) ? sec0[i] : tmp[i];
         }
+        for (int i = 0; i < n_seg; ++i) seg_sec_out[i] = seg_chunks[i] == 0 ? sec0[i] : tmp[i];
     }
     if (stats) {
+        unsigned long long h[5];
+        MKID_CUDA(ctx, cudaMemcpyAsync(h, d_stats, 40, cudaMemcpyDeviceToHost, ctx->stream));
+        MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         if (mkid_is_device_ptr(stats)) {
-            unsigned long long h[5];
-            MKID_CUDA(ctx, cudaMemcpyAsync(h, d_stats, 40, cudaMemcpyDeviceToHost, ctx->stream));
-            MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             mkid_decode_stats cur;
             MKID_CUDA(ctx, cudaMemcpy(&cur, stats, sizeof(cur), cudaMemcpyDeviceToHost));
             cur.n_eos += h[0]; cur.n_corrupt_eos += h[1]; cur.n_nonpixel += h[2]; cur.n_ignored += h[3]; cur.n_valid += h[4];
             MKID_CUDA(ctx, cudaMemcpy(stats, &cur, sizeof(cur), cudaMemcpyHostToDevice));
         } else {
-            unsigned long long h[5];
-            MKID_CUDA(ctx, cudaMemcpyAsync(h, d_stats, 40, cudaMemcpyDeviceToHost, ctx->stream));
-            MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             stats->n_eos += h[0]; stats->n_corrupt_eos += h[1]; stats->n_nonpixel += h[2];
             stats->n_ignored += h[3]; stats->n_valid += h[4];
         }
