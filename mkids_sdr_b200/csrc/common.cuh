@@ -25,7 +25,7 @@ struct mkid_ctx {
     // last segment table uploaded by the decode path (skips re-upload when unchanged)
     std::vector<char> dec_meta_host;
     void *dec_meta_dev = nullptr;
-    std::vector<char> dec_ranges_host;
+    std::vector<char> dec_ranges_host, dec_key;
     void *dec_ranges_dev = nullptr;
     size_t l2_flush_bytes = 0;
 };

@@ -14,10 +14,10 @@
 //     of its range).  When an end-of-second word closes a local second the row is written to
 //     rows[range][local second] and cleared.  No warp ever waits for another warp or CTA: no barriers, no
 //     look-back, no tickets.
-//   * decode_prefix_kernel (1 CTA): segmented exclusive scan of the ranges' end-of-second totals
-//     -> absolute second at the start of every range (+ seg_sec_out).
-//   * decode_commit_kernel: rows[range][ls] -> counts[base+ls][pixel], statistics; rows that turn out to
-//     lie beyond exptime are dropped and their histogram contribution is taken back.
+//   * decode_commit_kernel (one CTA per 16 ranges): sum of the end-of-second totals of the earlier ranges of the
+//     segment -> absolute second at the start of the range (+ seg_sec_out); rows[range][ls] summed per
+//     (roach, second) -> counts[second][pixel], statistics; rows that turn out to lie beyond exptime are
+//     dropped and their histogram contribution is taken back.
 //   * decode_stream_kernel<ABS> (gated on a device flag, normally exits at once): ranges with more than
 //     DEC_MAX_LS seconds are finished from the recorded resume point with the now known absolute second.
 #include <stdlib.h>
@@ -33,21 +33,20 @@ constexpr int DEC_THREADS = DEC_WARPS * 32;
 constexpr int DEC_CTAS_PER_SM = 2;
 constexpr int DEC_CHUNK = 4096;                    // words per chunk (wire format: half a bundle)
 constexpr int DEC_BUNDLE = 8192;                   // PacketMaster.c:44 BUFSIZE_INTS
-constexpr int DEC_BATCH = 256;                     // words per warp iteration (2 KiB)
+constexpr int DEC_UNIT = 256;                      // flat format: ranges are whole multiples of this many words
 constexpr int DEC_MAX_LS = 4;                      // local seconds kept per range on the relative pass
-constexpr int DEC_ROW = 264;                       // u32 per row: 256 pixels | non-pixel | corrupt EOS | words | start
+constexpr int DEC_ROW = 264;                       // u32 per row: 256 channels | - | corrupt EOS | words | start
 constexpr int DEC_SMEM_HIST = 4096;                // smem-privatised histogram entries per CTA
 
 struct DecRange {
     long long start;       // flat: first word (relative to words); wire: first half-bundle chunk
     int n_words;           // words in the range
-    int roach, seg, first_of_seg;
+    int roach, seg;
+    int seg_first;         // index of the first range of this range's segment
 };
 struct DecRangeOut {
-    int eos_total;         // end-of-second words in the range
     int n_ls;              // rows written on the relative pass (<= DEC_MAX_LS)
     int resume;            // < 0: range done; else first word the absolute pass must handle
-    int pad;
 };
 
 struct DecParams {
@@ -55,11 +54,14 @@ struct DecParams {
     const uint32_t *wire;      // wire format (or nullptr)
     const DecRange *ranges;
     DecRangeOut *rout;
+    int32_t *eos_tot;          // [n_ranges] end-of-second words per range
+    const int32_t *seg_sec;    // [n_seg] seconds closed before each segment
+    int32_t *seg_sec_out;      // [n_seg] ... and after it
     int n_ranges;
     uint32_t *rows;            // [n_ranges][DEC_MAX_LS][DEC_ROW]
-    const int32_t *base;       // [n_ranges] absolute second at the start of each range (absolute pass)
+    int32_t *base;             // [n_ranges] absolute second at the start of each range (commit -> absolute pass)
     int *flag;                 // != 0: some range needs the absolute pass
-    int n_pix, npix_per_roach, exptime, n_bins, field_shift;
+    int n_pix, npix_per_roach, exptime, n_bins, field_shift, map_mode;
     const uint16_t *bin_lut;
     uint32_t *counts;          // [exptime][n_pix]
     uint32_t *hist;            // [n_pix][n_bins] or nullptr
@@ -80,15 +82,23 @@ __device__ __forceinline__ uint32_t ld_stream_u1(const uint32_t *p) {
 }
 
 // One warp, one range.  J = words per lane per 128-bit load group (flat 2, wire 4), U = groups per batch.
+// One warp, one range.  J = words per lane per load group (flat: one 128-bit load = 2 words; wire: one 128-bit load
+// of low halves + one of high halves = 4 words); a group is 32*J consecutive words; R groups are kept in flight.
 // HIST: 0 = counts only, 1 = pulse-height histogram by global reductions, 2 = through the CTA's shared-memory copy
-template <bool WIRE, int HIST, bool ABS>
+// NEED_LO: the fast path also needs the low 32 bits of every word (histogram of the baseline field); otherwise only
+// the high halves are moved into registers (the DRAM sectors are the same, the register and L1 traffic halves)
+template <bool WIRE, int HIST, bool NEED_LO, bool ABS>
 struct RangeDecoder {
     static constexpr int J = WIRE ? 4 : 2;
-    static constexpr int U = DEC_BATCH / (32 * J);
+    static constexpr int G = 32 * J;                   // words per group
+    static constexpr int R = (WIRE ? 4 : 8) / (NEED_LO ? 2 : 1);   // ring depth: 16 registers, 512 (256) words per warp in flight
+    // position of (lane, j) inside a group: flat = lane-contiguous 32/64-bit loads, wire = one 128-bit load per lane
+    __device__ __forceinline__ int idx_of(int j) const { return WIRE ? 4 * lane + j : 32 * j + lane; }
 
     const DecParams &p;
-    uint32_t *cnt;             // this warp's shared-memory row [256]
-    uint32_t *s_hist;          // CTA histogram of roach cta_roach (SMEM_HIST)
+    uint32_t *cnt;             // this warp's shared-memory row [256]: entry adr counts words of channel adr
+    uint32_t cnt_s;            //   (channels >= npix_per_roach are the "non-pixel" words), as a shared address
+    uint32_t hist_s;           // CTA histogram of roach cta_roach (HIST == 2), shared address
     const uint16_t *s_lut;
     uint32_t *hist_r;          // global histogram of this range's roach
     int lane, r, roach, npix, n_bins, f_sh;
@@ -104,21 +114,21 @@ struct RangeDecoder {
     bool count_only;           // REL: more than DEC_MAX_LS seconds, only count end-of-second words from here on
     bool stop;                 // ABS: exptime reached
     int resume;
-    unsigned n_nonpix, n_bad;                          // per lane, current second
+    unsigned n_bad;                                    // per lane, current second
     unsigned st_eos, st_bad, st_nonpix, st_valid;      // ABS: per lane totals
     unsigned long long st_ign;
 
     __device__ __forceinline__ RangeDecoder(const DecParams &p_) : p(p_) {}
 
     __device__ __forceinline__ void bin(uint32_t hi, uint32_t lo) {
-        const uint32_t adr = hi >> 24;
-        if ((int)adr >= npix) { ++n_nonpix; return; }          // (adr == 255 never gets here)
-        atomicAdd(&cnt[adr], 1u);
+        const uint32_t adr = hi >> 24;                                   // (adr == 255 never gets here)
+        asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(cnt_s + adr * 4) : "memory");
         if (HIST) {
+            if ((int)adr >= npix) return;
             const uint32_t f = ((f_hi ? hi : lo) >> f_sh) & 0xFFFu;
             const uint32_t b = use_lut ? s_lut[f] : f;
             if ((int)b < n_bins) {
-                if (HIST == 2 && own_roach) atomicAdd(&s_hist[adr * n_bins + b], 1u);
+                if (HIST == 2 && own_roach) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_s + (adr * n_bins + b) * 4) : "memory");
                 else atomicAdd(&hist_r[adr * n_bins + b], 1u);
             }
         }
@@ -127,8 +137,8 @@ struct RangeDecoder {
     // the second that ends with the word at position pe (or with the range: pe = n_words - 1, closed = false)
     __device__ __forceinline__ void flush(int pe, bool closed) {
         __syncwarp();
-        const unsigned np = warp_sum(n_nonpix), nb = warp_sum(n_bad);
-        n_nonpix = n_bad = 0;
+        const unsigned nb = warp_sum(n_bad);
+        n_bad = 0;
         if (!ABS) {
             uint32_t *row = p.rows + ((size_t)r * DEC_MAX_LS + sec) * DEC_ROW;
             uint4 a = reinterpret_cast<uint4 *>(cnt)[lane * 2], b = reinterpret_cast<uint4 *>(cnt)[lane * 2 + 1];
@@ -137,7 +147,7 @@ struct RangeDecoder {
             reinterpret_cast<uint4 *>(cnt)[lane * 2] = make_uint4(0, 0, 0, 0);
             reinterpret_cast<uint4 *>(cnt)[lane * 2 + 1] = make_uint4(0, 0, 0, 0);
             if (lane == 0) {
-                row[256] = np; row[257] = nb;
+                row[256] = 0; row[257] = nb;
                 row[258] = (unsigned)(pe + 1 - row_start);
                 row[259] = (unsigned)row_start;
             }
@@ -145,9 +155,13 @@ struct RangeDecoder {
             uint32_t *dst = p.counts + (size_t)sec * p.n_pix + (size_t)roach * npix;
             for (int i = lane; i < 256; i += 32) {
                 const uint32_t v = cnt[i];
-                if (v) { atomicAdd(&dst[i], v); cnt[i] = 0; st_valid += v; }
+                if (v) {
+                    cnt[i] = 0;
+                    if (i < npix) { atomicAdd(&dst[i], v); st_valid += v; }
+                    else st_nonpix += v;
+                }
             }
-            if (lane == 0) { st_nonpix += np; st_bad += nb; st_eos += closed ? 1u : 0u; }
+            if (lane == 0) { st_bad += nb; st_eos += closed ? 1u : 0u; }
         }
         __syncwarp();
     }
@@ -166,7 +180,7 @@ struct RangeDecoder {
         }
     }
 
-    // ordered path for one load group: lane holds words idx = J*lane + j at positions pos_base + idx;
+    // ordered path for one group: lane holds words idx_of(j) at positions pos_base + idx_of(j);
     // valid: bit j set if that word exists and is to be handled
     __device__ __forceinline__ void slow_group(const uint32_t (&hi)[J], const uint32_t (&lo)[J], unsigned valid, int pos_base) {
         unsigned e = 0;
@@ -179,98 +193,101 @@ struct RangeDecoder {
             if (count_only) {
                 unsigned c = 0;
 #pragma unroll
-                for (int j = 0; j < J; ++j) c += ((e >> j) & 1u) && (J * lane + j >= done);
+                for (int j = 0; j < J; ++j) c += ((e >> j) & 1u) && (idx_of(j) >= done);
                 eos_total += (int)warp_sum(c);
                 return;
             }
             int cand = 0x7fffffff;
 #pragma unroll
             for (int j = J - 1; j >= 0; --j)
-                if (((e >> j) & 1u) && J * lane + j >= done) cand = J * lane + j;
+                if (((e >> j) & 1u) && idx_of(j) >= done) cand = idx_of(j);
             const int pe = __reduce_min_sync(0xffffffffu, cand);
 #pragma unroll
             for (int j = 0; j < J; ++j) {
-                const int idx = J * lane + j;
+                const int idx = idx_of(j);
                 if (((valid >> j) & 1u) && idx >= done && idx < pe) bin(hi[j], lo[j]);
             }
             if (pe == 0x7fffffff) return;
 #pragma unroll
             for (int j = 0; j < J; ++j)
-                if (J * lane + j == pe && (hi[j] & lo[j]) != 0xFFFFFFFFu) ++n_bad;      // "Corrupted EOS!" PacketMaster.c:331
+                if (idx_of(j) == pe && (hi[j] & lo[j]) != 0xFFFFFFFFu) ++n_bad;      // "Corrupted EOS!" PacketMaster.c:331
             close_second(pos_base + pe);
             done = pe + 1;
         }
     }
 
-    // batch with per-word guards: words at positions [b0, b0 + DEC_BATCH) restricted to [lo_bound, n_words)
-    __device__ __forceinline__ void guarded_batch(int b0, int lo_bound) {
-#pragma unroll 1
-        for (int u = 0; u < U; ++u) {
-            uint32_t hi[J], lo[J];
-            unsigned valid = 0;
-            const int g0 = b0 + u * 32 * J;
+    // group with per-word guards: words at positions [g0, g0 + G) restricted to [lo_bound, n_words)
+    __device__ __forceinline__ void guarded_group(int g0, int lo_bound) {
+        uint32_t hi[J], lo[J];
+        unsigned valid = 0;
 #pragma unroll
-            for (int j = 0; j < J; ++j) {
-                const int pos = g0 + J * lane + j;
-                hi[j] = lo[j] = 0;
-                if (pos >= lo_bound && pos < n_words && pos >= 0) {
-                    valid |= 1u << j;
-                    if (WIRE) {
-                        const long long hc = wire_chunk0 + (pos >> 12);
-                        const uint32_t *lp = w_wire + (size_t)(hc >> 1) * (2 * DEC_BUNDLE) + (size_t)(hc & 1) * DEC_CHUNK + (pos & 4095);
-                        lo[j] = bswap32(ld_stream_u1(lp));
-                        hi[j] = bswap32(ld_stream_u1(lp + DEC_BUNDLE));
-                    } else {
-                        const uint2 v = ld_stream_u2(w_flat + pos);
-                        lo[j] = v.x; hi[j] = v.y;
-                    }
+        for (int j = 0; j < J; ++j) {
+            const int pos = g0 + idx_of(j);
+            hi[j] = lo[j] = 0;
+            if (pos >= lo_bound && pos < n_words && pos >= 0) {
+                valid |= 1u << j;
+                if (WIRE) {
+                    const long long hc = wire_chunk0 + (pos >> 12);
+                    const uint32_t *lp = w_wire + (size_t)(hc >> 1) * (2 * DEC_BUNDLE) + (size_t)(hc & 1) * DEC_CHUNK + (pos & 4095);
+                    lo[j] = bswap32(ld_stream_u1(lp));
+                    hi[j] = bswap32(ld_stream_u1(lp + DEC_BUNDLE));
+                } else {
+                    const uint2 v = ld_stream_u2(w_flat + pos);
+                    lo[j] = v.x; hi[j] = v.y;
                 }
             }
-            if (__any_sync(0xffffffffu, valid != 0)) slow_group(hi, lo, valid, g0);
         }
+        slow_group(hi, lo, valid, g0);
     }
 
-    struct Batch { uint4 v[WIRE ? 2 * U : U]; };
+    struct Group { uint32_t hi[J], lo[NEED_LO ? J : 1]; };     // wire: still big-endian
 
-    __device__ __forceinline__ void load_batch(Batch &bt, int b0) const {
+    __device__ __forceinline__ void load_group(Group &g, int pos) const {
         if (WIRE) {
-            const long long hc = wire_chunk0 + (b0 >> 12);
-            const uint32_t *lp = w_wire + (size_t)(hc >> 1) * (2 * DEC_BUNDLE) + (size_t)(hc & 1) * DEC_CHUNK + (b0 & 4095) + 4 * lane;
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                bt.v[2 * u] = ld_stream_u4(reinterpret_cast<const uint4 *>(lp + u * 128));
-                bt.v[2 * u + 1] = ld_stream_u4(reinterpret_cast<const uint4 *>(lp + u * 128 + DEC_BUNDLE));
+            const long long hc = wire_chunk0 + (pos >> 12);
+            const uint32_t *lp = w_wire + (size_t)(hc >> 1) * (2 * DEC_BUNDLE) + (size_t)(hc & 1) * DEC_CHUNK + (pos & 4095) + 4 * lane;
+            const uint4 h = ld_stream_u4(reinterpret_cast<const uint4 *>(lp + DEC_BUNDLE));
+            g.hi[0] = h.x; g.hi[1] = h.y; g.hi[2] = h.z; g.hi[3] = h.w;
+            if (NEED_LO) {
+                const uint4 l = ld_stream_u4(reinterpret_cast<const uint4 *>(lp));
+                g.lo[0] = l.x; g.lo[1] = l.y; g.lo[2 % J] = l.z; g.lo[3 % J] = l.w;
             }
         } else {
-            const uint4 *q = reinterpret_cast<const uint4 *>(w_flat + b0) + lane;
 #pragma unroll
-            for (int u = 0; u < U; ++u) bt.v[u] = ld_stream_u4(q + u * 32);
+            for (int j = 0; j < J; ++j) {
+                const uint64_t *q = w_flat + pos + 32 * j + lane;
+                if (NEED_LO) { const uint2 v = ld_stream_u2(q); g.lo[j] = v.x; g.hi[j] = v.y; }
+                else g.hi[j] = ld_stream_u1(reinterpret_cast<const uint32_t *>(q) + 1);
+            }
+        }
+    }
+    __device__ __forceinline__ bool has_eos(const Group &g) const {
+        bool any = false;
+#pragma unroll
+        for (int j = 0; j < J; ++j) any |= WIRE ? (g.hi[j] & 0xFFu) == 0xFFu : g.hi[j] >= 0xFF000000u;
+        return __any_sync(0xffffffffu, any);
+    }
+    __device__ __forceinline__ void bin_group(const Group &g) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+            const uint32_t lo = NEED_LO ? g.lo[j] : 0u;
+            if (WIRE) bin(bswap32(g.hi[j]), bswap32(lo));
+            else bin(g.hi[j], lo);
         }
     }
 
-    // bins a full batch if it holds no end-of-second word (almost always); else returns false, nothing done
-    __device__ __forceinline__ bool fast_batch(const Batch &bt) {
-        bool any = false;
+    // one revolution of the ring starting at pos; CHECK: the range may end inside.  Returns false when the ring
+    // has to be left: ragged tail reached, or (force) the group at pos holds an end-of-second word.
+    template <bool CHECK>
+    __device__ __forceinline__ bool ring_round(Group (&ring)[R], int &pos, bool &force) {
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (WIRE) {
-                const uint4 h = bt.v[2 * u + 1];      // big-endian: the channel byte is the low byte
-                any |= ((h.x & 0xFFu) == 0xFFu) | ((h.y & 0xFFu) == 0xFFu) | ((h.z & 0xFFu) == 0xFFu) | ((h.w & 0xFFu) == 0xFFu);
-            } else {
-                any |= ((bt.v[u].y >> 24) == 0xFFu) | ((bt.v[u].w >> 24) == 0xFFu);
-            }
-        }
-        if (__any_sync(0xffffffffu, any)) return false;
-        if (count_only) return true;
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (WIRE) {
-                const uint4 l = bt.v[2 * u], h = bt.v[2 * u + 1];
-                bin(bswap32(h.x), bswap32(l.x)); bin(bswap32(h.y), bswap32(l.y));
-                bin(bswap32(h.z), bswap32(l.z)); bin(bswap32(h.w), bswap32(l.w));
-            } else {
-                bin(bt.v[u].y, bt.v[u].x); bin(bt.v[u].w, bt.v[u].z);
-            }
+        for (int g = 0; g < R; ++g) {
+            if (CHECK && pos + G > n_words) return false;
+            const Group x = ring[g];
+            if (!CHECK || pos + (R + 1) * G <= n_words) load_group(ring[g], pos + R * G);
+            if (has_eos(x)) { force = true; return false; }
+            if (!count_only) bin_group(x);
+            pos += G;
         }
         return true;
     }
@@ -283,7 +300,7 @@ struct RangeDecoder {
         w_flat = WIRE ? nullptr : p.words + rg.start;
         w_wire = p.wire; wire_chunk0 = rg.start;
         sec = 0; row_start = 0; eos_total = 0; count_only = false; stop = false; resume = -1;
-        n_nonpix = n_bad = 0;
+        n_bad = 0;
         int lo_bound = 0;
         if (ABS) {
             const DecRangeOut ro = p.rout[r];
@@ -295,31 +312,34 @@ struct RangeDecoder {
                 return;
             }
         }
-        // batches are anchored at a0 so that full batches are 16-byte aligned; the batch before the anchor (one
-        // word), the batch an absolute pass resumes in, the ragged tail and every batch that holds an
-        // end-of-second word go through the guarded, ordered path
-        const int a0 = WIRE ? 0 : (int)((reinterpret_cast<uintptr_t>(w_flat) >> 3) & 1);
-        int b = lo_bound < a0 ? a0 - DEC_BATCH : a0 + (lo_bound - a0) / DEC_BATCH * DEC_BATCH;
-        Batch cur;
-        bool have = false;
+        // The group an absolute pass resumes in, the ragged tail and every group that holds an end-of-second word
+        // go through the guarded, ordered path; everything else through the ring.
+        int pos = lo_bound / G * G;
+        bool force = false;
 #pragma unroll 1
-        for (; b < n_words && !stop; b += DEC_BATCH) {
-            bool guard = true;
-            if (b >= lo_bound && b + DEC_BATCH <= n_words) {
-                if (!have) load_batch(cur, b);
-                Batch nxt;
-                have = b + 2 * DEC_BATCH <= n_words;
-                if (have) load_batch(nxt, b + DEC_BATCH);
-                guard = !fast_batch(cur);
-                cur = nxt;
+        while (pos < n_words && !stop) {
+            if (force || pos < lo_bound || pos + G > n_words) {
+                guarded_group(pos, lo_bound);
+                pos += G;
+                force = false;
+                continue;
             }
-            if (guard) guarded_batch(b, lo_bound);
+            Group ring[R];
+#pragma unroll
+            for (int g = 0; g < R; ++g)
+                if (pos + (g + 1) * G <= n_words) load_group(ring[g], pos + g * G);
+            bool go = true;
+#pragma unroll 1
+            while (go && pos + 2 * R * G <= n_words) go = ring_round<false>(ring, pos, force);
+#pragma unroll 1
+            while (go) go = ring_round<true>(ring, pos, force);
         }
         if (!ABS) {
             int n_ls = DEC_MAX_LS;
             if (!count_only) { flush(n_words - 1, false); n_ls = sec + 1; }
             if (lane == 0) {
-                p.rout[r] = DecRangeOut{eos_total, n_ls, resume, 0};
+                p.rout[r] = DecRangeOut{n_ls, resume};
+                p.eos_tot[r] = eos_total;
                 if (resume >= 0) atomicOr(p.flag, 1);
             }
         } else if (!stop) {
@@ -328,7 +348,7 @@ struct RangeDecoder {
     }
 };
 
-template <bool WIRE, int HIST, bool ABS>
+template <bool WIRE, int HIST, bool NEED_LO, bool ABS>
 __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_stream_kernel(DecParams p) {
     __shared__ __align__(16) uint32_t s_cnt[DEC_WARPS][256];
     __shared__ uint32_t s_hist[HIST == 2 ? DEC_SMEM_HIST : 1];
@@ -344,9 +364,10 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_stream_ke
     __syncthreads();
 
     int r = blockIdx.x * DEC_WARPS + warp;
+    if (p.map_mode == 1 && HIST != 2) r = warp * gridDim.x + blockIdx.x;      // (experiment: warps of a CTA far apart)
     const int cta_roach = blockIdx.x * DEC_WARPS < p.n_ranges ? p.ranges[blockIdx.x * DEC_WARPS].roach : -1;
-    RangeDecoder<WIRE, HIST, ABS> d(p);
-    d.cnt = s_cnt[warp]; d.s_hist = s_hist; d.s_lut = s_lut; d.lane = lane;
+    RangeDecoder<WIRE, HIST, NEED_LO, ABS> d(p);
+    d.cnt = s_cnt[warp]; d.cnt_s = mk_smem_u32(s_cnt[warp]); d.hist_s = mk_smem_u32(s_hist); d.s_lut = s_lut; d.lane = lane;
     d.npix = p.npix_per_roach; d.n_bins = p.n_bins;
     d.use_lut = use_lut;
     d.f_hi = p.field_shift >= 32; d.f_sh = p.field_shift & 31;
@@ -375,79 +396,95 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_stream_ke
     }
 }
 
-// segmented exclusive scan of the ranges' end-of-second totals (one CTA)
-__global__ void __launch_bounds__(1024) decode_prefix_kernel(const DecRange *ranges, const DecRangeOut *rout, int n,
-                                                             const int32_t *seg_sec, int32_t *seg_sec_out, int32_t *base) {
-    __shared__ int s_sum[1024];
-    __shared__ int s_head[1024];
-    const int t = threadIdx.x;
-    const int K = (n + 1023) / 1024;
-    const int i0 = min(n, t * K), i1 = min(n, i0 + K);
-    int sum = 0, head = 0;
-    for (int i = i0; i < i1; ++i) {
-        if (ranges[i].first_of_seg) { sum = seg_sec[ranges[i].seg]; head = 1; }
-        sum += rout[i].eos_total;
-    }
-    s_sum[t] = sum; s_head[t] = head;
-    __syncthreads();
-    for (int d = 1; d < 1024; d <<= 1) {          // inclusive scan with (a o b) = (b.head ? b.sum : a.sum + b.sum, a.head | b.head)
-        int a_sum = 0, a_head = 0;
-        if (t >= d) { a_sum = s_sum[t - d]; a_head = s_head[t - d]; }
-        __syncthreads();
-        if (t >= d) {
-            if (!s_head[t]) s_sum[t] += a_sum;
-            s_head[t] |= a_head;
-        }
-        __syncthreads();
-    }
-    int run = t > 0 ? s_sum[t - 1] : 0;
-    for (int i = i0; i < i1; ++i) {
-        if (ranges[i].first_of_seg) run = seg_sec[ranges[i].seg];
-        base[i] = run;
-        run += rout[i].eos_total;
-        if (seg_sec_out && (i + 1 == n || ranges[i + 1].first_of_seg)) seg_sec_out[ranges[i].seg] = run;
-    }
-}
-
-// rows[range][local second] -> counts[second][pixel] + statistics; rows beyond exptime are dropped and their
-// histogram contribution (made before the second was known) is taken back
+// One CTA per DEC_COMMIT_RANGES consecutive ranges, thread t = channel t.  Absolute second at the start of every
+// range (sum of the end-of-second totals of the earlier ranges of its segment), then
+// rows[range][local second] -> counts[second][pixel] + statistics.  Consecutive ranges mostly lie in the same
+// (roach, second): their rows are summed in a register and reach counts[] as ONE reduction per pixel (the rows
+// of all ranges aimed at the same few thousand addresses would serialise in the L2 atomic units).  Rows that turn
+// out to lie beyond exptime are dropped and their histogram contribution (made before the second was known)
+// is taken back.
+constexpr int DEC_COMMIT_RANGES = 16;
 template <bool WIRE>
 __global__ void __launch_bounds__(256) decode_commit_kernel(DecParams p) {
+    constexpr int CR = DEC_COMMIT_RANGES;
     __shared__ unsigned long long s_st[5];
-    const int tid = threadIdx.x;
+    __shared__ int s_part[8];
+    __shared__ int s_base[CR], s_nls[CR], s_eos[CR], s_roach[CR], s_seg[CR], s_first[CR];
+    __shared__ unsigned s_bad0[CR];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 5) s_st[tid] = 0;
+    const int r0 = blockIdx.x * CR;
+    const int n_here = min(CR, p.n_ranges - r0);
+    const int f0 = p.ranges[r0].seg_first;
+    int part = 0;
+    for (int i = f0 + tid; i < r0; i += 256) part += p.eos_tot[i];
+    part = (int)warp_sum((unsigned)part);
+    if (lane == 0) s_part[warp] = part;
+    if (tid < n_here) {
+        const DecRange rg = p.ranges[r0 + tid];
+        s_nls[tid] = p.rout[r0 + tid].n_ls;
+        s_eos[tid] = p.eos_tot[r0 + tid];
+        s_roach[tid] = rg.roach; s_seg[tid] = rg.seg; s_first[tid] = rg.seg_first;
+        s_bad0[tid] = p.rows[((size_t)(r0 + tid) * DEC_MAX_LS) * DEC_ROW + 257];
+    }
     __syncthreads();
-    unsigned long long eos = 0, bad = 0, nonpix = 0, ign = 0;
-    unsigned valid = 0;
+    if (tid == 0) {
+        int run = p.seg_sec[s_seg[0]];
+        for (int w = 0; w < 8; ++w) run += s_part[w];
+        for (int i = 0; i < n_here; ++i) {
+            if (s_first[i] == r0 + i) run = p.seg_sec[s_seg[i]];          // a segment starts here
+            s_base[i] = run;
+            p.base[r0 + i] = run;
+            run += s_eos[i];
+            const bool last_of_seg = r0 + i + 1 == p.n_ranges || (i + 1 < n_here ? s_seg[i + 1] != s_seg[i] : p.ranges[r0 + i + 1].seg != s_seg[i]);
+            if (last_of_seg && p.seg_sec_out) p.seg_sec_out[s_seg[i]] = run;
+        }
+    }
+    // first rows of all ranges: independent loads, one latency
+    uint32_t v0[CR];
+#pragma unroll
+    for (int i = 0; i < CR; ++i) v0[i] = i < n_here ? p.rows[((size_t)(r0 + i) * DEC_MAX_LS) * DEC_ROW + tid] : 0u;
+    __syncthreads();
+
+    unsigned long long eos = 0, bad = 0, ign = 0, valid = 0, nonpix = 0;
     const bool use_lut = p.bin_lut != nullptr;
     const bool f_hi = p.field_shift >= 32;
     const int f_sh = p.field_shift & 31;
-    for (int r = blockIdx.x; r < p.n_ranges; r += gridDim.x) {
-        const DecRangeOut ro = p.rout[r];
-        const DecRange rg = p.ranges[r];
-        const int base = p.base[r];
-        for (int ls = 0; ls < ro.n_ls; ++ls) {
+    const bool is_pix = tid < p.npix_per_roach;
+    uint32_t acc = 0;
+    int key_sec = -1, key_roach = -1;
+    auto flush_acc = [&]() {
+        if (acc) atomicAdd(&p.counts[(size_t)key_sec * p.n_pix + (size_t)key_roach * p.npix_per_roach + tid], acc);
+        acc = 0;
+    };
+#pragma unroll
+    for (int i = 0; i < CR; ++i) {
+        if (i >= n_here) break;
+        const int base = s_base[i], nls = s_nls[i], roach = s_roach[i];
+        for (int ls = 0; ls < nls; ++ls) {
             const int sec = base + ls;
-            const uint32_t *row = p.rows + ((size_t)r * DEC_MAX_LS + ls) * DEC_ROW;
+            const uint32_t *row = p.rows + ((size_t)(r0 + i) * DEC_MAX_LS + ls) * DEC_ROW;
             if (sec < p.exptime) {
-                if (tid < p.npix_per_roach) {
-                    const uint32_t v = row[tid];
-                    if (v) { atomicAdd(&p.counts[(size_t)sec * p.n_pix + (size_t)rg.roach * p.npix_per_roach + tid], v); valid += v; }
-                }
-                if (tid == 0) { nonpix += row[256]; bad += row[257]; eos += ls < ro.eos_total ? 1 : 0; }
+                const uint32_t v = ls == 0 ? v0[i] : row[tid];
+                if (is_pix) {
+                    if (sec != key_sec || roach != key_roach) { flush_acc(); key_sec = sec; key_roach = roach; }
+                    acc += v; valid += v;
+                } else if (tid < 255) nonpix += v;                // (channel 255 is never counted in a row)
+                if (tid == 0) { bad += ls == 0 ? s_bad0[i] : row[257]; eos += ls < s_eos[i] ? 1 : 0; }
                 continue;
             }
             const unsigned n_w = row[258], w0 = row[259];
             if (tid == 0) ign += n_w;
             if (!p.hist) continue;
-            for (unsigned w = w0 + tid; w < w0 + n_w; w += blockDim.x) {
+            const long long start = p.ranges[r0 + i].start;
+            for (unsigned w = w0 + tid; w < w0 + n_w; w += 256) {
                 uint32_t hi, lo;
                 if (WIRE) {
-                    const long long hc = rg.start + (w >> 12);
+                    const long long hc = start + (w >> 12);
                     const uint32_t *lp = p.wire + (size_t)(hc >> 1) * (2 * DEC_BUNDLE) + (size_t)(hc & 1) * DEC_CHUNK + (w & 4095);
                     lo = bswap32(lp[0]); hi = bswap32(lp[DEC_BUNDLE]);
                 } else {
-                    const uint64_t x = p.words[rg.start + w];
+                    const uint64_t x = p.words[start + w];
                     hi = (uint32_t)(x >> 32); lo = (uint32_t)x;
                 }
                 const uint32_t adr = hi >> 24;
@@ -455,22 +492,28 @@ __global__ void __launch_bounds__(256) decode_commit_kernel(DecParams p) {
                 const uint32_t f = ((f_hi ? hi : lo) >> f_sh) & 0xFFFu;
                 const uint32_t b = use_lut ? p.bin_lut[f] : f;
                 if ((int)b < p.n_bins)
-                    atomicAdd(&p.hist[((size_t)rg.roach * p.npix_per_roach + adr) * p.n_bins + b], 0xFFFFFFFFu);
+                    atomicAdd(&p.hist[((size_t)roach * p.npix_per_roach + adr) * p.n_bins + b], 0xFFFFFFFFu);
             }
         }
     }
-    valid = warp_sum(valid);
-    if ((tid & 31) == 0 && valid) atomicAdd(&s_st[4], (unsigned long long)valid);
+    if (is_pix) flush_acc();
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+        valid += __shfl_xor_sync(0xffffffffu, valid, d);
+        nonpix += __shfl_xor_sync(0xffffffffu, nonpix, d);
+    }
+    if (lane == 0) {
+        if (valid) atomicAdd(&s_st[4], valid);
+        if (nonpix) atomicAdd(&s_st[2], nonpix);
+    }
     if (tid == 0) {
         if (eos) atomicAdd(&s_st[0], eos);
         if (bad) atomicAdd(&s_st[1], bad);
-        if (nonpix) atomicAdd(&s_st[2], nonpix);
         if (ign) atomicAdd(&s_st[3], ign);
     }
     __syncthreads();
     if (tid < 5 && s_st[tid]) atomicAdd(&p.stats[tid], s_st[tid]);
 }
-
 
 __global__ void counts_cap_kernel(const uint32_t *in, uint32_t *out, int64_t n, uint32_t cap) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -526,42 +569,64 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
     const bool wire_fmt = wire != nullptr;
     const int64_t n_pix = (int64_t)cfg->n_roaches * cfg->npix_per_roach;
 
-    // segments -> chunks -> ranges (about one per resident warp, whole chunks, never across a segment)
-    std::vector<int64_t> seg_chunks(n_seg), seg_len(n_seg);
+    // segments -> units -> ranges: about one range per resident warp, whole units (flat: 256 words, wire: one
+    // 4096-word half bundle), never across a segment, all ranges of (almost) equal length
+    const int unit_words = wire_fmt ? DEC_CHUNK : DEC_UNIT;
+    const int64_t min_units = 8192 / unit_words;                 // no range shorter than 64 KiB (unless its segment is)
+    std::vector<int64_t> seg_chunks(n_seg), seg_len(n_seg);     // seg_chunks: units per segment
     int64_t n_chunks = 0;
     for (int i = 0; i < n_seg; ++i) {
         const int64_t len = seg_len_in ? seg_len_in[i] : seg_offset[i + 1] - seg_offset[i];
         seg_len[i] = len;
         MKID_REQUIRE(ctx, len >= 0 && seg_offset[i] >= 0 && seg_offset[i] + len <= n_units, "segment offsets out of range");
         MKID_REQUIRE(ctx, seg_roach[i] >= 0 && seg_roach[i] < cfg->n_roaches, "segment roach out of range");
-        seg_chunks[i] = wire_fmt ? 2 * len : (len + DEC_CHUNK - 1) / DEC_CHUNK;
+        seg_chunks[i] = wire_fmt ? 2 * len : (len + DEC_UNIT - 1) / DEC_UNIT;
         n_chunks += seg_chunks[i];
     }
     std::vector<int32_t> sec0(n_seg, 0);
     if (seg_sec) for (int i = 0; i < n_seg; ++i) sec0[i] = seg_sec[i];
 
-    const int64_t warps_total = (int64_t)ctx->num_sms * DEC_CTAS_PER_SM * DEC_WARPS;
-    const int64_t per = std::max<int64_t>(2, (n_chunks + warps_total - 1) / warps_total);
+    // the range table only depends on the segment table: rebuilt (and uploaded) when that changes
+    std::vector<char> key(24 + (size_t)n_seg * 20);
+    {
+        const int64_t head[3] = {wire_fmt ? 1 : 0, n_seg, n_units};
+        memcpy(key.data(), head, 24);
+        memcpy(key.data() + 24, seg_offset, (size_t)n_seg * 8);
+        memcpy(key.data() + 24 + (size_t)n_seg * 8, seg_len.data(), (size_t)n_seg * 8);
+        memcpy(key.data() + 24 + (size_t)n_seg * 16, seg_roach, (size_t)n_seg * 4);
+    }
+    const bool same_table = key == ctx->dec_key;
     std::vector<DecRange> ranges;
+    if (!same_table) {
+    const int64_t warps_total = (int64_t)ctx->num_sms * DEC_CTAS_PER_SM * DEC_WARPS;
     for (int i = 0; i < n_seg; ++i) {
         const int64_t nc = seg_chunks[i];
-        const int64_t pieces = (nc + per - 1) / per;
-        bool first = true;
+        if (nc == 0) continue;
+        int64_t pieces = (int64_t)((double)nc * (double)warps_total / (double)n_chunks);        // floor: total <= warps_total
+        pieces = std::max<int64_t>(1, std::min<int64_t>(pieces, nc / min_units));
         for (int64_t q = 0; q < pieces; ++q) {
             const int64_t c0 = nc * q / pieces, c1 = nc * (q + 1) / pieces;
             if (c1 <= c0) continue;
             DecRange r;
             if (wire_fmt) { r.start = seg_offset[i] * 2 + c0; r.n_words = (int)((c1 - c0) * DEC_CHUNK); }
-            else { r.start = seg_offset[i] + c0 * DEC_CHUNK; r.n_words = (int)std::min<int64_t>((c1 - c0) * DEC_CHUNK, seg_len[i] - c0 * DEC_CHUNK); }
-            r.roach = seg_roach[i]; r.seg = i; r.first_of_seg = first ? 1 : 0;
-            first = false;
+            else { r.start = seg_offset[i] + c0 * DEC_UNIT; r.n_words = (int)std::min<int64_t>((c1 - c0) * DEC_UNIT, seg_len[i] - c0 * DEC_UNIT); }
+            r.roach = seg_roach[i]; r.seg = i; r.seg_first = 0;
             ranges.push_back(r);
         }
     }
-    const int n_ranges = (int)ranges.size();
+    // ranges of one roach next to each other (segments stay contiguous and in order): the 16 warps of a CTA then
+    // share one shared-memory histogram
+    static const bool no_sort = getenv("MKID_DEC_NOSORT") != nullptr;      // (experiment switch)
+    if (!no_sort) std::stable_sort(ranges.begin(), ranges.end(), [](const DecRange &a, const DecRange &b) { return a.roach < b.roach; });
+    for (int k = 0; k < (int)ranges.size(); ++k) ranges[k].seg_first = (k > 0 && ranges[k - 1].seg == ranges[k].seg) ? ranges[k - 1].seg_first : k;
     MKID_REQUIRE(ctx, ranges.size() <= (size_t)1 << 18, "decode: too many segments in one call");
     for (const DecRange &r : ranges) MKID_REQUIRE(ctx, (int64_t)r.n_words <= (int64_t)1 << 30, "decode: range too long");
 
+        ctx->dec_ranges_host.assign((const char *)ranges.data(), (const char *)ranges.data() + ranges.size() * sizeof(DecRange));
+        ctx->dec_ranges_dev = nullptr;          // forces the upload below
+        ctx->dec_key.swap(key);
+    }
+    const int n_ranges = (int)(ctx->dec_ranges_host.size() / sizeof(DecRange));
     // meta: stats (5 u64) | flag, pad | sec_out [n_seg] | sec [n_seg]
     const size_t meta_bytes = 48 + (size_t)n_seg * 8;
     char *meta = nullptr;
@@ -607,52 +672,72 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
     if (n_ranges > 0) {
         DecRange *d_ranges; DecRangeOut *d_rout; uint32_t *d_rows;
         if ((rc = mkid_scratch(ctx, SCR_AUX2, (size_t)n_ranges * sizeof(DecRange), (void **)&d_ranges))) return rc;
-        if ((rc = mkid_scratch(ctx, SCR_STATE, (size_t)n_ranges * (sizeof(DecRangeOut) + 4), (void **)&d_rout))) return rc;
+        if ((rc = mkid_scratch(ctx, SCR_STATE, (size_t)n_ranges * (sizeof(DecRangeOut) + 8), (void **)&d_rout))) return rc;
         if ((rc = mkid_scratch(ctx, SCR_AUX4, (size_t)n_ranges * DEC_MAX_LS * DEC_ROW * 4, (void **)&d_rows))) return rc;
         int32_t *d_base = (int32_t *)(d_rout + n_ranges);
-        {
-            std::vector<char> blob((const char *)ranges.data(), (const char *)ranges.data() + ranges.size() * sizeof(DecRange));
-            if (ctx->dec_ranges_dev != d_ranges || ctx->dec_ranges_host != blob) {
-                MKID_CUDA(ctx, cudaMemcpyAsync(d_ranges, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream));
-                MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-                ctx->dec_ranges_host.swap(blob);
-                ctx->dec_ranges_dev = d_ranges;
-            }
+        int32_t *d_eos = d_base + n_ranges;
+        if (ctx->dec_ranges_dev != d_ranges) {
+            MKID_CUDA(ctx, cudaMemcpyAsync(d_ranges, ctx->dec_ranges_host.data(), ctx->dec_ranges_host.size(), cudaMemcpyHostToDevice, ctx->stream));
+            MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->dec_ranges_dev = d_ranges;
         }
         DecParams p;
         p.words = wire_fmt ? nullptr : (const uint64_t *)d_in;
         p.wire = wire_fmt ? (const uint32_t *)d_in : nullptr;
         p.ranges = d_ranges; p.rout = d_rout; p.n_ranges = n_ranges; p.rows = d_rows; p.base = d_base; p.flag = d_flag;
+        p.eos_tot = d_eos; p.seg_sec = d_sec; p.seg_sec_out = d_sec_out;
         p.n_pix = (int)n_pix; p.npix_per_roach = cfg->npix_per_roach; p.exptime = cfg->exptime;
         p.field_shift = want_hist ? cfg->hist_field_shift : 0; p.n_bins = want_hist ? cfg->n_bins : 0;
         p.bin_lut = (const uint16_t *)d_lut; p.counts = (uint32_t *)d_counts; p.hist = (uint32_t *)d_hist;
         p.stats = d_stats;
+        static const int map_mode = getenv("MKID_DEC_MAP") ? atoi(getenv("MKID_DEC_MAP")) : 0;
+        p.map_mode = map_mode;
 
         const bool smem_hist = want_hist && (int64_t)cfg->npix_per_roach * cfg->n_bins <= DEC_SMEM_HIST;
         const int grid = (int)std::min<int64_t>((n_ranges + DEC_WARPS - 1) / DEC_WARPS, (int64_t)ctx->num_sms * DEC_CTAS_PER_SM);
         const int hist_mode = !want_hist ? 0 : smem_hist ? 2 : 1;
+        const bool need_lo = want_hist && cfg->hist_field_shift < 32;
+        auto launch = [&](auto kern) { kern<<<grid, DEC_THREADS, 0, ctx->stream>>>(p); };
         auto stream_pass = [&](auto abs_tag) {
-            constexpr bool ABS = decltype(abs_tag)::value;
+            constexpr bool ABS = decltype(abs_tag)::value;       // (the absolute pass is rare: one variant per mode)
+            constexpr bool LO_ALWAYS = ABS;
             if (wire_fmt) {
-                if (hist_mode == 0) decode_stream_kernel<true, 0, ABS><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
-                else if (hist_mode == 1) decode_stream_kernel<true, 1, ABS><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
-                else decode_stream_kernel<true, 2, ABS><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
+                if (hist_mode == 0) launch(decode_stream_kernel<true, 0, LO_ALWAYS, ABS>);
+                else if (hist_mode == 1) { if (need_lo || LO_ALWAYS) launch(decode_stream_kernel<true, 1, true, ABS>); else launch(decode_stream_kernel<true, 1, LO_ALWAYS, ABS>); }
+                else { if (need_lo || LO_ALWAYS) launch(decode_stream_kernel<true, 2, true, ABS>); else launch(decode_stream_kernel<true, 2, LO_ALWAYS, ABS>); }
             } else {
-                if (hist_mode == 0) decode_stream_kernel<false, 0, ABS><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
-                else if (hist_mode == 1) decode_stream_kernel<false, 1, ABS><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
-                else decode_stream_kernel<false, 2, ABS><<<grid, DEC_THREADS, 0, ctx->stream>>>(p);
+                if (hist_mode == 0) launch(decode_stream_kernel<false, 0, LO_ALWAYS, ABS>);
+                else if (hist_mode == 1) { if (need_lo || LO_ALWAYS) launch(decode_stream_kernel<false, 1, true, ABS>); else launch(decode_stream_kernel<false, 1, LO_ALWAYS, ABS>); }
+                else { if (need_lo || LO_ALWAYS) launch(decode_stream_kernel<false, 2, true, ABS>); else launch(decode_stream_kernel<false, 2, LO_ALWAYS, ABS>); }
             }
         };
+        // MKID_DEC_TIMING=1: per-kernel device times on stderr (CUDA events; synchronises)
+        static const bool timing = getenv("MKID_DEC_TIMING") != nullptr;
+        static cudaEvent_t ev[4] = {};
+        auto mark = [&](int i) {
+            if (!timing) return;
+            if (!ev[i]) cudaEventCreate(&ev[i]);
+            cudaEventRecord(ev[i], ctx->stream);
+        };
+        mark(0);
         stream_pass(std::false_type{});                      // relative pass: every word is read here, once
         MKID_CHECK_LAUNCH(ctx);
-        decode_prefix_kernel<<<1, 1024, 0, ctx->stream>>>(d_ranges, d_rout, n_ranges, d_sec, d_sec_out, d_base);
-        MKID_CHECK_LAUNCH(ctx);
-        const int cgrid = std::min(n_ranges, ctx->num_sms * 8);
+        mark(1);
+        const int cgrid = (n_ranges + DEC_COMMIT_RANGES - 1) / DEC_COMMIT_RANGES;
         if (wire_fmt) decode_commit_kernel<true><<<cgrid, 256, 0, ctx->stream>>>(p);
         else decode_commit_kernel<false><<<cgrid, 256, 0, ctx->stream>>>(p);
         MKID_CHECK_LAUNCH(ctx);
+        mark(2);
         stream_pass(std::true_type{});                       // absolute pass: exits at once unless a range overflowed
         MKID_CHECK_LAUNCH(ctx);
+        mark(3);
+        if (timing) {
+            float t[3];
+            MKID_CUDA(ctx, cudaEventSynchronize(ev[3]));
+            for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
+            fprintf(stderr, "[mkid decode timing] ranges %d | stream %.1f us  commit %.1f us  absolute %.1f us\n", n_ranges,
+                    t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f);
+        }
     }
     rc = mkid_stage_out_finish(ctx, counts_raw, counts_bytes, d_counts);
     if (rc) return rc;

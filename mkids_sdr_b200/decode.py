@@ -66,12 +66,13 @@ class PhotonDecoder:
         self.sec[:] = 0
 
     # ------------------------------------------------------------------ feeding
-    def decode_words(self, words, seg_offset, seg_roach, seg_sec=None, n_words=None, want_stats=True):
-        """words: u64 array (host numpy, torch tensor or DeviceBuffer).  Returns seg_sec_out."""
+    def decode_words(self, words, seg_offset, seg_roach, seg_sec=None, n_words=None, want_stats=True, want_sec=True):
+        """words: u64 array (host numpy, torch tensor or DeviceBuffer).  Returns seg_sec_out (None with
+        want_sec=False; with want_stats=False as well the call does not synchronise)."""
         off, roach, sec = _seg_arrays(seg_offset, seg_roach, seg_sec)
         if n_words is None:
             n_words = int(off[-1])
-        sec_out = np.zeros(roach.size, dtype=np.int32)
+        sec_out = np.zeros(roach.size, dtype=np.int32) if want_sec else None
         c = self.ctx
         c._check(c.lib.mkid_decode_words(c.h, _lib.ptr(words), n_words, _lib.ptr(off), _lib.ptr(roach), _lib.ptr(sec),
                                          _lib.ptr(sec_out), roach.size, ctypes.byref(self.cfg),
