@@ -108,6 +108,16 @@ int mkid_decode_words_seg(mkid_ctx *ctx, const uint64_t *words, int64_t n_words,
                           const mkid_decode_cfg *cfg, uint32_t *counts_raw, uint32_t *hist,
                           mkid_decode_stats *stats);
 
+/* Fully asynchronous variant for a producer on the same GPU (mkid_chan_process): segment i may hold up to
+ * seg_cap[i] words (host array) of which the first seg_len_dev[i] (DEVICE int32 array, written by an earlier
+ * kernel on the context stream) are decoded; the carried second counters are read from seg_sec_dev and written
+ * to seg_sec_out_dev (DEVICE int32 arrays, distinct).  Nothing is copied to the host; the call never
+ * synchronises.  Same arithmetic as mkid_decode_words_seg (PacketMaster.c:304-397). */
+int mkid_decode_words_dev(mkid_ctx *ctx, const uint64_t *words, int64_t n_words,
+                          const int64_t *seg_start, const int64_t *seg_cap, const int32_t *seg_len_dev,
+                          const int32_t *seg_roach, const int32_t *seg_sec_dev, int32_t *seg_sec_out_dev,
+                          int32_t n_segments, const mkid_decode_cfg *cfg, uint32_t *counts_raw, uint32_t *hist);
+
 /* Wire format of DataReadout/ReadoutControls/lib/PulseServer.c:318-352 as received by
  * PacketMaster.c:286-287: per bundle 8192 big-endian u32 low halves then 8192 big-endian
  * u32 high halves.  Segment offsets are in BUNDLES. */
@@ -183,7 +193,9 @@ int  mkid_chan_set_f32_phase_out(mkid_ctx *ctx, mkid_chan *ch, float *dev);
 int  mkid_chan_reset(mkid_ctx *ctx, mkid_chan *ch);
 /* iq: int16 [n_boards][n][2] (I,Q) host or device.  words: u64 [n_boards][words_cap];
  * n_words: int32 [n_boards] (host).  phase_out (optional): int16 [n_boards][n/512][256] Fix16_13
- * phase of the n/512 new output samples.  detect = 0 skips K5 (no words). */
+ * phase of the n/512 new output samples.  detect = 0 skips K5 (no words).
+ * n_words == NULL (iq and words in device memory, no phase_out): the call does not synchronise; the counts stay
+ * on the device (mkid_chan_n_words_dev) and words beyond words_cap are dropped. */
 int  mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq, int64_t n, int32_t detect,
                        uint64_t *words, int64_t words_cap, int32_t *n_words, int16_t *phase_out);
 /* K5 alone on a caller-supplied phase stream (bit-exact seam test and phase-snapshot triggering):
@@ -192,6 +204,11 @@ int  mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq, int64_t 
 /* device time (ms, CUDA events on the context stream) of the channelize kernel of the last
  * mkid_chan_process call; the call synchronises on that kernel's end event */
 int  mkid_chan_last_kernel_ms(mkid_ctx *ctx, mkid_chan *ch, float *ms);
+/* ... summed over the last `last_n` (<= 64) mkid_chan_process calls: one synchronisation at the end of a timed region */
+int  mkid_chan_kernel_ms_sum(mkid_ctx *ctx, mkid_chan *ch, int32_t last_n, float *ms_sum);
+/* device pointer to the int32 [n_boards] word counts of the last mkid_chan_process call (asynchronous chaining into
+ * mkid_decode_words_dev; valid until the channelizer is destroyed) */
+int  mkid_chan_n_words_dev(mkid_ctx *ctx, mkid_chan *ch, const int32_t **out);
 int  mkid_chan_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase, int64_t rows, int64_t t_abs0,
                       int64_t *t_next, uint64_t *words, int64_t words_cap, int32_t *n_words);
 /* synthetic ADC stream for tests and benchmarks (replaces the ROACH ADC): per board a comb of

@@ -66,6 +66,8 @@ _SIGNATURES = {
                                     POINTER(DecodeCfg), c_void_p, c_void_p, c_void_p]),
     'mkid_decode_words_seg': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_int32, POINTER(DecodeCfg), c_void_p, c_void_p, c_void_p]),
+    'mkid_decode_words_dev': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_int32, POINTER(DecodeCfg), c_void_p, c_void_p]),
     'mkid_decode_wire': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                    POINTER(DecodeCfg), c_void_p, c_void_p, c_void_p]),
     'mkid_counts_cap': (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32]),
@@ -84,6 +86,8 @@ _SIGNATURES = {
     'mkid_chan_process': (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p,
                                     c_void_p]),
     'mkid_chan_last_kernel_ms': (c_int32, [c_void_p, c_void_p, POINTER(c_float)]),
+    'mkid_chan_kernel_ms_sum': (c_int32, [c_void_p, c_void_p, c_int32, POINTER(c_float)]),
+    'mkid_chan_n_words_dev': (c_int32, [c_void_p, c_void_p, POINTER(c_void_p)]),
     'mkid_chan_detect': (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64,
                                    c_void_p]),
     'mkid_random_phases': (c_int32, [ctypes.c_uint32, c_int32, c_void_p]),

@@ -40,6 +40,8 @@ class ReadoutChain:
         self._words_dev = None
         self._cap = 0
         self.sec = np.zeros(n_boards, dtype=np.int32)
+        self._sec_dev = None
+        self._sec_on_host = True
 
     def set_board(self, b, bins, I_dds, Q_dds, zero_ch=None, centers_i=None, centers_q=None, thresholds=None):
         self.chan.set_board(b, bins, I_dds, Q_dds, zero_ch, centers_i, centers_q, thresholds)
@@ -48,6 +50,7 @@ class ReadoutChain:
         self.chan.reset()
         self.dec.reset()
         self.sec[:] = 0
+        self._sec_on_host = True
 
     def process(self, iq, n=None, words_host=None):
         """One batch: n samples per board.  Photon words stay in HBM and are decoded/binned in
@@ -55,6 +58,8 @@ class ReadoutChain:
         returned to the host.  Returns n_words per board."""
         if n is None:
             n = iq.shape[-2]
+        if not self._sec_on_host:
+            self.sync_state()
         cap = self.chan.words_capacity(n)
         if self._words_dev is None or self._cap < cap:
             self._words_dev = self.ctx.alloc(self.n_boards * cap * 8)
@@ -72,6 +77,42 @@ class ReadoutChain:
                                                int(n_words[b]) * 8))
             c.sync()
         return n_words
+
+    def process_async(self, iq, n=None):
+        """process() without any host round trip: iq in device memory; the word counts and the carried second
+        counters stay on the device, so consecutive batches queue up on the stream.  `sync_state()` brings the
+        host-side view (self.sec, word counts of the last batch) up to date."""
+        if n is None:
+            n = iq.shape[-2]
+        cap = self.chan.words_capacity(n)
+        if self._words_dev is None or self._cap < cap:
+            self._words_dev = self.ctx.alloc(self.n_boards * cap * 8)
+            self._cap = cap
+        if self._sec_dev is None:
+            self._sec_dev = [self.ctx.alloc(self.n_boards * 4), self.ctx.alloc(self.n_boards * 4)]
+            self._sec_cur = 0
+            self._sec_on_host = True
+        c = self.ctx
+        if self._sec_on_host:                       # host copy is the newer one: upload once
+            c._check(c.lib.mkid_memcpy(c.h, _lib.ptr(self._sec_dev[self._sec_cur]), _lib.ptr(self.sec), self.n_boards * 4))
+            c.sync()
+            self._sec_on_host = False
+        self.chan.process_async(iq, self._words_dev, self._cap, n=n)
+        start = np.arange(self.n_boards, dtype=np.int64) * self._cap
+        caps = np.full(self.n_boards, self._cap, dtype=np.int64)
+        self.dec.decode_words_dev(self._words_dev, start, caps, self.chan.n_words_dev(),
+                                  self.roach0 + np.arange(self.n_boards), self._sec_dev[self._sec_cur],
+                                  self._sec_dev[1 - self._sec_cur], self.n_boards * self._cap)
+        self._sec_cur = 1 - self._sec_cur
+
+    def sync_state(self):
+        """After process_async calls: returns the word counts of the last batch, refreshes self.sec."""
+        c = self.ctx
+        if self._sec_dev is not None and not self._sec_on_host:
+            c._check(c.lib.mkid_memcpy(c.h, _lib.ptr(self.sec), _lib.ptr(self._sec_dev[self._sec_cur]), self.n_boards * 4))
+        nw = self.chan.n_words()                      # synchronises
+        self._sec_on_host = True
+        return nw
 
     # ------------------------------------------------------------------ synthetic configuration
     @staticmethod

@@ -95,6 +95,37 @@ class Channelizer:
             words = (words, n_words)
         return words, phase
 
+    def process_async(self, iq, words_out, words_cap, n=None):
+        """Asynchronous process(): iq and words_out in device memory; nothing is copied back and the call does not
+        synchronise.  The per-board word counts stay on the device (n_words_dev())."""
+        if n is None:
+            n = iq.shape[-2]
+        c = self.ctx
+        c._check(c.lib.mkid_chan_process(c.h, self.h, _lib.ptr(iq), int(n), 1, _lib.ptr(words_out), int(words_cap), None, None))
+        self.t_consumed += n // 512
+
+    def n_words_dev(self):
+        """Device address of the int32 [n_boards] word counts of the last process call."""
+        out = ctypes.c_void_p()
+        c = self.ctx
+        c._check(c.lib.mkid_chan_n_words_dev(c.h, self.h, ctypes.byref(out)))
+        return out.value
+
+    def n_words(self):
+        """Word counts of the last process call (synchronises)."""
+        nw = np.zeros(self.n_boards, dtype=np.int32)
+        c = self.ctx
+        c._check(c.lib.mkid_memcpy(c.h, _lib.ptr(nw), self.n_words_dev(), nw.nbytes))
+        c.sync()
+        return nw
+
+    def kernel_ms_sum(self, last_n):
+        """Summed device time of the channelize kernel (K4) over the last `last_n` (<= 64) process calls."""
+        ms = ctypes.c_float()
+        c = self.ctx
+        c._check(c.lib.mkid_chan_kernel_ms_sum(c.h, self.h, int(last_n), ctypes.byref(ms)))
+        return float(ms.value)
+
     def last_kernel_ms(self):
         """Device time of the channelize kernel (K4) of the last process() call."""
         ms = ctypes.c_float()

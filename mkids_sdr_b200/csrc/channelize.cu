@@ -17,6 +17,7 @@
 //          for 4 outputs at once from a register window, centre subtract, atan2, Fix16_13 store.
 // FP32-issue-bound, not HBM-bound (about 150 instructions per ADC sample against 4 B read).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <type_traits>
@@ -75,7 +76,9 @@ struct mkid_chan {
     bool board_set[64] = {};
     bool fir_set = false;
     float *f32_out = nullptr;            // set by mkid_chan_set_f32_phase_out (device pointer)
-    cudaEvent_t ev_k4[2] = {nullptr, nullptr};
+    static constexpr int EV_RING = 64;   // K4 start/stop event pairs of the last EV_RING process calls
+    cudaEvent_t ev_k4[2 * EV_RING] = {};
+    int64_t n_calls = 0;
 };
 
 namespace {
@@ -481,51 +484,104 @@ __global__ void __launch_bounds__(256) candidates_kernel(const int16_t *__restri
     }
 }
 
-// K5a: greedy hold-off per channel (sequential in time, one thread per channel).
-__global__ void __launch_bounds__(32) resolve_kernel(const uint32_t *__restrict__ mask, int64_t rows, int64_t r_lo,
-                                                     int64_t r_hi, int64_t t_abs0, int L, int Lw, int n_win,
-                                                     int64_t *t_next, uint32_t *acc, uint32_t *win_cnt) {
-    const int board = blockIdx.y;
-    const int c = blockIdx.x * 32 + threadIdx.x;
+// K5a: greedy hold-off per channel (sequential in time per channel).  One CTA per 32 channels: all 8 warps
+// stream the CTA's 128-byte wide column of the candidate mask through a double-buffered shared-memory tile
+// (cp.async, 16 B per copy) and reduce it to one "word is non-zero" bit per (channel, word).  Four lanes of
+// every warp then walk their channel's non-zero words only: the per-trigger chain "next candidate at or after
+// the end of the dead time" runs at shared-memory latency and skips the dead time in one step.
+constexpr int RES_TW = 128;                           // mask words (x 32 rows) per tile
+__global__ void __launch_bounds__(256) resolve_kernel(const uint32_t *__restrict__ mask, int64_t rows, int64_t r_lo,
+                                                      int64_t r_hi, int64_t t_abs0, int L, int Lw, int n_win,
+                                                      int64_t *t_next, uint32_t *acc, uint32_t *win_cnt) {
+    __shared__ __align__(16) uint32_t tile[2][RES_TW][32];
+    __shared__ __align__(16) uint16_t summ[32][8];    // per channel: 128 non-zero flags of the current tile
+    const int board = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int c0 = blockIdx.x * 32;
     const int64_t n_groups = (rows + 31) >> 5;
-    const uint32_t *mk = mask + (size_t)board * n_groups * NCH;
-    int64_t tn = t_next[board * NCH + c];
+    const uint32_t *mk = mask + (size_t)board * n_groups * NCH + c0;
     uint32_t *ac = acc + (size_t)board * n_win * NCH;
     uint32_t *wc = win_cnt + (size_t)board * (n_win + 1);
-    const int64_t g_hi = (r_hi + 31) >> 5;
-    // first row this channel may trigger on: hold-off from earlier calls and the start-up guard
-    auto first_allowed = [&]() -> int64_t {
-        const int64_t t_min = tn > T_START ? tn : (int64_t)T_START;
-        const int64_t r = t_min - t_abs0;
-        return r > r_lo ? r : r_lo;
-    };
-    int64_t g = first_allowed() >> 5;
-    constexpr int RB_WORDS = 32;                      // 1024 rows per batch: one batch usually reaches the next trigger
-    while (g < g_hi) {
-        uint32_t wv[RB_WORDS];
-#pragma unroll
-        for (int u = 0; u < RB_WORDS; ++u) wv[u] = (g + u < g_hi) ? mk[(g + u) * NCH + c] : 0u;
-        bool jumped = false;
-#pragma unroll
-        for (int u = 0; u < RB_WORDS; ++u) {
-            uint32_t w = wv[u];
-            if (!w || jumped) continue;
-            const int64_t r_base = (g + u) << 5;
-            const int64_t lo = first_allowed();
-            if (lo > r_base) { const int64_t sh = lo - r_base; w = sh >= 32 ? 0u : (w >> sh) << sh; }
-            if (r_base + 32 > r_hi) { const int64_t keep = r_hi - r_base; w = keep <= 0 ? 0u : (w & (0xFFFFFFFFu >> (32 - keep))); }
-            if (!w) continue;
-            const int64_t r = r_base + (__ffs(w) - 1);
-            tn = t_abs0 + r + L;                         // hold-off: L >= 32, so the next trigger is in a later group
-            const int wi = (int)((r - r_lo) / Lw);
-            ac[(size_t)wi * NCH + c] = (uint32_t)(r + 1);
-            atomicAdd(&wc[wi], 1u);
-            g = first_allowed() >> 5;                   // jump over the dead time
-            jumped = true;
+    const int g_lo = (int)(r_lo >> 5), g_hi = (int)((r_hi + 31) >> 5);
+    const int n_tiles = (g_hi - g_lo + RES_TW - 1) / RES_TW;
+    auto prefetch = [&](int k) {                       // tile k -> buffer k & 1: RES_TW rows of 8 x 16 B
+        const int g0 = g_lo + k * RES_TW;
+        for (int i = tid; i < RES_TW * 8; i += 256) {
+            const int u = i >> 3, q = i & 7;
+            if (g0 + u < g_hi) {
+                const uint32_t dst = mk_smem_u32(&tile[k & 1][u][q * 4]);
+                const uint32_t *src = mk + (size_t)(g0 + u) * NCH + q * 4;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+            } else {
+                *reinterpret_cast<uint4 *>(&tile[k & 1][u][q * 4]) = make_uint4(0, 0, 0, 0);
+            }
         }
-        if (!jumped) g += RB_WORDS;
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    // resolver lanes: lane l < 4 of warp w owns channel c0 + 4*w + l.  Rows are 32-bit inside a call.
+    const bool resolver = lane < 4;
+    const int cl = warp * 4 + lane;                    // channel inside the CTA (resolver lanes)
+    const int c = c0 + cl;
+    const int rlo = (int)r_lo, rhi = (int)r_hi;
+    int64_t tn = 0;
+    int lo = rlo;                                      // first row this channel may trigger on
+    auto first_allowed = [&]() -> int {
+        const int64_t t_min = tn > T_START ? tn : (int64_t)T_START;   // hold-off from earlier calls, start-up guard
+        const int64_t r = t_min - t_abs0;
+        return r > (int64_t)rlo ? (r > (int64_t)rhi ? rhi : (int)r) : rlo;
+    };
+    if (resolver) { tn = t_next[board * NCH + c]; lo = first_allowed(); }
+    prefetch(0);
+    for (int k = 0; k < n_tiles; ++k) {
+        if (k + 1 < n_tiles) prefetch(k + 1);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncthreads();
+        const uint32_t(*t)[32] = tile[k & 1];
+        {   // non-zero flags: warp w covers words 16w .. 16w+15, lane = channel
+            uint32_t part = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) part |= (t[warp * 16 + i][lane] != 0u ? 1u : 0u) << i;
+            summ[lane][warp] = (uint16_t)part;
+        }
+        __syncthreads();
+        const int g0 = g_lo + k * RES_TW;
+        if (resolver && lo < ((g0 + RES_TW) << 5)) {   // (else: the whole tile lies in this channel's dead time)
+            uint4 sv = *reinterpret_cast<const uint4 *>(&summ[cl][0]);
+            uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+            for (;;) {
+                // drop the words that end before lo
+                const int u_min = (lo >> 5) - g0;
+                if (u_min >= RES_TW) break;
+                if (u_min > 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int sh = u_min - 32 * j;
+                        if (sh >= 32) sw[j] = 0u;
+                        else if (sh > 0) sw[j] &= 0xFFFFFFFFu << sh;
+                    }
+                }
+                int u = -1;
+#pragma unroll
+                for (int j = 3; j >= 0; --j)
+                    if (sw[j]) u = 32 * j + __ffs(sw[j]) - 1;
+                if (u < 0) break;
+                sw[u >> 5] &= ~(1u << (u & 31));
+                uint32_t w = t[u][cl];
+                const int r_base = (g0 + u) << 5;
+                if (lo > r_base) w &= 0xFFFFFFFFu << (lo - r_base);          // lo - r_base < 32 here
+                if (r_base + 32 > rhi) { const int keep = rhi - r_base; w = keep <= 0 ? 0u : (w & (0xFFFFFFFFu >> (32 - keep))); }
+                if (!w) continue;
+                const int r = r_base + (__ffs(w) - 1);
+                tn = t_abs0 + r + L;                     // hold-off: L >= 32, so the next trigger is in a later word
+                const int wi = (int)((unsigned)(r - rlo) / (unsigned)Lw);
+                ac[(size_t)wi * NCH + c] = (uint32_t)(r + 1);
+                atomicAdd(&wc[wi], 1u);
+                lo = first_allowed();
+            }
+        }
+        __syncthreads();
     }
-    t_next[board * NCH + c] = tn;
+    if (resolver) t_next[board * NCH + c] = tn;
 }
 
 // K5s: per board, add the end-of-second events and turn per-window counts into offsets.
@@ -582,9 +638,11 @@ __global__ void __launch_bounds__(256) emit_kernel(const int16_t *__restrict__ p
     if (a) {
         const int64_t r = (int64_t)a - 1;
         int S = 0;
+#pragma unroll 4
         for (int k = 1; k <= M; ++k) S += ph[(r - k) * NCH + c];
         int vmin = ph[r * NCH + c];
         int64_t tp = r;
+#pragma unroll 8
         for (int j = 1; j < W; ++j) {
             const int v = ph[(r + j) * NCH + c];
             if (v < vmin) { vmin = v; tp = r + j; }
@@ -739,6 +797,30 @@ int ensure(mkid_ctx *ctx, void **p, size_t *cap, size_t bytes) {
 }
 
 // K5 driver shared by mkid_chan_process and mkid_chan_detect
+// MKID_CHAN_TIMING=1: device time of every kernel of the chain on stderr (CUDA events, printed at the next call)
+struct ChainTimer {
+    static constexpr int N = 8;
+    cudaEvent_t ev[N] = {};
+    const char *name[N] = {};
+    int n = 0;
+    bool on = getenv("MKID_CHAN_TIMING") != nullptr;
+    void report() {
+        if (!on || n < 2) { n = 0; return; }
+        cudaEventSynchronize(ev[n - 1]);
+        fprintf(stderr, "[mkid chain timing]");
+        for (int i = 1; i < n; ++i) { float ms = 0; cudaEventElapsedTime(&ms, ev[i - 1], ev[i]); fprintf(stderr, " %s %.1f us", name[i], ms * 1e3f); }
+        fprintf(stderr, "\n");
+        n = 0;
+    }
+    void mark(cudaStream_t st, const char *nm) {
+        if (!on || n >= N) return;
+        if (!ev[n]) cudaEventCreate(&ev[n]);
+        cudaEventRecord(ev[n], st);
+        name[n++] = nm;
+    }
+};
+ChainTimer g_timer;
+
 int run_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase_dev, int64_t rows, int64_t r_lo, int64_t r_hi,
                int64_t t_abs0, uint64_t *words_dev, int64_t words_cap, bool have_mask) {
     const ChanDev &d = ch->d;
@@ -763,14 +845,18 @@ int run_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase_dev, int64_t r
         candidates_kernel<<<gc, 256, 0, ctx->stream>>>(phase_dev, rows, d.M, d.thr, ch->mask);
         MKID_CHECK_LAUNCH(ctx);
     }
-    resolve_kernel<<<dim3(NCH / 32, B), 32, 0, ctx->stream>>>(ch->mask, rows, r_lo, r_hi, t_abs0, d.L, d.Lw, n_win,
+    g_timer.mark(ctx->stream, "memsets");
+    resolve_kernel<<<dim3(NCH / 32, B), 256, 0, ctx->stream>>>(ch->mask, rows, r_lo, r_hi, t_abs0, d.L, d.Lw, n_win,
                                                              d.t_next, ch->acc, ch->win_cnt);
     MKID_CHECK_LAUNCH(ctx);
+    g_timer.mark(ctx->stream, "resolve");
     scan_kernel<<<B, 256, 0, ctx->stream>>>(ch->win_cnt, n_win, r_lo, r_hi, t_abs0, d.Lw, ch->n_words_dev);
     MKID_CHECK_LAUNCH(ctx);
+    g_timer.mark(ctx->stream, "scan");
     emit_kernel<<<dim3(n_win, B), 256, 0, ctx->stream>>>(phase_dev, rows, ch->acc, ch->win_cnt, n_win, r_lo, r_hi, t_abs0,
                                                          d.M, d.W, d.Lw, words_dev, words_cap);
     MKID_CHECK_LAUNCH(ctx);
+    g_timer.mark(ctx->stream, "emit");
     return MKID_OK;
 }
 
@@ -849,7 +935,7 @@ extern "C" void mkid_chan_destroy(mkid_ctx *ctx, mkid_chan *ch) {
     void *ps[] = {d.window, d.tw512, d.tw256, d.bins, d.ddsf, d.gain, d.cen_i, d.cen_q, d.thr, d.hist, d.t_next,
                   ch->n_words_dev, ch->halo, ch->phase_buf, ch->mask, ch->acc, ch->win_cnt, ch->words_dev, ch->in_dev};
     for (void *p : ps) if (p) cudaFree(p);
-    if (ch->ev_k4[0]) { cudaEventDestroy(ch->ev_k4[0]); cudaEventDestroy(ch->ev_k4[1]); }
+    for (int i = 0; i < 2 * mkid_chan::EV_RING; ++i) if (ch->ev_k4[i]) cudaEventDestroy(ch->ev_k4[i]);
     delete ch;
 }
 
@@ -947,7 +1033,9 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     MKID_REQUIRE(ctx, n >= d.H, "n must be at least the history length (59392 samples) per call");
     MKID_REQUIRE(ctx, ch->fir_set, "FIR taps not set (mkid_chan_set_fir)");
     for (int b = 0; b < d.n_boards; ++b) MKID_REQUIRE(ctx, ch->board_set[b], "a board is not configured (mkid_chan_set_board)");
-    if (detect) MKID_REQUIRE(ctx, words && n_words && words_cap > 0, "detect requested but no word buffer");
+    if (detect) MKID_REQUIRE(ctx, words && words_cap > 0, "detect requested but no word buffer");
+    if (detect && !n_words) MKID_REQUIRE(ctx, mkid_is_device_ptr(words) && mkid_is_device_ptr(iq) && !phase_out,
+                                         "asynchronous call (n_words == NULL): iq and words must be device memory, no phase_out");
     MKID_CUDA(ctx, cudaSetDevice(ctx->device));
     const int B = d.n_boards;
     const int64_t T = n / 512, rows = PRE_ROWS + T;
@@ -994,11 +1082,16 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     }
     const size_t smem = (size_t)(16 * FFT_STRIDE + 256 + FB * NCH) * sizeof(float2) + (size_t)FB * NCH * 4;   // fft exchange, twiddles, DDS + ADC staging
     MKID_CUDA(ctx, cudaFuncSetAttribute(channelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    if (!ch->ev_k4[0]) { cudaEventCreate(&ch->ev_k4[0]); cudaEventCreate(&ch->ev_k4[1]); }
-    MKID_CUDA(ctx, cudaEventRecord(ch->ev_k4[0], ctx->stream));
+    g_timer.report();
+    g_timer.mark(ctx->stream, "start");
+    cudaEvent_t *evp = &ch->ev_k4[2 * (ch->n_calls % mkid_chan::EV_RING)];
+    if (!evp[0]) { cudaEventCreate(&evp[0]); cudaEventCreate(&evp[1]); }
+    ch->n_calls++;
+    MKID_CUDA(ctx, cudaEventRecord(evp[0], ctx->stream));
     channelize_kernel<<<dim3(p.chunks_per_board, B), 256, smem, ctx->stream>>>(p);
     MKID_CHECK_LAUNCH(ctx);
-    MKID_CUDA(ctx, cudaEventRecord(ch->ev_k4[1], ctx->stream));
+    MKID_CUDA(ctx, cudaEventRecord(evp[1], ctx->stream));
+    g_timer.mark(ctx->stream, "channelize");
     if (phase_out) {
         for (int b = 0; b < B; ++b)
             MKID_CUDA(ctx, cudaMemcpyAsync(phase_out + (size_t)b * T * NCH, ch->phase_buf + ((size_t)b * rows + PRE_ROWS) * NCH,
@@ -1015,6 +1108,7 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
             wdev = ch->words_dev;
         }
         if ((rc = run_detect(ctx, ch, ch->phase_buf, rows, RES_LO, RES_LO + T, t_abs0, wdev, words_cap, true))) return rc;
+        if (n_words) {
         MKID_CUDA(ctx, cudaMemcpyAsync(n_words, ch->n_words_dev, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
         MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         int64_t mx = 0;
@@ -1030,6 +1124,7 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
         }
         if (mx > words_cap) return mkid_fail(ctx, MKID_EINVAL, "word buffer too small: need %lld per board, have %lld",
                                              (long long)mx, (long long)words_cap);
+        }
     }
     // history <- last H samples of this call (n >= H)
     update_history_kernel<<<dim3(32, B), 256, 0, ctx->stream>>>(d.hist, d.H, in_dev, n, B);
@@ -1041,9 +1136,33 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
 
 extern "C" int mkid_chan_last_kernel_ms(mkid_ctx *ctx, mkid_chan *ch, float *ms) {
     if (!ctx) return MKID_EINVAL;
-    MKID_REQUIRE(ctx, ch && ms && ch->ev_k4[0], "chan_last_kernel_ms: no process call yet");
-    MKID_CUDA(ctx, cudaEventSynchronize(ch->ev_k4[1]));
-    MKID_CUDA(ctx, cudaEventElapsedTime(ms, ch->ev_k4[0], ch->ev_k4[1]));
+    MKID_REQUIRE(ctx, ch && ms && ch->n_calls > 0, "chan_last_kernel_ms: no process call yet");
+    cudaEvent_t *evp = &ch->ev_k4[2 * ((ch->n_calls - 1) % mkid_chan::EV_RING)];
+    MKID_CUDA(ctx, cudaEventSynchronize(evp[1]));
+    MKID_CUDA(ctx, cudaEventElapsedTime(ms, evp[0], evp[1]));
+    return MKID_OK;
+}
+
+extern "C" int mkid_chan_kernel_ms_sum(mkid_ctx *ctx, mkid_chan *ch, int32_t last_n, float *ms_sum) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, ch && ms_sum && last_n >= 1 && last_n <= mkid_chan::EV_RING && last_n <= ch->n_calls,
+                 "chan_kernel_ms_sum: last_n must be 1..64 and not exceed the calls made");
+    float sum = 0.f;
+    for (int64_t k = ch->n_calls - last_n; k < ch->n_calls; ++k) {
+        cudaEvent_t *evp = &ch->ev_k4[2 * (k % mkid_chan::EV_RING)];
+        float ms = 0.f;
+        MKID_CUDA(ctx, cudaEventSynchronize(evp[1]));
+        MKID_CUDA(ctx, cudaEventElapsedTime(&ms, evp[0], evp[1]));
+        sum += ms;
+    }
+    *ms_sum = sum;
+    return MKID_OK;
+}
+
+extern "C" int mkid_chan_n_words_dev(mkid_ctx *ctx, mkid_chan *ch, const int32_t **out) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, ch && out && ch->n_words_dev, "chan_n_words_dev: NULL");
+    *out = ch->n_words_dev;
     return MKID_OK;
 }
 

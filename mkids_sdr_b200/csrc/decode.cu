@@ -43,6 +43,8 @@ struct DecRange {
     int n_words;           // words in the range
     int roach, seg;
     int seg_first;         // index of the first range of this range's segment
+    int seg_off;           // words between the start of the segment and the start of the range
+    int pad;
 };
 struct DecRangeOut {
     int n_ls;              // rows written on the relative pass (<= DEC_MAX_LS)
@@ -55,6 +57,7 @@ struct DecParams {
     const DecRange *ranges;
     DecRangeOut *rout;
     int32_t *eos_tot;          // [n_ranges] end-of-second words per range
+    const int32_t *seg_len_dev;// [n_seg] or nullptr: actual segment lengths in device memory (<= the host-side capacity)
     const int32_t *seg_sec;    // [n_seg] seconds closed before each segment
     int32_t *seg_sec_out;      // [n_seg] ... and after it
     int n_ranges;
@@ -295,6 +298,7 @@ struct RangeDecoder {
     __device__ void run(int r_, const DecRange &rg, int cta_roach) {
         r = r_;
         roach = rg.roach; n_words = rg.n_words;
+        if (p.seg_len_dev) n_words = max(0, min(n_words, p.seg_len_dev[rg.seg] - rg.seg_off));
         own_roach = roach == cta_roach;
         hist_r = HIST ? p.hist + (size_t)roach * npix * n_bins : nullptr;
         w_flat = WIRE ? nullptr : p.words + rg.start;
@@ -556,10 +560,26 @@ __global__ void quicklook_kernel(const uint32_t *counts_sec, const int32_t *pixe
     if (i < n) image[i] = (uint16_t)counts_sec[pixel_adr[i]];
 }
 
+// persistent device buffer i of the decode path (contents survive other calls on the context; lost on growth)
+int dec_private(mkid_ctx *ctx, int i, size_t bytes, void **out) {
+    if (ctx->dec_priv_bytes[i] < bytes) {
+        MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        if (ctx->dec_priv[i]) cudaFree(ctx->dec_priv[i]);
+        ctx->dec_priv[i] = nullptr; ctx->dec_priv_bytes[i] = 0;
+        const size_t cap = (bytes + 4095) / 4096 * 4096 * 2;
+        if (cudaMalloc(&ctx->dec_priv[i], cap) != cudaSuccess) return mkid_fail(ctx, MKID_ENOMEM, "cudaMalloc(%zu) failed", cap);
+        ctx->dec_priv_bytes[i] = cap;
+        if (i == 0) ctx->dec_meta_dev = nullptr; else ctx->dec_ranges_dev = nullptr;
+    }
+    *out = ctx->dec_priv[i];
+    return MKID_OK;
+}
+
 int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, int64_t n_units,
                   const int64_t *seg_offset, const int64_t *seg_len_in, const int32_t *seg_roach, const int32_t *seg_sec,
                   int32_t *seg_sec_out, int32_t n_seg, const mkid_decode_cfg *cfg, uint32_t *counts_raw,
-                  uint32_t *hist, mkid_decode_stats *stats) {
+                  uint32_t *hist, mkid_decode_stats *stats, const int32_t *seg_len_dev = nullptr,
+                  const int32_t *seg_sec_dev = nullptr, int32_t *seg_sec_out_dev = nullptr) {
     MKID_REQUIRE(ctx, cfg && seg_offset && seg_roach && n_seg > 0, "decode: missing cfg/segments");
     MKID_REQUIRE(ctx, cfg->npix_per_roach > 0 && cfg->npix_per_roach <= 255, "npix_per_roach must be 1..255");
     MKID_REQUIRE(ctx, cfg->n_roaches > 0 && cfg->exptime > 0 && counts_raw, "bad decode cfg");
@@ -572,7 +592,7 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
     // segments -> units -> ranges: about one range per resident warp, whole units (flat: 256 words, wire: one
     // 4096-word half bundle), never across a segment, all ranges of (almost) equal length
     const int unit_words = wire_fmt ? DEC_CHUNK : DEC_UNIT;
-    const int64_t min_units = 8192 / unit_words;                 // no range shorter than 64 KiB (unless its segment is)
+    const int64_t min_units = wire_fmt ? 1 : 1024 / DEC_UNIT;     // no range shorter than 1024 words (wire: one chunk)
     std::vector<int64_t> seg_chunks(n_seg), seg_len(n_seg);     // seg_chunks: units per segment
     int64_t n_chunks = 0;
     for (int i = 0; i < n_seg; ++i) {
@@ -610,7 +630,8 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
             DecRange r;
             if (wire_fmt) { r.start = seg_offset[i] * 2 + c0; r.n_words = (int)((c1 - c0) * DEC_CHUNK); }
             else { r.start = seg_offset[i] + c0 * DEC_UNIT; r.n_words = (int)std::min<int64_t>((c1 - c0) * DEC_UNIT, seg_len[i] - c0 * DEC_UNIT); }
-            r.roach = seg_roach[i]; r.seg = i; r.seg_first = 0;
+            r.roach = seg_roach[i]; r.seg = i; r.seg_first = 0; r.pad = 0;
+            r.seg_off = (int)(c0 * unit_words);
             ranges.push_back(r);
         }
     }
@@ -630,7 +651,7 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
     // meta: stats (5 u64) | flag, pad | sec_out [n_seg] | sec [n_seg]
     const size_t meta_bytes = 48 + (size_t)n_seg * 8;
     char *meta = nullptr;
-    int rc = mkid_scratch(ctx, SCR_META, meta_bytes, (void **)&meta);
+    int rc = dec_private(ctx, 0, meta_bytes, (void **)&meta);
     if (rc) return rc;
     unsigned long long *d_stats = (unsigned long long *)meta;
     int *d_flag = (int *)(meta + 40);
@@ -671,7 +692,7 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
 
     if (n_ranges > 0) {
         DecRange *d_ranges; DecRangeOut *d_rout; uint32_t *d_rows;
-        if ((rc = mkid_scratch(ctx, SCR_AUX2, (size_t)n_ranges * sizeof(DecRange), (void **)&d_ranges))) return rc;
+        if ((rc = dec_private(ctx, 1, (size_t)n_ranges * sizeof(DecRange), (void **)&d_ranges))) return rc;
         if ((rc = mkid_scratch(ctx, SCR_STATE, (size_t)n_ranges * (sizeof(DecRangeOut) + 8), (void **)&d_rout))) return rc;
         if ((rc = mkid_scratch(ctx, SCR_AUX4, (size_t)n_ranges * DEC_MAX_LS * DEC_ROW * 4, (void **)&d_rows))) return rc;
         int32_t *d_base = (int32_t *)(d_rout + n_ranges);
@@ -685,7 +706,8 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
         p.words = wire_fmt ? nullptr : (const uint64_t *)d_in;
         p.wire = wire_fmt ? (const uint32_t *)d_in : nullptr;
         p.ranges = d_ranges; p.rout = d_rout; p.n_ranges = n_ranges; p.rows = d_rows; p.base = d_base; p.flag = d_flag;
-        p.eos_tot = d_eos; p.seg_sec = d_sec; p.seg_sec_out = d_sec_out;
+        p.eos_tot = d_eos; p.seg_sec = seg_sec_dev ? seg_sec_dev : d_sec; p.seg_sec_out = seg_sec_out_dev ? seg_sec_out_dev : d_sec_out;
+        p.seg_len_dev = seg_len_dev;
         p.n_pix = (int)n_pix; p.npix_per_roach = cfg->npix_per_roach; p.exptime = cfg->exptime;
         p.field_shift = want_hist ? cfg->hist_field_shift : 0; p.n_bins = want_hist ? cfg->n_bins : 0;
         p.bin_lut = (const uint16_t *)d_lut; p.counts = (uint32_t *)d_counts; p.hist = (uint32_t *)d_hist;
@@ -790,6 +812,21 @@ extern "C" int mkid_decode_words_seg(mkid_ctx *ctx, const uint64_t *words, int64
     MKID_REQUIRE(ctx, (words || n_words == 0) && seg_len, "words / seg_len is NULL");
     return decode_common(ctx, words, nullptr, n_words, seg_start, seg_len, seg_roach, seg_sec, seg_sec_out, n_segments, cfg,
                          counts_raw, hist, stats);
+}
+
+extern "C" int mkid_decode_words_dev(mkid_ctx *ctx, const uint64_t *words, int64_t n_words, const int64_t *seg_start,
+                                     const int64_t *seg_cap, const int32_t *seg_len_dev, const int32_t *seg_roach,
+                                     const int32_t *seg_sec_dev, int32_t *seg_sec_out_dev, int32_t n_segments,
+                                     const mkid_decode_cfg *cfg, uint32_t *counts_raw, uint32_t *hist) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, words && seg_cap && seg_len_dev && seg_sec_dev && seg_sec_out_dev, "decode_words_dev: NULL argument");
+    MKID_REQUIRE(ctx, mkid_is_device_ptr(words) && mkid_is_device_ptr(seg_len_dev) && mkid_is_device_ptr(seg_sec_dev) &&
+                          mkid_is_device_ptr(seg_sec_out_dev) && seg_sec_dev != seg_sec_out_dev &&
+                          mkid_is_device_ptr(counts_raw) && (!hist || mkid_is_device_ptr(hist)),
+                 "decode_words_dev: words, lengths, second counters (distinct in/out) and products must be device memory");
+    for (int i = 0; i < n_segments; ++i) MKID_REQUIRE(ctx, seg_cap[i] > 0, "decode_words_dev: empty segment capacity");
+    return decode_common(ctx, words, nullptr, n_words, seg_start, seg_cap, seg_roach, nullptr, nullptr, n_segments, cfg,
+                         counts_raw, hist, nullptr, seg_len_dev, seg_sec_dev, seg_sec_out_dev);
 }
 
 extern "C" int mkid_decode_wire(mkid_ctx *ctx, const uint32_t *wire, int64_t n_bundles, const int64_t *seg_offset,

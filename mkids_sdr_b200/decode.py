@@ -96,6 +96,18 @@ class PhotonDecoder:
                                              ctypes.addressof(self.stats) if want_stats else None))
         return sec_out
 
+    def decode_words_dev(self, words, seg_start, seg_cap, seg_len_dev, seg_roach, sec_in_dev, sec_out_dev, n_words):
+        """Asynchronous chaining behind a producer on the same GPU: segment lengths and the carried second
+        counters live in device memory (addresses / DeviceBuffers); nothing is copied back, no synchronisation."""
+        start = np.ascontiguousarray(seg_start, dtype=np.int64)
+        cap = np.ascontiguousarray(seg_cap, dtype=np.int64)
+        roach = np.ascontiguousarray(seg_roach, dtype=np.int32)
+        c = self.ctx
+        c._check(c.lib.mkid_decode_words_dev(c.h, _lib.ptr(words), int(n_words), _lib.ptr(start), _lib.ptr(cap),
+                                             _lib.ptr(seg_len_dev), _lib.ptr(roach), _lib.ptr(sec_in_dev),
+                                             _lib.ptr(sec_out_dev), roach.size, ctypes.byref(self.cfg),
+                                             _lib.ptr(self.counts_dev), _lib.ptr(self.hist_dev)))
+
     def decode_wire(self, wire, seg_offset, seg_roach, seg_sec=None, n_bundles=None, want_stats=True):
         """wire: PulseServer bundles (bytes / u8 / u32 array, host or device)."""
         if isinstance(wire, (bytes, bytearray, memoryview)):

@@ -57,3 +57,31 @@ def test_thresholds_from_noise_and_trigger_rate(ctx):
     nw = chain.process(iq)
     # 16 ms of data, 24 channels, ~1000 pulses/s (depth 20-120 deg): tens to a few hundred words
     assert 100 < nw[0] < 24 * 40, nw
+
+
+def test_chain_async_equals_sync(ctx):
+    """process_async (no host round trip: word counts and carried seconds stay on the device) gives the same
+    per-pixel products, seconds and word counts as the synchronous process(), batch after batch."""
+    from mkids_sdr_b200.chain import ReadoutChain
+    from mkids_sdr_b200.channelizer import synth_adc
+    B, n_lut, n = 2, 2 ** 16, 2 ** 20
+    res = []
+    for mode in ('sync', 'async', 'mixed'):
+        chain, boards = ReadoutChain.synthetic(B, n_lut, 40, seed0=11, threshold=-2400, holdoff=100, ctx=ctx, exptime=3,
+                                               n_bins=16)
+        tb = np.stack([bd['tone_bins'] for bd in boards])
+        iq = ctx.to_device(synth_adc(B, n, tb, n_lut=n_lut, pulse_rate=4000., seed=21, ctx=ctx))
+        nw = None
+        for rep in range(3):
+            if mode == 'sync' or (mode == 'mixed' and rep == 1):
+                nw = chain.process(iq, n=n)
+            else:
+                chain.process_async(iq, n=n)
+                nw = chain.sync_state() if rep == 2 or mode == 'mixed' else None
+        if nw is None:
+            nw = chain.sync_state()
+        res.append((chain.dec.counts_raw(), chain.dec.hist(), chain.sec.copy(), np.asarray(nw).copy()))
+    for r in res[1:]:
+        for a, b in zip(res[0], r):
+            assert np.array_equal(a, b)
+    assert res[0][0].sum() > 100
