@@ -352,6 +352,13 @@ def decode_side_bench(ctx, peak):
         ms = ctx.elapsed_ms(2, 3) / k
         gbs = words.size * 8 / ms / 1e6
         out[name] = {'words_per_s': words.size / ms * 1e3, 'GB/s': gbs, 'frac_hbm': gbs / peak, 'ms': ms}
+    tp = os.path.join(ROOT, 'profiles', 'k6_traffic.json')
+    if os.path.exists(tp):
+        try:
+            out['dram_bytes_per_word_ncu'] = float(json.load(open(tp))['dram_bytes_per_word'])
+        except Exception:
+            pass
+    out['algorithmic_bytes_per_word'] = 8
     out['workload'] = 'Utils/bin.py-style decode + per-pixel binning, 2024 pixels, 16 x 1e7 photon words resident in HBM'
     return out
 
