@@ -229,6 +229,50 @@ typedef struct {
 int  mkid_synth_adc(mkid_ctx *ctx, const mkid_synth_params *prm, int32_t n_boards, const int32_t *tone_bin,
                     const float *tone_amp, const float *tone_phase, int64_t n, int64_t t_abs0_us, int16_t *out);
 
+/* ------------------------------------------------------------------ snapshot decode, software triggers, thresholds
+ * (the analysis scripts and the threshold derivation around the hot path) */
+
+/* 40-bit I/Q snapshot words of DataReadout/ChannelizerControls/pulse_triggering_IQ.py:121-147: per 16 bytes two
+ * samples, I = low 16 bits of the 20-bit field in bytes 6-8 / 11-13, Q = bytes 9-10 / 14-15, big-endian,
+ * two's complement (twos_comp, pulse_triggering.py:22-26).  I, Q: int16 [n_bytes/8]. */
+int mkid_iq_snapshot_decode(mkid_ctx *ctx, const uint8_t *buf, int64_t n_bytes, int16_t *I, int16_t *Q);
+/* pulse_triggering_IQ.py:152: deg = -360*arctan2(Q-Qc, I-Ic)/(2*pi), float64 */
+int mkid_phase_deg_from_iq(mkid_ctx *ctx, const int16_t *I, const int16_t *Q, int64_t n, double Ic, double Qc, double *deg);
+
+/* Software pulse triggers on float64 phase streams (degrees), phase: [n_streams][n]:
+ *   mode 0  rolling mean, pulse_triggering_v2.py:104-174 (= pulse_triggering_IQ.py:160-200): bob = start
+ *           (= 100 + meanlength); hit iff |np.mean(x[bob-M:bob]) - x[bob]| > threshold; bob += holdoff
+ *           (pulselength) after a hit; the scan ends when bob + tail > n (tail = pulselength).
+ *   mode 1  block mean, pulse_triggering.py:114-208 and contsnapshot ROACH_Pulses.py:614-725: means of fixed
+ *           blocks of mean_len samples, hit iff |mean[bob // mean_len] - x[bob]| > threshold; wrap_negative adds
+ *           360 to negative samples first (pulse_triggering.py:110-112).
+ * np.mean is evaluated in NumPy's float64 operation order (sum_order 0: pairwise summation of NumPy >= 1.9;
+ * 1: plain left-to-right sum of the NumPy 1.6 the reference ran on), so hit lists are bit-identical to the
+ * NumPy loop.  hits: int32 [n_streams][max_hits] sample indices in order; n_hits: int32 [n_streams] (may exceed
+ * max_hits: the list is then truncated). */
+typedef struct {
+    int32_t mode;
+    int32_t mean_len;       /* meanlength (mode 0) / averagelength (mode 1)              */
+    int32_t start;          /* first sample tested                                      */
+    int32_t holdoff;        /* samples skipped after a hit                              */
+    int32_t tail;           /* the scan stops when bob + tail > n                       */
+    int32_t wrap_negative;  /* mode 1 only                                              */
+    int32_t sum_order;      /* 0 = pairwise (NumPy >= 1.9), 1 = sequential (NumPy 1.6)  */
+    int32_t reserved;
+    double  threshold;      /* phase_threshold, degrees                                 */
+} mkid_trigger_cfg;
+int mkid_soft_trigger(mkid_ctx *ctx, const double *phase, int32_t n_streams, int64_t n, const mkid_trigger_cfg *cfg,
+                      int32_t *hits, int32_t max_hits, int32_t *n_hits);
+
+/* loadThresholds / loadSingleThreshold (ROACH_Pulses.py:259-288) for many channels at once, on raw Fix16_13 phase
+ * in DEVICE memory (e.g. the phase_out of mkid_chan_process): sample t of channel c of board b is
+ * phase[b*board_stride + t*row_stride + c].  Per channel: np.histogram(bins=100) -> n = float32(counts)/sum ->
+ * tot[i] = np.sum(n[:i]) -> med = edge[argmin|tot-0.5|], p5 = edge[argmin|tot-0.05|] ->
+ * threshold = int(-nsigma*|med-p5|) clamped at -25736.  thr_raw int32 [n_boards][n_ch]; med, p5 (optional) float64. */
+int mkid_thresholds_from_phase(mkid_ctx *ctx, const int16_t *phase, int32_t n_boards, int64_t board_stride,
+                               int64_t row_stride, int32_t n_ch, int64_t n_samples, double nsigma,
+                               int32_t *thr_raw, double *med, double *p5);
+
 /* ------------------------------------------------------------------ LUT synthesis (K1-K3)
  * mkid_comb_lut replaces AppForm.freqCombLUT (ChannelizerControls/ROACH_Setup.py:416-475; twin with GUI
  * offset/scale options ROACH_Setup_DAC.py:396-455): I[t] = sum a_n cos(2 pi f_n (t+offset)/fs + phi_n),

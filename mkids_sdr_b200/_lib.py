@@ -38,6 +38,11 @@ class SynthParams(Structure):
                 ('seed', ctypes.c_uint64)]
 
 
+class TriggerCfg(Structure):
+    _fields_ = [('mode', c_int32), ('mean_len', c_int32), ('start', c_int32), ('holdoff', c_int32), ('tail', c_int32),
+                ('wrap_negative', c_int32), ('sum_order', c_int32), ('reserved', c_int32), ('threshold', c_double)]
+
+
 class DecodeStats(Structure):
     _fields_ = [('n_eos', c_int64), ('n_corrupt_eos', c_int64), ('n_nonpixel', c_int64),
                 ('n_ignored', c_int64), ('n_valid', c_int64)]
@@ -90,6 +95,11 @@ _SIGNATURES = {
     'mkid_chan_n_words_dev': (c_int32, [c_void_p, c_void_p, POINTER(c_void_p)]),
     'mkid_chan_detect': (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64,
                                    c_void_p]),
+    'mkid_iq_snapshot_decode': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'mkid_phase_deg_from_iq': (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_void_p]),
+    'mkid_soft_trigger': (c_int32, [c_void_p, c_void_p, c_int32, c_int64, POINTER(TriggerCfg), c_void_p, c_int32, c_void_p]),
+    'mkid_thresholds_from_phase': (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int32, c_int64, c_double,
+                                             c_void_p, c_void_p, c_void_p]),
     'mkid_random_phases': (c_int32, [ctypes.c_uint32, c_int32, c_void_p]),
     'mkid_comb_lut': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_double, c_int32, c_int32, c_double,
                                 c_int32, c_double, c_int32, c_void_p, c_void_p, c_void_p]),

@@ -155,20 +155,23 @@ class ReadoutChain:
         return chain, boards
 
     def derive_thresholds(self, boards, n=2 ** 22, seed=7):
-        """loadThresholds (ROACH_Pulses.py:259-288) on a pulse-free stretch of the synthetic stream."""
+        """loadThresholds (ROACH_Pulses.py:259-288) on a pulse-free stretch of the synthetic stream: the raw phase
+        stays in HBM and all channels are histogrammed by one kernel (mkid_thresholds_from_phase)."""
+        from . import triggers
         tb = np.stack([bd['tone_bins'] for bd in boards])
-        iq = synth_adc(self.n_boards, n, tb, n_lut=self.n_lut, pulse_rate=0.0, seed=seed, ctx=self.ctx)
+        iq = self.ctx.alloc(self.n_boards * n * 4)
+        synth_adc(self.n_boards, n, tb, n_lut=self.n_lut, pulse_rate=0.0, seed=seed, out=iq, ctx=self.ctx)
+        T = n // 512
+        ph = self.ctx.alloc(self.n_boards * T * 256 * 2)
         self.chan.reset()
-        _, ph = self.chan.process(iq, detect=False, want_phase=True)
+        c = self.ctx
+        c._check(c.lib.mkid_chan_process(c.h, self.chan.h, _lib.ptr(iq), int(n), 0, None, 0, None, _lib.ptr(ph)))
         self.chan.reset()
+        thr_all, _, _ = triggers.thresholds_from_phase(ph, self.n_boards, T, min(20480, T - 64), row0=64, ctx=self.ctx)
+        iq.free(); ph.free()
         out = []
         for b in range(self.n_boards):
-            thr = np.full(256, -25736, np.int32)
-            for c in range(256):
-                if boards[b]['zero_ch'][c]:
-                    continue
-                t, _ = PulsesForm._threshold(ph[b, 64:64 + 20480, c].astype(np.int64))
-                thr[c] = t
+            thr = np.where(np.asarray(boards[b]['zero_ch']).astype(bool), -25736, thr_all[b]).astype(np.int32)
             self.chan.set_thresholds(b, thr)
             out.append(thr)
         return out

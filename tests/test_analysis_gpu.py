@@ -1,0 +1,109 @@
+"""GPU parity of the analysis kernels around the hot path: snapshot decoders,
+float64 software triggers (bit-identical hit lists vs the literal NumPy loops) and loadThresholds."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import control, trigger as otrig
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ctx():
+    from mkids_sdr_b200 import _lib
+    return _lib.default_context(0)
+
+
+def _pulse_stream(rng, n, rate=0.002, depth=(20., 120.), sigma=4.0, offset=0.0):
+    x = rng.normal(offset, sigma, n)
+    t = np.arange(n)
+    for t0 in np.nonzero(rng.random(n) < rate)[0]:
+        x[t0:] -= rng.uniform(*depth) * np.exp(-(t[t0:] - t0) / 30.0)
+    return x
+
+
+def test_rolling_trigger_matches_literal_loop(ctx, golden_dir):
+    from mkids_sdr_b200 import triggers
+    rng = np.random.default_rng(3)
+    streams = np.stack([_pulse_stream(rng, 16384) for _ in range(6)])
+    for M, L, thr in ((20, 1000, 25.), (10, 1000, 15.), (20, 300, 100.), (7, 50, 12.5)):
+        got = triggers.trigger_rolling(streams, meanlength=M, pulselength=L, phase_threshold=thr, ctx=ctx)
+        for s in range(streams.shape[0]):
+            assert got[s] == otrig.trigger_rolling_literal(streams[s], M, L, thr), (M, L, thr, s)
+    assert sum(len(g) for g in got) > 10
+    # the reference's own snapshot (ch_snap_0.txt, degrees)
+    deg = np.load(os.path.join(golden_dir, 'ch_snap_0.npy'))
+    for thr in (2.0, 5.0, 15.0):
+        assert triggers.trigger_rolling(deg, 20, 300, thr, ctx=ctx) == otrig.trigger_rolling_literal(deg, 20, 300, thr)
+
+
+def test_rolling_trigger_numpy16_summation_order(ctx):
+    """sum_order=1: the plain left-to-right sum NumPy 1.6 (the reference's EPD 7.3) used for np.mean."""
+    from mkids_sdr_b200 import triggers
+    rng = np.random.default_rng(8)
+    x = _pulse_stream(rng, 8192)
+    M, L, thr = 20, 500, 20.
+    hits, bob = [], 100 + M
+    while bob < len(x):
+        if bob + L > len(x):
+            break
+        acc = 0.0
+        for v in x[bob - M:bob]:
+            acc += v
+        if abs(acc / M - x[bob]) > thr:
+            hits.append(bob); bob += L
+        else:
+            bob += 1
+    assert triggers.trigger_rolling(x, M, L, thr, numpy16_sum=True, ctx=ctx) == hits
+
+
+def test_block_triggers_match_literal_loops(ctx):
+    from mkids_sdr_b200 import triggers
+    rng = np.random.default_rng(5)
+    streams = np.stack([_pulse_stream(rng, 20000, offset=o) for o in (0.0, 3.0, -2.0, 150.0)])
+    for A, thr in ((128, 25.), (64, 15.), (100, 40.), (300, 30.)):
+        got = triggers.trigger_block(streams, averagelength=A, phase_threshold=thr, ctx=ctx)
+        for s in range(streams.shape[0]):
+            assert got[s] == otrig.trigger_block_literal(streams[s], A, thr), (A, thr, s)
+    big = _pulse_stream(rng, 2 ** 18, rate=0.0005)
+    for A in (64, 32, 256):
+        assert triggers.trigger_contsnapshot(big, A, 25., ctx=ctx) == otrig.trigger_contsnapshot_literal(big, A, 25.)
+
+
+def test_iq_snapshot_and_phase_model(ctx):
+    from mkids_sdr_b200 import triggers
+    rng = np.random.default_rng(11)
+    buf = rng.integers(0, 256, 4 * 16384, dtype=np.uint8).tobytes()       # L_IQ = 16384 words of 4 bytes
+    I, Q = triggers.decode_iq_snapshot(buf, ctx=ctx)
+    I0, Q0 = control.decode_iq_snapshot(buf)
+    assert np.array_equal(I, I0) and np.array_equal(Q, Q0)
+    Il, Ql = control.decode_iq_snapshot_literal(buf[:1024])
+    assert np.array_equal(I[:128], Il) and np.array_equal(Q[:128], Ql)
+    deg = triggers.phase_deg_from_iq(I, Q, 12.5, -3.0, ctx=ctx)
+    ref = control.phase_deg_from_iq(I0, Q0, 12.5, -3.0)
+    assert np.max(np.abs(deg - ref)) <= 1e-12            # float64 atan2: CUDA (<= 2 ulp) vs libm
+
+
+def test_thresholds_from_device_phase_stream(ctx):
+    from mkids_sdr_b200 import triggers
+    rng = np.random.default_rng(2)
+    B, rows, C, n, row0 = 2, 20480 + 96, 256, 20480, 64
+    ph = np.empty((B, rows, C), dtype=np.int16)
+    for b in range(B):
+        for c in range(C):
+            sig = rng.uniform(5, 400)
+            x = rng.normal(rng.uniform(-3000, 3000), sig, rows)
+            if c % 7 == 0:                                   # pulses: a long negative tail
+                x -= np.abs(rng.normal(0, 6 * sig, rows)) * (rng.random(rows) < 0.03)
+            ph[b, :, c] = np.clip(np.round(x), -32768, 32767)
+    ph[0, :, 5] = 1234                                       # flat channel: outer edges widened by 0.5
+    ph[1, :, 9] = np.where(np.arange(rows) % 2, -7, 8)       # two values only
+    dev = ctx.to_device(ph)
+    thr, med, p5 = triggers.thresholds_from_phase(dev, B, rows, n, row0=row0, ctx=ctx)
+    for b in range(B):
+        for c in range(C):
+            t0, m0, q0 = control.threshold_from_phase(ph[b, row0:row0 + n, c].astype(np.int64))
+            assert (thr[b, c], med[b, c], p5[b, c]) == (t0, m0, q0), (b, c)
+    assert thr.min() >= -25736 and (thr < 0).sum() > 400
