@@ -118,6 +118,18 @@ int mkid_decode_words_dev(mkid_ctx *ctx, const uint64_t *words, int64_t n_words,
                           const int32_t *seg_roach, const int32_t *seg_sec_dev, int32_t *seg_sec_out_dev,
                           int32_t n_segments, const mkid_decode_cfg *cfg, uint32_t *counts_raw, uint32_t *hist);
 
+/* The per-(second, pixel) photon lists PacketMaster keeps and writes every second (photons[r][adr][plist],
+ * PacketMaster.c:371-380; write_sec_data :1012-1016): list_words holds the valid photon words sorted by
+ * key = sec * n_pix + pixel, in arrival order inside a key, every key truncated to max_events - 1 entries (the cap
+ * quirk); list_offsets int64 [exptime * n_pix + 1] holds the start of every key (last entry = total).  list_cap:
+ * capacity of list_words in words (n_words always suffices).  counts_raw (uncapped) and stats are accumulated as in
+ * mkid_decode_words.  Flat words only; a range of the input (>= 1024 words) may hold at most 4 end-of-second words.
+ * Synchronises. */
+int mkid_decode_lists(mkid_ctx *ctx, const uint64_t *words, int64_t n_words, const int64_t *seg_offset,
+                      const int32_t *seg_roach, const int32_t *seg_sec, int32_t *seg_sec_out, int32_t n_segments,
+                      const mkid_decode_cfg *cfg, uint32_t *counts_raw, uint64_t *list_words, int64_t list_cap,
+                      int64_t *list_offsets, mkid_decode_stats *stats);
+
 /* Wire format of DataReadout/ReadoutControls/lib/PulseServer.c:318-352 as received by
  * PacketMaster.c:286-287: per bundle 8192 big-endian u32 low halves then 8192 big-endian
  * u32 high halves.  Segment offsets are in BUNDLES. */

@@ -519,6 +519,138 @@ __global__ void __launch_bounds__(256) decode_commit_kernel(DecParams p) {
     if (tid < 5 && s_st[tid]) atomicAdd(&p.stats[tid], s_st[tid]);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Per-(second, pixel) photon lists: the product PacketMaster writes every second (photons[r][adr][plist],
+// PacketMaster.c:371-380, write_sec_data :1012-1016).  Key = sec * n_pix + pixel, arrival order inside a key,
+// each key truncated to max_events - 1 entries (the cap quirk).  Built from the rows of the relative pass:
+//   list_rowstart_kernel  thread = (roach, channel) walks the roach's ranges in stream order: rows[r][ls][ch] is
+//                         replaced by the number of earlier words of the same (second, pixel); the per-key totals
+//                         land in acc[sec][pixel]
+//   list_offsets_kernel   offsets = exclusive scan of min(acc, max_events - 1)
+//   list_scatter_kernel   one warp per range re-reads its words in order, ranks the words of one load step that hit
+//                         the same pixel with match.any, and stores word -> out[offsets[key] + rank]
+struct ListParams {
+    const uint64_t *words;
+    const DecRange *ranges;
+    const DecRangeOut *rout;
+    const int32_t *base, *eos_tot;
+    const int32_t *roach_first;   // [n_roaches + 1] first range of every roach (ranges are sorted by roach)
+    uint32_t *rows;
+    uint32_t *acc;                // [exptime][n_pix], zeroed
+    long long *offsets;           // [exptime * n_pix + 1]
+    uint64_t *out;
+    long long out_cap;
+    int n_ranges, n_roaches, n_pix, npix_per_roach, exptime, cap;     // cap = max_events - 1
+    int *flag;                    // set to 2 if out_cap is too small
+};
+
+__global__ void __launch_bounds__(256) list_rowstart_kernel(ListParams p) {
+    const int roach = blockIdx.x, ch = threadIdx.x;
+    const int r0 = p.roach_first[roach], r1 = p.roach_first[roach + 1];
+    const bool is_pix = ch < p.npix_per_roach;
+    int cur_sec = -1;
+    uint32_t run = 0;
+    uint32_t *acc_col = p.acc + (size_t)roach * p.npix_per_roach + ch;
+    for (int r = r0; r < r1; ++r) {
+        const int n_ls = p.rout[r].n_ls, base = p.base[r];
+        for (int ls = 0; ls < n_ls; ++ls) {
+            const int sec = base + ls;
+            uint32_t *cell = p.rows + ((size_t)r * DEC_MAX_LS + ls) * DEC_ROW + ch;
+            if (!is_pix || sec >= p.exptime) continue;
+            const uint32_t v = *cell;
+            if (sec != cur_sec) {              // seconds normally only grow along a roach stream: rare
+                if (cur_sec >= 0) acc_col[(size_t)cur_sec * p.n_pix] = run;
+                cur_sec = sec;
+                run = acc_col[(size_t)sec * p.n_pix];
+            }
+            *cell = run;
+            run += v;
+        }
+    }
+    if (is_pix && cur_sec >= 0) acc_col[(size_t)cur_sec * p.n_pix] = run;
+}
+
+__global__ void __launch_bounds__(1024) list_offsets_kernel(ListParams p) {
+    __shared__ long long s_part[1024];
+    const long long n = (long long)p.exptime * p.n_pix;
+    const int t = threadIdx.x;
+    const long long per = (n + 1023) / 1024, i0 = min(n, t * per), i1 = min(n, i0 + per);
+    long long sum = 0;
+    for (long long i = i0; i < i1; ++i) sum += min(p.acc[i], (uint32_t)p.cap);
+    s_part[t] = sum;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const long long a = t >= d ? s_part[t - d] : 0;
+        __syncthreads();
+        s_part[t] += a;
+        __syncthreads();
+    }
+    long long run = t > 0 ? s_part[t - 1] : 0;
+    for (long long i = i0; i < i1; ++i) { p.offsets[i] = run; run += min(p.acc[i], (uint32_t)p.cap); }
+    if (t == 1023) {
+        p.offsets[n] = s_part[1023];
+        if (s_part[1023] > p.out_cap) atomicOr(p.flag, 2);
+    }
+}
+
+__global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) list_scatter_kernel(ListParams p) {
+    __shared__ uint32_t s_cnt[DEC_WARPS][256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < DEC_WARPS * 256; i += DEC_THREADS) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+    if (*p.flag & 2) return;
+    uint32_t *cnt = s_cnt[warp];
+    const unsigned lt = (1u << lane) - 1u;
+    for (int r = blockIdx.x * DEC_WARPS + warp; r < p.n_ranges; r += gridDim.x * DEC_WARPS) {
+        const DecRange rg = p.ranges[r];
+        const int n_words = rg.n_words, base = p.base[r], n_ls = p.rout[r].n_ls, npix = p.npix_per_roach;
+        const uint64_t *w = p.words + rg.start;
+        int ls = 0;
+        uint64_t nxt = lane < n_words ? w[lane] : 0ull;
+        for (int pos = 0; pos < n_words; pos += 32) {
+            const uint64_t x = nxt;
+            if (pos + 32 + lane < n_words) nxt = w[pos + 32 + lane];
+            const bool valid = pos + lane < n_words;
+            const uint32_t adr = (uint32_t)(x >> 56);
+            unsigned eos = __ballot_sync(0xffffffffu, valid && adr == 255u);
+            unsigned todo = __ballot_sync(0xffffffffu, valid);
+            while (todo) {
+                // lanes below the first end-of-second word belong to the current local second
+                const int e = eos ? __ffs(eos) - 1 : 32;
+                const unsigned seg = todo & (e == 32 ? 0xFFFFFFFFu : ((1u << e) - 1u));
+                const bool mine = (seg >> lane) & 1u;
+                const int sec = base + ls;
+                const bool store = mine && (int)adr < npix && sec < p.exptime && ls < n_ls;
+                // rank among the lanes of this step that hit the same pixel (lane order = arrival order)
+                const unsigned peers = __match_any_sync(0xffffffffu, store ? adr : 0x100u + lane);
+                if (store) {
+                    const int leader = __ffs(peers) - 1;
+                    uint32_t old = 0;
+                    if (lane == leader) { old = cnt[adr]; cnt[adr] = old + __popc(peers); }
+                    old = __shfl_sync(peers, old, leader);
+                    const uint32_t rank = p.rows[((size_t)r * DEC_MAX_LS + ls) * DEC_ROW + adr] + old + __popc(peers & lt);
+                    if (rank < (uint32_t)p.cap) {
+                        const long long key = (long long)sec * p.n_pix + (long long)rg.roach * npix + adr;
+                        const long long at = p.offsets[key] + rank;
+                        if (at < p.out_cap) p.out[at] = x;
+                    }
+                }
+                __syncwarp();
+                todo &= ~seg;
+                if (e < 32) {                   // the end-of-second word closes the local second
+                    todo &= ~(1u << e);
+                    eos &= ~(1u << e);
+                    ++ls;
+                    for (int i = lane; i < 256; i += 32) cnt[i] = 0;
+                    __syncwarp();
+                }
+            }
+        }
+        for (int i = lane; i < 256; i += 32) cnt[i] = 0;
+        __syncwarp();
+    }
+}
+
 __global__ void counts_cap_kernel(const uint32_t *in, uint32_t *out, int64_t n, uint32_t cap) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -560,6 +692,8 @@ __global__ void quicklook_kernel(const uint32_t *counts_sec, const int32_t *pixe
     if (i < n) image[i] = (uint16_t)counts_sec[pixel_adr[i]];
 }
 
+struct ListRequest { uint64_t *list_words; int64_t list_cap; int64_t *list_offsets; };
+
 // persistent device buffer i of the decode path (contents survive other calls on the context; lost on growth)
 int dec_private(mkid_ctx *ctx, int i, size_t bytes, void **out) {
     if (ctx->dec_priv_bytes[i] < bytes) {
@@ -579,7 +713,7 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
                   const int64_t *seg_offset, const int64_t *seg_len_in, const int32_t *seg_roach, const int32_t *seg_sec,
                   int32_t *seg_sec_out, int32_t n_seg, const mkid_decode_cfg *cfg, uint32_t *counts_raw,
                   uint32_t *hist, mkid_decode_stats *stats, const int32_t *seg_len_dev = nullptr,
-                  const int32_t *seg_sec_dev = nullptr, int32_t *seg_sec_out_dev = nullptr) {
+                  const int32_t *seg_sec_dev = nullptr, int32_t *seg_sec_out_dev = nullptr, const ListRequest *lists = nullptr) {
     MKID_REQUIRE(ctx, cfg && seg_offset && seg_roach && n_seg > 0, "decode: missing cfg/segments");
     MKID_REQUIRE(ctx, cfg->npix_per_roach > 0 && cfg->npix_per_roach <= 255, "npix_per_roach must be 1..255");
     MKID_REQUIRE(ctx, cfg->n_roaches > 0 && cfg->exptime > 0 && counts_raw, "bad decode cfg");
@@ -638,7 +772,7 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
     // ranges of one roach next to each other (segments stay contiguous and in order): the 16 warps of a CTA then
     // share one shared-memory histogram
     static const bool no_sort = getenv("MKID_DEC_NOSORT") != nullptr;      // (experiment switch)
-    if (!no_sort) std::stable_sort(ranges.begin(), ranges.end(), [](const DecRange &a, const DecRange &b) { return a.roach < b.roach; });
+    if (!no_sort || lists) std::stable_sort(ranges.begin(), ranges.end(), [](const DecRange &a, const DecRange &b) { return a.roach < b.roach; });
     for (int k = 0; k < (int)ranges.size(); ++k) ranges[k].seg_first = (k > 0 && ranges[k - 1].seg == ranges[k].seg) ? ranges[k - 1].seg_first : k;
     MKID_REQUIRE(ctx, ranges.size() <= (size_t)1 << 18, "decode: too many segments in one call");
     for (const DecRange &r : ranges) MKID_REQUIRE(ctx, (int64_t)r.n_words <= (int64_t)1 << 30, "decode: range too long");
@@ -760,6 +894,52 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
             fprintf(stderr, "[mkid decode timing] ranges %d | stream %.1f us  commit %.1f us  absolute %.1f us\n", n_ranges,
                     t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f);
         }
+        if (lists) {
+            // the list product needs every range resolved by its rows: more than DEC_MAX_LS seconds inside one range
+            // (>= 1024 words) is not supported here
+            int flag_h = 0;
+            MKID_CUDA(ctx, cudaMemcpyAsync(&flag_h, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            MKID_REQUIRE(ctx, flag_h == 0, "decode_lists: more than 4 end-of-second words inside one range of the input");
+            const DecRange *hr = (const DecRange *)ctx->dec_ranges_host.data();
+            std::vector<int32_t> roach_first(cfg->n_roaches + 1, n_ranges);
+            for (int k = n_ranges - 1; k >= 0; --k) roach_first[hr[k].roach] = k;
+            for (int q = cfg->n_roaches - 1; q >= 0; --q) roach_first[q] = std::min(roach_first[q], roach_first[q + 1]);
+            const size_t n_keys = (size_t)cfg->exptime * n_pix;
+            char *lbuf;
+            if ((rc = mkid_scratch(ctx, SCR_AUX5, n_keys * 4 + (size_t)(cfg->n_roaches + 1) * 4 + 64, (void **)&lbuf))) return rc;
+            uint32_t *d_acc = (uint32_t *)lbuf;
+            int32_t *d_rf = (int32_t *)(lbuf + n_keys * 4);
+            MKID_CUDA(ctx, cudaMemsetAsync(d_acc, 0, n_keys * 4, ctx->stream));
+            MKID_CUDA(ctx, cudaMemcpyAsync(d_rf, roach_first.data(), roach_first.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            void *d_lw, *d_lo;
+            if ((rc = mkid_stage_out(ctx, lists->list_words, (size_t)lists->list_cap * 8, SCR_OUT2, false, &d_lw))) return rc;
+            if ((rc = mkid_stage_out(ctx, lists->list_offsets, (n_keys + 1) * 8, SCR_OUT3, false, &d_lo))) return rc;
+            ListParams lp;
+            lp.words = p.words; lp.ranges = d_ranges; lp.rout = d_rout; lp.base = d_base; lp.eos_tot = d_eos; lp.roach_first = d_rf;
+            lp.rows = d_rows; lp.acc = d_acc; lp.offsets = (long long *)d_lo; lp.out = (uint64_t *)d_lw; lp.out_cap = lists->list_cap;
+            lp.n_ranges = n_ranges; lp.n_roaches = cfg->n_roaches; lp.n_pix = (int)n_pix; lp.npix_per_roach = cfg->npix_per_roach;
+            lp.exptime = cfg->exptime; lp.cap = cfg->max_events - 1; lp.flag = d_flag;
+            list_rowstart_kernel<<<cfg->n_roaches, 256, 0, ctx->stream>>>(lp);
+            MKID_CHECK_LAUNCH(ctx);
+            list_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(lp);
+            MKID_CHECK_LAUNCH(ctx);
+            list_scatter_kernel<<<grid, DEC_THREADS, 0, ctx->stream>>>(lp);
+            MKID_CHECK_LAUNCH(ctx);
+            MKID_CUDA(ctx, cudaMemcpyAsync(&flag_h, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            MKID_REQUIRE(ctx, (flag_h & 2) == 0, "decode_lists: list_words capacity too small (see list_offsets[last])");
+            if ((rc = mkid_stage_out_finish(ctx, lists->list_words, (size_t)lists->list_cap * 8, d_lw))) return rc;
+            if ((rc = mkid_stage_out_finish(ctx, lists->list_offsets, (n_keys + 1) * 8, d_lo))) return rc;
+        }
+    }
+    if (lists && n_ranges == 0) {          // no words: every list is empty
+        void *d_lo;
+        const size_t ob = ((size_t)cfg->exptime * n_pix + 1) * 8;
+        if ((rc = mkid_stage_out(ctx, lists->list_offsets, ob, SCR_OUT3, false, &d_lo))) return rc;
+        MKID_CUDA(ctx, cudaMemsetAsync(d_lo, 0, ob, ctx->stream));
+        if ((rc = mkid_stage_out_finish(ctx, lists->list_offsets, ob, d_lo))) return rc;
     }
     rc = mkid_stage_out_finish(ctx, counts_raw, counts_bytes, d_counts);
     if (rc) return rc;
@@ -827,6 +1007,18 @@ extern "C" int mkid_decode_words_dev(mkid_ctx *ctx, const uint64_t *words, int64
     for (int i = 0; i < n_segments; ++i) MKID_REQUIRE(ctx, seg_cap[i] > 0, "decode_words_dev: empty segment capacity");
     return decode_common(ctx, words, nullptr, n_words, seg_start, seg_cap, seg_roach, nullptr, nullptr, n_segments, cfg,
                          counts_raw, hist, nullptr, seg_len_dev, seg_sec_dev, seg_sec_out_dev);
+}
+
+extern "C" int mkid_decode_lists(mkid_ctx *ctx, const uint64_t *words, int64_t n_words, const int64_t *seg_offset,
+                                 const int32_t *seg_roach, const int32_t *seg_sec, int32_t *seg_sec_out, int32_t n_segments,
+                                 const mkid_decode_cfg *cfg, uint32_t *counts_raw, uint64_t *list_words, int64_t list_cap,
+                                 int64_t *list_offsets, mkid_decode_stats *stats) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, (words || n_words == 0) && list_words && list_offsets && list_cap > 0 && cfg && cfg->max_events >= 2,
+                 "decode_lists: NULL argument");
+    ListRequest lr{list_words, list_cap, list_offsets};
+    return decode_common(ctx, words, nullptr, n_words, seg_offset, nullptr, seg_roach, seg_sec, seg_sec_out, n_segments, cfg,
+                         counts_raw, nullptr, stats, nullptr, nullptr, nullptr, &lr);
 }
 
 extern "C" int mkid_decode_wire(mkid_ctx *ctx, const uint32_t *wire, int64_t n_bundles, const int64_t *seg_offset,

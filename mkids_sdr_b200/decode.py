@@ -108,6 +108,23 @@ class PhotonDecoder:
                                              _lib.ptr(sec_out_dev), roach.size, ctypes.byref(self.cfg),
                                              _lib.ptr(self.counts_dev), _lib.ptr(self.hist_dev)))
 
+    def decode_lists(self, words, seg_offset, seg_roach, seg_sec=None, n_words=None):
+        """Decode + the per-(second, pixel) photon lists of PacketMaster (PacketMaster.c:371-380, :1012-1016).
+        Returns (list_words u64, list_offsets int64 [exptime*n_pix + 1], seg_sec_out): the words of key
+        k = sec*n_pix + pixel are list_words[list_offsets[k]:list_offsets[k+1]] in arrival order, at most
+        max_events-1 per key.  counts_raw / stats are accumulated as in decode_words."""
+        off, roach, sec = _seg_arrays(seg_offset, seg_roach, seg_sec)
+        if n_words is None:
+            n_words = int(off[-1])
+        sec_out = np.zeros(roach.size, dtype=np.int32)
+        lw = np.empty(max(n_words, 1), dtype=np.uint64)
+        lo = np.empty(self.exptime * self.n_pix + 1, dtype=np.int64)
+        c = self.ctx
+        c._check(c.lib.mkid_decode_lists(c.h, _lib.ptr(words), n_words, _lib.ptr(off), _lib.ptr(roach), _lib.ptr(sec),
+                                         _lib.ptr(sec_out), roach.size, ctypes.byref(self.cfg), _lib.ptr(self.counts_dev),
+                                         _lib.ptr(lw), lw.size, _lib.ptr(lo), ctypes.addressof(self.stats)))
+        return lw[:int(lo[-1])], lo, sec_out
+
     def decode_wire(self, wire, seg_offset, seg_roach, seg_sec=None, n_bundles=None, want_stats=True):
         """wire: PulseServer bundles (bytes / u8 / u32 array, host or device)."""
         if isinstance(wire, (bytes, bytearray, memoryview)):

@@ -156,3 +156,33 @@ def test_full_size_config1_properties(ctx):
     ref = odec.packetmaster_bin(streams, npix, secs)
     assert np.array_equal(raw, ref['raw_counts'])
     assert st['n_nonpixel'] == ref['n_nonpixel']
+
+
+def test_photon_lists_match_packetmaster(ctx):
+    """Per-(second, pixel) photon lists (PacketMaster.c:371-380): arrival order inside a key, cap quirk."""
+    from mkids_sdr_b200 import synth
+    from mkids_sdr_b200.decode import PhotonDecoder
+    R, npix, secs, cap = 4, 253, 3, 2500
+    streams, _ = synth.photon_streams(600000, R, npix, secs, seed=5, n_hot=3, hot_rate=3000)
+    dec = PhotonDecoder(R, npix, secs, cap, None, 0, ctx=ctx)
+    lens = [len(s) for s in streams]
+    off = np.concatenate([[0], np.cumsum(lens)])
+    lw, lo, sec_out = dec.decode_lists(np.concatenate(streams), off, np.arange(R))
+    ref = odec.packetmaster_bin(streams, npix, secs, cap, want_lists=True)
+    assert np.array_equal(lo, ref['list_offsets'])
+    assert np.array_equal(lw, ref['list_words'])
+    assert np.array_equal(dec.counts_raw(), ref['raw_counts'])
+    assert np.diff(lo).max() == cap - 1                       # hot pixels hit the cap
+    # literal word-by-word loop on a small ragged case, two segments per roach (carried seconds)
+    R2, npix2, secs2, cap2 = 2, 11, 4, 40
+    small = _ragged_streams(3, R2, npix2, secs2, 900)
+    dec2 = PhotonDecoder(R2, npix2, secs2, cap2, None, 0, ctx=ctx)
+    lw2, lo2, _ = dec2.decode_lists(np.concatenate(small), np.concatenate([[0], np.cumsum([len(s) for s in small])]),
+                                    np.arange(R2))
+    lit = odec.packetmaster_bin_literal(small, npix2, secs2, cap2)
+    for s in range(secs2):
+        for pix in range(R2 * npix2):
+            k = s * R2 * npix2 + pix
+            got = lw2[lo2[k]:lo2[k + 1]].tolist()
+            want = [int(w) for w in lit['lists'].get((s, pix), [])]
+            assert got == want, (s, pix)
