@@ -330,6 +330,7 @@ def decode_side_bench(ctx, peak):
     (replicated 16x = 1.28 GB so the input exceeds L2), device resident."""
     from mkids_sdr_b200 import synth
     from mkids_sdr_b200.decode import PhotonDecoder
+    from mkids_sdr_b200._lib import ptr as _lib_ptr
     R, npix, secs = 8, 253, 10
     streams, _ = synth.photon_streams(10 ** 7, R, npix, secs, seed=1234)
     lens = [len(s) for s in streams]
@@ -352,6 +353,33 @@ def decode_side_bench(ctx, peak):
         ms = ctx.elapsed_ms(2, 3) / k
         gbs = words.size * 8 / ms / 1e6
         out[name] = {'words_per_s': words.size / ms * 1e3, 'GB/s': gbs, 'frac_hbm': gbs / peak, 'ms': ms}
+    # PacketMaster's per-(second, pixel) photon lists (16 B/word algorithmic: read + sorted write); every replica of the
+    # file continues the seconds of the previous one so that all keys are distinct
+    try:
+        dec = PhotonDecoder(R, npix, secs * reps, 2500, None, 1, None, ctx=ctx)
+        sec0 = np.repeat(np.arange(reps) * secs, R).astype(np.int32)
+        lw_dev = ctx.alloc(words.size * 8)
+        lo_dev = ctx.alloc((secs * reps * R * npix + 1) * 8)
+        import ctypes as _ct
+        sec_out = np.zeros(roach.size, dtype=np.int32)
+
+        def run_lists():
+            ctx._check(ctx.lib.mkid_decode_lists(ctx.h, _lib_ptr(dw), words.size, _lib_ptr(offs), _lib_ptr(roach.astype(np.int32)),
+                                                 _lib_ptr(sec0), _lib_ptr(sec_out), roach.size, _ct.byref(dec.cfg),
+                                                 _lib_ptr(dec.counts_dev), _lib_ptr(lw_dev), words.size, _lib_ptr(lo_dev), None))
+        run_lists()
+        ctx.sync(); ctx.record(2)
+        k = 3
+        for _ in range(k):
+            run_lists()
+        ctx.record(3)
+        ms = ctx.elapsed_ms(2, 3) / k
+        gbs = words.size * 16 / ms / 1e6
+        out['photon_lists'] = {'words_per_s': words.size / ms * 1e3, 'GB/s': gbs, 'frac_hbm': gbs / peak, 'ms': ms,
+                               'algorithmic_bytes_per_word': 16}
+        lw_dev.free(); lo_dev.free()
+    except Exception as e:
+        out['photon_lists'] = {'error': str(e)}
     tp = os.path.join(ROOT, 'profiles', 'k6_traffic.json')
     if os.path.exists(tp):
         try:

@@ -551,32 +551,63 @@ __global__ void __launch_bounds__(256) list_rowstart_kernel(ListParams p) {
     int cur_sec = -1;
     uint32_t run = 0;
     uint32_t *acc_col = p.acc + (size_t)roach * p.npix_per_roach + ch;
-    for (int r = r0; r < r1; ++r) {
-        const int n_ls = p.rout[r].n_ls, base = p.base[r];
-        for (int ls = 0; ls < n_ls; ++ls) {
-            const int sec = base + ls;
-            uint32_t *cell = p.rows + ((size_t)r * DEC_MAX_LS + ls) * DEC_ROW + ch;
-            if (!is_pix || sec >= p.exptime) continue;
-            const uint32_t v = *cell;
-            if (sec != cur_sec) {              // seconds normally only grow along a roach stream: rare
-                if (cur_sec >= 0) acc_col[(size_t)cur_sec * p.n_pix] = run;
-                cur_sec = sec;
-                run = acc_col[(size_t)sec * p.n_pix];
+    for (int rb = r0; rb < r1; rb += 8) {          // 8 ranges per round: their loads are independent of the running count
+        int nls[8], bs[8];
+        uint32_t v0[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = min(rb + i, r1 - 1);
+            nls[i] = p.rout[r].n_ls; bs[i] = p.base[r];
+            v0[i] = p.rows[((size_t)r * DEC_MAX_LS) * DEC_ROW + ch];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = rb + i;
+            if (r >= r1) break;
+            for (int ls = 0; ls < nls[i]; ++ls) {
+                const int sec = bs[i] + ls;
+                uint32_t *cell = p.rows + ((size_t)r * DEC_MAX_LS + ls) * DEC_ROW + ch;
+                if (!is_pix || sec >= p.exptime) continue;
+                const uint32_t v = ls == 0 ? v0[i] : *cell;
+                if (sec != cur_sec) {              // seconds normally only grow along a roach stream: rare
+                    if (cur_sec >= 0) acc_col[(size_t)cur_sec * p.n_pix] = run;
+                    cur_sec = sec;
+                    run = acc_col[(size_t)sec * p.n_pix];
+                }
+                *cell = run;
+                run += v;
             }
-            *cell = run;
-            run += v;
         }
     }
     if (is_pix && cur_sec >= 0) acc_col[(size_t)cur_sec * p.n_pix] = run;
 }
 
-__global__ void __launch_bounds__(1024) list_offsets_kernel(ListParams p) {
-    __shared__ long long s_part[1024];
+// offsets = exclusive scan of min(acc, cap) over the keys: block sums, scan of the block sums, block scans
+constexpr int LIST_SCAN_BLOCK = 4096;                 // keys per CTA (1024 threads x 4, coalesced 128-bit loads)
+__global__ void __launch_bounds__(1024) list_blocksum_kernel(ListParams p, long long *block_sums) {
+    __shared__ long long s_w[32];
     const long long n = (long long)p.exptime * p.n_pix;
+    const long long i = ((long long)blockIdx.x * 1024 + threadIdx.x) * 4;
+    long long v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (i + k < n) v += min(p.acc[i + k], (uint32_t)p.cap);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        long long t = s_w[threadIdx.x];
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(0xffffffffu, t, d);
+        if (threadIdx.x == 0) block_sums[blockIdx.x] = t;
+    }
+}
+__global__ void __launch_bounds__(1024) list_blockscan_kernel(ListParams p, long long *block_sums, int n_blocks) {
+    __shared__ long long s_part[1024];          // exclusive scan of the block sums in place (one CTA)
     const int t = threadIdx.x;
-    const long long per = (n + 1023) / 1024, i0 = min(n, t * per), i1 = min(n, i0 + per);
+    const int per = (n_blocks + 1023) / 1024, i0 = min(n_blocks, t * per), i1 = min(n_blocks, i0 + per);
     long long sum = 0;
-    for (long long i = i0; i < i1; ++i) sum += min(p.acc[i], (uint32_t)p.cap);
+    for (int i = i0; i < i1; ++i) sum += block_sums[i];
     s_part[t] = sum;
     __syncthreads();
     for (int d = 1; d < 1024; d <<= 1) {
@@ -586,67 +617,121 @@ __global__ void __launch_bounds__(1024) list_offsets_kernel(ListParams p) {
         __syncthreads();
     }
     long long run = t > 0 ? s_part[t - 1] : 0;
-    for (long long i = i0; i < i1; ++i) { p.offsets[i] = run; run += min(p.acc[i], (uint32_t)p.cap); }
+    for (int i = i0; i < i1; ++i) { const long long v = block_sums[i]; block_sums[i] = run; run += v; }
     if (t == 1023) {
-        p.offsets[n] = s_part[1023];
+        p.offsets[(long long)p.exptime * p.n_pix] = s_part[1023];
         if (s_part[1023] > p.out_cap) atomicOr(p.flag, 2);
     }
 }
-
-__global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) list_scatter_kernel(ListParams p) {
-    __shared__ uint32_t s_cnt[DEC_WARPS][256];
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    for (int i = tid; i < DEC_WARPS * 256; i += DEC_THREADS) (&s_cnt[0][0])[i] = 0;
+__global__ void __launch_bounds__(1024) list_offsets_kernel(ListParams p, const long long *block_sums) {
+    __shared__ long long s_w[32];
+    const long long n = (long long)p.exptime * p.n_pix;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const long long i = ((long long)blockIdx.x * 1024 + t) * 4;
+    long long v[4], tot = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { v[k] = i + k < n ? (long long)min(p.acc[i + k], (uint32_t)p.cap) : 0; tot += v[k]; }
+    long long incl = tot;                       // inclusive scan over the warp, then over the 32 warps
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const long long a = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += a; }
+    if (lane == 31) s_w[warp] = incl;
     __syncthreads();
+    if (warp == 0) {
+        long long w = s_w[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const long long a = __shfl_up_sync(0xffffffffu, wi, d); if (lane >= d) wi += a; }
+        s_w[lane] = wi - w;                     // exclusive
+    }
+    __syncthreads();
+    long long run = block_sums[blockIdx.x] + s_w[warp] + incl - tot;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { if (i + k < n) p.offsets[i + k] = run; run += v[k]; }
+}
+
+// one warp per range re-reads its words in order; per local second the destination of the next word of every pixel
+// (offsets[key] + words of earlier ranges + words so far) and the slots left under the cap sit in shared memory
+constexpr int LIST_WARPS = 8;
+__global__ void __launch_bounds__(LIST_WARPS * 32) list_scatter_kernel(ListParams p) {
+    __shared__ long long s_dst[LIST_WARPS][256];
+    __shared__ int s_left[LIST_WARPS][256];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (*p.flag & 2) return;
-    uint32_t *cnt = s_cnt[warp];
+    long long *dst = s_dst[warp];
+    int *left = s_left[warp];
     const unsigned lt = (1u << lane) - 1u;
-    for (int r = blockIdx.x * DEC_WARPS + warp; r < p.n_ranges; r += gridDim.x * DEC_WARPS) {
+    // L2 policies: the input streams through (evict first); the scattered 8-byte stores must stay resident until their
+    // 32-byte sectors are complete (evict last), else every store costs a DRAM read-modify-write
+    uint64_t pol_in, pol_out;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_in));
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_out));
+    auto ld_in = [&](const uint64_t *q) -> uint64_t {
+        uint64_t v;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(q), "l"(pol_in));
+        return v;
+    };
+    for (int r = blockIdx.x * LIST_WARPS + warp; r < p.n_ranges; r += gridDim.x * LIST_WARPS) {
         const DecRange rg = p.ranges[r];
         const int n_words = rg.n_words, base = p.base[r], n_ls = p.rout[r].n_ls, npix = p.npix_per_roach;
         const uint64_t *w = p.words + rg.start;
         int ls = 0;
-        uint64_t nxt = lane < n_words ? w[lane] : 0ull;
-        for (int pos = 0; pos < n_words; pos += 32) {
-            const uint64_t x = nxt;
-            if (pos + 32 + lane < n_words) nxt = w[pos + 32 + lane];
-            const bool valid = pos + lane < n_words;
-            const uint32_t adr = (uint32_t)(x >> 56);
-            unsigned eos = __ballot_sync(0xffffffffu, valid && adr == 255u);
-            unsigned todo = __ballot_sync(0xffffffffu, valid);
-            while (todo) {
-                // lanes below the first end-of-second word belong to the current local second
-                const int e = eos ? __ffs(eos) - 1 : 32;
-                const unsigned seg = todo & (e == 32 ? 0xFFFFFFFFu : ((1u << e) - 1u));
-                const bool mine = (seg >> lane) & 1u;
-                const int sec = base + ls;
-                const bool store = mine && (int)adr < npix && sec < p.exptime && ls < n_ls;
-                // rank among the lanes of this step that hit the same pixel (lane order = arrival order)
-                const unsigned peers = __match_any_sync(0xffffffffu, store ? adr : 0x100u + lane);
-                if (store) {
-                    const int leader = __ffs(peers) - 1;
-                    uint32_t old = 0;
-                    if (lane == leader) { old = cnt[adr]; cnt[adr] = old + __popc(peers); }
-                    old = __shfl_sync(peers, old, leader);
-                    const uint32_t rank = p.rows[((size_t)r * DEC_MAX_LS + ls) * DEC_ROW + adr] + old + __popc(peers & lt);
-                    if (rank < (uint32_t)p.cap) {
-                        const long long key = (long long)sec * p.n_pix + (long long)rg.roach * npix + adr;
-                        const long long at = p.offsets[key] + rank;
-                        if (at < p.out_cap) p.out[at] = x;
-                    }
+        auto open_second = [&]() {              // destinations of local second ls (nothing is stored beyond exptime)
+            const int sec = base + ls;
+            const bool live = sec < p.exptime && ls < n_ls;
+            for (int i = lane; i < 256; i += 32) {
+                long long d = 0; int l = 0;
+                if (live && i < npix) {
+                    const uint32_t before = p.rows[((size_t)r * DEC_MAX_LS + ls) * DEC_ROW + i];
+                    d = p.offsets[(long long)sec * p.n_pix + (long long)rg.roach * npix + i] + before;
+                    l = before < (uint32_t)p.cap ? p.cap - (int)before : 0;
                 }
-                __syncwarp();
-                todo &= ~seg;
-                if (e < 32) {                   // the end-of-second word closes the local second
-                    todo &= ~(1u << e);
-                    eos &= ~(1u << e);
-                    ++ls;
-                    for (int i = lane; i < 256; i += 32) cnt[i] = 0;
+                dst[i] = d; left[i] = l;
+            }
+            __syncwarp();
+        };
+        open_second();
+        constexpr int LR = 8;                         // 32-word steps in flight
+        uint64_t ring[LR];
+#pragma unroll
+        for (int g = 0; g < LR; ++g) ring[g] = g * 32 + lane < n_words ? ld_in(w + g * 32 + lane) : 0ull;
+        for (int pos0 = 0; pos0 < n_words; pos0 += 32 * LR) {
+#pragma unroll
+            for (int g = 0; g < LR; ++g) {
+                const int pos = pos0 + g * 32;
+                if (pos >= n_words) break;
+                const uint64_t x = ring[g];
+                if (pos + 32 * LR + lane < n_words) ring[g] = ld_in(w + pos + 32 * LR + lane);
+                const bool valid = pos + lane < n_words;
+                const uint32_t adr = (uint32_t)(x >> 56);
+                unsigned eos = __ballot_sync(0xffffffffu, valid && adr == 255u);
+                unsigned todo = __ballot_sync(0xffffffffu, valid);
+                while (todo) {
+                    // lanes below the first end-of-second word belong to the current local second
+                    const int e = eos ? __ffs(eos) - 1 : 32;
+                    const unsigned seg = todo & (e == 32 ? 0xFFFFFFFFu : ((1u << e) - 1u));
+                    const bool store = ((seg >> lane) & 1u) && (int)adr < npix;
+                    // rank among the lanes of this step that hit the same pixel (lane order = arrival order)
+                    const unsigned peers = __match_any_sync(0xffffffffu, store ? adr : 0x100u + lane);
+                    if (store) {
+                        const int leader = __ffs(peers) - 1;
+                        long long d0 = 0; int l0 = 0;
+                        if (lane == leader) { d0 = dst[adr]; l0 = left[adr]; dst[adr] = d0 + __popc(peers); left[adr] = l0 - __popc(peers); }
+                        d0 = __shfl_sync(peers, d0, leader);
+                        l0 = __shfl_sync(peers, l0, leader);
+                        const int k = __popc(peers & lt);
+                        if (k < l0 && d0 + k < p.out_cap)
+                            asm volatile("st.global.L2::cache_hint.b64 [%0], %1, %2;" ::"l"(p.out + d0 + k), "l"(x), "l"(pol_out) : "memory");
+                    }
                     __syncwarp();
+                    todo &= ~seg;
+                    if (e < 32) {                   // the end-of-second word closes the local second
+                        todo &= ~(1u << e);
+                        eos &= ~(1u << e);
+                        ++ls;
+                        open_second();
+                    }
                 }
             }
         }
-        for (int i = lane; i < 256; i += 32) cnt[i] = 0;
         __syncwarp();
     }
 }
@@ -921,12 +1006,31 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
             lp.rows = d_rows; lp.acc = d_acc; lp.offsets = (long long *)d_lo; lp.out = (uint64_t *)d_lw; lp.out_cap = lists->list_cap;
             lp.n_ranges = n_ranges; lp.n_roaches = cfg->n_roaches; lp.n_pix = (int)n_pix; lp.npix_per_roach = cfg->npix_per_roach;
             lp.exptime = cfg->exptime; lp.cap = cfg->max_events - 1; lp.flag = d_flag;
+            static cudaEvent_t lev[4] = {};
+            auto lmark = [&](int i) { if (!timing) return; if (!lev[i]) cudaEventCreate(&lev[i]); cudaEventRecord(lev[i], ctx->stream); };
+            lmark(0);
             list_rowstart_kernel<<<cfg->n_roaches, 256, 0, ctx->stream>>>(lp);
             MKID_CHECK_LAUNCH(ctx);
-            list_offsets_kernel<<<1, 1024, 0, ctx->stream>>>(lp);
+            lmark(1);
+            const int n_sb = (int)((n_keys + LIST_SCAN_BLOCK - 1) / LIST_SCAN_BLOCK);
+            long long *d_bs;
+            if ((rc = mkid_scratch(ctx, SCR_AUX3, (size_t)n_sb * 8 + 64, (void **)&d_bs))) return rc;
+            list_blocksum_kernel<<<n_sb, 1024, 0, ctx->stream>>>(lp, d_bs);
             MKID_CHECK_LAUNCH(ctx);
-            list_scatter_kernel<<<grid, DEC_THREADS, 0, ctx->stream>>>(lp);
+            list_blockscan_kernel<<<1, 1024, 0, ctx->stream>>>(lp, d_bs, n_sb);
             MKID_CHECK_LAUNCH(ctx);
+            list_offsets_kernel<<<n_sb, 1024, 0, ctx->stream>>>(lp, d_bs);
+            MKID_CHECK_LAUNCH(ctx);
+            lmark(2);
+            list_scatter_kernel<<<(n_ranges + LIST_WARPS - 1) / LIST_WARPS, LIST_WARPS * 32, 0, ctx->stream>>>(lp);
+            MKID_CHECK_LAUNCH(ctx);
+            lmark(3);
+            if (timing) {
+                float t[3];
+                cudaEventSynchronize(lev[3]);
+                for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&t[i], lev[i], lev[i + 1]);
+                fprintf(stderr, "[mkid decode timing] lists: rowstart %.1f us  offsets %.1f us  scatter %.1f us\n", t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f);
+            }
             MKID_CUDA(ctx, cudaMemcpyAsync(&flag_h, d_flag, 4, cudaMemcpyDeviceToHost, ctx->stream));
             MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             MKID_REQUIRE(ctx, (flag_h & 2) == 0, "decode_lists: list_words capacity too small (see list_offsets[last])");
