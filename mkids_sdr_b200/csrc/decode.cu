@@ -94,7 +94,7 @@ template <bool WIRE, int HIST, bool NEED_LO, bool ABS>
 struct RangeDecoder {
     static constexpr int J = WIRE ? 4 : 2;
     static constexpr int G = 32 * J;                   // words per group
-    static constexpr int R = (WIRE ? 4 : 8) / (NEED_LO ? 2 : 1);   // ring depth: 16 registers, 512 (256) words per warp in flight
+    static constexpr int R = WIRE ? (NEED_LO ? 2 : 6) : (NEED_LO ? 4 : 8);   // ring depth: 16-24 registers per lane in flight
     // position of (lane, j) inside a group: flat = lane-contiguous 32/64-bit loads, wire = one 128-bit load per lane
     __device__ __forceinline__ int idx_of(int j) const { return WIRE ? 4 * lane + j : 32 * j + lane; }
 

@@ -125,14 +125,14 @@ class PhotonDecoder:
                                          _lib.ptr(lw), lw.size, _lib.ptr(lo), ctypes.addressof(self.stats)))
         return lw[:int(lo[-1])], lo, sec_out
 
-    def decode_wire(self, wire, seg_offset, seg_roach, seg_sec=None, n_bundles=None, want_stats=True):
+    def decode_wire(self, wire, seg_offset, seg_roach, seg_sec=None, n_bundles=None, want_stats=True, want_sec=True):
         """wire: PulseServer bundles (bytes / u8 / u32 array, host or device)."""
         if isinstance(wire, (bytes, bytearray, memoryview)):
             wire = np.frombuffer(wire, dtype=np.uint8)
         off, roach, sec = _seg_arrays(seg_offset, seg_roach, seg_sec)
         if n_bundles is None:
             n_bundles = int(off[-1])
-        sec_out = np.zeros(roach.size, dtype=np.int32)
+        sec_out = np.zeros(roach.size, dtype=np.int32) if want_sec else None
         c = self.ctx
         c._check(c.lib.mkid_decode_wire(c.h, _lib.ptr(wire), n_bundles, _lib.ptr(off), _lib.ptr(roach), _lib.ptr(sec),
                                         _lib.ptr(sec_out), roach.size, ctypes.byref(self.cfg),
