@@ -85,3 +85,42 @@ def test_chain_async_equals_sync(ctx):
         for a, b in zip(res[0], r):
             assert np.array_equal(a, b)
     assert res[0][0].sum() > 100
+
+
+def test_full_size_config3_properties(ctx):
+    """BASELINE config 3 at full size (8 boards x 2^25 samples per batch, N_lut = 2^19), checked through
+    size-independent properties: streaming invariance (one batch of 2^25 == two batches of 2^24: identical photon
+    words), checksum of checksums (histogram row sums == per-pixel counts == words emitted), time order."""
+    from mkids_sdr_b200.chain import ReadoutChain
+    from mkids_sdr_b200.channelizer import synth_adc
+    B, n_lut, n = 8, 2 ** 19, 2 ** 25
+    chain, boards = ReadoutChain.synthetic(B, n_lut, 253, seed0=42, ctx=ctx, exptime=4, n_bins=64)
+    tb = np.stack([bd['tone_bins'] for bd in boards])
+    iq = ctx.alloc(B * n * 4)
+    synth_adc(B, n, tb, n_lut=n_lut, pulse_rate=1000.0, seed=1000, out=iq, ctx=ctx)
+    cap = chain.chan.words_capacity(n)
+    wh = np.zeros((B, cap), dtype=np.uint64)
+    nw = chain.process(iq, n=n, words_host=wh)
+    whole = [wh[b, :nw[b]].copy() for b in range(B)]
+    counts, hist = chain.dec.counts_raw(), chain.dec.hist()
+    assert nw.min() > 5000                                     # ~1000 pulses/s x 253 channels x 65.5 ms
+    assert int(counts.sum()) == int(nw.sum())                  # no second boundary inside 65.5 ms: no EOS words
+    assert np.array_equal(hist.sum(axis=1), counts.sum(axis=0))
+    for b in range(B):
+        ts = (whole[b] & np.uint64(0xFFFFF)).astype(np.int64)
+        assert np.all(np.diff(ts) >= 0)                        # (time, channel) order
+        assert int((whole[b] >> np.uint64(56)).max()) < 253
+    # the same stream in two halves: [B][n] rows are contiguous per board, so copy each half into its own buffer
+    chain.reset()
+    half = ctx.alloc(B * (n // 2) * 4)
+    parts = [[] for _ in range(B)]
+    for h in range(2):
+        for b in range(B):
+            ctx._check(ctx.lib.mkid_memcpy(ctx.h, half.ptr + b * (n // 2) * 4, iq.ptr + (b * n + h * (n // 2)) * 4, (n // 2) * 4))
+        nwh = chain.process(half, n=n // 2, words_host=wh)
+        for b in range(B):
+            parts[b].append(wh[b, :nwh[b]].copy())
+    for b in range(B):
+        assert np.array_equal(np.concatenate(parts[b]), whole[b])
+    assert np.array_equal(chain.dec.counts_raw(), counts) and np.array_equal(chain.dec.hist(), hist)
+    iq.free(); half.free()
