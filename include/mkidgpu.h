@@ -285,6 +285,22 @@ int mkid_thresholds_from_phase(mkid_ctx *ctx, const int16_t *phase, int32_t n_bo
                                int64_t row_stride, int32_t n_ch, int64_t n_samples, double nsigma,
                                int32_t *thr_raw, double *med, double *p5);
 
+/* longsnapshot noise spectrum (ROACH_Pulses.py:521-537): phase_deg float64 [n_streams][n_samples];
+ * nSamplesPerFFT = n_samples / n_averages (integer division, 2^20/100 = 10485 in the reference);
+ * noise_db[s][k] = mean over the n_averages segments of 20*log10(|numpy.fft.fft(segment)[k]| / norm / 1e-6),
+ * float64 [n_streams][nSamplesPerFFT] (norm = 50.0 in the reference). */
+int mkid_noise_spectrum(mkid_ctx *ctx, const double *phase_deg, int32_t n_streams, int64_t n_samples,
+                        int32_t n_averages, double norm, double *noise_db);
+
+/* Per-pixel spectra products of the dashboard's image_Worker (ReadoutControls/ArconsDashboard.py:1282-1504) on the
+ * 10-bin per-pixel spectrum darray u32 [n_pix][10] ("data.bin", :1331-1337; K6 accumulates it with n_bins = 10):
+ * medians[10] = numpy.median over the pixels of every bin (:1338-1340); optional sky subtraction x - int(median)
+ * (subtract_sky); pc[p] = sum of the bins (:1453-1455); me[p] = (C0*E0 + ... + C9*E9)/pc[p], and h*c/me for
+ * wavelength bins (calc_mean_energy :1356-1363), float64 in the reference's operation order.
+ * bin_centres: E0..E9 (host, setup_thread :1299-1322). */
+int mkid_spectra_products(mkid_ctx *ctx, const uint32_t *darray, int32_t n_pix, const double *bin_centres, double hc,
+                          int32_t wavelength, int32_t sky_subtraction, double *medians, int64_t *pc, double *me);
+
 /* ------------------------------------------------------------------ LUT synthesis (K1-K3)
  * mkid_comb_lut replaces AppForm.freqCombLUT (ChannelizerControls/ROACH_Setup.py:416-475; twin with GUI
  * offset/scale options ROACH_Setup_DAC.py:396-455): I[t] = sum a_n cos(2 pi f_n (t+offset)/fs + phi_n),

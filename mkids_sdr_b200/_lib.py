@@ -102,6 +102,9 @@ _SIGNATURES = {
     'mkid_soft_trigger': (c_int32, [c_void_p, c_void_p, c_int32, c_int64, POINTER(TriggerCfg), c_void_p, c_int32, c_void_p]),
     'mkid_thresholds_from_phase': (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int64, c_int32, c_int64, c_double,
                                              c_void_p, c_void_p, c_void_p]),
+    'mkid_noise_spectrum': (c_int32, [c_void_p, c_void_p, c_int32, c_int64, c_int32, c_double, c_void_p]),
+    'mkid_spectra_products': (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_double, c_int32, c_int32, c_void_p,
+                                        c_void_p, c_void_p]),
     'mkid_random_phases': (c_int32, [ctypes.c_uint32, c_int32, c_void_p]),
     'mkid_comb_lut': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_double, c_int32, c_int32, c_double,
                                 c_int32, c_double, c_int32, c_void_p, c_void_p, c_void_p]),

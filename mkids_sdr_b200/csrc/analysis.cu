@@ -328,3 +328,147 @@ extern "C" int mkid_thresholds_from_phase(mkid_ctx *ctx, const int16_t *phase, i
     if (p5 && (rc = mkid_stage_out_finish(ctx, p5, cnt * 8, d_p5))) return rc;
     return MKID_OK;
 }
+
+// ---------------------------------------------------------------- longsnapshot noise spectrum (ROACH_Pulses.py:521-537)
+// noiseFFT[k] = mean over the nFFTAverages segments of 20*log10(|fft(segment)[k]| / norm / 1e-6).  The segment
+// length nLongsnapSamples/100 = 10485 is not a power of two: direct DFT with an exact twiddle table
+// (k*n mod N in integers, sincospi), float64; one CTA per (output bin block, stream).
+namespace {
+__global__ void dft_twiddle_kernel(int N, double2 *tw) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= N) return;
+    double s, c;
+    sincospi(2.0 * (double)m / (double)N, &s, &c);
+    tw[m] = make_double2(c, -s);                                   // e^{-2 pi i m / N}
+}
+__global__ void __launch_bounds__(128) noise_spectrum_kernel(const double *__restrict__ x, int64_t stream_stride, int N,
+                                                             int n_avg, double norm, const double2 *__restrict__ tw,
+                                                             double *out) {
+    extern __shared__ double s_x[];                                // one segment
+    const int s = blockIdx.y;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    const double *xs = x + (size_t)s * stream_stride;
+    double acc_db = 0.0;
+    for (int a = 0; a < n_avg; ++a) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < N; i += blockDim.x) s_x[i] = xs[(size_t)a * N + i];
+        __syncthreads();
+        if (k < N) {
+            double re = 0.0, im = 0.0;
+            int m = 0;                                             // k*n mod N
+            for (int n = 0; n < N; ++n) {
+                const double2 w = tw[m];
+                re = fma(s_x[n], w.x, re);
+                im = fma(s_x[n], w.y, im);
+                m += k; if (m >= N) m -= N;
+            }
+            const double mag = sqrt(re * re + im * im);
+            acc_db += 20.0 * log10(mag / norm / 1e-6);
+        }
+    }
+    if (k < N) out[(size_t)s * N + k] = acc_db / (double)n_avg;
+}
+}  // namespace
+
+extern "C" int mkid_noise_spectrum(mkid_ctx *ctx, const double *phase_deg, int32_t n_streams, int64_t n_samples,
+                                   int32_t n_averages, double norm, double *noise_db) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, phase_deg && noise_db && n_streams > 0 && n_averages > 0 && n_samples >= n_averages && norm > 0.0,
+                 "noise_spectrum: bad argument");
+    const int N = (int)(n_samples / n_averages);                   // nSamplesPerFFT (integer division, :522)
+    MKID_REQUIRE(ctx, N >= 1 && (size_t)N * 8 <= 200 * 1024, "noise_spectrum: segment must fit shared memory (<= 25600 samples)");
+    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    const void *d_x; void *d_o, *d_tw;
+    if ((rc = mkid_stage_in(ctx, phase_deg, (size_t)n_streams * n_samples * 8, SCR_IN, &d_x))) return rc;
+    if ((rc = mkid_stage_out(ctx, noise_db, (size_t)n_streams * N * 8, SCR_OUT0, false, &d_o))) return rc;
+    if ((rc = mkid_scratch(ctx, SCR_AUX2, (size_t)N * 16, &d_tw))) return rc;
+    dft_twiddle_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(N, (double2 *)d_tw);
+    MKID_CHECK_LAUNCH(ctx);
+    const size_t smem = (size_t)N * 8;
+    MKID_CUDA(ctx, cudaFuncSetAttribute(noise_spectrum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    noise_spectrum_kernel<<<dim3((N + 127) / 128, n_streams), 128, smem, ctx->stream>>>((const double *)d_x, n_samples, N, n_averages,
+                                                                                      norm, (const double2 *)d_tw, (double *)d_o);
+    MKID_CHECK_LAUNCH(ctx);
+    return mkid_stage_out_finish(ctx, noise_db, (size_t)n_streams * N * 8, d_o);
+}
+
+// ---------------------------------------------------------------- image_Worker spectra products (ArconsDashboard.py:1282-1504)
+// darray u32 [n_pix][10] (the per-pixel 10-bin spectrum K6 accumulates).  Per bin: numpy.median over the pixels
+// (bitonic sort in shared memory), optional sky subtraction x - int(median); pc[p] = sum of the 10 bins;
+// me[p] = (C0*E0 + ... + C9*E9) / pc[p] in the reference's left-to-right float64 order, h*c/me for wavelength bins.
+namespace {
+__global__ void __launch_bounds__(1024) spectra_median_kernel(const uint32_t *__restrict__ darray, int n_pix, int n_pow2,
+                                                              double *medians) {
+    extern __shared__ uint32_t s_v[];
+    const int bin = blockIdx.x, tid = threadIdx.x;
+    for (int i = tid; i < n_pow2; i += 1024) s_v[i] = i < n_pix ? darray[(size_t)i * 10 + bin] : 0xFFFFFFFFu;
+    __syncthreads();
+    for (int k = 2; k <= n_pow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = tid; i < n_pow2; i += 1024) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const uint32_t a = s_v[i], b = s_v[l];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) { s_v[i] = b; s_v[l] = a; }
+                }
+            }
+            __syncthreads();
+        }
+    if (tid == 0) {
+        // numpy.median: mean of the two middle elements for even n
+        const double m = (n_pix & 1) ? (double)s_v[n_pix / 2] : ((double)s_v[n_pix / 2 - 1] + (double)s_v[n_pix / 2]) / 2.0;
+        medians[bin] = m;
+    }
+}
+__global__ void spectra_products_kernel(const uint32_t *__restrict__ darray, int n_pix, const double *__restrict__ medians,
+                                        int sky, const double *__restrict__ E, double hc, int wavelength, long long *pc,
+                                        double *me) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pix) return;
+    long long sum = 0;
+    double num = 0.0;
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        long long cv = (long long)darray[(size_t)p * 10 + i];
+        if (sky) cv -= (long long)medians[i];                       // x - int(meds[i])
+        sum += cv;
+        const double term = __dmul_rn((double)cv, E[i]);
+        num = i == 0 ? term : __dadd_rn(num, term);
+    }
+    pc[p] = sum;
+    double m = __ddiv_rn(num, (double)sum);                          // inf / nan for an empty pixel, as numpy
+    if (wavelength) m = __ddiv_rn(hc, m);
+    me[p] = m;
+}
+}  // namespace
+
+extern "C" int mkid_spectra_products(mkid_ctx *ctx, const uint32_t *darray, int32_t n_pix, const double *bin_centres,
+                                     double hc, int32_t wavelength, int32_t sky_subtraction, double *medians,
+                                     int64_t *pc, double *me) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, darray && bin_centres && medians && pc && me && n_pix > 0, "spectra_products: NULL argument");
+    int n_pow2 = 1;
+    while (n_pow2 < n_pix) n_pow2 <<= 1;
+    MKID_REQUIRE(ctx, (size_t)n_pow2 * 4 <= 200 * 1024, "spectra_products: at most 51200 pixels");
+    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
+    int rc;
+    const void *d_in, *d_E; void *d_med, *d_pc, *d_me;
+    if ((rc = mkid_stage_in(ctx, darray, (size_t)n_pix * 40, SCR_IN, &d_in))) return rc;
+    if ((rc = mkid_stage_in(ctx, bin_centres, 80, SCR_IN1, &d_E))) return rc;
+    if ((rc = mkid_stage_out(ctx, medians, 80, SCR_OUT0, false, &d_med))) return rc;
+    if ((rc = mkid_stage_out(ctx, pc, (size_t)n_pix * 8, SCR_OUT1, false, &d_pc))) return rc;
+    if ((rc = mkid_stage_out(ctx, me, (size_t)n_pix * 8, SCR_OUT2, false, &d_me))) return rc;
+    const size_t smem = (size_t)n_pow2 * 4;
+    MKID_CUDA(ctx, cudaFuncSetAttribute(spectra_median_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    spectra_median_kernel<<<10, 1024, smem, ctx->stream>>>((const uint32_t *)d_in, n_pix, n_pow2, (double *)d_med);
+    MKID_CHECK_LAUNCH(ctx);
+    spectra_products_kernel<<<(n_pix + 255) / 256, 256, 0, ctx->stream>>>((const uint32_t *)d_in, n_pix, (const double *)d_med,
+                                                                         sky_subtraction, (const double *)d_E, hc, wavelength,
+                                                                         (long long *)d_pc, (double *)d_me);
+    MKID_CHECK_LAUNCH(ctx);
+    if ((rc = mkid_stage_out_finish(ctx, medians, 80, d_med))) return rc;
+    if ((rc = mkid_stage_out_finish(ctx, pc, (size_t)n_pix * 8, d_pc))) return rc;
+    return mkid_stage_out_finish(ctx, me, (size_t)n_pix * 8, d_me);
+}

@@ -90,3 +90,19 @@ def thresholds_from_phase(phase_dev, n_boards, rows, n_samples, row0=0, n_ch=256
                                                   float(Nsigma), _lib.ptr(thr), _lib.ptr(med), _lib.ptr(p5)))
     ctx.sync()
     return thr, med, p5
+
+
+def noise_spectrum(qdr_phase_values, nFFTAverages=100, norm1=50.0, ctx=None):
+    """longsnapshot noise spectrum (ROACH_Pulses.py:521-537).  Returns (noiseFFT [dB], noiseFFTFreqs) for a
+    1-D phase stream in degrees, or noiseFFT [streams][nSamplesPerFFT] for a 2-D input."""
+    ctx = ctx or _lib.default_context()
+    x = np.ascontiguousarray(qdr_phase_values, dtype=np.float64)
+    single = x.ndim == 1
+    x2 = x.reshape(1, -1) if single else x
+    s, n = x2.shape
+    nper = n // int(nFFTAverages)
+    out = np.empty((s, nper), np.float64)
+    ctx._check(ctx.lib.mkid_noise_spectrum(ctx.h, _lib.ptr(x2), s, n, int(nFFTAverages), float(norm1), _lib.ptr(out)))
+    ctx.sync()
+    freqs = np.fft.fftfreq(nper)
+    return (out[0], freqs) if single else (out, freqs)

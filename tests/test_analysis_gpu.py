@@ -107,3 +107,46 @@ def test_thresholds_from_device_phase_stream(ctx):
             t0, m0, q0 = control.threshold_from_phase(ph[b, row0:row0 + n, c].astype(np.int64))
             assert (thr[b, c], med[b, c], p5[b, c]) == (t0, m0, q0), (b, c)
     assert thr.min() >= -25736 and (thr < 0).sum() > 400
+
+
+def test_longsnapshot_noise_spectrum(ctx):
+    """ROACH_Pulses.py:521-537 with the reference's sizes: 2^20 samples, 100 averages of 10485-point FFTs."""
+    from mkids_sdr_b200 import triggers
+    rng = np.random.default_rng(4)
+    n = 2 ** 20
+    t = np.arange(n)
+    x = 3.0 * np.sin(2 * np.pi * 0.0123 * t) + rng.normal(0, 2.0, n) + 40.0
+    got, freqs = triggers.noise_spectrum(x, 100, 50.0, ctx=ctx)
+    nper = n // 100
+    ref = np.zeros(nper)
+    for i in range(100):
+        noise = np.abs(np.fft.fft(x[i * nper:(i + 1) * nper]))
+        ref += 20 * (np.log10(noise / 50.0 / 1e-6))
+    ref /= 100
+    assert got.shape == (nper,) and nper == 10485
+    assert np.max(np.abs(got - ref)) < 1e-8                     # dB; float64 DFT vs pocketfft
+    assert np.array_equal(freqs, np.fft.fftfreq(nper))
+
+
+@pytest.mark.parametrize('sky,bintype', [(False, 'wavelength'), (True, 'wavelength'), (True, 'energy')])
+def test_image_worker_spectra_products(ctx, sky, bintype):
+    """ArconsDashboard.py image_Worker: medians, sky subtraction, pc, mean energy, SNR -- bit-exact."""
+    from oracle import spectra as ospec
+    from mkids_sdr_b200.spectra import ImageWorker
+    rng = np.random.default_rng(12)
+    n_pix = 44 * 46
+    darray = rng.poisson(rng.uniform(5, 60, (n_pix, 1)) * np.linspace(1.5, 0.5, 10)[None, :]).astype(np.uint32)
+    darray[7] = 0                                              # an empty pixel
+    iw = ImageWorker(44, 46, ctx=ctx)
+    iw.bintype = bintype
+    iw.setup_thread()
+    iw.sky_subtraction = sky
+    iw.spectrum_pixel = [3, 50, 51, 900, 2001]
+    pc, me = iw.run(ctx.to_device(darray))
+    ref = ospec.image_worker(darray, bintype=bintype, sky_subtraction=sky, spectrum_pixel=iw.spectrum_pixel)
+    assert iw.E == ref['E']
+    assert iw.medians == ref['medians']
+    assert np.array_equal(pc, ref['pc'])
+    ok = np.isfinite(ref['me'])
+    assert np.array_equal(me[ok], ref['me'][ok]) and np.array_equal(np.isnan(me), np.isnan(ref['me']))
+    assert iw.SNR == ref['SNR'] and iw.integrated_SNR == ref['integrated_SNR']
