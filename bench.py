@@ -388,9 +388,10 @@ def decode_side_bench(ctx, peak):
         lo_dev = ctx.alloc((secs * reps * R * npix + 1) * 8)
         import ctypes as _ct
         sec_out = np.zeros(roach.size, dtype=np.int32)
+        roach32 = roach.astype(np.int32)
 
         def run_lists():
-            ctx._check(ctx.lib.mkid_decode_lists(ctx.h, _lib_ptr(dw), words.size, _lib_ptr(offs), _lib_ptr(roach.astype(np.int32)),
+            ctx._check(ctx.lib.mkid_decode_lists(ctx.h, _lib_ptr(dw), words.size, _lib_ptr(offs), _lib_ptr(roach32),
                                                  _lib_ptr(sec0), _lib_ptr(sec_out), roach.size, _ct.byref(dec.cfg),
                                                  _lib_ptr(dec.counts_dev), _lib_ptr(lw_dev), words.size, _lib_ptr(lo_dev), None))
         run_lists()

@@ -301,6 +301,26 @@ int mkid_noise_spectrum(mkid_ctx *ctx, const double *phase_deg, int32_t n_stream
 int mkid_spectra_products(mkid_ctx *ctx, const uint32_t *darray, int32_t n_pix, const double *bin_centres, double hc,
                           int32_t wavelength, int32_t sky_subtraction, double *medians, int64_t *pc, double *me);
 
+/* Matched-filter template builder: the per-pulse arithmetic of MakeTemplate
+ * (DataReadout/ReadoutControls/lib/pulses.py:239-427) batched over the pulses of one resonator.  The iqpulses table
+ * is two float32 arrays I, Q [n_pulses][2000] in DEVICE memory; the accept / reject comparisons on the per-pulse
+ * scalars stay with the caller (mkids_sdr_b200/template.py), exactly as in the reference loop.
+ *   mkid_tpl_median      numpy.median(table[:rows, :cols]) in float32 (:273-274)
+ *   mkid_tpl_prepare     per pulse: I += I1m - median(I[1:900]) IN PLACE (:283-284), P1 = arctan2(Q, I), P2 =
+ *                        rad2deg(unwrap(P1)) (float32), P3 = P2 - straight-line fit over samples [0,900)+[1800,2000)
+ *                        (float64, :294-295) -> P3 [n_pulses][2000]; stats [n_pulses][6]: mean(P3[:100]),
+ *                        mean(P3[1900:]), std(P3[:100]), max(P3[980:1050]), max(P3), and (as two int32 in the 6th
+ *                        double) the first index with P3 == that peak
+ *   mkid_tpl_convpeak    argmax[j] = first arg-max of numpy.convolve(kernel600, P3[j]); p3_at[j] = P3[j][1000 + argmax - 1160]
+ *   mkid_tpl_accumulate  tmpl[t] += sum, in list order, of P3[pulse[i]][(t - shift[i]) mod 2000] / norm[i]
+ *                        (tP += roll(P3, shift)/max(P3), :319-320, :371-372); if noise != NULL also
+ *                        noise[k] += |fft(deg2rad(roll(P3, shift)[50:850]))[k]|^2 (:376) */
+int mkid_tpl_median(mkid_ctx *ctx, const float *table, int32_t rows, int32_t cols, int64_t row_stride, float *out);
+int mkid_tpl_prepare(mkid_ctx *ctx, float *I, float *Q, int32_t n_pulses, float I1m, float Q1m, double *P3, double *stats);
+int mkid_tpl_convpeak(mkid_ctx *ctx, const double *P3, int32_t n_pulses, const double *kernel600, int32_t *argmax, double *p3_at);
+int mkid_tpl_accumulate(mkid_ctx *ctx, const double *P3, const int32_t *pulse, const int32_t *shift, const double *norm,
+                        int32_t n_list, double *tmpl, double *noise);
+
 /* ------------------------------------------------------------------ LUT synthesis (K1-K3)
  * mkid_comb_lut replaces AppForm.freqCombLUT (ChannelizerControls/ROACH_Setup.py:416-475; twin with GUI
  * offset/scale options ROACH_Setup_DAC.py:396-455): I[t] = sum a_n cos(2 pi f_n (t+offset)/fs + phi_n),

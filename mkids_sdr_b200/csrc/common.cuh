@@ -28,6 +28,7 @@ struct mkid_ctx {
     std::vector<char> dec_ranges_host, dec_key;
     // device buffers that hold the cached tables: private to the decode path (scratch slots are shared)
     void *dec_priv[2] = {};
+    cudaEvent_t dbg_events[8] = {};     // MKID_DEC_TIMING switch
     size_t dec_priv_bytes[2] = {};
     void *dec_ranges_dev = nullptr;
     size_t l2_flush_bytes = 0;

@@ -64,7 +64,7 @@ struct DecParams {
     uint32_t *rows;            // [n_ranges][DEC_MAX_LS][DEC_ROW]
     int32_t *base;             // [n_ranges] absolute second at the start of each range (commit -> absolute pass)
     int *flag;                 // != 0: some range needs the absolute pass
-    int n_pix, npix_per_roach, exptime, n_bins, field_shift, map_mode;
+    int n_pix, npix_per_roach, exptime, n_bins, field_shift;
     const uint16_t *bin_lut;
     uint32_t *counts;          // [exptime][n_pix]
     uint32_t *hist;            // [n_pix][n_bins] or nullptr
@@ -368,7 +368,6 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_stream_ke
     __syncthreads();
 
     int r = blockIdx.x * DEC_WARPS + warp;
-    if (p.map_mode == 1 && HIST != 2) r = warp * gridDim.x + blockIdx.x;      // (experiment: warps of a CTA far apart)
     const int cta_roach = blockIdx.x * DEC_WARPS < p.n_ranges ? p.ranges[blockIdx.x * DEC_WARPS].roach : -1;
     RangeDecoder<WIRE, HIST, NEED_LO, ABS> d(p);
     d.cnt = s_cnt[warp]; d.cnt_s = mk_smem_u32(s_cnt[warp]); d.hist_s = mk_smem_u32(s_hist); d.s_lut = s_lut; d.lane = lane;
@@ -837,30 +836,29 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
     const bool same_table = key == ctx->dec_key;
     std::vector<DecRange> ranges;
     if (!same_table) {
-    const int64_t warps_total = (int64_t)ctx->num_sms * DEC_CTAS_PER_SM * DEC_WARPS;
-    for (int i = 0; i < n_seg; ++i) {
-        const int64_t nc = seg_chunks[i];
-        if (nc == 0) continue;
-        int64_t pieces = (int64_t)((double)nc * (double)warps_total / (double)n_chunks);        // floor: total <= warps_total
-        pieces = std::max<int64_t>(1, std::min<int64_t>(pieces, nc / min_units));
-        for (int64_t q = 0; q < pieces; ++q) {
-            const int64_t c0 = nc * q / pieces, c1 = nc * (q + 1) / pieces;
-            if (c1 <= c0) continue;
-            DecRange r;
-            if (wire_fmt) { r.start = seg_offset[i] * 2 + c0; r.n_words = (int)((c1 - c0) * DEC_CHUNK); }
-            else { r.start = seg_offset[i] + c0 * DEC_UNIT; r.n_words = (int)std::min<int64_t>((c1 - c0) * DEC_UNIT, seg_len[i] - c0 * DEC_UNIT); }
-            r.roach = seg_roach[i]; r.seg = i; r.seg_first = 0; r.pad = 0;
-            r.seg_off = (int)(c0 * unit_words);
-            ranges.push_back(r);
+        const int64_t warps_total = (int64_t)ctx->num_sms * DEC_CTAS_PER_SM * DEC_WARPS;
+        for (int i = 0; i < n_seg; ++i) {
+            const int64_t nc = seg_chunks[i];
+            if (nc == 0) continue;
+            int64_t pieces = (int64_t)((double)nc * (double)warps_total / (double)n_chunks);        // floor: total <= warps_total
+            pieces = std::max<int64_t>(1, std::min<int64_t>(pieces, nc / min_units));
+            for (int64_t q = 0; q < pieces; ++q) {
+                const int64_t c0 = nc * q / pieces, c1 = nc * (q + 1) / pieces;
+                if (c1 <= c0) continue;
+                DecRange r;
+                if (wire_fmt) { r.start = seg_offset[i] * 2 + c0; r.n_words = (int)((c1 - c0) * DEC_CHUNK); }
+                else { r.start = seg_offset[i] + c0 * DEC_UNIT; r.n_words = (int)std::min<int64_t>((c1 - c0) * DEC_UNIT, seg_len[i] - c0 * DEC_UNIT); }
+                r.roach = seg_roach[i]; r.seg = i; r.seg_first = 0; r.pad = 0;
+                r.seg_off = (int)(c0 * unit_words);
+                ranges.push_back(r);
+            }
         }
-    }
-    // ranges of one roach next to each other (segments stay contiguous and in order): the 16 warps of a CTA then
-    // share one shared-memory histogram
-    static const bool no_sort = getenv("MKID_DEC_NOSORT") != nullptr;      // (experiment switch)
-    if (!no_sort || lists) std::stable_sort(ranges.begin(), ranges.end(), [](const DecRange &a, const DecRange &b) { return a.roach < b.roach; });
-    for (int k = 0; k < (int)ranges.size(); ++k) ranges[k].seg_first = (k > 0 && ranges[k - 1].seg == ranges[k].seg) ? ranges[k - 1].seg_first : k;
-    MKID_REQUIRE(ctx, ranges.size() <= (size_t)1 << 18, "decode: too many segments in one call");
-    for (const DecRange &r : ranges) MKID_REQUIRE(ctx, (int64_t)r.n_words <= (int64_t)1 << 30, "decode: range too long");
+        // ranges of one roach next to each other (segments stay contiguous and in order): the 16 warps of a CTA then
+        // share one shared-memory histogram
+        std::stable_sort(ranges.begin(), ranges.end(), [](const DecRange &a, const DecRange &b) { return a.roach < b.roach; });
+        for (int k = 0; k < (int)ranges.size(); ++k) ranges[k].seg_first = (k > 0 && ranges[k - 1].seg == ranges[k].seg) ? ranges[k - 1].seg_first : k;
+        MKID_REQUIRE(ctx, ranges.size() <= (size_t)1 << 18, "decode: too many segments in one call");
+        for (const DecRange &r : ranges) MKID_REQUIRE(ctx, (int64_t)r.n_words <= (int64_t)1 << 30, "decode: range too long");
 
         ctx->dec_ranges_host.assign((const char *)ranges.data(), (const char *)ranges.data() + ranges.size() * sizeof(DecRange));
         ctx->dec_ranges_dev = nullptr;          // forces the upload below
@@ -931,8 +929,6 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
         p.field_shift = want_hist ? cfg->hist_field_shift : 0; p.n_bins = want_hist ? cfg->n_bins : 0;
         p.bin_lut = (const uint16_t *)d_lut; p.counts = (uint32_t *)d_counts; p.hist = (uint32_t *)d_hist;
         p.stats = d_stats;
-        static const int map_mode = getenv("MKID_DEC_MAP") ? atoi(getenv("MKID_DEC_MAP")) : 0;
-        p.map_mode = map_mode;
 
         const bool smem_hist = want_hist && (int64_t)cfg->npix_per_roach * cfg->n_bins <= DEC_SMEM_HIST;
         const int grid = (int)std::min<int64_t>((n_ranges + DEC_WARPS - 1) / DEC_WARPS, (int64_t)ctx->num_sms * DEC_CTAS_PER_SM);
@@ -954,7 +950,7 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
         };
         // MKID_DEC_TIMING=1: per-kernel device times on stderr (CUDA events; synchronises)
         static const bool timing = getenv("MKID_DEC_TIMING") != nullptr;
-        static cudaEvent_t ev[4] = {};
+        cudaEvent_t *ev = ctx->dbg_events;
         auto mark = [&](int i) {
             if (!timing) return;
             if (!ev[i]) cudaEventCreate(&ev[i]);
@@ -1006,7 +1002,7 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
             lp.rows = d_rows; lp.acc = d_acc; lp.offsets = (long long *)d_lo; lp.out = (uint64_t *)d_lw; lp.out_cap = lists->list_cap;
             lp.n_ranges = n_ranges; lp.n_roaches = cfg->n_roaches; lp.n_pix = (int)n_pix; lp.npix_per_roach = cfg->npix_per_roach;
             lp.exptime = cfg->exptime; lp.cap = cfg->max_events - 1; lp.flag = d_flag;
-            static cudaEvent_t lev[4] = {};
+            cudaEvent_t *lev = ctx->dbg_events + 4;
             auto lmark = [&](int i) { if (!timing) return; if (!lev[i]) cudaEventCreate(&lev[i]); cudaEventRecord(lev[i], ctx->stream); };
             lmark(0);
             list_rowstart_kernel<<<cfg->n_roaches, 256, 0, ctx->stream>>>(lp);
