@@ -45,38 +45,69 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """SM clock / throttle reasons while the timed region runs: NVML every 5 ms (nvidia-smi, ~10 Hz, as fallback)."""
+
+    REASONS = {0x4: 'sw_power_cap', 0x8: 'hw_slowdown', 0x20: 'sw_thermal_slowdown', 0x40: 'hw_thermal_slowdown',
+               0x80: 'hw_power_brake_slowdown'}
 
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag = index, [], False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices: honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES', '')
+            phys = index
+            if vis and all(v.strip().isdigit() for v in vis.split(',')):
+                ids = [int(v) for v in vis.split(',')]
+                phys = ids[index] if index < len(ids) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_sm = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
 
     def run(self):
-        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-             'clocks_event_reasons.sw_power_cap')
+        if self.nvml is not None:
+            nv = self.nvml
+            while not self.stop_flag:
+                try:
+                    sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                    try:
+                        mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    except Exception:
+                        mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    self.rows.append((sm, self.max_sm, mask))
+                except Exception:
+                    pass
+                time.sleep(0.005)
+            return
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.sw_power_cap,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.hw_thermal_slowdown')
+        bits = [0x4, 0x8, 0x20, 0x40]
         while not self.stop_flag:
             try:
                 out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
                                       '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
-                self.rows.append([x.strip() for x in out.strip().split(',')])
+                r = [x.strip() for x in out.strip().split(',')]
+                mask = sum(b for b, v in zip(bits, r[2:6]) if v.lower().startswith('active'))
+                self.rows.append((float(r[0]), float(r[1]), mask))
             except Exception:
                 pass
             time.sleep(0.1)
 
     def summary(self):
-        sm, mx, reasons = [], 0, set()
-        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        sm = [r[0] for r in self.rows]
+        mx = max([r[1] for r in self.rows], default=0)
+        reasons = set()
         for r in self.rows:
-            try:
-                sm.append(float(r[0])); mx = max(mx, float(r[1]))
-                for nme, v in zip(names, r[3:7]):
-                    if v.lower().startswith('active'):
-                        reasons.add(nme)
-            except Exception:
-                continue
+            for bit, name in self.REASONS.items():
+                if r[2] & bit:
+                    reasons.add(name)
         return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': mx or None, 'reasons': sorted(reasons),
-                'samples': len(sm)}
+                'samples': len(sm), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
 # ------------------------------------------------------------------ CPU reference arm (oracle port)
@@ -120,8 +151,8 @@ def cpu_reference_rate(iq_boards, cfgs, n_samples_each, cores):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
-    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=100)
+    ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--log2-samples', type=int, default=25, help='ADC samples per board per step (log2)')
     ap.add_argument('--hist-bins', type=int, default=64)
@@ -174,7 +205,12 @@ def main():
     cores = len(os.sched_getaffinity(0))
 
     if args.impl == 'reference':
-        n_each = 1 << 21
+        # bounded sample per step: ~1.1 s of CPU work at 2^21 samples per core; shrink it when many steps are asked
+        # for so that the whole run stays within about two minutes
+        log2_each = 21
+        while log2_each > 17 and 1.2 * 2.0 ** (log2_each - 21) * (args.warmup + args.steps) > 120.0:
+            log2_each -= 1
+        n_each = 1 << log2_each
         iq_host = [iq_dev[b, :n_each].cpu().numpy() for b in range(min(B, cores))]
         vals = []
         for it in range(args.warmup + args.steps):
