@@ -167,6 +167,10 @@ def main():
     if args.impl == 'reference' and rank != 0:
         return 0
 
+    def stage(msg):
+        if os.environ.get('MKID_BENCH_VERBOSE'):
+            sys.stderr.write('[bench rank %d +%.1fs] %s\n' % (rank, time.time() - t_start, msg)); sys.stderr.flush()
+    t_start = time.time()
     import torch
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device: the product path has no CPU fallback')
@@ -176,6 +180,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
 
+    stage('process group up')
     from mkids_sdr_b200 import _lib
     from mkids_sdr_b200.chain import ReadoutChain
     from mkids_sdr_b200.channelizer import synth_adc
@@ -192,7 +197,9 @@ def main():
     chain, boards = ReadoutChain.synthetic(B, N_LUT, N_ACTIVE, seed0=42 + 8 * rank, ctx=ctx, exptime=exptime,
                                            n_roaches_total=n_roaches_total, roach0=B * rank, n_bins=args.hist_bins,
                                            counts_buf=counts_t, hist_buf=hist_t)
+    stage('chain configured')
     thr = chain.derive_thresholds(boards)
+    stage('thresholds derived')
     tone_bins = np.stack([bd['tone_bins'] for bd in boards])
 
     # synthetic ADC streams, generated on the GPU, resident in HBM (1 GiB per GPU at the default size)
@@ -249,6 +256,7 @@ def main():
         chain.sync_state()
         return chain.chan.kernel_ms_sum(min(k, 64)) * (k / min(k, 64))
 
+    stage('input synthesised')
     # ---------------------------------------------------------------- device-resident value
     run_steps(args.warmup, iq_dev)
     reduce_products()
@@ -274,6 +282,7 @@ def main():
     step_ms = max(dev_ms, wall_ms) / args.steps
     value = world * B * n / (step_ms * 1e-3) / 1e6
 
+    stage('device-resident steps done')
     # ---------------------------------------------------------------- end to end with host buffers
     pin_iq = torch.empty((B, n, 2), dtype=torch.int16).pin_memory()
     pin_iq.copy_(iq_dev.cpu())
@@ -475,4 +484,11 @@ def lut_side_bench(ctx):
 
 
 if __name__ == '__main__':
-    sys.exit(main())
+    try:
+        rc = main()
+    except BaseException:
+        import traceback
+        sys.stderr.write('[bench rank %s] failed:\n%s\n' % (os.environ.get('RANK', '0'), traceback.format_exc()))
+        sys.stderr.flush()
+        raise
+    sys.exit(rc)
