@@ -167,6 +167,14 @@ def main():
     if args.impl == 'reference' and rank != 0:
         return 0
 
+    # exactly ONE line goes to stdout (the JSON): libraries that write there (NCCL's version banner) land on stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(json_fd, (json.dumps(line) + '\n').encode())
+
     def stage(msg):
         if os.environ.get('MKID_BENCH_VERBOSE'):
             sys.stderr.write('[bench rank %d +%.1fs] %s\n' % (rank, time.time() - t_start, msg)); sys.stderr.flush()
@@ -232,7 +240,7 @@ def main():
                            'sample': desc},
                 'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
                 'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     def barrier():
@@ -364,7 +372,7 @@ def main():
         iq_host = [iq_dev[b, :n_each].cpu().numpy() for b in range(min(B, cores))]
         v, dt, desc = cpu_reference_rate(iq_host, cfgs_cpu, n_each, cores)
         line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc, 'seconds': dt}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0
