@@ -56,6 +56,13 @@ int  mkid_dev_alloc(mkid_ctx *ctx, size_t bytes, void **out);
 int  mkid_dev_free(mkid_ctx *ctx, void *p);
 int  mkid_memcpy(mkid_ctx *ctx, void *dst, const void *src, size_t bytes);   /* async on the stream */
 int  mkid_memset(mkid_ctx *ctx, void *dst, int value, size_t bytes);
+/* double-buffered host -> device uploads on a second stream, so that the copy of batch k+1 overlaps the processing of
+ * batch k: upload_async copies (pinned) host memory into a device buffer tagged with `slot` (0..3), upload_wait makes the
+ * context stream wait for that copy (asynchronously), upload_consumed marks the point of the context stream after which
+ * the buffer of `slot` may be overwritten by the next upload_async */
+int  mkid_upload_async(mkid_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, int slot);
+int  mkid_upload_wait(mkid_ctx *ctx, int slot);
+int  mkid_upload_consumed(mkid_ctx *ctx, int slot);
 /* writes > L2-size scratch so the next timed kernel starts with a cold L2 */
 int  mkid_flush_l2(mkid_ctx *ctx);
 const char *mkid_version(void);

@@ -67,6 +67,9 @@ _SIGNATURES = {
     'mkid_memcpy': (c_int32, [c_void_p, c_void_p, c_void_p, c_size_t]),
     'mkid_memset': (c_int32, [c_void_p, c_void_p, c_int32, c_size_t]),
     'mkid_flush_l2': (c_int32, [c_void_p]),
+    'mkid_upload_async': (c_int32, [c_void_p, c_void_p, c_void_p, c_size_t, c_int32]),
+    'mkid_upload_wait': (c_int32, [c_void_p, c_int32]),
+    'mkid_upload_consumed': (c_int32, [c_void_p, c_int32]),
     'mkid_decode_words': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                     POINTER(DecodeCfg), c_void_p, c_void_p, c_void_p]),
     'mkid_decode_words_seg': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
@@ -261,6 +264,16 @@ class Context:
         ms = c_float()
         self._check(self.lib.mkid_event_elapsed_ms(self.h, a, b, ctypes.byref(ms)))
         return float(ms.value)
+
+    def upload_async(self, dst_dev, src_host, nbytes, slot):
+        """Host -> device copy on the copy stream (overlaps the context stream); see upload_wait / upload_consumed."""
+        self._check(self.lib.mkid_upload_async(self.h, ptr(dst_dev), ptr(src_host), int(nbytes), int(slot)))
+
+    def upload_wait(self, slot):
+        self._check(self.lib.mkid_upload_wait(self.h, int(slot)))
+
+    def upload_consumed(self, slot):
+        self._check(self.lib.mkid_upload_consumed(self.h, int(slot)))
 
     def flush_l2(self):
         self._check(self.lib.mkid_flush_l2(self.h))

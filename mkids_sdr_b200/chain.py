@@ -105,6 +105,43 @@ class ReadoutChain:
                                   self._sec_dev[1 - self._sec_cur], self.n_boards * self._cap)
         self._sec_cur = 1 - self._sec_cur
 
+    def process_stream(self, batches, n, words_host=None, counts_host=None):
+        """Pipelined end-to-end path for a stream of HOST batches (pinned int16 [n_boards][n][2] arrays): the upload
+        of batch k+1 (second stream, double buffered) overlaps the processing of batch k.  After every batch the
+        photon words (whole per-board capacity, words_host u64 [n_boards][cap]), the per-(second,pixel) counts
+        (counts_host) and the word counts are copied back; yields the word counts of each batch."""
+        c = self.ctx
+        nbytes = self.n_boards * n * 4
+        if getattr(self, '_iq_dev', None) is None or self._iq_dev[0].nbytes < nbytes:
+            self._iq_dev = [c.alloc(nbytes), c.alloc(nbytes)]
+        cap = self.chan.words_capacity(n)
+        nw_host = np.zeros(self.n_boards, dtype=np.int32)
+        it = iter(batches)
+        nxt = next(it, None)
+        k = 0
+        if nxt is not None:
+            c.upload_async(self._iq_dev[0], nxt, nbytes, 0)
+        while nxt is not None:
+            cur = k & 1
+            nxt = next(it, None)
+            if nxt is not None:
+                c.upload_async(self._iq_dev[cur ^ 1], nxt, nbytes, cur ^ 1)      # waits for that buffer's consumer
+            c.upload_wait(cur)
+            self.process_async(self._iq_dev[cur], n=n)
+            c.upload_consumed(cur)
+            c._check(c.lib.mkid_memcpy(c.h, _lib.ptr(nw_host), self.chan.n_words_dev(), nw_host.nbytes))
+            if words_host is not None:
+                for b in range(self.n_boards):
+                    c._check(c.lib.mkid_memcpy(c.h, _lib.ptr(words_host[b]), self._words_dev.ptr + b * self._cap * 8,
+                                               min(cap, words_host.shape[1]) * 8))
+            if counts_host is not None:
+                c._check(c.lib.mkid_memcpy(c.h, _lib.ptr(counts_host), _lib.ptr(self.dec.counts_dev),
+                                           self.dec.exptime * self.dec.n_pix * 4))
+            c.sync()
+            k += 1
+            yield nw_host.copy()
+        self.sync_state()
+
     def sync_state(self):
         """After process_async calls: returns the word counts of the last batch, refreshes self.sec."""
         c = self.ctx

@@ -55,6 +55,8 @@ extern "C" void mkid_destroy(mkid_ctx *ctx) {
     for (int i = 0; i < 2; ++i) if (ctx->dec_priv[i]) cudaFree(ctx->dec_priv[i]);
     for (int i = 0; i < MKID_NUM_EVENTS; ++i) if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
     for (int i = 0; i < 8; ++i) if (ctx->dbg_events[i]) cudaEventDestroy(ctx->dbg_events[i]);
+    for (int i = 0; i < 4; ++i) { if (ctx->up_done[i]) cudaEventDestroy(ctx->up_done[i]); if (ctx->up_free[i]) cudaEventDestroy(ctx->up_free[i]); }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -96,6 +98,35 @@ extern "C" int mkid_dev_alloc(mkid_ctx *ctx, size_t bytes, void **out) {
 extern "C" int mkid_dev_free(mkid_ctx *ctx, void *p) { MKID_CUDA(ctx, cudaFree(p)); return MKID_OK; }
 extern "C" int mkid_memcpy(mkid_ctx *ctx, void *dst, const void *src, size_t bytes) {
     MKID_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, ctx->stream));
+    return MKID_OK;
+}
+// Double-buffered uploads on a second stream: the copy of batch k+1 runs while batch k is processed.
+extern "C" int mkid_upload_async(mkid_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes, int slot) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, dst_dev && src_host && slot >= 0 && slot < 4 && mkid_is_device_ptr(dst_dev), "upload_async: bad argument");
+    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->copy_stream) MKID_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    if (!ctx->up_done[slot]) {
+        MKID_CUDA(ctx, cudaEventCreateWithFlags(&ctx->up_done[slot], cudaEventDisableTiming));
+        MKID_CUDA(ctx, cudaEventCreateWithFlags(&ctx->up_free[slot], cudaEventDisableTiming));
+    }
+    // the previous consumer of this slot (mkid_upload_consumed) must be done before the buffer is overwritten
+    if (ctx->up_free_valid[slot]) MKID_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->up_free[slot], 0));
+    MKID_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+    MKID_CUDA(ctx, cudaEventRecord(ctx->up_done[slot], ctx->copy_stream));
+    return MKID_OK;
+}
+extern "C" int mkid_upload_wait(mkid_ctx *ctx, int slot) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, slot >= 0 && slot < 4 && ctx->up_done[slot], "upload_wait: no upload in this slot");
+    MKID_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->up_done[slot], 0));      // asynchronous: orders the context stream
+    return MKID_OK;
+}
+extern "C" int mkid_upload_consumed(mkid_ctx *ctx, int slot) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, slot >= 0 && slot < 4 && ctx->up_free[slot], "upload_consumed: no upload in this slot");
+    MKID_CUDA(ctx, cudaEventRecord(ctx->up_free[slot], ctx->stream));
+    ctx->up_free_valid[slot] = true;
     return MKID_OK;
 }
 extern "C" int mkid_memset(mkid_ctx *ctx, void *dst, int value, size_t bytes) {

@@ -29,6 +29,10 @@ struct mkid_ctx {
     // device buffers that hold the cached tables: private to the decode path (scratch slots are shared)
     void *dec_priv[2] = {};
     cudaEvent_t dbg_events[8] = {};     // MKID_DEC_TIMING switch
+    // double-buffered host -> device uploads that overlap the compute stream (mkid_upload_async)
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t up_done[4] = {}, up_free[4] = {};
+    bool up_free_valid[4] = {};
     size_t dec_priv_bytes[2] = {};
     void *dec_ranges_dev = nullptr;
     size_t l2_flush_bytes = 0;
