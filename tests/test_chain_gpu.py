@@ -159,3 +159,27 @@ def test_process_stream_equals_process(ctx):
             assert np.array_equal(res[0][0][k][b], res[1][0][k][b])
     assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
     assert sum(len(w) for w in res[0][0][0]) > 20
+
+
+def test_stress_config_shapes(ctx):
+    """BASELINE config 4 (20 000 resonators over 10 feedlines = 80 board streams of 250 channels, per-pixel 4096-bin
+    histograms [20 000][4096]): one GPU's share of an 8-GPU run (10 boards, roach ids 30..39) at a short batch, checked
+    through checksums: histogram row sums == per-pixel counts == words emitted, nothing outside this rank's pixels."""
+    from mkids_sdr_b200.chain import ReadoutChain
+    from mkids_sdr_b200.channelizer import synth_adc
+    B, n_lut, n, R_total, npix = 10, 2 ** 16, 2 ** 21, 80, 250
+    chain, boards = ReadoutChain.synthetic(B, n_lut, npix, seed0=130, threshold=-2600, ctx=ctx, exptime=2, npix_per_roach=npix,
+                                           n_roaches_total=R_total, roach0=30, hist_field='peak', n_bins=4096)
+    tb = np.stack([bd['tone_bins'] for bd in boards])
+    iq = ctx.alloc(B * n * 4)
+    synth_adc(B, n, tb, n_lut=n_lut, pulse_rate=3000.0, seed=77, out=iq, ctx=ctx)
+    for _ in range(2):
+        chain.process_async(iq, n=n)
+    nw = chain.sync_state()
+    counts, hist = chain.dec.counts_raw(), chain.dec.hist()
+    assert hist.shape == (R_total * npix, 4096) and counts.shape == (2, R_total * npix)
+    per_pix = counts.sum(axis=0)
+    assert np.array_equal(hist.sum(axis=1), per_pix)
+    assert per_pix[:30 * npix].sum() == 0 and per_pix[40 * npix:].sum() == 0
+    assert per_pix[30 * npix:40 * npix].sum() > 1000
+    iq.free()
