@@ -323,6 +323,12 @@ def main():
     if rank == 0:
         sampler.stop_flag = True
 
+    decode_sharded = None
+    if dist is not None and not args.no_extras:
+        try:
+            decode_sharded = decode_sharded_bench(ctx, torch, dist, rank, world, measured_peaks()[0])
+        except Exception as e:      # side measurement only
+            decode_sharded = {'error': str(e)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -359,6 +365,8 @@ def main():
             'photon_words_per_step': words_per_step,
             'clocks': sampler.summary()}
 
+    if decode_sharded is not None:
+        line['decode_sharded'] = decode_sharded
     if not args.no_extras:
         try:
             line['decode'] = decode_side_bench(ctx, peak)
@@ -378,6 +386,52 @@ def main():
     if dist is not None:
         dist.destroy_process_group()
     return 0
+
+
+def decode_sharded_bench(ctx, torch, dist, rank, world, peak):
+    """The second sharding mode of SURVEY 8e: a photon file set is split by packet-file chunk across the GPUs (every
+    rank decodes its own replicas of the 8-roach file, 1.28 GB per GPU resident in HBM: weak scaling), then ONE NCCL
+    sum-reduce of the per-pixel products (counts [10][2024] + 10-bin spectra [2024][10]).  Whole-job words/s, device
+    events, max over ranks."""
+    from mkids_sdr_b200 import synth
+    from mkids_sdr_b200.decode import PhotonDecoder
+    R, npix, secs, reps = 8, 253, 10, 16
+    streams, _ = synth.photon_streams(10 ** 7, R, npix, secs, seed=1234 + rank)
+    lens = [len(s) for s in streams]
+    words = np.tile(np.concatenate(streams), reps)
+    offs = np.concatenate([[0], np.cumsum(lens * reps)]).astype(np.int64)
+    roach = np.tile(np.arange(R), reps)
+    dw = ctx.to_device(words)
+    counts_t = torch.zeros(secs * R * npix, dtype=torch.int32, device='cuda')
+    hist_t = torch.zeros(R * npix * 10, dtype=torch.int32, device='cuda')
+    lut = np.arange(4096) * 10 // 4096
+    dec = PhotonDecoder(R, npix, secs, 2500, 'p1', 10, lut, ctx=ctx, counts_buf=counts_t, hist_buf=hist_t)
+
+    def one_pass():
+        dec.reset()                              # every pass is one complete job: partial products, then the reduce
+        dec.decode_words(dw, offs, roach, want_stats=False, want_sec=False)
+        ctx.sync()
+        dist.all_reduce(hist_t)
+        dist.all_reduce(counts_t)
+    for _ in range(3):
+        one_pass()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    k = 10
+    t0 = time.time()
+    for _ in range(k):
+        one_pass()
+    torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
+    el = torch.tensor([(time.time() - t0) * 1e3 / k], dtype=torch.float64, device='cuda')
+    dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    ms = float(el[0])
+    total = words.size * world
+    total_hist = int(hist_t.sum().item())
+    dw.free()
+    gbs = total * 8 / ms / 1e6
+    return {'words_per_s': total / ms * 1e3, 'GB/s': gbs, 'frac_hbm_per_gpu': gbs / world / peak, 'ms_per_pass': ms, 'n_gpus': world,
+            'collective': 'NCCL all_reduce(sum) of counts [10][2024] and spectra [2024][10] after every pass',
+            'checksum_spectra': total_hist, 'checksum_expected': int(10 ** 7 * reps * world),
+            'workload': '16 x 1e7 photon words per GPU (different seeds), decode + per-pixel counts + 10-bin spectra'}
 
 
 def decode_side_bench(ctx, peak):
