@@ -1,4 +1,7 @@
-"""Oracle: per-pixel spectra products of the dashboard's image_Worker (TEST INFRASTRUCTURE).
+"""PARITY UNPINNED: ArconsDashboard.py imports PyQt4 at module level and cannot be imported here; the reference holds no data.bin fixture.
+This file is a line-by-line restatement and is itself the parity definition for this stage.
+
+Oracle: per-pixel spectra products of the dashboard's image_Worker (TEST INFRASTRUCTURE).
 
 Restates DataReadout/ReadoutControls/ArconsDashboard.py:1282-1504 without Qt / files:
   * bin centres E0..E9              setup_thread :1299-1322

@@ -1,4 +1,7 @@
-"""Oracle: matched-filter template builder (TEST INFRASTRUCTURE).
+"""PARITY UNPINNED: lib/pulses.py imports PyTables (absent) at module level and cannot be imported here; the reference holds no iqpulses fixture.
+This file is a line-by-line restatement and is itself the parity definition for this stage.
+
+Oracle: matched-filter template builder (TEST INFRASTRUCTURE).
 
 Literal restatement of MakeTemplate, DataReadout/ReadoutControls/lib/pulses.py:239-427, without PyTables /
 matplotlib: the `iqpulses` table is passed in as two float32 arrays I, Q [n_pulses][2000] (2 us per sample).
