@@ -1,5 +1,6 @@
-"""PARITY UNPINNED: ArconsDashboard.py imports PyQt4 at module level and cannot be imported here; the reference holds no data.bin fixture.
-This file is a line-by-line restatement and is itself the parity definition for this stage.
+"""PINNED: bit-identical to the outputs of the reference's own image_Worker methods (ArconsDashboard.py:1282-1384), executed
+in the dev container by tests/golden/make_golden_analysis.py -> tests/golden/analysis_golden.npz
+(tests/test_oracle_golden.py::test_spectra_oracle_matches_reference_run).
 
 Oracle: per-pixel spectra products of the dashboard's image_Worker (TEST INFRASTRUCTURE).
 

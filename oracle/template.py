@@ -1,5 +1,6 @@
-"""PARITY UNPINNED: lib/pulses.py imports PyTables (absent) at module level and cannot be imported here; the reference holds no iqpulses fixture.
-This file is a line-by-line restatement and is itself the parity definition for this stage.
+"""PINNED: bit-identical to the outputs of the reference's own MakeTemplate (lib/pulses.py:239-427), executed in the dev
+container by tests/golden/make_golden_analysis.py on the same synthetic iqpulses table -> tests/golden/analysis_golden.npz
+(tests/test_oracle_golden.py::test_template_oracle_matches_reference_run).
 
 Oracle: matched-filter template builder (TEST INFRASTRUCTURE).
 

@@ -257,3 +257,40 @@ def test_read_pulses_wrap_and_hist():
     base_raw = ((w[sel] >> np.uint64(20)) & np.uint64(0xFFF)).astype(np.int64)
     h = np.bincount(lutb[base_raw][lutb[base_raw] < 40], minlength=40)
     assert np.array_equal(h, out['hgBase'])
+
+
+def test_template_oracle_matches_reference_run(golden_dir):
+    """oracle/template.py against the outputs of the reference's own MakeTemplate (lib/pulses.py:239-427), executed
+    in the dev container by tests/golden/make_golden_analysis.py on the same synthetic iqpulses table."""
+    import hashlib
+    from oracle import template as otpl
+    g = np.load(os.path.join(golden_dir, 'analysis_golden.npz'))
+    n, seed = (int(v) for v in g['tpl_params'])
+    I, Q = otpl.fake_pulses(n, seed=seed)
+    assert hashlib.sha256(I.tobytes() + Q.tobytes()).hexdigest() == str(g['tpl_input_sha256'])
+    r = otpl.make_template(I, Q)
+    assert r['count'] == float(g['tpl_count']) and r['flag'] == int(g['tpl_flag']) and r['pstart'] == int(g['tpl_pstart'][0])
+    assert np.array_equal(r['tPf'], g['tpl_phasetemplate'])
+    assert np.array_equal(r['noise'], g['tpl_phasenoise'])
+    assert np.array_equal(r['noiseidx'], g['tpl_phasenoiseidx'])
+    assert hashlib.sha256(I.tobytes() + Q.tobytes()).hexdigest() == str(g['tpl_shifted_rows_sha256'])   # in-place shifts
+
+
+def test_spectra_oracle_matches_reference_run(golden_dir):
+    """oracle/spectra.py against the reference's own image_Worker methods (ArconsDashboard.py:1282-1384)."""
+    from oracle import spectra as ospec
+    g = np.load(os.path.join(golden_dir, 'analysis_golden.npz'))
+    darray = g['iw_darray'].astype(np.int64)
+    sel = [int(v) for v in g['iw_spectrum_pixel']]
+    for sky, bt in ((False, 'wavelength'), (True, 'wavelength'), (True, 'energy')):
+        r = ospec.image_worker(darray, bintype=bt, sky_subtraction=sky, spectrum_pixel=sel)
+        key = 'iw_%d_%s_' % (int(sky), bt)
+        assert np.array_equal(np.array(r['E']), g[key + 'E'])
+        assert np.array_equal(np.array(r['medians']), g[key + 'medians'])
+        assert np.array_equal(r['pc'], g[key + 'pc'])
+        ref_me = g[key + 'me']
+        ok = np.isfinite(ref_me)
+        assert np.array_equal(r['me'][ok], ref_me[ok]) and np.array_equal(np.isfinite(r['me']), ok)
+        assert np.array_equal(np.array(r['totalcounts']), g[key + 'totalcounts'])
+        assert np.array_equal(np.array(r['SNR'], dtype=np.float64), g[key + 'SNR'])
+        assert r['integrated_SNR'] == float(g[key + 'integrated_SNR'])
