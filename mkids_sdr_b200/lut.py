@@ -18,9 +18,11 @@ def random_phases(n, seed=1000):
 
 
 def comb_lut(freqs, sample_rate, n_samples, amplitudes, phases=None, echo='yes', random_phase='yes', offset=0,
-             scale_override=None, ctx=None):
+             scale_override=None, ctx=None, out_I=None, out_Q=None):
     """Batched freqCombLUT.  freqs/amplitudes/phases: [batch][T] (or [T]).  Returns
-    (I int16 [batch][N], Q int16 [batch][N], scale [batch], phases_used [batch][T])."""
+    (I int16 [batch][N], Q int16 [batch][N], scale [batch], phases_used [batch][T]).  out_I / out_Q: optional
+    device buffers (int16 [batch][N]) that receive the tables instead of host arrays (the LUT then never leaves HBM,
+    e.g. on its way into mkid_pack_dram / the channelizer)."""
     ctx = ctx or _lib.default_context()
     f = np.atleast_2d(np.asarray(freqs, dtype=np.float64))
     batch, T = f.shape
@@ -28,8 +30,8 @@ def comb_lut(freqs, sample_rate, n_samples, amplitudes, phases=None, echo='yes',
     ph = np.zeros((batch, T)) if phases is None else np.atleast_2d(np.asarray(phases, dtype=np.float64))[:, :T]
     ph = np.ascontiguousarray(np.broadcast_to(ph, (batch, T))).copy()
     f = np.ascontiguousarray(f)
-    I = np.empty((batch, n_samples), dtype=np.int16)
-    Q = np.empty((batch, n_samples), dtype=np.int16)
+    I = out_I if out_I is not None else np.empty((batch, n_samples), dtype=np.int16)
+    Q = out_Q if out_Q is not None else np.empty((batch, n_samples), dtype=np.int16)
     scale = np.empty(batch, dtype=np.float64)
     fudge = SCALE_FUDGE if echo == 'yes' else 1.0
     ctx._check(ctx.lib.mkid_comb_lut(ctx.h, _lib.ptr(f), _lib.ptr(a), _lib.ptr(ph), T, float(sample_rate), int(n_samples),
