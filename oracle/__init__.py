@@ -18,6 +18,16 @@ Pinned against the reference's own fixtures (see tests/golden/make_golden.py):
                      PacketMaster.c inner loop is not compilable: needs hdf5.h)
                      -> restated in packetmaster_core.c; the bitfield layout is
                      pinned by ROACH_Pulses.py:805-811 and PacketMaster.c:306.
+and against OUTPUTS OF THE REFERENCE'S OWN CODE executed in the dev container (the method sources are read from the
+reference tree at run time, Python-2 -> 3 edits applied, run against a recording roach / mock widgets; only the
+numerical outputs are stored: tests/golden/make_golden_refrun.py -> refrun_golden.npz,
+make_golden_analysis.py -> analysis_golden.npz; tests/test_oracle_golden.py::*reference_run*):
+  * lut.py        <- ROACH_Setup_DAC.py define_DAC_LUT / freqCombLUT / define_DDS_LUT / select_bins / write_LUTs
+                     (12 tones, seed-1000 phases, DDS phases, DRAM image: bit-identical)
+  * control.py    <- ROACH_Pulses.py loadFIRcoeffs, loadIQcenters, loadThresholds (bit-identical)
+  * decode.py     <- ROACH_Pulses.py readPulses (10 steps, ring wraps: bit-identical)
+  * template.py   <- lib/pulses.py MakeTemplate (bit-identical)
+  * spectra.py    <- ArconsDashboard.py image_Worker methods (bit-identical)
   * channelizer.py: PARITY UNPINNED -- the firmware data plane is absent from
                      the reference; this float64 model is the parity definition.
 """

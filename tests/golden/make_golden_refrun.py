@@ -1,0 +1,280 @@
+"""Golden outputs of the reference's OWN AppForm methods, executed in the dev container (tests/golden/refrun_golden.npz).
+
+    python tests/golden/make_golden_refrun.py [/root/reference]
+
+The GUI modules cannot be imported (Python-2 syntax, PyQt4 / corr / matplotlib at module level), so this script reads
+the source text of individual METHODS from the reference tree AT RUN TIME and executes them:
+
+  * text edits: tabs expanded, `print x` -> `print(x)`, `xrange` -> `range`;
+  * AST edit:   every `/` becomes a call to a Python-2 division (integer floor division on ints, true division else);
+  * name space: Python-2 `round` (half away from zero, float result), `map` returning a list, `unicode`, `raw_input`,
+                a `struct` whose pack / unpack work on Python-2 style byte strings (latin-1 text);
+  * `self`:     a plain object holding the attributes the GUI would hold; unknown attributes (widgets, plot axes)
+                are mocks; `self.roach` records every write / serves canned reads.
+
+No reference source is stored in this repository, only the numerical OUTPUTS of the runs.
+
+  ROACH_Setup_DAC.py   freqCombLUT :396-455, define_DAC_LUT :457-483, define_DDS_LUT :485-511, select_bins :513-529,
+                       write_LUTs :531-557                                   (multi-tone comb, 12 tones, N = 2^12)
+  ROACH_Pulses.py      loadFIRcoeffs :59-111, loadIQcenters :948-956, loadThresholds :211-299, find_nearest, readPulses :782-919
+"""
+import ast
+import builtins
+import math
+import os
+import re
+import struct as _struct
+import sys
+import tempfile
+import types
+import warnings
+from unittest import mock
+
+import numpy
+
+ref = sys.argv[1] if len(sys.argv) > 1 else '/root/reference'
+here = os.path.dirname(os.path.abspath(__file__))
+CC = os.path.join(ref, 'DataReadout', 'ChannelizerControls')
+
+
+# ------------------------------------------------------------------ source -> executable methods
+def method_source(path, name):
+    lines = open(path).read().expandtabs(8).splitlines()
+    i0 = next(i for i, l in enumerate(lines) if re.match(r'^    def %s\(' % name, l))
+    i1 = next((i for i in range(i0 + 1, len(lines)) if re.match(r'^    def |^\S', lines[i])), len(lines))
+    out = []
+    for line in lines[i0:i1]:
+        m = re.match(r'^(\s*)print\s+(.*)$', line)
+        if m and not m.group(2).startswith('('):
+            line = '%sprint(%s)' % (m.group(1), m.group(2))
+        elif re.match(r'^\s*print\s*$', line):
+            line = line.replace('print', 'print()')
+        out.append(line.replace('xrange', 'range'))
+    return '\n'.join(out) + '\n'
+
+
+class _Py2Div(ast.NodeTransformer):
+    def visit_BinOp(self, node):
+        self.generic_visit(node)
+        if isinstance(node.op, ast.Div):
+            return ast.copy_location(ast.Call(func=ast.Name(id='_py2div', ctx=ast.Load()), args=[node.left, node.right],
+                                              keywords=[]), node)
+        return node
+
+
+def _py2div(a, b):
+    if isinstance(a, (int, numpy.integer)) and isinstance(b, (int, numpy.integer)) and not isinstance(a, bool):
+        return a // b
+    return a / b
+
+
+def _py2round(x, n=0):
+    m = 10 ** n
+    v = x * m
+    r = math.floor(abs(v) + 0.5) * (1 if v >= 0 else -1)
+    return float(r) / m
+
+
+class _Struct:                       # Python-2 byte strings as latin-1 text
+    @staticmethod
+    def pack(fmt, *a):
+        return _struct.pack(fmt, *[int(v) for v in a]).decode('latin-1')
+
+    @staticmethod
+    def unpack(fmt, s):
+        return _struct.unpack(fmt, s.encode('latin-1') if isinstance(s, str) else s)
+
+
+def build_class(path, names, extra_ns=None):
+    body = ''.join(method_source(path, n) for n in names)
+    tree = ast.parse('class Ref(object):\n' + body)
+    tree = ast.fix_missing_locations(_Py2Div().visit(tree))
+    printed = []
+    ns = dict(numpy=numpy, struct=_Struct, os=os, time=mock.MagicMock(), math=math, _py2div=_py2div, round=_py2round,
+              map=lambda f, *a: list(builtins.map(f, *a)), unicode=str, raw_input=lambda *a: 'y',
+              print=lambda *a, **k: printed.append(a), datetime=mock.MagicMock(), pickle=mock.MagicMock(),
+              roachNo=0, __file__=os.path.join(CC, 'x.py'))
+    ns.update(extra_ns or {})
+    exec(compile(tree, os.path.basename(path), 'exec'), ns)
+    return ns['Ref'], printed, ns
+
+
+class Roach:
+    def __init__(self, reads=None, read_ints=None):
+        self.log, self.reads, self.read_ints = [], dict(reads or {}), dict(read_ints or {})
+
+    def write_int(self, name, value, *a, **k):
+        self.log.append(('write_int', name, int(value)))
+
+    def write(self, name, data, *a, **k):
+        data = data.encode('latin-1') if isinstance(data, str) else bytes(data)
+        self.log.append(('write', name, data))
+
+    def read(self, name, size, *a, **k):
+        v = self.reads[name]
+        d = v.pop(0) if isinstance(v, list) else v
+        return d[:size].decode('latin-1')
+
+    def read_int(self, name, *a, **k):
+        return self.read_ints[name].pop(0)
+
+
+class Self:
+    """attribute bag: real values where set, mocks for widgets / axes"""
+
+    def __getattr__(self, k):
+        m = mock.MagicMock()
+        object.__setattr__(self, k, m)
+        return m
+
+
+def text_widget(s):
+    w = mock.MagicMock()
+    w.text.return_value = s
+    w.toPlainText.return_value = s
+    return w
+
+
+# ------------------------------------------------------------------ the runs
+def run_setup_dac():
+    Ref, printed, ns = build_class(os.path.join(CC, 'ROACH_Setup_DAC.py'),
+                                   ['freqCombLUT', 'define_DAC_LUT', 'define_DDS_LUT', 'select_bins', 'write_LUTs'])
+    fs, N = 512e6, 2 ** 12
+    res = fs / N
+    lo = 5.0e9
+    rng = numpy.random.default_rng(7)
+    k = numpy.sort(rng.choice(numpy.arange(-N // 2 + 8, N // 2 - 8), 12, replace=False))
+    dac_freqs = [lo + float(v) * res for v in k]
+    attens = rng.integers(0, 20, 12).astype(float)
+    s = Self()
+    for m in Ref.__dict__:
+        if not m.startswith('__'):
+            setattr(s, m, types.MethodType(getattr(Ref, m), s))
+    s.sampleRate, s.freqRes = fs, res
+    s.attens = numpy.array(attens)
+    s.minimumAttenuation, s.previous_scale_factor, s.last_scale_factor = 10, 5000.0, None
+    s.textbox_offset = text_widget('0')
+    s.textbox_customScale = text_widget('1')
+    s.cbox_keepScaleFactor = mock.MagicMock(); s.cbox_keepScaleFactor.isChecked.return_value = False
+    s.cbox_useScaleFactor = mock.MagicMock(); s.cbox_useScaleFactor.isChecked.return_value = False
+    s.textedit_DACfreqs = text_widget(' '.join(repr(f) for f in dac_freqs))
+    s.textbox_loFreq = text_widget(repr(lo))
+    s.roach = Roach()
+    s.dacStatus = 'off'
+    tmp = tempfile.mkdtemp()
+    s.textbox_saveDir = text_widget(tmp)
+    cwd = os.getcwd()
+    os.chdir(tmp)
+    try:
+        with warnings.catch_warnings():
+            warnings.simplefilter('ignore')
+            s.define_DAC_LUT()
+            phase = list(numpy.random.default_rng(3).uniform(-numpy.pi, numpy.pi, 256))
+            s.define_DDS_LUT(phase)
+            # write_LUTs writes the byte string through a text-mode file: give it a binary-safe open
+            ns['open'] = lambda p, mode='r': open(p, mode, encoding='latin-1', newline='')
+            s.write_LUTs()
+    finally:
+        os.chdir(cwd)
+    dram = [d for op, n, d in s.roach.log if op == 'write' and n == 'dram_memory'][0]
+    bins = [v for op, n, v in s.roach.log if op == 'write_int' and n == 'bins']
+    return dict(setup_N=numpy.array(N), setup_lo=numpy.array(lo), setup_dac_freqs=numpy.array(dac_freqs),
+                setup_attens=attens, setup_dds_phase=numpy.array(phase), setup_freqs_dac=numpy.array(s.freqs_dac),
+                setup_I_dac=numpy.asarray(s.I_dac, dtype=numpy.int64), setup_Q_dac=numpy.asarray(s.Q_dac, dtype=numpy.int64),
+                setup_I_dds=numpy.asarray(s.I_dds, dtype=numpy.int64), setup_Q_dds=numpy.asarray(s.Q_dds, dtype=numpy.int64),
+                setup_scale_factor=numpy.array(s.scale_factor), setup_bins=numpy.array(bins),
+                setup_dram=numpy.frombuffer(dram, dtype=numpy.uint8).copy())
+
+
+def run_pulses():
+    out = {}
+    path = os.path.join(CC, 'ROACH_Pulses.py')
+    Ref, printed, ns = build_class(path, ['loadFIRcoeffs', 'loadIQcenters', 'find_nearest', 'loadThresholds', 'readPulses'])
+
+    def new_self():
+        s = Self()
+        for m in Ref.__dict__:
+            if not m.startswith('__'):
+                setattr(s, m, types.MethodType(getattr(Ref, m), s))
+        return s
+    # ---- loadFIRcoeffs: 3 driven channels (one deleted), the reference's 30 us matched filter
+    s = new_self()
+    s.textedit_DACfreqs = text_widget('1.0 2.0 3.0')
+    s.fir = list(numpy.loadtxt(os.path.join(CC, 'LUT', 'matched_30us.txt')))
+    s.zeroChannels = [0, 1, 0] + [0] * 253
+    s.roach = Roach()
+    s.loadFIRcoeffs()
+    regs = [(n, d) for op, n, d in s.roach.log if op == 'write']
+    out['fir_reg_names'] = numpy.array([n for n, d in regs[:39]])
+    out['fir_reg_bytes'] = numpy.array([numpy.frombuffer(d, dtype=numpy.uint8) for n, d in regs[:39]])
+    out['fir_load_coeff'] = numpy.array([v for op, n, v in s.roach.log if op == 'write_int' and n == 'FIR_load_coeff'][:78])
+    out['fir_inactive_bytes'] = numpy.frombuffer(regs[39][1], dtype=numpy.uint8).copy()
+    # ---- loadIQcenters
+    s = new_self()
+    rng = numpy.random.default_rng(5)
+    centers = (rng.integers(-30000, 30000, 256) + 1j * rng.integers(-30000, 30000, 256)) * 1.0 + (0.37 - 0.81j)
+    s.iq_centers = numpy.array(centers)
+    s.roach = Roach()
+    s.loadIQcenters()
+    out['iq_centers_in'] = numpy.array(centers)
+    out['iq_center_writes'] = numpy.array([v for op, n, v in s.roach.log if op == 'write_int' and n == 'conv_phase_centers'])
+    out['iq_center_regs'] = numpy.array(sorted(set(n for op, n, v in s.roach.log)))
+    # ---- loadThresholds: 2 channels x 10 snapshots of 1024 words
+    s = new_self()
+    s.textedit_DACfreqs = text_widget('1.0 2.0')
+    s.customThresholds = numpy.array([360.0] * 256)
+    snaps = []
+    raw_all = []
+    for chn in range(2):
+        for st in range(10):
+            raw = numpy.clip(numpy.round(rng.normal(1500 * (chn + 1), 300 + 200 * chn, 2048) -
+                                         numpy.abs(rng.normal(0, 2500, 2048)) * (rng.random(2048) < 0.05)), -32768, 32767)
+            words = numpy.empty((1024, 2), dtype='>i2')
+            words[:, 1] = raw[0::2]; words[:, 0] = raw[1::2]
+            snaps.append(words.tobytes())
+            raw_all.append(raw.astype(numpy.int64))
+    s.roach = Roach(reads={'snapPhase_bram': snaps})
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        s.loadThresholds()
+    out['thr_raw_phase'] = numpy.array(raw_all).reshape(2, -1)
+    out['thr_thresholds_deg'] = numpy.array(s.thresholds, dtype=numpy.float64)
+    out['thr_medians_deg'] = numpy.array(s.medians, dtype=numpy.float64)
+    out['thr_capture_threshold'] = numpy.array([v for op, n, v in s.roach.log if op == 'write_int' and n == 'capture_threshold'])
+    # ---- readPulses: 3 steps incl. a ring wrap
+    s = new_self()
+    n = 2 ** 14
+    ch = rng.integers(0, 256, n)
+    peak = rng.integers(0, 4096, n); p1 = rng.integers(0, 4096, n); base = rng.integers(0, 4096, n); ts = rng.integers(0, 2 ** 20, n)
+    w = (ch.astype(numpy.uint64) << numpy.uint64(56)) | (peak.astype(numpy.uint64) << numpy.uint64(44)) | \
+        (p1.astype(numpy.uint64) << numpy.uint64(32)) | (base.astype(numpy.uint64) << numpy.uint64(20)) | ts.astype(numpy.uint64)
+    b0 = (w & numpy.uint64(0xFFFFFFFF)).astype('>u4').tobytes()
+    b1 = (w >> numpy.uint64(32)).astype('>u4').tobytes()
+    pairs = [(100, 5000), (16000, 300), (7, 7), (300, 900), (900, 2000), (2000, 2100), (16383, 1), (1, 40), (40, 4000), (4000, 9000)]
+    s.textedit_DACfreqs = text_widget('1.0 2.0')
+    s.textbox_seconds = text_widget('1')            # steps = int(seconds*10) = 10
+    s.textbox_channel = text_widget('3')
+    s.roach = Roach(reads={'pulses_bram0': b0, 'pulses_bram1': b1}, read_ints={'pulses_addr': [a for pr in pairs for a in pr]})
+    saved = []
+    ns['numpy'] = types.SimpleNamespace(**{k: getattr(numpy, k) for k in dir(numpy) if not k.startswith('__')})
+    ns['numpy'].savetxt = lambda name, arr, **k: saved.append(numpy.array(arr, dtype=numpy.float64))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        s.readPulses()
+    bars = [c.args for c in s.axes1.bar.call_args_list]
+    out['rp_words'] = w
+    out['rp_pairs'] = numpy.array(pairs)
+    out['rp_hgBase'] = numpy.asarray(bars[0][1]); out['rp_hgPeak'] = numpy.asarray(bars[1][1])
+    out['rp_hgPeakSubBase'] = numpy.asarray(bars[2][1])
+    out['rp_peaksCh_deg'] = saved[0]; out['rp_timesCh'] = saved[1]
+    cc = [a for a in printed if a and a[0] == 'total counts by channel: ']
+    out['rp_channel_count'] = numpy.array(cc[-1][1])
+    return out
+
+
+if __name__ == '__main__':
+    out = {}
+    out.update(run_setup_dac())
+    out.update(run_pulses())
+    numpy.savez_compressed(os.path.join(here, 'refrun_golden.npz'), **out)
+    print('wrote refrun_golden.npz:', {k: numpy.asarray(v).shape for k, v in out.items()})

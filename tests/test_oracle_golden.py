@@ -294,3 +294,65 @@ def test_spectra_oracle_matches_reference_run(golden_dir):
         assert np.array_equal(np.array(r['totalcounts']), g[key + 'totalcounts'])
         assert np.array_equal(np.array(r['SNR'], dtype=np.float64), g[key + 'SNR'])
         assert r['integrated_SNR'] == float(g[key + 'integrated_SNR'])
+
+
+def test_lut_oracle_matches_reference_run_multitone(golden_dir):
+    """oracle/lut.py against the reference's own define_DAC_LUT / freqCombLUT / define_DDS_LUT / select_bins /
+    write_LUTs (ROACH_Setup_DAC.py:396-557), executed in the dev container on a 12-tone comb at N = 2^12 with
+    seed-1000 random phases and non-zero DDS phases (tests/golden/make_golden_refrun.py)."""
+    g = np.load(os.path.join(golden_dir, 'refrun_golden.npz'))
+    fs, N, lo = 512e6, int(g['setup_N']), float(g['setup_lo'])
+    res = fs / N
+    dac_freqs = [float(f) for f in g['setup_dac_freqs']]
+    # define_DAC_LUT of the multi-tone GUI: mirror about LO, +fs if below LO, snap (py2 round), amplitudes from attens
+    freqs = [lo + (lo - f) for f in dac_freqs]
+    freqs = [f + fs if f < lo else f for f in freqs]
+    freqs_dac = lut.dac_freqs_multi(freqs, lo, res)
+    assert np.array_equal(np.array(freqs_dac), g['setup_freqs_dac'])
+    amps = lut.dac_amplitudes(g['setup_attens'])
+    I, Q, scale, _ = lut.freq_comb_lut('yes', freqs_dac, fs, res, amps)
+    assert scale == float(g['setup_scale_factor'])
+    assert np.array_equal(I, g['setup_I_dac']) and np.array_equal(Q, g['setup_Q_dac'])
+    # define_DDS_LUT + select_bins (on the ORIGINAL frequency list, :488-496)
+    fd = lut.dds_freqs(dac_freqs, lo, fs, res)
+    bins, resid = lut.select_bins(fd, fs, res)
+    assert np.array_equal(np.array(bins), g['setup_bins'])
+    I_dds, Q_dds, _ = lut.define_dds_lut(resid, fs, res, list(g['setup_dds_phase']))
+    assert np.array_equal(I_dds, g['setup_I_dds']) and np.array_equal(Q_dds, g['setup_Q_dds'])
+    assert np.array_equal(np.frombuffer(lut.pack_dram(I, Q, I_dds, Q_dds), dtype=np.uint8), g['setup_dram'])
+
+
+def test_control_oracle_matches_reference_run(golden_dir):
+    """loadFIRcoeffs / loadIQcenters / loadThresholds of ROACH_Pulses.py executed in the dev container."""
+    g = np.load(os.path.join(golden_dir, 'refrun_golden.npz'))
+    taps = np.load(os.path.join(golden_dir, 'fir_taps.npz'))['matched_30us']
+    regs = control.fir_registers(taps)
+    zero = control.fir_registers([0.] * 26)
+    for ch, rr in enumerate((regs, zero, regs)):                 # channel 1 is deleted (zeroChannels)
+        for n, (name, val, packed) in enumerate(rr):
+            assert str(g['fir_reg_names'][ch * 13 + n]) == name
+            assert bytes(g['fir_reg_bytes'][ch * 13 + n]) == packed
+    assert list(g['fir_load_coeff'][:4]) == [1, 0, 1, 0] and list(g['fir_load_coeff'][26:28]) == [3, 2]
+    assert bytes(g['fir_inactive_bytes']) == b'\x00\x00\x00\x00'
+    for c, w in zip(g['iq_centers_in'], g['iq_center_writes']):
+        assert control.iq_center_word(complex(c))[0] == int(w)
+    for ch in range(2):
+        thr, med, _ = control.threshold_from_phase(g['thr_raw_phase'][ch])
+        assert thr == int(g['thr_capture_threshold'][ch])
+        assert control.SCALE_TO_ANGLE * thr == g['thr_thresholds_deg'][ch]
+        assert control.SCALE_TO_ANGLE * med == g['thr_medians_deg'][ch]
+
+
+def test_read_pulses_oracle_matches_reference_run(golden_dir):
+    """oracle/decode.read_pulses against the reference's own readPulses (ROACH_Pulses.py:782-889): 10 steps,
+    two ring wraps, channel 3 selected."""
+    g = np.load(os.path.join(golden_dir, 'refrun_golden.npz'))
+    w = g['rp_words']
+    b0 = (w & np.uint64(0xFFFFFFFF)).astype('>u4').tobytes()
+    b1 = (w >> np.uint64(32)).astype('>u4').tobytes()
+    pairs = [tuple(int(v) for v in p) for p in g['rp_pairs']]
+    r = decode.read_pulses([b0] * len(pairs), [b1] * len(pairs), pairs, sel_ch=3)
+    assert np.array_equal(r['channel_count'], g['rp_channel_count'])
+    assert np.array_equal(r['hgBase'], g['rp_hgBase']) and np.array_equal(r['hgPeak'], g['rp_hgPeak'])
+    assert np.array_equal(r['hgPeakSubBase'], g['rp_hgPeakSubBase'])
+    assert np.array_equal(r['peak_deg'], g['rp_peaksCh_deg']) and np.array_equal(r['times'], g['rp_timesCh'])
