@@ -16,6 +16,7 @@ No reference source is stored in this repository, only the numerical OUTPUTS of 
 
   ROACH_Setup_DAC.py   freqCombLUT :396-455, define_DAC_LUT :457-483, define_DDS_LUT :485-511, select_bins :513-529,
                        write_LUTs :531-557                                   (multi-tone comb, 12 tones, N = 2^12)
+  pulse_triggering_v2.py  twos_comp :22-26 and the trigger loop :102-174 (rolling mean + I/Q snapshot decode)
   ROACH_Pulses.py      loadFIRcoeffs :59-111, loadIQcenters :948-956, loadThresholds :211-299, find_nearest, readPulses :782-919
 """
 import ast
@@ -272,9 +273,54 @@ def run_pulses():
     return out
 
 
+def run_trigger_script():
+    """The trigger loop of pulse_triggering_v2.py:102-174 (rolling-mean trigger with the 40-bit I/Q snapshot decode inside
+    the hit branch), dedented and executed with the script's own variable names."""
+    path = os.path.join(CC, 'pulse_triggering_v2.py')
+    lines = open(path).read().expandtabs(8).splitlines()
+    t0 = next(i for i, l in enumerate(lines) if re.match(r'^def twos_comp\(', l))
+    t1 = next(i for i in range(t0 + 1, len(lines)) if lines[i].strip() and not lines[i].startswith(' '))
+    i0 = next(i for i, l in enumerate(lines) if re.match(r'^\s+george = 0\s*$', l))
+    i1 = next(i for i in range(i0, len(lines)) if re.match(r'^\s+bob = bob \+ 1\s*$', lines[i]))
+    ind = len(lines[i0]) - len(lines[i0].lstrip())
+    body = '\n'.join(l[ind:] if l.strip() else '' for l in lines[i0:i1 + 1])
+    src = '\n'.join(lines[t0:t1]) + '\n' + body + '\n'
+    tree = ast.fix_missing_locations(_Py2Div().visit(ast.parse(src)))
+    rng = numpy.random.default_rng(21)
+    n = 16384
+    x = rng.normal(0, 4.0, n)
+    t = numpy.arange(n)
+    for p0 in numpy.nonzero(rng.random(n) < 0.0015)[0]:
+        x[p0:] -= rng.uniform(20, 120) * numpy.exp(-(t[p0:] - p0) / 30.0)
+    L_IQ = 64
+    snap = rng.integers(0, 256, 4 * L_IQ, dtype=numpy.uint8).tobytes()
+    hits, saved_iq = [], []
+    out = {}
+    for (M, L, thr) in ((20, 1000, 25.0), (10, 300, 15.0)):
+        ns = dict(np=numpy, _py2div=_py2div, datetime=__import__('datetime').datetime, ord=ord,
+                  meanlength=M, pulselength=L, phase_threshold=thr, number_of_phase_values=n, phasevalues=list(x),
+                  steps_IQ=1, L_IQ=L_IQ, bin_data_IQ='', bin_data_IQ_ord=[], bin_data_IQ_hex=[], total_pulses=0,
+                  final_pulse_count=0, savedirIQ='', savedirPhase='', roach=Roach(reads={'conv_phase_snapIQ_bram': snap}))
+        cur = []
+
+        def savetxt(name, arr, fmt=None, _ns=ns, _cur=cur):
+            if name.startswith('pulse_'):
+                _cur.append(_ns['bob'])
+            elif not saved_iq:
+                saved_iq.append(numpy.array(arr))
+        ns['np'] = types.SimpleNamespace(mean=numpy.mean, savetxt=savetxt, column_stack=numpy.column_stack)
+        exec(compile(tree, 'pulse_triggering_v2.py', 'exec'), ns)
+        out['trig_hits_%d_%d' % (M, L)] = numpy.array(cur)
+    out['trig_phase'] = x
+    out['trig_iq_snapshot'] = numpy.frombuffer(snap, dtype=numpy.uint8).copy()
+    out['trig_iq_decoded'] = saved_iq[0]
+    return out
+
+
 if __name__ == '__main__':
     out = {}
     out.update(run_setup_dac())
     out.update(run_pulses())
+    out.update(run_trigger_script())
     numpy.savez_compressed(os.path.join(here, 'refrun_golden.npz'), **out)
     print('wrote refrun_golden.npz:', {k: numpy.asarray(v).shape for k, v in out.items()})

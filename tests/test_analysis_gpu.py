@@ -33,6 +33,12 @@ def test_rolling_trigger_matches_literal_loop(ctx, golden_dir):
         for s in range(streams.shape[0]):
             assert got[s] == otrig.trigger_rolling_literal(streams[s], M, L, thr), (M, L, thr, s)
     assert sum(len(g) for g in got) > 10
+    # hit lists produced by the reference's own script loop (tests/golden/refrun_golden.npz)
+    g = np.load(os.path.join(golden_dir, 'refrun_golden.npz'))
+    assert triggers.trigger_rolling(g['trig_phase'], 20, 1000, 25.0, ctx=ctx) == [int(v) for v in g['trig_hits_20_1000']]
+    assert triggers.trigger_rolling(g['trig_phase'], 10, 300, 15.0, ctx=ctx) == [int(v) for v in g['trig_hits_10_300']]
+    Ig, Qg = triggers.decode_iq_snapshot(g['trig_iq_snapshot'].tobytes(), ctx=ctx)
+    assert np.array_equal(np.stack([Ig, Qg], axis=1), g['trig_iq_decoded'])
     # the reference's own snapshot (ch_snap_0.txt, degrees)
     deg = np.load(os.path.join(golden_dir, 'ch_snap_0.npy'))
     for thr in (2.0, 5.0, 15.0):

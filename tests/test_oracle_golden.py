@@ -356,3 +356,14 @@ def test_read_pulses_oracle_matches_reference_run(golden_dir):
     assert np.array_equal(r['hgBase'], g['rp_hgBase']) and np.array_equal(r['hgPeak'], g['rp_hgPeak'])
     assert np.array_equal(r['hgPeakSubBase'], g['rp_hgPeakSubBase'])
     assert np.array_equal(r['peak_deg'], g['rp_peaksCh_deg']) and np.array_equal(r['times'], g['rp_timesCh'])
+
+
+def test_trigger_oracle_matches_reference_run(golden_dir):
+    """oracle/trigger.py and the I/Q snapshot decode against the reference's own trigger loop
+    (pulse_triggering_v2.py:102-174, executed in the dev container)."""
+    g = np.load(os.path.join(golden_dir, 'refrun_golden.npz'))
+    x = g['trig_phase']
+    assert trigger.trigger_rolling_literal(x, 20, 1000, 25.0) == [int(v) for v in g['trig_hits_20_1000']]
+    assert trigger.trigger_rolling_literal(x, 10, 300, 15.0) == [int(v) for v in g['trig_hits_10_300']]
+    I, Q = control.decode_iq_snapshot(g['trig_iq_snapshot'].tobytes())
+    assert np.array_equal(np.stack([I, Q], axis=1), g['trig_iq_decoded'])
