@@ -74,10 +74,9 @@ class SetupForm:
     def define_DAC_LUT(self):
         f_base = float(self.lo_freq)
         freqs = [float(f) for f in self.dac_freqs]
-        if not self.multi_tone:
-            # single-tone GUI: mirror about LO, +fs if below (ROACH_Setup.py:486-495)
-            freqs = [f_base + (f_base - f) for f in freqs]
-            freqs = [f + self.sampleRate if f < f_base else f for f in freqs]
+        # both GUIs (ROACH_Setup.py:484-495, ROACH_Setup_DAC.py:464-475): mirror about LO, +fs if below
+        freqs = [f_base + (f_base - f) for f in freqs]
+        freqs = [f + self.sampleRate if f < f_base else f for f in freqs]
         self.freqs_dac = [_py2_round((f - f_base) / self.freqRes) * self.freqRes for f in freqs]
         atten_min = numpy.asarray(self.attens, dtype=float).min()
         amplitudes = [10 ** (+(atten_min - a) / 20.) for a in numpy.asarray(self.attens, dtype=float)]

@@ -102,10 +102,14 @@ def dac_freqs_single(dac_freq, lo_freq, sampleRate, freqRes):
     return [py2_round((f - f_base) / freqRes) * freqRes for f in freqs]
 
 
-def dac_freqs_multi(freqs, lo_freq, freqRes):
-    """define_DAC_LUT of ROACH_Setup_DAC.py:476-482 (multi-tone GUI)."""
+def dac_freqs_multi(freqs, lo_freq, freqRes, sampleRate=512e6):
+    """define_DAC_LUT of ROACH_Setup_DAC.py:457-478 (multi-tone GUI): exactly the single-tone recipe applied to the
+    whole list -- mirror about LO (:464-467), +fs if below LO (:473-475), snap to the freqRes grid (py2 round, :478).
+    (Pinned by the reference's own method executed in the dev container: tests/golden/refrun_golden.npz.)"""
     f_base = float(lo_freq)
-    return [py2_round((float(f) - f_base) / freqRes) * freqRes for f in freqs]
+    freqs = [f_base + (f_base - float(f)) for f in freqs]
+    freqs = [f + sampleRate if f < f_base else f for f in freqs]
+    return [py2_round((f - f_base) / freqRes) * freqRes for f in freqs]
 
 
 def dac_amplitudes(attens):

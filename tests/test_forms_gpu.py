@@ -115,3 +115,67 @@ def test_read_pulses_matches_reference_loop(ctx):
         assert pf.peaks[c] == ref['peaks'][c] and pf.p1[c] == ref['p1'][c]
     assert np.array_equal(pf.hgBase, ref['hgBase']) and np.array_equal(pf.hgPeak, ref['hgPeak'])
     assert np.array_equal(pf.hgPeakSubBase, ref['hgPeakSubBase'])
+
+
+def test_setup_form_matches_reference_run(ctx, tmp_path, golden_dir):
+    """SetupForm against the outputs of the reference's own ROACH_Setup_DAC.py methods executed in the dev container
+    (tests/golden/refrun_golden.npz): define_DAC_LUT (mirror about LO!), freqCombLUT with seed-1000 phases,
+    define_DDS_LUT with non-zero phases, select_bins register traffic, write_LUTs DRAM image."""
+    from mkids_sdr_b200.setup_form import SetupForm
+    g = np.load(os.path.join(golden_dir, 'refrun_golden.npz'))
+    N = int(g['setup_N'])
+    sf = SetupForm(N_lut_entries=N, multi_tone=True, ctx=ctx, LUT_saveDir=str(tmp_path))
+    sf.dac_freqs, sf.lo_freq = [float(f) for f in g['setup_dac_freqs']], float(g['setup_lo'])
+    sf.attens = np.array(g['setup_attens'])
+    sf.define_DAC_LUT()
+    sf.define_DDS_LUT(list(g['setup_dds_phase']))
+    sf.write_LUTs()
+    assert np.array_equal(np.array(sf.freqs_dac), g['setup_freqs_dac'])
+    assert sf.scale_factor == float(g['setup_scale_factor'])
+    assert np.array_equal(sf.I_dac, g['setup_I_dac']) and np.array_equal(sf.Q_dac, g['setup_Q_dac'])
+    assert np.array_equal(sf.I_dds, g['setup_I_dds']) and np.array_equal(sf.Q_dds, g['setup_Q_dds'])
+    assert sf.roach.writes('bins') == [int(v) for v in g['setup_bins']]
+    assert np.array_equal(np.frombuffer(sf.binaryData, dtype=np.uint8), g['setup_dram'])
+
+
+def test_pulses_form_matches_reference_run(ctx, golden_dir):
+    """PulsesForm.loadThresholds / readPulses against the reference's own methods executed in the dev container."""
+    from mkids_sdr_b200.pulses_form import PulsesForm
+    g = np.load(os.path.join(golden_dir, 'refrun_golden.npz'))
+    pf = PulsesForm(ctx=ctx)
+    pf.dac_freqs = [1.0, 2.0]
+    snaps = []
+    for ch in range(2):
+        raw = g['thr_raw_phase'][ch].reshape(10, 2048)
+        for st in range(10):
+            words = np.empty((1024, 2), dtype='>i2')
+            words[:, 1] = raw[st, 0::2]; words[:, 0] = raw[st, 1::2]
+            snaps.append(words.tobytes())
+
+    class Roach:
+        def __init__(self): self.snaps, self.caps = list(snaps), []
+        def write_int(self, name, v, *a):
+            if name == 'capture_threshold': self.caps.append(int(v))
+        def read(self, name, size): return self.snaps.pop(0)
+    pf.roach = Roach()
+    pf.loadThresholds(steps=10)
+    assert pf.roach.caps == [int(v) for v in g['thr_capture_threshold']]
+    assert np.array_equal(pf.thresholds, g['thr_thresholds_deg']) and np.array_equal(pf.medians, g['thr_medians_deg'])
+    # readPulses
+    w = g['rp_words']
+    b0 = (w & np.uint64(0xFFFFFFFF)).astype('>u4').tobytes()
+    b1 = (w >> np.uint64(32)).astype('>u4').tobytes()
+    pairs = [tuple(int(v) for v in p) for p in g['rp_pairs']]
+
+    class Roach2:
+        def __init__(self): self.addrs = [a for p in pairs for a in p]
+        def write_int(self, *a): pass
+        def read_int(self, name): return self.addrs.pop(0)
+        def read(self, name, size): return b0 if name == 'pulses_bram0' else b1
+    pf2 = PulsesForm(roach=Roach2(), ctx=ctx)
+    pf2.channel = 3
+    cc = pf2.readPulses(steps=len(pairs))
+    assert np.array_equal(cc, g['rp_channel_count'])
+    assert np.array_equal(pf2.hgBase, g['rp_hgBase']) and np.array_equal(pf2.hgPeak, g['rp_hgPeak'])
+    assert np.array_equal(pf2.hgPeakSubBase, g['rp_hgPeakSubBase'])
+    assert np.array_equal(pf2.peak_deg, g['rp_peaksCh_deg']) and np.array_equal(pf2.times, g['rp_timesCh'])

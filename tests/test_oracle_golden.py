@@ -305,9 +305,7 @@ def test_lut_oracle_matches_reference_run_multitone(golden_dir):
     res = fs / N
     dac_freqs = [float(f) for f in g['setup_dac_freqs']]
     # define_DAC_LUT of the multi-tone GUI: mirror about LO, +fs if below LO, snap (py2 round), amplitudes from attens
-    freqs = [lo + (lo - f) for f in dac_freqs]
-    freqs = [f + fs if f < lo else f for f in freqs]
-    freqs_dac = lut.dac_freqs_multi(freqs, lo, res)
+    freqs_dac = lut.dac_freqs_multi(dac_freqs, lo, res, fs)
     assert np.array_equal(np.array(freqs_dac), g['setup_freqs_dac'])
     amps = lut.dac_amplitudes(g['setup_attens'])
     I, Q, scale, _ = lut.freq_comb_lut('yes', freqs_dac, fs, res, amps)
