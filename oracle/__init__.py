@@ -26,6 +26,8 @@ make_golden_analysis.py -> analysis_golden.npz; tests/test_oracle_golden.py::*re
                      (12 tones, seed-1000 phases, DDS phases, DRAM image: bit-identical)
   * control.py    <- ROACH_Pulses.py loadFIRcoeffs, loadIQcenters, loadThresholds (bit-identical)
   * decode.py     <- ROACH_Pulses.py readPulses (10 steps, ring wraps: bit-identical)
+  * trigger.py    <- the trigger loops of pulse_triggering_v2.py and pulse_triggering.py (hit lists identical)
+  * fixed.py      <- Utils/bin.py, Utils/binTools.py run with Python-2 division (all functions, bit-identical)
   * template.py   <- lib/pulses.py MakeTemplate (bit-identical)
   * spectra.py    <- ArconsDashboard.py image_Worker methods (bit-identical)
   * channelizer.py: PARITY UNPINNED -- the firmware data plane is absent from

@@ -17,6 +17,8 @@ No reference source is stored in this repository, only the numerical OUTPUTS of 
   ROACH_Setup_DAC.py   freqCombLUT :396-455, define_DAC_LUT :457-483, define_DDS_LUT :485-511, select_bins :513-529,
                        write_LUTs :531-557                                   (multi-tone comb, 12 tones, N = 2^12)
   pulse_triggering_v2.py  twos_comp :22-26 and the trigger loop :102-174 (rolling mean + I/Q snapshot decode)
+  pulse_triggering.py  the block-mean trigger :104-208
+  Utils/bin.py, Utils/binTools.py  whole modules (extractBin, castBin, peakfit, masks) with Python-2 division
   ROACH_Pulses.py      loadFIRcoeffs :59-111, loadIQcenters :948-956, loadThresholds :211-299, find_nearest, readPulses :782-919
 """
 import ast
@@ -317,10 +319,99 @@ def run_trigger_script():
     return out
 
 
+def run_block_trigger_script():
+    """The block-mean trigger of pulse_triggering.py:104-208 (+360 wrap of negative samples, means of fixed blocks,
+    window [bob-100, bob+300), hold-off 200), dedented and executed with the script's own variable names."""
+    path = os.path.join(CC, 'pulse_triggering.py')
+    lines = open(path).read().expandtabs(8).splitlines()
+    t0 = next(i for i, l in enumerate(lines) if re.match(r'^def twos_comp\(', l))
+    t1 = next(i for i in range(t0 + 1, len(lines)) if lines[i].strip() and not lines[i].startswith(' '))
+    i0 = next(i for i, l in enumerate(lines) if re.match(r'^\s+for k in range\(number_of_phase_values\):\s*$', l))
+    i1 = next(i for i in range(i0, len(lines)) if re.match(r'^\s+bob = bob \+ 1\s*$', lines[i]))
+    ind = len(lines[i0]) - len(lines[i0].lstrip())
+    body = '\n'.join(l[ind:] if l.strip() else '' for l in lines[i0:i1 + 1])
+    src = '\n'.join(lines[t0:t1]) + '\n' + body + '\n'
+    tree = ast.fix_missing_locations(_Py2Div().visit(ast.parse(src)))
+    rng = numpy.random.default_rng(22)
+    n = 20000
+    out = {}
+    L_IQ = 64
+    snap = rng.integers(0, 256, 4 * L_IQ, dtype=numpy.uint8).tobytes()
+    for tag, offset, A, thr in (('a', 3.0, 128, 25.0), ('b', -2.0, 64, 15.0), ('c', 150.0, 100, 40.0)):
+        x = rng.normal(offset, 4.0, n)
+        t = numpy.arange(n)
+        for p0 in numpy.nonzero(rng.random(n) < 0.002)[0]:
+            x[p0:] -= rng.uniform(20, 120) * numpy.exp(-(t[p0:] - p0) / 30.0)
+        ns = dict(_py2div=_py2div, datetime=__import__('datetime').datetime, ord=ord, averagelength=A,
+                  numberofaverages=n // A, phase_threshold=thr, number_of_phase_values=n, phasevalues=list(x),
+                  steps_IQ=1, L_IQ=L_IQ, bin_data_IQ='', bin_data_IQ_ord=[], bin_data_IQ_hex=[], total_pulses=0,
+                  final_pulse_count=0, savedirIQ='', savedirPhase='', roach=Roach(reads={'conv_phase_snapIQ_bram': snap}))
+        cur = []
+
+        def savetxt(name, arr, fmt=None, _ns=ns, _cur=cur):
+            if name.startswith('pulse_'):
+                _cur.append(_ns['bob'])
+        ns['np'] = types.SimpleNamespace(mean=numpy.mean, zeros=numpy.zeros, ones=numpy.ones, savetxt=savetxt,
+                                         column_stack=numpy.column_stack)
+        exec(compile(tree, 'pulse_triggering.py', 'exec'), ns)
+        out['btrig_%s_phase' % tag] = x
+        out['btrig_%s_params' % tag] = numpy.array([A, thr])
+        out['btrig_%s_hits' % tag] = numpy.array(cur)
+    return out
+
+
+def run_utils_bin():
+    """Utils/bin.py and Utils/binTools.py executed with Python-2 division (under Python 3 extractBin / castBin are
+    silently wrong because of `int(value)/2**(nBits-1)`)."""
+    out = {}
+    rng = numpy.random.default_rng(31)
+    vals = [int(v) for v in rng.integers(0, 2 ** 40, 200)]
+    fl = [float(v) for v in numpy.concatenate([rng.uniform(-4, 4, 150), rng.uniform(-40, 40, 50)])]
+    ys = rng.uniform(-100, 100, (50, 3))
+    for fname in ('bin.py', 'binTools.py'):
+        src = open(os.path.join(ref, 'Utils', fname)).read().expandtabs(8)
+        src = '\n'.join(re.sub(r'^(\s*)print\s+(.*)$', r'\1print(\2)', l) for l in src.splitlines()) + '\n'
+        tree = ast.fix_missing_locations(_Py2Div().visit(ast.parse(src)))
+        ns = dict(_py2div=_py2div, round=_py2round, __name__='refutils')
+        exec(compile(tree, fname, 'exec'), ns)
+        tag = fname[:-3]
+        out['ub_values'] = numpy.array(vals, dtype=numpy.uint64)
+        out['ub_floats'] = numpy.array(fl)
+        for (nb, bp, after) in ((12, 9, 0), (12, 9, 20), (16, 13, 4), (18, 16, 0)):
+            if 'extractBin' in ns:
+                for fmt in ('rad', 'deg'):
+                    try:
+                        out['%s_extract_%d_%d_%d_%s' % (tag, nb, bp, after, fmt)] = numpy.array(
+                            [ns['extractBin'](v, nb, bp, after, fmt) for v in vals], dtype=numpy.float64)
+                    except TypeError:
+                        out['%s_extract_%d_%d_%d' % (tag, nb, bp, after)] = numpy.array(
+                            [ns['extractBin'](v, nb, bp, after) for v in vals], dtype=numpy.float64)
+                        break
+            if 'castBin' in ns and after == 0:
+                for q in ('Truncate', 'Round'):
+                    for fmt in ('uint', 'rad', 'deg'):
+                        try:
+                            out['%s_cast_%d_%d_%s_%s' % (tag, nb, bp, q, fmt)] = numpy.array(
+                                [ns['castBin'](v, nb, bp, q, fmt) for v in fl], dtype=numpy.float64)
+                        except Exception:
+                            pass
+        for name in ('binMask', 'bitmask'):
+            if name in ns:
+                out['%s_%s' % (tag, name)] = numpy.array([ns[name](k) for k in range(1, 40)], dtype=numpy.uint64)
+        if 'peakfit' in ns:
+            out['ub_peakfit_in'] = ys
+            out['%s_peakfit' % tag] = numpy.array([ns['peakfit'](*y) for y in ys])
+        if 'bin12_9ToRad' in ns:
+            out['%s_bin12_9ToRad' % tag] = numpy.array([ns['bin12_9ToRad'](v & 0xFFF) for v in vals], dtype=numpy.float64)
+    return out
+
+
 if __name__ == '__main__':
     out = {}
     out.update(run_setup_dac())
     out.update(run_pulses())
     out.update(run_trigger_script())
+    out.update(run_block_trigger_script())
+    out.update(run_utils_bin())
     numpy.savez_compressed(os.path.join(here, 'refrun_golden.npz'), **out)
     print('wrote refrun_golden.npz:', {k: numpy.asarray(v).shape for k, v in out.items()})

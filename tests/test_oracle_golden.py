@@ -365,3 +365,81 @@ def test_trigger_oracle_matches_reference_run(golden_dir):
     assert trigger.trigger_rolling_literal(x, 10, 300, 15.0) == [int(v) for v in g['trig_hits_10_300']]
     I, Q = control.decode_iq_snapshot(g['trig_iq_snapshot'].tobytes())
     assert np.array_equal(np.stack([I, Q], axis=1), g['trig_iq_decoded'])
+
+
+def _utils_cases(g, tag):
+    vals = [int(v) for v in g['ub_values']]
+    fl = [float(v) for v in g['ub_floats']]
+    for key in g.files:
+        if not key.startswith(tag + '_'):
+            continue
+        parts = key[len(tag) + 1:].split('_')
+        yield key, parts, vals, fl
+
+
+def test_fixed_oracle_matches_reference_run(golden_dir):
+    """oracle/fixed.py against the reference's Utils/bin.py and Utils/binTools.py executed with Python-2 division in the
+    dev container (under Python 3 the modules import but extractBin / castBin are silently wrong)."""
+    g = np.load(os.path.join(golden_dir, 'refrun_golden.npz'))
+    n_checked = 0
+    for tag in ('bin', 'binTools'):
+        for key, parts, vals, fl in _utils_cases(g, tag):
+            if parts[0] == 'extract':
+                nb, bp, after = int(parts[1]), int(parts[2]), int(parts[3])
+                fmt = parts[4] if len(parts) > 4 else 'rad'
+                got = np.array([fixed.extractBin(v, nb, bp, after, fmt) for v in vals], dtype=np.float64)
+            elif parts[0] == 'cast':
+                nb, bp, q, fmt = int(parts[1]), int(parts[2]), parts[3], parts[4]
+                got = np.array([fixed.castBin(v, nb, bp, q, fmt) for v in fl], dtype=np.float64)
+            elif parts[0] in ('binMask', 'bitmask'):
+                got = np.array([fixed.binMask(k) for k in range(1, 40)], dtype=np.uint64)
+            elif parts[0] == 'peakfit':
+                got = np.array([fixed.peakfit(*y) for y in g['ub_peakfit_in']])
+            elif parts[0] == 'bin12':
+                got = np.array([fixed.bin12_9ToRad(v & 0xFFF) for v in vals], dtype=np.float64)
+            else:
+                continue
+            assert np.array_equal(got, g[key]), key
+            n_checked += 1
+    assert n_checked >= 40
+
+
+def test_block_trigger_oracle_matches_reference_run(golden_dir):
+    """oracle/trigger.trigger_block_literal against the reference's own block-mean trigger loop
+    (pulse_triggering.py:104-208, executed in the dev container)."""
+    g = np.load(os.path.join(golden_dir, 'refrun_golden.npz'))
+    for tag in 'abc':
+        A, thr = g['btrig_%s_params' % tag]
+        hits = trigger.trigger_block_literal(g['btrig_%s_phase' % tag], int(A), float(thr))
+        assert hits == [int(v) for v in g['btrig_%s_hits' % tag]], tag
+    assert len(g['btrig_c_hits']) > 5
+
+
+def test_product_utils_scalar_paths_match_reference_run(golden_dir):
+    """The host-side scalar paths of mkids_sdr_b200/Utils/{bin,binTools}.py (drop-in for `from Utils.bin import *`,
+    lib/set_alpha.py:7) against the reference modules executed with Python-2 division."""
+    from mkids_sdr_b200.Utils import bin as pbin, binTools as ptools
+    g = np.load(os.path.join(golden_dir, 'refrun_golden.npz'))
+    n_checked = 0
+    for tag, mod in (('bin', pbin), ('binTools', ptools)):
+        for key, parts, vals, fl in _utils_cases(g, tag):
+            if parts[0] == 'extract':
+                nb, bp, after = int(parts[1]), int(parts[2]), int(parts[3])
+                fmt = parts[4] if len(parts) > 4 else 'rad'
+                got = np.array([mod.extractBin(v, nb, bp, after, fmt) for v in vals], dtype=np.float64)
+            elif parts[0] == 'cast':
+                nb, bp, q, fmt = int(parts[1]), int(parts[2]), parts[3], parts[4]
+                got = np.array([mod.castBin(v, nb, bp, q, fmt) for v in fl], dtype=np.float64)
+            elif parts[0] == 'peakfit':
+                got = np.array([mod.peakfit(*y) for y in g['ub_peakfit_in']])
+            elif parts[0] == 'bin12':
+                got = np.array([mod.bin12_9ToRad(v & 0xFFF) for v in vals], dtype=np.float64)
+            elif parts[0] == 'binMask':
+                got = np.array([mod.binMask(k) for k in range(1, 40)], dtype=np.uint64)
+            elif parts[0] == 'bitmask':
+                got = np.array([mod.bitmask(k) for k in range(1, 40)], dtype=np.uint64)
+            else:
+                continue
+            assert np.array_equal(got, g[key]), key
+            n_checked += 1
+    assert n_checked >= 40
