@@ -328,6 +328,17 @@ int mkid_tpl_convpeak(mkid_ctx *ctx, const double *P3, int32_t n_pulses, const d
 int mkid_tpl_accumulate(mkid_ctx *ctx, const double *P3, const int32_t *pulse, const int32_t *shift, const double *norm,
                         int32_t n_list, double *tmpl, double *noise);
 
+/* Dashboard image (ReadoutControls/ArconsDashboard.py:633-723 make_image) from the per-(second,pixel) counts in
+ * device memory (counts_raw [exptime][n_pix], uncapped): the per-second text images PacketMaster writes are
+ * image_s[i] = (uint16) min(counts_raw[s][pixel_adr[i]], max_events-1) (PacketMaster.c:1029-1045); image_counts =
+ * image_{t_f} when t_f == 0 or t_f == t_i, else sum of image_s for s in [t_i, t_f) (:673-677; the current second is
+ * NOT in that sum), minus skyrate*(t_f - t_i) if skyrate != NULL (:679-680); image = flipud(image_counts) times
+ * flat (if != NULL, :688-689).  skyrate is indexed like the text image, flat like the flipped frame; float64
+ * [rows][cols] each. */
+int mkid_dashboard_image(mkid_ctx *ctx, const uint32_t *counts_raw, int32_t n_pix, const int32_t *pixel_adr, int32_t rows,
+                         int32_t cols, int32_t t_i, int32_t t_f, int32_t max_events, const double *skyrate,
+                         const double *flat, double *image, double *image_counts);
+
 /* ------------------------------------------------------------------ LUT synthesis (K1-K3)
  * mkid_comb_lut replaces AppForm.freqCombLUT (ChannelizerControls/ROACH_Setup.py:416-475; twin with GUI
  * offset/scale options ROACH_Setup_DAC.py:396-455): I[t] = sum a_n cos(2 pi f_n (t+offset)/fs + phi_n),

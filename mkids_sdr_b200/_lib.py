@@ -112,6 +112,8 @@ _SIGNATURES = {
     'mkid_tpl_prepare': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_float, c_float, c_void_p, c_void_p]),
     'mkid_tpl_convpeak': (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     'mkid_tpl_accumulate': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    'mkid_dashboard_image': (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                       c_void_p, c_void_p, c_void_p, c_void_p]),
     'mkid_random_phases': (c_int32, [ctypes.c_uint32, c_int32, c_void_p]),
     'mkid_comb_lut': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_double, c_int32, c_int32, c_double,
                                 c_int32, c_double, c_int32, c_void_p, c_void_p, c_void_p]),

@@ -472,3 +472,58 @@ extern "C" int mkid_spectra_products(mkid_ctx *ctx, const uint32_t *darray, int3
     if ((rc = mkid_stage_out_finish(ctx, pc, (size_t)n_pix * 8, d_pc))) return rc;
     return mkid_stage_out_finish(ctx, me, (size_t)n_pix * 8, d_me);
 }
+
+// ---------------------------------------------------------------- dashboard image (ArconsDashboard.py:633-723 make_image)
+// Per-second quick-look images are gathers of the capped per-(second,pixel) counts through the beammap
+// (PacketMaster.c:1029-1045, uint16).  The dashboard sums the images of the seconds [t_i, t_f) (or shows second t_f
+// alone when t_f == 0 or t_f == t_i, :673-677), subtracts skyrate*(t_f - t_i) (:679-680), flips the rows back (:683)
+// and applies the flat field (:688-689).  All of it in one gather kernel, float64 like the NumPy code.
+namespace {
+__global__ void dashboard_image_kernel(const uint32_t *__restrict__ counts, int n_pix, const int32_t *__restrict__ pixel_adr,
+                                       int rows, int cols, int t_i, int t_f, int max_events, const double *__restrict__ skyrate,
+                                       const double *__restrict__ flat, double *image, double *image_counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;          // index into the (rows x cols) text image of a second
+    if (i >= rows * cols) return;
+    const int r = i / cols, c = i - r * cols;
+    const int adr = pixel_adr[i];
+    const uint32_t cap = (uint32_t)(max_events - 1);
+    double v;
+    if (t_f == 0 || t_f == t_i) {
+        v = (double)(uint16_t)min(counts[(size_t)t_f * n_pix + adr], cap);
+    } else {
+        v = 0.0;
+        for (int s = t_i; s < t_f; ++s) v += (double)(uint16_t)min(counts[(size_t)s * n_pix + adr], cap);   // sum(self.counts[ti:tf])
+    }
+    if (skyrate) v = __dsub_rn(v, __dmul_rn(skyrate[i], (double)(t_f - t_i)));
+    image_counts[i] = v;
+    // photon_count = flipud(reshape(image_counts, rawshape)): row r of the displayed frame is row rows-1-r of the text image
+    double pc = v;
+    const int o = (rows - 1 - r) * cols + c;
+    if (flat) pc = __dmul_rn(pc, flat[o]);
+    image[o] = pc;
+}
+}  // namespace
+
+extern "C" int mkid_dashboard_image(mkid_ctx *ctx, const uint32_t *counts_raw, int32_t n_pix, const int32_t *pixel_adr,
+                                    int32_t rows, int32_t cols, int32_t t_i, int32_t t_f, int32_t max_events,
+                                    const double *skyrate, const double *flat, double *image, double *image_counts) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, counts_raw && pixel_adr && image && image_counts && rows > 0 && cols > 0 && n_pix > 0 && t_i >= 0 &&
+                          t_f >= t_i && max_events >= 2, "dashboard_image: bad argument");
+    MKID_REQUIRE(ctx, mkid_is_device_ptr(counts_raw), "dashboard_image: counts_raw must be device memory ([exptime][n_pix])");
+    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int n = rows * cols;
+    int rc;
+    const void *d_adr, *d_sky = nullptr, *d_flat = nullptr; void *d_img, *d_ic;
+    if ((rc = mkid_stage_in(ctx, pixel_adr, (size_t)n * 4, SCR_IN, &d_adr))) return rc;
+    if (skyrate && (rc = mkid_stage_in(ctx, skyrate, (size_t)n * 8, SCR_IN1, &d_sky))) return rc;
+    if (flat && (rc = mkid_stage_in(ctx, flat, (size_t)n * 8, SCR_IN2, &d_flat))) return rc;
+    if ((rc = mkid_stage_out(ctx, image, (size_t)n * 8, SCR_OUT0, false, &d_img))) return rc;
+    if ((rc = mkid_stage_out(ctx, image_counts, (size_t)n * 8, SCR_OUT1, false, &d_ic))) return rc;
+    dashboard_image_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(counts_raw, n_pix, (const int32_t *)d_adr, rows, cols, t_i, t_f,
+                                                                  max_events, (const double *)d_sky, (const double *)d_flat,
+                                                                  (double *)d_img, (double *)d_ic);
+    MKID_CHECK_LAUNCH(ctx);
+    if ((rc = mkid_stage_out_finish(ctx, image, (size_t)n * 8, d_img))) return rc;
+    return mkid_stage_out_finish(ctx, image_counts, (size_t)n * 8, d_ic);
+}

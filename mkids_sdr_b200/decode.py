@@ -198,6 +198,60 @@ class PhotonDecoder:
         return img
 
 
+class Dashboard:
+    """Headless twin of the image part of ArconsDashboard (make_image, ArconsDashboard.py:633-723) fed straight from a
+    PhotonDecoder: attributes image_time, int_time, sky_subtraction, skyrate, taking_sky, skytime, skycount,
+    flat_field, flatFactors, brightpix, vmin, vmax, redpix as in the reference."""
+
+    def __init__(self, decoder, pixel_adr):
+        self.dec = decoder
+        self.pixel_adr = np.ascontiguousarray(pixel_adr, dtype=np.int32)
+        self.nypix, self.nxpix = self.pixel_adr.shape
+        self.image_time = 0
+        self.int_time = 1
+        self.sky_subtraction = False
+        self.taking_sky = False
+        self.skytime = 0
+        self.skycount = np.zeros(self.pixel_adr.shape)
+        self.skyrate = np.zeros(self.pixel_adr.shape)
+        self.flat_field = False
+        self.flatFactors = np.ones(self.pixel_adr.shape)
+        self.contrast_mode = False
+        self.brightpix = 1
+        self.vmin, self.vmax = 0, 0
+        self.redpix = None
+
+    def make_image(self):
+        """One call per second, like the dashboard's timer: returns photon_count (the displayed frame)."""
+        c = self.dec.ctx
+        rows, cols = self.pixel_adr.shape
+        tf = self.image_time
+        ti = max(tf - int(self.int_time), 0)
+        if self.taking_sky:                         # :655-656 (the flipped raw image of this second)
+            self.skycount += np.flipud(self.dec.quicklook_image(tf, self.pixel_adr).astype(np.float64))
+        image = np.empty((rows, cols), np.float64)
+        image_counts = np.empty((rows, cols), np.float64)
+        sky = np.ascontiguousarray(self.skyrate, dtype=np.float64) if self.sky_subtraction else None
+        flat = np.ascontiguousarray(self.flatFactors, dtype=np.float64) if self.flat_field else None
+        c._check(c.lib.mkid_dashboard_image(c.h, _lib.ptr(self.dec.counts_dev), self.dec.n_pix, _lib.ptr(self.pixel_adr), rows,
+                                            cols, ti, tf, self.dec.max_events, _lib.ptr(sky), _lib.ptr(flat), _lib.ptr(image),
+                                            _lib.ptr(image_counts)))
+        c.sync()
+        if not self.contrast_mode:                  # :695-699
+            # (photon_count is a flipped VIEW of image_counts in the reference: the in-place flat-field multiply
+            # reaches image_counts, so the contrast limit is taken from the flat-fielded values)
+            indices = np.sort((np.flipud(image) if self.flat_field else image_counts).reshape(1, -1))
+            self.vmin = 0
+            self.vmax = indices[0, -1 * int(self.brightpix)]
+        self.redpix = np.where(image > 2000) if tf == ti else np.where(image > 2000 * (tf - ti))     # :705-708
+        self.image_counts = image_counts.reshape(1, -1)
+        self.image_time += 1
+        if self.taking_sky and self.image_time == self.skytime:                                       # :718-721
+            self.taking_sky = False
+            self.skyrate = self.skycount / self.skytime
+        return image
+
+
 def unpack_fields(words, ctx=None):
     """ROACH_Pulses.py:805-811 on the GPU -> (ch u8, ts u32, base u16, peak u16, p1 u16)."""
     ctx = ctx or _lib.default_context()

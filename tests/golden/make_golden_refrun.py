@@ -17,6 +17,7 @@ No reference source is stored in this repository, only the numerical OUTPUTS of 
   ROACH_Setup_DAC.py   freqCombLUT :396-455, define_DAC_LUT :457-483, define_DDS_LUT :485-511, select_bins :513-529,
                        write_LUTs :531-557                                   (multi-tone comb, 12 tones, N = 2^12)
   pulse_triggering_v2.py  twos_comp :22-26 and the trigger loop :102-174 (rolling mean + I/Q snapshot decode)
+  ArconsDashboard.py   StartQt4.make_image :633-723 (7 seconds: sky taking, sky subtraction, integration, flat field)
   pulse_triggering.py  the block-mean trigger :104-208
   Utils/bin.py, Utils/binTools.py  whole modules (extractBin, castBin, peakfit, masks) with Python-2 division
   ROACH_Pulses.py      loadFIRcoeffs :59-111, loadIQcenters :948-956, loadThresholds :211-299, find_nearest, readPulses :782-919
@@ -406,6 +407,51 @@ def run_utils_bin():
     return out
 
 
+def run_dashboard_make_image():
+    """StartQt4.make_image of ReadoutControls/ArconsDashboard.py:633-723 over 7 consecutive seconds: sky taking for
+    the first two, then sky subtraction, a 3-second integration window and the flat field."""
+    path = os.path.join(ref, 'DataReadout', 'ReadoutControls', 'ArconsDashboard.py')
+    figs = []
+    plt = mock.MagicMock()
+    plt.figimage.side_effect = lambda img, **k: figs.append(numpy.array(img, dtype=numpy.float64))
+    Ref, printed, ns = build_class(path, ['make_image'], extra_ns=dict(
+        loadtxt=lambda f: f, shape=numpy.shape, flipud=numpy.flipud, reshape=numpy.reshape, sum=numpy.sum, sort=numpy.sort,
+        where=numpy.where, plt=plt, numXPixel=44, numYPixel=46))
+    rng = numpy.random.default_rng(17)
+    rows, cols, secs = 46, 44, 7
+    n_pix = rows * cols
+    pixel_adr = rng.permutation(n_pix).reshape(rows, cols)
+    counts = rng.poisson(rng.uniform(20, 900, n_pix), (secs, n_pix)).astype(numpy.int64)
+    counts[:, 11] = 2600                                  # above the 2500-event cap
+    counts[:, 12] = 2300
+    flat = rng.uniform(0.8, 1.2, (rows, cols))
+    s = Self()
+    s.make_image = types.MethodType(Ref.make_image, s)
+    s.nxpix, s.nypix = cols, rows
+    s.counts = numpy.zeros((secs + 1, n_pix)); s.rotated_counts = numpy.zeros((secs + 1, rows, cols))
+    s.image_time = 0
+    s.taking_sky, s.skytime, s.skycount = True, 2, numpy.zeros((rows, cols))
+    s.skyrate = numpy.zeros((rows, cols))
+    s.sky_subtraction = False
+    s.flatFactors = flat
+    s.ui = mock.MagicMock()
+    s.ui.int_time_spinBox.value.return_value = 3
+    s.ui.contrast_mode.isChecked.return_value = False
+    s.ui.brightpix.value.return_value = 5
+    out = dict(dash_pixel_adr=pixel_adr, dash_counts=counts, dash_flat=flat)
+    for t in range(secs):
+        s.sky_subtraction = t >= 3
+        s.ui.flat_field_radioButton.isChecked.return_value = t >= 5
+        capped = numpy.minimum(counts[t], 2499)
+        s.binfile = capped[pixel_adr].astype(numpy.uint16).astype(numpy.float64)      # the text image of second t
+        s.make_image()
+        out['dash_frame_%d' % t] = figs[-1]
+        out['dash_vmax_%d' % t] = numpy.array(s.vmax)
+        out['dash_redpix_%d' % t] = numpy.array(s.redpix)
+    out['dash_skyrate'] = numpy.array(s.skyrate)
+    return out
+
+
 if __name__ == '__main__':
     out = {}
     out.update(run_setup_dac())
@@ -413,5 +459,6 @@ if __name__ == '__main__':
     out.update(run_trigger_script())
     out.update(run_block_trigger_script())
     out.update(run_utils_bin())
+    out.update(run_dashboard_make_image())
     numpy.savez_compressed(os.path.join(here, 'refrun_golden.npz'), **out)
     print('wrote refrun_golden.npz:', {k: numpy.asarray(v).shape for k, v in out.items()})

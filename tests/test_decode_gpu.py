@@ -186,3 +186,30 @@ def test_photon_lists_match_packetmaster(ctx):
             got = lw2[lo2[k]:lo2[k + 1]].tolist()
             want = [int(w) for w in lit['lists'].get((s, pix), [])]
             assert got == want, (s, pix)
+
+
+def test_dashboard_make_image_matches_reference_run(ctx, golden_dir):
+    """decode.Dashboard (mkid_dashboard_image + the twin of make_image's bookkeeping) against the reference's own
+    StartQt4.make_image (ArconsDashboard.py:633-723) executed in the dev container over 7 seconds: sky taking, sky
+    subtraction (with the reference's orientation quirk), 3-second integration window that excludes the current
+    second, flat field, brightest-pixel contrast and the saturated-pixel list."""
+    import os
+    from mkids_sdr_b200 import _lib
+    from mkids_sdr_b200.decode import Dashboard, PhotonDecoder
+    g = np.load(os.path.join(golden_dir, 'refrun_golden.npz'))
+    counts = g['dash_counts'].astype(np.uint32)
+    secs, n_pix = counts.shape
+    dec = PhotonDecoder(8, 253, secs, 2500, None, 0, ctx=ctx)
+    ctx._check(ctx.lib.mkid_memcpy(ctx.h, _lib.ptr(dec.counts_dev), _lib.ptr(np.ascontiguousarray(counts)), counts.nbytes))
+    ctx.sync()
+    db = Dashboard(dec, g['dash_pixel_adr'])
+    db.taking_sky, db.skytime, db.int_time, db.brightpix = True, 2, 3, 5
+    db.flatFactors = g['dash_flat']
+    for t in range(secs):
+        db.sky_subtraction = t >= 3
+        db.flat_field = t >= 5
+        frame = db.make_image()
+        assert np.array_equal(frame, g['dash_frame_%d' % t]), t
+        assert db.vmax == float(g['dash_vmax_%d' % t]), t
+        assert np.array_equal(np.array(db.redpix), g['dash_redpix_%d' % t]), t
+    assert np.array_equal(db.skyrate, g['dash_skyrate'])
