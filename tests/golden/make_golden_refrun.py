@@ -20,6 +20,7 @@ No reference source is stored in this repository, only the numerical OUTPUTS of 
   ArconsDashboard.py   StartQt4.make_image :633-723 (7 seconds: sky taking, sky subtraction, integration, flat field)
   pulse_triggering.py  the block-mean trigger :104-208
   Utils/bin.py, Utils/binTools.py  whole modules (extractBin, castBin, peakfit, masks) with Python-2 division
+  ROACH_Pulses.py      the trigger loop of contsnapshot :625-725
   ROACH_Pulses.py      loadFIRcoeffs :59-111, loadIQcenters :948-956, loadThresholds :211-299, find_nearest, readPulses :782-919
 """
 import ast
@@ -452,6 +453,46 @@ def run_dashboard_make_image():
     return out
 
 
+def run_contsnapshot_loop():
+    """The trigger part of AppForm.contsnapshot, ROACH_Pulses.py:~625-725 (block means of 2^k samples, start 500, window
+    [bob-500, bob+1500), hold-off 1000), dedented and executed with the method's own variable names."""
+    path = os.path.join(CC, 'ROACH_Pulses.py')
+    lines = open(path).read().expandtabs(8).splitlines()
+    m0 = next(i for i, l in enumerate(lines) if re.match(r'^    def contsnapshot\(', l))
+    i0 = next(i for i in range(m0, len(lines)) if re.match(r'^\s+phase_threshold = float\(self\.textbox_phasethreshold', lines[i]))
+    i1 = next(i for i in range(i0, len(lines)) if re.match(r'^\s+bob = bob \+ 1\s*$', lines[i]))
+    ind = len(lines[i0]) - len(lines[i0].lstrip())
+    body = '\n'.join(l[ind:] if l.strip() else '' for l in lines[i0:i1 + 1]) + '\n'
+    tree = ast.fix_missing_locations(_Py2Div().visit(ast.parse(body)))
+    rng = numpy.random.default_rng(23)
+    out = {}
+    for tag, k, thr in (('a', 6, 25.0), ('b', 5, 40.0), ('c', 8, 15.0)):
+        n = 2 ** 15
+        x = rng.normal(60.0, 4.0, n)
+        t = numpy.arange(n)
+        for p0 in numpy.nonzero(rng.random(n) < 0.0012)[0]:
+            x[p0:] -= rng.uniform(20, 120) * numpy.exp(-(t[p0:] - p0) / 30.0)
+        hits = []
+        ns = {}
+
+        class Rec(list):
+            def extend(self, it, _ns=ns):
+                if not hits or hits[-1] != _ns['bob']:
+                    hits.append(_ns['bob'])
+        selfo = Self()
+        selfo.textbox_phasethreshold = text_widget(repr(thr))
+        selfo.textbox_averagelength = text_widget(str(k))
+        selfo.textbox_pulsesavepath = text_widget('/tmp/x/')
+        osm = mock.MagicMock(); osm.path.exists.return_value = True
+        ns.update(dict(_py2div=_py2div, numpy=numpy, datetime=__import__('datetime').datetime, os=osm, self=selfo,
+                       qdr_phase_values=x, nContsnapSamples=n, total_pulses=0, finalphasearray=Rec(), pulsenumberarray=Rec()))
+        exec(compile(tree, 'ROACH_Pulses.py:contsnapshot', 'exec'), ns)
+        out['ctrig_%s_phase' % tag] = x
+        out['ctrig_%s_params' % tag] = numpy.array([2 ** k, thr])
+        out['ctrig_%s_hits' % tag] = numpy.array(hits)
+    return out
+
+
 if __name__ == '__main__':
     out = {}
     out.update(run_setup_dac())
@@ -460,5 +501,6 @@ if __name__ == '__main__':
     out.update(run_block_trigger_script())
     out.update(run_utils_bin())
     out.update(run_dashboard_make_image())
+    out.update(run_contsnapshot_loop())
     numpy.savez_compressed(os.path.join(here, 'refrun_golden.npz'), **out)
     print('wrote refrun_golden.npz:', {k: numpy.asarray(v).shape for k, v in out.items()})

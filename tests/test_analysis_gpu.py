@@ -73,6 +73,14 @@ def test_block_triggers_match_literal_loops(ctx):
         got = triggers.trigger_block(streams, averagelength=A, phase_threshold=thr, ctx=ctx)
         for s in range(streams.shape[0]):
             assert got[s] == otrig.trigger_block_literal(streams[s], A, thr), (A, thr, s)
+    # hit lists produced by the reference's own loops (tests/golden/refrun_golden.npz)
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'refrun_golden.npz'))
+    for tag in 'abc':
+        A, thr = g['btrig_%s_params' % tag]
+        assert triggers.trigger_block(g['btrig_%s_phase' % tag], int(A), float(thr), ctx=ctx) == [int(v) for v in g['btrig_%s_hits' % tag]]
+        A, thr = g['ctrig_%s_params' % tag]
+        assert triggers.trigger_contsnapshot(g['ctrig_%s_phase' % tag], int(A), float(thr), ctx=ctx) == \
+            [int(v) for v in g['ctrig_%s_hits' % tag]]
     big = _pulse_stream(rng, 2 ** 18, rate=0.0005)
     for A in (64, 32, 256):
         assert triggers.trigger_contsnapshot(big, A, 25., ctx=ctx) == otrig.trigger_contsnapshot_literal(big, A, 25.)

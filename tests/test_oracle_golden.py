@@ -443,3 +443,14 @@ def test_product_utils_scalar_paths_match_reference_run(golden_dir):
             assert np.array_equal(got, g[key]), key
             n_checked += 1
     assert n_checked >= 40
+
+
+def test_contsnapshot_trigger_oracle_matches_reference_run(golden_dir):
+    """oracle/trigger.trigger_contsnapshot_literal against the trigger loop of AppForm.contsnapshot
+    (ROACH_Pulses.py:625-725) executed in the dev container."""
+    g = np.load(os.path.join(golden_dir, 'refrun_golden.npz'))
+    for tag in 'abc':
+        A, thr = g['ctrig_%s_params' % tag]
+        hits = trigger.trigger_contsnapshot_literal(g['ctrig_%s_phase' % tag], int(A), float(thr))
+        assert hits == [int(v) for v in g['ctrig_%s_hits' % tag]], tag
+        assert len(hits) > 5
