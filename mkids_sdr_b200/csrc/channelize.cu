@@ -125,6 +125,7 @@ struct K4Params {
     int16_t *phase;          // [B][rows][256]
     float *phase_f32;        // optional [B][n/512][256] unquantised phase (rad) of the new outputs (tests)
     int64_t rows;            // PRE_ROWS + n/512
+    int edge_rows;           // rows of chunk 0 (multiple of 32, >= EDGE_ROWS)
     int rows_per_chunk;      // multiple of 32
     int chunks_per_board;
     uint32_t *mask;          // [B][ceil(rows/32)][256] candidate bits (fused K5c), or nullptr
@@ -437,8 +438,8 @@ __global__ void __launch_bounds__(256, 2) channelize_kernel(K4Params p) {
     const int board = blockIdx.y;
     // output rows [row0,row1) of the phase buffer; row r is local output t = r - PRE_ROWS
     // chunk 0 is the short edge chunk (input history / stream start); the others are equal
-    const int64_t row0 = blockIdx.x == 0 ? 0 : EDGE_ROWS + (int64_t)(blockIdx.x - 1) * p.rows_per_chunk;
-    const int64_t row1 = blockIdx.x == 0 ? min((int64_t)EDGE_ROWS, p.rows) : min(row0 + (int64_t)p.rows_per_chunk, p.rows);
+    const int64_t row0 = blockIdx.x == 0 ? 0 : p.edge_rows + (int64_t)(blockIdx.x - 1) * p.rows_per_chunk;
+    const int64_t row1 = blockIdx.x == 0 ? min((int64_t)p.edge_rows, p.rows) : min(row0 + (int64_t)p.rows_per_chunk, p.rows);
     if (row0 >= row1) return;
     s_tw[tid] = p.d.tw256[tid];
     __syncthreads();
@@ -1061,7 +1062,9 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     p.d = d; p.in = in_dev; p.n = n; p.f0_abs = 2 * ch->t_consumed; p.phase = ch->phase_buf; p.rows = rows; p.phase_f32 = ch->f32_out;
     {   // chunk 0 = EDGE_ROWS rows (slow path, small); the rest in equal chunks: one wave of 2 CTAs per SM when
         // the chunks stay >= 256 rows, else fewer chunks
-        const int64_t rest = std::max<int64_t>(rows - EDGE_ROWS, 0);
+        static const int edge_env = getenv("MKID_K4_EDGE") ? atoi(getenv("MKID_K4_EDGE")) : 0;      // (experiment switch)
+        p.edge_rows = std::max(EDGE_ROWS, edge_env / 32 * 32);
+        const int64_t rest = std::max<int64_t>(rows - p.edge_rows, 0);
         int64_t chunks = std::max<int64_t>(1, (int64_t)ctx->num_sms * 2 / B - 1);
         while (chunks > 1 && rest / chunks < 256) chunks = (chunks + 1) / 2;
         int64_t rpc = (rest + chunks - 1) / chunks;
