@@ -414,6 +414,7 @@ def decode_sharded_bench(ctx, torch, dist, rank, world, peak):
         ctx.sync()
         dist.all_reduce(hist_t)
         dist.all_reduce(counts_t)
+        torch.cuda.synchronize()                 # the reduce runs on NCCL's stream; the next reset() must not race it
     for _ in range(3):
         one_pass()
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
@@ -432,6 +433,7 @@ def decode_sharded_bench(ctx, torch, dist, rank, world, peak):
     return {'words_per_s': total / ms * 1e3, 'GB/s': gbs, 'frac_hbm_per_gpu': gbs / world / peak, 'ms_per_pass': ms, 'n_gpus': world,
             'collective': 'NCCL all_reduce(sum) of counts [10][2024] and spectra [2024][10] after every pass',
             'checksum_spectra': total_hist, 'checksum_expected': int(10 ** 7 * reps * world),
+            'checksum_ok': total_hist == int(10 ** 7 * reps * world),
             'workload': '16 x 1e7 photon words per GPU (different seeds), decode + per-pixel counts + 10-bin spectra'}
 
 
@@ -514,6 +516,20 @@ def decode_side_bench(ctx, peak):
         gbs = words.size * 16 / ms / 1e6
         out['photon_lists'] = {'words_per_s': words.size / ms * 1e3, 'GB/s': gbs, 'frac_hbm': gbs / peak, 'ms': ms,
                                'algorithmic_bytes_per_word': 16}
+        # the time-ordered merged list of config 4 (key = (second, roach)): same 16 B/word, contiguous writes
+        def run_merged():
+            ctx._check(ctx.lib.mkid_decode_merged(ctx.h, _lib_ptr(dw), words.size, _lib_ptr(offs), _lib_ptr(roach32),
+                                                  _lib_ptr(sec0), _lib_ptr(sec_out), roach.size, _ct.byref(dec.cfg),
+                                                  _lib_ptr(dec.counts_dev), _lib_ptr(lw_dev), words.size, _lib_ptr(lo_dev), None))
+        run_merged()
+        ctx.sync(); ctx.record(2)
+        for _ in range(k):
+            run_merged()
+        ctx.record(3)
+        ms = ctx.elapsed_ms(2, 3) / k
+        gbs = words.size * 16 / ms / 1e6
+        out['merged_list'] = {'words_per_s': words.size / ms * 1e3, 'GB/s': gbs, 'frac_hbm': gbs / peak, 'ms': ms,
+                              'algorithmic_bytes_per_word': 16}
         lw_dev.free(); lo_dev.free()
     except Exception as e:
         out['photon_lists'] = {'error': str(e)}

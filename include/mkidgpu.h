@@ -137,6 +137,16 @@ int mkid_decode_lists(mkid_ctx *ctx, const uint64_t *words, int64_t n_words, con
                       const mkid_decode_cfg *cfg, uint32_t *counts_raw, uint64_t *list_words, int64_t list_cap,
                       int64_t *list_offsets, mkid_decode_stats *stats);
 
+/* The time-ordered merged photon list of a readout (what PacketMaster's per-second flush
+ * PacketMaster.c:316-342 hands on, without the per-pixel split): every valid pixel word of the seconds < exptime,
+ * sorted by key = sec * n_roaches + roach, stream order inside a key (= timestamp order, the firmware emits the
+ * words of a board in time order).  No cap.  list_offsets int64 [exptime * n_roaches + 1].  Other arguments,
+ * accumulation of counts_raw / stats and the limits are those of mkid_decode_lists.  Synchronises. */
+int mkid_decode_merged(mkid_ctx *ctx, const uint64_t *words, int64_t n_words, const int64_t *seg_offset,
+                       const int32_t *seg_roach, const int32_t *seg_sec, int32_t *seg_sec_out, int32_t n_segments,
+                       const mkid_decode_cfg *cfg, uint32_t *counts_raw, uint64_t *list_words, int64_t list_cap,
+                       int64_t *list_offsets, mkid_decode_stats *stats);
+
 /* Wire format of DataReadout/ReadoutControls/lib/PulseServer.c:318-352 as received by
  * PacketMaster.c:286-287: per bundle 8192 big-endian u32 low halves then 8192 big-endian
  * u32 high halves.  Segment offsets are in BUNDLES. */

@@ -547,7 +547,7 @@ __global__ void __launch_bounds__(256) list_rowstart_kernel(ListParams p) {
     const int roach = blockIdx.x, ch = threadIdx.x;
     const int r0 = p.roach_first[roach], r1 = p.roach_first[roach + 1];
     const bool is_pix = ch < p.npix_per_roach;
-    int cur_sec = -1;
+    int cur_sec = -1, max_sec = -1;
     uint32_t run = 0;
     uint32_t *acc_col = p.acc + (size_t)roach * p.npix_per_roach + ch;
     for (int rb = r0; rb < r1; rb += 8) {          // 8 ranges per round: their loads are independent of the running count
@@ -571,7 +571,10 @@ __global__ void __launch_bounds__(256) list_rowstart_kernel(ListParams p) {
                 if (sec != cur_sec) {              // seconds normally only grow along a roach stream: rare
                     if (cur_sec >= 0) acc_col[(size_t)cur_sec * p.n_pix] = run;
                     cur_sec = sec;
-                    run = acc_col[(size_t)sec * p.n_pix];
+                    // acc is zeroed before this kernel and this thread is the only writer of its column: a second
+                    // that was not visited yet needs no (dependent, ~1 us) read
+                    run = sec > max_sec ? 0u : acc_col[(size_t)sec * p.n_pix];
+                    max_sec = max(max_sec, sec);
                 }
                 *cell = run;
                 run += v;
@@ -780,6 +783,134 @@ __global__ void __launch_bounds__(LIST_WARPS * 32) list_scatter_kernel(ListParam
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Time-ordered merged photon list ("merged photon list sorted by (sec, roach, ts)"): every valid
+// pixel word of seconds < exptime, key = sec * n_roaches + roach, stream order inside a key (the timestamps of one
+// board only grow inside a second).  No cap: that is a property of the per-pixel lists.  Built from the same rows:
+//   merge_rangesum_kernel   warp per range: rsum[r][ls] = words of local second ls that hit a pixel
+//   merge_rowstart_kernel   CTA per roach: rsum[r][ls] <- words of earlier ranges with the same key; acc[key] = total
+//   list_block*/offsets     offsets = exclusive scan of acc (shared with the per-pixel lists, n_pix := n_roaches)
+//   merge_scatter_kernel    warp per range re-reads its words in order and stores the pixel words of every 32-word step
+//                           as one contiguous run (ballot compaction): coalesced, sectors merge in L2
+__global__ void __launch_bounds__(256) merge_rangesum_kernel(ListParams p, uint32_t *rsum) {
+    const int r = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= p.n_ranges) return;
+    const int n_ls = p.rout[r].n_ls;
+#pragma unroll
+    for (int ls = 0; ls < DEC_MAX_LS; ++ls) {
+        uint32_t v = 0;
+        if (ls < n_ls) {
+            const uint32_t *row = p.rows + ((size_t)r * DEC_MAX_LS + ls) * DEC_ROW;
+            for (int i = lane; i < p.npix_per_roach; i += 32) v += row[i];
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+        if (lane == 0) rsum[(size_t)r * DEC_MAX_LS + ls] = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) merge_rowstart_kernel(ListParams p, uint32_t *rsum) {
+    __shared__ uint32_t s_v[256][DEC_MAX_LS];
+    __shared__ int s_nls[256], s_base[256];
+    const int roach = blockIdx.x, t = threadIdx.x;
+    const int r0 = p.roach_first[roach], r1 = p.roach_first[roach + 1];
+    int cur_sec = -1, max_sec = -1;                    // carried by thread 0 along the roach's stream
+    uint32_t run = 0;
+    for (int rb = r0; rb < r1; rb += 256) {
+        const int r = rb + t;
+        if (r < r1) {
+            s_nls[t] = p.rout[r].n_ls; s_base[t] = p.base[r];
+#pragma unroll
+            for (int ls = 0; ls < DEC_MAX_LS; ++ls) s_v[t][ls] = rsum[(size_t)r * DEC_MAX_LS + ls];
+        }
+        __syncthreads();
+        if (t == 0) {
+            const int n = min(256, r1 - rb);
+            for (int i = 0; i < n; ++i)
+                for (int ls = 0; ls < s_nls[i]; ++ls) {
+                    const int sec = s_base[i] + ls;
+                    if (sec >= p.exptime) continue;
+                    if (sec != cur_sec) {
+                        if (cur_sec >= 0) p.acc[(size_t)cur_sec * p.n_roaches + roach] = run;
+                        cur_sec = sec;
+                        run = sec > max_sec ? 0u : p.acc[(size_t)sec * p.n_roaches + roach];   // (see list_rowstart_kernel)
+                        max_sec = max(max_sec, sec);
+                    }
+                    const uint32_t v = s_v[i][ls];
+                    s_v[i][ls] = run;
+                    run += v;
+                }
+        }
+        __syncthreads();
+        if (r < r1) {
+#pragma unroll
+            for (int ls = 0; ls < DEC_MAX_LS; ++ls) rsum[(size_t)r * DEC_MAX_LS + ls] = s_v[t][ls];
+        }
+        __syncthreads();
+    }
+    if (t == 0 && cur_sec >= 0) p.acc[(size_t)cur_sec * p.n_roaches + roach] = run;
+}
+
+__global__ void __launch_bounds__(LIST_WARPS * 32) merge_scatter_kernel(ListParams p, const uint32_t *rsum) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (*p.flag & 2) return;
+    const unsigned lt = (1u << lane) - 1u;
+    uint64_t pol_in;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_in));
+    auto ld_in = [&](const uint64_t *q) -> uint64_t {
+        uint64_t v;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(q), "l"(pol_in));
+        return v;
+    };
+    for (int r = blockIdx.x * LIST_WARPS + warp; r < p.n_ranges; r += gridDim.x * LIST_WARPS) {
+        const DecRange rg = p.ranges[r];
+        const int n_words = rg.n_words, base = p.base[r], n_ls = p.rout[r].n_ls, npix = p.npix_per_roach;
+        const uint64_t *w = p.words + rg.start;
+        int ls = 0;
+        auto open_second = [&]() -> long long {        // next output index of local second ls, -1: nothing is stored
+            const int sec = base + ls;
+            if (sec >= p.exptime || ls >= n_ls) return -1ll;
+            return p.offsets[(long long)sec * p.n_roaches + rg.roach] + rsum[(size_t)r * DEC_MAX_LS + ls];
+        };
+        long long dst = open_second();
+        constexpr int LR = 8;
+        uint64_t ring[LR];
+#pragma unroll
+        for (int g = 0; g < LR; ++g) ring[g] = g * 32 + lane < n_words ? ld_in(w + g * 32 + lane) : 0ull;
+        for (int pos0 = 0; pos0 < n_words; pos0 += 32 * LR) {
+#pragma unroll
+            for (int g = 0; g < LR; ++g) {
+                const int pos = pos0 + g * 32;
+                if (pos >= n_words) break;
+                const uint64_t x = ring[g];
+                if (pos + 32 * LR + lane < n_words) ring[g] = ld_in(w + pos + 32 * LR + lane);
+                const bool valid = pos + lane < n_words;
+                const uint32_t adr = (uint32_t)(x >> 56);
+                unsigned eos = __ballot_sync(0xffffffffu, valid && adr == 255u);
+                unsigned todo = __ballot_sync(0xffffffffu, valid);
+                while (todo) {
+                    const int e = eos ? __ffs(eos) - 1 : 32;
+                    const unsigned seg = todo & (e == 32 ? 0xFFFFFFFFu : ((1u << e) - 1u));
+                    const bool store = ((seg >> lane) & 1u) && (int)adr < npix && dst >= 0;
+                    const unsigned m = __ballot_sync(0xffffffffu, store);
+                    if (store) {
+                        const long long at = dst + __popc(m & lt);
+                        if (at < p.out_cap) p.out[at] = x;
+                    }
+                    if (dst >= 0) dst += __popc(m);
+                    todo &= ~seg;
+                    if (e < 32) {
+                        todo &= ~(1u << e);
+                        eos &= ~(1u << e);
+                        ++ls;
+                        dst = open_second();
+                    }
+                }
+            }
+        }
+    }
+}
+
 __global__ void counts_cap_kernel(const uint32_t *in, uint32_t *out, int64_t n, uint32_t cap) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -821,7 +952,7 @@ __global__ void quicklook_kernel(const uint32_t *counts_sec, const int32_t *pixe
     if (i < n) image[i] = (uint16_t)counts_sec[pixel_adr[i]];
 }
 
-struct ListRequest { uint64_t *list_words; int64_t list_cap; int64_t *list_offsets; };
+struct ListRequest { uint64_t *list_words; int64_t list_cap; int64_t *list_offsets; bool by_roach; };
 
 // persistent device buffer i of the decode path (contents survive other calls on the context; lost on growth)
 int dec_private(mkid_ctx *ctx, int i, size_t bytes, void **out) {
@@ -1031,7 +1162,7 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
             std::vector<int32_t> roach_first(cfg->n_roaches + 1, n_ranges);
             for (int k = n_ranges - 1; k >= 0; --k) roach_first[hr[k].roach] = k;
             for (int q = cfg->n_roaches - 1; q >= 0; --q) roach_first[q] = std::min(roach_first[q], roach_first[q + 1]);
-            const size_t n_keys = (size_t)cfg->exptime * n_pix;
+            const size_t n_keys = (size_t)cfg->exptime * (lists->by_roach ? (size_t)cfg->n_roaches : (size_t)n_pix);
             char *lbuf;
             if ((rc = mkid_scratch(ctx, SCR_AUX5, n_keys * 4 + (size_t)(cfg->n_roaches + 1) * 4 + 64, (void **)&lbuf))) return rc;
             uint32_t *d_acc = (uint32_t *)lbuf;
@@ -1049,8 +1180,20 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
             lp.exptime = cfg->exptime; lp.cap = cfg->max_events - 1; lp.flag = d_flag;
             cudaEvent_t *lev = ctx->dbg_events + 4;
             auto lmark = [&](int i) { if (!timing) return; if (!lev[i]) cudaEventCreate(&lev[i]); cudaEventRecord(lev[i], ctx->stream); };
+            uint32_t *d_rsum = nullptr;
+            if (lists->by_roach) {
+                if ((rc = mkid_scratch(ctx, SCR_AUX2, (size_t)n_ranges * DEC_MAX_LS * 4 + 64, (void **)&d_rsum))) return rc;
+                lp.n_pix = cfg->n_roaches;              // the scan kernels run over exptime * n_pix keys
+                lp.cap = 0x7FFFFFFF;
+            }
             lmark(0);
-            list_rowstart_kernel<<<cfg->n_roaches, 256, 0, ctx->stream>>>(lp);
+            if (lists->by_roach) {
+                merge_rangesum_kernel<<<(n_ranges + 7) / 8, 256, 0, ctx->stream>>>(lp, d_rsum);
+                MKID_CHECK_LAUNCH(ctx);
+                merge_rowstart_kernel<<<cfg->n_roaches, 256, 0, ctx->stream>>>(lp, d_rsum);
+            } else {
+                list_rowstart_kernel<<<cfg->n_roaches, 256, 0, ctx->stream>>>(lp);
+            }
             MKID_CHECK_LAUNCH(ctx);
             lmark(1);
             const int n_sb = (int)((n_keys + LIST_SCAN_BLOCK - 1) / LIST_SCAN_BLOCK);
@@ -1063,9 +1206,13 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
             list_offsets_kernel<<<n_sb, 1024, 0, ctx->stream>>>(lp, d_bs);
             MKID_CHECK_LAUNCH(ctx);
             lmark(2);
-            const size_t lsm = sizeof(ListWarpSmem) * LIST_WARPS;
-            MKID_CUDA(ctx, cudaFuncSetAttribute(list_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
-            list_scatter_kernel<<<(n_ranges + LIST_WARPS - 1) / LIST_WARPS, LIST_WARPS * 32, lsm, ctx->stream>>>(lp);
+            if (lists->by_roach) {
+                merge_scatter_kernel<<<(n_ranges + LIST_WARPS - 1) / LIST_WARPS, LIST_WARPS * 32, 0, ctx->stream>>>(lp, d_rsum);
+            } else {
+                const size_t lsm = sizeof(ListWarpSmem) * LIST_WARPS;
+                MKID_CUDA(ctx, cudaFuncSetAttribute(list_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
+                list_scatter_kernel<<<(n_ranges + LIST_WARPS - 1) / LIST_WARPS, LIST_WARPS * 32, lsm, ctx->stream>>>(lp);
+            }
             MKID_CHECK_LAUNCH(ctx);
             lmark(3);
             if (timing) {
@@ -1083,7 +1230,7 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
     }
     if (lists && n_ranges == 0) {          // no words: every list is empty
         void *d_lo;
-        const size_t ob = ((size_t)cfg->exptime * n_pix + 1) * 8;
+        const size_t ob = ((size_t)cfg->exptime * (lists->by_roach ? (size_t)cfg->n_roaches : (size_t)n_pix) + 1) * 8;
         if ((rc = mkid_stage_out(ctx, lists->list_offsets, ob, SCR_OUT3, false, &d_lo))) return rc;
         MKID_CUDA(ctx, cudaMemsetAsync(d_lo, 0, ob, ctx->stream));
         if ((rc = mkid_stage_out_finish(ctx, lists->list_offsets, ob, d_lo))) return rc;
@@ -1163,7 +1310,18 @@ extern "C" int mkid_decode_lists(mkid_ctx *ctx, const uint64_t *words, int64_t n
     if (!ctx) return MKID_EINVAL;
     MKID_REQUIRE(ctx, (words || n_words == 0) && list_words && list_offsets && list_cap > 0 && cfg && cfg->max_events >= 2,
                  "decode_lists: NULL argument");
-    ListRequest lr{list_words, list_cap, list_offsets};
+    ListRequest lr{list_words, list_cap, list_offsets, false};
+    return decode_common(ctx, words, nullptr, n_words, seg_offset, nullptr, seg_roach, seg_sec, seg_sec_out, n_segments, cfg,
+                         counts_raw, nullptr, stats, nullptr, nullptr, nullptr, &lr);
+}
+
+extern "C" int mkid_decode_merged(mkid_ctx *ctx, const uint64_t *words, int64_t n_words, const int64_t *seg_offset,
+                                  const int32_t *seg_roach, const int32_t *seg_sec, int32_t *seg_sec_out, int32_t n_segments,
+                                  const mkid_decode_cfg *cfg, uint32_t *counts_raw, uint64_t *list_words, int64_t list_cap,
+                                  int64_t *list_offsets, mkid_decode_stats *stats) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, (words || n_words == 0) && list_words && list_offsets && list_cap > 0 && cfg, "decode_merged: NULL argument");
+    ListRequest lr{list_words, list_cap, list_offsets, true};
     return decode_common(ctx, words, nullptr, n_words, seg_offset, nullptr, seg_roach, seg_sec, seg_sec_out, n_segments, cfg,
                          counts_raw, nullptr, stats, nullptr, nullptr, nullptr, &lr);
 }

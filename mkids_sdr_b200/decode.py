@@ -125,6 +125,23 @@ class PhotonDecoder:
                                          _lib.ptr(lw), lw.size, _lib.ptr(lo), ctypes.addressof(self.stats)))
         return lw[:int(lo[-1])], lo, sec_out
 
+    def decode_merged(self, words, seg_offset, seg_roach, seg_sec=None, n_words=None):
+        """Decode + the time-ordered merged photon list: every valid pixel word of the seconds
+        < exptime sorted by (second, roach), stream (= timestamp) order inside.  Returns (list_words u64,
+        list_offsets int64 [exptime*n_roaches + 1], seg_sec_out); the words of second s from roach r are
+        list_words[list_offsets[s*n_roaches + r]:list_offsets[s*n_roaches + r + 1]]."""
+        off, roach, sec = _seg_arrays(seg_offset, seg_roach, seg_sec)
+        if n_words is None:
+            n_words = int(off[-1])
+        sec_out = np.zeros(roach.size, dtype=np.int32)
+        lw = np.empty(max(n_words, 1), dtype=np.uint64)
+        lo = np.empty(self.exptime * self.cfg.n_roaches + 1, dtype=np.int64)
+        c = self.ctx
+        c._check(c.lib.mkid_decode_merged(c.h, _lib.ptr(words), n_words, _lib.ptr(off), _lib.ptr(roach), _lib.ptr(sec),
+                                          _lib.ptr(sec_out), roach.size, ctypes.byref(self.cfg), _lib.ptr(self.counts_dev),
+                                          _lib.ptr(lw), lw.size, _lib.ptr(lo), ctypes.addressof(self.stats)))
+        return lw[:int(lo[-1])], lo, sec_out
+
     def decode_wire(self, wire, seg_offset, seg_roach, seg_sec=None, n_bundles=None, want_stats=True, want_sec=True):
         """wire: PulseServer bundles (bytes / u8 / u32 array, host or device)."""
         if isinstance(wire, (bytes, bytearray, memoryview)):

@@ -151,6 +151,28 @@ def packetmaster_bin(streams, npix_per_roach, exptime, max_events=MAX_EVENTS_PER
     return out
 
 
+def merged_list(streams, npix_per_roach, exptime, sec0=None):
+    """Time-ordered merged photon list ("sorted by (sec, roach, ts)"): what the per-second flush
+    of PacketMaster.c:316-342 sees before the per-pixel split.  Every valid pixel word (adr < npix_per_roach, second
+    < exptime; the second of a word = end-of-second words seen before it in its roach stream, PacketMaster.c:304-342),
+    key = sec * R + roach, stream order inside a key.  Returns (words, offsets[exptime*R + 1])."""
+    R = len(streams)
+    keys_all, words_all = [], []
+    for r, words in enumerate(streams):
+        w = np.asarray(words, dtype=np.uint64)
+        adr = (w >> np.uint64(56)).astype(np.int64)
+        is_eos = adr == 255
+        sec = np.cumsum(is_eos) - is_eos + (0 if sec0 is None else int(sec0[r]))
+        ok = (sec < exptime) & ~is_eos & (adr < npix_per_roach)
+        keys_all.append(sec[ok] * R + r)
+        words_all.append(w[ok])
+    keys = np.concatenate(keys_all) if keys_all else np.zeros(0, np.int64)
+    ww = np.concatenate(words_all) if words_all else np.zeros(0, np.uint64)
+    order = np.argsort(keys, kind='stable')
+    offsets = np.concatenate([[0], np.cumsum(np.bincount(keys, minlength=exptime * R))])
+    return ww[order], offsets
+
+
 def quicklook_image(counts_sec, pixel_adr):
     """write_sec_data PacketMaster.c:1029-1045: image[row][col] =
     photon_counts[sec][pixel_adr[row][col]] as uint16."""

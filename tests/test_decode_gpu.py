@@ -188,6 +188,65 @@ def test_photon_lists_match_packetmaster(ctx):
             assert got == want, (s, pix)
 
 
+def test_merged_photon_list(ctx):
+    """Time-ordered merged list of config 4: (second, roach) keys, stream order inside, no cap; literal check of the
+    ordering on a small ragged case fed as two segments per roach with carried seconds."""
+    from mkids_sdr_b200 import synth
+    from mkids_sdr_b200.decode import PhotonDecoder
+    R, npix, secs = 8, 253, 5
+    streams, _ = synth.photon_streams(2 * 10 ** 6, R, npix, secs, seed=11, n_hot=3, hot_rate=3000)
+    dec = PhotonDecoder(R, npix, secs, 2500, None, 0, ctx=ctx)
+    off = np.concatenate([[0], np.cumsum([len(s) for s in streams])])
+    lw, lo, sec_out = dec.decode_merged(np.concatenate(streams), off, np.arange(R))
+    ref_w, ref_o = odec.merged_list(streams, npix, secs)
+    assert np.array_equal(lo, ref_o)
+    assert np.array_equal(lw, ref_w)
+    assert np.array_equal(dec.counts_raw(), odec.packetmaster_bin(streams, npix, secs)['raw_counts'])
+    ts = (lw & np.uint64(0xFFFFF)).astype(np.int64)                 # timestamps only grow inside a (second, roach)
+    for k in range(secs * R):
+        assert np.all(np.diff(ts[lo[k]:lo[k + 1]]) >= 0)
+    # ragged, more seconds in the stream than exptime, second segment of every roach continues the first
+    R2, npix2, secs2 = 3, 37, 4
+    small = _ragged_streams(9, R2, npix2, secs2 + 1, 5000)
+    halves, roach, seg_sec = [], [], []
+    for r, st in enumerate(small):
+        cut = st.size // 2 + r
+        n_eos_first = int(((st[:cut] >> np.uint64(56)) == 255).sum())
+        halves += [st[:cut], st[cut:]]
+        roach += [r, r]
+        seg_sec += [0, n_eos_first]
+    dec2 = PhotonDecoder(R2, npix2, secs2, 2500, None, 0, ctx=ctx)
+    off2 = np.concatenate([[0], np.cumsum([h.size for h in halves])])
+    lw2, lo2, so2 = dec2.decode_merged(np.concatenate(halves), off2, roach, seg_sec)
+    ref_w2, ref_o2 = odec.merged_list(small, npix2, secs2)
+    assert np.array_equal(lo2, ref_o2) and np.array_equal(lw2, ref_w2)
+    # segments out of time order (second half of every roach first): a key that straddles the cut is revisited
+    firsts, seconds = halves[0::2], halves[1::2]
+    rev = [h for pair in zip(seconds, firsts) for h in pair]
+    rev_sec = [v for pair in zip(seg_sec[1::2], seg_sec[0::2]) for v in pair]
+    off4 = np.concatenate([[0], np.cumsum([h.size for h in rev])])
+    wa, oa = odec.merged_list(seconds, npix2, secs2, sec0=seg_sec[1::2])
+    wb, ob = odec.merged_list(firsts, npix2, secs2)
+    want = np.concatenate([np.concatenate([wa[oa[k]:oa[k + 1]], wb[ob[k]:ob[k + 1]]]) for k in range(secs2 * R2)])
+    dec4 = PhotonDecoder(R2, npix2, secs2, 2500, None, 0, ctx=ctx)
+    lw4, lo4, _ = dec4.decode_merged(np.concatenate(rev), off4, roach, rev_sec)
+    assert np.array_equal(lo4, ref_o2) and np.array_equal(lw4, want)
+    # the same input through the per-pixel lists (cap far away): every key holds its second-half words first
+    dec5 = PhotonDecoder(R2, npix2, secs2, 10 ** 6, None, 0, ctx=ctx)
+    lw5, lo5, _ = dec5.decode_lists(np.concatenate(rev), off4, roach, rev_sec)
+    la = odec.packetmaster_bin([np.concatenate([np.full(s0, 0xFFFFFFFFFFFFFFFF, np.uint64), h]) for s0, h in zip(seg_sec[1::2], seconds)],
+                               npix2, secs2, 10 ** 6, want_lists=True)
+    lb = odec.packetmaster_bin(firsts, npix2, secs2, 10 ** 6, want_lists=True)
+    wa5, oa5, wb5, ob5 = la['list_words'], la['list_offsets'], lb['list_words'], lb['list_offsets']
+    want5 = np.concatenate([np.concatenate([wa5[oa5[k]:oa5[k + 1]], wb5[ob5[k]:ob5[k + 1]]]) for k in range(secs2 * R2 * npix2)])
+    assert np.array_equal(lw5, want5)
+    assert np.array_equal(np.diff(lo5), np.diff(oa5) + np.diff(ob5))
+    # empty input
+    dec3 = PhotonDecoder(R2, npix2, secs2, 2500, None, 0, ctx=ctx)
+    lw3, lo3, _ = dec3.decode_merged(np.zeros(0, np.uint64), [0, 0], [1])
+    assert lw3.size == 0 and not lo3.any()
+
+
 def test_dashboard_make_image_matches_reference_run(ctx, golden_dir):
     """decode.Dashboard (mkid_dashboard_image + the twin of make_image's bookkeeping) against the reference's own
     StartQt4.make_image (ArconsDashboard.py:633-723) executed in the dev container over 7 seconds: sky taking, sky

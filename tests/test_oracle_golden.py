@@ -216,6 +216,25 @@ def test_packetmaster_vectorised_equals_literal():
         assert list(vec['list_words'][off[k]:off[k + 1]]) == words
 
 
+def test_merged_list_equals_literal_walk():
+    """oracle.decode.merged_list against a word-by-word walk in PacketMaster's loop order (PacketMaster.c:304-342)."""
+    streams, npix, secs, cap = _mini_streams(seed=4)
+    R = len(streams)
+    per_key = {}
+    for r, st in enumerate(streams):
+        sec = 0
+        for w in st.tolist():
+            adr = w >> 56
+            if adr == 255:
+                sec += 1
+            elif adr < npix and sec < secs:
+                per_key.setdefault(sec * R + r, []).append(w)
+    ww, off = decode.merged_list(streams, npix, secs)
+    assert off[-1] == ww.size == sum(len(v) for v in per_key.values())
+    for k in range(secs * R):
+        assert ww[off[k]:off[k + 1]].tolist() == per_key.get(k, [])
+
+
 def test_packetmaster_c_core_equals_numpy():
     import ctypes
     so = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle', '_build', 'libpm_core.so')
