@@ -526,8 +526,8 @@ __global__ void __launch_bounds__(256) decode_commit_kernel(DecParams p) {
 //                         replaced by the number of earlier words of the same (second, pixel); the per-key totals
 //                         land in acc[sec][pixel]
 //   list_offsets_kernel   offsets = exclusive scan of min(acc, max_events - 1)
-//   list_scatter_kernel   one warp per range re-reads its words in order, ranks the words of one load step that hit
-//                         the same pixel with match.any, and stores word -> out[offsets[key] + rank]
+//   list_scatter_kernel   one CTA per range re-reads its words in order, sorts blocks of 2048 words by pixel in shared
+//                         memory (stable) and stores word -> out[offsets[key] + rank] as whole sectors
 struct ListParams {
     const uint64_t *words;
     const DecRange *ranges;
@@ -650,23 +650,31 @@ __global__ void __launch_bounds__(1024) list_offsets_kernel(ListParams p, const 
     for (int k = 0; k < 4; ++k) { if (i + k < n) p.offsets[i + k] = run; run += v[k]; }
 }
 
-// one warp per range re-reads its words in order.  Per local second the index of the next list slot of every pixel
-// (offsets[key] + words of earlier ranges + words so far) and the slots left under the cap sit in shared memory; the
-// words of a pixel are staged there four at a time and leave as whole, aligned 32-byte sectors (single 8-byte
-// stores scattered over the output cost a DRAM read-modify-write each: 2.9x traffic measured), partial sectors only
-// at the start and the end of a (range, second).
-constexpr int LIST_WARPS = 8;
-struct ListWarpSmem {
-    long long dst[256];        // next list index of every pixel
-    uint64_t stage[256][4];    // the sector that is being filled
-    int left[256];             // slots left under the cap
-    unsigned char lo[256];     // first valid slot of the sector being filled (non-zero only for the first one)
+// One CTA per range re-reads its words in blocks of 2048 and sorts every block by pixel in shared memory, stably
+// (arrival order inside a pixel): warp w ranks words [256 w, 256 w + 256) of the block step by step (ballots among
+// the 32 words of a step + the warp's own running count per pixel), the counts of the warps are scanned per pixel and
+// over the pixels, and the block leaves as one run per pixel.  Only whole, aligned 32-byte sectors are stored (single
+// 8-byte stores scattered over the output cost a DRAM read-modify-write each: 2.9x traffic measured); the up to
+// three words of a pixel that do not fill a sector yet are carried to the next block, partial sectors are written
+// only at the start and the end of a (range, second).  A block ends early at an end-of-second word.
+constexpr int LIST_WARPS = 8;                         // (also the warps of merge_scatter_kernel)
+constexpr int LB_STEPS = 8, LB_BLOCK = LIST_WARPS * LB_STEPS * 32;
+struct ListBlockSmem {
+    uint64_t sorted[LB_BLOCK + 256 * 3];   // carried + new words of the block, pixel by pixel
+    uint64_t carry[256][3];
+    long long dst[256];                    // list index of the first carried (else next) word of every pixel
+    uint32_t wcnt[LIST_WARPS][256];        // words of pixel p ranked by warp w -> words of pixel p in earlier warps
+    uint32_t pstart[256];                  // start of the pixel's run in sorted[]
+    int left[256];                         // slots left under the cap
+    uint16_t take[256], nemit[256], ntot[256];
+    unsigned char ncarry[256];
+    uint32_t wsum[LIST_WARPS];
+    int first_eos;
 };
 __global__ void __launch_bounds__(LIST_WARPS * 32) list_scatter_kernel(ListParams p) {
-    extern __shared__ __align__(16) unsigned char s_raw[];
+    __shared__ ListBlockSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (*p.flag & 2) return;
-    ListWarpSmem &sm = reinterpret_cast<ListWarpSmem *>(s_raw)[warp];
     const unsigned lt = (1u << lane) - 1u;
     uint64_t pol_in;           // the input streams through L2 (evict first)
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_in));
@@ -675,111 +683,136 @@ __global__ void __launch_bounds__(LIST_WARPS * 32) list_scatter_kernel(ListParam
         asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(q), "l"(pol_in));
         return v;
     };
-    for (int r = blockIdx.x * LIST_WARPS + warp; r < p.n_ranges; r += gridDim.x * LIST_WARPS) {
+    for (int r = blockIdx.x; r < p.n_ranges; r += gridDim.x) {
         const DecRange rg = p.ranges[r];
         const int n_words = rg.n_words, base = p.base[r], n_ls = p.rout[r].n_ls, npix = p.npix_per_roach;
         const uint64_t *w = p.words + rg.start;
-        int ls = 0;
-        auto flush_partial = [&]() {            // what is staged but not yet a whole sector
-            for (int i = lane; i < 256; i += 32) {
-                const long long d = sm.dst[i];
-                const int hi = (int)(d & 3), lo = sm.lo[i];
-                for (int q = lo; q < hi; ++q) {
-                    const long long at = (d & ~3ll) + q;
-                    if (at < p.out_cap) p.out[at] = sm.stage[i][q];
-                }
-            }
-            __syncwarp();
-        };
-        auto open_second = [&]() {              // slots of local second ls (nothing is stored beyond exptime)
+        int ls = 0, pos = 0;
+        auto open_second = [&]() {              // thread = pixel: slots of local second ls (nothing is stored beyond exptime)
             const int sec = base + ls;
-            const bool live = sec < p.exptime && ls < n_ls;
-            for (int i = lane; i < 256; i += 32) {
-                long long d = 0; int l = 0;
-                if (live && i < npix) {
-                    const uint32_t before = p.rows[((size_t)r * DEC_MAX_LS + ls) * DEC_ROW + i];
-                    d = p.offsets[(long long)sec * p.n_pix + (long long)rg.roach * npix + i] + before;
-                    l = before < (uint32_t)p.cap ? p.cap - (int)before : 0;
-                }
-                sm.dst[i] = d; sm.left[i] = l; sm.lo[i] = (unsigned char)(d & 3);
+            long long d = 0; int l = 0;
+            if (sec < p.exptime && ls < n_ls && tid < npix) {
+                const uint32_t before = p.rows[((size_t)r * DEC_MAX_LS + ls) * DEC_ROW + tid];
+                d = p.offsets[(long long)sec * p.n_pix + (long long)rg.roach * npix + tid] + before;
+                l = before < (uint32_t)p.cap ? p.cap - (int)before : 0;
             }
-            __syncwarp();
+            sm.dst[tid] = d; sm.left[tid] = l; sm.ncarry[tid] = 0;
+        };
+        auto flush_carry = [&]() {              // thread = pixel: what is carried but not yet a whole sector
+            const int c = sm.ncarry[tid];
+            const long long d = sm.dst[tid];
+            for (int j = 0; j < c; ++j) if (d + j < p.out_cap) p.out[d + j] = sm.carry[tid][j];
+            sm.ncarry[tid] = 0;
         };
         open_second();
-        constexpr int LR = 8;                         // 32-word steps in flight
-        uint64_t ring[LR];
+        __syncthreads();
+        while (pos < n_words) {
+            const int rem = n_words - pos;
+            uint64_t x[LB_STEPS];
 #pragma unroll
-        for (int g = 0; g < LR; ++g) ring[g] = g * 32 + lane < n_words ? ld_in(w + g * 32 + lane) : 0ull;
-        for (int pos0 = 0; pos0 < n_words; pos0 += 32 * LR) {
+            for (int s = 0; s < LB_STEPS; ++s) {
+                const int idx = warp * (LB_STEPS * 32) + s * 32 + lane;
+                x[s] = idx < rem ? ld_in(w + pos + idx) : 0ull;
+            }
+            for (int i = tid; i < LIST_WARPS * 256; i += LIST_WARPS * 32) (&sm.wcnt[0][0])[i] = 0u;
+            if (tid == 0) sm.first_eos = LB_BLOCK;
+            __syncthreads();
+            unsigned fe = LB_BLOCK;
 #pragma unroll
-            for (int g = 0; g < LR; ++g) {
-                const int pos = pos0 + g * 32;
-                if (pos >= n_words) break;
-                const uint64_t x = ring[g];
-                if (pos + 32 * LR + lane < n_words) ring[g] = ld_in(w + pos + 32 * LR + lane);
-                const bool valid = pos + lane < n_words;
-                const uint32_t adr = (uint32_t)(x >> 56);
-                unsigned eos = __ballot_sync(0xffffffffu, valid && adr == 255u);
-                unsigned todo = __ballot_sync(0xffffffffu, valid);
-                while (todo) {
-                    // lanes below the first end-of-second word belong to the current local second
-                    const int e = eos ? __ffs(eos) - 1 : 32;
-                    const unsigned seg = todo & (e == 32 ? 0xFFFFFFFFu : ((1u << e) - 1u));
-                    const bool store = ((seg >> lane) & 1u) && (int)adr < npix;
-                    // rank among the lanes of this step that hit the same pixel (lane order = arrival order)
-                    const unsigned peers = __match_any_sync(0xffffffffu, store ? adr : 0x100u + lane);
-                    long long d0 = 0;
-                    int ns = 0, k = 0;
-                    if (store) {
-                        const int leader = __ffs(peers) - 1, n = __popc(peers);
-                        int l0 = 0;
-                        if (lane == leader) {
-                            d0 = sm.dst[adr]; l0 = sm.left[adr];
-                            const int take = min(n, max(l0, 0));
-                            sm.dst[adr] = d0 + take; sm.left[adr] = l0 - n;
-                        }
-                        d0 = __shfl_sync(peers, d0, leader);
-                        l0 = __shfl_sync(peers, l0, leader);
-                        ns = min(n, max(l0, 0));                    // words of this pixel that still fit under the cap
-                        k = __popc(peers & lt);
-                    }
-                    // sector by sector (almost always one round): stage, then the lane that completes a sector stores it
-                    int kb = 0;
-                    while (__any_sync(0xffffffffu, kb < ns)) {
-                        const int room = 4 - (int)((d0 + kb) & 3);
-                        const int take = min(room, ns - kb);
-                        const bool mine = kb < ns && k >= kb && k < kb + take;
-                        if (mine) sm.stage[adr][(d0 + k) & 3] = x;
-                        __syncwarp();
-                        if (mine && k == kb + take - 1 && ((d0 + kb + take) & 3) == 0) {
-                            const long long at = d0 + kb + take - 4;
-                            const int lo = sm.lo[adr];
-                            if (lo == 0 && at + 4 <= p.out_cap) {
-                                const uint4 a = *reinterpret_cast<const uint4 *>(&sm.stage[adr][0]);
-                                const uint4 b = *reinterpret_cast<const uint4 *>(&sm.stage[adr][2]);
-                                *reinterpret_cast<uint4 *>(p.out + at) = a;
-                                *reinterpret_cast<uint4 *>(p.out + at + 2) = b;
-                            } else {
-                                for (int q = lo; q < 4; ++q) if (at + q < p.out_cap) p.out[at + q] = sm.stage[adr][q];
-                                sm.lo[adr] = 0;
-                            }
-                        }
-                        __syncwarp();
-                        if (kb < ns) kb += take;
-                    }
-                    todo &= ~seg;
-                    if (e < 32) {                   // the end-of-second word closes the local second
-                        todo &= ~(1u << e);
-                        eos &= ~(1u << e);
-                        flush_partial();
-                        ++ls;
-                        open_second();
-                    }
+            for (int s = LB_STEPS - 1; s >= 0; --s) {
+                const int idx = warp * (LB_STEPS * 32) + s * 32 + lane;
+                if (idx < rem && (uint32_t)(x[s] >> 56) == 255u) fe = idx;
+            }
+            fe = __reduce_min_sync(0xffffffffu, fe);
+            if (lane == 0 && fe < (unsigned)LB_BLOCK) atomicMin(&sm.first_eos, (int)fe);
+            __syncthreads();
+            const int first_eos = sm.first_eos;
+            const int n_here = min(first_eos, min(rem, LB_BLOCK));
+            // rank of every word among the words of its pixel that this warp holds
+            uint32_t rk[LB_STEPS];
+            unsigned stored = 0;
+#pragma unroll
+            for (int s = 0; s < LB_STEPS; ++s) {
+                const int idx = warp * (LB_STEPS * 32) + s * 32 + lane;
+                const uint32_t adr = (uint32_t)(x[s] >> 56);
+                const bool store = idx < n_here && (int)adr < npix;
+                // lanes of this step that hit the same pixel: eight ballots over the channel bits (MATCH.ANY runs on the
+                // ADU pipe at about one per 64 cycles per SM and bounded this kernel: 95 % ADU busy measured)
+                unsigned peers = __ballot_sync(0xffffffffu, store);
+#pragma unroll
+                for (int b = 0; b < 8; ++b) {
+                    const unsigned m = __ballot_sync(0xffffffffu, (adr >> b) & 1u);
+                    peers &= ((adr >> b) & 1u) ? m : ~m;
+                }
+                rk[s] = 0;
+                if (store) {
+                    const int leader = __ffs(peers) - 1;
+                    uint32_t old = 0;
+                    if (lane == leader) { old = sm.wcnt[warp][adr]; sm.wcnt[warp][adr] = old + __popc(peers); }
+                    old = __shfl_sync(peers, old, leader);
+                    rk[s] = old + __popc(peers & lt);
+                    stored |= 1u << s;
+                }
+                __syncwarp();
+            }
+            __syncthreads();
+            {   // thread = pixel: scan over the warps, cap, scan over the pixels, sectors that can leave
+                uint32_t tot = 0;
+#pragma unroll
+                for (int q = 0; q < LIST_WARPS; ++q) { const uint32_t t = sm.wcnt[q][tid]; sm.wcnt[q][tid] = tot; tot += t; }
+                const int l = sm.left[tid];
+                const uint32_t tk = min(tot, (uint32_t)l);
+                sm.left[tid] = l - (int)tk;
+                const uint32_t c = sm.ncarry[tid], n = c + tk;
+                uint32_t incl = n;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const uint32_t a = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += a; }
+                if (lane == 31) sm.wsum[warp] = incl;
+                __syncthreads();
+                uint32_t before = 0;
+#pragma unroll
+                for (int q = 0; q < LIST_WARPS; ++q) before += q < warp ? sm.wsum[q] : 0u;
+                const uint32_t ps = before + incl - n;
+                const long long d0 = sm.dst[tid], e_al = (d0 + n) & ~3ll;
+                sm.pstart[tid] = ps;
+                sm.take[tid] = (uint16_t)tk; sm.ntot[tid] = (uint16_t)n;
+                sm.nemit[tid] = (uint16_t)(e_al > d0 ? e_al - d0 : 0);
+                for (uint32_t j = 0; j < c; ++j) sm.sorted[ps + j] = sm.carry[tid][j];
+            }
+            __syncthreads();
+#pragma unroll
+            for (int s = 0; s < LB_STEPS; ++s) {
+                if ((stored >> s) & 1u) {
+                    const uint32_t adr = (uint32_t)(x[s] >> 56);
+                    const uint32_t k = sm.wcnt[warp][adr] + rk[s];
+                    if (k < sm.take[adr]) sm.sorted[sm.pstart[adr] + sm.ncarry[adr] + k] = x[s];
                 }
             }
+            __syncthreads();
+            const int total = (int)(sm.pstart[255] + sm.ntot[255]);
+            for (int i = tid; i < total; i += LIST_WARPS * 32) {
+                const uint64_t v = sm.sorted[i];
+                const uint32_t adr = (uint32_t)(v >> 56);
+                const uint32_t off = (uint32_t)i - sm.pstart[adr], ne = sm.nemit[adr];
+                if (off < ne) {
+                    const long long at = sm.dst[adr] + off;
+                    if (at < p.out_cap) p.out[at] = v;
+                } else {
+                    sm.carry[adr][off - ne] = v;
+                }
+            }
+            __syncthreads();
+            { const uint32_t n = sm.ntot[tid], ne = sm.nemit[tid]; sm.dst[tid] += ne; sm.ncarry[tid] = (unsigned char)(n - ne); }
+            pos += n_here;
+            if (n_here == first_eos) {          // the end-of-second word at pos closes the local second
+                flush_carry();
+                ++ls; ++pos;
+                open_second();
+            }
+            __syncthreads();
         }
-        __syncwarp();
-        flush_partial();
+        flush_carry();
+        __syncthreads();
     }
 }
 
@@ -1209,9 +1242,7 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
             if (lists->by_roach) {
                 merge_scatter_kernel<<<(n_ranges + LIST_WARPS - 1) / LIST_WARPS, LIST_WARPS * 32, 0, ctx->stream>>>(lp, d_rsum);
             } else {
-                const size_t lsm = sizeof(ListWarpSmem) * LIST_WARPS;
-                MKID_CUDA(ctx, cudaFuncSetAttribute(list_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lsm));
-                list_scatter_kernel<<<(n_ranges + LIST_WARPS - 1) / LIST_WARPS, LIST_WARPS * 32, lsm, ctx->stream>>>(lp);
+                list_scatter_kernel<<<n_ranges, LIST_WARPS * 32, 0, ctx->stream>>>(lp);
             }
             MKID_CHECK_LAUNCH(ctx);
             lmark(3);
