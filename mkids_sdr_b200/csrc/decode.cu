@@ -651,7 +651,7 @@ __global__ void __launch_bounds__(1024) list_offsets_kernel(ListParams p, const 
 }
 
 // One CTA per range re-reads its words in blocks of 2048 and sorts every block by pixel in shared memory, stably
-// (arrival order inside a pixel): warp w ranks words [256 w, 256 w + 256) of the block step by step (ballots among
+// (arrival order inside a pixel): warp w ranks words [256 w, 256 w + 256) of the block step by step (lane masks of
 // the 32 words of a step + the warp's own running count per pixel), the counts of the warps are scanned per pixel and
 // over the pixels, and the block leaves as one run per pixel.  Only whole, aligned 32-byte sectors are stored (single
 // 8-byte stores scattered over the output cost a DRAM read-modify-write each: 2.9x traffic measured); the up to
@@ -663,7 +663,8 @@ struct ListBlockSmem {
     uint64_t sorted[LB_BLOCK + 256 * 3];   // carried + new words of the block, pixel by pixel
     uint64_t carry[256][3];
     long long dst[256];                    // list index of the first carried (else next) word of every pixel
-    uint32_t wcnt[LIST_WARPS][256];        // words of pixel p ranked by warp w -> words of pixel p in earlier warps
+    uint32_t wmask[LIST_WARPS][256];       // lanes of the current step that hit pixel p (zero between steps)
+    uint16_t wcnt[LIST_WARPS][256];        // words of pixel p ranked by warp w -> words of pixel p in earlier warps
     uint32_t pstart[256];                  // start of the pixel's run in sorted[]
     int left[256];                         // slots left under the cap
     uint16_t take[256], nemit[256], ntot[256];
@@ -683,6 +684,7 @@ __global__ void __launch_bounds__(LIST_WARPS * 32) list_scatter_kernel(ListParam
         asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(q), "l"(pol_in));
         return v;
     };
+    for (int i = tid; i < LIST_WARPS * 256; i += LIST_WARPS * 32) (&sm.wmask[0][0])[i] = 0u;
     for (int r = blockIdx.x; r < p.n_ranges; r += gridDim.x) {
         const DecRange rg = p.ranges[r];
         const int n_words = rg.n_words, base = p.base[r], n_ls = p.rout[r].n_ls, npix = p.npix_per_roach;
@@ -714,7 +716,7 @@ __global__ void __launch_bounds__(LIST_WARPS * 32) list_scatter_kernel(ListParam
                 const int idx = warp * (LB_STEPS * 32) + s * 32 + lane;
                 x[s] = idx < rem ? ld_in(w + pos + idx) : 0ull;
             }
-            for (int i = tid; i < LIST_WARPS * 256; i += LIST_WARPS * 32) (&sm.wcnt[0][0])[i] = 0u;
+            for (int i = tid; i < LIST_WARPS * 256 / 2; i += LIST_WARPS * 32) reinterpret_cast<uint32_t *>(&sm.wcnt[0][0])[i] = 0u;
             if (tid == 0) sm.first_eos = LB_BLOCK;
             __syncthreads();
             unsigned fe = LB_BLOCK;
@@ -736,20 +738,17 @@ __global__ void __launch_bounds__(LIST_WARPS * 32) list_scatter_kernel(ListParam
                 const int idx = warp * (LB_STEPS * 32) + s * 32 + lane;
                 const uint32_t adr = (uint32_t)(x[s] >> 56);
                 const bool store = idx < n_here && (int)adr < npix;
-                // lanes of this step that hit the same pixel: eight ballots over the channel bits (MATCH.ANY runs on the
-                // ADU pipe at about one per 64 cycles per SM and bounded this kernel: 95 % ADU busy measured)
-                unsigned peers = __ballot_sync(0xffffffffu, store);
-#pragma unroll
-                for (int b = 0; b < 8; ++b) {
-                    const unsigned m = __ballot_sync(0xffffffffu, (adr >> b) & 1u);
-                    peers &= ((adr >> b) & 1u) ? m : ~m;
-                }
+                // lanes of this step that hit the same pixel, through shared memory: every lane sets its bit in the warp's
+                // mask of the pixel and reads the mask back (MATCH.ANY and VOTE both run on the ADU pipe - about 64 and 6
+                // cycles per SM each - and bounded this kernel: 95 % / 76 % ADU busy measured)
+                if (store) atomicOr(&sm.wmask[warp][adr], 1u << lane);
+                __syncwarp();
+                uint32_t peers = 0, old = 0;
+                if (store) { peers = sm.wmask[warp][adr]; old = sm.wcnt[warp][adr]; }
+                __syncwarp();
                 rk[s] = 0;
                 if (store) {
-                    const int leader = __ffs(peers) - 1;
-                    uint32_t old = 0;
-                    if (lane == leader) { old = sm.wcnt[warp][adr]; sm.wcnt[warp][adr] = old + __popc(peers); }
-                    old = __shfl_sync(peers, old, leader);
+                    if ((peers & lt) == 0u) { sm.wcnt[warp][adr] = (uint16_t)(old + __popc(peers)); sm.wmask[warp][adr] = 0u; }
                     rk[s] = old + __popc(peers & lt);
                     stored |= 1u << s;
                 }
@@ -759,7 +758,7 @@ __global__ void __launch_bounds__(LIST_WARPS * 32) list_scatter_kernel(ListParam
             {   // thread = pixel: scan over the warps, cap, scan over the pixels, sectors that can leave
                 uint32_t tot = 0;
 #pragma unroll
-                for (int q = 0; q < LIST_WARPS; ++q) { const uint32_t t = sm.wcnt[q][tid]; sm.wcnt[q][tid] = tot; tot += t; }
+                for (int q = 0; q < LIST_WARPS; ++q) { const uint32_t t = sm.wcnt[q][tid]; sm.wcnt[q][tid] = (uint16_t)tot; tot += t; }
                 const int l = sm.left[tid];
                 const uint32_t tk = min(tot, (uint32_t)l);
                 sm.left[tid] = l - (int)tk;
