@@ -543,43 +543,65 @@ struct ListParams {
     int *flag;                    // set to 2 if out_cap is too small
 };
 
+// The (row, second) entries of the ranges [rb, rb + 256) of one roach in stream order, seconds >= exptime left out:
+// built by the whole CTA (256 threads) so that the walks below are tight loops over shared memory
+struct RowEntries {
+    int row[256 * DEC_MAX_LS], sec[256 * DEC_MAX_LS];      // row = range * DEC_MAX_LS + local second
+    int n, wsum[8];
+};
+__device__ __forceinline__ void build_row_entries(const ListParams &p, int rb, int r1, RowEntries &E) {
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5, r = rb + t;
+    int nls = 0, base = 0;
+    if (r < r1) { nls = p.rout[r].n_ls; base = p.base[r]; }
+    const int cnt = max(0, min(nls, p.exptime - base));
+    int incl = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int a = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += a; }
+    if (lane == 31) E.wsum[warp] = incl;
+    __syncthreads();
+    int before = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) before += q < warp ? E.wsum[q] : 0;
+    int at = before + incl - cnt;
+    for (int ls = 0; ls < cnt; ++ls, ++at) { E.row[at] = r * DEC_MAX_LS + ls; E.sec[at] = base + ls; }
+    if (t == 255) E.n = before + incl;
+    __syncthreads();
+}
+
 __global__ void __launch_bounds__(256) list_rowstart_kernel(ListParams p) {
+    __shared__ RowEntries E;
     const int roach = blockIdx.x, ch = threadIdx.x;
     const int r0 = p.roach_first[roach], r1 = p.roach_first[roach + 1];
     const bool is_pix = ch < p.npix_per_roach;
     int cur_sec = -1, max_sec = -1;
     uint32_t run = 0;
     uint32_t *acc_col = p.acc + (size_t)roach * p.npix_per_roach + ch;
-    for (int rb = r0; rb < r1; rb += 8) {          // 8 ranges per round: their loads are independent of the running count
-        int nls[8], bs[8];
-        uint32_t v0[8];
+    uint32_t *col = p.rows + ch;
+    for (int rb = r0; rb < r1; rb += 256) {
+        build_row_entries(p, rb, r1, E);
+        const int n = E.n;
+        if (is_pix)
+            for (int e0 = 0; e0 < n; e0 += 16) {   // 16 entries per round: their loads are independent of the running count
+                uint32_t v[16];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = min(rb + i, r1 - 1);
-            nls[i] = p.rout[r].n_ls; bs[i] = p.base[r];
-            v0[i] = p.rows[((size_t)r * DEC_MAX_LS) * DEC_ROW + ch];
-        }
+                for (int i = 0; i < 16; ++i) v[i] = e0 + i < n ? col[(size_t)E.row[e0 + i] * DEC_ROW] : 0u;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = rb + i;
-            if (r >= r1) break;
-            for (int ls = 0; ls < nls[i]; ++ls) {
-                const int sec = bs[i] + ls;
-                uint32_t *cell = p.rows + ((size_t)r * DEC_MAX_LS + ls) * DEC_ROW + ch;
-                if (!is_pix || sec >= p.exptime) continue;
-                const uint32_t v = ls == 0 ? v0[i] : *cell;
-                if (sec != cur_sec) {              // seconds normally only grow along a roach stream: rare
-                    if (cur_sec >= 0) acc_col[(size_t)cur_sec * p.n_pix] = run;
-                    cur_sec = sec;
-                    // acc is zeroed before this kernel and this thread is the only writer of its column: a second
-                    // that was not visited yet needs no (dependent, ~1 us) read
-                    run = sec > max_sec ? 0u : acc_col[(size_t)sec * p.n_pix];
-                    max_sec = max(max_sec, sec);
+                for (int i = 0; i < 16; ++i) {
+                    if (e0 + i >= n) break;
+                    const int sec = E.sec[e0 + i];
+                    if (sec != cur_sec) {          // seconds normally only grow along a roach stream: rare
+                        if (cur_sec >= 0) acc_col[(size_t)cur_sec * p.n_pix] = run;
+                        cur_sec = sec;
+                        // acc is zeroed before this kernel and this thread is the only writer of its column: a second
+                        // that was not visited yet needs no (dependent, ~1 us) read
+                        run = sec > max_sec ? 0u : acc_col[(size_t)sec * p.n_pix];
+                        max_sec = max(max_sec, sec);
+                    }
+                    col[(size_t)E.row[e0 + i] * DEC_ROW] = run;
+                    run += v[i];
                 }
-                *cell = run;
-                run += v;
             }
-        }
+        __syncthreads();
     }
     if (is_pix && cur_sec >= 0) acc_col[(size_t)cur_sec * p.n_pix] = run;
 }
@@ -665,12 +687,12 @@ struct ListBlockSmem {
     long long dst[256];                    // list index of the first carried (else next) word of every pixel
     uint32_t wmask[LIST_WARPS][256];       // lanes of the current step that hit pixel p (zero between steps)
     uint16_t wcnt[LIST_WARPS][256];        // words of pixel p ranked by warp w -> words of pixel p in earlier warps
-    uint32_t pstart[256];                  // start of the pixel's run in sorted[]
     int left[256];                         // slots left under the cap
-    uint16_t take[256], nemit[256], ntot[256];
+    uint32_t slot[256];                    // packed for the scatter: (take << 16) | (pstart + ncarry)
+    long long outd[256];                   // packed for the copy-out: ((dst - pstart) << 12) | (pstart + nemit)
     unsigned char ncarry[256];
     uint32_t wsum[LIST_WARPS];
-    int first_eos;
+    int first_eos, total;
 };
 __global__ void __launch_bounds__(LIST_WARPS * 32) list_scatter_kernel(ListParams p) {
     __shared__ ListBlockSmem sm;
@@ -755,7 +777,8 @@ __global__ void __launch_bounds__(LIST_WARPS * 32) list_scatter_kernel(ListParam
                 __syncwarp();
             }
             __syncthreads();
-            {   // thread = pixel: scan over the warps, cap, scan over the pixels, sectors that can leave
+            uint32_t my_n, my_ne;   // thread = pixel: scan over the warps, cap, scan over the pixels, sectors that can leave
+            {
                 uint32_t tot = 0;
 #pragma unroll
                 for (int q = 0; q < LIST_WARPS; ++q) { const uint32_t t = sm.wcnt[q][tid]; sm.wcnt[q][tid] = (uint16_t)tot; tot += t; }
@@ -773,9 +796,11 @@ __global__ void __launch_bounds__(LIST_WARPS * 32) list_scatter_kernel(ListParam
                 for (int q = 0; q < LIST_WARPS; ++q) before += q < warp ? sm.wsum[q] : 0u;
                 const uint32_t ps = before + incl - n;
                 const long long d0 = sm.dst[tid], e_al = (d0 + n) & ~3ll;
-                sm.pstart[tid] = ps;
-                sm.take[tid] = (uint16_t)tk; sm.ntot[tid] = (uint16_t)n;
-                sm.nemit[tid] = (uint16_t)(e_al > d0 ? e_al - d0 : 0);
+                const uint32_t ne = (uint32_t)(e_al > d0 ? e_al - d0 : 0);
+                my_n = n; my_ne = ne;
+                if (tid == 255) sm.total = (int)(ps + n);
+                sm.slot[tid] = (tk << 16) | (ps + c);
+                sm.outd[tid] = ((d0 - (long long)ps) << 12) | (long long)(ps + ne);
                 for (uint32_t j = 0; j < c; ++j) sm.sorted[ps + j] = sm.carry[tid][j];
             }
             __syncthreads();
@@ -783,25 +808,26 @@ __global__ void __launch_bounds__(LIST_WARPS * 32) list_scatter_kernel(ListParam
             for (int s = 0; s < LB_STEPS; ++s) {
                 if ((stored >> s) & 1u) {
                     const uint32_t adr = (uint32_t)(x[s] >> 56);
-                    const uint32_t k = sm.wcnt[warp][adr] + rk[s];
-                    if (k < sm.take[adr]) sm.sorted[sm.pstart[adr] + sm.ncarry[adr] + k] = x[s];
+                    const uint32_t k = sm.wcnt[warp][adr] + rk[s], sl = sm.slot[adr];
+                    if (k < (sl >> 16)) sm.sorted[(sl & 0xFFFFu) + k] = x[s];
                 }
             }
             __syncthreads();
-            const int total = (int)(sm.pstart[255] + sm.ntot[255]);
+            const int total = sm.total;
             for (int i = tid; i < total; i += LIST_WARPS * 32) {
                 const uint64_t v = sm.sorted[i];
                 const uint32_t adr = (uint32_t)(v >> 56);
-                const uint32_t off = (uint32_t)i - sm.pstart[adr], ne = sm.nemit[adr];
-                if (off < ne) {
-                    const long long at = sm.dst[adr] + off;
+                const long long od = sm.outd[adr];
+                const int e_end = (int)(od & 0xFFF);             // first slot of the pixel's run that stays behind
+                if (i < e_end) {
+                    const long long at = (od >> 12) + i;
                     if (at < p.out_cap) p.out[at] = v;
                 } else {
-                    sm.carry[adr][off - ne] = v;
+                    sm.carry[adr][i - e_end] = v;
                 }
             }
             __syncthreads();
-            { const uint32_t n = sm.ntot[tid], ne = sm.nemit[tid]; sm.dst[tid] += ne; sm.ncarry[tid] = (unsigned char)(n - ne); }
+            sm.dst[tid] += my_ne; sm.ncarry[tid] = (unsigned char)(my_n - my_ne);
             pos += n_here;
             if (n_here == first_eos) {          // the end-of-second word at pos closes the local second
                 flush_carry();
@@ -842,45 +868,31 @@ __global__ void __launch_bounds__(256) merge_rangesum_kernel(ListParams p, uint3
 }
 
 __global__ void __launch_bounds__(256) merge_rowstart_kernel(ListParams p, uint32_t *rsum) {
-    __shared__ uint32_t s_v[256][DEC_MAX_LS];
-    __shared__ int s_nls[256], s_base[256];
+    __shared__ RowEntries E;
+    __shared__ uint32_t s_v[256 * DEC_MAX_LS];
     const int roach = blockIdx.x, t = threadIdx.x;
     const int r0 = p.roach_first[roach], r1 = p.roach_first[roach + 1];
-    int cur_sec = -1, max_sec = -1;                    // carried by thread 0 along the roach's stream
-    uint32_t run = 0;
     for (int rb = r0; rb < r1; rb += 256) {
-        const int r = rb + t;
-        if (r < r1) {
-            s_nls[t] = p.rout[r].n_ls; s_base[t] = p.base[r];
-#pragma unroll
-            for (int ls = 0; ls < DEC_MAX_LS; ++ls) s_v[t][ls] = rsum[(size_t)r * DEC_MAX_LS + ls];
-        }
+        build_row_entries(p, rb, r1, E);
+        const int n = E.n;
+        for (int e = t; e < n; e += 256) s_v[e] = rsum[E.row[e]];
         __syncthreads();
-        if (t == 0) {
-            const int n = min(256, r1 - rb);
-            for (int i = 0; i < n; ++i)
-                for (int ls = 0; ls < s_nls[i]; ++ls) {
-                    const int sec = s_base[i] + ls;
-                    if (sec >= p.exptime) continue;
-                    if (sec != cur_sec) {
-                        if (cur_sec >= 0) p.acc[(size_t)cur_sec * p.n_roaches + roach] = run;
-                        cur_sec = sec;
-                        run = sec > max_sec ? 0u : p.acc[(size_t)sec * p.n_roaches + roach];   // (see list_rowstart_kernel)
-                        max_sec = max(max_sec, sec);
-                    }
-                    const uint32_t v = s_v[i][ls];
-                    s_v[i][ls] = run;
-                    run += v;
-                }
-        }
-        __syncthreads();
-        if (r < r1) {
-#pragma unroll
-            for (int ls = 0; ls < DEC_MAX_LS; ++ls) rsum[(size_t)r * DEC_MAX_LS + ls] = s_v[t][ls];
+        // every entry sums the earlier entries of its second (at most 1024 entries: brute force over shared memory, all
+        // threads read the same entry at a time); acc carries the seconds from chunk to chunk
+        for (int e = t; e < n; e += 256) {
+            const int sec = E.sec[e];
+            uint32_t sum = p.acc[(size_t)sec * p.n_roaches + roach];
+            bool last = true;
+            for (int q = 0; q < n; ++q) {
+                const bool same = E.sec[q] == sec;
+                if (same && q < e) sum += s_v[q];
+                if (same && q > e) last = false;
+            }
+            rsum[E.row[e]] = sum;
+            if (last) p.acc[(size_t)sec * p.n_roaches + roach] = sum + s_v[e];
         }
         __syncthreads();
     }
-    if (t == 0 && cur_sec >= 0) p.acc[(size_t)cur_sec * p.n_roaches + roach] = run;
 }
 
 __global__ void __launch_bounds__(LIST_WARPS * 32) merge_scatter_kernel(ListParams p, const uint32_t *rsum) {
