@@ -130,12 +130,21 @@ int mkid_decode_words_dev(mkid_ctx *ctx, const uint64_t *words, int64_t n_words,
  * key = sec * n_pix + pixel, in arrival order inside a key, every key truncated to max_events - 1 entries (the cap
  * quirk); list_offsets int64 [exptime * n_pix + 1] holds the start of every key (last entry = total).  list_cap:
  * capacity of list_words in words (n_words always suffices).  counts_raw (uncapped) and stats are accumulated as in
- * mkid_decode_words.  Flat words only; a range of the input (>= 1024 words) may hold at most 4 end-of-second words.
+ * mkid_decode_words.  Flat words (wire format: mkid_decode_wire_lists); a range of the input (>= 1024 words) may hold at most 4 end-of-second words.
  * Synchronises. */
 int mkid_decode_lists(mkid_ctx *ctx, const uint64_t *words, int64_t n_words, const int64_t *seg_offset,
                       const int32_t *seg_roach, const int32_t *seg_sec, int32_t *seg_sec_out, int32_t n_segments,
                       const mkid_decode_cfg *cfg, uint32_t *counts_raw, uint64_t *list_words, int64_t list_cap,
                       int64_t *list_offsets, mkid_decode_stats *stats);
+
+/* mkid_decode_lists (merged == 0) or mkid_decode_merged (merged != 0) on the wire format PacketMaster receives
+ * (PulseServer bundles, PulseServer.c:318-352; segments in whole bundles as in mkid_decode_wire): the photon lists of
+ * PacketMaster.c:371-380 straight from the socket buffers.  list_words are host-order u64 (`packet` of
+ * PacketMaster.c:305); list_cap = 8192 * n_bundles always suffices. */
+int mkid_decode_wire_lists(mkid_ctx *ctx, const uint32_t *wire, int64_t n_bundles, const int64_t *seg_offset,
+                           const int32_t *seg_roach, const int32_t *seg_sec, int32_t *seg_sec_out, int32_t n_segments,
+                           const mkid_decode_cfg *cfg, uint32_t *counts_raw, int32_t merged, uint64_t *list_words,
+                           int64_t list_cap, int64_t *list_offsets, mkid_decode_stats *stats);
 
 /* The time-ordered merged photon list of a readout (what PacketMaster's per-second flush
  * PacketMaster.c:316-342 hands on, without the per-pixel split): every valid pixel word of the seconds < exptime,

@@ -80,6 +80,8 @@ _SIGNATURES = {
                                     POINTER(DecodeCfg), c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     'mkid_decode_merged': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                      POINTER(DecodeCfg), c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'mkid_decode_wire_lists': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                         POINTER(DecodeCfg), c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
     'mkid_decode_wire': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                    POINTER(DecodeCfg), c_void_p, c_void_p, c_void_p]),
     'mkid_counts_cap': (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_int32]),

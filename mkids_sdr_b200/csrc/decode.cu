@@ -530,6 +530,7 @@ __global__ void __launch_bounds__(256) decode_commit_kernel(DecParams p) {
 //                         memory (stable) and stores word -> out[offsets[key] + rank] as whole sectors
 struct ListParams {
     const uint64_t *words;
+    const uint32_t *wire;         // wire format (PulseServer bundles) instead of words
     const DecRange *ranges;
     const DecRangeOut *rout;
     const int32_t *base, *eos_tot;
@@ -672,6 +673,24 @@ __global__ void __launch_bounds__(1024) list_offsets_kernel(ListParams p, const 
     for (int k = 0; k < 4; ++k) { if (i + k < n) p.offsets[i + k] = run; run += v[k]; }
 }
 
+// word `pos` of a range, host order; wire format: low and high halves sit in 4096-word blocks of big-endian u32
+// (PulseServer.c:318-352), rg.start counts such blocks
+template <bool WIRE>
+__device__ __forceinline__ uint64_t list_load_word(const ListParams &p, const DecRange &rg, int pos, uint64_t pol_in) {
+    if (WIRE) {
+        const long long hc = rg.start + (pos >> 12);
+        const uint32_t *lp = p.wire + (size_t)(hc >> 1) * (2 * DEC_BUNDLE) + (size_t)(hc & 1) * DEC_CHUNK + (pos & 4095);
+        uint32_t lo, hi;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(lo) : "l"(lp), "l"(pol_in));
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b32 %0, [%1], %2;" : "=r"(hi) : "l"(lp + DEC_BUNDLE), "l"(pol_in));
+        return (uint64_t)bswap32(hi) << 32 | bswap32(lo);
+    } else {
+        uint64_t v;
+        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(p.words + rg.start + pos), "l"(pol_in));
+        return v;
+    }
+}
+
 // One CTA per range re-reads its words in blocks of 2048 and sorts every block by pixel in shared memory, stably
 // (arrival order inside a pixel): warp w ranks words [256 w, 256 w + 256) of the block step by step (lane masks of
 // the 32 words of a step + the warp's own running count per pixel), the counts of the warps are scanned per pixel and
@@ -694,6 +713,7 @@ struct ListBlockSmem {
     uint32_t wsum[LIST_WARPS];
     int first_eos, total;
 };
+template <bool WIRE>
 __global__ void __launch_bounds__(LIST_WARPS * 32) list_scatter_kernel(ListParams p) {
     __shared__ ListBlockSmem sm;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -701,16 +721,10 @@ __global__ void __launch_bounds__(LIST_WARPS * 32) list_scatter_kernel(ListParam
     const unsigned lt = (1u << lane) - 1u;
     uint64_t pol_in;           // the input streams through L2 (evict first)
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_in));
-    auto ld_in = [&](const uint64_t *q) -> uint64_t {
-        uint64_t v;
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(q), "l"(pol_in));
-        return v;
-    };
     for (int i = tid; i < LIST_WARPS * 256; i += LIST_WARPS * 32) (&sm.wmask[0][0])[i] = 0u;
     for (int r = blockIdx.x; r < p.n_ranges; r += gridDim.x) {
         const DecRange rg = p.ranges[r];
         const int n_words = rg.n_words, base = p.base[r], n_ls = p.rout[r].n_ls, npix = p.npix_per_roach;
-        const uint64_t *w = p.words + rg.start;
         int ls = 0, pos = 0;
         auto open_second = [&]() {              // thread = pixel: slots of local second ls (nothing is stored beyond exptime)
             const int sec = base + ls;
@@ -736,7 +750,7 @@ __global__ void __launch_bounds__(LIST_WARPS * 32) list_scatter_kernel(ListParam
 #pragma unroll
             for (int s = 0; s < LB_STEPS; ++s) {
                 const int idx = warp * (LB_STEPS * 32) + s * 32 + lane;
-                x[s] = idx < rem ? ld_in(w + pos + idx) : 0ull;
+                x[s] = idx < rem ? list_load_word<WIRE>(p, rg, pos + idx, pol_in) : 0ull;
             }
             for (int i = tid; i < LIST_WARPS * 256 / 2; i += LIST_WARPS * 32) reinterpret_cast<uint32_t *>(&sm.wcnt[0][0])[i] = 0u;
             if (tid == 0) sm.first_eos = LB_BLOCK;
@@ -829,7 +843,7 @@ __global__ void __launch_bounds__(LIST_WARPS * 32) list_scatter_kernel(ListParam
             __syncthreads();
             sm.dst[tid] += my_ne; sm.ncarry[tid] = (unsigned char)(my_n - my_ne);
             pos += n_here;
-            if (n_here == first_eos) {          // the end-of-second word at pos closes the local second
+            if (first_eos < LB_BLOCK) {         // the end-of-second word at pos closes the local second
                 flush_carry();
                 ++ls; ++pos;
                 open_second();
@@ -895,21 +909,16 @@ __global__ void __launch_bounds__(256) merge_rowstart_kernel(ListParams p, uint3
     }
 }
 
+template <bool WIRE>
 __global__ void __launch_bounds__(LIST_WARPS * 32) merge_scatter_kernel(ListParams p, const uint32_t *rsum) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (*p.flag & 2) return;
     const unsigned lt = (1u << lane) - 1u;
     uint64_t pol_in;
     asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_in));
-    auto ld_in = [&](const uint64_t *q) -> uint64_t {
-        uint64_t v;
-        asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.b64 %0, [%1], %2;" : "=l"(v) : "l"(q), "l"(pol_in));
-        return v;
-    };
     for (int r = blockIdx.x * LIST_WARPS + warp; r < p.n_ranges; r += gridDim.x * LIST_WARPS) {
         const DecRange rg = p.ranges[r];
         const int n_words = rg.n_words, base = p.base[r], n_ls = p.rout[r].n_ls, npix = p.npix_per_roach;
-        const uint64_t *w = p.words + rg.start;
         int ls = 0;
         auto open_second = [&]() -> long long {        // next output index of local second ls, -1: nothing is stored
             const int sec = base + ls;
@@ -920,14 +929,14 @@ __global__ void __launch_bounds__(LIST_WARPS * 32) merge_scatter_kernel(ListPara
         constexpr int LR = 8;
         uint64_t ring[LR];
 #pragma unroll
-        for (int g = 0; g < LR; ++g) ring[g] = g * 32 + lane < n_words ? ld_in(w + g * 32 + lane) : 0ull;
+        for (int g = 0; g < LR; ++g) ring[g] = g * 32 + lane < n_words ? list_load_word<WIRE>(p, rg, g * 32 + lane, pol_in) : 0ull;
         for (int pos0 = 0; pos0 < n_words; pos0 += 32 * LR) {
 #pragma unroll
             for (int g = 0; g < LR; ++g) {
                 const int pos = pos0 + g * 32;
                 if (pos >= n_words) break;
                 const uint64_t x = ring[g];
-                if (pos + 32 * LR + lane < n_words) ring[g] = ld_in(w + pos + 32 * LR + lane);
+                if (pos + 32 * LR + lane < n_words) ring[g] = list_load_word<WIRE>(p, rg, pos + 32 * LR + lane, pol_in);
                 const bool valid = pos + lane < n_words;
                 const uint32_t adr = (uint32_t)(x >> 56);
                 unsigned eos = __ballot_sync(0xffffffffu, valid && adr == 255u);
@@ -1218,7 +1227,7 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
             if ((rc = mkid_stage_out(ctx, lists->list_words, (size_t)lists->list_cap * 8, SCR_OUT2, false, &d_lw))) return rc;
             if ((rc = mkid_stage_out(ctx, lists->list_offsets, (n_keys + 1) * 8, SCR_OUT3, false, &d_lo))) return rc;
             ListParams lp;
-            lp.words = p.words; lp.ranges = d_ranges; lp.rout = d_rout; lp.base = d_base; lp.eos_tot = d_eos; lp.roach_first = d_rf;
+            lp.words = p.words; lp.wire = p.wire; lp.ranges = d_ranges; lp.rout = d_rout; lp.base = d_base; lp.eos_tot = d_eos; lp.roach_first = d_rf;
             lp.rows = d_rows; lp.acc = d_acc; lp.offsets = (long long *)d_lo; lp.out = (uint64_t *)d_lw; lp.out_cap = lists->list_cap;
             lp.n_ranges = n_ranges; lp.n_roaches = cfg->n_roaches; lp.n_pix = (int)n_pix; lp.npix_per_roach = cfg->npix_per_roach;
             lp.exptime = cfg->exptime; lp.cap = cfg->max_events - 1; lp.flag = d_flag;
@@ -1251,9 +1260,12 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
             MKID_CHECK_LAUNCH(ctx);
             lmark(2);
             if (lists->by_roach) {
-                merge_scatter_kernel<<<(n_ranges + LIST_WARPS - 1) / LIST_WARPS, LIST_WARPS * 32, 0, ctx->stream>>>(lp, d_rsum);
+                const int mgrid = (n_ranges + LIST_WARPS - 1) / LIST_WARPS;
+                if (wire_fmt) merge_scatter_kernel<true><<<mgrid, LIST_WARPS * 32, 0, ctx->stream>>>(lp, d_rsum);
+                else merge_scatter_kernel<false><<<mgrid, LIST_WARPS * 32, 0, ctx->stream>>>(lp, d_rsum);
             } else {
-                list_scatter_kernel<<<n_ranges, LIST_WARPS * 32, 0, ctx->stream>>>(lp);
+                if (wire_fmt) list_scatter_kernel<true><<<n_ranges, LIST_WARPS * 32, 0, ctx->stream>>>(lp);
+                else list_scatter_kernel<false><<<n_ranges, LIST_WARPS * 32, 0, ctx->stream>>>(lp);
             }
             MKID_CHECK_LAUNCH(ctx);
             lmark(3);
@@ -1365,6 +1377,18 @@ extern "C" int mkid_decode_merged(mkid_ctx *ctx, const uint64_t *words, int64_t 
     MKID_REQUIRE(ctx, (words || n_words == 0) && list_words && list_offsets && list_cap > 0 && cfg, "decode_merged: NULL argument");
     ListRequest lr{list_words, list_cap, list_offsets, true};
     return decode_common(ctx, words, nullptr, n_words, seg_offset, nullptr, seg_roach, seg_sec, seg_sec_out, n_segments, cfg,
+                         counts_raw, nullptr, stats, nullptr, nullptr, nullptr, &lr);
+}
+
+extern "C" int mkid_decode_wire_lists(mkid_ctx *ctx, const uint32_t *wire, int64_t n_bundles, const int64_t *seg_offset,
+                                      const int32_t *seg_roach, const int32_t *seg_sec, int32_t *seg_sec_out, int32_t n_segments,
+                                      const mkid_decode_cfg *cfg, uint32_t *counts_raw, int32_t merged, uint64_t *list_words,
+                                      int64_t list_cap, int64_t *list_offsets, mkid_decode_stats *stats) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, wire && list_words && list_offsets && list_cap > 0 && cfg && (merged || cfg->max_events >= 2),
+                 "decode_wire_lists: NULL argument");
+    ListRequest lr{list_words, list_cap, list_offsets, merged != 0};
+    return decode_common(ctx, nullptr, wire, n_bundles, seg_offset, nullptr, seg_roach, seg_sec, seg_sec_out, n_segments, cfg,
                          counts_raw, nullptr, stats, nullptr, nullptr, nullptr, &lr);
 }
 

@@ -142,6 +142,24 @@ class PhotonDecoder:
                                           _lib.ptr(lw), lw.size, _lib.ptr(lo), ctypes.addressof(self.stats)))
         return lw[:int(lo[-1])], lo, sec_out
 
+    def decode_wire_lists(self, wire, seg_offset, seg_roach, seg_sec=None, n_bundles=None, merged=False):
+        """decode_lists (merged=False) or decode_merged (merged=True) on PulseServer bundles (bytes / u8 / u32 array,
+        host or device; segments in whole bundles): PacketMaster's photon lists straight from the socket buffers."""
+        if isinstance(wire, (bytes, bytearray, memoryview)):
+            wire = np.frombuffer(wire, dtype=np.uint8)
+        off, roach, sec = _seg_arrays(seg_offset, seg_roach, seg_sec)
+        if n_bundles is None:
+            n_bundles = int(off[-1])
+        sec_out = np.zeros(roach.size, dtype=np.int32)
+        lw = np.empty(max(n_bundles * 8192, 1), dtype=np.uint64)
+        lo = np.empty(self.exptime * (self.cfg.n_roaches if merged else self.n_pix) + 1, dtype=np.int64)
+        c = self.ctx
+        c._check(c.lib.mkid_decode_wire_lists(c.h, _lib.ptr(wire), n_bundles, _lib.ptr(off), _lib.ptr(roach), _lib.ptr(sec),
+                                              _lib.ptr(sec_out), roach.size, ctypes.byref(self.cfg), _lib.ptr(self.counts_dev),
+                                              1 if merged else 0, _lib.ptr(lw), lw.size, _lib.ptr(lo),
+                                              ctypes.addressof(self.stats)))
+        return lw[:int(lo[-1])], lo, sec_out
+
     def decode_wire(self, wire, seg_offset, seg_roach, seg_sec=None, n_bundles=None, want_stats=True, want_sec=True):
         """wire: PulseServer bundles (bytes / u8 / u32 array, host or device)."""
         if isinstance(wire, (bytes, bytearray, memoryview)):

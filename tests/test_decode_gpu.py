@@ -247,6 +247,49 @@ def test_merged_photon_list(ctx):
     assert lw3.size == 0 and not lo3.any()
 
 
+def test_lists_long_ranges(ctx):
+    """Ranges of several 2048-word sort blocks (the range table only grows beyond one block above ~1e7 words): lists
+    and merged list of 2.4e7 words against the oracle."""
+    from mkids_sdr_b200 import synth
+    from mkids_sdr_b200.decode import PhotonDecoder
+    R, npix, secs, cap = 8, 253, 10, 2500
+    streams, _ = synth.photon_streams(24 * 10 ** 6, R, npix, secs, seed=77, n_hot=5, hot_rate=3000)
+    off = np.concatenate([[0], np.cumsum([len(s) for s in streams])])
+    words = ctx.to_device(np.concatenate(streams))
+    ref = odec.packetmaster_bin(streams, npix, secs, cap, want_lists=True)
+    dec = PhotonDecoder(R, npix, secs, cap, None, 0, ctx=ctx)
+    lw, lo, _ = dec.decode_lists(words, off, np.arange(R), n_words=int(off[-1]))
+    assert np.array_equal(lo, ref['list_offsets'])
+    assert np.array_equal(lw, ref['list_words'])
+    dec2 = PhotonDecoder(R, npix, secs, cap, None, 0, ctx=ctx)
+    mw, mo, _ = dec2.decode_merged(words, off, np.arange(R), n_words=int(off[-1]))
+    ref_w, ref_o = odec.merged_list(streams, npix, secs)
+    assert np.array_equal(mo, ref_o) and np.array_equal(mw, ref_w)
+    words.free()
+
+
+def test_lists_from_wire_bundles(ctx):
+    """Per-pixel lists and the merged list straight from PulseServer bundles equal those of the flat streams (the
+    channel-254 filler that pads the last bundle is a non-pixel word)."""
+    from mkids_sdr_b200 import synth
+    from mkids_sdr_b200.decode import PhotonDecoder
+    R, npix, secs, cap = 4, 253, 3, 2500
+    streams, _ = synth.photon_streams(500000, R, npix, secs, seed=21, n_hot=2, hot_rate=3000)
+    wire = synth.streams_to_wire(streams)
+    nb = [w.size // 65536 for w in wire]
+    off = np.concatenate([[0], np.cumsum(nb)])
+    allw = np.concatenate(wire)
+    ref = odec.packetmaster_bin(streams, npix, secs, cap, want_lists=True)
+    dec = PhotonDecoder(R, npix, secs, cap, None, 0, ctx=ctx)
+    lw, lo, _ = dec.decode_wire_lists(allw, off, np.arange(R))
+    assert np.array_equal(lo, ref['list_offsets']) and np.array_equal(lw, ref['list_words'])
+    assert np.array_equal(dec.counts_raw(), ref['raw_counts'])
+    dec2 = PhotonDecoder(R, npix, secs, cap, None, 0, ctx=ctx)
+    mw, mo, _ = dec2.decode_wire_lists(allw, off, np.arange(R), merged=True)
+    ref_w, ref_o = odec.merged_list(streams, npix, secs)
+    assert np.array_equal(mo, ref_o) and np.array_equal(mw, ref_w)
+
+
 def test_dashboard_make_image_matches_reference_run(ctx, golden_dir):
     """decode.Dashboard (mkid_dashboard_image + the twin of make_image's bookkeeping) against the reference's own
     StartQt4.make_image (ArconsDashboard.py:633-723) executed in the dev container over 7 seconds: sky taking, sky
