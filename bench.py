@@ -552,7 +552,7 @@ def lut_side_bench(ctx):
     f = (k % N) * FS / N
     amps = 10 ** (-(np.random.default_rng(1).integers(0, 20, T)) / 20.)
     out = {}
-    for batch in (1, 8, 64):
+    for batch in (1, 8, 64, 512):                  # batch sizes 1, 8, 64, 512
         ff = np.tile(f, (batch, 1)); aa = np.tile(amps, (batch, 1))
         for where in ('host', 'device'):
             kw = {}

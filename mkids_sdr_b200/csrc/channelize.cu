@@ -485,29 +485,31 @@ __global__ void __launch_bounds__(256) candidates_kernel(const int16_t *__restri
     }
 }
 
-// K5a: greedy hold-off per channel (sequential in time per channel).  One CTA per 32 channels: all 8 warps
-// stream the CTA's 128-byte wide column of the candidate mask through a double-buffered shared-memory tile
-// (cp.async, 16 B per copy) and reduce it to one "word is non-zero" bit per (channel, word).  Four lanes of
-// every warp then walk their channel's non-zero words only: the per-trigger chain "next candidate at or after
-// the end of the dead time" runs at shared-memory latency and skips the dead time in one step.
-constexpr int RES_TW = 128;                           // mask words (x 32 rows) per tile
+// K5a: greedy hold-off per channel (sequential in time per channel).  One CTA per 8 channels (256 CTAs for 8 boards):
+// all 8 warps stream the CTA's 32-byte wide column of the candidate mask through a double-buffered shared-memory
+// tile of 512 mask words (cp.async, 16 B per copy; a batch of 2^16 rows is 4 tiles, so the walk costs 4 memory round
+// trips) and reduce it to one "word is non-zero" bit per (channel, word).  Lane 0 of warp w then walks the non-zero
+// words of channel w only: the per-trigger chain "next candidate at or after the end of the dead time" runs at
+// shared-memory latency and skips the dead time in one step.
+constexpr int RES_CH = 8;                             // channels per CTA (= warps)
+constexpr int RES_TW = 512;                           // mask words (x 32 rows) per tile
 __global__ void __launch_bounds__(256) resolve_kernel(const uint32_t *__restrict__ mask, int64_t rows, int64_t r_lo,
                                                       int64_t r_hi, int64_t t_abs0, int L, int Lw, int n_win,
                                                       int64_t *t_next, uint32_t *acc, uint32_t *win_cnt) {
-    __shared__ __align__(16) uint32_t tile[2][RES_TW][32];
-    __shared__ __align__(16) uint16_t summ[32][8];    // per channel: 128 non-zero flags of the current tile
+    __shared__ __align__(16) uint32_t tile[2][RES_TW][RES_CH];
+    __shared__ __align__(16) uint16_t summ[RES_CH][RES_TW / 16];   // per channel: non-zero flags of the current tile
     const int board = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int c0 = blockIdx.x * 32;
+    const int c0 = blockIdx.x * RES_CH;
     const int64_t n_groups = (rows + 31) >> 5;
     const uint32_t *mk = mask + (size_t)board * n_groups * NCH + c0;
     uint32_t *ac = acc + (size_t)board * n_win * NCH;
     uint32_t *wc = win_cnt + (size_t)board * (n_win + 1);
     const int g_lo = (int)(r_lo >> 5), g_hi = (int)((r_hi + 31) >> 5);
     const int n_tiles = (g_hi - g_lo + RES_TW - 1) / RES_TW;
-    auto prefetch = [&](int k) {                       // tile k -> buffer k & 1: RES_TW rows of 8 x 16 B
+    auto prefetch = [&](int k) {                       // tile k -> buffer k & 1: RES_TW rows of 2 x 16 B
         const int g0 = g_lo + k * RES_TW;
-        for (int i = tid; i < RES_TW * 8; i += 256) {
-            const int u = i >> 3, q = i & 7;
+        for (int i = tid; i < RES_TW * 2; i += 256) {
+            const int u = i >> 1, q = i & 1;
             if (g0 + u < g_hi) {
                 const uint32_t dst = mk_smem_u32(&tile[k & 1][u][q * 4]);
                 const uint32_t *src = mk + (size_t)(g0 + u) * NCH + q * 4;
@@ -518,13 +520,14 @@ __global__ void __launch_bounds__(256) resolve_kernel(const uint32_t *__restrict
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    // resolver lanes: lane l < 4 of warp w owns channel c0 + 4*w + l.  Rows are 32-bit inside a call.
-    const bool resolver = lane < 4;
-    const int cl = warp * 4 + lane;                    // channel inside the CTA (resolver lanes)
+    // resolver lanes: lane 0 of warp w owns channel c0 + w.  Rows are 32-bit inside a call.
+    const bool resolver = lane == 0;
+    const int cl = warp;                               // channel inside the CTA (resolver lanes)
     const int c = c0 + cl;
     const int rlo = (int)r_lo, rhi = (int)r_hi;
     int64_t tn = 0;
     int lo = rlo;                                      // first row this channel may trigger on
+    int last_r = -1, wi = 0, w_end = rlo + Lw;         // last trigger of this call, window of the next one
     auto first_allowed = [&]() -> int {
         const int64_t t_min = tn > T_START ? tn : (int64_t)T_START;   // hold-off from earlier calls, start-up guard
         const int64_t r = t_min - t_abs0;
@@ -537,51 +540,46 @@ __global__ void __launch_bounds__(256) resolve_kernel(const uint32_t *__restrict
         else asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 1;" ::: "memory");
         __syncthreads();
-        const uint32_t(*t)[32] = tile[k & 1];
-        {   // non-zero flags: warp w covers words 16w .. 16w+15, lane = channel
+        uint32_t(*t)[RES_CH] = tile[k & 1];
+        {   // non-zero flags: thread = (channel, group of 16 words)
+            const int ch = tid & (RES_CH - 1), grp = tid >> 3;
             uint32_t part = 0;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) part |= (t[warp * 16 + i][lane] != 0u ? 1u : 0u) << i;
-            summ[lane][warp] = (uint16_t)part;
+            for (int i = 0; i < 16; ++i) part |= (t[grp * 16 + i][ch] != 0u ? 1u : 0u) << i;
+            summ[ch][grp] = (uint16_t)part;
         }
         __syncthreads();
         const int g0 = g_lo + k * RES_TW;
         if (resolver && lo < ((g0 + RES_TW) << 5)) {   // (else: the whole tile lies in this channel's dead time)
-            uint4 sv = *reinterpret_cast<const uint4 *>(&summ[cl][0]);
-            uint32_t sw[4] = {sv.x, sv.y, sv.z, sv.w};
+            uint32_t *sw = reinterpret_cast<uint32_t *>(&summ[cl][0]);     // RES_TW / 32 words of flags, only this lane's
+            // the chain below is serial per channel (about 40 rounds per 2^16 rows): 32-bit rows, no division
             for (;;) {
-                // drop the words that end before lo
-                const int u_min = (lo >> 5) - g0;
+                // first non-zero word that does not end before lo
+                const int u_min = max((lo >> 5) - g0, 0);
                 if (u_min >= RES_TW) break;
-                if (u_min > 0) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int sh = u_min - 32 * j;
-                        if (sh >= 32) sw[j] = 0u;
-                        else if (sh > 0) sw[j] &= 0xFFFFFFFFu << sh;
-                    }
-                }
                 int u = -1;
-#pragma unroll
-                for (int j = 3; j >= 0; --j)
-                    if (sw[j]) u = 32 * j + __ffs(sw[j]) - 1;
+                for (int j = u_min >> 5; j < RES_TW / 32; ++j) {
+                    uint32_t v = sw[j];
+                    if (j == (u_min >> 5)) v &= 0xFFFFFFFFu << (u_min & 31);
+                    if (v) { u = 32 * j + __ffs(v) - 1; break; }
+                }
                 if (u < 0) break;
-                sw[u >> 5] &= ~(1u << (u & 31));
                 uint32_t w = t[u][cl];
                 const int r_base = (g0 + u) << 5;
                 if (lo > r_base) w &= 0xFFFFFFFFu << (lo - r_base);          // lo - r_base < 32 here
                 if (r_base + 32 > rhi) { const int keep = rhi - r_base; w = keep <= 0 ? 0u : (w & (0xFFFFFFFFu >> (32 - keep))); }
-                if (!w) continue;
+                if (!w) { lo = max(lo, r_base + 32); continue; }
                 const int r = r_base + (__ffs(w) - 1);
-                tn = t_abs0 + r + L;                     // hold-off: L >= 32, so the next trigger is in a later word
-                const int wi = (int)((unsigned)(r - rlo) / (unsigned)Lw);
+                last_r = r;
+                while (r >= w_end) { ++wi; w_end += Lw; }                    // window of the trigger (rows only grow)
                 ac[(size_t)wi * NCH + c] = (uint32_t)(r + 1);
                 atomicAdd(&wc[wi], 1u);
-                lo = first_allowed();
+                lo = min(r + L, rhi);                    // hold-off: L >= 32, so the next trigger is in a later word
             }
         }
         __syncthreads();
     }
+    if (resolver && last_r >= 0) tn = t_abs0 + last_r + L;
     if (resolver) t_next[board * NCH + c] = tn;
 }
 
@@ -689,6 +687,90 @@ __global__ void __launch_bounds__(256) emit_kernel(const int16_t *__restrict__ p
             int rank = 0;
             for (int i = 0; i < n; ++i) rank += s_keys[i] < k;
             if ((int64_t)off + rank < words_cap) out[off + rank] = ~0ull;
+        }
+    }
+}
+
+// K5b for M <= 32 and W <= 32 (the defaults are 20 and 32): one WARP per photon word.  The per-thread version above
+// walks its M + W phase samples (one 32-byte sector each, 512 B apart) a few loads at a time; here the lanes of a warp
+// fetch the baseline rows and the peak window of a trigger in two instructions, two triggers per round, and reduce
+// with REDUX.  Same integer / double arithmetic, same word order.
+__global__ void __launch_bounds__(256) emit_warp_kernel(const int16_t *__restrict__ phase, int64_t rows,
+                                                        const uint32_t *__restrict__ acc, const uint32_t *__restrict__ win_off,
+                                                        int n_win, int64_t r_lo, int64_t r_hi, int64_t t_abs0, int M, int W,
+                                                        int Lw, uint64_t *words, int64_t words_cap) {
+    __shared__ uint32_t s_keys[NCH + 2];
+    __shared__ int s_n;
+    const int board = blockIdx.y, wi = blockIdx.x, c = threadIdx.x, lane = c & 31, warp = c >> 5;
+    const int16_t *ph = phase + (size_t)board * rows * NCH;
+    const uint32_t a = acc[((size_t)board * n_win + wi) * NCH + c];
+    const int64_t w_lo = r_lo + (int64_t)wi * Lw;          // first row of the window
+    if (c == 0) s_n = 0;
+    __syncthreads();
+    if (a) s_keys[atomicAdd(&s_n, 1)] = ((uint32_t)((int64_t)a - 1 - w_lo) << 9) | (uint32_t)(c + 1);
+    if (c == 0) {                                          // end-of-second event inside this window?
+        const int64_t ta = t_abs0 + w_lo;
+        const int64_t tb = min(t_abs0 + w_lo + Lw, t_abs0 + r_hi);
+        const int64_t B = ta <= 0 ? SEC_US : ((ta + SEC_US - 1) / SEC_US) * SEC_US;
+        if (B < tb) s_keys[atomicAdd(&s_n, 1)] = ((uint32_t)(B - ta) << 9);          // channel field 0: before all channels
+    }
+    __syncthreads();
+    const int n = s_n;
+    const uint32_t off = win_off[(size_t)board * (n_win + 1) + wi];
+    uint64_t *out = words + (size_t)board * words_cap;
+    for (int i0 = warp; i0 < n; i0 += 16) {
+        uint32_t key[2];
+        int vb[2], vw[2], ve[2];
+        bool live[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {                      // all loads of both triggers first
+            const int i = i0 + 8 * u;
+            live[u] = i < n;
+            key[u] = live[u] ? s_keys[i] : 0u;
+            const int ch = (int)(key[u] & 0x1FFu) - 1;
+            vb[u] = 0; vw[u] = 0; ve[u] = 0;
+            if (live[u] && ch >= 0) {
+                const int16_t *q = ph + (w_lo + (int64_t)(key[u] >> 9)) * NCH + ch;
+                if (lane < M) vb[u] = q[-(int64_t)(1 + lane) * NCH];
+                if (lane < W) vw[u] = q[(int64_t)lane * NCH];
+                if (lane == 0) ve[u] = q[(int64_t)W * NCH];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!live[u]) continue;                         // (warp-uniform)
+            const uint32_t k = key[u];
+            int rank = 0;
+            for (int q = lane; q < n; q += 32) rank += s_keys[q] < k;
+            rank = __reduce_add_sync(0xffffffffu, rank);
+            const int ch = (int)(k & 0x1FFu) - 1;
+            if (ch < 0) {                                   // the end-of-second word
+                if (lane == 0 && (int64_t)off + rank < words_cap) out[off + rank] = ~0ull;
+                continue;
+            }
+            const int S = __reduce_add_sync(0xffffffffu, vb[u]);
+            // minimum of the window, first occurrence: (value, index) packed
+            unsigned mk = lane < W ? ((unsigned)(vw[u] + 32768) << 5) | (unsigned)lane : 0xFFFFFFFFu;
+            mk = __reduce_min_sync(0xffffffffu, mk);
+            const int j = (int)(mk & 31u), vmin = (int)(mk >> 5) - 32768;
+            const int w_prev = __shfl_sync(0xffffffffu, vw[u], (j + 31) & 31), w_next = __shfl_sync(0xffffffffu, vw[u], (j + 1) & 31);
+            const int b_first = __shfl_sync(0xffffffffu, vb[u], 0), e_last = __shfl_sync(0xffffffffu, ve[u], 0);
+            if (lane == 0) {
+                const double y1 = (double)(j >= 1 ? w_prev : b_first), y2 = (double)vmin, y3 = (double)(j + 1 < W ? w_next : e_last);
+                const double den = __dsub_rn(__dadd_rn(y3, y1), __dmul_rn(2.0, y2));
+                double y4 = y2;
+                if (den != 0.0) {
+                    const double dy = __dsub_rn(y3, y1);
+                    y4 = __dsub_rn(y2, __ddiv_rn(__dmul_rn(0.125, __dmul_rn(dy, dy)), den));
+                }
+                const int peak = (__double2int_rz(__dmul_rn(y4, 0.0625)) + 2048) & 0xFFF;
+                const int p1 = (vmin / 16 + 2048) & 0xFFF;
+                const int base = (S / (16 * M) + 2048) & 0xFFF;
+                const int64_t t = t_abs0 + w_lo + (int64_t)(k >> 9);
+                const uint32_t ts = (uint32_t)(t % SEC_US);
+                const uint64_t word = ((uint64_t)ch << 56) | ((uint64_t)peak << 44) | ((uint64_t)p1 << 32) | ((uint64_t)base << 20) | ts;
+                if ((int64_t)off + rank < words_cap) out[off + rank] = word;
+            }
         }
     }
 }
@@ -847,15 +929,19 @@ int run_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase_dev, int64_t r
         MKID_CHECK_LAUNCH(ctx);
     }
     g_timer.mark(ctx->stream, "memsets");
-    resolve_kernel<<<dim3(NCH / 32, B), 256, 0, ctx->stream>>>(ch->mask, rows, r_lo, r_hi, t_abs0, d.L, d.Lw, n_win,
+    resolve_kernel<<<dim3(NCH / RES_CH, B), 256, 0, ctx->stream>>>(ch->mask, rows, r_lo, r_hi, t_abs0, d.L, d.Lw, n_win,
                                                              d.t_next, ch->acc, ch->win_cnt);
     MKID_CHECK_LAUNCH(ctx);
     g_timer.mark(ctx->stream, "resolve");
     scan_kernel<<<B, 256, 0, ctx->stream>>>(ch->win_cnt, n_win, r_lo, r_hi, t_abs0, d.Lw, ch->n_words_dev);
     MKID_CHECK_LAUNCH(ctx);
     g_timer.mark(ctx->stream, "scan");
-    emit_kernel<<<dim3(n_win, B), 256, 0, ctx->stream>>>(phase_dev, rows, ch->acc, ch->win_cnt, n_win, r_lo, r_hi, t_abs0,
-                                                         d.M, d.W, d.Lw, words_dev, words_cap);
+    if (d.M >= 1 && d.M <= 32 && d.W >= 1 && d.W <= 32)
+        emit_warp_kernel<<<dim3(n_win, B), 256, 0, ctx->stream>>>(phase_dev, rows, ch->acc, ch->win_cnt, n_win, r_lo, r_hi,
+                                                                  t_abs0, d.M, d.W, d.Lw, words_dev, words_cap);
+    else
+        emit_kernel<<<dim3(n_win, B), 256, 0, ctx->stream>>>(phase_dev, rows, ch->acc, ch->win_cnt, n_win, r_lo, r_hi, t_abs0,
+                                                             d.M, d.W, d.Lw, words_dev, words_cap);
     MKID_CHECK_LAUNCH(ctx);
     g_timer.mark(ctx->stream, "emit");
     return MKID_OK;
