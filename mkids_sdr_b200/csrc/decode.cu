@@ -519,6 +519,77 @@ __global__ void __launch_bounds__(256) decode_commit_kernel(DecParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Short segments chained behind a producer on the same GPU (mkid_decode_words_dev: the per-board photon words of one
+// channelizer batch, ~10^4 words each): one CTA per segment does the whole job in ONE launch - block scan of the
+// end-of-second words for the second of every word, direct reductions into counts / hist, statistics, carried
+// second - instead of the three launches of the range machinery (45 us for 75 k words).
+struct DecSeg { long long start; int cap, roach; };
+constexpr int DEC_SMALL_MAX_WORDS = 1 << 18;           // total capacity up to which the dev entry point takes this path
+__global__ void __launch_bounds__(1024) decode_small_kernel(DecParams p, const DecSeg *segs) {
+    __shared__ int s_w[33];                              // exclusive end-of-second counts of the warps | chunk total
+    __shared__ unsigned long long s_st[5];
+    const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DecSeg sg = segs[seg];
+    const int len = max(0, min(sg.cap, p.seg_len_dev[seg]));
+    const uint64_t *w = p.words + sg.start;
+    const bool use_lut = p.bin_lut != nullptr, f_hi = p.field_shift >= 32;
+    const int f_sh = p.field_shift & 31, npix = p.npix_per_roach;
+    const unsigned lt = (1u << lane) - 1u;
+    if (tid < 5) s_st[tid] = 0;
+    int sec = p.seg_sec[seg];                            // second at the start of the chunk
+    unsigned n_eos = 0, n_bad = 0, n_nonpix = 0, n_ign = 0, n_valid = 0;
+    for (int base = 0; base < len; base += 1024) {
+        const int i = base + tid;
+        const bool valid = i < len;
+        const uint64_t x = valid ? w[i] : 0ull;
+        const uint32_t hi = (uint32_t)(x >> 32), lo = (uint32_t)x, adr = hi >> 24;
+        const bool is_eos = valid && adr == 255u;
+        const unsigned b = __ballot_sync(0xffffffffu, is_eos);
+        if (lane == 0) s_w[warp] = __popc(b);
+        __syncthreads();
+        if (warp == 0) {
+            const int v = s_w[lane];
+            int incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int a = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += a; }
+            s_w[lane] = incl - v;
+            if (lane == 31) s_w[32] = incl;
+        }
+        __syncthreads();
+        const int my_sec = sec + s_w[warp] + __popc(b & lt);           // end-of-second words before this one
+        sec += s_w[32];
+        if (valid) {
+            if (my_sec >= p.exptime) ++n_ign;
+            else if (is_eos) { ++n_eos; if (x != ~0ull) ++n_bad; }
+            else if ((int)adr >= npix) ++n_nonpix;
+            else {
+                ++n_valid;
+                const size_t pix = (size_t)sg.roach * npix + adr;
+                atomicAdd(&p.counts[(size_t)my_sec * p.n_pix + pix], 1u);
+                if (p.hist) {
+                    const uint32_t f = ((f_hi ? hi : lo) >> f_sh) & 0xFFFu;
+                    const uint32_t bin = use_lut ? p.bin_lut[f] : f;
+                    if ((int)bin < p.n_bins) atomicAdd(&p.hist[pix * p.n_bins + bin], 1u);
+                }
+            }
+        }
+        __syncthreads();                                 // s_w is rewritten by the next chunk
+    }
+    if (tid == 0 && p.seg_sec_out) p.seg_sec_out[seg] = sec;
+    n_eos = warp_sum(n_eos); n_bad = warp_sum(n_bad); n_nonpix = warp_sum(n_nonpix);
+    n_ign = warp_sum(n_ign); n_valid = warp_sum(n_valid);
+    if (lane == 0) {
+        if (n_eos) atomicAdd(&s_st[0], (unsigned long long)n_eos);
+        if (n_bad) atomicAdd(&s_st[1], (unsigned long long)n_bad);
+        if (n_nonpix) atomicAdd(&s_st[2], (unsigned long long)n_nonpix);
+        if (n_ign) atomicAdd(&s_st[3], (unsigned long long)n_ign);
+        if (n_valid) atomicAdd(&s_st[4], (unsigned long long)n_valid);
+    }
+    __syncthreads();
+    if (tid < 5 && s_st[tid]) atomicAdd(&p.stats[tid], s_st[tid]);
+}
+
+// ------------------------------------------------------------------------------------------------
 // Per-(second, pixel) photon lists: the product PacketMaster writes every second (photons[r][adr][plist],
 // PacketMaster.c:371-380, write_sec_data :1012-1016).  Key = sec * n_pix + pixel, arrival order inside a key,
 // each key truncated to max_events - 1 entries (the cap quirk).  Built from the rows of the relative pass:
@@ -1053,10 +1124,12 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
     std::vector<int32_t> sec0(n_seg, 0);
     if (seg_sec) for (int i = 0; i < n_seg; ++i) sec0[i] = seg_sec[i];
 
+    // short segments behind a producer on the same GPU: one launch (decode_small_kernel), a segment table instead of ranges
+    const bool small = seg_len_dev && !wire_fmt && !lists && n_units <= DEC_SMALL_MAX_WORDS && n_seg <= 65535;
     // the range table only depends on the segment table: rebuilt (and uploaded) when that changes
     std::vector<char> key(24 + (size_t)n_seg * 20);
     {
-        const int64_t head[3] = {wire_fmt ? 1 : 0, n_seg, n_units};
+        const int64_t head[3] = {wire_fmt ? 1 : (small ? 2 : 0), n_seg, n_units};
         memcpy(key.data(), head, 24);
         memcpy(key.data() + 24, seg_offset, (size_t)n_seg * 8);
         memcpy(key.data() + 24 + (size_t)n_seg * 8, seg_len.data(), (size_t)n_seg * 8);
@@ -1064,7 +1137,16 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
     }
     const bool same_table = key == ctx->dec_key;
     std::vector<DecRange> ranges;
-    if (!same_table) {
+    if (!same_table && small) {
+        std::vector<DecSeg> st(n_seg);
+        for (int i = 0; i < n_seg; ++i) {
+            MKID_REQUIRE(ctx, seg_len[i] <= 0x7FFFFFFF, "decode: segment too long");
+            st[i].start = seg_offset[i]; st[i].cap = (int)seg_len[i]; st[i].roach = seg_roach[i];
+        }
+        ctx->dec_ranges_host.assign((const char *)st.data(), (const char *)st.data() + st.size() * sizeof(DecSeg));
+        ctx->dec_ranges_dev = nullptr;
+        ctx->dec_key.swap(key);
+    } else if (!same_table) {
         const int64_t warps_total = (int64_t)ctx->num_sms * DEC_CTAS_PER_SM * DEC_WARPS;
         for (int i = 0; i < n_seg; ++i) {
             const int64_t nc = seg_chunks[i];
@@ -1093,7 +1175,7 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
         ctx->dec_ranges_dev = nullptr;          // forces the upload below
         ctx->dec_key.swap(key);
     }
-    const int n_ranges = (int)(ctx->dec_ranges_host.size() / sizeof(DecRange));
+    const int n_ranges = small ? 0 : (int)(ctx->dec_ranges_host.size() / sizeof(DecRange));
     // meta: stats (5 u64) | flag, pad | sec_out [n_seg] | sec [n_seg]
     const size_t meta_bytes = 48 + (size_t)n_seg * 8;
     char *meta = nullptr;
@@ -1136,6 +1218,26 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
         if (rc) return rc;
     }
 
+    if (small) {
+        DecSeg *d_segs;
+        if ((rc = dec_private(ctx, 1, ctx->dec_ranges_host.size(), (void **)&d_segs))) return rc;
+        if (ctx->dec_ranges_dev != d_segs) {
+            MKID_CUDA(ctx, cudaMemcpyAsync(d_segs, ctx->dec_ranges_host.data(), ctx->dec_ranges_host.size(), cudaMemcpyHostToDevice, ctx->stream));
+            MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            ctx->dec_ranges_dev = d_segs;
+        }
+        DecParams p;
+        memset(&p, 0, sizeof(p));
+        p.words = (const uint64_t *)d_in;
+        p.seg_sec = seg_sec_dev ? seg_sec_dev : d_sec; p.seg_sec_out = seg_sec_out_dev ? seg_sec_out_dev : d_sec_out;
+        p.seg_len_dev = seg_len_dev;
+        p.n_pix = (int)n_pix; p.npix_per_roach = cfg->npix_per_roach; p.exptime = cfg->exptime;
+        p.field_shift = want_hist ? cfg->hist_field_shift : 0; p.n_bins = want_hist ? cfg->n_bins : 0;
+        p.bin_lut = (const uint16_t *)d_lut; p.counts = (uint32_t *)d_counts; p.hist = (uint32_t *)d_hist;
+        p.stats = d_stats;
+        decode_small_kernel<<<n_seg, 1024, 0, ctx->stream>>>(p, d_segs);
+        MKID_CHECK_LAUNCH(ctx);
+    }
     if (n_ranges > 0) {
         DecRange *d_ranges; DecRangeOut *d_rout; uint32_t *d_rows;
         if ((rc = dec_private(ctx, 1, (size_t)n_ranges * sizeof(DecRange), (void **)&d_ranges))) return rc;

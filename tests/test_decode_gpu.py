@@ -90,6 +90,45 @@ def test_decode_piecewise_equals_whole(ctx):
     _check(dec, streams, npix, secs, cap)
 
 
+@pytest.mark.parametrize('scale', [1, 40])
+def test_decode_words_dev_segments(ctx, scale):
+    """The device-chained entry point (segment lengths and carried seconds in device memory): short segments take the
+    one-launch path (decode_small_kernel), long ones the range machinery; dense and corrupt end-of-second words,
+    non-pixel channels, capacity > length, seconds beyond exptime, two calls with carried seconds."""
+    from mkids_sdr_b200.decode import PhotonDecoder
+    R, npix, secs, cap_ev = 3, 37, 6, 2500
+    rng = np.random.default_rng(17)
+    streams = []
+    for r in range(R):
+        n = (3000 + 500 * r) * scale
+        st = odec.pack_word(rng.integers(0, npix + 3, n), rng.integers(0, 4096, n), rng.integers(0, 4096, n),
+                            rng.integers(0, 4096, n), np.sort(rng.integers(0, 10 ** 6, n)))
+        eos = rng.random(n) < (0.002 / scale)
+        st[eos] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        st[np.flatnonzero(eos)[1::5]] = np.uint64(0xFF00000000000123)          # corrupt end-of-second words
+        streams.append(st)
+    dec = PhotonDecoder(R, npix, secs, cap_ev, 'base', 4096, ctx=ctx)
+    seg_cap = np.array([len(s) + 777 for s in streams], dtype=np.int64)      # capacity > length
+    seg_start = np.concatenate([[0], np.cumsum(seg_cap)[:-1]]).astype(np.int64)
+    sec_a, sec_b = ctx.to_device(np.zeros(R, np.int32)), ctx.to_device(np.zeros(R, np.int32))
+    halves = [[s[:len(s) // 3] for s in streams], [s[len(s) // 3:] for s in streams]]
+    for part, (sin, sout) in zip(halves, ((sec_a, sec_b), (sec_b, sec_a))):
+        buf = np.full(int(seg_cap.sum()), 0x1234567812345678, dtype=np.uint64)   # junk beyond the lengths
+        for r in range(R):
+            buf[seg_start[r]:seg_start[r] + len(part[r])] = part[r]
+        dw = ctx.to_device(buf)
+        ln = ctx.to_device(np.array([len(x) for x in part], dtype=np.int32))
+        dec.decode_words_dev(dw, seg_start, seg_cap, ln, np.arange(R), sin, sout, buf.size)
+        ctx.sync()
+        dw.free(); ln.free()
+    ref = odec.packetmaster_bin(streams, npix, secs, cap_ev)
+    assert np.array_equal(dec.counts_raw(), ref['raw_counts'])
+    assert np.array_equal(dec.hist(), odec.pixel_field_hist(streams, npix, secs, 'base', None, 4096))
+    sec_out = sec_a.download(np.int32, R)
+    assert list(sec_out) == [int(((s >> np.uint64(56)) == 255).sum()) for s in streams]
+    assert ref['n_ignored'] > 0 and ref['n_corrupt_eos'] > 0
+
+
 def test_decode_wire_bundles(ctx):
     from mkids_sdr_b200 import synth
     from mkids_sdr_b200.decode import PhotonDecoder
