@@ -69,6 +69,7 @@ struct mkid_chan {
     uint32_t *mask = nullptr; size_t mask_bytes = 0;
     uint32_t *acc = nullptr; size_t acc_bytes = 0;
     uint32_t *win_cnt = nullptr; size_t win_bytes = 0;    // [B][n_win] counts then offsets
+    bool detect_clean = false;           // acc / win_cnt are all zero (the emit kernels clear what they consume)
     int32_t *n_words_dev = nullptr;
     int16_t *halo = nullptr; size_t halo_bytes = 0;
     uint64_t *words_dev = nullptr; size_t words_bytes = 0;
@@ -621,7 +622,7 @@ __global__ void __launch_bounds__(256) scan_kernel(uint32_t *win_cnt, int n_win,
 
 // K5b: build the photon words of one window and write them in (time, channel) order.
 __global__ void __launch_bounds__(256) emit_kernel(const int16_t *__restrict__ phase, int64_t rows,
-                                                   const uint32_t *__restrict__ acc, const uint32_t *__restrict__ win_off,
+                                                   uint32_t *acc, uint32_t *win_off,
                                                    int n_win, int64_t r_lo, int64_t r_hi, int64_t t_abs0, int M, int W,
                                                    int Lw, uint64_t *words, int64_t words_cap) {
     __shared__ uint32_t s_keys[NCH + 2];
@@ -629,6 +630,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const int16_t *__restrict__ p
     const int board = blockIdx.y, wi = blockIdx.x, c = threadIdx.x;
     const int16_t *ph = phase + (size_t)board * rows * NCH;
     const uint32_t a = acc[((size_t)board * n_win + wi) * NCH + c];
+    if (a) acc[((size_t)board * n_win + wi) * NCH + c] = 0u;        // left clean for the next batch (no memset per call)
     const int64_t w_lo = r_lo + (int64_t)wi * Lw;          // first row of the window
     if (c == 0) s_n = 0;
     __syncthreads();
@@ -669,9 +671,10 @@ __global__ void __launch_bounds__(256) emit_kernel(const int16_t *__restrict__ p
         int64_t B = ta <= 0 ? SEC_US : ((ta + SEC_US - 1) / SEC_US) * SEC_US;
         if (B < tb) s_keys[atomicAdd(&s_n, 1)] = ((uint32_t)(B - ta) << 9);          // channel field 0: before all channels
     }
+    const uint32_t off = win_off[(size_t)board * (n_win + 1) + wi];
     __syncthreads();
     const int n = s_n;
-    const uint32_t off = win_off[(size_t)board * (n_win + 1) + wi];
+    if (c == 0) win_off[(size_t)board * (n_win + 1) + wi] = 0u;     // (every thread of the CTA has read it)
     uint64_t *out = words + (size_t)board * words_cap;
     if (a) {
         int rank = 0;
@@ -696,7 +699,7 @@ __global__ void __launch_bounds__(256) emit_kernel(const int16_t *__restrict__ p
 // fetch the baseline rows and the peak window of a trigger in two instructions, two triggers per round, and reduce
 // with REDUX.  Same integer / double arithmetic, same word order.
 __global__ void __launch_bounds__(256) emit_warp_kernel(const int16_t *__restrict__ phase, int64_t rows,
-                                                        const uint32_t *__restrict__ acc, const uint32_t *__restrict__ win_off,
+                                                        uint32_t *acc, uint32_t *win_off,
                                                         int n_win, int64_t r_lo, int64_t r_hi, int64_t t_abs0, int M, int W,
                                                         int Lw, uint64_t *words, int64_t words_cap) {
     __shared__ uint32_t s_keys[NCH + 2];
@@ -704,6 +707,7 @@ __global__ void __launch_bounds__(256) emit_warp_kernel(const int16_t *__restric
     const int board = blockIdx.y, wi = blockIdx.x, c = threadIdx.x, lane = c & 31, warp = c >> 5;
     const int16_t *ph = phase + (size_t)board * rows * NCH;
     const uint32_t a = acc[((size_t)board * n_win + wi) * NCH + c];
+    if (a) acc[((size_t)board * n_win + wi) * NCH + c] = 0u;        // left clean for the next batch (no memset per call)
     const int64_t w_lo = r_lo + (int64_t)wi * Lw;          // first row of the window
     if (c == 0) s_n = 0;
     __syncthreads();
@@ -714,9 +718,10 @@ __global__ void __launch_bounds__(256) emit_warp_kernel(const int16_t *__restric
         const int64_t B = ta <= 0 ? SEC_US : ((ta + SEC_US - 1) / SEC_US) * SEC_US;
         if (B < tb) s_keys[atomicAdd(&s_n, 1)] = ((uint32_t)(B - ta) << 9);          // channel field 0: before all channels
     }
+    const uint32_t off = win_off[(size_t)board * (n_win + 1) + wi];
     __syncthreads();
     const int n = s_n;
-    const uint32_t off = win_off[(size_t)board * (n_win + 1) + wi];
+    if (c == 0) win_off[(size_t)board * (n_win + 1) + wi] = 0u;     // (every thread of the CTA has read it)
     uint64_t *out = words + (size_t)board * words_cap;
     for (int i0 = warp; i0 < n; i0 += 16) {
         uint32_t key[2];
@@ -917,12 +922,17 @@ int run_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase_dev, int64_t r
     const int n_win = (int)((r_hi - r_lo + d.Lw - 1) / d.Lw);
     cap = ch->acc_bytes;
     if ((rc = ensure(ctx, (void **)&ch->acc, &cap, (size_t)B * n_win * NCH * 4))) return rc;
+    if (cap != ch->acc_bytes) ch->detect_clean = false;
     ch->acc_bytes = cap;
     cap = ch->win_bytes;
     if ((rc = ensure(ctx, (void **)&ch->win_cnt, &cap, (size_t)B * (n_win + 1) * 4))) return rc;
+    if (cap != ch->win_bytes) ch->detect_clean = false;
     ch->win_bytes = cap;
-    MKID_CUDA(ctx, cudaMemsetAsync(ch->acc, 0, (size_t)B * n_win * NCH * 4, ctx->stream));
-    MKID_CUDA(ctx, cudaMemsetAsync(ch->win_cnt, 0, (size_t)B * (n_win + 1) * 4, ctx->stream));
+    if (!ch->detect_clean) {             // first call, reallocation or a call that failed half-way
+        MKID_CUDA(ctx, cudaMemsetAsync(ch->acc, 0, ch->acc_bytes, ctx->stream));
+        MKID_CUDA(ctx, cudaMemsetAsync(ch->win_cnt, 0, ch->win_bytes, ctx->stream));
+    }
+    ch->detect_clean = false;
     if (!have_mask) {
         dim3 gc((unsigned)((rows + CAND_ROWS - 1) / CAND_ROWS), B);
         candidates_kernel<<<gc, 256, 0, ctx->stream>>>(phase_dev, rows, d.M, d.thr, ch->mask);
@@ -943,6 +953,7 @@ int run_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase_dev, int64_t r
         emit_kernel<<<dim3(n_win, B), 256, 0, ctx->stream>>>(phase_dev, rows, ch->acc, ch->win_cnt, n_win, r_lo, r_hi, t_abs0,
                                                              d.M, d.W, d.Lw, words_dev, words_cap);
     MKID_CHECK_LAUNCH(ctx);
+    ch->detect_clean = true;             // every entry resolve / scan wrote has been consumed and cleared by emit
     g_timer.mark(ctx->stream, "emit");
     return MKID_OK;
 }
