@@ -118,7 +118,25 @@ struct CombParams {
     unsigned int cap;
     double fudge, scale_override;
     int16_t *I, *Q;                      // [batch][N]
+    const double2 *tw;                   // [N1] e^{+2 pi j k / N1} = (cos, sin): the twiddles of every radix-4 stage
+    const double2 *tone;                 // [batch][T] (cos phi, sin phi) of every tone
 };
+
+// tables shared by all CTAs of comb_ifft_kernel (a double-precision sincospi costs ~100 instructions: computed per
+// butterfly it was 60 % of that kernel's instruction stream)
+__global__ void comb_prep_kernel(CombParams p, int batch, double2 *tw, double2 *tone) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < p.N1) {
+        double s, c;
+        sincospi(2.0 * (double)i / (double)p.N1, &s, &c);
+        tw[i] = make_double2(c, s);
+    }
+    if (i < batch * p.T) {
+        double sp, cp;
+        sincos(p.phase[i], &sp, &cp);
+        tone[i] = make_double2(cp, sp);
+    }
+}
 
 // ---- K1a: per (n2, batch) a length-N1 Stockham radix-4 IFFT in shared memory
 template <int N1>
@@ -133,9 +151,10 @@ __global__ void __launch_bounds__(N1 / 4) comb_ifft_kernel(CombParams p) {
     for (int i = tid; i < p.T; i += NT) {
         const long long k = p.kbin[(size_t)b * p.T + i];
         const long long m = (k * (long long)n2) % p.N;
-        double s, c, sp, cp;
+        double s, c;
         sincospi(2.0 * (double)m / (double)p.N, &s, &c);
-        sincos(p.phase[(size_t)b * p.T + i], &sp, &cp);
+        const double2 tn = p.tone[(size_t)b * p.T + i];
+        const double cp = tn.x, sp = tn.y;
         const double a = p.amp[(size_t)b * p.T + i];
         const double re = a * (c * cp - s * sp), im = a * (s * cp + c * sp);
         const int k1 = (int)(k % N1);
@@ -153,8 +172,8 @@ __global__ void __launch_bounds__(N1 / 4) comb_ifft_kernel(CombParams p) {
         if (Ns > 1) {
 #pragma unroll
             for (int r = 1; r < 4; ++r) {
-                double s, c;
-                sincospi(2.0 * (double)(r * k) / (double)(Ns * 4), &s, &c);     // e^{+2 pi j r k/(4 Ns)}
+                const double2 w = __ldg(&p.tw[r * k * (N1 / (4 * Ns))]);      // e^{+2 pi j r k/(4 Ns)}: the same double
+                const double c = w.x, s = w.y;                                  // arguments as sincospi(2 r k / (4 Ns))
                 v[r] = make_double2(v[r].x * c - v[r].y * s, v[r].x * s + v[r].y * c);
             }
         }
@@ -429,6 +448,14 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
     p.freq = d_freq; p.amp = d_amp; p.phase = d_phase; p.kbin = d_k; p.T = n_tones; p.N = N; p.N1 = N1; p.N2 = N2; p.offset = offset;
     p.fs = sample_rate; p.x = x; p.maxbits = d_max; p.scale = d_scale; p.exact_max = d_emax; p.list = list;
     p.count = d_count; p.cap = cap; p.fudge = fudge; p.scale_override = scale_override; p.I = (int16_t *)dI; p.Q = (int16_t *)dQ;
+    double2 *d_tw;
+    if ((rc = mkid_scratch(ctx, SCR_AUX2, ((size_t)N1 + TB) * 16, (void **)&d_tw))) return rc;
+    p.tw = d_tw; p.tone = d_tw + N1;
+    {
+        const int n_prep = (int)std::max<size_t>((size_t)N1, TB);
+        comb_prep_kernel<<<(n_prep + 255) / 256, 256, 0, ctx->stream>>>(p, batch, d_tw, d_tw + N1);
+        MKID_CHECK_LAUNCH(ctx);
+    }
     dim3 g1(N2, batch);
     switch (N1) {
     case 16: comb_ifft_kernel<16><<<g1, 4, 0, ctx->stream>>>(p); break;
