@@ -123,12 +123,17 @@ struct CombParams {
 };
 
 // tables shared by all CTAs of comb_ifft_kernel (a double-precision sincospi costs ~100 instructions: computed per
-// butterfly it was 60 % of that kernel's instruction stream)
+// butterfly it was 60 % of that kernel's instruction stream).  tw holds, for every radix-4 stage Ns = 4, 16, ... < N1,
+// the Ns factors e^{+2 pi j k / (4 Ns)}, k < Ns, at offset (Ns - 4) / 3: the lanes of a warp read CONSECUTIVE entries
+// (a strided gather from one length-N1 table cost as many L1 wavefronts as all the shared-memory traffic of the FFT).
 __global__ void comb_prep_kernel(CombParams p, int batch, double2 *tw, double2 *tone) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < p.N1) {
+    if (i < (p.N1 - 4) / 3) {
+        int Ns = 4;
+        while ((4 * Ns - 4) / 3 <= i) Ns *= 4;
+        const int k = i - (Ns - 4) / 3;
         double s, c;
-        sincospi(2.0 * (double)i / (double)p.N1, &s, &c);
+        sincospi(2.0 * (double)k / (double)(4 * Ns), &s, &c);
         tw[i] = make_double2(c, s);
     }
     if (i < batch * p.T) {
@@ -150,14 +155,14 @@ __global__ void __launch_bounds__(N1 / 4) comb_ifft_kernel(CombParams p) {
     // sparse fill: G[k mod N1] += a e^{j phi} e^{2 pi j k n2 / N}
     for (int i = tid; i < p.T; i += NT) {
         const long long k = p.kbin[(size_t)b * p.T + i];
-        const long long m = (k * (long long)n2) % p.N;
+        const long long m = (k * (long long)n2) & (long long)(p.N - 1);      // N is a power of two
         double s, c;
         sincospi(2.0 * (double)m / (double)p.N, &s, &c);
         const double2 tn = p.tone[(size_t)b * p.T + i];
         const double cp = tn.x, sp = tn.y;
         const double a = p.amp[(size_t)b * p.T + i];
         const double re = a * (c * cp - s * sp), im = a * (s * cp + c * sp);
-        const int k1 = (int)(k % N1);
+        const int k1 = (int)(k & (N1 - 1));
         atomicAdd(&bufA[k1].x, re);
         atomicAdd(&bufA[k1].y, im);
     }
@@ -170,12 +175,14 @@ __global__ void __launch_bounds__(N1 / 4) comb_ifft_kernel(CombParams p) {
 #pragma unroll
         for (int r = 0; r < 4; ++r) v[r] = in[j + r * NT];
         if (Ns > 1) {
-#pragma unroll
-            for (int r = 1; r < 4; ++r) {
-                const double2 w = __ldg(&p.tw[r * k * (N1 / (4 * Ns))]);      // e^{+2 pi j r k/(4 Ns)}: the same double
-                const double c = w.x, s = w.y;                                  // arguments as sincospi(2 r k / (4 Ns))
-                v[r] = make_double2(v[r].x * c - v[r].y * s, v[r].x * s + v[r].y * c);
-            }
+            // the bulk result only has to be good to ~1e-9 relative (samples within 1e-4 LSB of a rounding boundary are
+            // re-evaluated exactly): w^2 and w^3 by multiplication instead of two more table reads
+            const double2 w1 = __ldg(&p.tw[(Ns - 4) / 3 + k]);                  // e^{+2 pi j k/(4 Ns)}
+            const double2 w2 = make_double2(w1.x * w1.x - w1.y * w1.y, 2.0 * w1.x * w1.y);
+            const double2 w3 = make_double2(w2.x * w1.x - w2.y * w1.y, w2.x * w1.y + w2.y * w1.x);
+            v[1] = make_double2(v[1].x * w1.x - v[1].y * w1.y, v[1].x * w1.y + v[1].y * w1.x);
+            v[2] = make_double2(v[2].x * w2.x - v[2].y * w2.y, v[2].x * w2.y + v[2].y * w2.x);
+            v[3] = make_double2(v[3].x * w3.x - v[3].y * w3.y, v[3].x * w3.y + v[3].y * w3.x);
         }
         // inverse radix-4 butterfly (twiddle +j)
         const double2 t0 = make_double2(v[0].x + v[2].x, v[0].y + v[2].y), t1 = make_double2(v[0].x - v[2].x, v[0].y - v[2].y);
@@ -189,12 +196,13 @@ __global__ void __launch_bounds__(N1 / 4) comb_ifft_kernel(CombParams p) {
         __syncthreads();
         double2 *tmp = in; in = out; out = tmp;
     }
-    // x[n2 + N2 * n1] = in[n1]
+    // sample t = n2 + N2 * n1 is stored at x[n2 * N1 + n1]: whole lines per warp (the time-ordered layout made every
+    // 16-byte store its own L1 wavefront); the consumers transpose (comb_quantise_kernel) or do not care about order
     double mx = 0.0;
-    double2 *x = p.x + (size_t)b * p.N;
+    double2 *x = p.x + (size_t)b * p.N + (size_t)n2 * N1;
     for (int n1 = tid; n1 < N1; n1 += NT) {
         const double2 v = in[n1];
-        x[n2 + p.N2 * n1] = v;
+        x[n1] = v;
         mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
     }
     for (int d = 16; d > 0; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
@@ -206,23 +214,26 @@ __global__ void __launch_bounds__(N1 / 4) comb_ifft_kernel(CombParams p) {
     }
 }
 
-// bulk value of I (uses t+offset) or Q at sample t
-__device__ __forceinline__ double bulk_value(const CombParams &p, int b, int t, int isQ) {
-    const double2 *x = p.x + (size_t)b * p.N;
-    if (isQ) return x[t].y;
-    return x[(t + p.offset) & (p.N - 1)].x;      // N is a power of two; offset may be negative
-}
-
-// ---- K1b: samples that can hold the max -> list
+// ---- K1b: samples that can hold the max -> list.  Order-free: walks x in storage order; entry s = n2 * N1 + n1 is
+// Q at t = n2 + N2 * n1 and I at t - offset (I[t] is the real part at t + offset, ROACH_Setup_DAC.py:419-420)
 __global__ void comb_max_candidates_kernel(CombParams p) {
     const int b = blockIdx.y;
     const double mx = __longlong_as_double((long long)p.maxbits[b]);
     const double lim = mx * (1.0 - 1e-8);
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * p.N; i += gridDim.x * blockDim.x) {
-        const int t = i >> 1, isQ = i & 1;
-        if (fabs(bulk_value(p, b, t, isQ)) >= lim) {
-            const unsigned pos = atomicAdd(&p.count[b], 1u);
-            if (pos < p.cap) p.list[(size_t)b * p.cap + pos] = (unsigned)t | ((unsigned)isQ << 31);
+    const double2 *x = p.x + (size_t)b * p.N;
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < p.N; s += gridDim.x * blockDim.x) {
+        const double2 v = x[s];
+        const bool hq = fabs(v.y) >= lim, hi = fabs(v.x) >= lim;
+        if (hq | hi) {
+            const unsigned t = (unsigned)(s / p.N1) + (unsigned)p.N2 * (unsigned)(s % p.N1);
+            if (hq) {
+                const unsigned pos = atomicAdd(&p.count[b], 1u);
+                if (pos < p.cap) p.list[(size_t)b * p.cap + pos] = t | (1u << 31);
+            }
+            if (hi) {
+                const unsigned pos = atomicAdd(&p.count[b], 1u);
+                if (pos < p.cap) p.list[(size_t)b * p.cap + pos] = (t - (unsigned)p.offset) & (unsigned)(p.N - 1);
+            }
         }
     }
 }
@@ -270,19 +281,52 @@ __global__ void comb_scale_kernel(CombParams p, int batch) {
     p.count[b] = 0;                                            // the list is reused by the quantiser
 }
 
-// ---- K1d: quantise; flag samples within eps of an integer for exact re-evaluation
-__global__ void comb_quantise_kernel(CombParams p, double eps) {
-    const int b = blockIdx.y;
-    const double sc = p.scale[b];
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * p.N; i += gridDim.x * blockDim.x) {
-        const int t = i >> 1, isQ = i & 1;
-        const double v = __ddiv_rn(__dmul_rn(bulk_value(p, b, t, isQ), 32767.0), sc);
-        if (fabs(v - rint(v)) < eps) {
-            const unsigned pos = atomicAdd(&p.count[b], 1u);
-            if (pos < p.cap) p.list[(size_t)b * p.cap + pos] = (unsigned)t | ((unsigned)isQ << 31);
+// ---- K1d: quantise; flag samples within eps of an integer for exact re-evaluation.  One CTA per tile of QT_A values of
+// n2 x QT_C values of n1: reads runs of QT_C entries of x (storage order), transposes the int16 results through shared
+// memory and stores runs of QT_A consecutive samples.  Unflagged samples are further than eps from a rounding boundary,
+// so x * (32767 / scale) truncates to the same integer as the reference's (x * 32767) / scale; the flagged ones are
+// overwritten by comb_fixup_kernel with the reference-order value.
+constexpr int QT_A = 64, QT_C = 32;
+__global__ void __launch_bounds__(256) comb_quantise_kernel(CombParams p, double eps) {
+    __shared__ int16_t sI[QT_C][QT_A + 2], sQ[QT_C][QT_A + 2];
+    const int b = blockIdx.y, tid = threadIdx.x;
+    const int tiles_c = (p.N1 + QT_C - 1) / QT_C;
+    const int a0 = (blockIdx.x / tiles_c) * QT_A, c0 = (blockIdx.x % tiles_c) * QT_C;
+    const double rs = __ddiv_rn(32767.0, p.scale[b]);
+    const double2 *x = p.x + (size_t)b * p.N;
+    const unsigned nmask = (unsigned)(p.N - 1);
+#pragma unroll
+    for (int i = 0; i < QT_A * QT_C / 256; ++i) {
+        const int e = tid + i * 256, a = e / QT_C, c = e % QT_C;
+        if (a0 + a < p.N2 && c0 + c < p.N1) {
+            const double2 v = x[(size_t)(a0 + a) * p.N1 + c0 + c];
+            const double vi = v.x * rs, vq = v.y * rs;
+            const bool fi = fabs(vi - rint(vi)) < eps, fq = fabs(vq - rint(vq)) < eps;
+            if (fi | fq) {
+                const unsigned t = (unsigned)(a0 + a) + (unsigned)p.N2 * (unsigned)(c0 + c);
+                if (fq) {
+                    const unsigned pos = atomicAdd(&p.count[b], 1u);
+                    if (pos < p.cap) p.list[(size_t)b * p.cap + pos] = t | (1u << 31);
+                }
+                if (fi) {
+                    const unsigned pos = atomicAdd(&p.count[b], 1u);
+                    if (pos < p.cap) p.list[(size_t)b * p.cap + pos] = (t - (unsigned)p.offset) & nmask;
+                }
+            }
+            sI[c][a] = (int16_t)max(-32768, min(32767, __double2int_rz(vi)));
+            sQ[c][a] = (int16_t)max(-32768, min(32767, __double2int_rz(vq)));
         }
-        const int16_t q = (int16_t)max(-32768, min(32767, __double2int_rz(v)));
-        (isQ ? p.Q : p.I)[(size_t)b * p.N + t] = q;
+    }
+    __syncthreads();
+    int16_t *Io = p.I + (size_t)b * p.N, *Qo = p.Q + (size_t)b * p.N;
+#pragma unroll
+    for (int i = 0; i < QT_A * QT_C / 256; ++i) {
+        const int e = tid + i * 256, c = e / QT_A, a = e % QT_A;
+        if (a0 + a < p.N2 && c0 + c < p.N1) {
+            const unsigned t = (unsigned)(a0 + a) + (unsigned)p.N2 * (unsigned)(c0 + c);
+            Qo[t] = sQ[c][a];
+            Io[(t - (unsigned)p.offset) & nmask] = sI[c][a];
+        }
     }
 }
 
@@ -452,7 +496,7 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
     if ((rc = mkid_scratch(ctx, SCR_AUX2, ((size_t)N1 + TB) * 16, (void **)&d_tw))) return rc;
     p.tw = d_tw; p.tone = d_tw + N1;
     {
-        const int n_prep = (int)std::max<size_t>((size_t)N1, TB);
+        const int n_prep = (int)std::max<size_t>((size_t)N1, TB);      // (N1 - 4) / 3 table entries, TB tones
         comb_prep_kernel<<<(n_prep + 255) / 256, 256, 0, ctx->stream>>>(p, batch, d_tw, d_tw + N1);
         MKID_CHECK_LAUNCH(ctx);
     }
@@ -464,7 +508,8 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
     default: comb_ifft_kernel<1024><<<g1, 256, 0, ctx->stream>>>(p); break;
     }
     MKID_CHECK_LAUNCH(ctx);
-    const int gs = std::min(2 * N / 256, ctx->num_sms * 8);
+    const int gs = std::min(N / 256, ctx->num_sms * 8);
+    const int q_tiles = ((N2 + QT_A - 1) / QT_A) * ((N1 + QT_C - 1) / QT_C);
     const size_t wsm = (size_t)4 * n_tones * 8;
     if (scale_override <= 0.0) {
         comb_max_candidates_kernel<<<dim3(gs, batch), 256, 0, ctx->stream>>>(p);
@@ -474,7 +519,7 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
     }
     comb_scale_kernel<<<(batch + 63) / 64, 64, 0, ctx->stream>>>(p, batch);
     MKID_CHECK_LAUNCH(ctx);
-    comb_quantise_kernel<<<dim3(gs, batch), 256, 0, ctx->stream>>>(p, 1e-4);
+    comb_quantise_kernel<<<dim3(q_tiles, batch), 256, 0, ctx->stream>>>(p, 1e-4);
     MKID_CHECK_LAUNCH(ctx);
     comb_fixup_kernel<<<dim3(64, batch), 128, wsm, ctx->stream>>>(p);
     MKID_CHECK_LAUNCH(ctx);
