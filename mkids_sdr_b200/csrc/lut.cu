@@ -97,6 +97,36 @@ __device__ void sincos_cr(double x, double *s_out, double *c_out) {
     }
 }
 
+// sin(x) (want_cos = 0) or cos(x) (want_cos = 1) alone: the same reduction and the same operations as sincos_cr for the
+// one series the quadrant asks for (bit-identical to the corresponding output of sincos_cr), half the double-double work.
+// The series is chosen per lane by selecting the coefficients, not by branching.
+__device__ double sin_or_cos_cr(double x, int want_cos) {
+    const double PIO2_1 = 1.5707963267948966, PIO2_2 = 6.123233995736766e-17, PIO2_3 = -1.4973849048591698e-33;
+    const double k = rint(__dmul_rn(x, 0.6366197723675814));
+    dd p = two_prod(k, PIO2_1);
+    dd r = two_sum(x, -p.hi);
+    r.lo = __dsub_rn(r.lo, p.lo);
+    r = two_sum(r.hi, r.lo);
+    dd q = two_prod(k, PIO2_2);
+    r = dd_add(r, dd{-q.hi, -q.lo});
+    r.lo = __dsub_rn(r.lo, __dmul_rn(k, PIO2_3));
+    r = two_sum(r.hi, r.lo);
+    const dd z = dd_mul(r, r);
+    const int quad = (int)((long long)k & 3);
+    const bool cos_series = ((quad ^ want_cos) & 1) != 0;
+    dd ps = {cos_series ? c_C[12][0] : c_S[12][0], cos_series ? c_C[12][1] : c_S[12][1]};
+#pragma unroll 1
+    for (int i = 11; i >= 0; --i) {
+        const double c0 = cos_series ? c_C[i][0] : c_S[i][0], c1 = cos_series ? c_C[i][1] : c_S[i][1];
+        ps = dd_add(dd_mul(ps, z), dd{c0, c1});
+    }
+    const dd a = cos_series ? dd{1.0, 0.0} : r;                 // 1 + z * C(z)   |   r + (r * z) * S(z)
+    const dd m = cos_series ? z : dd_mul(r, z);
+    const double v = dd_add(a, dd_mul(m, ps)).hi;
+    const bool neg = ((want_cos ? quad + 1 : quad) & 2) != 0;
+    return neg ? -v : v;
+}
+
 // argument of the reference: ((2*pi*f)*(t+offset))/fs + phi, evaluated left to right in float64
 // (ROACH_Setup.py:439-440)
 __device__ __forceinline__ double ref_arg(double f, double t, double fs, double phi) {
@@ -143,6 +173,15 @@ __global__ void comb_prep_kernel(CombParams p, int batch, double2 *tw, double2 *
     }
 }
 
+// shared-memory position of FFT element i: 16-byte elements are served per quarter-warp (8 lanes over the 8 four-bank
+// groups), so the bank group is i & 7.  Stage Ns = 1 stores element 4 j + r and stage Ns = 4 element 16 q + k + 4 r from
+// lane j = 4 q + k: 4-way and 2-way conflicts in the plain layout.  XOR-ing the group with bits of i >> 3 keeps every
+// aligned run of 8 elements conflict-free (all loads, stores of the stages Ns >= 16) and spreads those two stores.
+__device__ __forceinline__ int fft_swz(int i) {
+    const int h = i >> 3;
+    return i ^ ((h ^ (h << 1)) & 7);
+}
+
 // ---- K1a: per (n2, batch) a length-N1 Stockham radix-4 IFFT in shared memory
 template <int N1>
 __global__ void __launch_bounds__(N1 / 4) comb_ifft_kernel(CombParams p) {
@@ -163,8 +202,8 @@ __global__ void __launch_bounds__(N1 / 4) comb_ifft_kernel(CombParams p) {
         const double a = p.amp[(size_t)b * p.T + i];
         const double re = a * (c * cp - s * sp), im = a * (s * cp + c * sp);
         const int k1 = (int)(k & (N1 - 1));
-        atomicAdd(&bufA[k1].x, re);
-        atomicAdd(&bufA[k1].y, im);
+        atomicAdd(&bufA[fft_swz(k1)].x, re);
+        atomicAdd(&bufA[fft_swz(k1)].y, im);
     }
     __syncthreads();
     double2 *in = bufA, *out = bufB;
@@ -173,7 +212,7 @@ __global__ void __launch_bounds__(N1 / 4) comb_ifft_kernel(CombParams p) {
         const int j = tid, k = j % Ns;
         double2 v[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) v[r] = in[j + r * NT];
+        for (int r = 0; r < 4; ++r) v[r] = in[fft_swz(j + r * NT)];
         if (Ns > 1) {
             // the bulk result only has to be good to ~1e-9 relative (samples within 1e-4 LSB of a rounding boundary are
             // re-evaluated exactly): w^2 and w^3 by multiplication instead of two more table reads
@@ -189,10 +228,10 @@ __global__ void __launch_bounds__(N1 / 4) comb_ifft_kernel(CombParams p) {
         const double2 t2 = make_double2(v[1].x + v[3].x, v[1].y + v[3].y);
         const double2 t3 = make_double2(-(v[1].y - v[3].y), v[1].x - v[3].x);       // (v1 - v3) * (+j)
         const int j0 = (j - k) * 4 + k;
-        out[j0] = make_double2(t0.x + t2.x, t0.y + t2.y);
-        out[j0 + Ns] = make_double2(t1.x + t3.x, t1.y + t3.y);
-        out[j0 + 2 * Ns] = make_double2(t0.x - t2.x, t0.y - t2.y);
-        out[j0 + 3 * Ns] = make_double2(t1.x - t3.x, t1.y - t3.y);
+        out[fft_swz(j0)] = make_double2(t0.x + t2.x, t0.y + t2.y);
+        out[fft_swz(j0 + Ns)] = make_double2(t1.x + t3.x, t1.y + t3.y);
+        out[fft_swz(j0 + 2 * Ns)] = make_double2(t0.x - t2.x, t0.y - t2.y);
+        out[fft_swz(j0 + 3 * Ns)] = make_double2(t1.x - t3.x, t1.y - t3.y);
         __syncthreads();
         double2 *tmp = in; in = out; out = tmp;
     }
@@ -201,7 +240,7 @@ __global__ void __launch_bounds__(N1 / 4) comb_ifft_kernel(CombParams p) {
     double mx = 0.0;
     double2 *x = p.x + (size_t)b * p.N + (size_t)n2 * N1;
     for (int n1 = tid; n1 < N1; n1 += NT) {
-        const double2 v = in[n1];
+        const double2 v = in[fft_swz(n1)];
         x[n1] = v;
         mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
     }
@@ -244,9 +283,7 @@ __device__ double exact_sample(const CombParams &p, int b, int t, int isQ, doubl
     const double tt = isQ ? (double)t : (double)(t + p.offset);
     for (int i = lane; i < p.T; i += 32) {
         const double arg = ref_arg(p.freq[(size_t)b * p.T + i], tt, p.fs, p.phase[(size_t)b * p.T + i]);
-        double s, c;
-        sincos_cr(arg, &s, &c);
-        s_terms[i] = __dmul_rn(p.amp[(size_t)b * p.T + i], isQ ? s : c);
+        s_terms[i] = __dmul_rn(p.amp[(size_t)b * p.T + i], sin_or_cos_cr(arg, !isQ));
     }
     __syncwarp();
     double acc = 0.0;
@@ -402,7 +439,9 @@ __global__ void pack_dram_kernel(const int16_t *I_dac, const int16_t *Q_dac, con
 
 __global__ void sincos_cr_test_kernel(const double *x, int64_t n, double *s, double *c) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) sincos_cr(x[i], &s[i], &c[i]);
+    if (i >= n) return;
+    if (i & 1) { s[i] = sin_or_cos_cr(x[i], 0); c[i] = sin_or_cos_cr(x[i], 1); }    // both evaluators are under test
+    else sincos_cr(x[i], &s[i], &c[i]);
 }
 
 // ------------------------------------------------------------------ MT19937 (numpy.random.seed / uniform)
