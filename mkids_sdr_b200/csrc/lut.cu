@@ -14,6 +14,7 @@
 // K2  DDS tables are small (256 channels x N/256 samples): evaluated directly in reference order.
 // K3  big-endian 8 x int16 DRAM image (ROACH_Setup.py:560-569).
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -492,10 +493,18 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
     MKID_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t TB = (size_t)batch * n_tones;
     // host: spectral line of every tone; must be on the fs/N grid (define_DAC_LUT snaps to it, :498)
-    std::vector<long long> kbin(TB);
-    std::vector<double> ph(phase, phase + TB);
+    // one host block in the device layout freq | amp | phase | kbin: a single upload
+    std::vector<double> hmeta(TB * 4);
+    double *ph = hmeta.data() + 2 * TB;
+    long long *kbin = reinterpret_cast<long long *>(hmeta.data() + 3 * TB);
+    memcpy(hmeta.data(), freq_hz, TB * 8);
+    memcpy(hmeta.data() + TB, amp, TB * 8);
+    memcpy(ph, phase, TB * 8);
     for (int b = 0; b < batch; ++b) {
-        if (random_phase) mkid_random_phases(1000u, n_tones, ph.data() + (size_t)b * n_tones);
+        if (random_phase) {                                   // every call re-seeds (:426): the same draws for every set
+            if (b == 0) mkid_random_phases(1000u, n_tones, ph);
+            else memcpy(ph + (size_t)b * n_tones, ph, (size_t)n_tones * 8);
+        }
         for (int i = 0; i < n_tones; ++i) {
             const double k = freq_hz[(size_t)b * n_tones + i] * (double)N / sample_rate;
             const double kr = nearbyint(k);
@@ -505,14 +514,17 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
             kbin[(size_t)b * n_tones + i] = kk;
         }
     }
-    if (random_phase) memcpy(phase, ph.data(), TB * 8);
+    if (random_phase) memcpy(phase, ph, TB * 8);
     // device buffers
     const unsigned cap = 1u << 17;
     char *meta; double2 *x; unsigned *list;
     int rc;
     const size_t meta_bytes = TB * 32 + (size_t)batch * 48;
     if ((rc = mkid_scratch(ctx, SCR_META, meta_bytes, (void **)&meta))) return rc;
-    if ((rc = mkid_scratch(ctx, SCR_AUX0, (size_t)batch * N * 16, (void **)&x))) return rc;
+    int sub = (int)std::max<size_t>(1, ((size_t)512 << 20) / ((size_t)N * 16));
+    if (const char *e = getenv("MKID_LUT_GROUP")) sub = std::max(1, atoi(e));      // experiment switch
+    sub = std::min(sub, batch);
+    if ((rc = mkid_scratch(ctx, SCR_AUX0, (size_t)sub * N * 16, (void **)&x))) return rc;
     if ((rc = mkid_scratch(ctx, SCR_AUX1, (size_t)batch * cap * 4, (void **)&list))) return rc;
     CombParams p;
     double *d_freq = (double *)meta, *d_amp = d_freq + TB, *d_phase = d_amp + TB;
@@ -520,10 +532,7 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
     unsigned long long *d_max = (unsigned long long *)(d_k + TB), *d_emax = d_max + batch;
     double *d_scale = (double *)(d_emax + batch);
     unsigned *d_count = (unsigned *)(d_scale + batch);
-    MKID_CUDA(ctx, cudaMemcpyAsync(d_freq, freq_hz, TB * 8, cudaMemcpyHostToDevice, ctx->stream));
-    MKID_CUDA(ctx, cudaMemcpyAsync(d_amp, amp, TB * 8, cudaMemcpyHostToDevice, ctx->stream));
-    MKID_CUDA(ctx, cudaMemcpyAsync(d_phase, ph.data(), TB * 8, cudaMemcpyHostToDevice, ctx->stream));
-    MKID_CUDA(ctx, cudaMemcpyAsync(d_k, kbin.data(), TB * 8, cudaMemcpyHostToDevice, ctx->stream));
+    MKID_CUDA(ctx, cudaMemcpyAsync(d_freq, hmeta.data(), TB * 32, cudaMemcpyHostToDevice, ctx->stream));
     MKID_CUDA(ctx, cudaMemsetAsync(d_max, 0, (size_t)batch * 48 - 0, ctx->stream));
     void *dI, *dQ;
     if ((rc = mkid_stage_out(ctx, I, (size_t)batch * N * 2, SCR_OUT0, false, &dI))) return rc;
@@ -539,35 +548,46 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
         comb_prep_kernel<<<(n_prep + 255) / 256, 256, 0, ctx->stream>>>(p, batch, d_tw, d_tw + N1);
         MKID_CHECK_LAUNCH(ctx);
     }
-    dim3 g1(N2, batch);
-    switch (N1) {
-    case 16: comb_ifft_kernel<16><<<g1, 4, 0, ctx->stream>>>(p); break;
-    case 64: comb_ifft_kernel<64><<<g1, 16, 0, ctx->stream>>>(p); break;
-    case 256: comb_ifft_kernel<256><<<g1, 64, 0, ctx->stream>>>(p); break;
-    default: comb_ifft_kernel<1024><<<g1, 256, 0, ctx->stream>>>(p); break;
-    }
-    MKID_CHECK_LAUNCH(ctx);
     const int gs = std::min(N / 256, ctx->num_sms * 8);
     const int q_tiles = ((N2 + QT_A - 1) / QT_A) * ((N1 + QT_C - 1) / QT_C);
     const size_t wsm = (size_t)4 * n_tones * 8;
-    if (scale_override <= 0.0) {
-        comb_max_candidates_kernel<<<dim3(gs, batch), 256, 0, ctx->stream>>>(p);
+    // groups of `sub` LUT sets share ONE bulk buffer of <= 512 MiB (64 sets of 2^19 samples), so a large batch does not
+    // scale the scratch.  Measured: L2-sized groups (4 / 8 / 16 sets) are SLOWER, 40 / 54.5 / 55.4 k sets per second
+    // against 74.3 k for groups of 64: short launches pay their tails, the L2 hits do not make up for it.
+    for (int b0 = 0; b0 < batch; b0 += sub) {
+        const int nb = std::min(sub, batch - b0);
+        CombParams q = p;
+        const size_t t0 = (size_t)b0 * n_tones;
+        q.freq += t0; q.amp += t0; q.phase += t0; q.kbin += t0; q.tone += t0;
+        q.maxbits += b0; q.scale += b0; q.exact_max += b0; q.count += b0; q.list += (size_t)b0 * cap;
+        q.I += (size_t)b0 * N; q.Q += (size_t)b0 * N;
+        dim3 g1(N2, nb);
+        switch (N1) {
+        case 16: comb_ifft_kernel<16><<<g1, 4, 0, ctx->stream>>>(q); break;
+        case 64: comb_ifft_kernel<64><<<g1, 16, 0, ctx->stream>>>(q); break;
+        case 256: comb_ifft_kernel<256><<<g1, 64, 0, ctx->stream>>>(q); break;
+        default: comb_ifft_kernel<1024><<<g1, 256, 0, ctx->stream>>>(q); break;
+        }
         MKID_CHECK_LAUNCH(ctx);
-        comb_exact_max_kernel<<<dim3(64, batch), 128, wsm, ctx->stream>>>(p);
+        if (scale_override <= 0.0) {
+            comb_max_candidates_kernel<<<dim3(gs, nb), 256, 0, ctx->stream>>>(q);
+            MKID_CHECK_LAUNCH(ctx);
+            comb_exact_max_kernel<<<dim3(64, nb), 128, wsm, ctx->stream>>>(q);
+            MKID_CHECK_LAUNCH(ctx);
+        }
+        comb_scale_kernel<<<(nb + 63) / 64, 64, 0, ctx->stream>>>(q, nb);
+        MKID_CHECK_LAUNCH(ctx);
+        comb_quantise_kernel<<<dim3(q_tiles, nb), 256, 0, ctx->stream>>>(q, 1e-4);
+        MKID_CHECK_LAUNCH(ctx);
+        comb_fixup_kernel<<<dim3(64, nb), 128, wsm, ctx->stream>>>(q);
         MKID_CHECK_LAUNCH(ctx);
     }
-    comb_scale_kernel<<<(batch + 63) / 64, 64, 0, ctx->stream>>>(p, batch);
-    MKID_CHECK_LAUNCH(ctx);
-    comb_quantise_kernel<<<dim3(q_tiles, batch), 256, 0, ctx->stream>>>(p, 1e-4);
-    MKID_CHECK_LAUNCH(ctx);
-    comb_fixup_kernel<<<dim3(64, batch), 128, wsm, ctx->stream>>>(p);
-    MKID_CHECK_LAUNCH(ctx);
     // overflow of the candidate / fix-up list would silently skip exact re-evaluation: check
-    std::vector<unsigned> cnt(batch);
-    std::vector<double> sc(batch);
-    MKID_CUDA(ctx, cudaMemcpyAsync(cnt.data(), d_count, (size_t)batch * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    MKID_CUDA(ctx, cudaMemcpyAsync(sc.data(), d_scale, (size_t)batch * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<double> back((size_t)batch + (batch + 1) / 2);          // scale[batch] | count[batch]: adjacent on the device
+    MKID_CUDA(ctx, cudaMemcpyAsync(back.data(), d_scale, (size_t)batch * 12, cudaMemcpyDeviceToHost, ctx->stream));
     MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const double *sc = back.data();
+    const unsigned *cnt = reinterpret_cast<const unsigned *>(back.data() + batch);
     for (int b = 0; b < batch; ++b) {
         if (cnt[b] > cap) return mkid_fail(ctx, MKID_EINVAL, "comb_lut: %u samples need exact re-evaluation (> %u)", cnt[b], cap);
         if (scale_out) scale_out[b] = sc[b];
