@@ -185,15 +185,16 @@ __device__ __forceinline__ int fft_swz(int i) {
 
 // ---- K1a: per (n2, batch) a length-N1 Stockham radix-4 IFFT in shared memory
 template <int N1>
-__global__ void __launch_bounds__(N1 / 4) comb_ifft_kernel(CombParams p) {
+__global__ void __launch_bounds__(N1 / 4 < 32 ? 32 : N1 / 4) comb_ifft_kernel(CombParams p) {
     __shared__ double2 bufA[N1], bufB[N1];
     __shared__ double s_red[32];
     const int n2 = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
-    constexpr int NT = N1 / 4;
-    for (int i = tid; i < N1; i += NT) bufA[i] = make_double2(0.0, 0.0);
+    constexpr int NT = N1 / 4;                       // butterflies per stage
+    constexpr int BT = NT < 32 ? 32 : NT;            // threads per CTA: whole warps (the short tables leave lanes idle)
+    for (int i = tid; i < N1; i += BT) bufA[i] = make_double2(0.0, 0.0);
     __syncthreads();
     // sparse fill: G[k mod N1] += a e^{j phi} e^{2 pi j k n2 / N}
-    for (int i = tid; i < p.T; i += NT) {
+    for (int i = tid; i < p.T; i += BT) {
         const long long k = p.kbin[(size_t)b * p.T + i];
         const long long m = (k * (long long)n2) & (long long)(p.N - 1);      // N is a power of two
         double s, c;
@@ -210,6 +211,7 @@ __global__ void __launch_bounds__(N1 / 4) comb_ifft_kernel(CombParams p) {
     double2 *in = bufA, *out = bufB;
 #pragma unroll 1
     for (int Ns = 1; Ns < N1; Ns *= 4) {
+      if (BT == NT || tid < NT) {
         const int j = tid, k = j % Ns;
         double2 v[4];
 #pragma unroll
@@ -233,6 +235,7 @@ __global__ void __launch_bounds__(N1 / 4) comb_ifft_kernel(CombParams p) {
         out[fft_swz(j0 + Ns)] = make_double2(t1.x + t3.x, t1.y + t3.y);
         out[fft_swz(j0 + 2 * Ns)] = make_double2(t0.x - t2.x, t0.y - t2.y);
         out[fft_swz(j0 + 3 * Ns)] = make_double2(t1.x - t3.x, t1.y - t3.y);
+      }
         __syncthreads();
         double2 *tmp = in; in = out; out = tmp;
     }
@@ -240,7 +243,7 @@ __global__ void __launch_bounds__(N1 / 4) comb_ifft_kernel(CombParams p) {
     // 16-byte store its own L1 wavefront); the consumers transpose (comb_quantise_kernel) or do not care about order
     double mx = 0.0;
     double2 *x = p.x + (size_t)b * p.N + (size_t)n2 * N1;
-    for (int n1 = tid; n1 < N1; n1 += NT) {
+    for (int n1 = tid; n1 < N1; n1 += BT) {
         const double2 v = in[fft_swz(n1)];
         x[n1] = v;
         mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
@@ -249,7 +252,7 @@ __global__ void __launch_bounds__(N1 / 4) comb_ifft_kernel(CombParams p) {
     if ((tid & 31) == 0) s_red[tid >> 5] = mx;
     __syncthreads();
     if (tid == 0) {
-        for (int i = 1; i < (NT + 31) / 32; ++i) mx = fmax(mx, s_red[i]);
+        for (int i = 1; i < BT / 32; ++i) mx = fmax(mx, s_red[i]);
         atomicMax(&p.maxbits[b], (unsigned long long)__double_as_longlong(mx));
     }
 }
@@ -548,7 +551,7 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
         comb_prep_kernel<<<(n_prep + 255) / 256, 256, 0, ctx->stream>>>(p, batch, d_tw, d_tw + N1);
         MKID_CHECK_LAUNCH(ctx);
     }
-    const int gs = std::min(N / 256, ctx->num_sms * 8);
+    const int gs = std::max(1, std::min(N / 256, ctx->num_sms * 8));
     const int q_tiles = ((N2 + QT_A - 1) / QT_A) * ((N1 + QT_C - 1) / QT_C);
     const size_t wsm = (size_t)4 * n_tones * 8;
     // groups of `sub` LUT sets share ONE bulk buffer of <= 512 MiB (64 sets of 2^19 samples), so a large batch does not
@@ -563,8 +566,8 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
         q.I += (size_t)b0 * N; q.Q += (size_t)b0 * N;
         dim3 g1(N2, nb);
         switch (N1) {
-        case 16: comb_ifft_kernel<16><<<g1, 4, 0, ctx->stream>>>(q); break;
-        case 64: comb_ifft_kernel<64><<<g1, 16, 0, ctx->stream>>>(q); break;
+        case 16: comb_ifft_kernel<16><<<g1, 32, 0, ctx->stream>>>(q); break;
+        case 64: comb_ifft_kernel<64><<<g1, 32, 0, ctx->stream>>>(q); break;
         case 256: comb_ifft_kernel<256><<<g1, 64, 0, ctx->stream>>>(q); break;
         default: comb_ifft_kernel<1024><<<g1, 256, 0, ctx->stream>>>(q); break;
         }

@@ -92,6 +92,27 @@ def test_comb_lut_options_offset_scale_batch(ctx):
     assert np.array_equal(Q[0], np.trunc(Qf * 32767 / 9.5).astype(np.int64))
 
 
+@pytest.mark.parametrize('N,T,offset', [(64, 3, 0), (256, 9, -3), (1024, 20, 5), (2048, 31, 1), (4096, 64, -1000)])
+def test_comb_lut_small_tables_and_groups(ctx, N, T, offset, monkeypatch):
+    """Short tables (IFFT lengths 16 / 64 / 256, partial quantise tiles), negative and odd I offsets, and a batch that
+    spans several bulk-buffer groups (MKID_LUT_GROUP) with a short last group."""
+    from mkids_sdr_b200 import lut
+    rng = np.random.default_rng(N + T)
+    batch = 5
+    fl, al, pl = [], [], []
+    for b in range(batch):
+        k = rng.choice(np.arange(-N // 2 + 1, N // 2), T, replace=False)
+        fl.append((k % N) * FS / N); al.append(rng.uniform(0.05, 1.0, T)); pl.append(rng.uniform(-3, 3, T))
+    monkeypatch.setenv('MKID_LUT_GROUP', '2')
+    I, Q, sc, _ = lut.comb_lut(fl, FS, N, al, pl, echo='yes', random_phase='no', offset=offset, ctx=ctx)
+    monkeypatch.delenv('MKID_LUT_GROUP')
+    I1, Q1, sc1, _ = lut.comb_lut(fl, FS, N, al, pl, echo='yes', random_phase='no', offset=offset, ctx=ctx)
+    assert np.array_equal(I, I1) and np.array_equal(Q, Q1) and np.array_equal(sc, sc1)
+    for b in range(batch):
+        Io, Qo, so, _ = olut.freq_comb_lut('yes', list(fl[b]), FS, FS / N, list(al[b]), list(pl[b]), 'no', offset=offset)
+        assert sc[b] == so and np.array_equal(I[b], Io) and np.array_equal(Q[b], Qo)
+
+
 @pytest.mark.parametrize('N', [2 ** 16, 2 ** 19])
 def test_dds_lut_and_dram_identical_to_oracle(ctx, N):
     from mkids_sdr_b200 import lut
