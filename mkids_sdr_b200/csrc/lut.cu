@@ -151,6 +151,7 @@ struct CombParams {
     int16_t *I, *Q;                      // [batch][N]
     const double2 *tw;                   // [N1] e^{+2 pi j k / N1} = (cos, sin): the twiddles of every radix-4 stage
     const double2 *tone;                 // [batch][T] (cos phi, sin phi) of every tone
+    double *row_max;                     // [batch][N2] max(|I|,|Q|) of the N1 bulk samples of one n2 (one IFFT CTA)
 };
 
 // tables shared by all CTAs of comb_ifft_kernel (a double-precision sincospi costs ~100 instructions: computed per
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(N1 / 4 < 32 ? 32 : N1 / 4) comb_ifft_kernel(Co
     }
     __syncthreads();
     double2 *in = bufA, *out = bufB;
+    double mx = 0.0;
 #pragma unroll 1
     for (int Ns = 1; Ns < N1; Ns *= 4) {
       if (BT == NT || tid < NT) {
@@ -231,44 +233,50 @@ __global__ void __launch_bounds__(N1 / 4 < 32 ? 32 : N1 / 4) comb_ifft_kernel(Co
         const double2 t2 = make_double2(v[1].x + v[3].x, v[1].y + v[3].y);
         const double2 t3 = make_double2(-(v[1].y - v[3].y), v[1].x - v[3].x);       // (v1 - v3) * (+j)
         const int j0 = (j - k) * 4 + k;
-        out[fft_swz(j0)] = make_double2(t0.x + t2.x, t0.y + t2.y);
-        out[fft_swz(j0 + Ns)] = make_double2(t1.x + t3.x, t1.y + t3.y);
-        out[fft_swz(j0 + 2 * Ns)] = make_double2(t0.x - t2.x, t0.y - t2.y);
-        out[fft_swz(j0 + 3 * Ns)] = make_double2(t1.x - t3.x, t1.y - t3.y);
+        const double2 o0 = make_double2(t0.x + t2.x, t0.y + t2.y), o1 = make_double2(t1.x + t3.x, t1.y + t3.y);
+        const double2 o2 = make_double2(t0.x - t2.x, t0.y - t2.y), o3 = make_double2(t1.x - t3.x, t1.y - t3.y);
+        if (Ns * 4 < N1) {
+            out[fft_swz(j0)] = o0;
+            out[fft_swz(j0 + Ns)] = o1;
+            out[fft_swz(j0 + 2 * Ns)] = o2;
+            out[fft_swz(j0 + 3 * Ns)] = o3;
+        } else {
+            // last stage (k = j, j0 = j): straight from the registers to HBM.  Sample t = n2 + N2 * n1 is stored at
+            // x[n2 * N1 + n1]: whole lines per warp (the time-ordered layout made every 16-byte store its own L1
+            // wavefront); the consumers transpose (comb_quantise_kernel) or do not care about order
+            double2 *x = p.x + (size_t)b * p.N + (size_t)n2 * N1 + j;
+            x[0] = o0; x[NT] = o1; x[2 * NT] = o2; x[3 * NT] = o3;
+            mx = fmax(fmax(fmax(fabs(o0.x), fabs(o0.y)), fmax(fabs(o1.x), fabs(o1.y))),
+                      fmax(fmax(fabs(o2.x), fabs(o2.y)), fmax(fabs(o3.x), fabs(o3.y))));
+        }
       }
-        __syncthreads();
+        if (Ns * 4 < N1) __syncthreads();
         double2 *tmp = in; in = out; out = tmp;
-    }
-    // sample t = n2 + N2 * n1 is stored at x[n2 * N1 + n1]: whole lines per warp (the time-ordered layout made every
-    // 16-byte store its own L1 wavefront); the consumers transpose (comb_quantise_kernel) or do not care about order
-    double mx = 0.0;
-    double2 *x = p.x + (size_t)b * p.N + (size_t)n2 * N1;
-    for (int n1 = tid; n1 < N1; n1 += BT) {
-        const double2 v = in[fft_swz(n1)];
-        x[n1] = v;
-        mx = fmax(mx, fmax(fabs(v.x), fabs(v.y)));
     }
     for (int d = 16; d > 0; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
     if ((tid & 31) == 0) s_red[tid >> 5] = mx;
     __syncthreads();
     if (tid == 0) {
         for (int i = 1; i < BT / 32; ++i) mx = fmax(mx, s_red[i]);
+        p.row_max[(size_t)b * p.N2 + n2] = mx;
         atomicMax(&p.maxbits[b], (unsigned long long)__double_as_longlong(mx));
     }
 }
 
-// ---- K1b: samples that can hold the max -> list.  Order-free: walks x in storage order; entry s = n2 * N1 + n1 is
-// Q at t = n2 + N2 * n1 and I at t - offset (I[t] is the real part at t + offset, ROACH_Setup_DAC.py:419-420)
-__global__ void comb_max_candidates_kernel(CombParams p) {
-    const int b = blockIdx.y;
+// ---- K1b: samples that can hold the max -> list.  One CTA per (n2, set): only the rows whose own maximum (left by
+// the IFFT CTA) reaches the limit are read at all - one to three of the N2 rows of a set.  Entry n1 of row n2 is Q at
+// t = n2 + N2 * n1 and I at t - offset (I[t] is the real part at t + offset, ROACH_Setup_DAC.py:419-420)
+__global__ void __launch_bounds__(256) comb_max_candidates_kernel(CombParams p) {
+    const int n2 = blockIdx.x, b = blockIdx.y;
     const double mx = __longlong_as_double((long long)p.maxbits[b]);
     const double lim = mx * (1.0 - 1e-8);
-    const double2 *x = p.x + (size_t)b * p.N;
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < p.N; s += gridDim.x * blockDim.x) {
-        const double2 v = x[s];
+    if (p.row_max[(size_t)b * p.N2 + n2] < lim) return;
+    const double2 *x = p.x + (size_t)b * p.N + (size_t)n2 * p.N1;
+    for (int n1 = threadIdx.x; n1 < p.N1; n1 += blockDim.x) {
+        const double2 v = x[n1];
         const bool hq = fabs(v.y) >= lim, hi = fabs(v.x) >= lim;
         if (hq | hi) {
-            const unsigned t = (unsigned)(s / p.N1) + (unsigned)p.N2 * (unsigned)(s % p.N1);
+            const unsigned t = (unsigned)n2 + (unsigned)p.N2 * (unsigned)n1;
             if (hq) {
                 const unsigned pos = atomicAdd(&p.count[b], 1u);
                 if (pos < p.cap) p.list[(size_t)b * p.cap + pos] = t | (1u << 31);
@@ -544,14 +552,13 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
     p.fs = sample_rate; p.x = x; p.maxbits = d_max; p.scale = d_scale; p.exact_max = d_emax; p.list = list;
     p.count = d_count; p.cap = cap; p.fudge = fudge; p.scale_override = scale_override; p.I = (int16_t *)dI; p.Q = (int16_t *)dQ;
     double2 *d_tw;
-    if ((rc = mkid_scratch(ctx, SCR_AUX2, ((size_t)N1 + TB) * 16, (void **)&d_tw))) return rc;
-    p.tw = d_tw; p.tone = d_tw + N1;
+    if ((rc = mkid_scratch(ctx, SCR_AUX2, ((size_t)N1 + TB) * 16 + (size_t)batch * N2 * 8, (void **)&d_tw))) return rc;
+    p.tw = d_tw; p.tone = d_tw + N1; p.row_max = (double *)(d_tw + N1 + TB);
     {
         const int n_prep = (int)std::max<size_t>((size_t)N1, TB);      // (N1 - 4) / 3 table entries, TB tones
         comb_prep_kernel<<<(n_prep + 255) / 256, 256, 0, ctx->stream>>>(p, batch, d_tw, d_tw + N1);
         MKID_CHECK_LAUNCH(ctx);
     }
-    const int gs = std::max(1, std::min(N / 256, ctx->num_sms * 8));
     const int q_tiles = ((N2 + QT_A - 1) / QT_A) * ((N1 + QT_C - 1) / QT_C);
     const size_t wsm = (size_t)4 * n_tones * 8;
     // groups of `sub` LUT sets share ONE bulk buffer of <= 512 MiB (64 sets of 2^19 samples), so a large batch does not
@@ -562,7 +569,7 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
         CombParams q = p;
         const size_t t0 = (size_t)b0 * n_tones;
         q.freq += t0; q.amp += t0; q.phase += t0; q.kbin += t0; q.tone += t0;
-        q.maxbits += b0; q.scale += b0; q.exact_max += b0; q.count += b0; q.list += (size_t)b0 * cap;
+        q.row_max += (size_t)b0 * N2; q.maxbits += b0; q.scale += b0; q.exact_max += b0; q.count += b0; q.list += (size_t)b0 * cap;
         q.I += (size_t)b0 * N; q.Q += (size_t)b0 * N;
         dim3 g1(N2, nb);
         switch (N1) {
@@ -573,7 +580,7 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
         }
         MKID_CHECK_LAUNCH(ctx);
         if (scale_override <= 0.0) {
-            comb_max_candidates_kernel<<<dim3(gs, nb), 256, 0, ctx->stream>>>(q);
+            comb_max_candidates_kernel<<<dim3(N2, nb), 256, 0, ctx->stream>>>(q);
             MKID_CHECK_LAUNCH(ctx);
             comb_exact_max_kernel<<<dim3(64, nb), 128, wsm, ctx->stream>>>(q);
             MKID_CHECK_LAUNCH(ctx);
