@@ -263,6 +263,128 @@ __global__ void __launch_bounds__(N1 / 4 < 32 ? 32 : N1 / 4) comb_ifft_kernel(Co
     }
 }
 
+// ---- K1a for N1 = 1024: radices 16 x 16 x 4.  Two of the five radix-4 stages of comb_ifft_kernel are done in registers
+// (a 16-point inverse DFT per thread), so an FFT makes three trips through shared memory instead of five: that kernel is
+// bound by shared-memory wavefronts.  One CTA of 256 threads transforms four rows n2 (64 threads each) in place.
+__device__ __forceinline__ double2 zmul(double2 a, double2 w) { return make_double2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
+__device__ __forceinline__ void idft4(double2 &a0, double2 &a1, double2 &a2, double2 &a3) {     // X[m] = sum a[r] (+j)^(r m)
+    const double2 t0 = make_double2(a0.x + a2.x, a0.y + a2.y), t1 = make_double2(a0.x - a2.x, a0.y - a2.y);
+    const double2 t2 = make_double2(a1.x + a3.x, a1.y + a3.y), t3 = make_double2(-(a1.y - a3.y), a1.x - a3.x);
+    a0 = make_double2(t0.x + t2.x, t0.y + t2.y); a1 = make_double2(t1.x + t3.x, t1.y + t3.y);
+    a2 = make_double2(t0.x - t2.x, t0.y - t2.y); a3 = make_double2(t1.x - t3.x, t1.y - t3.y);
+}
+// in place: on return y[c + 4 d] = sum_r v[r] e^{+2 pi j r (c + 4 d) / 16} sits in v[4 c + d]
+__device__ __forceinline__ void idft16(double2 (&v)[16]) {
+#pragma unroll
+    for (int bb = 0; bb < 4; ++bb) idft4(v[bb], v[4 + bb], v[8 + bb], v[12 + bb]);      // over a (r = 4 a + b): v[4 c + b] = U_b[c]
+    const double c1 = 0.92387953251128674, s1 = 0.38268343236508977, r2 = 0.70710678118654752;
+    // U_b[c] *= W^(b c), W = e^{+2 pi j / 16}
+    v[5] = zmul(v[5], make_double2(c1, s1));                                              // c = 1, b = 1: W^1
+    v[6] = make_double2((v[6].x - v[6].y) * r2, (v[6].x + v[6].y) * r2);                  // c = 1, b = 2: W^2
+    v[7] = zmul(v[7], make_double2(s1, c1));                                              // c = 1, b = 3: W^3
+    v[9] = make_double2((v[9].x - v[9].y) * r2, (v[9].x + v[9].y) * r2);                  // c = 2, b = 1: W^2
+    v[10] = make_double2(-v[10].y, v[10].x);                                              // c = 2, b = 2: W^4 = +j
+    v[11] = make_double2(-(v[11].x + v[11].y) * r2, (v[11].x - v[11].y) * r2);            // c = 2, b = 3: W^6
+    v[13] = zmul(v[13], make_double2(s1, c1));                                            // c = 3, b = 1: W^3
+    v[14] = make_double2(-(v[14].x + v[14].y) * r2, (v[14].x - v[14].y) * r2);            // c = 3, b = 2: W^6
+    v[15] = zmul(v[15], make_double2(-c1, -s1));                                          // c = 3, b = 3: W^9
+#pragma unroll
+    for (int c = 0; c < 4; ++c) idft4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);   // over b: v[4 c + d] = y[c + 4 d]
+}
+// element i of an FFT in shared memory: bank group (i & 7) XOR bits 4..6 of i.  Aligned runs of 8 elements (all loads,
+// the stores of the second stage) stay conflict-free and the first stage's stores at stride 16 spread over the groups.
+__device__ __forceinline__ int swz16(int i) { return i ^ ((i >> 4) & 7); }
+
+template <int R16_F>                                         // rows (FFTs) per CTA, 64 threads each
+__global__ void __launch_bounds__(64 * R16_F, 512 / (64 * R16_F)) comb_ifft1024_r16_kernel(CombParams p) {
+    extern __shared__ __align__(16) unsigned char smem_r16[];
+    double2 *buf_all = reinterpret_cast<double2 *>(smem_r16);           // [R16_F][1024]
+    __shared__ double s_red[8];
+    constexpr int N1 = 1024;
+    const int tid = threadIdx.x, b = blockIdx.y, f = tid >> 6, j = tid & 63;
+    const int n2_0 = blockIdx.x * R16_F, n2 = n2_0 + f;
+    double2 *buf = buf_all + f * N1;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) buf_all[tid + 64 * R16_F * i] = make_double2(0.0, 0.0);
+    __syncthreads();
+    // sparse fill of the four rows: G[k mod N1] += a e^{j phi} e^{2 pi j k n2 / N}; consecutive rows differ by e^{2 pi j k / N}
+    for (int i = tid; i < p.T; i += 64 * R16_F) {
+        const long long k = p.kbin[(size_t)b * p.T + i];
+        const long long m = (k * (long long)n2_0) & (long long)(p.N - 1);      // N is a power of two
+        double s, c, ss = 0.0, cs = 1.0;
+        sincospi(2.0 * (double)m / (double)p.N, &s, &c);
+        if (R16_F > 1) sincospi(2.0 * (double)k / (double)p.N, &ss, &cs);
+        const double2 tn = p.tone[(size_t)b * p.T + i];
+        const double a = p.amp[(size_t)b * p.T + i];
+        double2 g = zmul(make_double2(a * tn.x, a * tn.y), make_double2(c, s));
+        const int k1 = swz16((int)(k & (N1 - 1)));
+#pragma unroll
+        for (int ff = 0; ff < R16_F; ++ff) {
+            if (n2_0 + ff < p.N2) {
+                atomicAdd(&buf_all[ff * N1 + k1].x, g.x);
+                atomicAdd(&buf_all[ff * N1 + k1].y, g.y);
+            }
+            if (R16_F > 1) g = zmul(g, make_double2(cs, ss));
+        }
+    }
+    __syncthreads();
+    double2 v[16];
+    // stage A: radix 16, Ns = 1 (no twiddles): element 16 j + m
+#pragma unroll
+    for (int r = 0; r < 16; ++r) v[r] = buf[swz16(j + 64 * r)];
+    idft16(v);
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+#pragma unroll
+        for (int d = 0; d < 4; ++d) buf[swz16(16 * j + c + 4 * d)] = v[4 * c + d];
+    __syncthreads();
+    // stage B: radix 16, Ns = 16: v[r] *= e^{2 pi j r k / 256}, k = j mod 16; element (j - k) 16 + k + 16 m
+    {
+        const int k = j & 15;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) v[r] = buf[swz16(j + 64 * r)];
+        const double2 w1 = __ldg(&p.tw[(64 - 4) / 3 + k]);                   // table of stage Ns = 64: e^{2 pi j k / 256}
+        double2 w = w1;
+        v[1] = zmul(v[1], w);
+#pragma unroll
+        for (int r = 2; r < 16; ++r) { w = zmul(w, w1); v[r] = zmul(v[r], w); }
+        idft16(v);
+        __syncthreads();
+        const int base = (j - k) * 16 + k;
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int d = 0; d < 4; ++d) buf[swz16(base + 16 * (c + 4 * d))] = v[4 * c + d];
+    }
+    __syncthreads();
+    // stage C: radix 4, Ns = 256, four butterflies per thread, straight to HBM: x[n2 * N1 + jj + 256 m]
+    double mx = 0.0;
+    if (n2 < p.N2) {
+        double2 *x = p.x + (size_t)b * p.N + (size_t)n2 * N1;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int jj = j + 64 * u;
+            double2 a0 = buf[swz16(jj)], a1 = buf[swz16(jj + 256)], a2 = buf[swz16(jj + 512)], a3 = buf[swz16(jj + 768)];
+            const double2 w1 = __ldg(&p.tw[(256 - 4) / 3 + jj]);            // e^{2 pi j jj / 1024}
+            const double2 w2 = zmul(w1, w1), w3 = zmul(w2, w1);
+            a1 = zmul(a1, w1); a2 = zmul(a2, w2); a3 = zmul(a3, w3);
+            idft4(a0, a1, a2, a3);
+            x[jj] = a0; x[jj + 256] = a1; x[jj + 512] = a2; x[jj + 768] = a3;
+            mx = fmax(mx, fmax(fmax(fmax(fabs(a0.x), fabs(a0.y)), fmax(fabs(a1.x), fabs(a1.y))),
+                               fmax(fmax(fabs(a2.x), fabs(a2.y)), fmax(fabs(a3.x), fabs(a3.y)))));
+        }
+    }
+    for (int d = 16; d > 0; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+    if ((tid & 31) == 0) s_red[tid >> 5] = mx;
+    __syncthreads();
+    if (j == 0 && n2 < p.N2) {
+        mx = fmax(s_red[2 * f], s_red[2 * f + 1]);
+        p.row_max[(size_t)b * p.N2 + n2] = mx;
+        atomicMax(&p.maxbits[b], (unsigned long long)__double_as_longlong(mx));
+    }
+}
+
 // ---- K1b: samples that can hold the max -> list.  One CTA per (n2, set): only the rows whose own maximum (left by
 // the IFFT CTA) reaches the limit are read at all - one to three of the N2 rows of a set.  Entry n1 of row n2 is Q at
 // t = n2 + N2 * n1 and I at t - offset (I[t] is the real part at t + offset, ROACH_Setup_DAC.py:419-420)
@@ -534,7 +656,17 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
     if ((rc = mkid_scratch(ctx, SCR_META, meta_bytes, (void **)&meta))) return rc;
     int sub = (int)std::max<size_t>(1, ((size_t)512 << 20) / ((size_t)N * 16));
     if (const char *e = getenv("MKID_LUT_GROUP")) sub = std::max(1, atoi(e));      // experiment switch
-    sub = std::min(sub, batch);
+    bool radix16 = true;
+    if (const char *e = getenv("MKID_LUT_RADIX4")) radix16 = atoi(e) == 0;           // experiment switch: five radix-4 stages
+    int r16_f = 4;
+    if (const char *e = getenv("MKID_LUT_R16F")) r16_f = atoi(e);                     // experiment switch: rows per CTA (1, 2, 4)
+    if (radix16 && N1 == 1024) {
+        static bool attr_set[64] = {};
+        if (!attr_set[ctx->device & 63]) {
+            MKID_CUDA(ctx, cudaFuncSetAttribute(comb_ifft1024_r16_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 1024 * 16));
+            attr_set[ctx->device & 63] = true;
+        }
+    }
     if ((rc = mkid_scratch(ctx, SCR_AUX0, (size_t)sub * N * 16, (void **)&x))) return rc;
     if ((rc = mkid_scratch(ctx, SCR_AUX1, (size_t)batch * cap * 4, (void **)&list))) return rc;
     CombParams p;
@@ -576,7 +708,12 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
         case 16: comb_ifft_kernel<16><<<g1, 32, 0, ctx->stream>>>(q); break;
         case 64: comb_ifft_kernel<64><<<g1, 32, 0, ctx->stream>>>(q); break;
         case 256: comb_ifft_kernel<256><<<g1, 64, 0, ctx->stream>>>(q); break;
-        default: comb_ifft_kernel<1024><<<g1, 256, 0, ctx->stream>>>(q); break;
+        default:
+            if (radix16 && r16_f == 1) comb_ifft1024_r16_kernel<1><<<dim3(N2, nb), 64, 1024 * 16, ctx->stream>>>(q);
+            else if (radix16 && r16_f == 2) comb_ifft1024_r16_kernel<2><<<dim3((N2 + 1) / 2, nb), 128, 2 * 1024 * 16, ctx->stream>>>(q);
+            else if (radix16) comb_ifft1024_r16_kernel<4><<<dim3((N2 + 3) / 4, nb), 256, 4 * 1024 * 16, ctx->stream>>>(q);
+            else comb_ifft_kernel<1024><<<g1, 256, 0, ctx->stream>>>(q);
+            break;
         }
         MKID_CHECK_LAUNCH(ctx);
         if (scale_override <= 0.0) {
