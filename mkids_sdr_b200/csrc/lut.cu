@@ -151,6 +151,8 @@ struct CombParams {
     int16_t *I, *Q;                      // [batch][N]
     const double2 *tw;                   // [N1] e^{+2 pi j k / N1} = (cos, sin): the twiddles of every radix-4 stage
     const double2 *tone;                 // [batch][T] (cos phi, sin phi) of every tone
+    double *sigma;                       // [batch] estimate of the rms difference reference - bulk of one sample (signal units)
+    double *eps;                         // [batch] flag distance of the quantiser (LSB)
     double *row_max;                     // [batch][N2] max(|I|,|Q|) of the N1 bulk samples of one n2 (one IFFT CTA)
 };
 
@@ -172,6 +174,17 @@ __global__ void comb_prep_kernel(CombParams p, int batch, double2 *tw, double2 *
         double sp, cp;
         sincos(p.phase[i], &sp, &cp);
         tone[i] = make_double2(cp, sp);
+    }
+    if (i < batch) {
+        // The reference rounds 2*pi*f, the product with t, the division by fs and the sum with phi: four roundings of an
+        // argument of up to 2 pi N rad, each below 2^-53 relative, independent from tone to tone.  The bulk IFFT has none
+        // of them (its own error is ~1e-15 of the scale), so reference - bulk of one sample is a sum of T terms
+        // a_n * (argument error): rms below 2.2e-16 * 2 pi N * sqrt(sum a_n^2) (twice the rms of four uniform roundings
+        // at the LARGEST argument).  Candidates for the max and samples near a truncation boundary are taken within
+        // 8 of these sigmas and re-evaluated in the reference's order.
+        double ss = 0.0;
+        for (int n = 0; n < p.T; ++n) { const double a = p.amp[(size_t)i * p.T + n]; ss += a * a; }
+        p.sigma[i] = 2.2e-16 * 6.283185307179586 * (double)p.N * sqrt(ss);
     }
 }
 
@@ -391,7 +404,7 @@ __global__ void __launch_bounds__(64 * R16_F, 512 / (64 * R16_F)) comb_ifft1024_
 __global__ void __launch_bounds__(256) comb_max_candidates_kernel(CombParams p) {
     const int n2 = blockIdx.x, b = blockIdx.y;
     const double mx = __longlong_as_double((long long)p.maxbits[b]);
-    const double lim = mx * (1.0 - 1e-8);
+    const double lim = mx - fmax(1e-8 * mx, 8.0 * p.sigma[b]);
     if (p.row_max[(size_t)b * p.N2 + n2] < lim) return;
     const double2 *x = p.x + (size_t)b * p.N + (size_t)n2 * p.N1;
     for (int n1 = threadIdx.x; n1 < p.N1; n1 += blockDim.x) {
@@ -449,6 +462,8 @@ __global__ void comb_scale_kernel(CombParams p, int batch) {
     if (p.fudge != 1.0) sc = __dmul_rn(p.fudge, sc);           // scaleFudgeFactor*scale_factor (:453-455)
     if (p.scale_override > 0.0) sc = p.scale_override;         // keep-old / custom scale       (:456-459)
     p.scale[b] = sc;
+    // flag distance in LSB: 8 sigma, at least 1e-7 (covers the bulk's own error)
+    p.eps[b] = fmax(1e-7, 8.0 * p.sigma[b] * 32767.0 / sc);
     p.count[b] = 0;                                            // the list is reused by the quantiser
 }
 
@@ -458,12 +473,13 @@ __global__ void comb_scale_kernel(CombParams p, int batch) {
 // so x * (32767 / scale) truncates to the same integer as the reference's (x * 32767) / scale; the flagged ones are
 // overwritten by comb_fixup_kernel with the reference-order value.
 constexpr int QT_A = 64, QT_C = 32;
-__global__ void __launch_bounds__(256) comb_quantise_kernel(CombParams p, double eps) {
+__global__ void __launch_bounds__(256) comb_quantise_kernel(CombParams p) {
     __shared__ int16_t sI[QT_C][QT_A + 2], sQ[QT_C][QT_A + 2];
     const int b = blockIdx.y, tid = threadIdx.x;
     const int tiles_c = (p.N1 + QT_C - 1) / QT_C;
     const int a0 = (blockIdx.x / tiles_c) * QT_A, c0 = (blockIdx.x % tiles_c) * QT_C;
     const double rs = __ddiv_rn(32767.0, p.scale[b]);
+    const double eps = p.eps[b];
     const double2 *x = p.x + (size_t)b * p.N;
     const unsigned nmask = (unsigned)(p.N - 1);
 #pragma unroll
@@ -684,8 +700,8 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
     p.fs = sample_rate; p.x = x; p.maxbits = d_max; p.scale = d_scale; p.exact_max = d_emax; p.list = list;
     p.count = d_count; p.cap = cap; p.fudge = fudge; p.scale_override = scale_override; p.I = (int16_t *)dI; p.Q = (int16_t *)dQ;
     double2 *d_tw;
-    if ((rc = mkid_scratch(ctx, SCR_AUX2, ((size_t)N1 + TB) * 16 + (size_t)batch * N2 * 8, (void **)&d_tw))) return rc;
-    p.tw = d_tw; p.tone = d_tw + N1; p.row_max = (double *)(d_tw + N1 + TB);
+    if ((rc = mkid_scratch(ctx, SCR_AUX2, ((size_t)N1 + TB) * 16 + (size_t)batch * (N2 + 2) * 8, (void **)&d_tw))) return rc;
+    p.tw = d_tw; p.tone = d_tw + N1; p.sigma = (double *)(d_tw + N1 + TB); p.eps = p.sigma + batch; p.row_max = p.eps + batch;
     {
         const int n_prep = (int)std::max<size_t>((size_t)N1, TB);      // (N1 - 4) / 3 table entries, TB tones
         comb_prep_kernel<<<(n_prep + 255) / 256, 256, 0, ctx->stream>>>(p, batch, d_tw, d_tw + N1);
@@ -701,7 +717,7 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
         CombParams q = p;
         const size_t t0 = (size_t)b0 * n_tones;
         q.freq += t0; q.amp += t0; q.phase += t0; q.kbin += t0; q.tone += t0;
-        q.row_max += (size_t)b0 * N2; q.maxbits += b0; q.scale += b0; q.exact_max += b0; q.count += b0; q.list += (size_t)b0 * cap;
+        q.row_max += (size_t)b0 * N2; q.sigma += b0; q.eps += b0; q.maxbits += b0; q.scale += b0; q.exact_max += b0; q.count += b0; q.list += (size_t)b0 * cap;
         q.I += (size_t)b0 * N; q.Q += (size_t)b0 * N;
         dim3 g1(N2, nb);
         switch (N1) {
@@ -724,7 +740,7 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
         }
         comb_scale_kernel<<<(nb + 63) / 64, 64, 0, ctx->stream>>>(q, nb);
         MKID_CHECK_LAUNCH(ctx);
-        comb_quantise_kernel<<<dim3(q_tiles, nb), 256, 0, ctx->stream>>>(q, 1e-4);
+        comb_quantise_kernel<<<dim3(q_tiles, nb), 256, 0, ctx->stream>>>(q);
         MKID_CHECK_LAUNCH(ctx);
         comb_fixup_kernel<<<dim3(64, nb), 128, wsm, ctx->stream>>>(q);
         MKID_CHECK_LAUNCH(ctx);
