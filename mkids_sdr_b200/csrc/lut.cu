@@ -137,7 +137,8 @@ __device__ __forceinline__ double ref_arg(double f, double t, double fs, double 
 
 struct CombParams {
     const double *freq, *amp, *phase;    // [batch][T]
-    const long long *kbin;               // [batch][T] spectral line index in [0, N)
+    long long *kbin;                     // [batch][T] spectral line index in [0, N) (written by comb_prep_kernel)
+    unsigned int *bad;                   // set when a tone is not on the fs/N grid
     int T, N, N1, N2, offset;
     double fs;
     double2 *x;                          // [batch][N] bulk result
@@ -174,6 +175,13 @@ __global__ void comb_prep_kernel(CombParams p, int batch, double2 *tw, double2 *
         double sp, cp;
         sincos(p.phase[i], &sp, &cp);
         tone[i] = make_double2(cp, sp);
+        // spectral line of the tone; must be on the fs/N grid (define_DAC_LUT snaps to it, :498)
+        const double k = __ddiv_rn(__dmul_rn(p.freq[i], (double)p.N), p.fs);
+        const double kr = rint(k);
+        if (!(fabs(k - kr) < 1e-6)) atomicOr(p.bad, 1u);
+        long long kk = (long long)kr % p.N;
+        if (kk < 0) kk += p.N;
+        p.kbin[i] = kk;
     }
     if (i < batch) {
         // The reference rounds 2*pi*f, the product with t, the division by fs and the sum with phi: four roundings of an
@@ -641,27 +649,15 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
     const int N2 = N / N1;
     MKID_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t TB = (size_t)batch * n_tones;
-    // host: spectral line of every tone; must be on the fs/N grid (define_DAC_LUT snaps to it, :498)
-    // one host block in the device layout freq | amp | phase | kbin: a single upload
-    std::vector<double> hmeta(TB * 4);
+    // one host block in the device layout freq | amp | phase: a single upload (the spectral lines are derived on the GPU)
+    std::vector<double> hmeta(TB * 3);
     double *ph = hmeta.data() + 2 * TB;
-    long long *kbin = reinterpret_cast<long long *>(hmeta.data() + 3 * TB);
     memcpy(hmeta.data(), freq_hz, TB * 8);
     memcpy(hmeta.data() + TB, amp, TB * 8);
     memcpy(ph, phase, TB * 8);
-    for (int b = 0; b < batch; ++b) {
-        if (random_phase) {                                   // every call re-seeds (:426): the same draws for every set
-            if (b == 0) mkid_random_phases(1000u, n_tones, ph);
-            else memcpy(ph + (size_t)b * n_tones, ph, (size_t)n_tones * 8);
-        }
-        for (int i = 0; i < n_tones; ++i) {
-            const double k = freq_hz[(size_t)b * n_tones + i] * (double)N / sample_rate;
-            const double kr = nearbyint(k);
-            MKID_REQUIRE(ctx, fabs(k - kr) < 1e-6, "comb_lut: tone frequency is not a multiple of sampleRate/n_samples");
-            long long kk = (long long)kr % N;
-            if (kk < 0) kk += N;
-            kbin[(size_t)b * n_tones + i] = kk;
-        }
+    if (random_phase) {                                       // every call re-seeds (:426): the same draws for every set
+        mkid_random_phases(1000u, n_tones, ph);
+        for (int b = 1; b < batch; ++b) memcpy(ph + (size_t)b * n_tones, ph, (size_t)n_tones * 8);
     }
     if (random_phase) memcpy(phase, ph, TB * 8);
     // device buffers
@@ -691,14 +687,14 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
     unsigned long long *d_max = (unsigned long long *)(d_k + TB), *d_emax = d_max + batch;
     double *d_scale = (double *)(d_emax + batch);
     unsigned *d_count = (unsigned *)(d_scale + batch);
-    MKID_CUDA(ctx, cudaMemcpyAsync(d_freq, hmeta.data(), TB * 32, cudaMemcpyHostToDevice, ctx->stream));
+    MKID_CUDA(ctx, cudaMemcpyAsync(d_freq, hmeta.data(), TB * 24, cudaMemcpyHostToDevice, ctx->stream));
     MKID_CUDA(ctx, cudaMemsetAsync(d_max, 0, (size_t)batch * 48 - 0, ctx->stream));
     void *dI, *dQ;
     if ((rc = mkid_stage_out(ctx, I, (size_t)batch * N * 2, SCR_OUT0, false, &dI))) return rc;
     if ((rc = mkid_stage_out(ctx, Q, (size_t)batch * N * 2, SCR_OUT1, false, &dQ))) return rc;
     p.freq = d_freq; p.amp = d_amp; p.phase = d_phase; p.kbin = d_k; p.T = n_tones; p.N = N; p.N1 = N1; p.N2 = N2; p.offset = offset;
     p.fs = sample_rate; p.x = x; p.maxbits = d_max; p.scale = d_scale; p.exact_max = d_emax; p.list = list;
-    p.count = d_count; p.cap = cap; p.fudge = fudge; p.scale_override = scale_override; p.I = (int16_t *)dI; p.Q = (int16_t *)dQ;
+    p.count = d_count; p.bad = d_count + batch; p.cap = cap; p.fudge = fudge; p.scale_override = scale_override; p.I = (int16_t *)dI; p.Q = (int16_t *)dQ;
     double2 *d_tw;
     if ((rc = mkid_scratch(ctx, SCR_AUX2, ((size_t)N1 + TB) * 16 + (size_t)batch * (N2 + 2) * 8, (void **)&d_tw))) return rc;
     p.tw = d_tw; p.tone = d_tw + N1; p.sigma = (double *)(d_tw + N1 + TB); p.eps = p.sigma + batch; p.row_max = p.eps + batch;
@@ -746,11 +742,12 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
         MKID_CHECK_LAUNCH(ctx);
     }
     // overflow of the candidate / fix-up list would silently skip exact re-evaluation: check
-    std::vector<double> back((size_t)batch + (batch + 1) / 2);          // scale[batch] | count[batch]: adjacent on the device
-    MKID_CUDA(ctx, cudaMemcpyAsync(back.data(), d_scale, (size_t)batch * 12, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<double> back((size_t)batch + (batch + 2) / 2);          // scale[batch] | count[batch] | bad: adjacent on the device
+    MKID_CUDA(ctx, cudaMemcpyAsync(back.data(), d_scale, (size_t)batch * 12 + 4, cudaMemcpyDeviceToHost, ctx->stream));
     MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const double *sc = back.data();
     const unsigned *cnt = reinterpret_cast<const unsigned *>(back.data() + batch);
+    MKID_REQUIRE(ctx, cnt[batch] == 0, "comb_lut: tone frequency is not a multiple of sampleRate/n_samples");
     for (int b = 0; b < batch; ++b) {
         if (cnt[b] > cap) return mkid_fail(ctx, MKID_EINVAL, "comb_lut: %u samples need exact re-evaluation (> %u)", cnt[b], cap);
         if (scale_out) scale_out[b] = sc[b];

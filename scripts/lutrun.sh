@@ -1,4 +1,2 @@
 timeout 300 python -m pytest tests/test_lut_gpu.py tests/test_forms_gpu.py -m gpu -x -q 2>&1 | tail -4
 python scripts/bench_lut.py 2>&1 | tail -7
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 18 --csv --log-file gpurun_out/r01d_launches_lut.csv python scripts/prof_lut.py 64 > gpurun_out/ncu_lut.log 2>&1; tail -1 gpurun_out/ncu_lut.log
-ncu --set full --clock-control none --import-source on -k regex:comb_ifft1024 -s 1 -c 1 -f -o gpurun_out/r01d_k1_ifft_r16 python scripts/prof_lut.py 64 > gpurun_out/ncu_lut2.log 2>&1; tail -1 gpurun_out/ncu_lut2.log

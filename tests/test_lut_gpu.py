@@ -113,6 +113,21 @@ def test_comb_lut_small_tables_and_groups(ctx, N, T, offset, monkeypatch):
         assert sc[b] == so and np.array_equal(I[b], Io) and np.array_equal(Q[b], Qo)
 
 
+def test_comb_lut_rejects_off_grid_tone(ctx):
+    """freqCombLUT is only called with tones snapped to the fs/N grid (define_DAC_LUT, ROACH_Setup.py:498); a tone
+    off the grid has no spectral line and must be an error, in any set of the batch, and the context stays usable."""
+    from mkids_sdr_b200 import lut
+    from mkids_sdr_b200._lib import MkidError
+    N = 2 ** 12
+    good = np.array([3.0, 17.0, 900.0]) * FS / N
+    bad = good.copy(); bad[1] += 0.3 * FS / N
+    with pytest.raises(MkidError, match='not a multiple'):
+        lut.comb_lut([good, bad], FS, N, [1.0, 0.5, 0.25], ctx=ctx)
+    I, Q, sc, ph = lut.comb_lut(good, FS, N, [1.0, 0.5, 0.25], ctx=ctx)
+    Io, Qo, so, _ = olut.freq_comb_lut('yes', list(good), FS, FS / N, [1.0, 0.5, 0.25])
+    assert sc[0] == so and np.array_equal(I[0], Io) and np.array_equal(Q[0], Qo)
+
+
 @pytest.mark.parametrize('N', [2 ** 16, 2 ** 19])
 def test_dds_lut_and_dram_identical_to_oracle(ctx, N):
     from mkids_sdr_b200 import lut
