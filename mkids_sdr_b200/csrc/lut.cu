@@ -432,33 +432,35 @@ __global__ void __launch_bounds__(256) comb_max_candidates_kernel(CombParams p) 
     }
 }
 
-// reference-order evaluation of one sample by one warp: terms in parallel, sum sequentially
+// reference-order evaluation of one sample by the whole CTA: terms in parallel (T / 128 double-double sin or cos per
+// thread: the latency of a call with few sets is the latency of ONE sample), sum sequentially in tone order
 __device__ double exact_sample(const CombParams &p, int b, int t, int isQ, double *s_terms) {
-    const int lane = threadIdx.x & 31;
     const double tt = isQ ? (double)t : (double)(t + p.offset);
-    for (int i = lane; i < p.T; i += 32) {
+    for (int i = threadIdx.x; i < p.T; i += blockDim.x) {
         const double arg = ref_arg(p.freq[(size_t)b * p.T + i], tt, p.fs, p.phase[(size_t)b * p.T + i]);
         s_terms[i] = __dmul_rn(p.amp[(size_t)b * p.T + i], sin_or_cos_cr(arg, !isQ));
     }
-    __syncwarp();
-    double acc = 0.0;
-    if (lane == 0)
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double acc = 0.0;
         for (int i = 0; i < p.T; ++i) acc = __dadd_rn(acc, s_terms[i]);
-    acc = __shfl_sync(0xffffffffu, acc, 0);
-    __syncwarp();
+        s_terms[p.T] = acc;
+    }
+    __syncthreads();
+    const double acc = s_terms[p.T];
+    __syncthreads();                     // the next sample overwrites s_terms
     return acc;
 }
 
-// ---- K1c: exact max over the candidates (one warp per candidate), then the scale
+// ---- K1c: exact max over the candidates (one CTA per candidate), then the scale
 __global__ void __launch_bounds__(128) comb_exact_max_kernel(CombParams p) {
     extern __shared__ double s_dyn[];
-    const int b = blockIdx.y, warp = threadIdx.x >> 5;
-    double *terms = s_dyn + (size_t)warp * p.T;
+    const int b = blockIdx.y;
     const unsigned n = min(p.count[b], p.cap);
-    for (unsigned c = blockIdx.x * 4 + warp; c < n; c += gridDim.x * 4) {
+    for (unsigned c = blockIdx.x; c < n; c += gridDim.x) {
         const unsigned e = p.list[(size_t)b * p.cap + c];
-        const double v = fabs(exact_sample(p, b, (int)(e & 0x7fffffffu), (int)(e >> 31), terms));
-        if ((threadIdx.x & 31) == 0) atomicMax(&p.exact_max[b], (unsigned long long)__double_as_longlong(v));
+        const double v = fabs(exact_sample(p, b, (int)(e & 0x7fffffffu), (int)(e >> 31), s_dyn));
+        if (threadIdx.x == 0) atomicMax(&p.exact_max[b], (unsigned long long)__double_as_longlong(v));
     }
 }
 
@@ -528,16 +530,15 @@ __global__ void __launch_bounds__(256) comb_quantise_kernel(CombParams p) {
 // ---- K1e: exact re-evaluation of the flagged samples
 __global__ void __launch_bounds__(128) comb_fixup_kernel(CombParams p) {
     extern __shared__ double s_dyn[];
-    const int b = blockIdx.y, warp = threadIdx.x >> 5;
-    double *terms = s_dyn + (size_t)warp * p.T;
+    const int b = blockIdx.y;
     const unsigned n = min(p.count[b], p.cap);
     const double sc = p.scale[b];
-    for (unsigned c = blockIdx.x * 4 + warp; c < n; c += gridDim.x * 4) {
+    for (unsigned c = blockIdx.x; c < n; c += gridDim.x) {
         const unsigned e = p.list[(size_t)b * p.cap + c];
         const int t = (int)(e & 0x7fffffffu), isQ = (int)(e >> 31);
-        const double x = exact_sample(p, b, t, isQ, terms);
+        const double x = exact_sample(p, b, t, isQ, s_dyn);
         const double v = __ddiv_rn(__dmul_rn(x, 32767.0), sc);           // int(i*amp_full_scale/scale_factor) (:461-462)
-        if ((threadIdx.x & 31) == 0)
+        if (threadIdx.x == 0)
             (isQ ? p.Q : p.I)[(size_t)b * p.N + t] = (int16_t)max(-32768, min(32767, __double2int_rz(v)));
     }
 }
@@ -704,7 +705,8 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
         MKID_CHECK_LAUNCH(ctx);
     }
     const int q_tiles = ((N2 + QT_A - 1) / QT_A) * ((N1 + QT_C - 1) / QT_C);
-    const size_t wsm = (size_t)4 * n_tones * 8;
+    const size_t wsm = (size_t)(n_tones + 1) * 8;
+    const int fix_ctas = batch >= 16 ? 64 : 256;             // few sets: spread the ~100 flagged samples of a set
     // groups of `sub` LUT sets share ONE bulk buffer of <= 512 MiB (64 sets of 2^19 samples), so a large batch does not
     // scale the scratch.  Measured: L2-sized groups (4 / 8 / 16 sets) are SLOWER, 40 / 54.5 / 55.4 k sets per second
     // against 74.3 k for groups of 64: short launches pay their tails, the L2 hits do not make up for it.
@@ -731,14 +733,14 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
         if (scale_override <= 0.0) {
             comb_max_candidates_kernel<<<dim3(N2, nb), 256, 0, ctx->stream>>>(q);
             MKID_CHECK_LAUNCH(ctx);
-            comb_exact_max_kernel<<<dim3(64, nb), 128, wsm, ctx->stream>>>(q);
+            comb_exact_max_kernel<<<dim3(16, nb), 128, wsm, ctx->stream>>>(q);
             MKID_CHECK_LAUNCH(ctx);
         }
         comb_scale_kernel<<<(nb + 63) / 64, 64, 0, ctx->stream>>>(q, nb);
         MKID_CHECK_LAUNCH(ctx);
         comb_quantise_kernel<<<dim3(q_tiles, nb), 256, 0, ctx->stream>>>(q);
         MKID_CHECK_LAUNCH(ctx);
-        comb_fixup_kernel<<<dim3(64, nb), 128, wsm, ctx->stream>>>(q);
+        comb_fixup_kernel<<<dim3(fix_ctas, nb), 128, wsm, ctx->stream>>>(q);
         MKID_CHECK_LAUNCH(ctx);
     }
     // overflow of the candidate / fix-up list would silently skip exact re-evaluation: check
