@@ -317,7 +317,7 @@ __device__ __forceinline__ void idft16(double2 (&v)[16]) {
 __device__ __forceinline__ int swz16(int i) { return i ^ ((i >> 4) & 7); }
 
 template <int R16_F>                                         // rows (FFTs) per CTA, 64 threads each
-__global__ void __launch_bounds__(64 * R16_F, 512 / (64 * R16_F)) comb_ifft1024_r16_kernel(CombParams p) {
+__global__ void __launch_bounds__(64 * R16_F, 768 / (64 * R16_F)) comb_ifft1024_r16_kernel(CombParams p) {
     extern __shared__ __align__(16) unsigned char smem_r16[];
     double2 *buf_all = reinterpret_cast<double2 *>(smem_r16);           // [R16_F][1024]
     __shared__ double s_red[8];
