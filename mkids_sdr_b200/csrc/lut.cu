@@ -5,8 +5,10 @@
 //
 // K1  every comb frequency is a multiple of fs/N, so I + jQ = N * IDFT(X) with one spectral line
 //     per tone.  Bulk: four-step fp64 IFFT, N = N2 x N1 (N1 a power of four <= 1024): for each
-//     n2 < N2 a shared-memory Stockham radix-4 IFFT of length N1 over the (sparse) lines, fused
-//     with the global max search.  The reference evaluates every sample as a sequential float64 sum of
+//     n2 < N2 a shared-memory Stockham IFFT of length N1 over the (sparse) lines (N1 = 1024, the
+//     2^19-sample tables: radices 16 x 16 x 4 with the 16-point DFTs in registers; shorter tables:
+//     radix 4), fused with the max search; then max candidates -> exact max -> scale -> tiled-
+//     transpose quantise -> exact fix-up of the flagged samples.  The reference evaluates every sample as a sequential float64 sum of
 //     a*cos(((2*pi*f)*t)/fs + phi); its int() truncation can flip on samples whose scaled value
 //     is within the reference's own rounding error of an integer.  Those samples (and the
 //     candidates for the max that sets the scale) are re-evaluated in the reference's operation
@@ -205,6 +207,14 @@ __device__ __forceinline__ int fft_swz(int i) {
     return i ^ ((h ^ (h << 1)) & 7);
 }
 
+__device__ __forceinline__ double2 zmul(double2 a, double2 w) { return make_double2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
+__device__ __forceinline__ void idft4(double2 &a0, double2 &a1, double2 &a2, double2 &a3) {     // X[m] = sum a[r] (+j)^(r m)
+    const double2 t0 = make_double2(a0.x + a2.x, a0.y + a2.y), t1 = make_double2(a0.x - a2.x, a0.y - a2.y);
+    const double2 t2 = make_double2(a1.x + a3.x, a1.y + a3.y), t3 = make_double2(-(a1.y - a3.y), a1.x - a3.x);
+    a0 = make_double2(t0.x + t2.x, t0.y + t2.y); a1 = make_double2(t1.x + t3.x, t1.y + t3.y);
+    a2 = make_double2(t0.x - t2.x, t0.y - t2.y); a3 = make_double2(t1.x - t3.x, t1.y - t3.y);
+}
+
 // ---- K1a: per (n2, batch) a length-N1 Stockham radix-4 IFFT in shared memory
 template <int N1>
 __global__ void __launch_bounds__(N1 / 4 < 32 ? 32 : N1 / 4) comb_ifft_kernel(CombParams p) {
@@ -222,56 +232,48 @@ __global__ void __launch_bounds__(N1 / 4 < 32 ? 32 : N1 / 4) comb_ifft_kernel(Co
         double s, c;
         sincospi(2.0 * (double)m / (double)p.N, &s, &c);
         const double2 tn = p.tone[(size_t)b * p.T + i];
-        const double cp = tn.x, sp = tn.y;
         const double a = p.amp[(size_t)b * p.T + i];
-        const double re = a * (c * cp - s * sp), im = a * (s * cp + c * sp);
-        const int k1 = (int)(k & (N1 - 1));
-        atomicAdd(&bufA[fft_swz(k1)].x, re);
-        atomicAdd(&bufA[fft_swz(k1)].y, im);
+        const double2 g = zmul(make_double2(a * tn.x, a * tn.y), make_double2(c, s));
+        const int k1 = fft_swz((int)(k & (N1 - 1)));
+        atomicAdd(&bufA[k1].x, g.x);
+        atomicAdd(&bufA[k1].y, g.y);
     }
     __syncthreads();
     double2 *in = bufA, *out = bufB;
     double mx = 0.0;
 #pragma unroll 1
     for (int Ns = 1; Ns < N1; Ns *= 4) {
-      if (BT == NT || tid < NT) {
-        const int j = tid, k = j % Ns;
-        double2 v[4];
+        const bool last = Ns * 4 == N1;
+        if (BT == NT || tid < NT) {
+            const int j = tid, k = j % Ns;
+            double2 v[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) v[r] = in[fft_swz(j + r * NT)];
-        if (Ns > 1) {
-            // the bulk result only has to be good to ~1e-9 relative (samples within 1e-4 LSB of a rounding boundary are
-            // re-evaluated exactly): w^2 and w^3 by multiplication instead of two more table reads
-            const double2 w1 = __ldg(&p.tw[(Ns - 4) / 3 + k]);                  // e^{+2 pi j k/(4 Ns)}
-            const double2 w2 = make_double2(w1.x * w1.x - w1.y * w1.y, 2.0 * w1.x * w1.y);
-            const double2 w3 = make_double2(w2.x * w1.x - w2.y * w1.y, w2.x * w1.y + w2.y * w1.x);
-            v[1] = make_double2(v[1].x * w1.x - v[1].y * w1.y, v[1].x * w1.y + v[1].y * w1.x);
-            v[2] = make_double2(v[2].x * w2.x - v[2].y * w2.y, v[2].x * w2.y + v[2].y * w2.x);
-            v[3] = make_double2(v[3].x * w3.x - v[3].y * w3.y, v[3].x * w3.y + v[3].y * w3.x);
+            for (int r = 0; r < 4; ++r) v[r] = in[fft_swz(j + r * NT)];
+            if (Ns > 1) {
+                // the bulk result only has to be good to ~1e-9 relative (samples within eps LSB of a rounding boundary
+                // are re-evaluated exactly): w^2 and w^3 by multiplication instead of two more table reads
+                const double2 w1 = __ldg(&p.tw[(Ns - 4) / 3 + k]);              // e^{+2 pi j k/(4 Ns)}
+                const double2 w2 = zmul(w1, w1), w3 = zmul(w2, w1);
+                v[1] = zmul(v[1], w1); v[2] = zmul(v[2], w2); v[3] = zmul(v[3], w3);
+            }
+            idft4(v[0], v[1], v[2], v[3]);                                      // inverse radix-4 butterfly (twiddle +j)
+            if (!last) {
+                const int j0 = (j - k) * 4 + k;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) out[fft_swz(j0 + r * Ns)] = v[r];
+            } else {
+                // last stage (k = j, j0 = j): straight from the registers to HBM.  Sample t = n2 + N2 * n1 is stored at
+                // x[n2 * N1 + n1]: whole lines per warp (the time-ordered layout made every 16-byte store its own L1
+                // wavefront); the consumers transpose (comb_quantise_kernel) or do not care about order
+                double2 *x = p.x + (size_t)b * p.N + (size_t)n2 * N1 + j;
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    x[r * NT] = v[r];
+                    mx = fmax(mx, fmax(fabs(v[r].x), fabs(v[r].y)));
+                }
+            }
         }
-        // inverse radix-4 butterfly (twiddle +j)
-        const double2 t0 = make_double2(v[0].x + v[2].x, v[0].y + v[2].y), t1 = make_double2(v[0].x - v[2].x, v[0].y - v[2].y);
-        const double2 t2 = make_double2(v[1].x + v[3].x, v[1].y + v[3].y);
-        const double2 t3 = make_double2(-(v[1].y - v[3].y), v[1].x - v[3].x);       // (v1 - v3) * (+j)
-        const int j0 = (j - k) * 4 + k;
-        const double2 o0 = make_double2(t0.x + t2.x, t0.y + t2.y), o1 = make_double2(t1.x + t3.x, t1.y + t3.y);
-        const double2 o2 = make_double2(t0.x - t2.x, t0.y - t2.y), o3 = make_double2(t1.x - t3.x, t1.y - t3.y);
-        if (Ns * 4 < N1) {
-            out[fft_swz(j0)] = o0;
-            out[fft_swz(j0 + Ns)] = o1;
-            out[fft_swz(j0 + 2 * Ns)] = o2;
-            out[fft_swz(j0 + 3 * Ns)] = o3;
-        } else {
-            // last stage (k = j, j0 = j): straight from the registers to HBM.  Sample t = n2 + N2 * n1 is stored at
-            // x[n2 * N1 + n1]: whole lines per warp (the time-ordered layout made every 16-byte store its own L1
-            // wavefront); the consumers transpose (comb_quantise_kernel) or do not care about order
-            double2 *x = p.x + (size_t)b * p.N + (size_t)n2 * N1 + j;
-            x[0] = o0; x[NT] = o1; x[2 * NT] = o2; x[3 * NT] = o3;
-            mx = fmax(fmax(fmax(fabs(o0.x), fabs(o0.y)), fmax(fabs(o1.x), fabs(o1.y))),
-                      fmax(fmax(fabs(o2.x), fabs(o2.y)), fmax(fabs(o3.x), fabs(o3.y))));
-        }
-      }
-        if (Ns * 4 < N1) __syncthreads();
+        if (!last) __syncthreads();
         double2 *tmp = in; in = out; out = tmp;
     }
     for (int d = 16; d > 0; d >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, d));
@@ -287,13 +289,6 @@ __global__ void __launch_bounds__(N1 / 4 < 32 ? 32 : N1 / 4) comb_ifft_kernel(Co
 // ---- K1a for N1 = 1024: radices 16 x 16 x 4.  Two of the five radix-4 stages of comb_ifft_kernel are done in registers
 // (a 16-point inverse DFT per thread), so an FFT makes three trips through shared memory instead of five: that kernel is
 // bound by shared-memory wavefronts.  One CTA of 256 threads transforms four rows n2 (64 threads each) in place.
-__device__ __forceinline__ double2 zmul(double2 a, double2 w) { return make_double2(a.x * w.x - a.y * w.y, a.x * w.y + a.y * w.x); }
-__device__ __forceinline__ void idft4(double2 &a0, double2 &a1, double2 &a2, double2 &a3) {     // X[m] = sum a[r] (+j)^(r m)
-    const double2 t0 = make_double2(a0.x + a2.x, a0.y + a2.y), t1 = make_double2(a0.x - a2.x, a0.y - a2.y);
-    const double2 t2 = make_double2(a1.x + a3.x, a1.y + a3.y), t3 = make_double2(-(a1.y - a3.y), a1.x - a3.x);
-    a0 = make_double2(t0.x + t2.x, t0.y + t2.y); a1 = make_double2(t1.x + t3.x, t1.y + t3.y);
-    a2 = make_double2(t0.x - t2.x, t0.y - t2.y); a3 = make_double2(t1.x - t3.x, t1.y - t3.y);
-}
 // in place: on return y[c + 4 d] = sum_r v[r] e^{+2 pi j r (c + 4 d) / 16} sits in v[4 c + d]
 __device__ __forceinline__ void idft16(double2 (&v)[16]) {
 #pragma unroll
