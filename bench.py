@@ -575,7 +575,33 @@ def lut_side_bench(ctx):
                                                        'GB/s_written': batch * N * 4 / dt / 1e9}
             for v in kw.values():
                 v.free()
-    out['workload'] = '256 tones, 2^19-sample int16 I/Q comb (freqCombLUT incl. seed-1000 phases, scale, exact quantisation)'
+    # the whole LUT set of one board: comb + the 256 DDS tables + the 8*N-byte DRAM image (define_LUTs + write_LUTs),
+    # everything left in HBM
+    res = FS / N
+    resid = np.rint((f - np.rint(f * 512 / FS) * FS / 512) / res) * res      # select_bins (ROACH_Setup.py:534-550)
+    for batch in (1, 64):
+        ff = np.tile(f, (batch, 1)); aa = np.tile(amps, (batch, 1)); rr = np.tile(resid, (batch, 1))
+        bufs = [ctx.alloc(batch * N * 2) for _ in range(4)]
+        img = ctx.alloc(batch * N * 8)
+
+        def one():
+            lut.comb_lut(ff, FS, N, aa, ctx=ctx, out_I=bufs[0], out_Q=bufs[1])
+            lut.dds_lut(rr, np.zeros_like(rr), FS, N, ctx=ctx, out_I=bufs[2], out_Q=bufs[3])
+            lut.pack_dram(bufs[0], bufs[1], bufs[2], bufs[3], ctx=ctx, n=batch * N, out=img)
+        one()
+        ctx.sync()
+        t0 = time.time()
+        reps = 5
+        for _ in range(reps):
+            one()
+        ctx.sync()
+        dt = (time.time() - t0) / reps
+        out['full_set_batch%d_device' % batch] = {'luts_per_s': batch / dt, 'ms_per_call': dt * 1e3,
+                                                  'GB/s_written': batch * N * 16 / dt / 1e9}
+        for v in bufs + [img]:
+            v.free()
+    out['workload'] = ('256 tones, 2^19-sample int16 I/Q comb (freqCombLUT incl. seed-1000 phases, scale, exact quantisation); '
+                       'full_set = comb + 256 DDS tables + DRAM image (16 B per sample written)')
     return out
 
 

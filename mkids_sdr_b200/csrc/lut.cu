@@ -538,21 +538,32 @@ __global__ void __launch_bounds__(128) comb_fixup_kernel(CombParams p) {
     }
 }
 
-// ---- K2: DDS tables, one CTA per (channel, batch); direct reference-order evaluation
+// ---- K2: DDS tables, one CTA per (channel, batch).  The argument of every sample is the reference's own float64
+// expression (ref_arg), so only sin / cos decide the result.  Bulk: the CUDA double-precision sincos (<= 2 ulp, i.e.
+// <= 1.5e-11 LSB after scaling) for all samples; the correctly rounded double-double series (13 times the work) only
+// where it can matter: the samples that can hold the table's maximum (its exact value is the scale) and the samples
+// whose scaled value is within 1e-9 LSB of a truncation boundary.  The residuals are multiples of fs2/size, so sin and
+// cos hit 0 and +-1 often (~1 % of the samples are of either kind, thousands in a channel whose residual is a multiple
+// of a high power of two): they are first collected in a shared-memory list and then evaluated by all threads of the
+// CTA, not in divergent branches.
 __global__ void __launch_bounds__(256) dds_lut_kernel(const double *resid, const double *phase, double fs2, int size,
                                                       int n_lut, int ch_shift, int offset, int16_t *I_dds,
                                                       int16_t *Q_dds, double *scales) {
-    extern __shared__ double s_dyn[];            // I[size] | Q[size]
+    extern __shared__ double s_dyn[];            // I[size] | Q[size] | list[2 * size] (uint16: t | isI << 15)
     __shared__ double s_red[8];
+    __shared__ unsigned long long s_max;
+    __shared__ unsigned s_n;
     double *sI = s_dyn, *sQ = s_dyn + size;
+    unsigned short *list = reinterpret_cast<unsigned short *>(s_dyn + 2 * size);
     const int m = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
     const double f = resid[(size_t)b * 256 + m], ph = phase[(size_t)b * 256 + m];
+    if (tid == 0) { s_max = 0ull; s_n = 0u; }
     double mx = 0.0;
     for (int t = tid; t < size; t += 256) {
         double s, c;
-        sincos_cr(ref_arg(f, (double)t, fs2, ph), &s, &c);
+        sincos(ref_arg(f, (double)t, fs2, ph), &s, &c);
         sQ[t] = s;                                // amplitude 1., accumulated onto 0. : exact
-        if (offset != 0) { double s2; sincos_cr(ref_arg(f, (double)(t + offset), fs2, ph), &s2, &c); }
+        if (offset != 0) c = cos(ref_arg(f, (double)(t + offset), fs2, ph));
         sI[t] = c;
         mx = fmax(mx, fmax(fabs(c), fabs(s)));
     }
@@ -561,13 +572,43 @@ __global__ void __launch_bounds__(256) dds_lut_kernel(const double *resid, const
     __syncthreads();
     mx = s_red[0];
     for (int i = 1; i < 8; ++i) mx = fmax(mx, s_red[i]);
-    if (tid == 0 && scales) scales[(size_t)b * 256 + m] = mx;
+    // exact maximum: every sample within 1e-13 of the bulk maximum, correctly rounded (bit patterns of non-negative
+    // doubles order like the values)
+    const double lim = mx * (1.0 - 1e-13);
+    for (int t = tid; t < size; t += 256) {
+        if (fabs(sQ[t]) >= lim) list[atomicAdd(&s_n, 1u)] = (unsigned short)t;
+        if (fabs(sI[t]) >= lim) list[atomicAdd(&s_n, 1u)] = (unsigned short)(t | 0x8000);
+    }
+    __syncthreads();
+    for (unsigned i = tid; i < s_n; i += 256) {
+        const int e = list[i], t = e & 0x7fff, isI = e >> 15;
+        const double v = sin_or_cos_cr(ref_arg(f, (double)(isI ? t + offset : t), fs2, ph), isI);
+        (isI ? sI : sQ)[t] = v;
+        atomicMax(&s_max, (unsigned long long)__double_as_longlong(fabs(v)));
+    }
+    __syncthreads();
+    mx = __longlong_as_double((long long)s_max);
+    if (tid == 0) { if (scales) scales[(size_t)b * 256 + m] = mx; s_n = 0u; }
+    __syncthreads();
     const int slot = 2 * ((m + ch_shift) & 255);
     int16_t *Io = I_dds + (size_t)b * n_lut, *Qo = Q_dds + (size_t)b * n_lut;
+    // a sample that is not flagged is further than 1e-9 from an integer: x * (32767 / mx) truncates like the reference's
+    // (x * 32767) / mx
+    const double rs = __ddiv_rn(32767.0, mx);
     for (int t = tid; t < size; t += 256) {
         const int dst = (t >> 1) * 512 + slot + (t & 1);                 // ROACH_Setup.py:526-530
-        Io[dst] = (int16_t)__double2int_rz(__ddiv_rn(__dmul_rn(sI[t], 32767.0), mx));
-        Qo[dst] = (int16_t)__double2int_rz(__ddiv_rn(__dmul_rn(sQ[t], 32767.0), mx));
+        const double vi = sI[t] * rs, vq = sQ[t] * rs;
+        if (fabs(vi - rint(vi)) < 1e-9) list[atomicAdd(&s_n, 1u)] = (unsigned short)(t | 0x8000);
+        else Io[dst] = (int16_t)__double2int_rz(vi);
+        if (fabs(vq - rint(vq)) < 1e-9) list[atomicAdd(&s_n, 1u)] = (unsigned short)t;
+        else Qo[dst] = (int16_t)__double2int_rz(vq);
+    }
+    __syncthreads();
+    for (unsigned i = tid; i < s_n; i += 256) {
+        const int e = list[i], t = e & 0x7fff, isI = e >> 15;
+        const int dst = (t >> 1) * 512 + slot + (t & 1);
+        const double x = sin_or_cos_cr(ref_arg(f, (double)(isI ? t + offset : t), fs2, ph), isI);
+        (isI ? Io : Qo)[dst] = (int16_t)__double2int_rz(__ddiv_rn(__dmul_rn(x, 32767.0), mx));
     }
 }
 
@@ -773,8 +814,8 @@ extern "C" int mkid_dds_lut(mkid_ctx *ctx, const double *resid_hz, const double 
     void *dI, *dQ;
     if ((rc = mkid_stage_out(ctx, I_dds, (size_t)batch * n_lut * 2, SCR_OUT0, false, &dI))) return rc;
     if ((rc = mkid_stage_out(ctx, Q_dds, (size_t)batch * n_lut * 2, SCR_OUT1, false, &dQ))) return rc;
-    const size_t smem = (size_t)size * 16;
-    MKID_REQUIRE(ctx, smem <= 200 * 1024, "dds_lut: table too long for shared memory");
+    const size_t smem = (size_t)size * 20;                        // I, Q (fp64) and the list of samples for the exact path
+    MKID_REQUIRE(ctx, smem <= 200 * 1024 && size <= 32768, "dds_lut: table too long for shared memory");
     MKID_CUDA(ctx, cudaFuncSetAttribute(dds_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dds_lut_kernel<<<dim3(256, batch), 256, smem, ctx->stream>>>(d_res, d_ph, fs2, size, n_lut, ch_shift, offset, (int16_t *)dI,
                                                                  (int16_t *)dQ, d_sc);

@@ -41,24 +41,32 @@ def comb_lut(freqs, sample_rate, n_samples, amplitudes, phases=None, echo='yes',
     return I, Q, scale, ph
 
 
-def dds_lut(residuals, phases, sample_rate, n_lut, ch_shift=CH_SHIFT, offset=0, ctx=None):
-    """Batched define_DDS_LUT tables.  residuals/phases [batch][256] -> (I_dds, Q_dds int16 [batch][n_lut], scales)."""
+def dds_lut(residuals, phases, sample_rate, n_lut, ch_shift=CH_SHIFT, offset=0, ctx=None, out_I=None, out_Q=None):
+    """Batched define_DDS_LUT tables.  residuals/phases [batch][256] -> (I_dds, Q_dds int16 [batch][n_lut], scales).
+    out_I / out_Q: optional device buffers (int16 [batch][n_lut]) that receive the tables instead of host arrays."""
     ctx = ctx or _lib.default_context()
     r = np.ascontiguousarray(np.atleast_2d(np.asarray(residuals, dtype=np.float64)))
     batch = r.shape[0]
     p = np.ascontiguousarray(np.broadcast_to(np.atleast_2d(np.asarray(phases, dtype=np.float64)), r.shape))
     assert r.shape[1] == 256
-    I = np.empty((batch, n_lut), dtype=np.int16)
-    Q = np.empty((batch, n_lut), dtype=np.int16)
+    I = out_I if out_I is not None else np.empty((batch, n_lut), dtype=np.int16)
+    Q = out_Q if out_Q is not None else np.empty((batch, n_lut), dtype=np.int16)
     sc = np.empty((batch, 256), dtype=np.float64)
     ctx._check(ctx.lib.mkid_dds_lut(ctx.h, _lib.ptr(r), _lib.ptr(p), float(sample_rate), int(n_lut), int(ch_shift), int(offset), batch,
                                     _lib.ptr(I), _lib.ptr(Q), _lib.ptr(sc)))
     return I, Q, sc
 
 
-def pack_dram(I_dac, Q_dac, I_dds, Q_dds, ctx=None):
-    """write_LUTs byte image (ROACH_Setup.py:560-569) -> bytes of length 8*N."""
+def pack_dram(I_dac, Q_dac, I_dds, Q_dds, ctx=None, n=None, out=None):
+    """write_LUTs byte image (ROACH_Setup.py:560-569) -> bytes of length 8*N.  With n (int16 samples per table) the
+    four tables and out may be device buffers (the image of a batch of sets is the images of the sets back to back);
+    out is then returned instead of bytes."""
     ctx = ctx or _lib.default_context()
+    if n is not None:
+        assert out is not None
+        ctx._check(ctx.lib.mkid_pack_dram(ctx.h, _lib.ptr(I_dac), _lib.ptr(Q_dac), _lib.ptr(I_dds), _lib.ptr(Q_dds), int(n),
+                                          _lib.ptr(out)))
+        return out
     arrs = [np.ascontiguousarray(np.asarray(x).astype(np.int16)) for x in (I_dac, Q_dac, I_dds, Q_dds)]
     n = arrs[0].size
     assert all(x.size == n for x in arrs)
