@@ -151,6 +151,37 @@ def test_dds_lut_and_dram_identical_to_oracle(ctx, N):
         assert img == olut.pack_dram(Idac, Qdac, I[0], Q[0])
 
 
+def test_device_resident_lut_sets_equal_host_path(ctx):
+    """Two whole LUT sets (comb + 256 DDS tables + DRAM image) left in device buffers equal the host-array path and the
+    oracle's write_LUTs image, set by set."""
+    from mkids_sdr_b200 import lut
+    N, T, batch = 2 ** 16, 256, 2
+    rng = np.random.default_rng(77)
+    res = FS / N
+    fl, al, rl, pl = [], [], [], []
+    for b in range(batch):
+        k = np.sort(rng.choice(np.arange(-N // 2 + 1, N // 2), T, replace=False))
+        f = (k % N) * FS / N
+        fl.append(f); al.append(rng.uniform(0.1, 1.0, T))
+        rl.append(olut.select_bins([float(v) for v in f], FS, res)[1]); pl.append(rng.uniform(-np.pi, np.pi, 256))
+    bufs = [ctx.alloc(batch * N * 2) for _ in range(4)]
+    img = ctx.alloc(batch * N * 8)
+    lut.comb_lut(fl, FS, N, al, ctx=ctx, out_I=bufs[0], out_Q=bufs[1])
+    lut.dds_lut(rl, pl, FS, N, ctx=ctx, out_I=bufs[2], out_Q=bufs[3])
+    lut.pack_dram(bufs[0], bufs[1], bufs[2], bufs[3], ctx=ctx, n=batch * N, out=img)
+    got = img.download(np.uint8)
+    I, Q, _, _ = lut.comb_lut(fl, FS, N, al, ctx=ctx)
+    Id, Qd, _ = lut.dds_lut(rl, pl, FS, N, ctx=ctx)
+    assert np.array_equal(bufs[0].download(np.int16).reshape(batch, N), I)
+    assert np.array_equal(bufs[3].download(np.int16).reshape(batch, N), Qd)
+    for b in range(batch):
+        assert got[b * 8 * N:(b + 1) * 8 * N].tobytes() == olut.pack_dram(I[b], Q[b], Id[b], Qd[b])
+        Io, Qo, _, _ = olut.freq_comb_lut('yes', list(fl[b]), FS, res, list(al[b]))
+        assert np.array_equal(I[b], Io) and np.array_equal(Q[b], Qo)
+    for v in bufs + [img]:
+        v.free()
+
+
 def test_full_size_config2_properties(ctx):
     """BASELINE config 1 at full size: 256 tones, N = 2^19; oracle on a sample of the outputs plus
     size-independent properties (scale, Parseval-like power, periodic extension)."""
