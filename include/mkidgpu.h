@@ -375,7 +375,8 @@ int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double *amp, doubl
 /* define_DDS_LUT (ROACH_Setup.py:506-532): 256 single-tone tables of n_lut/256 samples at
  * sample_rate/512*2, each normalised to its own max, scattered to
  * [j*512 + 2*((m+ch_shift)%256) + s].  offset: the GUI sample offset applied to I only
- * (ROACH_Setup_DAC.py:397,421).  resid/phase: [batch][256] host or device. */
+ * (ROACH_Setup_DAC.py:397,421).  resid/phase: [batch][256] host or device; I_dds / Q_dds host, or device with
+ * 4-byte alignment. */
 int mkid_dds_lut(mkid_ctx *ctx, const double *resid_hz, const double *phase, double sample_rate, int32_t n_lut,
                  int32_t ch_shift, int32_t offset, int32_t batch, int16_t *I_dds, int16_t *Q_dds, double *scales_out);
 /* write_LUTs (ROACH_Setup.py:560-569): per sample pair 16 bytes, big-endian int16

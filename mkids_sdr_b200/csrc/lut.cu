@@ -547,8 +547,7 @@ __global__ void __launch_bounds__(128) comb_fixup_kernel(CombParams p) {
 // of a high power of two): they are first collected in a shared-memory list and then evaluated by all threads of the
 // CTA, not in divergent branches.
 __global__ void __launch_bounds__(256) dds_lut_kernel(const double *resid, const double *phase, double fs2, int size,
-                                                      int n_lut, int ch_shift, int offset, int16_t *I_dds,
-                                                      int16_t *Q_dds, double *scales) {
+                                                      int offset, int16_t *I_dds, int16_t *Q_dds, double *scales) {
     extern __shared__ double s_dyn[];            // I[size] | Q[size] | list[2 * size] (uint16: t | isI << 15)
     __shared__ double s_red[8];
     __shared__ unsigned long long s_max;
@@ -590,13 +589,13 @@ __global__ void __launch_bounds__(256) dds_lut_kernel(const double *resid, const
     mx = __longlong_as_double((long long)s_max);
     if (tid == 0) { if (scales) scales[(size_t)b * 256 + m] = mx; s_n = 0u; }
     __syncthreads();
-    const int slot = 2 * ((m + ch_shift) & 255);
-    int16_t *Io = I_dds + (size_t)b * n_lut, *Qo = Q_dds + (size_t)b * n_lut;
+    // channel-major tables [b][m][t] (whole lines per warp); dds_interleave_kernel scatters them to the reference's layout
+    int16_t *Io = I_dds + ((size_t)b * 256 + m) * size, *Qo = Q_dds + ((size_t)b * 256 + m) * size;
     // a sample that is not flagged is further than 1e-9 from an integer: x * (32767 / mx) truncates like the reference's
     // (x * 32767) / mx
     const double rs = __ddiv_rn(32767.0, mx);
     for (int t = tid; t < size; t += 256) {
-        const int dst = (t >> 1) * 512 + slot + (t & 1);                 // ROACH_Setup.py:526-530
+        const int dst = t;
         const double vi = sI[t] * rs, vq = sQ[t] * rs;
         if (fabs(vi - rint(vi)) < 1e-9) list[atomicAdd(&s_n, 1u)] = (unsigned short)(t | 0x8000);
         else Io[dst] = (int16_t)__double2int_rz(vi);
@@ -606,9 +605,37 @@ __global__ void __launch_bounds__(256) dds_lut_kernel(const double *resid, const
     __syncthreads();
     for (unsigned i = tid; i < s_n; i += 256) {
         const int e = list[i], t = e & 0x7fff, isI = e >> 15;
-        const int dst = (t >> 1) * 512 + slot + (t & 1);
+        const int dst = t;
         const double x = sin_or_cos_cr(ref_arg(f, (double)(isI ? t + offset : t), fs2, ph), isI);
         (isI ? Io : Qo)[dst] = (int16_t)__double2int_rz(__ddiv_rn(__dmul_rn(x, 32767.0), mx));
+    }
+}
+
+// ---- K2b: channel-major pairs [b][m][j] (samples 2j, 2j+1 of channel m as one 32-bit word) -> the reference's layout
+// dds[j*512 + 2*((m+ch_shift)%256) + s] (ROACH_Setup.py:526-530): a 32-bit transpose with a rotation of the channel
+// axis, tiles of 32 x 32 words through shared memory.  (Stored straight from dds_lut_kernel, every 2-byte sample was its
+// own 32-byte sector: 1 KiB stride.)
+__global__ void __launch_bounds__(256) dds_interleave_kernel(const uint32_t *I_cm, const uint32_t *Q_cm, int half, int ch_shift,
+                                                             uint32_t *I_dds, uint32_t *Q_dds) {
+    __shared__ uint32_t tI[32][33], tQ[32][33];
+    const int b = blockIdx.y, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int m0 = (blockIdx.x & 7) * 32, j0 = (blockIdx.x >> 3) * 32;
+    const size_t base = (size_t)b * 256 * half;
+    if (j0 + tx < half) {
+#pragma unroll
+        for (int r = ty; r < 32; r += 8) {
+            tI[r][tx] = I_cm[base + (size_t)(m0 + r) * half + j0 + tx];
+            tQ[r][tx] = Q_cm[base + (size_t)(m0 + r) * half + j0 + tx];
+        }
+    }
+    __syncthreads();
+    const int slot = (m0 + tx + ch_shift) & 255;
+#pragma unroll
+    for (int r = ty; r < 32; r += 8) {
+        if (j0 + r < half) {
+            I_dds[base + (size_t)(j0 + r) * 256 + slot] = tI[tx][r];
+            Q_dds[base + (size_t)(j0 + r) * 256 + slot] = tQ[tx][r];
+        }
     }
 }
 
@@ -817,8 +844,14 @@ extern "C" int mkid_dds_lut(mkid_ctx *ctx, const double *resid_hz, const double 
     const size_t smem = (size_t)size * 20;                        // I, Q (fp64) and the list of samples for the exact path
     MKID_REQUIRE(ctx, smem <= 200 * 1024 && size <= 32768, "dds_lut: table too long for shared memory");
     MKID_CUDA(ctx, cudaFuncSetAttribute(dds_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dds_lut_kernel<<<dim3(256, batch), 256, smem, ctx->stream>>>(d_res, d_ph, fs2, size, n_lut, ch_shift, offset, (int16_t *)dI,
-                                                                 (int16_t *)dQ, d_sc);
+    int16_t *cmI, *cmQ;                                           // channel-major tables, interleaved by a second kernel
+    if ((rc = mkid_scratch(ctx, SCR_AUX0, (size_t)batch * n_lut * 2, (void **)&cmI))) return rc;
+    if ((rc = mkid_scratch(ctx, SCR_AUX1, (size_t)batch * n_lut * 2, (void **)&cmQ))) return rc;
+    dds_lut_kernel<<<dim3(256, batch), 256, smem, ctx->stream>>>(d_res, d_ph, fs2, size, offset, cmI, cmQ, d_sc);
+    MKID_CHECK_LAUNCH(ctx);
+    const int half = size / 2;
+    dds_interleave_kernel<<<dim3(8 * ((half + 31) / 32), batch), 256, 0, ctx->stream>>>(
+        (const uint32_t *)cmI, (const uint32_t *)cmQ, half, ch_shift, (uint32_t *)dI, (uint32_t *)dQ);
     MKID_CHECK_LAUNCH(ctx);
     if (scales_out) {
         MKID_CUDA(ctx, cudaMemcpyAsync(scales_out, d_sc, (size_t)batch * 256 * 8, cudaMemcpyDefault, ctx->stream));

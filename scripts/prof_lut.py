@@ -1,4 +1,4 @@
-"""LUT synthesis run for ncu (BASELINE config 1 at batch 64, tables left in HBM): python scripts/prof_lut.py [batch]"""
+"""LUT synthesis run for ncu (BASELINE config 1 at batch 64: comb, DDS tables, DRAM image; tables left in HBM): python scripts/prof_lut.py [batch]"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -13,5 +13,12 @@ ff = np.tile(f, (batch, 1)); aa = np.tile(amps, (batch, 1))
 oi, oq = ctx.alloc(batch * N * 2), ctx.alloc(batch * N * 2)
 for it in range(2):
     lut.comb_lut(ff, FS, N, aa, ctx=ctx, out_I=oi, out_Q=oq)
+res = FS / N
+resid = np.rint((f - np.rint(f * 512 / FS) * FS / 512) / res) * res
+rr = np.tile(resid, (batch, 1))
+di, dq, img = ctx.alloc(batch * N * 2), ctx.alloc(batch * N * 2), ctx.alloc(batch * N * 8)
+for it in range(2):
+    lut.dds_lut(rr, np.zeros_like(rr), FS, N, ctx=ctx, out_I=di, out_Q=dq)
+    lut.pack_dram(oi, oq, di, dq, ctx=ctx, n=batch * N, out=img)
 ctx.sync()
-print('comb_lut batch', batch, 'done')
+print('comb_lut + dds_lut + pack_dram batch', batch, 'done')
