@@ -117,9 +117,13 @@ __device__ double sin_or_cos_cr(double x, int want_cos) {
     const dd z = dd_mul(r, r);
     const int quad = (int)((long long)k & 3);
     const bool cos_series = ((quad ^ want_cos) & 1) != 0;
-    dd ps = {cos_series ? c_C[12][0] : c_S[12][0], cos_series ? c_C[12][1] : c_S[12][1]};
+    // terms beyond z^(top+2) are below 2^-106 of the result for the given bound on z = r^2 (the DDS tables call this
+    // almost only next to multiples of pi/2, where r ~ 1e-13 and two terms are the whole series)
+    const double za = fabs(z.hi);
+    const int top = za < 1e-16 ? 2 : (za < 1e-8 ? 4 : (za < 1e-3 ? 7 : (za < 0.05 ? 10 : 12)));
+    dd ps = {cos_series ? c_C[top][0] : c_S[top][0], cos_series ? c_C[top][1] : c_S[top][1]};
 #pragma unroll 1
-    for (int i = 11; i >= 0; --i) {
+    for (int i = top - 1; i >= 0; --i) {
         const double c0 = cos_series ? c_C[i][0] : c_S[i][0], c1 = cos_series ? c_C[i][1] : c_S[i][1];
         ps = dd_add(dd_mul(ps, z), dd{c0, c1});
     }
