@@ -324,12 +324,16 @@ def main():
     if rank == 0:
         sampler.stop_flag = True
 
-    decode_sharded = None
+    decode_sharded = lut_sharded = None
     if dist is not None and not args.no_extras:
         try:
             decode_sharded = decode_sharded_bench(ctx, torch, dist, rank, world, measured_peaks()[0])
         except Exception as e:      # side measurement only
             decode_sharded = {'error': str(e)}
+        try:
+            lut_sharded = lut_sharded_bench(ctx, torch, dist, rank, world)
+        except Exception as e:
+            lut_sharded = {'error': str(e)}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -368,6 +372,8 @@ def main():
 
     if decode_sharded is not None:
         line['decode_sharded'] = decode_sharded
+    if lut_sharded is not None:
+        line['lut_sharded'] = lut_sharded
     if not args.no_extras:
         try:
             line['decode'] = decode_side_bench(ctx, peak)
@@ -438,6 +444,49 @@ def decode_sharded_bench(ctx, torch, dist, rank, world, peak):
             'checksum_spectra': total_hist, 'checksum_expected': int(10 ** 7 * reps * world),
             'checksum_ok': total_hist == int(10 ** 7 * reps * world),
             'workload': '16 x 1e7 photon words per GPU (different seeds), decode + per-pixel counts + 10-bin spectra'}
+
+
+def lut_sharded_bench(ctx, torch, dist, rank, world):
+    """SURVEY 8e, first row: the LUT sets of the boards are independent, boards -> GPUs, no collective on the data
+    path.  Every rank synthesises the whole LUT sets (comb + 256 DDS tables + DRAM image) of 64 boards, left in HBM
+    (weak scaling); whole-job sets/s, max over ranks.  The boards of all ranks use the same tones, so the images must be
+    identical on every rank: one all-gather of a checksum (outside the timed region) checks that."""
+    from mkids_sdr_b200 import lut
+    N, T, batch = 2 ** 19, 256, 64
+    k = np.sort(np.random.default_rng(0).choice(np.arange(-N // 2 + 1, N // 2), T, replace=False))
+    f = (k % N) * FS / N
+    amps = 10 ** (-(np.random.default_rng(1).integers(0, 20, T)) / 20.)
+    res = FS / N
+    resid = np.rint((f - np.rint(f * 512 / FS) * FS / 512) / res) * res      # select_bins (ROACH_Setup.py:534-550)
+    ff = np.tile(f, (batch, 1)); aa = np.tile(amps, (batch, 1)); rr = np.tile(resid, (batch, 1))
+    bufs = [ctx.alloc(batch * N * 2) for _ in range(4)]
+    img = ctx.alloc(batch * N * 8)
+
+    def one():
+        lut.comb_lut(ff, FS, N, aa, ctx=ctx, out_I=bufs[0], out_Q=bufs[1])
+        lut.dds_lut(rr, np.zeros_like(rr), FS, N, ctx=ctx, out_I=bufs[2], out_Q=bufs[3])
+        lut.pack_dram(bufs[0], bufs[1], bufs[2], bufs[3], ctx=ctx, n=batch * N, out=img)
+    for _ in range(3):
+        one()
+    ctx.sync(); dist.barrier(); torch.cuda.synchronize()
+    reps = 10
+    t0 = time.time()
+    for _ in range(reps):
+        one()
+    ctx.sync(); dist.barrier(); torch.cuda.synchronize()
+    el = torch.tensor([(time.time() - t0) * 1e3 / reps], dtype=torch.float64, device='cuda')
+    dist.all_reduce(el, op=dist.ReduceOp.MAX)
+    ms = float(el[0])
+    first = img.download(np.uint8, count=8 * N)                       # the image of the first board of this rank
+    cs = torch.tensor([int(first.astype(np.int64).sum())], dtype=torch.int64, device='cuda')
+    allcs = [torch.zeros_like(cs) for _ in range(world)]
+    dist.all_gather(allcs, cs)
+    for v in bufs + [img]:
+        v.free()
+    return {'luts_per_s': world * batch / ms * 1e3, 'ms_per_call': ms, 'sets_per_gpu_per_call': batch, 'n_gpus': world,
+            'GB/s_written': world * batch * N * 16 / ms / 1e6, 'collective': 'none on the data path',
+            'checksum_ok': all(int(c[0]) == int(cs[0]) for c in allcs),
+            'workload': 'whole LUT sets (comb + 256 DDS tables + DRAM image), 64 boards per GPU'}
 
 
 def decode_side_bench(ctx, peak):
