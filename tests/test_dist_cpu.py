@@ -64,6 +64,48 @@ def test_two_rank_chunk_sharding_and_reduce():
     assert res[3] > 0 and res[4] > 0
 
 
+def _lut_worker(rank, world, port, q):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from mkids_sdr_b200 import dist as mdist
+    from oracle import lut as olut
+    n_boards, N, T, FS = 5, 2 ** 10, 8, 512e6
+
+    def board_tables(b):                     # the oracle stands in for mkid_comb_lut: one LUT set per board
+        rng = np.random.default_rng(100 + b)
+        k = np.sort(rng.choice(np.arange(-N // 2 + 1, N // 2), T, replace=False))
+        I, Q, sc, _ = olut.freq_comb_lut('yes', list((k % N) * FS / N), FS, FS / N, list(rng.uniform(0.1, 1.0, T)))
+        return np.concatenate([I, Q]).astype(np.int64)
+    sums = torch.zeros(n_boards * 2, dtype=torch.int64)       # per board: sum and a position-weighted sum of its tables
+    for b in mdist.assign_boards(n_boards, world, rank):
+        t = board_tables(b)
+        sums[2 * b] = int(t.sum()); sums[2 * b + 1] = int((t * np.arange(1, t.size + 1)).sum())
+    mdist.reduce_products([sums])            # LUT synthesis has no data-path collective; this only gathers the check
+    if rank == 0:
+        ref = []
+        for b in range(n_boards):
+            t = board_tables(b)
+            ref += [int(t.sum()), int((t * np.arange(1, t.size + 1)).sum())]
+        q.put(sums.tolist() == ref)
+    dist.destroy_process_group()
+
+
+def test_two_rank_lut_board_sharding():
+    """LUT sets shard by board with no collective; every board is synthesised by exactly one rank."""
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_lut_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok
+
+
 def test_assign_boards():
     from mkids_sdr_b200 import dist as mdist
     for total, world in ((8, 1), (8, 2), (8, 8), (80, 8), (10, 4)):
