@@ -729,7 +729,9 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
     }
     if (random_phase) memcpy(phase, ph, TB * 8);
     // device buffers
-    const unsigned cap = 1u << 17;
+    // list of samples for the exact path, per set: ~100 (max candidates: a handful) at 2^19 samples and 256 tones; the flag
+    // distance grows with N * sqrt(sum a^2), so the longest tables get a longer list
+    const unsigned cap = std::max(1u << 17, (unsigned)N >> 5);
     char *meta; double2 *x; unsigned *list;
     int rc;
     const size_t meta_bytes = TB * 32 + (size_t)batch * 48;
