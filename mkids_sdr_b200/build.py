@@ -16,7 +16,7 @@ OUT = os.path.join(HERE, 'libmkidgpu.so')
 STAMP = os.path.join(HERE, '.libmkidgpu.stamp')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
-         '-Xcompiler', '-fPIC', '-Xcompiler', '-O3', '--expt-relaxed-constexpr', '-Xptxas', '-v']
+         '-Xcompiler', '-fPIC', '-Xcompiler', '-O3', '--expt-relaxed-constexpr', '-Xptxas', '-v', '-cudart', 'shared']
 
 
 def _sources():
@@ -57,7 +57,11 @@ def build(force=False, verbose=False):
     open(os.path.join(objdir, 'ptxas.log'), 'w').write('\n'.join(log))
     if verbose:
         print('\n'.join(log))
-    subprocess.check_call([NVCC, '-shared', '-o', OUT] + objs + ['-gencode', 'arch=compute_100a,code=sm_100a'])
+    # shared cudart: the library must not carry a private copy of the runtime (and of every
+    # entry point it names); the rpath is the image's toolkit, torch's copy has the same SONAME
+    subprocess.check_call([NVCC, '-shared', '-cudart', 'shared', '-o', OUT] + objs +
+                          ['-gencode', 'arch=compute_100a,code=sm_100a',
+                           '-Xlinker', '-rpath', '-Xlinker', '/usr/local/cuda/lib64'])
     open(STAMP, 'w').write(dig)
     return OUT
 
