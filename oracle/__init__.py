@@ -14,10 +14,12 @@ Pinned against the reference's own fixtures (see tests/golden/make_golden.py):
                      the py3-safe functions
   * control.py    <- LUT/*.txt FIR tap files (quantised taps), ch_snap_0.txt
   * trigger.py    <- ch_snap_0.txt
-  * decode.py     <- oracle/_ref/packetmaster_ref (the reference's own
-                     PacketMaster.c inner loop is not compilable: needs hdf5.h)
-                     -> restated in packetmaster_core.c; the bitfield layout is
-                     pinned by ROACH_Pulses.py:805-811 and PacketMaster.c:306.
+  * decode.py, packetmaster_core.c
+                  <- oracle/_ref/libpm_ref_*.so: the reference's OWN receive loop
+                     (PacketMaster.c:304-397), extracted as text at build time and
+                     compiled by build_pm_ref.py with the process shell stubbed
+                     (pm_ref.py is its ctypes front; tests/test_pm_ref_cpu.py);
+                     the bitfield layout is pinned by ROACH_Pulses.py:805-811.
 and against OUTPUTS OF THE REFERENCE'S OWN CODE executed in the dev container (the method sources are read from the
 reference tree at run time, Python-2 -> 3 edits applied, run against a recording roach / mock widgets; only the
 numerical outputs are stored: tests/golden/make_golden_refrun.py -> refrun_golden.npz,

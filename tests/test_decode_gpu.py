@@ -3,6 +3,7 @@ import numpy as np
 import pytest
 
 from oracle import decode as odec
+from oracle import pm_ref
 
 pytestmark = pytest.mark.gpu
 
@@ -23,6 +24,12 @@ def _check(dec, streams, npix, exptime, cap, field='peak', bin_lut=None, n_bins=
     if field:
         h = odec.pixel_field_hist(streams, npix, exptime, field, bin_lut, n_bins)
         assert np.array_equal(dec.hist(), h)
+    # ... and against the reference's own loop (PacketMaster.c:304-397 compiled by oracle/build_pm_ref.py)
+    if pm_ref.available(len(streams), npix, cap):
+        r = pm_ref.run(streams, npix, exptime, cap)
+        assert np.array_equal(dec.counts(), r['counts'])
+        for k in ('n_eos', 'n_corrupt_eos', 'n_nonpixel'):
+            assert st[k] == r[k], k
 
 
 def _ragged_streams(seed, R, npix, secs, per_sec, hot=True):
