@@ -33,6 +33,7 @@ def main():
     s = g.Self()
     s.freqCombLUT = types.MethodType(Ref.freqCombLUT, s)
     s.sampleRate, s.freqRes = fs, fs / N
+    s.minimumAttenuation, s.previous_scale_factor, s.last_scale_factor = 10, 5000.0, None
     t0 = time.time()
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from oracle import channelizer as oc
-from tests.chan_common import board_config, make_gpu_channelizer
+from tests.chan_common import board_config, compare_words_with_model, make_gpu_channelizer
 
 pytestmark = pytest.mark.gpu
 
@@ -94,21 +94,21 @@ def test_streaming_is_chunk_invariant_and_matches_oracle_detect(ctx):
 
 
 def test_full_chain_against_float64_oracle(ctx):
-    """End to end: words from the float64 model vs the GPU chain; differences can only come from
-    +-1 LSB phase rounding flips near a threshold (reported, bounded)."""
+    """End to end: words from the float64 model vs the GPU chain.  Differences can only come from +-1 LSB phase rounding
+    flips next to a threshold: measured (printed) and every one of them explained (tests/chan_common.py)."""
     cfg, ks = board_config(n_tones=32, seed=9, L=100, thr=-2500)
     n = 2 ** 21
     iq = _synth(ctx, ks[None, :], n, cfg.N_lut, seed=3, pulse_rate=5000.)
     ch = make_gpu_channelizer([cfg], ctx)
-    w_gpu, _ = ch.process(iq)
+    w_gpu, raw_gpu = ch.process(iq, want_phase=True)
     _, raw_ref = oc.channelize_phase(iq[0], cfg)
     T = n // 512
-    ref = oc.detect_emit(raw_ref, cfg, 0, np.zeros(256, np.int64), T - 64 - cfg.M)
-    a, b = set(int(x) for x in w_gpu[0]), set(ref)
-    assert len(b) > 300
-    # same triggers (channel, timestamp) almost everywhere; field values may differ by 1 code
-    key = lambda w: (w >> 56, w & 0xFFFFF)
-    ka, kb = set(map(key, a)), set(map(key, b))
-    assert len(ka ^ kb) <= 0.01 * len(kb), (len(ka ^ kb), len(kb))
-    assert len(a & b) >= 0.90 * len(b), (len(a & b), len(b))
+    r = compare_words_with_model(w_gpu[0], raw_gpu[0], raw_ref, cfg, T)
+    print('\n[32-tone chain vs float64 model] %d oracle words, %d GPU words, %d triggers differ (%d marginal, %d shadow, %d unexplained), '
+          '%d of %d common words differ by one code' % (r['n_ref'], r['n_gpu'], r['only'], r['marginal'], r['shadow'],
+                                                        len(r['unexplained']), r['word_diff'], r['common']))
+    assert r['n_ref'] > 300
+    assert not r['unexplained'], r['unexplained']
+    assert r['only'] <= 0.005 * r['n_ref'], (r['only'], r['n_ref'])         # measured: see the printed line / DESIGN.md
+    assert r['word_diff'] <= 0.005 * r['common'], (r['word_diff'], r['common'])
     ch.close()

@@ -141,10 +141,11 @@ def test_dds_lut_and_dram_identical_to_oracle(ctx, N):
         I, Q, sc = lut.dds_lut(resid, phases, FS, N, ctx=ctx)
         Io, Qo, so = olut.define_dds_lut(resid, FS, res, phases)
         n_bad += int((I[0] != Io).sum() + (Q[0] != Qo).sum())
-        assert np.array_equal(sc[0], so) or n_bad <= 2
-    # the libm of the host decides sin/cos ties in the oracle; the GPU path is correctly rounded:
-    # allow at most two +-1 LSB differences over 4*N samples (DESIGN.md "LUT exactness"), normally 0
-    assert n_bad <= 2, n_bad
+        assert np.array_equal(sc[0], so)
+    # the libm of the host decides sin/cos ties in the oracle while the GPU path is correctly rounded, so a +-1 LSB
+    # difference is conceivable (DESIGN.md "LUT exactness"); measured on these configurations: 0 of 4*N samples
+    print('\n[dds lut N=%d] samples differing from the oracle: %d of %d' % (N, n_bad, 4 * N))
+    assert n_bad == 0, n_bad
     if N == 2 ** 16:
         Idac = rng.integers(-32768, 32768, N).astype(np.int16); Qdac = rng.integers(-32768, 32768, N).astype(np.int16)
         img = lut.pack_dram(Idac, Qdac, I[0], Q[0], ctx=ctx)
