@@ -196,3 +196,9 @@ def test_full_size_config2_properties(ctx):
     assert scale[0] == so
     assert np.array_equal(I[0], Io) and np.array_equal(Q[0], Qo)
     assert max(np.abs(I[0]).max(), np.abs(Q[0]).max()) == int(32767 / 1.1)
+    # ... and against the reference's LITERAL freqCombLUT run once at this size (tests/golden/make_golden_refrun_fullsize.py)
+    import hashlib, json, os
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'refrun_fullsize_lut.json')))
+    assert hashlib.sha256(I[0].astype('<i2').tobytes()).hexdigest() == g['sha256_I']
+    assert hashlib.sha256(Q[0].astype('<i2').tobytes()).hexdigest() == g['sha256_Q']
+    assert repr(float(scale[0])) == g['scale_factor']

@@ -473,3 +473,20 @@ def test_contsnapshot_trigger_oracle_matches_reference_run(golden_dir):
         hits = trigger.trigger_contsnapshot_literal(g['ctrig_%s_phase' % tag], int(A), float(thr))
         assert hits == [int(v) for v in g['ctrig_%s_hits' % tag]], tag
         assert len(hits) > 5
+
+
+def test_lut_oracle_matches_reference_run_at_full_size(golden_dir):
+    """Row a1 at the BASELINE size: the oracle's vectorised freqCombLUT (256 tones x 2^19 samples) against the sha256 of
+    the reference's own literal freqCombLUT, executed once from the reference tree (make_golden_refrun_fullsize.py)."""
+    import hashlib
+    import json
+    g = json.load(open(os.path.join(golden_dir, 'refrun_fullsize_lut.json')))
+    N, T, FS = g['N'], g['T'], 512e6
+    k = np.sort(np.random.default_rng(0).choice(np.arange(-N // 2 + 1, N // 2), T, replace=False))
+    f = (k % N) * FS / N
+    amps = lut.dac_amplitudes(np.random.default_rng(1).integers(0, 20, T))
+    I, Q, scale, _ = lut.freq_comb_lut('yes', list(f), FS, FS / N, amps)
+    assert repr(float(scale)) == g['scale_factor']
+    assert hashlib.sha256(np.asarray(I).astype('<i2').tobytes()).hexdigest() == g['sha256_I']
+    assert hashlib.sha256(np.asarray(Q).astype('<i2').tobytes()).hexdigest() == g['sha256_Q']
+    assert [int(v) for v in I[:8]] == g['I_first'] and int(np.asarray(I).sum()) == g['I_sum']
