@@ -10,7 +10,7 @@ from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int32, c_i
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'libmkidgpu.so')
+LIB_PATH = os.environ.get('MKIDGPU_LIB') or os.path.join(_HERE, 'libmkidgpu.so')     # (override: kernel experiments)
 
 MKID_OK, MKID_ENODEV, MKID_EINVAL, MKID_ENOMEM, MKID_ECUDA, MKID_ENCCL = 0, -1, -2, -3, -4, -5
 

@@ -15,7 +15,8 @@ CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libmkidgpu.so')
 STAMP = os.path.join(HERE, '.libmkidgpu.stamp')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-FLAGS = ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
+EXTRA = os.environ.get('MKID_NVCC_EXTRA', '').split()      # e.g. -DK4_... for kernel experiments
+FLAGS = EXTRA + ['-std=c++17', '-O3', '-lineinfo', '-gencode', 'arch=compute_100a,code=sm_100a',
          '-Xcompiler', '-fPIC', '-Xcompiler', '-O3', '--expt-relaxed-constexpr', '-Xptxas', '-v', '-cudart', 'shared']
 
 

@@ -50,11 +50,11 @@ struct ChanDev {                         // device-resident configuration + stat
     float fir[FIRT];      // c_k / (2047*32767)
     float2 fir2[FIRT];    // (c_k, c_k) pairs: packed f32x2 FMA operands
     int16_t *bins;        // [B][256]
-    float2 *ddsf;         // [B][Ld][256]  (I, Q) as float, channel-minor
-    float *gain;          // [B][256] 0 (zeroed FIR) or 1
+    uint32_t *dds;        // [B][Ld][256]  I | Q << 16 (int16 pair), channel-minor; zeroed channels hold 0
+    float *gain;          // [B][256] 0 (zeroed FIR) or 1 (kept for reporting; the kernel uses the zeroed DDS entries)
     float *cen_i, *cen_q; // [B][256] 8*I_c, 8*Q_c
     int32_t *thr;         // [B][256]
-    uint32_t *hist;       // [B][H] input history (packed int16 I,Q)
+    uint32_t *hist;       // [B][H + 2048] input history (packed int16 I,Q), then the first 2048 samples of the current call
     int64_t *t_next;      // [B][256]
     int H;
 };
@@ -138,8 +138,7 @@ struct K4Params {
 __device__ __forceinline__ float atan2_fast(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-    float t = __fdividef(mn, mx);
-    t = mx == 0.f ? 0.f : t;
+    const float t = __fdividef(mn, fmaxf(mx, 1e-30f));       // 0 / 0 -> 0 (both zero only for a zeroed channel at the centre)
     const float s = t * t;
     float p = 2.4566796610e-03f;
     p = fmaf(p, s, -1.4401168771e-02f);
@@ -159,7 +158,7 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
 // One chunk of output rows of one board.  EDGE = the chunk touches the start of the call (input
 // history) or the start of the stream (frames before time 0 contribute nothing).
 template <bool EDGE, bool F32>
-__device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_fft, uint32_t *s_adc, float2 *s_dds,
+__device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_fft, uint32_t *s_adc, uint32_t *s_dds,
                                                  uint64_t *s_bar, const float2 *s_tw, int board, int64_t row0,
                                                  int64_t row1) {
     const int tid = threadIdx.x;
@@ -180,10 +179,9 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
     const int bin = d.bins[board * NCH + tid];
     const int par = bin & 1;
     const float2 *zsrc = s_fft + par * FFT_STRIDE + (bin >> 1);      // + 2*i*FFT_STRIDE per frame
-    const bool live = d.gain[board * NCH + tid] != 0.f;
     const float cen_i = d.cen_i[board * NCH + tid], cen_q = d.cen_q[board * NCH + tid];
     const uint32_t *in = p.in + (size_t)board * p.n;
-    const uint32_t *hist = d.hist + (size_t)board * d.H;
+    const uint32_t *hist = d.hist + (size_t)board * (d.H + 2048);
     int16_t *phase = p.phase + (size_t)board * p.rows * NCH + tid;
     // fused candidate mask (K5c): bit (r & 31) of mask[r >> 5][c] iff M*raw[r] - sum_{k=1..M} raw[r-k] < M*thr
     const int thM = M * d.thr[board * NCH + tid];
@@ -219,13 +217,13 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
     }
     sw[7] = make_float2(0.f, 0.f);
     // staging buffers: the 2048 ADC samples of the next block (8 KiB, contiguous in HBM) and the 8 x 256 DDS
-    // values of the current block (16 KiB, contiguous in the repacked LUT) arrive by 1-D TMA bulk copies issued
+    // values of the current block (8 KiB of int16 pairs, contiguous in the repacked LUT) arrive by 1-D TMA bulk copies issued
     // by thread 0 and signalled on mbarriers, while the arithmetic runs.  EDGE chunks (input history, time < 0)
     // fill their own ADC column with plain loads instead.
     uint32_t *adc_c = s_adc + tid;
-    float2 *dds_c = s_dds + tid;
+    const uint32_t *dds_c = s_dds + tid;
     const uint32_t *adc_blk = in + HOP * fb_first;                // first sample of the block being staged
-    const float2 *dds_blk = d.ddsf + (size_t)board * d.Ld * NCH;  // + dds_row * NCH
+    const uint32_t *dds_blk = d.dds + (size_t)board * d.Ld * NCH;  // + dds_row * NCH
     uint32_t par_adc = 0, par_dds = 0;
     if (EDGE) {
 #pragma unroll
@@ -235,8 +233,8 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
         mk_bulk_g2s(s_adc, adc_blk, FB * HOP * 4, &s_bar[0]);
     }
     if (tid == 0) {
-        mk_mbar_expect_tx(&s_bar[1], FB * NCH * 8);
-        mk_bulk_g2s(s_dds, dds_blk + (size_t)dds_row * NCH, FB * NCH * 8, &s_bar[1]);
+        mk_mbar_expect_tx(&s_bar[1], FB * NCH * 4);
+        mk_bulk_g2s(s_dds, dds_blk + (size_t)dds_row * NCH, FB * NCH * 4, &s_bar[1]);
     }
 
     // ---- channel-stage state in chunk-relative rows (32-bit): row r = row0 + rl
@@ -266,7 +264,7 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
 #pragma unroll
         for (int i = 0; i < FB; ++i) {
             float2 z = zsrc[(2 * i) * FFT_STRIDE];
-            const float2 dvi = dds_c[i * NCH];
+            const float2 dvi = unpack(dds_c[i * NCH]);          // zeroed channels hold (0, 0): y = +-0, w = +0 as in the model
             if ((i & 1) == 0 && par) { z.x = -z.x; z.y = -z.y; }           // even i: f_abs + 1 odd
             y[i].x = z.x * dvi.x + z.y * dvi.y;
             y[i].y = z.y * dvi.x - z.x * dvi.y;
@@ -313,8 +311,7 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
         float ph[4];
 #pragma unroll
         for (int jj = 0; jj < 4; ++jj) {
-            // zeroed FIR (deleted / inactive channel): w = +0 exactly, as in the model
-            const float a = (live ? ar[jj] : 0.f) - cen_i, b = (live ? ai[jj] : 0.f) - cen_q;
+            const float a = ar[jj] - cen_i, b = ai[jj] - cen_q;
             ph[jj] = atan2_fast(b, a);
             raw[jj] = __float2int_rn(ph[jj] * 8192.0f);
         }
@@ -382,6 +379,18 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
             for (int i = 0; i < 16; ++i) v[i] = reg[j + 16 * i];
             fft16(v);
             __syncwarp();
+#ifdef K4_TW_ON_LOAD
+            // A_j[q], q = 4*k1+k2, sits in v[4*k2+k1] -> reg[q*17 + j]; the twiddle W256^(j*q) is applied by the reader
+#pragma unroll
+            for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+                for (int k2 = 0; k2 < 4; ++k2) reg[(4 * k1 + k2) * 17 + j] = v[4 * k2 + k1];
+            __syncwarp();
+            // B_i[j] = A_i[j] * W256^(i*j): data and twiddle loads of one element are issued together
+            v[0] = reg[j * 17];
+#pragma unroll
+            for (int i = 1; i < 16; ++i) v[i] = cmul(reg[j * 17 + i], s_tw[i * 16 + j]);
+#else
             // B_j[q] = A_j[q] * W256^(j*q) -> reg[q*17 + j];  A_j[q], q = 4*k1+k2, sits in v[4*k2+k1]
 #pragma unroll
             for (int k1 = 0; k1 < 4; ++k1)
@@ -395,6 +404,7 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
             __syncwarp();
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = reg[j * 17 + i];
+#endif
             fft16(v);
             __syncwarp();
             // X[q + 16*r], r = 4*k1+k2 in v[4*k2+k1]
@@ -416,8 +426,8 @@ __device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_ff
         rl += 4;
         dds_row = (dds_row + FB) & ld_mask;
         if (tid == 0 && blk + 1 < n_blocks) {            // all threads passed the barrier inside channel_stage
-            mk_mbar_expect_tx(&s_bar[1], FB * NCH * 8);
-            mk_bulk_g2s(s_dds, dds_blk + (size_t)dds_row * NCH, FB * NCH * 8, &s_bar[1]);
+            mk_mbar_expect_tx(&s_bar[1], FB * NCH * 4);
+            mk_bulk_g2s(s_dds, dds_blk + (size_t)dds_row * NCH, FB * NCH * 4, &s_bar[1]);
         }
         ring_base = (ring_base + FB) & (RING - 1);
     }
@@ -427,8 +437,8 @@ __global__ void __launch_bounds__(256, 2) channelize_kernel(K4Params p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *s_fft = reinterpret_cast<float2 *>(smem_raw);                         // [16][FFT_STRIDE]
     float2 *s_tw = s_fft + 16 * FFT_STRIDE;                                       // [16][16]
-    float2 *s_dds = s_tw + 256;                                                    // [8][256] DDS values of the block
-    uint32_t *s_adc = reinterpret_cast<uint32_t *>(s_dds + FB * NCH);             // [8][256] ADC samples of the next block
+    uint32_t *s_dds = reinterpret_cast<uint32_t *>(s_tw + 256);                    // [8][256] DDS values of the block (int16 pairs)
+    uint32_t *s_adc = s_dds + FB * NCH;                                            // [8][256] ADC samples of the next block
     __shared__ __align__(8) uint64_t s_bar[2];                                     // mbarriers: ADC, DDS staging
     if (threadIdx.x == 0) {
         mk_mbar_init(&s_bar[0], 1);
@@ -451,6 +461,339 @@ __global__ void __launch_bounds__(256, 2) channelize_kernel(K4Params p) {
     if (p.phase_f32) channelize_chunk<true, true>(p, s_fft, s_adc, s_dds, s_bar, s_tw, board, row0, row1);     // test hook: slow path
     else if (edge) channelize_chunk<true, false>(p, s_fft, s_adc, s_dds, s_bar, s_tw, board, row0, row1);
     else channelize_chunk<false, false>(p, s_fft, s_adc, s_dds, s_bar, s_tw, board, row0, row1);
+}
+
+// ------------------------------------------------------------------------------------------
+// K4, warp-specialised form (the default).  One CTA per SM, 1024 threads in four roles that work on DIFFERENT blocks of
+// 8 frames at the same time, so that the shared-memory-bound FFT and the FP32-bound PFB / channel stages overlap
+// instead of alternating behind block-wide barriers (setmaxnreg gives every role the registers it needs):
+//   CHAN  threads   0..255 (96 regs): thread c = channel c: gather its bin from exchange buffer kb mod 4, DDS mix,
+//         transposed-form 26-tap FIR, centre, atan2, Fix16_13 store, candidate mask.
+//   PFB   threads 256..511 (40 regs): thread k = branches k, k+256: sliding register window over the ADC blocks that
+//         arrive by 1-D TMA bulk copies, first radix-2 stage, 16 STS.64 into exchange buffer k mod 4.
+//   FFT0 / FFT1  threads 512..767 / 768..1023 (56 regs): group g transforms the blocks kb = g (mod 2) in place: 16
+//         FFT-256 per block, 16 lanes each, two radix-16 passes; a half-warp needs only __syncwarp.
+// Hand-over by mbarriers (256 arrivals each): u_full[buf] PFB -> FFT, x_done[buf] FFT -> CHAN, u_free[buf] CHAN -> PFB.
+// PFB and CHAN each have one named barrier per block (before their elected thread re-arms the ADC / DDS stage).
+// Every chunk is a regular chunk: the samples in front of the call come from `edge` = [input history | first 2048
+// samples of the call], which is all zeros in front of the start of the stream (frames before time 0 contribute +-0).
+constexpr int WS_THREADS = 1024;
+constexpr int WS_NBUF = 4;
+
+struct WsParams {
+    ChanDev d;
+    const uint32_t *in;      // [B][n] packed samples of this call
+    const uint32_t *edge;    // [B][H + 2048]: history, then a copy of the first 2048 samples of the call
+    int64_t n;
+    int64_t f0_abs;          // absolute frame index of local frame 0 (always even)
+    int16_t *phase;          // [B][rows][256]
+    float *phase_f32;        // optional (tests): unquantised phase of the new outputs [B][n/512][256]
+    int64_t rows;            // PRE_ROWS + n/512
+    int rows_per_chunk;      // multiple of 32
+    int chunks_per_board;
+    uint32_t *mask;          // [B][ceil(rows/32)][256] candidate bits, or nullptr
+    int16_t *halo;           // [B][chunks][32][256]
+};
+
+__device__ __forceinline__ void mk_mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mk_smem_u32(bar)) : "memory");
+}
+// wait with a long suspend hint: the warp sleeps in hardware until the phase completes instead of polling
+__device__ __forceinline__ void mk_mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(mk_smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
+}
+
+template <bool F32>
+__global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2 *s_u = reinterpret_cast<float2 *>(smem_raw);                           // [4][16][FFT_STRIDE]
+    float2 *s_tw = s_u + WS_NBUF * 16 * FFT_STRIDE;                               // [16][16]
+    uint32_t *s_adc = reinterpret_cast<uint32_t *>(s_tw + 256);                   // [2][8][256]
+    uint32_t *s_dds = s_adc + 2 * FB * NCH;                                       // [2][8][256]
+    __shared__ __align__(8) uint64_t s_bar[4 + 3 * WS_NBUF];     // adc_full[2], dds_full[2], u_full[4], x_done[4], u_free[4]
+    uint64_t *adc_full = s_bar, *dds_full = s_bar + 2, *u_full = s_bar + 4, *x_done = u_full + WS_NBUF, *u_free = x_done + WS_NBUF;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        mk_mbar_init(&adc_full[0], 1); mk_mbar_init(&adc_full[1], 1);
+        mk_mbar_init(&dds_full[0], 1); mk_mbar_init(&dds_full[1], 1);
+        for (int i = 0; i < WS_NBUF; ++i) { mk_mbar_init(&u_full[i], NCH); mk_mbar_init(&x_done[i], NCH); mk_mbar_init(&u_free[i], NCH); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 256) s_tw[tid] = p.d.tw256[tid];
+    __syncthreads();
+
+    const int board = blockIdx.y;
+    const ChanDev &d = p.d;
+    const int M = d.M;
+    const int64_t row0 = (int64_t)blockIdx.x * p.rows_per_chunk;
+    const int64_t row1 = min(row0 + (int64_t)p.rows_per_chunk, p.rows);
+    // rows [row0,row1) are stored; rows from r_start on are computed (the M rows in front of the chunk feed the
+    // rolling baseline of the trigger); row r is local output t = r - PRE_ROWS
+    const int64_t r_start = p.mask ? (row0 - M > 0 ? row0 - M : 0) : row0;
+    const int64_t tl0 = r_start - PRE_ROWS, tl1 = row1 - PRE_ROWS;
+    const int64_t fb_first = ((2 * tl0 - 24) >> 3) << 3;           // first frame block: floor to a multiple of 8
+    const int n_blocks = row0 < row1 ? (int)((2 * tl1 - fb_first + FB - 1) / FB) : 0;
+    auto unpack = [](uint32_t v) -> float2 {
+        return make_float2((float)(int16_t)(v & 0xFFFF), (float)(int16_t)(v >> 16));
+    };
+
+    if (tid >= 2 * NCH) {
+        // =============================== FFT groups ===============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        const int g = (tid - 2 * NCH) >> 8, lt = tid & 255, j = lt & 15;
+        for (int kb = g; kb < n_blocks; kb += 2) {
+            const int buf = kb % WS_NBUF;
+            mk_mbar_wait_sleep(&u_full[buf], (uint32_t)((kb / WS_NBUF) & 1));
+            float2 *reg = s_u + buf * 16 * FFT_STRIDE + (lt >> 4) * FFT_STRIDE;
+            float2 v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = reg[j + 16 * i];
+            fft16(v);
+            __syncwarp();
+            // B_j[q] = A_j[q] * W256^(j*q) -> reg[q*17 + j];  A_j[q], q = 4*k1+k2, sits in v[4*k2+k1]
+#pragma unroll
+            for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+                for (int k2 = 0; k2 < 4; ++k2) {
+                    const int q = 4 * k1 + k2;
+                    float2 x = v[4 * k2 + k1];
+                    if (q != 0) x = cmul(x, s_tw[q * 16 + j]);
+                    reg[q * 17 + j] = x;
+                }
+            __syncwarp();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = reg[j * 17 + i];
+            fft16(v);
+            __syncwarp();
+            // X[q + 16*r], r = 4*k1+k2 in v[4*k2+k1]
+#pragma unroll
+            for (int k1 = 0; k1 < 4; ++k1)
+#pragma unroll
+                for (int k2 = 0; k2 < 4; ++k2) reg[j + 16 * (4 * k1 + k2)] = v[4 * k2 + k1];
+            mk_mbar_arrive(&x_done[buf]);
+        }
+        return;
+    }
+
+    if (tid >= NCH) {
+        // =============================== PFB: polyphase filter + first radix-2 stage ===============================
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (n_blocks == 0) return;
+        const int k = tid - NCH;                                      // branches k and k + 256
+        float hA[PTAPS], hB[PTAPS];
+#pragma unroll
+        for (int q = 0; q < PTAPS; ++q) { hA[q] = d.window[NFFT * q + k]; hB[q] = d.window[NFFT * q + HOP + k]; }
+        const float2 w512 = d.tw512[k];
+        const uint32_t *in = p.in + (size_t)board * p.n;
+        const uint32_t *edge = p.edge + (size_t)board * (d.H + 2048) + d.H;   // edge[idx] valid for -H <= idx < 2048
+        auto arm_adc = [&](int blk) {                                 // elected thread: block blk -> stage blk & 1
+            const int64_t s0 = HOP * (fb_first + (int64_t)blk * FB);
+            const uint32_t *src = s0 >= 0 ? in + s0 : edge + s0;
+            mk_mbar_expect_tx(&adc_full[blk & 1], FB * HOP * 4);
+            mk_bulk_g2s(s_adc + (blk & 1) * FB * NCH, src, FB * HOP * 4, &adc_full[blk & 1]);
+        };
+        if (k == 0) {
+            arm_adc(0);
+            if (n_blocks > 1) arm_adc(1);
+        }
+        // warm-up: s[j] = x[256*(f+1) - 2048 + k + 256*j], j = 0..6 for f = fb_first
+        float2 sw[8];
+#pragma unroll
+        for (int j = 0; j < 7; ++j) {
+            const int64_t idx = HOP * (fb_first + 1) - WIN + k + HOP * j;
+            sw[j] = unpack(idx >= 0 ? in[idx] : edge[idx]);
+        }
+        sw[7] = make_float2(0.f, 0.f);
+        for (int blk = 0; blk < n_blocks; ++blk) {
+            const int buf = blk % WS_NBUF;
+            if (blk >= WS_NBUF) mk_mbar_wait_sleep(&u_free[buf], (uint32_t)((blk / WS_NBUF - 1) & 1));   // CHAN has gathered block blk - 4
+            mk_mbar_wait_sleep(&adc_full[blk & 1], (uint32_t)((blk >> 1) & 1));
+            const uint32_t *adc_c = s_adc + (blk & 1) * FB * NCH + k;
+            float2 *ub = s_u + buf * 16 * FFT_STRIDE + k;
+#pragma unroll
+            for (int i = 0; i < FB; ++i) {
+                sw[(i + 7) & 7] = unpack(adc_c[i * NCH]);
+                float2 u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
+#pragma unroll
+                for (int q = 0; q < PTAPS; ++q) {
+                    u0 = __ffma2_rn(make_float2(hA[q], hA[q]), sw[(2 * q + i) & 7], u0);
+                    u1 = __ffma2_rn(make_float2(hB[q], hB[q]), sw[(2 * q + 1 + i) & 7], u1);
+                }
+                ub[(2 * i) * FFT_STRIDE] = cadd(u0, u1);                      // even bins
+                ub[(2 * i + 1) * FFT_STRIDE] = cmul(csub(u0, u1), w512);      // odd bins
+            }
+            mk_mbar_arrive(&u_full[buf]);
+            asm volatile("bar.sync 1, 256;" ::: "memory");                   // every PFB thread has read ADC stage blk & 1
+            if (k == 0 && blk + 2 < n_blocks) arm_adc(blk + 2);
+        }
+        return;
+    }
+
+    // =============================== CHAN: thread = channel ===============================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+    if (n_blocks == 0) return;
+    const int bin = d.bins[board * NCH + tid];
+    const int par = bin & 1;
+    const int zoff = par * FFT_STRIDE + (bin >> 1);                // + 2*i*FFT_STRIDE per frame, + buffer base
+    const float cen_i = d.cen_i[board * NCH + tid], cen_q = d.cen_q[board * NCH + tid];
+    int16_t *phase = p.phase + (size_t)board * p.rows * NCH + tid;
+    // fused candidate mask (K5c): bit (r & 31) of mask[r >> 5][c] iff M*raw[r] - sum_{k=1..M} raw[r-k] < M*thr
+    const int thM = M * d.thr[board * NCH + tid];
+    const int64_t r_eval0 = row0 > RES_LO ? row0 : RES_LO;
+    int16_t *halo = p.halo ? p.halo + (((size_t)board * p.chunks_per_board + blockIdx.x) * 32) * NCH + tid : nullptr;
+    uint32_t *mk = p.mask ? p.mask + (size_t)board * ((p.rows + 31) >> 5) * NCH + tid : nullptr;
+    int S = 0;
+    uint32_t bits = 0;
+    const int ld_mask = d.Ld - 1;                               // Ld is a power of two
+    const uint32_t *dds_blk = d.dds + (size_t)board * d.Ld * NCH;
+    const int dds_row0 = (int)((p.f0_abs + fb_first) & ld_mask);   // f_abs mod Ld of the first frame of block 0
+    auto arm_dds = [&](int kb) {
+        const int row = (dds_row0 + kb * FB) & ld_mask;
+        mk_mbar_expect_tx(&dds_full[kb & 1], FB * NCH * 4);
+        mk_bulk_g2s(s_dds + (kb & 1) * FB * NCH, dds_blk + (size_t)row * NCH, FB * NCH * 4, &dds_full[kb & 1]);
+    };
+    if (tid == 0) {
+        arm_dds(0);
+        if (n_blocks > 1) arm_dds(1);
+    }
+    // ---- state in chunk-relative rows (32-bit): row r = row0 + rl
+    const int n_rows = (int)(row1 - row0);
+    const int rl_start = (int)(r_start - row0);                       // <= 0: first computed row
+    const int rl_eval0 = (int)(r_eval0 - row0);                       // first row whose trigger condition is evaluated
+    int16_t *phase_c = phase + row0 * NCH;                            // this thread's column at the chunk's first row
+    uint32_t *mk_c = mk ? mk + (row0 >> 5) * NCH : nullptr;           // row0 is a multiple of 32
+    float *f32_c = (F32 && p.phase_f32) ? p.phase_f32 + ((size_t)board * (p.rows - PRE_ROWS) + (row0 - PRE_ROWS)) * NCH + tid : nullptr;
+    int rl = (int)((fb_first >> 1) + PRE_ROWS - row0);                // relative row of the first output of block 0
+    const int rl_fast = rl_eval0 > M ? rl_eval0 : M;                  // from here on no boundary cases
+
+    // Transposed-form FIR: every new frame adds its contribution to the 13 outputs it belongs to.
+    // acc[] holds 16 output accumulators (4 completing in this block + 12 pending); the slot of the
+    // output with block-relative index m is (m + 4*block) mod 16, static inside each of the 4 ring
+    // phases RB = 8*(block mod 4).
+    float2 acc[16];
+#pragma unroll
+    for (int m = 0; m < 16; ++m) acc[m] = make_float2(0.f, 0.f);
+
+    auto channel_stage = [&](auto RBc, const float2 *xbuf, const uint32_t *dds_c, uint64_t *free_bar) {
+        constexpr int RB = decltype(RBc)::value;
+        constexpr int A0 = RB / 2;                                       // slot of output m = 0
+        // gather the bin, remove the half-frame hop phase of odd bins ((-1)^(bin*(f_abs+1)); f_abs of
+        // frame i has the parity of i because block starts and call starts are even), mix with conj(dds)
+        float2 y[FB];
+        const float2 *zsrc = xbuf + zoff;
+        float2 z[FB];
+#pragma unroll
+        for (int i = 0; i < FB; ++i) z[i] = zsrc[(2 * i) * FFT_STRIDE];
+#pragma unroll
+        for (int i = 0; i < FB; ++i) {
+            const float2 dvi = unpack(dds_c[i * NCH]);          // zeroed channels hold (0, 0): y = +-0, w = +0 as in the model
+            float2 zz = z[i];
+            if ((i & 1) == 0 && par) { zz.x = -zz.x; zz.y = -zz.y; }         // even i: f_abs + 1 odd
+            y[i].x = zz.x * dvi.x + zz.y * dvi.y;
+            y[i].y = zz.y * dvi.x - zz.x * dvi.y;
+        }
+        mk_mbar_arrive(free_bar);                                // the bins of this block are in registers: the buffer may be refilled
+        // output t = fb/2 + m uses frames 2t+1-25+k, k = 0..25: frame fb+i carries tap k = i - 2m + 24
+#pragma unroll
+        for (int k = 0; k < FIRT; ++k) {
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const int i = k - 24 + 2 * m;
+                if (i >= 0 && i < FB) acc[(A0 + m) & 15] = __ffma2_rn(d.fir2[k], y[i], acc[(A0 + m) & 15]);
+            }
+        }
+        float ar[4], ai[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            ar[jj] = acc[(A0 + jj) & 15].x; ai[jj] = acc[(A0 + jj) & 15].y;
+            acc[(A0 + jj) & 15] = make_float2(0.f, 0.f);                  // becomes output m = 12 + jj of the next block
+        }
+        if (rl + 3 < rl_start || rl >= n_rows) return;
+        const bool fast = rl >= rl_fast && rl + 3 < n_rows;
+        // rows leaving the rolling baseline while these 4 outputs enter it (M >= 4, so they were stored by
+        // an earlier block)
+        int old[4] = {0, 0, 0, 0};
+        if (mk) {
+            if (fast) {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) old[jj] = phase_c[(rl + jj - M) * NCH];
+            } else {
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) {
+                    const int ro = rl + jj - M;
+                    if (ro >= rl_start && rl + jj >= rl_start) old[jj] = ro >= 0 ? phase_c[ro * NCH] : halo[(32 + ro) * NCH];
+                }
+            }
+        }
+        int raw[4];
+        float ph[4];
+#pragma unroll
+        for (int jj = 0; jj < 4; ++jj) {
+            const float a = ar[jj] - cen_i, b = ai[jj] - cen_q;
+            ph[jj] = atan2_fast(b, a);
+            raw[jj] = __float2int_rn(ph[jj] * 8192.0f);
+        }
+        if (fast) {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                phase_c[(rl + jj) * NCH] = (int16_t)raw[jj];
+                if (F32) { if (f32_c && rl + jj + (int)(row0 - PRE_ROWS) >= 0) f32_c[(size_t)(rl + jj) * NCH] = ph[jj]; }
+                if (mk) {
+                    if ((M * raw[jj] - S) < thM) bits |= 1u << ((rl + jj) & 31);
+                    S += raw[jj] - old[jj];
+                }
+            }
+            if (mk && (rl & 31) == 28) { mk_c[(rl >> 5) * NCH] = bits; bits = 0; }
+        } else {
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+                const int r = rl + jj;
+                if (r < rl_start || r >= n_rows) continue;
+                if (r >= 0) phase_c[r * NCH] = (int16_t)raw[jj];
+                else halo[(32 + r) * NCH] = (int16_t)raw[jj];
+                if (F32) { if (f32_c && r >= 0 && r + (int)(row0 - PRE_ROWS) >= 0) f32_c[(size_t)r * NCH] = ph[jj]; }
+                if (mk) {
+                    if (r >= rl_eval0 && (M * raw[jj] - S) < thM) bits |= 1u << (r & 31);
+                    S += raw[jj] - old[jj];
+                    if (r >= 0 && ((r & 31) == 31 || r == n_rows - 1)) { mk_c[(r >> 5) * NCH] = bits; bits = 0; }
+                }
+            }
+        }
+    };
+
+    int ring_base = (int)(fb_first & (RING - 1));               // ring phase of block 0: 0, 8, 16 or 24
+    for (int kb = 0; kb < n_blocks; ++kb) {
+        const int buf = kb % WS_NBUF;
+        mk_mbar_wait_sleep(&x_done[buf], (uint32_t)((kb / WS_NBUF) & 1));
+        mk_mbar_wait_sleep(&dds_full[kb & 1], (uint32_t)((kb >> 1) & 1));
+        const float2 *xbuf = s_u + buf * 16 * FFT_STRIDE;
+        const uint32_t *dds_c = s_dds + (kb & 1) * FB * NCH + tid;
+        switch (ring_base) {
+        case 0: channel_stage(std::integral_constant<int, 0>{}, xbuf, dds_c, &u_free[buf]); break;
+        case 8: channel_stage(std::integral_constant<int, 8>{}, xbuf, dds_c, &u_free[buf]); break;
+        case 16: channel_stage(std::integral_constant<int, 16>{}, xbuf, dds_c, &u_free[buf]); break;
+        default: channel_stage(std::integral_constant<int, 24>{}, xbuf, dds_c, &u_free[buf]); break;
+        }
+        rl += 4;
+        ring_base = (ring_base + FB) & (RING - 1);
+        asm volatile("bar.sync 2, 256;" ::: "memory");              // every CHAN thread has read DDS stage kb & 1
+        if (tid == 0 && kb + 2 < n_blocks) arm_dds(kb + 2);
+    }
+}
+
+// edge[b] = [history (H samples) | first 2048 samples of this call]
+__global__ void edge_head_kernel(uint32_t *edge, int H, const uint32_t *in, int64_t n) {
+    const int board = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 2048) edge[(size_t)board * (H + 2048) + H + i] = in[(size_t)board * n + i];
 }
 
 // ------------------------------------------------------------------------------------------
@@ -783,7 +1126,7 @@ __global__ void __launch_bounds__(256) emit_warp_kernel(const int16_t *__restric
 // history <- last H samples of [history | new input]
 __global__ void update_history_kernel(uint32_t *hist, int H, const uint32_t *in, int64_t n, int n_boards) {
     const int board = blockIdx.y;
-    uint32_t *h = hist + (size_t)board * H;
+    uint32_t *h = hist + (size_t)board * (H + 2048);
     const uint32_t *x = in + (size_t)board * n;
     // out-of-place is required when n < H (shift): use a two-phase grid-stride that reads before writing
     // only when n >= H (pure copy); the n < H case is handled on the host by a staging buffer.
@@ -791,14 +1134,14 @@ __global__ void update_history_kernel(uint32_t *hist, int H, const uint32_t *in,
         h[i] = x[n - H + i];
 }
 
-__global__ void pack_dds_kernel(const int16_t *I, const int16_t *Q, int n_lut, float2 *out) {
+__global__ void pack_dds_kernel(const int16_t *I, const int16_t *Q, int n_lut, const float *gain, uint32_t *out) {
     // out[t][m] = lut[(t/2)*512 + 2*((m+154)%256) + (t&1)]   (define_DDS_LUT layout, ROACH_Setup.py:526-530)
     const int Ld = n_lut / 256;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= Ld * NCH) return;
     const int t = idx / NCH, m = idx % NCH;
     const int src = (t >> 1) * 512 + 2 * ((m + 154) & 255) + (t & 1);
-    out[idx] = make_float2((float)I[src], (float)Q[src]);
+    out[idx] = gain[m] != 0.f ? ((uint32_t)(uint16_t)I[src] | ((uint32_t)(uint16_t)Q[src] << 16)) : 0u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -989,12 +1332,12 @@ extern "C" int mkid_chan_create(mkid_ctx *ctx, const mkid_chan_params *prm, mkid
     bad |= A((void **)&d.tw512, 256 * 8);
     bad |= A((void **)&d.tw256, 256 * 8);
     bad |= A((void **)&d.bins, (size_t)B * NCH * 2);
-    bad |= A((void **)&d.ddsf, (size_t)B * d.Ld * NCH * 8);
+    bad |= A((void **)&d.dds, (size_t)B * d.Ld * NCH * 4);
     bad |= A((void **)&d.gain, (size_t)B * NCH * 4);
     bad |= A((void **)&d.cen_i, (size_t)B * NCH * 4);
     bad |= A((void **)&d.cen_q, (size_t)B * NCH * 4);
     bad |= A((void **)&d.thr, (size_t)B * NCH * 4);
-    bad |= A((void **)&d.hist, (size_t)B * d.H * 4);
+    bad |= A((void **)&d.hist, (size_t)B * (d.H + 2048) * 4);
     bad |= A((void **)&d.t_next, (size_t)B * NCH * 8);
     bad |= A((void **)&ch->n_words_dev, (size_t)B * 4);
     if (bad) { mkid_chan_destroy(ctx, ch); return mkid_fail(ctx, MKID_ENOMEM, "chan_create: device allocation failed"); }
@@ -1030,7 +1373,7 @@ extern "C" void mkid_chan_destroy(mkid_ctx *ctx, mkid_chan *ch) {
     if (!ch) return;
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     ChanDev &d = ch->d;
-    void *ps[] = {d.window, d.tw512, d.tw256, d.bins, d.ddsf, d.gain, d.cen_i, d.cen_q, d.thr, d.hist, d.t_next,
+    void *ps[] = {d.window, d.tw512, d.tw256, d.bins, d.dds, d.gain, d.cen_i, d.cen_q, d.thr, d.hist, d.t_next,
                   ch->n_words_dev, ch->halo, ch->phase_buf, ch->mask, ch->acc, ch->win_cnt, ch->words_dev, ch->in_dev};
     for (void *p : ps) if (p) cudaFree(p);
     for (int i = 0; i < 2 * mkid_chan::EV_RING; ++i) if (ch->ev_k4[i]) cudaEventDestroy(ch->ev_k4[i]);
@@ -1096,8 +1439,8 @@ extern "C" int mkid_chan_set_board(mkid_ctx *ctx, mkid_chan *ch, int32_t board, 
     MKID_CUDA(ctx, cudaMemcpyAsync(tmp, I_dds, (size_t)d.n_lut * 2, cudaMemcpyDefault, ctx->stream));
     MKID_CUDA(ctx, cudaMemcpyAsync(tmp + d.n_lut, Q_dds, (size_t)d.n_lut * 2, cudaMemcpyDefault, ctx->stream));
     const int total = d.Ld * NCH;
-    pack_dds_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(tmp, tmp + d.n_lut, d.n_lut,
-                                                                 d.ddsf + (size_t)board * d.Ld * NCH);
+    pack_dds_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(tmp, tmp + d.n_lut, d.n_lut, d.gain + (size_t)board * NCH,
+                                                                 d.dds + (size_t)board * d.Ld * NCH);
     MKID_CHECK_LAUNCH(ctx);
     MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     ch->board_set[board] = true;
@@ -1116,7 +1459,7 @@ extern "C" int mkid_chan_reset(mkid_ctx *ctx, mkid_chan *ch) {
     if (!ctx) return MKID_EINVAL;
     MKID_REQUIRE(ctx, ch, "chan_reset: NULL");
     ChanDev &d = ch->d;
-    MKID_CUDA(ctx, cudaMemsetAsync(d.hist, 0, (size_t)d.n_boards * d.H * 4, ctx->stream));
+    MKID_CUDA(ctx, cudaMemsetAsync(d.hist, 0, (size_t)d.n_boards * (d.H + 2048) * 4, ctx->stream));
     MKID_CUDA(ctx, cudaMemsetAsync(d.t_next, 0, (size_t)d.n_boards * NCH * 8, ctx->stream));
     ch->t_consumed = 0;
     return MKID_OK;
@@ -1155,9 +1498,12 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
         ch->phase_rows = (size_t)rows;
     }
     // K4
+    static const bool legacy = getenv("MKID_K4_LEGACY") != nullptr;      // (the block-synchronous kernel, kept for A/B runs)
     K4Params p;
     p.d = d; p.in = in_dev; p.n = n; p.f0_abs = 2 * ch->t_consumed; p.phase = ch->phase_buf; p.rows = rows; p.phase_f32 = ch->f32_out;
-    {   // chunk 0 = EDGE_ROWS rows (slow path, small); the rest in equal chunks: one wave of 2 CTAs per SM when
+    WsParams w;
+    w.d = d; w.in = in_dev; w.edge = d.hist; w.n = n; w.f0_abs = p.f0_abs; w.phase = ch->phase_buf; w.phase_f32 = ch->f32_out; w.rows = rows;
+    if (legacy) {   // chunk 0 = EDGE_ROWS rows (slow path, small); the rest in equal chunks: one wave of 2 CTAs per SM when
         // the chunks stay >= 256 rows, else fewer chunks
         static const int edge_env = getenv("MKID_K4_EDGE") ? atoi(getenv("MKID_K4_EDGE")) : 0;      // (experiment switch)
         p.edge_rows = std::max(EDGE_ROWS, edge_env / 32 * 32);
@@ -1168,6 +1514,14 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
         rpc = std::max<int64_t>(32, (rpc + 31) / 32 * 32);
         p.rows_per_chunk = (int)rpc;
         p.chunks_per_board = 1 + (int)((rest + rpc - 1) / rpc);
+    } else {        // equal chunks, one CTA per SM in a single wave
+        int64_t chunks = std::max<int64_t>(1, (int64_t)ctx->num_sms / B);
+        while (chunks > 1 && rows / chunks < 128) chunks = (chunks + 1) / 2;
+        int64_t rpc = (rows + chunks - 1) / chunks;
+        rpc = std::max<int64_t>(32, (rpc + 31) / 32 * 32);
+        w.rows_per_chunk = (int)rpc;
+        w.chunks_per_board = (int)((rows + rpc - 1) / rpc);
+        p.chunks_per_board = w.chunks_per_board;
     }
     p.mask = nullptr; p.halo = nullptr;
     if (detect) {       // K5c fused into K4: the candidate mask is produced while the phase is in registers
@@ -1180,16 +1534,32 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
         ch->halo_bytes = cap;
         p.mask = ch->mask; p.halo = ch->halo;
     }
-    const size_t smem = (size_t)(16 * FFT_STRIDE + 256 + FB * NCH) * sizeof(float2) + (size_t)FB * NCH * 4;   // fft exchange, twiddles, DDS + ADC staging
-    MKID_CUDA(ctx, cudaFuncSetAttribute(channelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    w.mask = p.mask; w.halo = p.halo;
     g_timer.report();
     g_timer.mark(ctx->stream, "start");
     cudaEvent_t *evp = &ch->ev_k4[2 * (ch->n_calls % mkid_chan::EV_RING)];
     if (!evp[0]) { cudaEventCreate(&evp[0]); cudaEventCreate(&evp[1]); }
     ch->n_calls++;
-    MKID_CUDA(ctx, cudaEventRecord(evp[0], ctx->stream));
-    channelize_kernel<<<dim3(p.chunks_per_board, B), 256, smem, ctx->stream>>>(p);
-    MKID_CHECK_LAUNCH(ctx);
+    if (legacy) {
+        const size_t smem = (size_t)(16 * FFT_STRIDE + 256) * sizeof(float2) + (size_t)2 * FB * NCH * 4;   // fft exchange, twiddles, DDS + ADC staging
+        MKID_CUDA(ctx, cudaFuncSetAttribute(channelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MKID_CUDA(ctx, cudaEventRecord(evp[0], ctx->stream));
+        channelize_kernel<<<dim3(p.chunks_per_board, B), 256, smem, ctx->stream>>>(p);
+        MKID_CHECK_LAUNCH(ctx);
+    } else {
+        const size_t smem = (size_t)(WS_NBUF * 16 * FFT_STRIDE + 256) * sizeof(float2) + (size_t)4 * FB * NCH * 4;
+        MKID_CUDA(ctx, cudaEventRecord(evp[0], ctx->stream));
+        edge_head_kernel<<<dim3(8, B), 256, 0, ctx->stream>>>(d.hist, d.H, in_dev, n);
+        MKID_CHECK_LAUNCH(ctx);
+        if (ch->f32_out) {
+            MKID_CUDA(ctx, cudaFuncSetAttribute(channelize_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            channelize_ws_kernel<true><<<dim3(w.chunks_per_board, B), WS_THREADS, smem, ctx->stream>>>(w);
+        } else {
+            MKID_CUDA(ctx, cudaFuncSetAttribute(channelize_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            channelize_ws_kernel<false><<<dim3(w.chunks_per_board, B), WS_THREADS, smem, ctx->stream>>>(w);
+        }
+        MKID_CHECK_LAUNCH(ctx);
+    }
     MKID_CUDA(ctx, cudaEventRecord(evp[1], ctx->stream));
     g_timer.mark(ctx->stream, "channelize");
     if (phase_out) {
