@@ -93,10 +93,21 @@ __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
 }
 __device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }   // a * (-i)
 
-// forward 4-point DFT in place: (a0,a1,a2,a3) -> (X0,X1,X2,X3)
+// forward 4-point DFT in place: (a0,a1,a2,a3) -> (X0,X1,X2,X3).  The six complex additions that do not cross the real and
+// imaginary parts are packed f32x2 operations (FADD2 / FFMA2 with -1: one issue slot for both halves, same roundings
+// as two scalar FADDs); the two outputs that take the -i rotation stay scalar.
+#ifndef K4_SCALAR_FFT
+__device__ __forceinline__ float2 padd(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 psub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }   // a - b, exact product
+#else
+__device__ __forceinline__ float2 padd(float2 a, float2 b) { return cadd(a, b); }
+__device__ __forceinline__ float2 psub(float2 a, float2 b) { return csub(a, b); }
+#endif
 __device__ __forceinline__ void fft4(float2 &a0, float2 &a1, float2 &a2, float2 &a3) {
-    float2 t0 = cadd(a0, a2), t1 = csub(a0, a2), t2 = cadd(a1, a3), t3 = mul_mi(csub(a1, a3));
-    a0 = cadd(t0, t2); a2 = csub(t0, t2); a1 = cadd(t1, t3); a3 = csub(t1, t3);
+    const float2 t0 = padd(a0, a2), t1 = psub(a0, a2), t2 = padd(a1, a3), d = psub(a1, a3);
+    a0 = padd(t0, t2); a2 = psub(t0, t2);
+    a1 = make_float2(t1.x + d.y, t1.y - d.x);          // t1 + (-i) d
+    a3 = make_float2(t1.x - d.y, t1.y + d.x);          // t1 - (-i) d
 }
 
 // forward 16-point DFT; on return X[4*k1 + k2] is in v[4*k2 + k1]
@@ -467,12 +478,13 @@ __global__ void __launch_bounds__(256, 2) channelize_kernel(K4Params p) {
 // K4, warp-specialised form (the default).  One CTA per SM, 1024 threads in four roles that work on DIFFERENT blocks of
 // 8 frames at the same time, so that the shared-memory-bound FFT and the FP32-bound PFB / channel stages overlap
 // instead of alternating behind block-wide barriers (setmaxnreg gives every role the registers it needs):
-//   CHAN  threads   0..255 (96 regs): thread c = channel c: gather its bin from exchange buffer kb mod 4, DDS mix,
-//         transposed-form 26-tap FIR, centre, atan2, Fix16_13 store, candidate mask.
-//   PFB   threads 256..511 (40 regs): thread k = branches k, k+256: sliding register window over the ADC blocks that
-//         arrive by 1-D TMA bulk copies, first radix-2 stage, 16 STS.64 into exchange buffer k mod 4.
-//   FFT0 / FFT1  threads 512..767 / 768..1023 (56 regs): group g transforms the blocks kb = g (mod 2) in place: 16
+//   FFT0 / FFT1  threads 0..255 / 256..511 (56 regs): group g transforms the blocks kb = g (mod 2) in place: 16
 //         FFT-256 per block, 16 lanes each, two radix-16 passes; a half-warp needs only __syncwarp.
+//   PFB   threads 512..767 (40 regs): thread k = branches k, k+256: sliding register window over the ADC blocks that
+//         arrive by 1-D TMA bulk copies, first radix-2 stage, 16 STS.64 into exchange buffer k mod 4.
+//   CHAN  threads 768..1023 (96 regs): thread c = channel c: gather its bin from exchange buffer kb mod 4, DDS mix,
+//         transposed-form 26-tap FIR, centre, atan2, Fix16_13 store, candidate mask.  The role with the longest
+//         dependent chains has the highest warp ids (the issue arbiter prefers them).
 // Hand-over by mbarriers (256 arrivals each): u_full[buf] PFB -> FFT, x_done[buf] FFT -> CHAN, u_free[buf] CHAN -> PFB.
 // PFB and CHAN each have one named barrier per block (before their elected thread re-arms the ADC / DDS stage).
 // Every chunk is a regular chunk: the samples in front of the call come from `edge` = [input history | first 2048
@@ -539,16 +551,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
     // rolling baseline of the trigger); row r is local output t = r - PRE_ROWS
     const int64_t r_start = p.mask ? (row0 - M > 0 ? row0 - M : 0) : row0;
     const int64_t tl0 = r_start - PRE_ROWS, tl1 = row1 - PRE_ROWS;
-    const int64_t fb_first = ((2 * tl0 - 24) >> 3) << 3;           // first frame block: floor to a multiple of 8
+    // first frame block: floor to a multiple of 32 frames, so that block 0 is in ring phase 0 of the FIR accumulators
+    const int64_t fb_first = ((2 * tl0 - 24) >> 5) << 5;
     const int n_blocks = row0 < row1 ? (int)((2 * tl1 - fb_first + FB - 1) / FB) : 0;
     auto unpack = [](uint32_t v) -> float2 {
         return make_float2((float)(int16_t)(v & 0xFFFF), (float)(int16_t)(v >> 16));
     };
 
-    if (tid >= 2 * NCH) {
+    if (tid < 2 * NCH) {
         // =============================== FFT groups ===============================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
-        const int g = (tid - 2 * NCH) >> 8, lt = tid & 255, j = lt & 15;
+        const int g = tid >> 8, lt = tid & 255, j = lt & 15;
         for (int kb = g; kb < n_blocks; kb += 2) {
             const int buf = kb % WS_NBUF;
             mk_mbar_wait_sleep(&u_full[buf], (uint32_t)((kb / WS_NBUF) & 1));
@@ -583,11 +596,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
         return;
     }
 
-    if (tid >= NCH) {
+    if (tid < 3 * NCH) {
         // =============================== PFB: polyphase filter + first radix-2 stage ===============================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (n_blocks == 0) return;
-        const int k = tid - NCH;                                      // branches k and k + 256
+        const int k = tid - 2 * NCH;                                  // branches k and k + 256
         float hA[PTAPS], hB[PTAPS];
 #pragma unroll
         for (int q = 0; q < PTAPS; ++q) { hA[q] = d.window[NFFT * q + k]; hB[q] = d.window[NFFT * q + HOP + k]; }
@@ -640,16 +653,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
     // =============================== CHAN: thread = channel ===============================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
     if (n_blocks == 0) return;
-    const int bin = d.bins[board * NCH + tid];
+    const int c = tid - 3 * NCH;                                  // channel
+    const int bin = d.bins[board * NCH + c];
     const int par = bin & 1;
     const int zoff = par * FFT_STRIDE + (bin >> 1);                // + 2*i*FFT_STRIDE per frame, + buffer base
-    const float cen_i = d.cen_i[board * NCH + tid], cen_q = d.cen_q[board * NCH + tid];
-    int16_t *phase = p.phase + (size_t)board * p.rows * NCH + tid;
+    const float cen_i = d.cen_i[board * NCH + c], cen_q = d.cen_q[board * NCH + c];
+    int16_t *phase = p.phase + (size_t)board * p.rows * NCH + c;
     // fused candidate mask (K5c): bit (r & 31) of mask[r >> 5][c] iff M*raw[r] - sum_{k=1..M} raw[r-k] < M*thr
-    const int thM = M * d.thr[board * NCH + tid];
+    const int thM = M * d.thr[board * NCH + c];
     const int64_t r_eval0 = row0 > RES_LO ? row0 : RES_LO;
-    int16_t *halo = p.halo ? p.halo + (((size_t)board * p.chunks_per_board + blockIdx.x) * 32) * NCH + tid : nullptr;
-    uint32_t *mk = p.mask ? p.mask + (size_t)board * ((p.rows + 31) >> 5) * NCH + tid : nullptr;
+    int16_t *halo = p.halo ? p.halo + (((size_t)board * p.chunks_per_board + blockIdx.x) * 32) * NCH + c : nullptr;
+    uint32_t *mk = p.mask ? p.mask + (size_t)board * ((p.rows + 31) >> 5) * NCH + c : nullptr;
     int S = 0;
     uint32_t bits = 0;
     const int ld_mask = d.Ld - 1;                               // Ld is a power of two
@@ -660,7 +674,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
         mk_mbar_expect_tx(&dds_full[kb & 1], FB * NCH * 4);
         mk_bulk_g2s(s_dds + (kb & 1) * FB * NCH, dds_blk + (size_t)row * NCH, FB * NCH * 4, &dds_full[kb & 1]);
     };
-    if (tid == 0) {
+    if (c == 0) {
         arm_dds(0);
         if (n_blocks > 1) arm_dds(1);
     }
@@ -670,7 +684,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
     const int rl_eval0 = (int)(r_eval0 - row0);                       // first row whose trigger condition is evaluated
     int16_t *phase_c = phase + row0 * NCH;                            // this thread's column at the chunk's first row
     uint32_t *mk_c = mk ? mk + (row0 >> 5) * NCH : nullptr;           // row0 is a multiple of 32
-    float *f32_c = (F32 && p.phase_f32) ? p.phase_f32 + ((size_t)board * (p.rows - PRE_ROWS) + (row0 - PRE_ROWS)) * NCH + tid : nullptr;
+    float *f32_c = (F32 && p.phase_f32) ? p.phase_f32 + ((size_t)board * (p.rows - PRE_ROWS) + (row0 - PRE_ROWS)) * NCH + c : nullptr;
     int rl = (int)((fb_first >> 1) + PRE_ROWS - row0);                // relative row of the first output of block 0
     const int rl_fast = rl_eval0 > M ? rl_eval0 : M;                  // from here on no boundary cases
 
@@ -707,7 +721,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
 #pragma unroll
             for (int m = 0; m < 16; ++m) {
                 const int i = k - 24 + 2 * m;
-                if (i >= 0 && i < FB) acc[(A0 + m) & 15] = __ffma2_rn(d.fir2[k], y[i], acc[(A0 + m) & 15]);
+                if (i >= 0 && i < FB) acc[(A0 + m) & 15] = __ffma2_rn(make_float2(d.fir[k], d.fir[k]), y[i], acc[(A0 + m) & 15]);
             }
         }
         float ar[4], ai[4];
@@ -769,23 +783,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
         }
     };
 
-    int ring_base = (int)(fb_first & (RING - 1));               // ring phase of block 0: 0, 8, 16 or 24
-    for (int kb = 0; kb < n_blocks; ++kb) {
+    // The ring phase of block kb is 8 * (kb mod 4) (fb_first is a multiple of 32 frames): four statically addressed
+    // copies in sequence, so that the accumulators never move between registers.
+    auto one_block = [&](auto RBc, int kb) {
         const int buf = kb % WS_NBUF;
         mk_mbar_wait_sleep(&x_done[buf], (uint32_t)((kb / WS_NBUF) & 1));
         mk_mbar_wait_sleep(&dds_full[kb & 1], (uint32_t)((kb >> 1) & 1));
-        const float2 *xbuf = s_u + buf * 16 * FFT_STRIDE;
-        const uint32_t *dds_c = s_dds + (kb & 1) * FB * NCH + tid;
-        switch (ring_base) {
-        case 0: channel_stage(std::integral_constant<int, 0>{}, xbuf, dds_c, &u_free[buf]); break;
-        case 8: channel_stage(std::integral_constant<int, 8>{}, xbuf, dds_c, &u_free[buf]); break;
-        case 16: channel_stage(std::integral_constant<int, 16>{}, xbuf, dds_c, &u_free[buf]); break;
-        default: channel_stage(std::integral_constant<int, 24>{}, xbuf, dds_c, &u_free[buf]); break;
-        }
+        channel_stage(RBc, s_u + buf * 16 * FFT_STRIDE, s_dds + (kb & 1) * FB * NCH + c, &u_free[buf]);
         rl += 4;
-        ring_base = (ring_base + FB) & (RING - 1);
         asm volatile("bar.sync 2, 256;" ::: "memory");              // every CHAN thread has read DDS stage kb & 1
-        if (tid == 0 && kb + 2 < n_blocks) arm_dds(kb + 2);
+        if (c == 0 && kb + 2 < n_blocks) arm_dds(kb + 2);
+    };
+    for (int kb = 0; kb < n_blocks; kb += 4) {
+        one_block(std::integral_constant<int, 0>{}, kb);
+        if (kb + 1 >= n_blocks) break;
+        one_block(std::integral_constant<int, 8>{}, kb + 1);
+        if (kb + 2 >= n_blocks) break;
+        one_block(std::integral_constant<int, 16>{}, kb + 2);
+        if (kb + 3 >= n_blocks) break;
+        one_block(std::integral_constant<int, 24>{}, kb + 3);
     }
 }
 
