@@ -4,18 +4,10 @@
 // The arithmetic is the model defined in oracle/channelizer.py (the firmware data plane is absent
 // from the reference; see include/mkidgpu.h for the control-plane interfaces each stage follows).
 //
-// K4 layout: one CTA = (board, chunk of output rows); 256 threads.  Work proceeds in blocks of
-// 8 frames (hop 256 samples, 2x oversampled):
-//   PFB    thread k owns branches k and k+256; an 8-deep sliding register window means every
-//          ADC sample is loaded from HBM exactly once per chunk (4 B coalesced per lane per frame);
-//          the first radix-2 DIF stage of the 512-point FFT is done in registers.
-//   FFT    16 FFTs of 256 points per block (8 frames x even/odd bins), 16 threads each, two radix-16
-//          passes in registers with one padded shared-memory exchange; the 16 threads of one FFT sit
-//          in one warp, so the exchange needs only __syncwarp.
-//   CHAN   thread c = channel c: gather its bin, DDS mix (packed LUT read through L2), append to a
-//          32-frame shared-memory ring (private column per thread, no block barrier), 26-tap FIR
-//          for 4 outputs at once from a register window, centre subtract, atan2, Fix16_13 store.
-// FP32-issue-bound, not HBM-bound (about 150 instructions per ADC sample against 4 B read).
+// K4 layout: one CTA per SM = (board, chunk of output rows), 1024 threads in four roles (PFB, 2 x FFT, channel stage)
+// that work on different blocks of 8 frames (hop 256 samples, 2x oversampled) at the same time; see the comment in front
+// of channelize_ws_kernel.  Per ADC sample: 4 B read from HBM once, about 130 instructions, 111 FP32 lane operations:
+// the kernel is bound by the FP32 pipe, the issue slots and the shared-memory pipe together (each 65-75 % busy), not by HBM.
 #include <math.h>
 #include <stdlib.h>
 
@@ -38,7 +30,6 @@ constexpr int PRE_ROWS = 96;             // output rows recomputed in front of e
 constexpr int RES_LO = 32;               // first resolved row of the phase buffer in mkid_chan_process
 constexpr int T_START = 64;              // first absolute output index that may trigger
 constexpr int FFT_STRIDE = 272;          // 16 x 17 padded float2 per 256-point FFT
-constexpr int EDGE_ROWS = 160;            // rows of chunk 0: everything that can touch the input history
 constexpr int CAND_ROWS = 1024;          // rows per CTA of the candidate kernel
 constexpr int64_t SEC_US = 1000000;
 
@@ -47,8 +38,7 @@ struct ChanDev {                         // device-resident configuration + stat
     float *window;        // [2048]
     float2 *tw512;        // [256]  W512^k
     float2 *tw256;        // [16][16] W256^(j*q) stored [q][j]
-    float fir[FIRT];      // c_k / (2047*32767)
-    float2 fir2[FIRT];    // (c_k, c_k) pairs: packed f32x2 FMA operands
+    float fir[FIRT];      // c_k / (2047*32767): scalar operands of the packed f32x2 FMAs of the FIR
     int16_t *bins;        // [B][256]
     uint32_t *dds;        // [B][Ld][256]  I | Q << 16 (int16 pair), channel-minor; zeroed channels hold 0
     float *gain;          // [B][256] 0 (zeroed FIR) or 1 (kept for reporting; the kernel uses the zeroed DDS entries)
@@ -129,21 +119,6 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
     for (int k2 = 0; k2 < 4; ++k2) fft4(v[4 * k2], v[4 * k2 + 1], v[4 * k2 + 2], v[4 * k2 + 3]);
 }
 
-struct K4Params {
-    ChanDev d;
-    const uint32_t *in;      // [B][n] packed samples of this call
-    int64_t n;               // samples per board in this call
-    int64_t f0_abs;          // absolute frame index of local frame 0 (always even)
-    int16_t *phase;          // [B][rows][256]
-    float *phase_f32;        // optional [B][n/512][256] unquantised phase (rad) of the new outputs (tests)
-    int64_t rows;            // PRE_ROWS + n/512
-    int edge_rows;           // rows of chunk 0 (multiple of 32, >= EDGE_ROWS)
-    int rows_per_chunk;      // multiple of 32
-    int chunks_per_board;
-    uint32_t *mask;          // [B][ceil(rows/32)][256] candidate bits (fused K5c), or nullptr
-    int16_t *halo;           // [B][chunks][32][256] phase rows recomputed in front of a chunk (baseline history)
-};
-
 // atan2 for the phase stage: branch-free, |error| < 4e-7 rad (minimax degree-8 polynomial in t^2 on
 // [0,1], fast division), exact signed-zero / axis behaviour of atan2f where the model needs it.
 __device__ __forceinline__ float atan2_fast(float y, float x) {
@@ -164,314 +139,6 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
     p = ay > ax ? 1.5707963267948966f - p : p;
     p = x < 0.f ? 3.14159265358979f - p : p;
     return copysignf(p, y);
-}
-
-// One chunk of output rows of one board.  EDGE = the chunk touches the start of the call (input
-// history) or the start of the stream (frames before time 0 contribute nothing).
-template <bool EDGE, bool F32>
-__device__ __forceinline__ void channelize_chunk(const K4Params &p, float2 *s_fft, uint32_t *s_adc, uint32_t *s_dds,
-                                                 uint64_t *s_bar, const float2 *s_tw, int board, int64_t row0,
-                                                 int64_t row1) {
-    const int tid = threadIdx.x;
-    // rows [row0,row1) are stored; rows from r_start on are computed (the M rows in front of the chunk
-    // feed the rolling baseline of the trigger); row r is local output t = r - PRE_ROWS
-    const int M = p.d.M;
-    const int64_t r_start = p.mask ? (row0 - M > 0 ? row0 - M : 0) : row0;
-    const int64_t tl0 = r_start - PRE_ROWS, tl1 = row1 - PRE_ROWS;
-    const ChanDev &d = p.d;
-    // ---- per-thread constants
-    float2 hA[PTAPS], hB[PTAPS];           // (h, h) pairs for packed f32x2 FMAs
-#pragma unroll
-    for (int q = 0; q < PTAPS; ++q) {
-        hA[q] = make_float2(d.window[NFFT * q + tid], d.window[NFFT * q + tid]);
-        hB[q] = make_float2(d.window[NFFT * q + HOP + tid], d.window[NFFT * q + HOP + tid]);
-    }
-    const float2 w512 = d.tw512[tid];
-    const int bin = d.bins[board * NCH + tid];
-    const int par = bin & 1;
-    const float2 *zsrc = s_fft + par * FFT_STRIDE + (bin >> 1);      // + 2*i*FFT_STRIDE per frame
-    const float cen_i = d.cen_i[board * NCH + tid], cen_q = d.cen_q[board * NCH + tid];
-    const uint32_t *in = p.in + (size_t)board * p.n;
-    const uint32_t *hist = d.hist + (size_t)board * (d.H + 2048);
-    int16_t *phase = p.phase + (size_t)board * p.rows * NCH + tid;
-    // fused candidate mask (K5c): bit (r & 31) of mask[r >> 5][c] iff M*raw[r] - sum_{k=1..M} raw[r-k] < M*thr
-    const int thM = M * d.thr[board * NCH + tid];
-    const int64_t r_eval0 = row0 > RES_LO ? row0 : RES_LO;
-    int16_t *halo = p.halo ? p.halo + (((size_t)board * p.chunks_per_board + blockIdx.x) * 32) * NCH + tid : nullptr;
-    uint32_t *mk = p.mask ? p.mask + (size_t)board * ((p.rows + 31) >> 5) * NCH + tid : nullptr;
-    int S = 0;
-    uint32_t bits = 0;
-
-    // first frame block: the FIR of output tl0 needs frames 2*tl0 - 24 .. 2*tl0 + 1
-    const int64_t fb_first = ((2 * tl0 - 24) >> 3) << 3;       // floor to a multiple of 8
-    const int n_blocks = (int)((2 * tl1 - fb_first + FB - 1) / FB);
-    const int ld_mask = d.Ld - 1;                               // Ld is a power of two
-    int dds_row = (int)((p.f0_abs + fb_first) & ld_mask);       // f_abs mod Ld of the block's first frame
-    int ring_base = (int)(fb_first & (RING - 1));               // 0, 8, 16 or 24
-    const uint32_t *src = in + HOP * fb_first + tid;            // sample of frame fb_first handled by this thread
-
-    auto load_sample = [&](int64_t nidx) -> uint32_t {          // EDGE only
-        if (nidx >= 0) return in[nidx];
-        const int64_t h = (int64_t)d.H + nidx;
-        return h >= 0 ? hist[h] : 0u;
-    };
-    auto unpack = [](uint32_t v) -> float2 {
-        return make_float2((float)(int16_t)(v & 0xFFFF), (float)(int16_t)(v >> 16));
-    };
-
-    // ---- PFB warm-up: s[j] = x[256*(f+1) - 2048 + k + 256*j], j = 0..6 for f = fb_first
-    float2 sw[8];
-#pragma unroll
-    for (int j = 0; j < 7; ++j) {
-        if (EDGE) sw[j] = unpack(load_sample(HOP * (fb_first + 1) - WIN + tid + HOP * j));
-        else sw[j] = unpack(src[HOP * (j - 7)]);
-    }
-    sw[7] = make_float2(0.f, 0.f);
-    // staging buffers: the 2048 ADC samples of the next block (8 KiB, contiguous in HBM) and the 8 x 256 DDS
-    // values of the current block (8 KiB of int16 pairs, contiguous in the repacked LUT) arrive by 1-D TMA bulk copies issued
-    // by thread 0 and signalled on mbarriers, while the arithmetic runs.  EDGE chunks (input history, time < 0)
-    // fill their own ADC column with plain loads instead.
-    uint32_t *adc_c = s_adc + tid;
-    const uint32_t *dds_c = s_dds + tid;
-    const uint32_t *adc_blk = in + HOP * fb_first;                // first sample of the block being staged
-    const uint32_t *dds_blk = d.dds + (size_t)board * d.Ld * NCH;  // + dds_row * NCH
-    uint32_t par_adc = 0, par_dds = 0;
-    if (EDGE) {
-#pragma unroll
-        for (int i = 0; i < FB; ++i) adc_c[i * NCH] = load_sample(HOP * (fb_first + i) + tid);
-    } else if (tid == 0) {
-        mk_mbar_expect_tx(&s_bar[0], FB * HOP * 4);
-        mk_bulk_g2s(s_adc, adc_blk, FB * HOP * 4, &s_bar[0]);
-    }
-    if (tid == 0) {
-        mk_mbar_expect_tx(&s_bar[1], FB * NCH * 4);
-        mk_bulk_g2s(s_dds, dds_blk + (size_t)dds_row * NCH, FB * NCH * 4, &s_bar[1]);
-    }
-
-    // ---- channel-stage state in chunk-relative rows (32-bit): row r = row0 + rl
-    const int n_rows = (int)(row1 - row0);
-    const int rl_start = (int)(r_start - row0);                       // <= 0: first computed row
-    const int rl_eval0 = (int)(r_eval0 - row0);                       // first row whose trigger condition is evaluated
-    int16_t *phase_c = phase + row0 * NCH;                            // this thread's column at the chunk's first row
-    uint32_t *mk_c = mk ? mk + (row0 >> 5) * NCH : nullptr;           // row0 is a multiple of 32
-    float *f32_c = p.phase_f32 ? p.phase_f32 + ((size_t)board * (p.rows - PRE_ROWS) + (row0 - PRE_ROWS)) * NCH + tid : nullptr;
-    int rl = (int)((fb_first >> 1) + PRE_ROWS - row0);                // relative row of the block's first output
-    const int rl_fast = rl_eval0 > M ? rl_eval0 : M;                  // from here on no boundary cases
-
-    // Transposed-form FIR: every new frame adds its contribution to the 13 outputs it belongs to.
-    // acc[] holds 16 output accumulators (4 completing in this block + 12 pending); the slot of the
-    // output with block-relative index m is (m + 4*block) mod 16, static inside each of the 4 ring
-    // phases RB = 8*(block mod 4).  No shared-memory history of the mixed samples is needed.
-    float2 acc[16];
-#pragma unroll
-    for (int m = 0; m < 16; ++m) acc[m] = make_float2(0.f, 0.f);
-
-    auto channel_stage = [&](auto RBc, int blk) {
-        constexpr int RB = decltype(RBc)::value;
-        constexpr int A0 = RB / 2;                                       // slot of output m = 0
-        // gather the bin, remove the half-frame hop phase of odd bins ((-1)^(bin*(f_abs+1)); f_abs of
-        // frame i has the parity of i because block starts and call starts are even), mix with conj(dds)
-        float2 y[FB];
-#pragma unroll
-        for (int i = 0; i < FB; ++i) {
-            float2 z = zsrc[(2 * i) * FFT_STRIDE];
-            const float2 dvi = unpack(dds_c[i * NCH]);          // zeroed channels hold (0, 0): y = +-0, w = +0 as in the model
-            if ((i & 1) == 0 && par) { z.x = -z.x; z.y = -z.y; }           // even i: f_abs + 1 odd
-            y[i].x = z.x * dvi.x + z.y * dvi.y;
-            y[i].y = z.y * dvi.x - z.x * dvi.y;
-            if (EDGE) {
-                const int64_t f_abs = p.f0_abs + fb_first + (int64_t)blk * FB + i;
-                if (f_abs < 0) { y[i].x = 0.f; y[i].y = 0.f; }
-            }
-        }
-        // every thread has gathered its bins: the next block's PFB may overwrite s_fft
-        __syncthreads();
-        // output t = fb/2 + m uses frames 2t+1-25+k, k = 0..25: frame fb+i carries tap k = i - 2m + 24
-#pragma unroll
-        for (int k = 0; k < FIRT; ++k) {
-#pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const int i = k - 24 + 2 * m;
-                if (i >= 0 && i < FB) acc[(A0 + m) & 15] = __ffma2_rn(d.fir2[k], y[i], acc[(A0 + m) & 15]);
-            }
-        }
-        float ar[4], ai[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            ar[jj] = acc[(A0 + jj) & 15].x; ai[jj] = acc[(A0 + jj) & 15].y;
-            acc[(A0 + jj) & 15] = make_float2(0.f, 0.f);                  // becomes output m = 12 + jj of the next block
-        }
-        if (rl + 3 < rl_start || rl >= n_rows) return;
-        const bool fast = rl >= rl_fast && rl + 3 < n_rows;
-        // rows leaving the rolling baseline while these 4 outputs enter it (M >= 4, so they were stored by
-        // an earlier block)
-        int old[4] = {0, 0, 0, 0};
-        if (mk) {
-            if (fast) {
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) old[jj] = phase_c[(rl + jj - M) * NCH];
-            } else {
-#pragma unroll
-                for (int jj = 0; jj < 4; ++jj) {
-                    const int ro = rl + jj - M;
-                    if (ro >= rl_start && rl + jj >= rl_start) old[jj] = ro >= 0 ? phase_c[ro * NCH] : halo[(32 + ro) * NCH];
-                }
-            }
-        }
-        int raw[4];
-        float ph[4];
-#pragma unroll
-        for (int jj = 0; jj < 4; ++jj) {
-            const float a = ar[jj] - cen_i, b = ai[jj] - cen_q;
-            ph[jj] = atan2_fast(b, a);
-            raw[jj] = __float2int_rn(ph[jj] * 8192.0f);
-        }
-        if (fast) {
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                phase_c[(rl + jj) * NCH] = (int16_t)raw[jj];
-                if (F32) { if (f32_c && rl + jj + (int)(row0 - PRE_ROWS) >= 0) f32_c[(size_t)(rl + jj) * NCH] = ph[jj]; }
-                if (mk) {
-                    if ((M * raw[jj] - S) < thM) bits |= 1u << ((rl + jj) & 31);
-                    S += raw[jj] - old[jj];
-                }
-            }
-            if (mk && (rl & 31) == 28) { mk_c[(rl >> 5) * NCH] = bits; bits = 0; }
-        } else {
-#pragma unroll
-            for (int jj = 0; jj < 4; ++jj) {
-                const int r = rl + jj;
-                if (r < rl_start || r >= n_rows) continue;
-                if (r >= 0) phase_c[r * NCH] = (int16_t)raw[jj];
-                else halo[(32 + r) * NCH] = (int16_t)raw[jj];
-                if (F32) { if (f32_c && r >= 0 && r + (int)(row0 - PRE_ROWS) >= 0) f32_c[(size_t)r * NCH] = ph[jj]; }
-                if (mk) {
-                    if (r >= rl_eval0 && (M * raw[jj] - S) < thM) bits |= 1u << (r & 31);
-                    S += raw[jj] - old[jj];
-                    if (r >= 0 && ((r & 31) == 31 || r == n_rows - 1)) { mk_c[(r >> 5) * NCH] = bits; bits = 0; }
-                }
-            }
-        }
-    };
-
-    for (int blk = 0; blk < n_blocks; ++blk) {
-        if (!EDGE) { mk_mbar_wait(&s_bar[0], par_adc); par_adc ^= 1; }      // this block's ADC samples have landed
-        // ================= PFB + first radix-2 stage for 8 frames =================
-#pragma unroll
-        for (int i = 0; i < FB; ++i) {
-            sw[(i + 7) & 7] = unpack(adc_c[i * NCH]);
-            float2 u0 = make_float2(0.f, 0.f), u1 = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int q = 0; q < PTAPS; ++q) {
-                u0 = __ffma2_rn(hA[q], sw[(2 * q + i) & 7], u0);
-                u1 = __ffma2_rn(hB[q], sw[(2 * q + 1 + i) & 7], u1);
-            }
-            s_fft[(2 * i) * FFT_STRIDE + tid] = cadd(u0, u1);                      // even bins
-            s_fft[(2 * i + 1) * FFT_STRIDE + tid] = cmul(csub(u0, u1), w512);      // odd bins
-        }
-        // prefetch: next block's ADC samples and this block's DDS values (consumed after the FFT)
-        src += HOP * FB;
-        adc_blk += HOP * FB;
-        if (EDGE && blk + 1 < n_blocks) {           // own column: read above by this thread only
-#pragma unroll
-            for (int i = 0; i < FB; ++i) adc_c[i * NCH] = load_sample(HOP * (fb_first + (int64_t)(blk + 1) * FB + i) + tid);
-        }
-        __syncthreads();
-        if (!EDGE && tid == 0 && blk + 1 < n_blocks) {   // every thread has consumed the ADC staging buffer
-            mk_mbar_expect_tx(&s_bar[0], FB * HOP * 4);
-            mk_bulk_g2s(s_adc, adc_blk, FB * HOP * 4, &s_bar[0]);
-        }
-        // ================= 16 x FFT-256: two radix-16 passes =================
-        {
-            float2 *reg = s_fft + (tid >> 4) * FFT_STRIDE;
-            const int j = tid & 15;
-            float2 v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = reg[j + 16 * i];
-            fft16(v);
-            __syncwarp();
-#ifdef K4_TW_ON_LOAD
-            // A_j[q], q = 4*k1+k2, sits in v[4*k2+k1] -> reg[q*17 + j]; the twiddle W256^(j*q) is applied by the reader
-#pragma unroll
-            for (int k1 = 0; k1 < 4; ++k1)
-#pragma unroll
-                for (int k2 = 0; k2 < 4; ++k2) reg[(4 * k1 + k2) * 17 + j] = v[4 * k2 + k1];
-            __syncwarp();
-            // B_i[j] = A_i[j] * W256^(i*j): data and twiddle loads of one element are issued together
-            v[0] = reg[j * 17];
-#pragma unroll
-            for (int i = 1; i < 16; ++i) v[i] = cmul(reg[j * 17 + i], s_tw[i * 16 + j]);
-#else
-            // B_j[q] = A_j[q] * W256^(j*q) -> reg[q*17 + j];  A_j[q], q = 4*k1+k2, sits in v[4*k2+k1]
-#pragma unroll
-            for (int k1 = 0; k1 < 4; ++k1)
-#pragma unroll
-                for (int k2 = 0; k2 < 4; ++k2) {
-                    const int q = 4 * k1 + k2;
-                    float2 x = v[4 * k2 + k1];
-                    if (q != 0) x = cmul(x, s_tw[q * 16 + j]);
-                    reg[q * 17 + j] = x;
-                }
-            __syncwarp();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = reg[j * 17 + i];
-#endif
-            fft16(v);
-            __syncwarp();
-            // X[q + 16*r], r = 4*k1+k2 in v[4*k2+k1]
-#pragma unroll
-            for (int k1 = 0; k1 < 4; ++k1)
-#pragma unroll
-                for (int k2 = 0; k2 < 4; ++k2) reg[j + 16 * (4 * k1 + k2)] = v[4 * k2 + k1];
-        }
-        __syncthreads();
-        // ================= channel stage: thread = channel =================
-        // The ring position of a block takes only 4 values; one statically addressed copy per value.
-        mk_mbar_wait(&s_bar[1], par_dds); par_dds ^= 1;                   // DDS values of this block have landed
-        switch (ring_base) {
-        case 0: channel_stage(std::integral_constant<int, 0>{}, blk); break;
-        case 8: channel_stage(std::integral_constant<int, 8>{}, blk); break;
-        case 16: channel_stage(std::integral_constant<int, 16>{}, blk); break;
-        default: channel_stage(std::integral_constant<int, 24>{}, blk); break;
-        }
-        rl += 4;
-        dds_row = (dds_row + FB) & ld_mask;
-        if (tid == 0 && blk + 1 < n_blocks) {            // all threads passed the barrier inside channel_stage
-            mk_mbar_expect_tx(&s_bar[1], FB * NCH * 4);
-            mk_bulk_g2s(s_dds, dds_blk + (size_t)dds_row * NCH, FB * NCH * 4, &s_bar[1]);
-        }
-        ring_base = (ring_base + FB) & (RING - 1);
-    }
-}
-
-__global__ void __launch_bounds__(256, 2) channelize_kernel(K4Params p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    float2 *s_fft = reinterpret_cast<float2 *>(smem_raw);                         // [16][FFT_STRIDE]
-    float2 *s_tw = s_fft + 16 * FFT_STRIDE;                                       // [16][16]
-    uint32_t *s_dds = reinterpret_cast<uint32_t *>(s_tw + 256);                    // [8][256] DDS values of the block (int16 pairs)
-    uint32_t *s_adc = s_dds + FB * NCH;                                            // [8][256] ADC samples of the next block
-    __shared__ __align__(8) uint64_t s_bar[2];                                     // mbarriers: ADC, DDS staging
-    if (threadIdx.x == 0) {
-        mk_mbar_init(&s_bar[0], 1);
-        mk_mbar_init(&s_bar[1], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    const int tid = threadIdx.x;
-    const int board = blockIdx.y;
-    // output rows [row0,row1) of the phase buffer; row r is local output t = r - PRE_ROWS
-    // chunk 0 is the short edge chunk (input history / stream start); the others are equal
-    const int64_t row0 = blockIdx.x == 0 ? 0 : p.edge_rows + (int64_t)(blockIdx.x - 1) * p.rows_per_chunk;
-    const int64_t row1 = blockIdx.x == 0 ? min((int64_t)p.edge_rows, p.rows) : min(row0 + (int64_t)p.rows_per_chunk, p.rows);
-    if (row0 >= row1) return;
-    s_tw[tid] = p.d.tw256[tid];
-    __syncthreads();
-    const int64_t r_start = p.mask ? (row0 - p.d.M > 0 ? row0 - p.d.M : 0) : row0;
-    const int64_t fb_first = ((2 * (r_start - PRE_ROWS) - 24) >> 3) << 3;
-    // earliest sample read: 256*(fb_first+1) - 2048; earliest absolute frame: f0_abs + fb_first
-    const bool edge = (HOP * (fb_first + 1) - WIN < 0) || (p.f0_abs + fb_first < 0);
-    if (p.phase_f32) channelize_chunk<true, true>(p, s_fft, s_adc, s_dds, s_bar, s_tw, board, row0, row1);     // test hook: slow path
-    else if (edge) channelize_chunk<true, false>(p, s_fft, s_adc, s_dds, s_bar, s_tw, board, row0, row1);
-    else channelize_chunk<false, false>(p, s_fft, s_adc, s_dds, s_bar, s_tw, board, row0, row1);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -507,11 +174,26 @@ struct WsParams {
     int16_t *halo;           // [B][chunks][32][256]
 };
 
+#ifdef K4_WARP_ARRIVE
+// One arrival per WARP (barrier counts are warps): the lanes' shared-memory accesses are ordered before the elected lane's
+// releasing arrive by __syncwarp.
+constexpr int WS_ARRIVALS = NCH / 32;
+__device__ __forceinline__ void mk_mbar_arrive(uint64_t *bar) {
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mk_smem_u32(bar)) : "memory");
+}
+#else
+constexpr int WS_ARRIVALS = NCH;
 __device__ __forceinline__ void mk_mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mk_smem_u32(bar)) : "memory");
 }
+#endif
 // wait with a long suspend hint: the warp sleeps in hardware until the phase completes instead of polling
 __device__ __forceinline__ void mk_mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
+#ifndef K4_SLEEP_WAIT
+    mk_mbar_wait(bar, parity);
+    return;
+#endif
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -536,7 +218,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
     if (tid == 0) {
         mk_mbar_init(&adc_full[0], 1); mk_mbar_init(&adc_full[1], 1);
         mk_mbar_init(&dds_full[0], 1); mk_mbar_init(&dds_full[1], 1);
-        for (int i = 0; i < WS_NBUF; ++i) { mk_mbar_init(&u_full[i], NCH); mk_mbar_init(&x_done[i], NCH); mk_mbar_init(&u_free[i], NCH); }
+        for (int i = 0; i < WS_NBUF; ++i) { mk_mbar_init(&u_full[i], WS_ARRIVALS); mk_mbar_init(&x_done[i], WS_ARRIVALS); mk_mbar_init(&u_free[i], WS_ARRIVALS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (tid < 256) s_tw[tid] = p.d.tw256[tid];
@@ -1380,7 +1062,7 @@ extern "C" int mkid_chan_create(mkid_ctx *ctx, const mkid_chan_params *prm, mkid
     MKID_CUDA(ctx, cudaMemcpy(d.window, h.data(), WIN * 4, cudaMemcpyHostToDevice));
     MKID_CUDA(ctx, cudaMemcpy(d.tw512, t512.data(), 256 * 8, cudaMemcpyHostToDevice));
     MKID_CUDA(ctx, cudaMemcpy(d.tw256, t256.data(), 256 * 8, cudaMemcpyHostToDevice));
-    for (int k = 0; k < FIRT; ++k) { d.fir[k] = 0.f; d.fir2[k] = make_float2(0.f, 0.f); }
+    for (int k = 0; k < FIRT; ++k) d.fir[k] = 0.f;
     *out = ch;
     return mkid_chan_reset(ctx, ch);
 }
@@ -1402,7 +1084,6 @@ extern "C" int mkid_chan_set_fir(mkid_ctx *ctx, mkid_chan *ch, const int32_t *fi
     for (int k = 0; k < FIRT; ++k) {
         MKID_REQUIRE(ctx, fir_int[k] >= -2048 && fir_int[k] <= 2047, "FIR taps are 12-bit two's complement");
         ch->d.fir[k] = (float)((double)fir_int[k] / (2047.0 * 32767.0));
-        ch->d.fir2[k] = make_float2(ch->d.fir[k], ch->d.fir[k]);
     }
     ch->fir_set = true;
     return MKID_OK;
@@ -1513,60 +1194,39 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
         if ((rc = ensure(ctx, (void **)&ch->phase_buf, &cap, (size_t)B * rows * NCH * 2))) return rc;
         ch->phase_rows = (size_t)rows;
     }
-    // K4
-    static const bool legacy = getenv("MKID_K4_LEGACY") != nullptr;      // (the block-synchronous kernel, kept for A/B runs)
-    K4Params p;
-    p.d = d; p.in = in_dev; p.n = n; p.f0_abs = 2 * ch->t_consumed; p.phase = ch->phase_buf; p.rows = rows; p.phase_f32 = ch->f32_out;
+    // K4: equal chunks of rows, one CTA per SM in a single wave
     WsParams w;
-    w.d = d; w.in = in_dev; w.edge = d.hist; w.n = n; w.f0_abs = p.f0_abs; w.phase = ch->phase_buf; w.phase_f32 = ch->f32_out; w.rows = rows;
-    if (legacy) {   // chunk 0 = EDGE_ROWS rows (slow path, small); the rest in equal chunks: one wave of 2 CTAs per SM when
-        // the chunks stay >= 256 rows, else fewer chunks
-        static const int edge_env = getenv("MKID_K4_EDGE") ? atoi(getenv("MKID_K4_EDGE")) : 0;      // (experiment switch)
-        p.edge_rows = std::max(EDGE_ROWS, edge_env / 32 * 32);
-        const int64_t rest = std::max<int64_t>(rows - p.edge_rows, 0);
-        int64_t chunks = std::max<int64_t>(1, (int64_t)ctx->num_sms * 2 / B - 1);
-        while (chunks > 1 && rest / chunks < 256) chunks = (chunks + 1) / 2;
-        int64_t rpc = (rest + chunks - 1) / chunks;
-        rpc = std::max<int64_t>(32, (rpc + 31) / 32 * 32);
-        p.rows_per_chunk = (int)rpc;
-        p.chunks_per_board = 1 + (int)((rest + rpc - 1) / rpc);
-    } else {        // equal chunks, one CTA per SM in a single wave
+    w.d = d; w.in = in_dev; w.edge = d.hist; w.n = n; w.f0_abs = 2 * ch->t_consumed; w.phase = ch->phase_buf; w.phase_f32 = ch->f32_out; w.rows = rows;
+    {
         int64_t chunks = std::max<int64_t>(1, (int64_t)ctx->num_sms / B);
         while (chunks > 1 && rows / chunks < 128) chunks = (chunks + 1) / 2;
         int64_t rpc = (rows + chunks - 1) / chunks;
         rpc = std::max<int64_t>(32, (rpc + 31) / 32 * 32);
         w.rows_per_chunk = (int)rpc;
         w.chunks_per_board = (int)((rows + rpc - 1) / rpc);
-        p.chunks_per_board = w.chunks_per_board;
     }
-    p.mask = nullptr; p.halo = nullptr;
+    w.mask = nullptr; w.halo = nullptr;
     if (detect) {       // K5c fused into K4: the candidate mask is produced while the phase is in registers
         const int64_t n_groups = (rows + 31) >> 5;
         cap = ch->mask_bytes;
         if ((rc = ensure(ctx, (void **)&ch->mask, &cap, (size_t)B * n_groups * NCH * 4))) return rc;
         ch->mask_bytes = cap;
         cap = ch->halo_bytes;
-        if ((rc = ensure(ctx, (void **)&ch->halo, &cap, (size_t)B * p.chunks_per_board * 32 * NCH * 2))) return rc;
+        if ((rc = ensure(ctx, (void **)&ch->halo, &cap, (size_t)B * w.chunks_per_board * 32 * NCH * 2))) return rc;
         ch->halo_bytes = cap;
-        p.mask = ch->mask; p.halo = ch->halo;
+        w.mask = ch->mask; w.halo = ch->halo;
     }
-    w.mask = p.mask; w.halo = p.halo;
     g_timer.report();
     g_timer.mark(ctx->stream, "start");
     cudaEvent_t *evp = &ch->ev_k4[2 * (ch->n_calls % mkid_chan::EV_RING)];
     if (!evp[0]) { cudaEventCreate(&evp[0]); cudaEventCreate(&evp[1]); }
     ch->n_calls++;
-    if (legacy) {
-        const size_t smem = (size_t)(16 * FFT_STRIDE + 256) * sizeof(float2) + (size_t)2 * FB * NCH * 4;   // fft exchange, twiddles, DDS + ADC staging
-        MKID_CUDA(ctx, cudaFuncSetAttribute(channelize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MKID_CUDA(ctx, cudaEventRecord(evp[0], ctx->stream));
-        channelize_kernel<<<dim3(p.chunks_per_board, B), 256, smem, ctx->stream>>>(p);
-        MKID_CHECK_LAUNCH(ctx);
-    } else {
+    {
         const size_t smem = (size_t)(WS_NBUF * 16 * FFT_STRIDE + 256) * sizeof(float2) + (size_t)4 * FB * NCH * 4;
-        MKID_CUDA(ctx, cudaEventRecord(evp[0], ctx->stream));
+        // edge buffer <- first 2048 samples of this call (behind the history of the previous ones)
         edge_head_kernel<<<dim3(8, B), 256, 0, ctx->stream>>>(d.hist, d.H, in_dev, n);
         MKID_CHECK_LAUNCH(ctx);
+        MKID_CUDA(ctx, cudaEventRecord(evp[0], ctx->stream));
         if (ch->f32_out) {
             MKID_CUDA(ctx, cudaFuncSetAttribute(channelize_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             channelize_ws_kernel<true><<<dim3(w.chunks_per_board, B), WS_THREADS, smem, ctx->stream>>>(w);
