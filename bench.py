@@ -110,42 +110,121 @@ class ClockSampler(threading.Thread):
                 'samples': len(sm), 'source': 'nvml' if self.nvml is not None else 'nvidia-smi'}
 
 
-# ------------------------------------------------------------------ CPU reference arm (oracle port)
-def _cpu_worker(args):
-    import numpy as np   # noqa
-    from oracle import channelizer as oc
-    from oracle import decode as odec
-    iq, cfgd, slabs = args
-    cfg = oc.ChanConfig(cfgd['bins'], cfgd['I_dds'], cfgd['Q_dds'], cfgd['fir_int'], thresholds=cfgd['thr'],
-                        zero_ch=cfgd['zero_ch'], M=20, L=1000, W=32)
-    n = iq.shape[0]
-    step = n // slabs
-    hist = None
-    raws = []
-    for s in range(slabs):
-        a, b = s * step, (s + 1) * step
-        h = iq[max(0, a - 2 * 8192):a] if a else None
-        _, raw = oc.channelize_phase(iq[a:b], cfg, f0=a // 256, history=h)
-        raws.append(raw)
-    raw = np.concatenate(raws)
-    words = oc.detect_emit(raw, cfg, 0, np.zeros(256, np.int64), raw.shape[0] - 64 - cfg.M)
-    res = odec.packetmaster_bin([np.array(words, dtype=np.uint64)], 253, 4)
-    return len(words), int(res['counts'].sum())
+# ------------------------------------------------------------------ NUMA placement of the rank
+def numa_bind(torch, local_rank):
+    """Pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host buffers are allocated
+    (first touch places them on that node): the end-to-end leg of 8 ranks then uploads from both sockets' memory."""
+    try:
+        prop = torch.cuda.get_device_properties(local_rank)
+        bus = '%04x:%02x:%02x.0' % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        node = int(open('/sys/bus/pci/devices/%s/numa_node' % bus).read().strip())
+        if node < 0:
+            return {'node': None}
+        cpus = set()
+        for part in open('/sys/devices/system/node/node%d/cpulist' % node).read().strip().split(','):
+            lo, _, hi = part.partition('-')
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = cpus & os.sched_getaffinity(0)
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+        return {'node': node, 'cpus': len(allowed)}
+    except Exception as e:          # placement is an optimisation only
+        return {'node': None, 'error': str(e)[:80]}
 
 
-def cpu_reference_rate(iq_boards, cfgs, n_samples_each, cores):
-    """Oracle (NumPy float64 port of the model + integer detection + PacketMaster binning) on
-    `cores` processes, one board slice each.  Returns (MS/s, seconds, description)."""
-    import multiprocessing as mp
-    jobs = [(np.ascontiguousarray(iq_boards[i % len(iq_boards)][:n_samples_each]), cfgs[i % len(cfgs)], 2)
-            for i in range(cores)]
-    ctxmp = mp.get_context('spawn')        # the parent holds a CUDA context: never fork it
-    t0 = time.time()
-    with ctxmp.Pool(cores) as pool:
-        pool.map(_cpu_worker, jobs)
-    dt = time.time() - t0
-    total = cores * n_samples_each
-    return total / dt / 1e6, dt, '%d board slices x 2^%d samples, one process per core' % (cores, int(np.log2(n_samples_each)))
+# ------------------------------------------------------------------ one chain leg (device resident)
+class ChainLeg:
+    """The full chain over `B` boards of this rank: products (counts [exptime][n_pix] + hist [n_pix][bins]) in ONE device
+    tensor, summed over the ranks by ONE NCCL all-reduce queued on the context stream (mkid_hist_allreduce)."""
+
+    def __init__(self, torch, ctx, reducer, B, n, n_lut, n_active, npix_per_roach, n_roaches_total, roach0, seed0, synth_seed,
+                 hist_bins, exptime, want_merged=True):
+        from mkids_sdr_b200.chain import ReadoutChain
+        from mkids_sdr_b200.channelizer import synth_adc
+        self.torch, self.ctx, self.reducer, self.B, self.n = torch, ctx, reducer, B, n
+        self.n_pix = n_roaches_total * npix_per_roach
+        self.n_counts, self.n_hist = exptime * self.n_pix, self.n_pix * hist_bins
+        self.products = torch.zeros(self.n_counts + self.n_hist, dtype=torch.int32, device='cuda')
+        torch.cuda.synchronize()
+        self.chain, self.boards = ReadoutChain.synthetic(
+            B, n_lut, n_active, seed0=seed0, ctx=ctx, exptime=exptime, n_roaches_total=n_roaches_total, roach0=roach0,
+            n_bins=hist_bins, npix_per_roach=npix_per_roach, counts_buf=self.products[:self.n_counts],
+            hist_buf=self.products[self.n_counts:], want_merged=want_merged)
+        self.thr = self.chain.derive_thresholds(self.boards)
+        tone_bins = np.stack([bd['tone_bins'] for bd in self.boards])
+        self.iq = torch.empty((B, n, 2), dtype=torch.int16, device='cuda')
+        synth_adc(B, n, tone_bins, n_lut=n_lut, pulse_rate=1000.0, seed=synth_seed, out=self.iq, ctx=ctx)
+        ctx.sync()
+
+    def run(self, k):
+        """k batches queued back to back (no host round trip: word counts and carried seconds stay on the device), then
+        the one reduce of the products, all on the context stream."""
+        for _ in range(k):
+            self.chain.process_async(self.iq, n=self.n)
+        self.ctx.record(4)
+        self.reducer.allreduce(self.products, self.n_counts + self.n_hist)
+        self.ctx.record(5)
+
+    def timed(self, steps, warmup, barrier, world, dist):
+        torch, ctx = self.torch, self.ctx
+        self.run(max(warmup, 1))
+        self.chain.sync_state()
+        barrier()
+        l0 = ctx.launches
+        ctx.record(0)
+        t0 = time.time()
+        self.run(steps)
+        ctx.record(1)
+        self.chain.sync_state()
+        barrier()
+        wall = (time.time() - t0) * 1e3
+        kk = max(1, min(steps, 64))
+        k4_ms = self.chain.chan.kernel_ms_sum(kk) / kk
+        el = torch.tensor([max(ctx.elapsed_ms(0, 1), 0.0), wall, ctx.elapsed_ms(4, 5)], dtype=torch.float64, device='cuda')
+        if dist is not None:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms, red_ms = float(el[0]), float(el[1]), float(el[2])
+        step_ms = max(dev_ms, wall_ms) / steps           # device events; the wall clock is the cross-check
+        return dict(step_ms=step_ms, value=world * self.B * self.n / (step_ms * 1e-3) / 1e6, k4_ms=k4_ms,
+                    launches=int(ctx.launches - l0), reduce_ms=red_ms, reduce_bytes=int((self.n_counts + self.n_hist) * 4),
+                    dev_ms=dev_ms, wall_ms=wall_ms)
+
+    def free(self):
+        self.iq = self.products = None
+        self.chain = None
+        self.torch.cuda.empty_cache()
+
+
+def reference_arm(args, cores, config):
+    """`--impl reference`: the oracle port of the chain on all host cores, CPU only (no GPU, no libmkidgpu.so).  A step =
+    every core channelizes, detects and bins its resident 2^k-sample board stream (a bounded sample of the workload)."""
+    from oracle import cpu_arm
+    log2_each = 21
+    while log2_each > 18 and 1.1 * 2.0 ** (log2_each - 21) * (args.warmup + args.steps + 1) > 150.0:
+        log2_each -= 1
+    arm = cpu_arm.CpuArm(cores, 1 << log2_each, cpu_arm.fir_int_default())
+    for _ in range(args.warmup):
+        arm.step()
+    secs = [arm.step() for _ in range(args.steps)]
+    arm.close()
+    dt = float(np.mean(secs))
+    v = cores * (1 << log2_each) / dt / 1e6
+    desc = arm.describe()
+    return {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': max(args.gpus, 1), 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': dt * 1e3, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f64', 'data': 'synthetic', 'config': config,
+            'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc,
+                             'setup_seconds_untimed': arm.setup_seconds},
+            'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+
+
+def workload_config(n, hist_bins):
+    return {'workload': 'full ARCONS chain with matched-filter pulse detection: 8 boards x 256 channels per GPU (253 driven), '
+                        'channelize->phase->detect->photon words->decode/bin/hist + merged time-ordered list',
+            'boards_per_gpu': BOARDS_PER_GPU, 'samples_per_board_per_step': n, 'n_lut': N_LUT, 'fir': 'matched_30us',
+            'pulse_rate_hz': 1000, 'hist_bins': hist_bins, 'hist_field': 'peak',
+            'l2': 'inputs (%.0f MiB per GPU per step) are larger than the 126 MB L2' % (BOARDS_PER_GPU * n * 4 / 2 ** 20),
+            'sharding': 'boards per GPU, no data-path collective; ONE NCCL all-reduce of the per-pixel products per job'}
 
 
 def main():
@@ -155,9 +234,10 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--log2-samples', type=int, default=25, help='ADC samples per board per step (log2)')
-    ap.add_argument('--hist-bins', type=int, default=64)
+    ap.add_argument('--hist-bins', type=int, default=4096)
     ap.add_argument('--no-cpu-baseline', action='store_true')
-    ap.add_argument('--no-extras', action='store_true', help='skip the decode / LUT side measurements')
+    ap.add_argument('--no-extras', action='store_true', help='skip the strong-scaling / stress / decode / LUT side measurements')
+    ap.add_argument('--stress', action='store_true', help='run the config-5 stress leg at any GPU count (default: 8 GPUs only)')
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', '0'))
@@ -175,73 +255,34 @@ def main():
     def emit(line):
         os.write(json_fd, (json.dumps(line) + '\n').encode())
 
+    t_start = time.time()
+
     def stage(msg):
         if os.environ.get('MKID_BENCH_VERBOSE'):
             sys.stderr.write('[bench rank %d +%.1fs] %s\n' % (rank, time.time() - t_start, msg)); sys.stderr.flush()
-    t_start = time.time()
+
+    n = 1 << args.log2_samples
+    B = BOARDS_PER_GPU
+    config = workload_config(n, args.hist_bins)
+    cores = len(os.sched_getaffinity(0))
+    if args.impl == 'reference':
+        emit(reference_arm(args, cores, config))
+        return 0
+
     import torch
     if not torch.cuda.is_available():
         raise SystemExit('bench.py needs a CUDA device: the product path has no CPU fallback')
     torch.cuda.set_device(local_rank)
     dist = None
-    if world > 1 and args.impl == 'b200':
+    if world > 1:
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=torch.device('cuda', local_rank))
-
-    stage('process group up')
+    numa = numa_bind(torch, local_rank) if world > 1 else {'node': None}
+    stage('process group up, numa %s' % numa)
     from mkids_sdr_b200 import _lib
-    from mkids_sdr_b200.chain import ReadoutChain
-    from mkids_sdr_b200.channelizer import synth_adc
+    from mkids_sdr_b200.dist import ProductReducer
     ctx = _lib.default_context(local_rank)
-
-    n = 1 << args.log2_samples
-    B = BOARDS_PER_GPU
-    n_roaches_total = B * world
-    n_pix = n_roaches_total * 253
-    exptime = 64
-    # per-pixel products live in torch tensors so that NCCL can reduce them in place
-    counts_t = torch.zeros(exptime * n_pix, dtype=torch.int32, device='cuda')
-    hist_t = torch.zeros(n_pix * args.hist_bins, dtype=torch.int32, device='cuda')
-    chain, boards = ReadoutChain.synthetic(B, N_LUT, N_ACTIVE, seed0=42 + 8 * rank, ctx=ctx, exptime=exptime,
-                                           n_roaches_total=n_roaches_total, roach0=B * rank, n_bins=args.hist_bins,
-                                           counts_buf=counts_t, hist_buf=hist_t)
-    stage('chain configured')
-    thr = chain.derive_thresholds(boards)
-    stage('thresholds derived')
-    tone_bins = np.stack([bd['tone_bins'] for bd in boards])
-
-    # synthetic ADC streams, generated on the GPU, resident in HBM (1 GiB per GPU at the default size)
-    iq_dev = torch.empty((B, n, 2), dtype=torch.int16, device='cuda')
-    synth_adc(B, n, tone_bins, n_lut=N_LUT, pulse_rate=1000.0, seed=1000 + rank, out=iq_dev, ctx=ctx)
-    ctx.sync()
-
-    cfgs_cpu = [dict(bins=bd['bins'], I_dds=bd['I_dds'], Q_dds=bd['Q_dds'], fir_int=chain.fir_int, thr=thr[b],
-                     zero_ch=bd['zero_ch'].astype(bool)) for b, bd in enumerate(boards)]
-    cores = len(os.sched_getaffinity(0))
-
-    if args.impl == 'reference':
-        # bounded sample per step: ~1.1 s of CPU work at 2^21 samples per core; shrink it when many steps are asked
-        # for so that the whole run stays within about two minutes
-        log2_each = 21
-        while log2_each > 17 and 1.2 * 2.0 ** (log2_each - 21) * (args.warmup + args.steps) > 120.0:
-            log2_each -= 1
-        n_each = 1 << log2_each
-        iq_host = [iq_dev[b, :n_each].cpu().numpy() for b in range(min(B, cores))]
-        vals = []
-        for it in range(args.warmup + args.steps):
-            v, dt, desc = cpu_reference_rate(iq_host, cfgs_cpu, n_each, cores)
-            if it >= args.warmup:
-                vals.append((v, dt))
-        v = float(np.mean([x[0] for x in vals]))
-        line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': n_gpus, 'steps': args.steps,
-                'warmup': args.warmup, 'ms_per_step': float(np.mean([x[1] for x in vals]) * 1e3), 'higher_is_better': True,
-                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-                'config': {'workload': 'full ARCONS chain, 8 boards x 256 channels per GPU (bounded CPU sample)',
-                           'sample': desc},
-                'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc},
-                'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        emit(line)
-        return 0
+    reducer = ProductReducer(ctx, rank, world)           # the library's own NCCL communicator (C ABI)
 
     def barrier():
         ctx.sync()
@@ -250,51 +291,22 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def reduce_products():
-        if dist is not None:
-            ctx.sync()
-            dist.all_reduce(hist_t)
-            dist.all_reduce(counts_t)
-
-    def run_steps(k, iq):
-        """k batches queued back to back: no host round trip inside (word counts and carried seconds stay on the
-        device); returns the summed device time of the channelize kernel."""
-        for _ in range(k):
-            chain.process_async(iq, n=n)
-        chain.sync_state()
-        kk = max(1, min(k, 64))
-        return chain.chan.kernel_ms_sum(kk) * (k / kk)
-
-    stage('input synthesised')
-    # ---------------------------------------------------------------- device-resident value
-    run_steps(max(args.warmup, 1), iq_dev)            # (at least one untimed pass: buffers, range tables, NCCL)
-    reduce_products()
-    barrier()
+    exptime = 16
+    # ---------------------------------------------------------------- headline: weak scaling, 8 boards per GPU
+    leg = ChainLeg(torch, ctx, reducer, B, n, N_LUT, N_ACTIVE, 253, B * world, B * rank, 42 + 8 * rank, 1000 + rank,
+                   args.hist_bins, exptime)
+    stage('chain configured, thresholds derived, input synthesised')
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    l0 = ctx.launches
-    ctx.record(0)
-    t0 = time.time()
-    k4_ms = run_steps(args.steps, iq_dev)
-    reduce_products()
-    ctx.record(1)
-    barrier()
-    wall = time.time() - t0
-    dev_ms = ctx.elapsed_ms(0, 1)
-    launches = ctx.launches - l0
-    el = torch.tensor([max(dev_ms, 0.0), wall * 1e3], dtype=torch.float64, device='cuda')
-    if dist is not None:
-        dist.all_reduce(el, op=dist.ReduceOp.MAX)
-    dev_ms, wall_ms = float(el[0]), float(el[1])
-    # device-event time of the K steps (barrier + synchronize on both sides); the wall clock is the cross-check
-    step_ms = max(dev_ms, wall_ms) / args.steps
-    value = world * B * n / (step_ms * 1e-3) / 1e6
-
+    res = leg.timed(args.steps, args.warmup, barrier, world, dist)
     stage('device-resident steps done')
+    chain = leg.chain
+    n_pix = leg.n_pix
+
     # ---------------------------------------------------------------- end to end with host buffers
     pin_iq = torch.empty((B, n, 2), dtype=torch.int16).pin_memory()
-    pin_iq.copy_(iq_dev.cpu())
+    pin_iq.copy_(leg.iq.cpu())
     cap = chain.chan.words_capacity(n)
     pin_words = torch.empty((B, cap), dtype=torch.int64).pin_memory()
     pin_counts = torch.empty(exptime * n_pix, dtype=torch.int32).pin_memory()
@@ -308,40 +320,65 @@ def main():
         for nwk in chain.process_stream((pin_iq for _ in range(k)), n, words_host=words_np, counts_host=pin_counts):
             nw += int(nwk.sum())
         return nw
+    k_e2e = max(min(args.steps // 2, 25), 1)
     e2e_steps(1)
     barrier()
     t0 = time.time()
-    nw = e2e_steps(max(args.steps // 2, 1))
-    reduce_products()
+    nw = e2e_steps(k_e2e)
+    reducer.allreduce(leg.products, leg.n_counts + leg.n_hist)
     barrier()
     e2e_ms = (time.time() - t0) * 1e3
     el = torch.tensor([e2e_ms], dtype=torch.float64, device='cuda')
     if dist is not None:
         dist.all_reduce(el, op=dist.ReduceOp.MAX)
-    e2e_step_ms = float(el[0]) / max(args.steps // 2, 1)
+    e2e_step_ms = float(el[0]) / k_e2e
     e2e_value = world * B * n / (e2e_step_ms * 1e-3) / 1e6
-    words_per_step = nw / max(args.steps // 2, 1)
+    words_per_step = nw / k_e2e
     if rank == 0:
         sampler.stop_flag = True
+    del pin_iq, pin_words, pin_counts
+    fir_int = np.array(chain.fir_int)
+    leg.free()
+    stage('end-to-end done')
 
-    decode_sharded = lut_sharded = None
-    if dist is not None and not args.no_extras:
-        try:
-            decode_sharded = decode_sharded_bench(ctx, torch, dist, rank, world, measured_peaks()[0])
-        except Exception as e:      # side measurement only
-            decode_sharded = {'error': str(e)}
-        try:
-            lut_sharded = lut_sharded_bench(ctx, torch, dist, rank, world)
-        except Exception as e:
-            lut_sharded = {'error': str(e)}
+    extras = {}
+    if not args.no_extras:
+        # ------------------------------------------------------------ config 4 as written: the SAME 8 boards split over the GPUs
+        if dist is not None and 8 % world == 0:
+            try:
+                Bs = 8 // world
+                sl = ChainLeg(torch, ctx, reducer, Bs, n, N_LUT, N_ACTIVE, 253, 8, Bs * rank, 42 + Bs * rank, 1000 + rank,
+                              args.hist_bins, exptime)
+                r = sl.timed(max(args.steps // 2, 5), 3, barrier, 1, dist)       # world = 1: total work is the 8 boards
+                extras['strong_scaling'] = {'value': 8 * n / (r['step_ms'] * 1e-3) / 1e6, 'unit': UNIT, 'ms_per_step': r['step_ms'],
+                                            'boards_total': 8, 'boards_per_gpu': Bs, 'n_gpus': world, 'k4_ms_per_launch': r['k4_ms'],
+                                            'reduce_ms': r['reduce_ms'], 'scaling': 'strong',
+                                            'workload': 'BASELINE config 4: 8 boards sharded %d per GPU over %d GPUs' % (Bs, world)}
+                sl.free()
+            except Exception as e:      # side measurement only
+                extras['strong_scaling'] = {'error': str(e)[:200]}
+        # ------------------------------------------------------------ config 5: 20 000 resonators, NCCL-reduced [20000][4096]
+        if (world == 8 or args.stress) and 80 % world == 0:
+            try:
+                extras['stress_config5'] = stress_leg(torch, ctx, reducer, dist, rank, world, barrier, measured_peaks()[0])
+            except Exception as e:
+                extras['stress_config5'] = {'error': str(e)[:200]}
+        if dist is not None:
+            for name, fn in (('decode_sharded', lambda: decode_sharded_bench(ctx, torch, dist, rank, world, measured_peaks()[0], reducer)),
+                             ('lut_sharded', lambda: lut_sharded_bench(ctx, torch, dist, rank, world))):
+                try:
+                    extras[name] = fn()
+                except Exception as e:
+                    extras[name] = {'error': str(e)[:200]}
+    stage('side legs done')
     if rank != 0:
+        reducer.close()
         if dist is not None:
             dist.destroy_process_group()
         return 0
 
     peak, peak_src = measured_peaks()
-    k4_avg_ms = k4_ms / args.steps
-    achieved = BYTES_PER_SAMPLE * B * n / (k4_avg_ms * 1e-3) / 1e9
+    achieved = BYTES_PER_SAMPLE * B * n / (res['k4_ms'] * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, 'profiles', 'k4_traffic.json')
     if os.path.exists(tp):
@@ -349,53 +386,81 @@ def main():
             traffic = float(json.load(open(tp))['dram_bytes_per_sample']) * B * n
         except Exception:
             traffic = None
-    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': n_gpus, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-            'data': 'synthetic',
-            'config': {'workload': 'full ARCONS chain with matched-filter pulse detection: 8 boards x 256 channels per GPU '
-                                   '(253 driven), channelize->phase->detect->photon words->decode/bin/hist',
-                       'boards_per_gpu': B, 'samples_per_board_per_step': n, 'n_lut': N_LUT, 'fir': 'matched_30us',
-                       'pulse_rate_hz': 1000, 'hist_bins': args.hist_bins,
-                       'l2': 'inputs (%.0f MiB per GPU per step) are larger than the 126 MB L2' % (B * n * 4 / 2 ** 20),
-                       'sharding': 'boards per GPU, no data-path collective; one NCCL all-reduce of per-pixel products'},
-            'roofline': {'bound': 'hbm', 'kernel': 'channelize_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+    line = {'metric': METRIC, 'value': res['value'], 'unit': UNIT, 'n_gpus': n_gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': res['step_ms'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': config,
+            'roofline': {'bound': 'hbm', 'kernel': 'channelize_ws_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                         'kernel_ms_per_launch': k4_avg_ms, 'kernel_share_of_step': k4_avg_ms / step_ms,
-                         'note': 'algorithmic 4 B per complex ADC sample; the kernel is FP32-issue-bound, not HBM-bound '
-                                 '(see DESIGN.md)'},
+                         'kernel_ms_per_launch': res['k4_ms'], 'kernel_share_of_step': res['k4_ms'] / res['step_ms'],
+                         'note': 'algorithmic 4 B per complex ADC sample; the kernel is bound by the FP32 pipe / issue slots / shared '
+                                 'memory together, not by HBM (111 FP32 lane operations per sample: FP32 roof = 0.20 of the HBM roof, '
+                                 'see DESIGN.md)'},
+            'collective': {'what': 'ONE mkid_hist_allreduce (NCCL sum, uint32) of counts [%d][%d] + hist [%d][%d] per job, on the '
+                                   'context stream' % (exptime, n_pix, n_pix, args.hist_bins),
+                           'bytes': res['reduce_bytes'], 'ms': res['reduce_ms'],
+                           'bus_GB/s': (2.0 * (world - 1) / world * res['reduce_bytes'] / (res['reduce_ms'] * 1e-3) / 1e9) if world > 1 and res['reduce_ms'] > 0 else None,
+                           'share_of_timed_region': res['reduce_ms'] / max(res['dev_ms'], 1e-9)},
             'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(B * n * 4),
-                    'd2h_bytes_per_step': int(B * cap * 8 + pin_counts.numel() * 4 + B * 4), 'ms_per_step': e2e_step_ms,
-                    'api': 'ReadoutChain.process_stream (upload of batch k+1 overlaps the kernels of batch k)'},
-            'gpu_launches': int(launches),
+                    'd2h_bytes_per_step': int(B * cap * 8 + exptime * n_pix * 4 + B * 4), 'ms_per_step': e2e_step_ms, 'steps': k_e2e,
+                    'api': 'ReadoutChain.process_stream (upload of batch k+1 overlaps the kernels of batch k)', 'numa': numa},
+            'gpu_launches': res['launches'],
             'photon_words_per_step': words_per_step,
             'clocks': sampler.summary()}
-
-    if decode_sharded is not None:
-        line['decode_sharded'] = decode_sharded
-    if lut_sharded is not None:
-        line['lut_sharded'] = lut_sharded
+    line.update(extras)
     if not args.no_extras:
-        try:
-            line['decode'] = decode_side_bench(ctx, peak)
-        except Exception as e:      # side measurement only
-            line['decode'] = {'error': str(e)}
-        try:
-            line['lut'] = lut_side_bench(ctx)
-        except Exception as e:
-            line['lut'] = {'error': str(e)}
-
+        for name, fn in (('decode', lambda: decode_side_bench(ctx, peak)), ('lut', lambda: lut_side_bench(ctx))):
+            try:
+                line[name] = fn()
+            except Exception as e:      # side measurement only
+                line[name] = {'error': str(e)[:200]}
     if not args.no_cpu_baseline:
-        n_each = 1 << 21
-        iq_host = [iq_dev[b, :n_each].cpu().numpy() for b in range(min(B, cores))]
-        v, dt, desc = cpu_reference_rate(iq_host, cfgs_cpu, n_each, cores)
-        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': desc, 'seconds': dt}
+        try:
+            from oracle import cpu_arm
+            arm = cpu_arm.CpuArm(cores, 1 << 21, fir_int)
+            secs = [arm.step() for _ in range(3)]
+            arm.close()
+            dt = float(np.mean(secs))
+            line['cpu_baseline'] = {'value': cores * (1 << 21) / dt / 1e6, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                    'sample': arm.describe(), 'seconds_per_pass': dt, 'passes': 3,
+                                    'setup_seconds_untimed': arm.setup_seconds}
+        except Exception as e:
+            line['cpu_baseline'] = {'error': str(e)[:200]}
     emit(line)
+    reducer.close()
     if dist is not None:
         dist.destroy_process_group()
     return 0
 
 
-def decode_sharded_bench(ctx, torch, dist, rank, world, peak):
+def stress_leg(torch, ctx, reducer, dist, rank, world, barrier, peak):
+    """BASELINE config 5 / SURVEY 8d config 5: 20 000 resonators = 80 board streams of 250 active channels (10 feedlines x 8
+    sub-boards), 80 / world per GPU, channelize + detect + per-pixel 4096-bin peak histograms [20000][4096] u32 (328 MB)
+    summed over the GPUs by ONE NCCL all-reduce (mkid_hist_allreduce) per job."""
+    Bs = 80 // world
+    n = 1 << 23
+    steps = 8
+    leg = ChainLeg(torch, ctx, reducer, Bs, n, N_LUT, 250, 250, 80, Bs * rank, 100 + Bs * rank, 2000 + rank, 4096, 4,
+                   want_merged=False)
+    r = leg.timed(steps, 3, barrier, world, dist)
+    # checksum across ranks: the reduced histogram must be identical everywhere and hold every binned word
+    cs = torch.stack([leg.products[leg.n_counts:].sum(dtype=torch.int64), leg.products[:leg.n_counts].sum(dtype=torch.int64)])
+    allcs = [torch.zeros_like(cs) for _ in range(world)]
+    if dist is not None:
+        dist.all_gather(allcs, cs)
+    else:
+        allcs = [cs]
+    same = all(bool((c == allcs[0]).all()) for c in allcs)
+    leg.free()
+    bus = (2.0 * (world - 1) / world * r['reduce_bytes'] / (r['reduce_ms'] * 1e-3) / 1e9) if world > 1 and r['reduce_ms'] > 0 else None
+    return {'value': r['value'], 'unit': UNIT, 'ms_per_step': r['step_ms'], 'steps': steps, 'boards_total': 80, 'boards_per_gpu': Bs,
+            'resonators': 80 * 250, 'samples_per_board_per_step': n, 'k4_ms_per_launch': r['k4_ms'],
+            'hist_shape': [20000, 4096], 'reduce_bytes': r['reduce_bytes'], 'reduce_ms': r['reduce_ms'], 'reduce_bus_GB/s': bus,
+            'reduce_share_of_job': r['reduce_ms'] / max(r['dev_ms'], 1e-9), 'checksum_identical_on_all_ranks': same,
+            'hist_sum': int(allcs[0][0]), 'counts_sum': int(allcs[0][1]),
+            'frac_hbm_k4': 4.0 * Bs * n / (r['k4_ms'] * 1e-3) / 1e9 / peak}
+
+
+def decode_sharded_bench(ctx, torch, dist, rank, world, peak, reducer):
     """The second sharding mode of SURVEY 8e: a photon file set is split by packet-file chunk across the GPUs (every
     rank decodes its own replicas of the 8-roach file, 1.28 GB per GPU resident in HBM: weak scaling), then ONE NCCL
     sum-reduce of the per-pixel products (counts [10][2024] + 10-bin spectra [2024][10]).  Whole-job words/s, device
@@ -416,14 +481,12 @@ def decode_sharded_bench(ctx, torch, dist, rank, world, peak):
     counts_t, hist_t = buf_t[:n_counts], buf_t[n_counts:]
     lut = np.arange(4096) * 10 // 4096
     dec = PhotonDecoder(R, npix, secs, 2500, 'p1', 10, lut, ctx=ctx, counts_buf=counts_t, hist_buf=hist_t)
-    ext = torch.cuda.ExternalStream(int(ctx.stream or 0), device=torch.device('cuda', torch.cuda.current_device()))
     torch.cuda.synchronize()                     # buf_t was zeroed on torch's stream
 
     def one_pass():
         dec.reset()                              # every pass is one complete job: partial products, then the reduce
         dec.decode_words(dw, offs, roach, want_stats=False, want_sec=False)
-        with torch.cuda.stream(ext):
-            dist.all_reduce(buf_t)
+        reducer.allreduce(buf_t, buf_t.numel())      # mkid_hist_allreduce on the context stream
     for _ in range(3):
         one_pass()
     torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
@@ -440,7 +503,7 @@ def decode_sharded_bench(ctx, torch, dist, rank, world, peak):
     dw.free()
     gbs = total * 8 / ms / 1e6
     return {'words_per_s': total / ms * 1e3, 'GB/s': gbs, 'frac_hbm_per_gpu': gbs / world / peak, 'ms_per_pass': ms, 'n_gpus': world,
-            'collective': 'ONE NCCL all_reduce(sum) of counts [10][2024] + spectra [2024][10] per pass, queued on the context stream (no host sync inside a pass)',
+            'collective': 'ONE mkid_hist_allreduce (NCCL sum) of counts [10][2024] + spectra [2024][10] per pass, queued on the context stream (no host sync inside a pass)',
             'checksum_spectra': total_hist, 'checksum_expected': int(10 ** 7 * reps * world),
             'checksum_ok': total_hist == int(10 ** 7 * reps * world),
             'workload': '16 x 1e7 photon words per GPU (different seeds), decode + per-pixel counts + 10-bin spectra'}

@@ -44,6 +44,12 @@ const char *mkid_last_error(mkid_ctx *ctx);     /* ctx may be NULL: last init er
 int  mkid_sync(mkid_ctx *ctx);
 /* the CUDA stream of the context as an opaque handle (cudaStream_t) */
 void *mkid_stream(mkid_ctx *ctx);
+/* Ordering against a stream the library does not own (the context stream is non-blocking: work queued by PyTorch or by
+ * the caller on another stream is NOT ordered against it otherwise).  mkid_wait_stream: everything queued on
+ * ext_stream (cudaStream_t, NULL = the legacy default stream) so far happens before what is queued on the context
+ * afterwards; mkid_stream_wait_ctx: the reverse. */
+int  mkid_wait_stream(mkid_ctx *ctx, void *ext_stream);
+int  mkid_stream_wait_ctx(mkid_ctx *ctx, void *ext_stream);
 /* number of kernels this context has launched since creation (bench "gpu_launches") */
 int64_t mkid_launch_count(mkid_ctx *ctx);
 /* device timing on the context stream: record returns an event slot id (0..63) */
@@ -155,6 +161,18 @@ int mkid_decode_merged(mkid_ctx *ctx, const uint64_t *words, int64_t n_words, co
                        const int32_t *seg_roach, const int32_t *seg_sec, int32_t *seg_sec_out, int32_t n_segments,
                        const mkid_decode_cfg *cfg, uint32_t *counts_raw, uint64_t *list_words, int64_t list_cap,
                        int64_t *list_offsets, mkid_decode_stats *stats);
+
+/* The same merged list for ONE batch behind a producer on the same GPU (the per-board word regions of
+ * mkid_chan_process), fully asynchronous like mkid_decode_words_dev: segment i (in roach order) holds seg_len_dev[i]
+ * (DEVICE) of at most seg_cap[i] words starting at seg_start[i]; seg_sec_dev[i] (DEVICE) = seconds closed before it.
+ * Key = local second * n_segments + i, local second = end-of-second words seen before the word inside the batch
+ * (at most MKID_MERGE_MAX_SEC - 1; later words join the last key).  list_words (DEVICE, capacity list_cap) receives
+ * every valid pixel word (adr < npix_per_roach, absolute second < exptime) in stream order inside its key,
+ * list_offsets (DEVICE int32 [MKID_MERGE_MAX_SEC * n_segments + 1]) the start of every key.  Never synchronises. */
+#define MKID_MERGE_MAX_SEC 4
+int mkid_merge_words_dev(mkid_ctx *ctx, const uint64_t *words, const int64_t *seg_start, const int64_t *seg_cap,
+                         const int32_t *seg_len_dev, const int32_t *seg_sec_dev, int32_t n_segments,
+                         const mkid_decode_cfg *cfg, uint64_t *list_words, int64_t list_cap, int32_t *list_offsets);
 
 /* Wire format of DataReadout/ReadoutControls/lib/PulseServer.c:318-352 as received by
  * PacketMaster.c:286-287: per bundle 8192 big-endian u32 low halves then 8192 big-endian
@@ -385,6 +403,25 @@ int mkid_pack_dram(mkid_ctx *ctx, const int16_t *I_dac, const int16_t *Q_dac, co
                    const int16_t *Q_dds, int64_t n, uint8_t *out);
 /* test hook: the correctly rounded double sin/cos the exact LUT paths use */
 int mkid_sincos_cr(mkid_ctx *ctx, const double *x, int64_t n, double *s, double *c);
+
+/* ------------------------------------------------------------------ multi-GPU: the one collective of the path
+ * Replaces: the single aggregator of the reference, `++photon_counts[sec][ready_roach*NPIXELS_PER_ROACH+adr]`
+ * (DataReadout/ReadoutControls/lib/PacketMaster.c:371-381): one process receives all roaches.  Here every rank (one
+ * process per GPU) decodes its boards / packet-file chunks into its own copy of the per-pixel products
+ * (counts [sec][pixel], hist [pixel][bin], plain uint32 sums) and the copies are summed ONCE over NVLink by NCCL, in
+ * place, on the context stream (no host synchronisation).  Sums are order independent: identical at any GPU count.
+ * Apply mkid_counts_cap afterwards for the 2500-event quirk (PacketMaster.c:373-380).
+ * NCCL is bound at run time (libnccl.so.2); without it these calls return MKID_ENCCL and nothing else is affected.
+ *   mkid_nccl_unique_id : rank 0 creates the 128-byte id (ncclGetUniqueId) and hands it to the others by any means
+ *   mkid_nccl_init      : every rank, collectively (ncclCommInitRank); *comm is an ncclComm_t
+ *   mkid_hist_allreduce : every rank ends with the sum (the dashboards of all ranks can read it)
+ *   mkid_hist_reduce    : only `root` ends with the sum (PacketMaster's single writer)                         */
+int  mkid_nccl_version(mkid_ctx *ctx, int32_t *version);
+int  mkid_nccl_unique_id(mkid_ctx *ctx, uint8_t id_out[128]);
+int  mkid_nccl_init(mkid_ctx *ctx, const uint8_t id[128], int32_t n_ranks, int32_t rank, void **comm_out);
+int  mkid_nccl_destroy(mkid_ctx *ctx, void *comm);
+int  mkid_hist_allreduce(mkid_ctx *ctx, void *comm, uint32_t *products_dev, size_t n);
+int  mkid_hist_reduce(mkid_ctx *ctx, void *comm, uint32_t *products_dev, size_t n, int32_t root);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get('MKIDGPU_LIB') or os.path.join(_HERE, 'libmkidgpu.so')     # (override: kernel experiments)
 
+MERGE_MAX_SEC = 4            # MKID_MERGE_MAX_SEC of include/mkidgpu.h
 MKID_OK, MKID_ENODEV, MKID_EINVAL, MKID_ENOMEM, MKID_ECUDA, MKID_ENCCL = 0, -1, -2, -3, -4, -5
 
 
@@ -57,6 +58,15 @@ _SIGNATURES = {
     'mkid_last_error': (c_char_p, [c_void_p]),
     'mkid_sync': (c_int32, [c_void_p]),
     'mkid_stream': (c_void_p, [c_void_p]),
+    'mkid_merge_words_dev': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
+    'mkid_wait_stream': (c_int32, [c_void_p, c_void_p]),
+    'mkid_stream_wait_ctx': (c_int32, [c_void_p, c_void_p]),
+    'mkid_nccl_version': (c_int32, [c_void_p, c_void_p]),
+    'mkid_nccl_unique_id': (c_int32, [c_void_p, c_void_p]),
+    'mkid_nccl_init': (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
+    'mkid_nccl_destroy': (c_int32, [c_void_p, c_void_p]),
+    'mkid_hist_allreduce': (c_int32, [c_void_p, c_void_p, c_void_p, c_size_t]),
+    'mkid_hist_reduce': (c_int32, [c_void_p, c_void_p, c_void_p, c_size_t, c_int32]),
     'mkid_launch_count': (c_int64, [c_void_p]),
     'mkid_event_record': (c_int32, [c_void_p, c_int32]),
     'mkid_event_elapsed_ms': (c_int32, [c_void_p, c_int32, c_int32, POINTER(c_float)]),

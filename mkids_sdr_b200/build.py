@@ -62,7 +62,7 @@ def build(force=False, verbose=False):
     # entry point it names); the rpath is the image's toolkit, torch's copy has the same SONAME
     subprocess.check_call([NVCC, '-shared', '-cudart', 'shared', '-o', OUT] + objs +
                           ['-gencode', 'arch=compute_100a,code=sm_100a',
-                           '-Xlinker', '-rpath', '-Xlinker', '/usr/local/cuda/lib64'])
+                           '-Xlinker', '-rpath', '-Xlinker', '/usr/local/cuda/lib64', '-ldl'])
     open(STAMP, 'w').write(dig)
     return OUT
 

@@ -3,12 +3,13 @@ decode / per-pixel binning / histogram (K4 + K5 + K6), configured from the refer
 
 This is the public API a user of the reference switches to for the data path:
 
-    chain = ReadoutChain.from_setup(setup_forms, pulses_forms, ...)   # or .synthetic(...)
+    chain = ReadoutChain(n_boards, n_lut, fir_int, ...); chain.set_board(b, ...)      # or ReadoutChain.synthetic(...)
     out = chain.process(iq)          # iq: int16 [n_boards][n][2], host or device
 
 Boards (ROACH streams / feedlines) are independent; several GPUs each run their own chain over
 their own boards and sum the per-pixel histograms once (see dist.py).
 """
+import ctypes
 import os
 
 import numpy as np
@@ -26,7 +27,7 @@ FS = 512e6
 class ReadoutChain:
     def __init__(self, n_boards, n_lut, fir_int, mean_len=20, holdoff=1000, peak_win=32, npix_per_roach=253,
                  exptime=64, n_roaches_total=None, roach0=0, hist_field='peak', n_bins=64, bin_lut=None, ctx=None,
-                 counts_buf=None, hist_buf=None):
+                 counts_buf=None, hist_buf=None, want_merged=False):
         self.ctx = ctx or _lib.default_context()
         self.n_boards, self.n_lut = n_boards, n_lut
         self.roach0 = roach0
@@ -39,6 +40,10 @@ class ReadoutChain:
                                  bin_lut=bin_lut, ctx=self.ctx, counts_buf=counts_buf, hist_buf=hist_buf)
         self._words_dev = None
         self._cap = 0
+        # time-ordered merged photon list of every batch, device resident: merged_words_dev /
+        # merged_offsets_dev (int32 [MERGE_MAX_SEC * n_boards + 1], key = local second * n_boards + board)
+        self.want_merged = bool(want_merged)
+        self.merged_words_dev = self.merged_offsets_dev = None
         self.sec = np.zeros(n_boards, dtype=np.int32)
         self._sec_dev = None
         self._sec_on_host = True
@@ -103,6 +108,14 @@ class ReadoutChain:
         self.dec.decode_words_dev(self._words_dev, start, caps, self.chan.n_words_dev(),
                                   self.roach0 + np.arange(self.n_boards), self._sec_dev[self._sec_cur],
                                   self._sec_dev[1 - self._sec_cur], self.n_boards * self._cap)
+        if self.want_merged:
+            if self.merged_words_dev is None or self.merged_words_dev.nbytes < self.n_boards * self._cap * 8:
+                self.merged_words_dev = c.alloc(self.n_boards * self._cap * 8)
+                self.merged_offsets_dev = c.alloc((_lib.MERGE_MAX_SEC * self.n_boards + 1) * 4)
+            c._check(c.lib.mkid_merge_words_dev(c.h, _lib.ptr(self._words_dev), _lib.ptr(start), _lib.ptr(caps),
+                                                self.chan.n_words_dev(), _lib.ptr(self._sec_dev[self._sec_cur]),
+                                                self.n_boards, ctypes.byref(self.dec.cfg), _lib.ptr(self.merged_words_dev),
+                                                self.n_boards * self._cap, _lib.ptr(self.merged_offsets_dev)))
         self._sec_cur = 1 - self._sec_cur
 
     def process_stream(self, batches, n, words_host=None, counts_host=None):

@@ -52,6 +52,7 @@ extern "C" void mkid_destroy(mkid_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (int i = 0; i < 16; ++i) if (ctx->scratch[i]) cudaFree(ctx->scratch[i]);
     if (ctx->l2_flush) cudaFree(ctx->l2_flush);
+    if (ctx->merge_dev) cudaFree(ctx->merge_dev);
     for (int i = 0; i < 2; ++i) if (ctx->dec_priv[i]) cudaFree(ctx->dec_priv[i]);
     for (int i = 0; i < MKID_NUM_EVENTS; ++i) if (ctx->events[i]) cudaEventDestroy(ctx->events[i]);
     for (int i = 0; i < 8; ++i) if (ctx->dbg_events[i]) cudaEventDestroy(ctx->dbg_events[i]);

@@ -36,6 +36,10 @@ struct mkid_ctx {
     size_t dec_priv_bytes[2] = {};
     void *dec_ranges_dev = nullptr;
     size_t l2_flush_bytes = 0;
+    // segment table + per-key counts of mkid_merge_words_dev (private: the scratch slots are shared between entry points)
+    void *merge_dev = nullptr;
+    size_t merge_bytes = 0;
+    std::vector<char> merge_host;
 };
 
 enum { SCR_IN = 0, SCR_IN1, SCR_IN2, SCR_IN3, SCR_OUT0, SCR_OUT1, SCR_OUT2, SCR_OUT3, SCR_STATE, SCR_META, SCR_AUX0, SCR_AUX1, SCR_AUX2, SCR_AUX3, SCR_AUX4, SCR_AUX5 };

@@ -590,6 +590,100 @@ __global__ void __launch_bounds__(1024) decode_small_kernel(DecParams p, const D
 }
 
 // ------------------------------------------------------------------------------------------------
+// Time-ordered merged photon list of ONE channelizer batch, device-chained like decode_small_kernel (SURVEY 8d config 4:
+// "merged photon list sorted by (sec, roach, ts)"; what PacketMaster's per-second flush hands on, PacketMaster.c:316-342,
+// without the per-pixel split).  Key = local second * n_segments + segment; the words of a board are already in time
+// order, so the list is a stable compaction: every valid pixel word (adr < npix, absolute second < exptime) in stream
+// order inside its key.  Two launches of one CTA per segment: per-key counts, then offsets + copy.
+constexpr int MERGE_MAX_SEC = 4;                       // end-of-second words a batch segment may hold (later words join the last key)
+struct MergeParams {
+    const uint64_t *words;
+    const int32_t *seg_len_dev, *seg_sec_dev;
+    int n_seg, npix_per_roach, exptime;
+    int32_t *cnt;                                      // [MERGE_MAX_SEC][n_seg]
+    uint64_t *out;
+    long long out_cap;
+    int32_t *offsets;                                  // [MERGE_MAX_SEC * n_seg + 1]
+};
+template <bool COPY>
+__global__ void __launch_bounds__(1024) merge_small_kernel(MergeParams p, const DecSeg *segs) {
+    __shared__ int s_eos[33], s_val[33];
+    __shared__ int s_base[MERGE_MAX_SEC], s_cnt[MERGE_MAX_SEC];
+    const int seg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const DecSeg sg = segs[seg];
+    const int len = max(0, min(sg.cap, p.seg_len_dev[seg]));
+    const uint64_t *w = p.words + sg.start;
+    const int sec0 = p.seg_sec_dev[seg];
+    const unsigned lt = (1u << lane) - 1u;
+    if (tid < MERGE_MAX_SEC) s_cnt[tid] = 0;
+    if (COPY && tid < MERGE_MAX_SEC) {                 // start of key (tid, seg): counts of all earlier keys
+        int b = 0;
+        for (int k = 0; k < tid * p.n_seg + seg; ++k) b += p.cnt[k];
+        s_base[tid] = b;
+    }
+    if (COPY && seg == 0) {                            // the offsets table (exclusive scan of the counts)
+        const int n_keys = MERGE_MAX_SEC * p.n_seg;
+        if (tid == 0) { int run = 0; for (int k = 0; k < n_keys; ++k) { p.offsets[k] = run; run += p.cnt[k]; } p.offsets[n_keys] = run; }
+    }
+    __syncthreads();
+    int ls_run = 0, val_run = 0;                       // end-of-second words / valid words before this chunk
+    int done_before[MERGE_MAX_SEC];                    // valid words of this segment in keys before ls (COPY)
+#pragma unroll
+    for (int l = 0; l < MERGE_MAX_SEC; ++l) {
+        int a = 0;
+        if (COPY) for (int q = 0; q < l; ++q) a += p.cnt[q * p.n_seg + seg];
+        done_before[l] = a;
+    }
+    for (int base = 0; base < len; base += 1024) {
+        const int i = base + tid;
+        const bool in = i < len;
+        const uint64_t x = in ? w[i] : 0ull;
+        const uint32_t adr = (uint32_t)(x >> 56);
+        const bool is_eos = in && adr == 255u;
+        const unsigned be = __ballot_sync(0xffffffffu, is_eos);
+        if (lane == 0) s_eos[warp] = __popc(be);
+        __syncthreads();
+        if (warp == 0) {
+            const int v = s_eos[lane];
+            int incl = v;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const int a = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += a; }
+            s_eos[lane] = incl - v;
+            if (lane == 31) s_eos[32] = incl;
+        }
+        __syncthreads();
+        const int ls_true = ls_run + s_eos[warp] + __popc(be & lt);
+        const int ls = min(ls_true, MERGE_MAX_SEC - 1);
+        const bool valid = in && !is_eos && (int)adr < p.npix_per_roach && sec0 + ls_true < p.exptime;
+        if (!COPY) {
+            if (valid) atomicAdd(&s_cnt[ls], 1);
+        } else {
+            const unsigned bv = __ballot_sync(0xffffffffu, valid);
+            if (lane == 0) s_val[warp] = __popc(bv);
+            __syncthreads();
+            if (warp == 0) {
+                const int v = s_val[lane];
+                int incl = v;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) { const int a = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += a; }
+                s_val[lane] = incl - v;
+                if (lane == 31) s_val[32] = incl;
+            }
+            __syncthreads();
+            if (valid) {
+                const int rank = val_run + s_val[warp] + __popc(bv & lt);       // valid words of the segment before this one
+                const long long pos = (long long)s_base[ls] + (rank - done_before[ls]);
+                if (pos < p.out_cap) p.out[pos] = x;
+            }
+            val_run += s_val[32];
+        }
+        ls_run += s_eos[32];
+        __syncthreads();
+    }
+    if (!COPY && tid < MERGE_MAX_SEC) p.cnt[tid * p.n_seg + seg] = s_cnt[tid];
+}
+
+// ------------------------------------------------------------------------------------------------
 // Per-(second, pixel) photon lists: the product PacketMaster writes every second (photons[r][adr][plist],
 // PacketMaster.c:371-380, write_sec_data :1012-1016).  Key = sec * n_pix + pixel, arrival order inside a key,
 // each key truncated to max_events - 1 entries (the cap quirk).  Built from the rows of the relative pass:
@@ -1457,6 +1551,47 @@ extern "C" int mkid_decode_words_dev(mkid_ctx *ctx, const uint64_t *words, int64
     for (int i = 0; i < n_segments; ++i) MKID_REQUIRE(ctx, seg_cap[i] > 0, "decode_words_dev: empty segment capacity");
     return decode_common(ctx, words, nullptr, n_words, seg_start, seg_cap, seg_roach, nullptr, nullptr, n_segments, cfg,
                          counts_raw, hist, nullptr, seg_len_dev, seg_sec_dev, seg_sec_out_dev);
+}
+
+extern "C" int mkid_merge_words_dev(mkid_ctx *ctx, const uint64_t *words, const int64_t *seg_start, const int64_t *seg_cap,
+                                    const int32_t *seg_len_dev, const int32_t *seg_sec_dev, int32_t n_segments,
+                                    const mkid_decode_cfg *cfg, uint64_t *list_words, int64_t list_cap, int32_t *list_offsets) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, words && seg_start && seg_cap && seg_len_dev && seg_sec_dev && cfg && list_words && list_offsets && list_cap > 0,
+                 "merge_words_dev: NULL argument");
+    MKID_REQUIRE(ctx, n_segments >= 1 && n_segments <= 1024, "merge_words_dev: 1..1024 segments");
+    MKID_REQUIRE(ctx, mkid_is_device_ptr(words) && mkid_is_device_ptr(seg_len_dev) && mkid_is_device_ptr(seg_sec_dev) &&
+                          mkid_is_device_ptr(list_words) && mkid_is_device_ptr(list_offsets),
+                 "merge_words_dev: words, lengths, second counters and outputs must be device memory");
+    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
+    // segment table + per-key counts in a private scratch slot (re-uploaded only when it changes)
+    std::vector<DecSeg> segs(n_segments);
+    for (int i = 0; i < n_segments; ++i) segs[i] = DecSeg{(long long)seg_start[i], (int)std::min<int64_t>(seg_cap[i], INT32_MAX), i};
+    const size_t tab_bytes = segs.size() * sizeof(DecSeg), cnt_bytes = (size_t)MERGE_MAX_SEC * n_segments * 4;
+    const size_t need = ((tab_bytes + 15) / 16) * 16 + cnt_bytes;
+    if (ctx->merge_bytes < need) {
+        if (ctx->merge_dev) { MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); MKID_CUDA(ctx, cudaFree(ctx->merge_dev)); ctx->merge_dev = nullptr; }
+        if (cudaMalloc(&ctx->merge_dev, need) != cudaSuccess) return mkid_fail(ctx, MKID_ENOMEM, "merge_words_dev: device allocation failed");
+        ctx->merge_bytes = need;
+        ctx->merge_host.clear();
+    }
+    void *scr = ctx->merge_dev;
+    std::vector<char> key((const char *)segs.data(), (const char *)segs.data() + tab_bytes);
+    if (key != ctx->merge_host) {                          // (re-uploaded only when the table changes: no host round trip per batch)
+        MKID_CUDA(ctx, cudaMemcpyAsync(scr, segs.data(), tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        ctx->merge_host = key;
+    }
+    MergeParams p;
+    p.words = words; p.seg_len_dev = seg_len_dev; p.seg_sec_dev = seg_sec_dev; p.n_seg = n_segments;
+    p.npix_per_roach = cfg->npix_per_roach; p.exptime = cfg->exptime;
+    p.cnt = (int32_t *)((char *)scr + ((tab_bytes + 15) / 16) * 16);
+    p.out = list_words; p.out_cap = list_cap; p.offsets = list_offsets;
+    merge_small_kernel<false><<<n_segments, 1024, 0, ctx->stream>>>(p, (const DecSeg *)scr);
+    MKID_CHECK_LAUNCH(ctx);
+    merge_small_kernel<true><<<n_segments, 1024, 0, ctx->stream>>>(p, (const DecSeg *)scr);
+    MKID_CHECK_LAUNCH(ctx);
+    return MKID_OK;
 }
 
 extern "C" int mkid_decode_lists(mkid_ctx *ctx, const uint64_t *words, int64_t n_words, const int64_t *seg_offset,

@@ -52,3 +52,52 @@ def reduce_products(tensors, group=None):
     for t in tensors:
         dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return tensors
+
+
+class ProductReducer:
+    """The one collective of the path through the C ABI (mkid_hist_allreduce / mkid_hist_reduce): an NCCL communicator
+    owned by the library, its unique id handed from rank 0 to the others through the existing torch.distributed group
+    (any backend) or through any callable `bcast(bytes_or_None) -> bytes`.  The reduce is queued on the context's own
+    stream: decode -> reduce -> next batch need no host synchronisation."""
+
+    def __init__(self, ctx, rank, world, bcast=None):
+        import ctypes
+        from . import _lib
+        self.ctx, self.rank, self.world = ctx, rank, world
+        self.comm = ctypes.c_void_p()
+        if world == 1:
+            return
+        uid = (ctypes.c_uint8 * 128)()
+        if rank == 0:
+            ctx._check(ctx.lib.mkid_nccl_unique_id(ctx.h, uid))
+        if bcast is None:
+            import torch
+            import torch.distributed as dist
+            dev = 'cuda' if dist.get_backend() == 'nccl' else 'cpu'
+            t = torch.tensor(list(uid), dtype=torch.uint8, device=dev)
+            dist.broadcast(t, 0)
+            data = bytes(t.cpu().tolist())
+        else:
+            data = bcast(bytes(uid) if rank == 0 else None)
+        uid = (ctypes.c_uint8 * 128).from_buffer_copy(data)
+        ctx._check(ctx.lib.mkid_nccl_init(ctx.h, uid, world, rank, ctypes.byref(self.comm)))
+
+    def allreduce(self, buf, n):
+        """In-place sum over all ranks of n uint32 values at device address `buf` (DeviceBuffer / tensor / int)."""
+        if self.world == 1:
+            return
+        from . import _lib
+        c = self.ctx
+        c._check(c.lib.mkid_hist_allreduce(c.h, self.comm, _lib.ptr(buf), int(n)))
+
+    def reduce(self, buf, n, root=0):
+        if self.world == 1:
+            return
+        from . import _lib
+        c = self.ctx
+        c._check(c.lib.mkid_hist_reduce(c.h, self.comm, _lib.ptr(buf), int(n), int(root)))
+
+    def close(self):
+        if self.comm:
+            self.ctx.lib.mkid_nccl_destroy(self.ctx.h, self.comm)
+            self.comm = None

@@ -361,3 +361,52 @@ def test_dashboard_make_image_matches_reference_run(ctx, golden_dir):
         assert db.vmax == float(g['dash_vmax_%d' % t]), t
         assert np.array_equal(np.array(db.redpix), g['dash_redpix_%d' % t]), t
     assert np.array_equal(db.skyrate, g['dash_skyrate'])
+
+
+def test_merge_words_dev_matches_numpy(ctx):
+    """Device-chained merged list of one batch (mkid_merge_words_dev): segments with end-of-second words, non-pixel
+    channels, junk beyond the device-side lengths, a carried second that runs into exptime."""
+    import ctypes
+    from mkids_sdr_b200 import _lib
+    from mkids_sdr_b200.decode import PhotonDecoder
+    R, npix, exptime = 5, 37, 6
+    rng = np.random.default_rng(3)
+    caps = np.array([9000, 3000, 1, 20000, 7000], dtype=np.int64)
+    lens = np.array([8100, 0, 1, 17777, 6999], dtype=np.int32)
+    sec0 = np.array([0, 2, 5, 4, 3], dtype=np.int32)
+    start = np.concatenate([[0], np.cumsum(caps)[:-1]]).astype(np.int64)
+    buf = rng.integers(0, 2 ** 63, int(caps.sum()), dtype=np.int64).astype(np.uint64)       # junk everywhere
+    segs = []
+    for i in range(R):
+        n = int(lens[i])
+        w = odec.pack_word(rng.integers(0, npix + 3, n), rng.integers(0, 4096, n), rng.integers(0, 4096, n),
+                           rng.integers(0, 4096, n), np.sort(rng.integers(0, 10 ** 6, n)))
+        if n > 100:
+            eos = np.sort(rng.choice(np.arange(10, n), 3 if i != 3 else 6, replace=False))   # segment 3: more than MERGE_MAX_SEC - 1
+            w[eos] = np.uint64(0xFFFFFFFFFFFFFFFF)
+        buf[start[i]:start[i] + n] = w
+        segs.append(w)
+    dec = PhotonDecoder(R, npix, exptime, ctx=ctx)
+    dw, dl, ds = ctx.to_device(buf), ctx.to_device(lens), ctx.to_device(sec0)
+    out = ctx.alloc(int(caps.sum()) * 8)
+    off = ctx.alloc((_lib.MERGE_MAX_SEC * R + 1) * 4)
+    ctx._check(ctx.lib.mkid_merge_words_dev(ctx.h, _lib.ptr(dw), _lib.ptr(start), _lib.ptr(caps), _lib.ptr(dl), _lib.ptr(ds), R,
+                                            ctypes.byref(dec.cfg), _lib.ptr(out), int(caps.sum()), _lib.ptr(off)))
+    ctx.sync()
+    offs = off.download(np.int32, _lib.MERGE_MAX_SEC * R + 1)
+    words = out.download(np.uint64, int(offs[-1]))
+    exp = []
+    exp_off = [0]
+    for ls in range(_lib.MERGE_MAX_SEC):
+        for i in range(R):
+            w = segs[i]
+            adr = (w >> np.uint64(56)).astype(np.int64)
+            is_eos = adr == 255
+            ls_true = np.cumsum(is_eos) - is_eos
+            key = np.minimum(ls_true, _lib.MERGE_MAX_SEC - 1)
+            ok = (~is_eos) & (adr < npix) & (sec0[i] + ls_true < exptime) & (key == ls)
+            exp.append(w[ok])
+            exp_off.append(exp_off[-1] + int(ok.sum()))
+    assert np.array_equal(offs, np.array(exp_off, dtype=np.int32))
+    assert np.array_equal(words, np.concatenate(exp))
+    assert offs[-1] > 20000
