@@ -233,6 +233,66 @@ class PhotonDecoder:
         return img
 
 
+def parse_beammap(beam_names, npix_per_roach):
+    """update_beammap_names (PacketMaster.c:880-904): the beammap holds one dataset name "/r<roach>/p<pixel>/" per image
+    position; pixel_adr = roach * NPIXELS_PER_ROACH + pixel (strtok on '/', then atoi past the leading letter: leading
+    digits only, 0 when there are none).  beam_names: [rows][cols] strings.  Returns int32 [rows][cols]."""
+    import re
+
+    def atoi(t):
+        m = re.match(r'\s*([+-]?\d+)', t)
+        return int(m.group(1)) if m else 0
+    names = np.asarray(beam_names, dtype=object)
+    out = np.zeros(names.shape, dtype=np.int32)
+    for idx, name in np.ndenumerate(names):
+        toks = [t for t in str(name).split('/') if t]              # strtok skips empty tokens
+        roach = atoi(toks[0][1:]) if len(toks) > 0 else 0
+        pixel = atoi(toks[1][1:]) if len(toks) > 1 else 0
+        out[idx] = roach * npix_per_roach + pixel
+    return out
+
+
+def write_quicklook_file(obs_filepath, image, sec):
+    """write_quicklook_image_v2 (PacketMaster.c:679-727): `<dir of obs>/bin/<obs root>_<sec>.txt`, one image row per line,
+    every value followed by a blank ("%d "); `bin/lock.<sec>` exists while the file is being written, which is what
+    the dashboard's check_files polls (ArconsDashboard.py:1217-1227).  image: uint16 [rows][cols].  Returns the path."""
+    import os
+    obs_dir, obs_name = os.path.split(str(obs_filepath))
+    root = obs_name.split('.')[0]                                   # sscanf "%[^.].h5"
+    bin_dir = os.path.join(obs_dir, 'bin')
+    os.makedirs(bin_dir, exist_ok=True)
+    path = os.path.join(bin_dir, '%s_%d.txt' % (root, sec))
+    lock = os.path.join(bin_dir, 'lock.%d' % sec)
+    open(lock, 'w').close()
+    img = np.asarray(image).astype(np.uint16)
+    with open(path, 'wb') as f:
+        for row in img:
+            f.write((''.join('%d ' % v for v in row) + '\n').encode())
+    os.remove(lock)
+    return path
+
+
+class QuickLookWriter:
+    """The per-second count images PacketMaster leaves for the dashboard (write_sec_data, PacketMaster.c:1024-1045): the
+    image of second s is written once EVERY roach stream has closed it, each second once, in order.  Call `flush` with
+    the decoder's per-roach second counters after feeding data."""
+
+    def __init__(self, decoder, pixel_adr, obs_filepath):
+        self.dec, self.obs_filepath = decoder, obs_filepath
+        self.pixel_adr = np.ascontiguousarray(pixel_adr, dtype=np.int32)
+        self.next_sec = 0
+        self.written = []
+
+    def flush(self, sec_per_roach=None):
+        sec = np.asarray(self.dec.sec if sec_per_roach is None else sec_per_roach)
+        ready = int(min(int(sec.min()), self.dec.exptime))
+        while self.next_sec < ready:
+            img = self.dec.quicklook_image(self.next_sec, self.pixel_adr)
+            self.written.append(write_quicklook_file(self.obs_filepath, img, self.next_sec))
+            self.next_sec += 1
+        return self.written
+
+
 class Dashboard:
     """Headless twin of the image part of ArconsDashboard (make_image, ArconsDashboard.py:633-723) fed straight from a
     PhotonDecoder: attributes image_time, int_time, sky_subtraction, skyrate, taking_sky, skytime, skycount,

@@ -1,20 +1,17 @@
 """Headless twin of the "channelizer" GUI's hot-path methods (class AppForm of
-DataReadout/ChannelizerControls/ROACH_Pulses.py): FIR / centre / bin / threshold loading and the
-photon read-out.  Same method names and attributes; `self.roach` is injectable.
+DataReadout/ChannelizerControls/ROACH_Pulses.py): FIR / centre / bin / threshold loading and the photon read-out.
+Same method names, attributes and register traffic as the reference; `self.roach` is injectable.  The register
+protocol lives in registers.py; the arithmetic is vectorised, the thresholds are derived on the GPU
+(mkid_thresholds_from_phase) and the photon words are unpacked on the GPU (mkid_unpack_fields).
 """
-import math
 import os
-import struct
 
 import numpy
 
+from . import _lib
 from . import decode as _decode
+from . import registers as _regs
 from .fake_roach import FakeRoach
-
-
-def _py2_round(x):
-    x = float(x)
-    return math.floor(x + 0.5) if x >= 0 else -math.floor(-x + 0.5)
 
 
 class PulsesForm:
@@ -28,7 +25,7 @@ class PulsesForm:
         self.dac_freqs = []                                  # textedit_DACfreqs (Hz)
         self.lo_freq = 0.0                                   # textbox_loFreq
         self.lutDir = './'                                   # textbox_lutDir
-        self.fir = [0.] * 26                                 # importFIRcoeffs :1088-1103
+        self.fir = [0.] * _regs.FIR_TAPS                     # importFIRcoeffs :1088-1103
         self.zeroChannels = [0] * 256
         self.customThresholds = numpy.array([360.0] * 256)   # 360.0 = "none" (:45)
         self.thresholds = numpy.array([0.] * 256)
@@ -37,112 +34,62 @@ class PulsesForm:
         self.scale_factor = 1.
         self.channel = 0                                     # textbox_channel
         self.seconds = 1                                     # textbox_seconds
+        self.Nsigma = 2.5                                    # (:216)
 
-    # ------------------------------------------------------------------ a6
+    # ------------------------------------------------------------------ a6  (ROACH_Pulses.py:59-111, 1088-1103)
     def importFIRcoeffs(self, path):
-        """ROACH_Pulses.py:1088-1103."""
         self.fir = list(numpy.loadtxt(path))
 
     def loadFIRcoeffs(self):
-        """ROACH_Pulses.py:59-111: 12-bit taps, pairs packed c[2n+1]<<12 | c[2n] into 13 registers
-        per channel; deleted and inactive channels get zero taps.  Sets self.fir_int."""
-        N_freqs = len(self.dac_freqs)
-        taps = 26
-        self.fir_int = [int(v) for v in numpy.array(self.fir) * (2 ** 11 - 1)]
-        for ch in range(N_freqs):
-            if self.zeroChannels[ch]:
-                lpf = numpy.array([0.] * taps) * (2 ** 11 - 1)
-            else:
-                lpf = numpy.array(self.fir) * (2 ** 11 - 1)
-            for n in range(taps // 2):
-                coeff0 = numpy.binary_repr(int(lpf[2 * n]), 12)
-                coeff1 = numpy.binary_repr(int(lpf[2 * n + 1]), 12)
-                coeffs = int(coeff1 + coeff0, 2)
-                coeffs_bin = struct.pack('>l', coeffs)
-                register_name = 'FIR_b' + str(2 * n) + 'b' + str(2 * n + 1)
-                self.roach.write(register_name, coeffs_bin)
-                self.roach.write_int('FIR_load_coeff', (ch << 1) + (1 << 0))
-                self.roach.write_int('FIR_load_coeff', (ch << 1) + (0 << 0))
-        lpf = numpy.array([0.] * taps)
-        for ch in range(N_freqs, 256):
-            for n in range(taps // 2):
-                coeffs = struct.pack('>h', int(lpf[2 * n + 1])) + struct.pack('>h', int(lpf[2 * n]))
-                register_name = 'FIR_b' + str(2 * n) + 'b' + str(2 * n + 1)
-                self.roach.write(register_name, coeffs)
-                self.roach.write_int('FIR_load_coeff', (ch << 1) + (1 << 0))
-                self.roach.write_int('FIR_load_coeff', (ch << 1) + (0 << 0))
+        """The 13 FIR registers of every channel: the quantised taps for the driven channels, zeros for deleted
+        (zeroChannels) and undriven ones.  Sets self.fir_int (the 26 integers the data path runs with)."""
+        n_driven = len(self.dac_freqs)
+        self.fir_int = [int(v) for v in _regs.fir_taps_int(self.fir)]
+        live = _regs.fir_register_words(self.fir_int)
+        dead = numpy.zeros_like(live)
+        for ch in range(_regs.N_CHANNELS):
+            zeroed = ch >= n_driven or self.zeroChannels[ch]
+            _regs.write_fir(self.roach, dead if zeroed else live, [ch])
 
-    # ------------------------------------------------------------------ a7
+    # ------------------------------------------------------------------ a7  (ROACH_Pulses.py:948-956)
     def loadIQcenters(self):
-        """ROACH_Pulses.py:948-956."""
-        self.centers_int = []
-        for ch in range(256):
-            I_c = int(self.iq_centers[ch].real / 2 ** 3)
-            Q_c = int(self.iq_centers[ch].imag / 2 ** 3)
-            self.centers_int.append((I_c, Q_c))
-            center = (I_c << 16) + (Q_c << 0)
-            self.roach.write_int('conv_phase_centers', center)
-            self.roach.write_int('conv_phase_load_centers', (ch << 1) + (1 << 0))
-            self.roach.write_int('conv_phase_load_centers', 0)
+        i_c, q_c, words = _regs.center_words(self.iq_centers)
+        self.centers_int = list(zip(i_c.tolist(), q_c.tolist()))
+        _regs.write_centers(self.roach, words)
 
-    # ------------------------------------------------------------------ a3
+    # ------------------------------------------------------------------ a3  (ROACH_Pulses.py:958-974)
     def select_bins(self, readout_freqs):
-        """ROACH_Pulses.py:958-974."""
-        fft_len = 2 ** 9
-        i = 0
-        residuals = []
-        self.fft_bins = []
-        for f in readout_freqs:
-            fft_bin = int(_py2_round(f * fft_len / self.sampleRate))
-            fft_freq = fft_bin * self.sampleRate / fft_len
-            freq_residual = _py2_round((f - fft_freq) / self.freqRes) * self.freqRes
-            residuals.append(freq_residual)
-            self.fft_bins.append(fft_bin)
-            self.roach.write_int('bins', fft_bin)
-            self.roach.write_int('load_bins', (i << 1) + (1 << 0))
-            self.roach.write_int('load_bins', (i << 1) + (0 << 0))
-            i = i + 1
-        return residuals
+        fft_bins, resid = _regs.coarse_fine(readout_freqs, self.sampleRate, self.freqRes)
+        self.fft_bins = fft_bins.tolist()
+        _regs.write_bins(self.roach, self.fft_bins)
+        return resid.tolist()
 
     def toggleDAC(self):
-        """ROACH_Pulses.py:927-946 without the sleeps."""
+        """ROACH_Pulses.py:927-946 (no sleeps: nothing here waits for hardware)."""
         if self.dacStatus == 'off':
-            self.roach.write_int('startDAC', 1)
-            while self.roach.read_int('DRAM_LUT_rd_valid') != 0:
-                self.roach.write_int('startDAC', 0)
-                self.roach.write_int('startDAC', 1)
+            _regs.dac_start(self.roach)
             self.dacStatus = 'on'
         else:
-            self.roach.write_int('startDAC', 0)
+            _regs.dac_stop(self.roach)
             self.dacStatus = 'off'
 
     def loadLUTs(self):
-        """ROACH_Pulses.py:976-1011: luts.dat -> dram_memory, centers.dat -> iq_centers, bins."""
+        """The hand-over from the set-up GUI (ROACH_Pulses.py:976-1011): luts.dat -> dram_memory, centers.dat -> centres,
+        coarse bins from the tone list, DAC restarted."""
         self.scale_factor = 1.
-        self.iq_centers = numpy.array([0. + 0j] * 256)
         if self.dacStatus == 'off':
-            self.roach.write_int('startDAC', 0)
+            _regs.dac_stop(self.roach)
         else:
             self.toggleDAC()
-        saveDir = str(self.lutDir)
-        f = open(os.path.join(saveDir, 'luts.dat'), 'rb')
-        binaryData = f.read()
-        f.close()
-        self.binaryData = binaryData
-        self.roach.write('dram_memory', binaryData)
-        x = numpy.atleast_2d(numpy.loadtxt(os.path.join(saveDir, 'centers.dat')))
-        N_freqs = len(x[:, 0])
-        for n in range(N_freqs):
-            self.iq_centers[n] = complex(x[n, 0], x[n, 1])
-        freqs = [float(v) for v in self.dac_freqs]
-        f_base = float(self.lo_freq)
-        for n in range(len(freqs)):
-            if freqs[n] < f_base:
-                freqs[n] = freqs[n] + 512e6
-        freqs_dds = [0 for j in range(256)]
-        for n in range(len(freqs)):
-            freqs_dds[n] = _py2_round((freqs[n] - f_base) / self.freqRes) * self.freqRes
-        self.freq_residuals = self.select_bins(freqs_dds)
+        with open(os.path.join(str(self.lutDir), 'luts.dat'), 'rb') as f:
+            self.binaryData = f.read()
+        self.roach.write('dram_memory', self.binaryData)
+        centres = numpy.atleast_2d(numpy.loadtxt(os.path.join(str(self.lutDir), 'centers.dat')))
+        self.iq_centers = numpy.zeros(256, dtype=complex)
+        self.iq_centers[:len(centres)] = centres[:, 0] + 1j * centres[:, 1]
+        tones = numpy.zeros(256)
+        tones[:len(self.dac_freqs)] = _regs.baseband_tones(self.dac_freqs, self.lo_freq, 512e6, self.freqRes, mirror=False)
+        self.freq_residuals = self.select_bins(tones.tolist())
         self.loadIQcenters()
         self.toggleDAC()
 
@@ -155,52 +102,51 @@ class PulsesForm:
         I_dds[1::2], I_dds[0::2] = a[:, 4], a[:, 5]
         return I_dds, Q_dds
 
-    # ------------------------------------------------------------------ a10
-    def loadThresholds(self, steps=10):
-        """ROACH_Pulses.py:211-299 without raw_input/pickle: per channel `steps` phase snapshots of
-        1024 words, histogram CDF, threshold = int(-2.5*|med - p5|) clamped at -25736."""
-        Nsigma = 2.5
-        N_freqs = len(self.dac_freqs)
-        self.thresholds, self.medians = numpy.array([0.] * N_freqs), numpy.array([0.] * N_freqs)
-        self.thresholds_raw = numpy.zeros(N_freqs, dtype=numpy.int64)
-        L = 2 ** 10
-        scale_to_angle = 360. / 2 ** 16 * 4 / numpy.pi
-        for ch in range(N_freqs):
-            bin_data_phase = b''
-            for n in range(steps):
-                self.roach.write_int('ch_we', ch)
-                self.roach.write_int('startSnap', 0)
-                self.roach.write_int('snapPhase_ctrl', 1)
-                self.roach.write_int('snapPhase_ctrl', 0)
-                self.roach.write_int('startSnap', 1)
-                bin_data_phase = bin_data_phase + self.roach.read('snapPhase_bram', 4 * L)
-            a = numpy.frombuffer(bin_data_phase, dtype='>i2').reshape(-1, 2)
-            phase = numpy.stack([a[:, 1], a[:, 0]], axis=1).reshape(-1).astype(numpy.int64)   # :251-253
-            threshold, med = self._threshold(phase, Nsigma)
-            self.thresholds[ch] = scale_to_angle * threshold
-            self.medians[ch] = scale_to_angle * med
-            if self.customThresholds[ch] != 360.0:
-                threshold = self.customThresholds[ch] / scale_to_angle
-                if threshold < -25736:
-                    threshold = -25736
-            self.thresholds_raw[ch] = int(threshold)
-            self.roach.write_int('capture_threshold', int(threshold))
-            self.roach.write_int('capture_load_thresh', (ch << 1) + (1 << 0))
-            self.roach.write_int('capture_load_thresh', (ch << 1) + (0 << 0))
+    # ------------------------------------------------------------------ a10  (ROACH_Pulses.py:211-353)
+    def _thresholds_gpu(self, phase_cols):
+        """phase_cols: int16 [n_samples][n_ch] raw Fix16_13 snapshots -> (threshold_raw int, median edge) per channel, by
+        the histogram-CDF rule of ROACH_Pulses.py:259-277 evaluated on the GPU (all channels in one launch)."""
+        from . import triggers
+        ctx = self.ctx or _lib.default_context()
+        n, n_ch = phase_cols.shape
+        dev = ctx.to_device(numpy.ascontiguousarray(phase_cols, dtype=numpy.int16))
+        thr, med, _ = triggers.thresholds_from_phase(dev, 1, n, n, n_ch=n_ch, Nsigma=self.Nsigma, ctx=ctx)
+        dev.free()
+        return thr[0], med[0]
 
-    @staticmethod
-    def _threshold(phase, Nsigma=2.5):
-        n, bins = numpy.histogram(phase, bins=100)
-        n = numpy.array(n, dtype='float32') / numpy.sum(n)
-        tot = numpy.zeros(len(bins))
-        for i in range(len(bins)):
-            tot[i] = numpy.sum(n[:i])
-        med = bins[(numpy.abs(tot - 0.5)).argmin()]
-        thresh = bins[(numpy.abs(tot - 0.05)).argmin()]
-        threshold = int(-Nsigma * abs(med - thresh))
-        if threshold < -25736:
-            threshold = -25736
-        return threshold, med
+    def _apply_threshold(self, ch, thr_raw, med_edge):
+        self.thresholds[ch] = _regs.PHASE_LSB_DEG * thr_raw
+        self.medians[ch] = _regs.PHASE_LSB_DEG * med_edge
+        value = thr_raw
+        if self.customThresholds[ch] != 360.0:
+            value = _regs.custom_threshold_raw(self.customThresholds[ch])
+        self.thresholds_raw[ch] = int(value)
+        _regs.write_threshold(self.roach, ch, int(value))
+
+    def loadThresholds(self, steps=10, batched=False):
+        """Per driven channel: `steps` phase snapshots, threshold = int(-Nsigma * |median - 5 % point|) of the 100-bin
+        histogram CDF, not below -pi; custom thresholds override.  batched=False keeps the reference's register order
+        (snapshots of a channel, then its threshold); batched=True takes all snapshots first and derives every
+        threshold in one kernel launch."""
+        n_driven = len(self.dac_freqs)
+        self.thresholds, self.medians = numpy.zeros(n_driven), numpy.zeros(n_driven)
+        self.thresholds_raw = numpy.zeros(n_driven, dtype=numpy.int64)
+        if batched:
+            cols = numpy.stack([_regs.snapshot_phase(self.roach, ch, steps) for ch in range(n_driven)], axis=1)
+            thr, med = self._thresholds_gpu(cols)
+            for ch in range(n_driven):
+                self._apply_threshold(ch, int(thr[ch]), float(med[ch]))
+            return
+        for ch in range(n_driven):
+            thr, med = self._thresholds_gpu(_regs.snapshot_phase(self.roach, ch, steps)[:, None])
+            self._apply_threshold(ch, int(thr[0]), float(med[0]))
+
+    def loadSingleThreshold(self, ch, steps=10):
+        """ROACH_Pulses.py:301-353: the same rule for one channel (self.thresholds / medians keep their length)."""
+        if not hasattr(self, 'thresholds_raw') or len(self.thresholds_raw) <= ch:
+            self.thresholds_raw = numpy.zeros(max(ch + 1, len(self.thresholds)), dtype=numpy.int64)
+        thr, med = self._thresholds_gpu(_regs.snapshot_phase(self.roach, ch, steps)[:, None])
+        self._apply_threshold(ch, int(thr[0]), float(med[0]))
 
     # ------------------------------------------------------------------ a14
     def readPulses(self, steps=None):

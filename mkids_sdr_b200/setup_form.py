@@ -1,23 +1,17 @@
 """Headless twin of the "templar" GUI's LUT path (class AppForm of
 DataReadout/ChannelizerControls/ROACH_Setup.py and its multi-tone variant ROACH_Setup_DAC.py).
 
-Same method names, argument order and attributes as the reference; Qt widgets become plain
-attributes, `self.roach` is injectable (FakeRoach by default) and the hot loops run on the GPU.
+Same method names, argument order, attributes and register traffic as the reference; Qt widgets become plain
+attributes, `self.roach` is injectable (FakeRoach by default).  The tone placement and the register protocol are the
+vectorised helpers of registers.py; the hot loops (comb, DDS tables, DRAM image) run on the GPU.
 """
-import math
 import os
-import struct
 
 import numpy
 
 from . import lut as _lut
+from . import registers as _regs
 from .fake_roach import FakeRoach
-
-
-def _py2_round(x):
-    """Python-2 round(): half away from zero (ROACH_Setup.py:498,517,540,542 were written for it)."""
-    x = float(x)
-    return math.floor(x + 0.5) if x >= 0 else -math.floor(-x + 0.5)
 
 
 class SetupForm:
@@ -70,121 +64,106 @@ class SetupForm:
             self.last_scale_factor = self.scale_factor
         return I[0].astype(numpy.int64), Q[0].astype(numpy.int64)
 
-    # ------------------------------------------------------------------ a2
+    # ------------------------------------------------------------------ a2  (ROACH_Setup.py:477-504, ROACH_Setup_DAC.py:457-483)
     def define_DAC_LUT(self):
-        f_base = float(self.lo_freq)
-        freqs = [float(f) for f in self.dac_freqs]
-        # both GUIs (ROACH_Setup.py:484-495, ROACH_Setup_DAC.py:464-475): mirror about LO, +fs if below
-        freqs = [f_base + (f_base - f) for f in freqs]
-        freqs = [f + self.sampleRate if f < f_base else f for f in freqs]
-        self.freqs_dac = [_py2_round((f - f_base) / self.freqRes) * self.freqRes for f in freqs]
-        atten_min = numpy.asarray(self.attens, dtype=float).min()
-        amplitudes = [10 ** (+(atten_min - a) / 20.) for a in numpy.asarray(self.attens, dtype=float)]
+        """DAC comb: tones mirrored about the LO onto the freqRes grid, amplitudes from the attenuations relative to
+        the smallest one, comb synthesised by freqCombLUT('yes', ...)."""
+        self.freqs_dac = _regs.baseband_tones(self.dac_freqs, self.lo_freq, self.sampleRate, self.freqRes, mirror=True).tolist()
+        attens = numpy.asarray(self.attens, dtype=float)
+        loudest = attens.min()
+        amplitudes = [10 ** (+(loudest - a) / 20.) for a in attens]
         self.I_dac, self.Q_dac = self.freqCombLUT('yes', self.freqs_dac, self.sampleRate, self.freqRes, amplitudes)
 
-    # ------------------------------------------------------------------ a3
+    # ------------------------------------------------------------------ a3  (ROACH_Setup.py:534-550)
     def select_bins(self, readout_freqs):
-        """ROACH_Setup.py:534-550: fft bin + residual per channel, three register writes each."""
-        fft_len = 2 ** 9
-        i = 0
-        residuals = []
-        self.fft_bins = []
-        for f in readout_freqs:
-            fft_bin = int(_py2_round(f * fft_len / self.sampleRate))
-            fft_freq = fft_bin * self.sampleRate / fft_len
-            freq_residual = _py2_round((f - fft_freq) / self.freqRes) * self.freqRes
-            residuals.append(freq_residual)
-            self.fft_bins.append(fft_bin)
-            self.roach.write_int('bins', fft_bin)
-            self.roach.write_int('load_bins', (i << 1) + (1 << 0))
-            self.roach.write_int('load_bins', (i << 1) + (0 << 0))
-            i = i + 1
-        return residuals
+        """Coarse fs/512 bin + residual per channel; the bins go to the firmware (three register writes each)."""
+        fft_bins, resid = _regs.coarse_fine(readout_freqs, self.sampleRate, self.freqRes)
+        self.fft_bins = fft_bins.tolist()
+        _regs.write_bins(self.roach, self.fft_bins)
+        return resid.tolist()
 
-    # ------------------------------------------------------------------ a4
+    # ------------------------------------------------------------------ a4  (ROACH_Setup.py:506-532)
     def define_DDS_LUT(self, phase=[0.] * 256):
-        """ROACH_Setup.py:506-532 (256 tables on the GPU in one launch)."""
-        ch_shift = 154
-        freqs = [float(f) for f in self.dac_freqs]
-        f_base = float(self.lo_freq)
-        for n in range(len(freqs)):
-            if freqs[n] < f_base:
-                freqs[n] = freqs[n] + self.sampleRate
-        freqs_dds = [0 for j in range(256)]
-        for n in range(len(freqs)):
-            freqs_dds[n] = _py2_round((freqs[n] - f_base) / self.freqRes) * self.freqRes
-        freq_residuals = self.select_bins(freqs_dds)
-        self.freq_residuals = freq_residuals
-        L = int(self.sampleRate / self.freqRes)
-        I, Q, sc = _lut.dds_lut([freq_residuals], [list(phase[:256])], self.sampleRate, L, ch_shift, self.offset,
+        """256 fine-mixer tables (residual tone of every channel at 2 MS/s, start phase `phase[m]`), interleaved with
+        the channel lag of 154; one GPU launch."""
+        tones = numpy.zeros(_regs.N_CHANNELS)
+        tones[:len(self.dac_freqs)] = _regs.baseband_tones(self.dac_freqs, self.lo_freq, self.sampleRate, self.freqRes,
+                                                           mirror=False)
+        self.freq_residuals = self.select_bins(tones.tolist())
+        n_lut = int(self.sampleRate / self.freqRes)
+        I, Q, sc = _lut.dds_lut([self.freq_residuals], [list(phase[:256])], self.sampleRate, n_lut, 154, self.offset,
                                 ctx=self.ctx)
         self.I_dds, self.Q_dds = I[0].astype(numpy.int64), Q[0].astype(numpy.int64)
         self.dds_scales = sc[0]
 
     def define_LUTs(self):
         """ROACH_Setup.py:395-414."""
-        self.iq_centers = numpy.array([0. + 0j] * 256)
+        self.iq_centers = numpy.zeros(256, dtype=complex)
         self.define_DAC_LUT()
         self.define_DDS_LUT()
         self.write_LUTs()
 
-    # ------------------------------------------------------------------ a5
+    # ------------------------------------------------------------------ a5  (ROACH_Setup.py:552-578)
     def write_LUTs(self):
-        """ROACH_Setup.py:552-578: dac.npy.npz, DRAM image to 'dram_memory', luts.dat."""
+        """dac.npy.npz, the 8*N-byte DRAM image to 'dram_memory' (packed on the GPU) and to luts.dat."""
         if self.dacStatus == 'off':
-            self.roach.write_int('startDAC', 0)
+            _regs.dac_stop(self.roach)
         else:
             self.toggleDAC()
         if self.save_npz:
             numpy.savez(os.path.join(self.LUT_saveDir, 'dac.npy'), I_dac=self.I_dac, Q_dac=self.Q_dac, I_dds=self.I_dds,
                         Q_dds=self.Q_dds)
-        binaryData = _lut.pack_dram(self.I_dac, self.Q_dac, self.I_dds, self.Q_dds, ctx=self.ctx)
-        self.binaryData = binaryData
-        self.roach.write('dram_memory', binaryData)
-        f = open(os.path.join(self.LUT_saveDir, 'luts.dat'), 'wb')
-        f.write(binaryData)
-        f.close()
+        self.binaryData = _lut.pack_dram(self.I_dac, self.Q_dac, self.I_dds, self.Q_dds, ctx=self.ctx)
+        self.roach.write('dram_memory', self.binaryData)
+        with open(os.path.join(self.LUT_saveDir, 'luts.dat'), 'wb') as f:
+            f.write(self.binaryData)
 
     def toggleDAC(self):
-        """ROACH_Setup.py:881-914 without the sleeps."""
+        """ROACH_Setup.py:881-914 (no sleeps)."""
         if self.dacStatus == 'off':
-            self.roach.write_int('startDAC', 1)
-            while self.roach.read_int('DRAM_LUT_rd_valid') != 0:
-                self.roach.write_int('startDAC', 0)
-                self.roach.write_int('startDAC', 1)
+            _regs.dac_start(self.roach)
             self.dacStatus = 'on'
         else:
-            self.roach.write_int('startDAC', 0)
+            _regs.dac_stop(self.roach)
             self.dacStatus = 'off'
 
-    # ------------------------------------------------------------------ a7
+    # ------------------------------------------------------------------ a7  (ROACH_Setup.py:595-625)
     def findIQcenters(self, I, Q):
-        """ROACH_Setup.py:621-625."""
-        I_0 = (I.max() + I.min()) / 2.
-        Q_0 = (Q.max() + Q.min()) / 2.
-        return complex(I_0, Q_0)
+        """Centre of an IQ loop: midpoint of the extreme values of each component."""
+        return complex((I.max() + I.min()) / 2., (Q.max() + Q.min()) / 2.)
 
     def loadIQcenters(self):
-        """ROACH_Setup.py:595-606, plus centers.dat (:611)."""
-        for ch in range(256):
-            I_c = int(self.iq_centers[ch].real / 2 ** 3)
-            Q_c = int(self.iq_centers[ch].imag / 2 ** 3)
-            center = (I_c << 16) + (Q_c << 0)
-            self.roach.write_int('conv_phase_centers', center)
-            self.roach.write_int('conv_phase_load_centers', (ch << 1) + (1 << 0))
-            self.roach.write_int('conv_phase_load_centers', 0)
+        """Centres to the firmware and to centers.dat (:611)."""
+        _regs.write_centers(self.roach, _regs.center_words(self.iq_centers)[2])
         numpy.savetxt(os.path.join(self.LUT_saveDir, 'centers.dat'),
                       numpy.column_stack([self.iq_centers.real, self.iq_centers.imag]))
 
+    def rotateLoopsReady(self):
+        """ROACH_Setup.py:645-671 (without the LO sweep that follows it in the GUI): read the averaged IQ point of every
+        channel, rotate the loops, restart the DAC that write_LUTs stopped."""
+        I_avg, Q_avg = _regs.snapshot_avg_iq(self.roach)
+        phase = self.rotateLoops(I_avg, Q_avg)
+        self.toggleDAC()
+        return phase
+
+    def rotateLoops(self, I_avg, Q_avg):
+        """The DDS start phase of every driven channel becomes the angle of its averaged IQ point about its centre
+        (arctan2(Q - Qc, I - Ic), ROACH_Setup.py:661-664); the DDS tables and the DRAM image are rebuilt."""
+        n = len(self.dac_freqs)
+        c = numpy.asarray(self.iq_centers[:n])
+        phase = [0.] * 256
+        phase[:n] = numpy.arctan2(numpy.asarray(Q_avg, float)[:n] - c.imag, numpy.asarray(I_avg, float)[:n] - c.real).tolist()
+        self.define_DDS_LUT(phase)
+        self.write_LUTs()
+        return phase
+
     def loadFreqsAttens(self, freqFile, f_offset=0.0):
-        """Freq-file format of ROACH_Setup_DAC.py:892-927: row 0 = previous scale factor, rows =
-        f_GHz I_c Q_c atten."""
+        """Frequency file of ROACH_Setup_DAC.py:892-927: row 0 = previous scale factor, then f_GHz I_c Q_c atten."""
         x = numpy.atleast_2d(numpy.loadtxt(freqFile))
         self.previous_scale_factor = x[0, 0]
-        N_freqs = len(x[1:, 0])
-        self.dac_freqs = [l * 1e9 + f_offset for l in x[1:, 0]]
-        self.iq_centers = numpy.array([0. + 0j] * 256)
-        for n in range(N_freqs):
-            self.iq_centers[n] = complex(x[n + 1, 1], x[n + 1, 2])
-        self.attens = x[1:, 3]
-        self.minimumAttenuation = numpy.array(x[1:, 3]).min()
+        body = x[1:]
+        self.dac_freqs = [f_ghz * 1e9 + f_offset for f_ghz in body[:, 0]]
+        self.iq_centers = numpy.zeros(256, dtype=complex)
+        self.iq_centers[:len(body)] = body[:, 1] + 1j * body[:, 2]
+        self.attens = body[:, 3]
+        self.minimumAttenuation = numpy.array(body[:, 3]).min()

@@ -1,4 +1,6 @@
 """GPU parity: K6 decode / binning / histogram through the C ABI vs the oracle (bit-exact)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -410,3 +412,36 @@ def test_merge_words_dev_matches_numpy(ctx):
     assert np.array_equal(offs, np.array(exp_off, dtype=np.int32))
     assert np.array_equal(words, np.concatenate(exp))
     assert offs[-1] > 20000
+
+
+def test_quicklook_files_and_beammap_parse(ctx, tmp_path):
+    """The per-second `<obs>_<sec>.txt` images PacketMaster leaves for the dashboard (PacketMaster.c:679-727, 1024-1045)
+    and the beammap "/r%d/p%d/" parse (:880-904); the dashboard reads the file with numpy.loadtxt
+    (ArconsDashboard.py:635)."""
+    from mkids_sdr_b200 import synth
+    from mkids_sdr_b200.decode import PhotonDecoder, QuickLookWriter, parse_beammap
+    R, npix, secs = 4, 253, 3
+    rows, cols = 23, 44                                                  # 1012 = 4 x 253 pixels
+    rng = np.random.default_rng(8)
+    perm = rng.permutation(R * npix)
+    names = np.array(['/r%d/p%d/' % (a // npix, a % npix) for a in perm], dtype=object).reshape(rows, cols)
+    adr = parse_beammap(names, npix)
+    assert np.array_equal(adr.reshape(-1), perm)
+    assert parse_beammap([['/r2/p17/t1319000000', 'r1/p5', '/rX/p3/']], npix).tolist() == [[2 * npix + 17, npix + 5, 3]]
+    streams, _ = synth.photon_streams(300000, R, npix, secs, seed=4, n_hot=2, hot_rate=3000)
+    dec = PhotonDecoder(R, npix, secs, ctx=ctx)
+    ql = QuickLookWriter(dec, adr, str(tmp_path / 'obs_20110726-114310.h5'))
+    # roach 0 lags one second behind: only the seconds every roach has closed may be written
+    assert ql.flush(np.array([1, 2, 2, 2])) == []                        # nothing decoded yet: dec.sec is what counts
+    dec.feed_streams(streams)
+    files = ql.flush(np.array([2, 3, 3, 3]))
+    assert [os.path.basename(f) for f in files] == ['obs_20110726-114310_0.txt', 'obs_20110726-114310_1.txt']
+    files = ql.flush()
+    assert len(files) == 3 and not any(n.startswith('lock.') for n in os.listdir(tmp_path / 'bin'))
+    ref = odec.packetmaster_bin(streams, npix, secs)
+    for s, f in enumerate(files):
+        img = np.loadtxt(f)
+        assert img.shape == (rows, cols)
+        assert np.array_equal(img, odec.quicklook_image(ref['counts'][s], adr))
+        assert open(f).read().split('\n')[0].endswith(' ')               # "%d " after every value
+    assert ref['counts'].max() == 2499

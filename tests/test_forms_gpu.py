@@ -179,3 +179,67 @@ def test_pulses_form_matches_reference_run(ctx, golden_dir):
     assert np.array_equal(pf2.hgBase, g['rp_hgBase']) and np.array_equal(pf2.hgPeak, g['rp_hgPeak'])
     assert np.array_equal(pf2.hgPeakSubBase, g['rp_hgPeakSubBase'])
     assert np.array_equal(pf2.peak_deg, g['rp_peaksCh_deg']) and np.array_equal(pf2.times, g['rp_timesCh'])
+
+
+def test_thresholds_batched_and_single_equal_the_reference_order(ctx, golden_dir):
+    """loadThresholds(batched=True) (all snapshots first, one kernel launch) and loadSingleThreshold
+    (ROACH_Pulses.py:301-353) give the thresholds of the reference-run golden data; custom thresholds override."""
+    from mkids_sdr_b200.pulses_form import PulsesForm
+    g = np.load(os.path.join(golden_dir, 'refrun_golden.npz'))
+
+    def snaps_of(ch):
+        raw = g['thr_raw_phase'][ch].reshape(10, 2048)
+        out = []
+        for st in range(10):
+            words = np.empty((1024, 2), dtype='>i2')
+            words[:, 1] = raw[st, 0::2]; words[:, 0] = raw[st, 1::2]
+            out.append(words.tobytes())
+        return out
+
+    class Roach:
+        def __init__(self, snaps): self.snaps, self.caps, self.log = list(snaps), [], []
+        def write_int(self, name, v, *a):
+            self.log.append((name, int(v)))
+            if name == 'capture_threshold': self.caps.append(int(v))
+        def read(self, name, size): return self.snaps.pop(0)
+    pf = PulsesForm(roach=Roach(snaps_of(0) + snaps_of(1)), ctx=ctx)
+    pf.dac_freqs = [1.0, 2.0]
+    pf.loadThresholds(steps=10, batched=True)
+    assert pf.roach.caps == [int(v) for v in g['thr_capture_threshold']]
+    assert np.array_equal(pf.thresholds, g['thr_thresholds_deg']) and np.array_equal(pf.medians, g['thr_medians_deg'])
+    # single channel, with and without a custom threshold
+    pf.roach = Roach(snaps_of(1) + snaps_of(1))
+    pf.loadSingleThreshold(1)
+    assert pf.roach.caps == [int(g['thr_capture_threshold'][1])]
+    assert pf.roach.log[-2:] == [('capture_load_thresh', 3), ('capture_load_thresh', 2)]
+    pf.customThresholds[1] = -30.0
+    pf.loadSingleThreshold(1)
+    assert pf.roach.caps[-1] == int(-30.0 / control.SCALE_TO_ANGLE)
+    assert pf.thresholds[1] == g['thr_thresholds_deg'][1]                     # the derived value is still reported
+
+
+def test_rotate_loops_ready(ctx):
+    """rotateLoopsReady (ROACH_Setup.py:645-671): phases = arctan2(Q - Qc, I - Ic) of the averaged IQ read-out, DDS tables
+    rebuilt with them (== the oracle's define_dds_lut), DRAM image rewritten, DAC restarted."""
+    from mkids_sdr_b200.setup_form import SetupForm
+    N = 2 ** 12
+    sf = SetupForm(N_lut_entries=N, multi_tone=True, ctx=ctx)
+    sf.save_npz = False
+    sf.LUT_saveDir = os.environ.get('TMPDIR', '/tmp')
+    sf.lo_freq = 5.0e9
+    rng = np.random.default_rng(5)
+    k = np.sort(rng.choice(np.arange(-N // 2 + 8, N // 2 - 8), 6, replace=False))
+    sf.dac_freqs = [sf.lo_freq + float(v) * FS / N for v in k]
+    sf.attens = np.zeros(6)
+    sf.iq_centers = np.zeros(256, dtype=complex)
+    sf.iq_centers[:6] = rng.integers(-50, 50, 6) + 1j * rng.integers(-50, 50, 6)
+    sf.define_LUTs()
+    I_avg = rng.integers(-10 ** 5, 10 ** 5, 256); Q_avg = rng.integers(-10 ** 5, 10 ** 5, 256)
+    sf.roach.mem['avgIQ_bram'] = np.concatenate([I_avg, Q_avg]).astype('>i4').tobytes()
+    phase = sf.rotateLoopsReady()
+    exp = np.arctan2(Q_avg[:6] - sf.iq_centers[:6].imag, I_avg[:6] - sf.iq_centers[:6].real)
+    assert np.array_equal(np.array(phase[:6]), exp) and phase[6:] == [0.] * 250
+    Io, Qo, _ = olut.define_dds_lut(sf.freq_residuals, FS, FS / N, phase)
+    assert np.array_equal(sf.I_dds, Io) and np.array_equal(sf.Q_dds, Qo)
+    assert sf.dacStatus == 'on' and sf.roach.writes('startDAC')[-1] == 1
+    assert sf.binaryData == olut.pack_dram(sf.I_dac, sf.Q_dac, sf.I_dds, sf.Q_dds)
