@@ -431,9 +431,9 @@ def test_quicklook_files_and_beammap_parse(ctx, tmp_path):
     streams, _ = synth.photon_streams(300000, R, npix, secs, seed=4, n_hot=2, hot_rate=3000)
     dec = PhotonDecoder(R, npix, secs, ctx=ctx)
     ql = QuickLookWriter(dec, adr, str(tmp_path / 'obs_20110726-114310.h5'))
-    # roach 0 lags one second behind: only the seconds every roach has closed may be written
-    assert ql.flush(np.array([1, 2, 2, 2])) == []                        # nothing decoded yet: dec.sec is what counts
     dec.feed_streams(streams)
+    # roach 0 lags behind: only the seconds EVERY roach has closed may be written
+    assert ql.flush(np.array([0, 2, 2, 2])) == []
     files = ql.flush(np.array([2, 3, 3, 3]))
     assert [os.path.basename(f) for f in files] == ['obs_20110726-114310_0.txt', 'obs_20110726-114310_1.txt']
     files = ql.flush()
