@@ -265,6 +265,10 @@ int  mkid_chan_kernel_ms_sum(mkid_ctx *ctx, mkid_chan *ch, int32_t last_n, float
 /* device pointer to the int32 [n_boards] word counts of the last mkid_chan_process call (asynchronous chaining into
  * mkid_decode_words_dev; valid until the channelizer is destroyed) */
 int  mkid_chan_n_words_dev(mkid_ctx *ctx, mkid_chan *ch, const int32_t **out);
+/* Asynchronous calls (n_words == NULL) cannot report a word buffer that was too small: a sticky device flag records it.
+ * *flag != 0: some call since the last clear produced more words than words_cap for a board (the surplus was dropped,
+ * the streaming state stayed consistent).  Synchronises. */
+int  mkid_chan_overflowed(mkid_ctx *ctx, mkid_chan *ch, int32_t *flag, int32_t clear);
 int  mkid_chan_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase, int64_t rows, int64_t t_abs0,
                       int64_t *t_next, uint64_t *words, int64_t words_cap, int32_t *n_words);
 /* synthetic ADC stream for tests and benchmarks (replaces the ROACH ADC): per board a comb of

@@ -59,6 +59,7 @@ _SIGNATURES = {
     'mkid_sync': (c_int32, [c_void_p]),
     'mkid_stream': (c_void_p, [c_void_p]),
     'mkid_merge_words_dev': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
+    'mkid_chan_overflowed': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32]),
     'mkid_wait_stream': (c_int32, [c_void_p, c_void_p]),
     'mkid_stream_wait_ctx': (c_int32, [c_void_p, c_void_p]),
     'mkid_nccl_version': (c_int32, [c_void_p, c_void_p]),

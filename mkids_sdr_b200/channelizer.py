@@ -86,9 +86,10 @@ class Channelizer:
             words = words_out if words_out is not None else np.empty((self.n_boards, cap), dtype=np.uint64)
             n_words = np.zeros(self.n_boards, dtype=np.int32)
         phase = np.empty((self.n_boards, T, N_CH), dtype=np.int16) if want_phase else None
-        c._check(c.lib.mkid_chan_process(c.h, self.h, _lib.ptr(iq), int(n), 1 if detect else 0, _lib.ptr(words), cap,
-                                         _lib.ptr(n_words), _lib.ptr(phase)))
-        self.t_consumed += T
+        rc = c.lib.mkid_chan_process(c.h, self.h, _lib.ptr(iq), int(n), 1 if detect else 0, _lib.ptr(words), cap,
+                                     _lib.ptr(n_words), _lib.ptr(phase))
+        self.t_consumed += T if rc in (0, _lib.MKID_EINVAL) and n % 2048 == 0 else 0      # (a too small word buffer still consumes the call)
+        c._check(rc)
         if detect and words_out is None:
             words = [words[b, :n_words[b]].copy() for b in range(self.n_boards)]
         elif detect:
@@ -118,6 +119,14 @@ class Channelizer:
         c._check(c.lib.mkid_memcpy(c.h, _lib.ptr(nw), self.n_words_dev(), nw.nbytes))
         c.sync()
         return nw
+
+    def overflowed(self, clear=True):
+        """True if some process call since the last clear produced more words than its word buffer could hold (the
+        only way an asynchronous call can report it).  Synchronises."""
+        flag = ctypes.c_int32()
+        c = self.ctx
+        c._check(c.lib.mkid_chan_overflowed(c.h, self.h, ctypes.byref(flag), 1 if clear else 0))
+        return bool(flag.value)
 
     def kernel_ms_sum(self, last_n):
         """Summed device time of the channelize kernel (K4) over the last `last_n` (<= 64) process calls."""

@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const uint32_t *__restrict
 
 // K5s: per board, add the end-of-second events and turn per-window counts into offsets.
 __global__ void __launch_bounds__(256) scan_kernel(uint32_t *win_cnt, int n_win, int64_t r_lo, int64_t r_hi,
-                                                   int64_t t_abs0, int Lw, int32_t *n_words) {
+                                                   int64_t t_abs0, int Lw, int32_t *n_words, int64_t words_cap, int32_t *overflow) {
     __shared__ uint32_t s_part[256];
     const int board = blockIdx.x, tid = threadIdx.x;
     uint32_t *wc = win_cnt + (size_t)board * (n_win + 1);
@@ -652,6 +652,7 @@ __global__ void __launch_bounds__(256) scan_kernel(uint32_t *win_cnt, int n_win,
         uint32_t run = 0;
         for (int i = 0; i < 256; ++i) { uint32_t v = s_part[i]; s_part[i] = run; run += v; }
         n_words[board] = (int32_t)run;
+        if ((int64_t)run > words_cap) atomicOr(overflow, 1);          // sticky: the emit kernels drop the words beyond the capacity
     }
     __syncthreads();
     uint32_t run = s_part[tid];
@@ -984,7 +985,7 @@ int run_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase_dev, int64_t r
                                                              d.t_next, ch->acc, ch->win_cnt);
     MKID_CHECK_LAUNCH(ctx);
     g_timer.mark(ctx->stream, "resolve");
-    scan_kernel<<<B, 256, 0, ctx->stream>>>(ch->win_cnt, n_win, r_lo, r_hi, t_abs0, d.Lw, ch->n_words_dev);
+    scan_kernel<<<B, 256, 0, ctx->stream>>>(ch->win_cnt, n_win, r_lo, r_hi, t_abs0, d.Lw, ch->n_words_dev, words_cap, ch->n_words_dev + B);
     MKID_CHECK_LAUNCH(ctx);
     g_timer.mark(ctx->stream, "scan");
     if (d.M >= 1 && d.M <= 32 && d.W >= 1 && d.W <= 32)
@@ -1037,7 +1038,7 @@ extern "C" int mkid_chan_create(mkid_ctx *ctx, const mkid_chan_params *prm, mkid
     bad |= A((void **)&d.thr, (size_t)B * NCH * 4);
     bad |= A((void **)&d.hist, (size_t)B * (d.H + 2048) * 4);
     bad |= A((void **)&d.t_next, (size_t)B * NCH * 8);
-    bad |= A((void **)&ch->n_words_dev, (size_t)B * 4);
+    bad |= A((void **)&ch->n_words_dev, (size_t)(B + 1) * 4);          // [B] word counts + the sticky overflow flag
     if (bad) { mkid_chan_destroy(ctx, ch); return mkid_fail(ctx, MKID_ENOMEM, "chan_create: device allocation failed"); }
     // default window (Hamming-windowed sinc, sum 1, float32) and twiddles, computed in double on the host
     std::vector<float> h(WIN);
@@ -1158,6 +1159,7 @@ extern "C" int mkid_chan_reset(mkid_ctx *ctx, mkid_chan *ch) {
     ChanDev &d = ch->d;
     MKID_CUDA(ctx, cudaMemsetAsync(d.hist, 0, (size_t)d.n_boards * (d.H + 2048) * 4, ctx->stream));
     MKID_CUDA(ctx, cudaMemsetAsync(d.t_next, 0, (size_t)d.n_boards * NCH * 8, ctx->stream));
+    MKID_CUDA(ctx, cudaMemsetAsync(ch->n_words_dev, 0, (size_t)(d.n_boards + 1) * 4, ctx->stream));
     ch->t_consumed = 0;
     return MKID_OK;
 }
@@ -1244,6 +1246,7 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
                                            (size_t)T * NCH * 2, cudaMemcpyDefault, ctx->stream));
     }
     const int64_t t_abs0 = ch->t_consumed - PRE_ROWS;
+    int64_t overflow_need = 0;
     if (detect) {
         uint64_t *wdev;
         if (mkid_is_device_ptr(words)) wdev = words;
@@ -1268,8 +1271,7 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
                                                    ctx->stream));
             MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         }
-        if (mx > words_cap) return mkid_fail(ctx, MKID_EINVAL, "word buffer too small: need %lld per board, have %lld",
-                                             (long long)mx, (long long)words_cap);
+        overflow_need = mx > words_cap ? mx : 0;
         }
     }
     // history <- last H samples of this call (n >= H)
@@ -1277,6 +1279,10 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     MKID_CHECK_LAUNCH(ctx);
     ch->t_consumed += T;
     if (!mkid_is_device_ptr(iq) || phase_out) MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    // reported only now: the streaming state (hold-off times, input history, time) is that of a completed call, the
+    // words beyond the capacity are lost
+    if (overflow_need) return mkid_fail(ctx, MKID_EINVAL, "word buffer too small: need %lld per board, have %lld (the call completed, "
+                                        "the words beyond the capacity are lost)", (long long)overflow_need, (long long)words_cap);
     return MKID_OK;
 }
 
@@ -1302,6 +1308,15 @@ extern "C" int mkid_chan_kernel_ms_sum(mkid_ctx *ctx, mkid_chan *ch, int32_t las
         sum += ms;
     }
     *ms_sum = sum;
+    return MKID_OK;
+}
+
+extern "C" int mkid_chan_overflowed(mkid_ctx *ctx, mkid_chan *ch, int32_t *flag, int32_t clear) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, ch && flag, "chan_overflowed: NULL");
+    MKID_CUDA(ctx, cudaMemcpyAsync(flag, ch->n_words_dev + ch->d.n_boards, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (clear) MKID_CUDA(ctx, cudaMemsetAsync(ch->n_words_dev + ch->d.n_boards, 0, 4, ctx->stream));
+    MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return MKID_OK;
 }
 

@@ -112,3 +112,32 @@ def test_full_chain_against_float64_oracle(ctx):
     assert r['only'] <= 0.005 * r['n_ref'], (r['only'], r['n_ref'])         # measured: see the printed line / DESIGN.md
     assert r['word_diff'] <= 0.005 * r['common'], (r['word_diff'], r['common'])
     ch.close()
+
+
+def test_word_buffer_overflow_keeps_the_stream_consistent(ctx):
+    """A word buffer that is too small is an error, but the call completes: hold-off times, input history and time are
+    those of a finished call, so the NEXT call gives exactly what it gives after an undisturbed one; asynchronous calls
+    report it through the sticky flag (mkid_chan_overflowed)."""
+    from mkids_sdr_b200 import _lib
+    cfg, ks = board_config(n_tones=16, seed=5, L=100, thr=-2200)
+    n = 2 ** 19
+    iq = _synth(ctx, ks[None, :], 2 * n, cfg.N_lut, seed=11, pulse_rate=5000.)
+    a, b = np.ascontiguousarray(iq[:, :n]), np.ascontiguousarray(iq[:, n:])
+    ch = make_gpu_channelizer([cfg], ctx)
+    w_a, _ = ch.process(a)
+    w_b, ph_b = ch.process(b, want_phase=True)
+    assert len(w_a[0]) > 40 and not ch.overflowed()
+    ch.reset()
+    with pytest.raises(_lib.MkidError, match='word buffer too small'):
+        ch.process(a, words_cap=8)
+    assert ch.overflowed() and not ch.overflowed()                     # sticky until cleared
+    w_b2, ph_b2 = ch.process(b, want_phase=True)
+    assert np.array_equal(ph_b2, ph_b) and np.array_equal(w_b2[0], w_b[0])
+    # asynchronous call with a small device buffer: no error code, the flag says it
+    ch.reset()
+    wdev = ctx.alloc(8 * 8)
+    ch.process_async(ctx.to_device(a), wdev, 8, n=n)
+    assert ch.overflowed()
+    w_b3, _ = ch.process(b)
+    assert np.array_equal(w_b3[0], w_b[0])
+    ch.close()
