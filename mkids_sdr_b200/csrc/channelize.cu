@@ -153,11 +153,13 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
 //         transposed-form 26-tap FIR, centre, atan2, Fix16_13 store, candidate mask.  The role with the longest
 //         dependent chains has the highest warp ids (the issue arbiter prefers them).
 // Hand-over by mbarriers (256 arrivals each): u_full[buf] PFB -> FFT, x_done[buf] FFT -> CHAN, u_free[buf] CHAN -> PFB.
-// PFB and CHAN each have one named barrier per block (before their elected thread re-arms the ADC / DDS stage).
+// No role has a barrier of its own: an ADC / DDS stage (6 / 5 of them) is refilled by an elected thread once the mbarrier
+// chain u_full -> x_done -> u_free proves that every thread of the role has consumed it (see the comments at arm_adc / arm_dds).
 // Every chunk is a regular chunk: the samples in front of the call come from `edge` = [input history | first 2048
 // samples of the call], which is all zeros in front of the start of the stream (frames before time 0 contribute +-0).
 constexpr int WS_THREADS = 1024;
 constexpr int WS_NBUF = 4;
+constexpr int WS_ADC_STAGES = 6, WS_DDS_STAGES = 5;       // 8 KiB each; with the exchange buffers 227 KiB of shared memory
 
 struct WsParams {
     ChanDev d;
@@ -210,14 +212,16 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *s_u = reinterpret_cast<float2 *>(smem_raw);                           // [4][16][FFT_STRIDE]
     float2 *s_tw = s_u + WS_NBUF * 16 * FFT_STRIDE;                               // [16][16]
-    uint32_t *s_adc = reinterpret_cast<uint32_t *>(s_tw + 256);                   // [2][8][256]
-    uint32_t *s_dds = s_adc + 2 * FB * NCH;                                       // [2][8][256]
-    __shared__ __align__(8) uint64_t s_bar[4 + 3 * WS_NBUF];     // adc_full[2], dds_full[2], u_full[4], x_done[4], u_free[4]
-    uint64_t *adc_full = s_bar, *dds_full = s_bar + 2, *u_full = s_bar + 4, *x_done = u_full + WS_NBUF, *u_free = x_done + WS_NBUF;
+    uint32_t *s_adc = reinterpret_cast<uint32_t *>(s_tw + 256);                   // [6][8][256]
+    uint32_t *s_dds = s_adc + WS_ADC_STAGES * FB * NCH;                           // [5][8][256]
+    // adc_full[6], dds_full[5], u_full[4], x_done[4], u_free[4]
+    __shared__ __align__(8) uint64_t s_bar[WS_ADC_STAGES + WS_DDS_STAGES + 3 * WS_NBUF];
+    uint64_t *adc_full = s_bar, *dds_full = s_bar + WS_ADC_STAGES, *u_full = dds_full + WS_DDS_STAGES;
+    uint64_t *x_done = u_full + WS_NBUF, *u_free = x_done + WS_NBUF;
     const int tid = threadIdx.x;
     if (tid == 0) {
-        mk_mbar_init(&adc_full[0], 1); mk_mbar_init(&adc_full[1], 1);
-        mk_mbar_init(&dds_full[0], 1); mk_mbar_init(&dds_full[1], 1);
+        for (int i = 0; i < WS_ADC_STAGES; ++i) mk_mbar_init(&adc_full[i], 1);
+        for (int i = 0; i < WS_DDS_STAGES; ++i) mk_mbar_init(&dds_full[i], 1);
         for (int i = 0; i < WS_NBUF; ++i) { mk_mbar_init(&u_full[i], WS_ARRIVALS); mk_mbar_init(&x_done[i], WS_ARRIVALS); mk_mbar_init(&u_free[i], WS_ARRIVALS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -289,16 +293,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
         const float2 w512 = d.tw512[k];
         const uint32_t *in = p.in + (size_t)board * p.n;
         const uint32_t *edge = p.edge + (size_t)board * (d.H + 2048) + d.H;   // edge[idx] valid for -H <= idx < 2048
-        auto arm_adc = [&](int blk) {                                 // elected thread: block blk -> stage blk & 1
+        auto arm_adc = [&](int blk) {                                 // elected thread: block blk -> stage blk mod 6
+            const int st = blk % WS_ADC_STAGES;
             const int64_t s0 = HOP * (fb_first + (int64_t)blk * FB);
             const uint32_t *src = s0 >= 0 ? in + s0 : edge + s0;
-            mk_mbar_expect_tx(&adc_full[blk & 1], FB * HOP * 4);
-            mk_bulk_g2s(s_adc + (blk & 1) * FB * NCH, src, FB * HOP * 4, &adc_full[blk & 1]);
+            mk_mbar_expect_tx(&adc_full[st], FB * HOP * 4);
+            mk_bulk_g2s(s_adc + st * FB * NCH, src, FB * HOP * 4, &adc_full[st]);
         };
-        if (k == 0) {
-            arm_adc(0);
-            if (n_blocks > 1) arm_adc(1);
-        }
+        if (k == 0)
+            for (int b0 = 0; b0 < WS_ADC_STAGES && b0 < n_blocks; ++b0) arm_adc(b0);
         // warm-up: s[j] = x[256*(f+1) - 2048 + k + 256*j], j = 0..6 for f = fb_first
         float2 sw[8];
 #pragma unroll
@@ -309,9 +312,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
         sw[7] = make_float2(0.f, 0.f);
         for (int blk = 0; blk < n_blocks; ++blk) {
             const int buf = blk % WS_NBUF;
-            if (blk >= WS_NBUF) mk_mbar_wait_sleep(&u_free[buf], (uint32_t)((blk / WS_NBUF - 1) & 1));   // CHAN has gathered block blk - 4
-            mk_mbar_wait_sleep(&adc_full[blk & 1], (uint32_t)((blk >> 1) & 1));
-            const uint32_t *adc_c = s_adc + (blk & 1) * FB * NCH + k;
+            if (blk >= WS_NBUF) {
+                mk_mbar_wait_sleep(&u_free[buf], (uint32_t)((blk / WS_NBUF - 1) & 1));   // CHAN has gathered block blk - 4
+                // u_free(blk - 4) follows x_done(blk - 4), which follows u_full(blk - 4): EVERY PFB thread has finished
+                // block blk - 4, so its ADC stage can be refilled (6 stages: block blk + 2 goes there) without a barrier
+                if (k == 0 && blk + 2 < n_blocks) arm_adc(blk + 2);
+            }
+            const int st = blk % WS_ADC_STAGES;
+            mk_mbar_wait_sleep(&adc_full[st], (uint32_t)((blk / WS_ADC_STAGES) & 1));
+            const uint32_t *adc_c = s_adc + st * FB * NCH + k;
             float2 *ub = s_u + buf * 16 * FFT_STRIDE + k;
 #pragma unroll
             for (int i = 0; i < FB; ++i) {
@@ -326,8 +335,6 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
                 ub[(2 * i + 1) * FFT_STRIDE] = cmul(csub(u0, u1), w512);      // odd bins
             }
             mk_mbar_arrive(&u_full[buf]);
-            asm volatile("bar.sync 1, 256;" ::: "memory");                   // every PFB thread has read ADC stage blk & 1
-            if (k == 0 && blk + 2 < n_blocks) arm_adc(blk + 2);
         }
         return;
     }
@@ -351,15 +358,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
     const int ld_mask = d.Ld - 1;                               // Ld is a power of two
     const uint32_t *dds_blk = d.dds + (size_t)board * d.Ld * NCH;
     const int dds_row0 = (int)((p.f0_abs + fb_first) & ld_mask);   // f_abs mod Ld of the first frame of block 0
-    auto arm_dds = [&](int kb) {
+    auto arm_dds = [&](int kb) {                                  // elected thread: block kb -> stage kb mod 5
+        const int st = kb % WS_DDS_STAGES;
         const int row = (dds_row0 + kb * FB) & ld_mask;
-        mk_mbar_expect_tx(&dds_full[kb & 1], FB * NCH * 4);
-        mk_bulk_g2s(s_dds + (kb & 1) * FB * NCH, dds_blk + (size_t)row * NCH, FB * NCH * 4, &dds_full[kb & 1]);
+        mk_mbar_expect_tx(&dds_full[st], FB * NCH * 4);
+        mk_bulk_g2s(s_dds + st * FB * NCH, dds_blk + (size_t)row * NCH, FB * NCH * 4, &dds_full[st]);
     };
-    if (c == 0) {
-        arm_dds(0);
-        if (n_blocks > 1) arm_dds(1);
-    }
+    if (c == 0)
+        for (int b0 = 0; b0 < WS_DDS_STAGES && b0 < n_blocks; ++b0) arm_dds(b0);
     // ---- state in chunk-relative rows (32-bit): row r = row0 + rl
     const int n_rows = (int)(row1 - row0);
     const int rl_start = (int)(r_start - row0);                       // <= 0: first computed row
@@ -470,11 +476,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
     auto one_block = [&](auto RBc, int kb) {
         const int buf = kb % WS_NBUF;
         mk_mbar_wait_sleep(&x_done[buf], (uint32_t)((kb / WS_NBUF) & 1));
-        mk_mbar_wait_sleep(&dds_full[kb & 1], (uint32_t)((kb >> 1) & 1));
-        channel_stage(RBc, s_u + buf * 16 * FFT_STRIDE, s_dds + (kb & 1) * FB * NCH + c, &u_free[buf]);
+        // x_done(kb) follows u_full(kb), which follows u_free(kb - 4): EVERY CHAN thread has read the DDS values of block
+        // kb - 4, so that stage can be refilled (5 stages: block kb + 1 goes there) without a barrier
+        if (c == 0 && kb >= WS_NBUF && kb + 1 < n_blocks) arm_dds(kb + 1);
+        const int st = kb % WS_DDS_STAGES;
+        mk_mbar_wait_sleep(&dds_full[st], (uint32_t)((kb / WS_DDS_STAGES) & 1));
+        channel_stage(RBc, s_u + buf * 16 * FFT_STRIDE, s_dds + st * FB * NCH + c, &u_free[buf]);
         rl += 4;
-        asm volatile("bar.sync 2, 256;" ::: "memory");              // every CHAN thread has read DDS stage kb & 1
-        if (c == 0 && kb + 2 < n_blocks) arm_dds(kb + 2);
     };
     for (int kb = 0; kb < n_blocks; kb += 4) {
         one_block(std::integral_constant<int, 0>{}, kb);
@@ -1224,7 +1232,7 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     if (!evp[0]) { cudaEventCreate(&evp[0]); cudaEventCreate(&evp[1]); }
     ch->n_calls++;
     {
-        const size_t smem = (size_t)(WS_NBUF * 16 * FFT_STRIDE + 256) * sizeof(float2) + (size_t)4 * FB * NCH * 4;
+        const size_t smem = (size_t)(WS_NBUF * 16 * FFT_STRIDE + 256) * sizeof(float2) + (size_t)(WS_ADC_STAGES + WS_DDS_STAGES) * FB * NCH * 4;
         // edge buffer <- first 2048 samples of this call (behind the history of the previous ones)
         edge_head_kernel<<<dim3(8, B), 256, 0, ctx->stream>>>(d.hist, d.H, in_dev, n);
         MKID_CHECK_LAUNCH(ctx);
