@@ -119,22 +119,21 @@ __device__ __forceinline__ void fft16(float2 (&v)[16]) {
     for (int k2 = 0; k2 < 4; ++k2) fft4(v[4 * k2], v[4 * k2 + 1], v[4 * k2 + 2], v[4 * k2 + 3]);
 }
 
-// atan2 for the phase stage: branch-free, |error| < 4e-7 rad (minimax degree-8 polynomial in t^2 on
+// atan2 for the phase stage: branch-free, |error| < 4e-7 rad (minimax degree-7 polynomial in t^2 on
 // [0,1], fast division), exact signed-zero / axis behaviour of atan2f where the model needs it.
 __device__ __forceinline__ float atan2_fast(float y, float x) {
     const float ax = fabsf(x), ay = fabsf(y);
     const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
     const float t = __fdividef(mn, fmaxf(mx, 1e-30f));       // 0 / 0 -> 0 (both zero only for a zeroed channel at the centre)
     const float s = t * t;
-    float p = 2.4566796610e-03f;
-    p = fmaf(p, s, -1.4401168771e-02f);
-    p = fmaf(p, s, 3.9780896098e-02f);
-    p = fmaf(p, s, -7.2348273357e-02f);
-    p = fmaf(p, s, 1.0498930424e-01f);
-    p = fmaf(p, s, -1.4161224578e-01f);
-    p = fmaf(p, s, 1.9985906047e-01f);
-    p = fmaf(p, s, -3.3332596978e-01f);
-    p = fmaf(p, s, 9.9999988637e-01f);
+    float p = -4.0562719287e-03f;                 // degree 7 in t^2: 3.8e-8 rad in exact arithmetic, 1.2e-7 rad as evaluated in float32
+    p = fmaf(p, s, 2.1868927929e-02f);
+    p = fmaf(p, s, -5.5920632268e-02f);
+    p = fmaf(p, s, 9.6427808134e-02f);
+    p = fmaf(p, s, -1.3908846780e-01f);
+    p = fmaf(p, s, 1.9946606613e-01f);
+    p = fmaf(p, s, -3.3329864130e-01f);
+    p = fmaf(p, s, 9.9999933635e-01f);
     p = p * t;
     p = ay > ax ? 1.5707963267948966f - p : p;
     p = x < 0.f ? 3.14159265358979f - p : p;
