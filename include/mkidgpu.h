@@ -50,6 +50,8 @@ void *mkid_stream(mkid_ctx *ctx);
  * afterwards; mkid_stream_wait_ctx: the reverse. */
 int  mkid_wait_stream(mkid_ctx *ctx, void *ext_stream);
 int  mkid_stream_wait_ctx(mkid_ctx *ctx, void *ext_stream);
+/* the stream of `ctx` waits for event `slot` of another context on the same GPU (recorded with mkid_event_record) */
+int  mkid_stream_wait_event(mkid_ctx *ctx, mkid_ctx *owner, int32_t slot);
 /* number of kernels this context has launched since creation (bench "gpu_launches") */
 int64_t mkid_launch_count(mkid_ctx *ctx);
 /* device timing on the context stream: record returns an event slot id (0..63) */
@@ -265,6 +267,14 @@ int  mkid_chan_kernel_ms_sum(mkid_ctx *ctx, mkid_chan *ch, int32_t last_n, float
 /* device pointer to the int32 [n_boards] word counts of the last mkid_chan_process call (asynchronous chaining into
  * mkid_decode_words_dev; valid until the channelizer is destroyed) */
 int  mkid_chan_n_words_dev(mkid_ctx *ctx, mkid_chan *ch, const int32_t **out);
+/* Two-stage pipeline over two contexts of one GPU.  mkid_chan_set_pipelined(on): consecutive process calls alternate
+ * between two sets of phase rows / candidate masks.  mkid_chan_process(..., detect = 2, ...) runs the channelizer kernel
+ * (with the candidate mask) only; mkid_chan_detect_pending then runs resolve / scan / emit for THAT call, on the stream of
+ * the context it is given -- which may be a second context, ordered by mkid_event_record / mkid_stream_wait_event: the
+ * detection of batch k then runs under the channelizer kernel of batch k + 1 (mkids_sdr_b200/chain.py does this).
+ * words / words_cap / n_words as in mkid_chan_process. */
+int  mkid_chan_set_pipelined(mkid_ctx *ctx, mkid_chan *ch, int32_t on);
+int  mkid_chan_detect_pending(mkid_ctx *ctx, mkid_chan *ch, uint64_t *words, int64_t words_cap, int32_t *n_words);
 /* Asynchronous calls (n_words == NULL) cannot report a word buffer that was too small: a sticky device flag records it.
  * *flag != 0: some call since the last clear produced more words than words_cap for a board (the surplus was dropped,
  * the streaming state stayed consistent).  Synchronises. */

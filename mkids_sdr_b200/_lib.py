@@ -60,6 +60,9 @@ _SIGNATURES = {
     'mkid_stream': (c_void_p, [c_void_p]),
     'mkid_merge_words_dev': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_int64, c_void_p]),
     'mkid_chan_overflowed': (c_int32, [c_void_p, c_void_p, c_void_p, c_int32]),
+    'mkid_chan_set_pipelined': (c_int32, [c_void_p, c_void_p, c_int32]),
+    'mkid_chan_detect_pending': (c_int32, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    'mkid_stream_wait_event': (c_int32, [c_void_p, c_void_p, c_int32]),
     'mkid_wait_stream': (c_int32, [c_void_p, c_void_p]),
     'mkid_stream_wait_ctx': (c_int32, [c_void_p, c_void_p]),
     'mkid_nccl_version': (c_int32, [c_void_p, c_void_p]),
@@ -276,6 +279,10 @@ class Context:
 
     def record(self, slot):
         self._check(self.lib.mkid_event_record(self.h, slot))
+
+    def wait_event(self, owner, slot):
+        """This context's stream waits for event `slot` recorded on another context of the same GPU."""
+        self._check(self.lib.mkid_stream_wait_event(self.h, owner.h, int(slot)))
 
     def elapsed_ms(self, a, b):
         ms = c_float()

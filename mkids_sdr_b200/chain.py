@@ -27,8 +27,13 @@ FS = 512e6
 class ReadoutChain:
     def __init__(self, n_boards, n_lut, fir_int, mean_len=20, holdoff=1000, peak_win=32, npix_per_roach=253,
                  exptime=64, n_roaches_total=None, roach0=0, hist_field='peak', n_bins=64, bin_lut=None, ctx=None,
-                 counts_buf=None, hist_buf=None, want_merged=False):
+                 counts_buf=None, hist_buf=None, want_merged=False, pipelined=False):
         self.ctx = ctx or _lib.default_context()
+        # pipelined: a second context (stream) on the same GPU takes detection, decode and the merged list of batch k
+        # while the channelizer kernel of batch k + 1 runs on the first one (process_async / process_stream only)
+        self.pipelined = bool(pipelined)
+        self.ctx2 = _lib.Context(self.ctx.device) if self.pipelined else self.ctx
+        self._k = 0
         self.n_boards, self.n_lut = n_boards, n_lut
         self.roach0 = roach0
         self.chan = Channelizer(n_boards, n_lut, mean_len, holdoff, peak_win, ctx=self.ctx)
@@ -37,7 +42,9 @@ class ReadoutChain:
         if bin_lut is None and hist_field and n_bins < 4096:
             bin_lut = np.arange(4096) * n_bins // 4096           # coarse pulse-height spectrum
         self.dec = PhotonDecoder(n_roaches_total, npix_per_roach, exptime, hist_field=hist_field, n_bins=n_bins,
-                                 bin_lut=bin_lut, ctx=self.ctx, counts_buf=counts_buf, hist_buf=hist_buf)
+                                 bin_lut=bin_lut, ctx=self.ctx2, counts_buf=counts_buf, hist_buf=hist_buf)
+        if self.pipelined:
+            self.ctx._check(self.ctx.lib.mkid_chan_set_pipelined(self.ctx.h, self.chan.h, 1))
         self._words_dev = None
         self._cap = 0
         # time-ordered merged photon list of every batch, device resident: merged_words_dev /
@@ -52,6 +59,8 @@ class ReadoutChain:
         self.chan.set_board(b, bins, I_dds, Q_dds, zero_ch, centers_i, centers_q, thresholds)
 
     def reset(self):
+        self.join()
+        self.ctx.sync()
         self.chan.reset()
         self.dec.reset()
         self.sec[:] = 0
@@ -102,9 +111,20 @@ class ReadoutChain:
             c._check(c.lib.mkid_memcpy(c.h, _lib.ptr(self._sec_dev[self._sec_cur]), _lib.ptr(self.sec), self.n_boards * 4))
             c.sync()
             self._sec_on_host = False
-        self.chan.process_async(iq, self._words_dev, self._cap, n=n)
         start = np.arange(self.n_boards, dtype=np.int64) * self._cap
         caps = np.full(self.n_boards, self._cap, dtype=np.int64)
+        b = self.ctx2                                   # == c unless pipelined
+        if self.pipelined:
+            par = self._k & 1
+            if self._k >= 2:
+                c.wait_event(b, 40 + par)               # the detection of batch k - 2 has released this set of phase rows
+            c._check(c.lib.mkid_chan_process(c.h, self.chan.h, _lib.ptr(iq), int(n), 2, None, 0, None, None))
+            self.chan.t_consumed += n // 512
+            c.record(42 + par)
+            b.wait_event(c, 42 + par)
+            b._check(b.lib.mkid_chan_detect_pending(b.h, self.chan.h, _lib.ptr(self._words_dev), int(self._cap), None))
+        else:
+            self.chan.process_async(iq, self._words_dev, self._cap, n=n)
         self.dec.decode_words_dev(self._words_dev, start, caps, self.chan.n_words_dev(),
                                   self.roach0 + np.arange(self.n_boards), self._sec_dev[self._sec_cur],
                                   self._sec_dev[1 - self._sec_cur], self.n_boards * self._cap)
@@ -112,10 +132,13 @@ class ReadoutChain:
             if self.merged_words_dev is None or self.merged_words_dev.nbytes < self.n_boards * self._cap * 8:
                 self.merged_words_dev = c.alloc(self.n_boards * self._cap * 8)
                 self.merged_offsets_dev = c.alloc((_lib.MERGE_MAX_SEC * self.n_boards + 1) * 4)
-            c._check(c.lib.mkid_merge_words_dev(c.h, _lib.ptr(self._words_dev), _lib.ptr(start), _lib.ptr(caps),
+            b._check(b.lib.mkid_merge_words_dev(b.h, _lib.ptr(self._words_dev), _lib.ptr(start), _lib.ptr(caps),
                                                 self.chan.n_words_dev(), _lib.ptr(self._sec_dev[self._sec_cur]),
                                                 self.n_boards, ctypes.byref(self.dec.cfg), _lib.ptr(self.merged_words_dev),
                                                 self.n_boards * self._cap, _lib.ptr(self.merged_offsets_dev)))
+        if self.pipelined:
+            b.record(40 + (self._k & 1))
+        self._k += 1
         self._sec_cur = 1 - self._sec_cur
 
     def process_stream(self, batches, n, words_host=None, counts_host=None):
@@ -142,6 +165,7 @@ class ReadoutChain:
             c.upload_wait(cur)
             self.process_async(self._iq_dev[cur], n=n)
             c.upload_consumed(cur)
+            self.join()
             c._check(c.lib.mkid_memcpy(c.h, _lib.ptr(nw_host), self.chan.n_words_dev(), nw_host.nbytes))
             if words_host is not None:
                 for b in range(self.n_boards):
@@ -155,8 +179,21 @@ class ReadoutChain:
             yield nw_host.copy()
         self.sync_state()
 
+    @property
+    def launches(self):
+        """Kernels launched through this chain's context(s)."""
+        return self.ctx.launches + (self.ctx2.launches if self.pipelined else 0)
+
+    def join(self):
+        """Pipelined mode: the first context's stream waits for everything queued on the second one (call before queuing
+        work on `ctx` that reads the products, e.g. the reduce over the GPUs)."""
+        if self.pipelined:
+            self.ctx2.record(44)
+            self.ctx.wait_event(self.ctx2, 44)
+
     def sync_state(self):
         """After process_async calls: returns the word counts of the last batch, refreshes self.sec."""
+        self.join()
         c = self.ctx
         if self._sec_dev is not None and not self._sec_on_host:
             c._check(c.lib.mkid_memcpy(c.h, _lib.ptr(self.sec), _lib.ptr(self._sec_dev[self._sec_cur]), self.n_boards * 4))
@@ -208,6 +245,8 @@ class ReadoutChain:
         """loadThresholds (ROACH_Pulses.py:259-288) on a pulse-free stretch of the synthetic stream: the raw phase
         stays in HBM and all channels are histogrammed by one kernel (mkid_thresholds_from_phase)."""
         from . import triggers
+        self.join()
+        self.ctx.sync()
         tb = np.stack([bd['tone_bins'] for bd in boards])
         iq = self.ctx.alloc(self.n_boards * n * 4)
         synth_adc(self.n_boards, n, tb, n_lut=self.n_lut, pulse_rate=0.0, seed=seed, out=iq, ctx=self.ctx)

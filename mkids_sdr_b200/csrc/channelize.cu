@@ -55,8 +55,12 @@ struct mkid_chan {
     ChanDev d;
     int64_t t_consumed = 0;              // output samples (us) produced so far per board
     // scratch owned by the object
-    int16_t *phase_buf = nullptr; size_t phase_rows = 0;
-    uint32_t *mask = nullptr; size_t mask_bytes = 0;
+    // phase rows and candidate mask exist twice: with mkid_chan_set_pipelined the calls alternate between the two sets,
+    // so that the detection of batch k (on another stream) can run under the channelizer kernel of batch k + 1
+    int16_t *phase_set[2] = {nullptr, nullptr}; size_t phase_rows_set[2] = {0, 0};
+    uint32_t *mask_set[2] = {nullptr, nullptr}; size_t mask_bytes_set[2] = {0, 0};
+    bool alternate = false;
+    struct Pending { bool valid = false; int set = 0; int64_t rows = 0, T = 0, t_abs0 = 0; } pending;
     uint32_t *acc = nullptr; size_t acc_bytes = 0;
     uint32_t *win_cnt = nullptr; size_t win_bytes = 0;    // [B][n_win] counts then offsets
     bool detect_clean = false;           // acc / win_cnt are all zero (the emit kernels clear what they consume)
@@ -959,15 +963,19 @@ struct ChainTimer {
 ChainTimer g_timer;
 
 int run_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase_dev, int64_t rows, int64_t r_lo, int64_t r_hi,
-               int64_t t_abs0, uint64_t *words_dev, int64_t words_cap, bool have_mask) {
+               int64_t t_abs0, uint64_t *words_dev, int64_t words_cap, const uint32_t *mask_ready) {
     const ChanDev &d = ch->d;
     const int B = d.n_boards;
     const int64_t n_groups = (rows + 31) >> 5;
     int rc;
     size_t cap;
-    cap = ch->mask_bytes;
-    if ((rc = ensure(ctx, (void **)&ch->mask, &cap, (size_t)B * n_groups * NCH * 4))) return rc;
-    ch->mask_bytes = cap;
+    const bool have_mask = mask_ready != nullptr;
+    if (!have_mask) {                                   // detection on caller-supplied phase rows: mask set 0 as scratch
+        cap = ch->mask_bytes_set[0];
+        if ((rc = ensure(ctx, (void **)&ch->mask_set[0], &cap, (size_t)B * n_groups * NCH * 4))) return rc;
+        ch->mask_bytes_set[0] = cap;
+    }
+    const uint32_t *mask = have_mask ? mask_ready : ch->mask_set[0];
     const int n_win = (int)((r_hi - r_lo + d.Lw - 1) / d.Lw);
     cap = ch->acc_bytes;
     if ((rc = ensure(ctx, (void **)&ch->acc, &cap, (size_t)B * n_win * NCH * 4))) return rc;
@@ -984,11 +992,11 @@ int run_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase_dev, int64_t r
     ch->detect_clean = false;
     if (!have_mask) {
         dim3 gc((unsigned)((rows + CAND_ROWS - 1) / CAND_ROWS), B);
-        candidates_kernel<<<gc, 256, 0, ctx->stream>>>(phase_dev, rows, d.M, d.thr, ch->mask);
+        candidates_kernel<<<gc, 256, 0, ctx->stream>>>(phase_dev, rows, d.M, d.thr, ch->mask_set[0]);
         MKID_CHECK_LAUNCH(ctx);
     }
     g_timer.mark(ctx->stream, "memsets");
-    resolve_kernel<<<dim3(NCH / RES_CH, B), 256, 0, ctx->stream>>>(ch->mask, rows, r_lo, r_hi, t_abs0, d.L, d.Lw, n_win,
+    resolve_kernel<<<dim3(NCH / RES_CH, B), 256, 0, ctx->stream>>>(mask, rows, r_lo, r_hi, t_abs0, d.L, d.Lw, n_win,
                                                              d.t_next, ch->acc, ch->win_cnt);
     MKID_CHECK_LAUNCH(ctx);
     g_timer.mark(ctx->stream, "resolve");
@@ -1080,7 +1088,7 @@ extern "C" void mkid_chan_destroy(mkid_ctx *ctx, mkid_chan *ch) {
     if (ctx) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
     ChanDev &d = ch->d;
     void *ps[] = {d.window, d.tw512, d.tw256, d.bins, d.dds, d.gain, d.cen_i, d.cen_q, d.thr, d.hist, d.t_next,
-                  ch->n_words_dev, ch->halo, ch->phase_buf, ch->mask, ch->acc, ch->win_cnt, ch->words_dev, ch->in_dev};
+                  ch->n_words_dev, ch->halo, ch->phase_set[0], ch->phase_set[1], ch->mask_set[0], ch->mask_set[1], ch->acc, ch->win_cnt, ch->words_dev, ch->in_dev};
     for (void *p : ps) if (p) cudaFree(p);
     for (int i = 0; i < 2 * mkid_chan::EV_RING; ++i) if (ch->ev_k4[i]) cudaEventDestroy(ch->ev_k4[i]);
     delete ch;
@@ -1171,6 +1179,66 @@ extern "C" int mkid_chan_reset(mkid_ctx *ctx, mkid_chan *ch) {
     return MKID_OK;
 }
 
+namespace {
+// resolve / scan / emit on the rows of a finished channelizer call; with n_words (host) the counts and, for a host word
+// buffer, the words are fetched (synchronises).  *overflow_need = words per board that would have been needed, or 0.
+int detect_and_fetch(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase_buf, const uint32_t *mask, int64_t rows, int64_t T,
+                     int64_t t_abs0, uint64_t *words, int64_t words_cap, int32_t *n_words, int64_t *overflow_need) {
+    const int B = ch->d.n_boards;
+    int rc;
+    size_t cap;
+    uint64_t *wdev;
+    if (mkid_is_device_ptr(words)) wdev = words;
+    else {
+        cap = ch->words_bytes;
+        if ((rc = ensure(ctx, (void **)&ch->words_dev, &cap, (size_t)B * words_cap * 8))) return rc;
+        ch->words_bytes = cap;
+        wdev = ch->words_dev;
+    }
+    if ((rc = run_detect(ctx, ch, phase_buf, rows, RES_LO, RES_LO + T, t_abs0, wdev, words_cap, mask))) return rc;
+    if (n_words) {
+        MKID_CUDA(ctx, cudaMemcpyAsync(n_words, ch->n_words_dev, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        int64_t mx = 0;
+        for (int b = 0; b < B; ++b) mx = std::max<int64_t>(mx, n_words[b]);
+        if (wdev != words) {
+            const int64_t ncopy = std::min<int64_t>(mx, words_cap);
+            for (int b = 0; b < B; ++b)
+                if (n_words[b] > 0)
+                    MKID_CUDA(ctx, cudaMemcpyAsync(words + (size_t)b * words_cap, wdev + (size_t)b * words_cap,
+                                                   (size_t)std::min<int64_t>(n_words[b], ncopy) * 8, cudaMemcpyDeviceToHost,
+                                                   ctx->stream));
+            MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        *overflow_need = mx > words_cap ? mx : 0;
+    }
+    return MKID_OK;
+}
+}  // namespace
+
+extern "C" int mkid_chan_set_pipelined(mkid_ctx *ctx, mkid_chan *ch, int32_t on) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, ch, "chan_set_pipelined: NULL");
+    ch->alternate = on != 0;
+    return MKID_OK;
+}
+
+extern "C" int mkid_chan_detect_pending(mkid_ctx *ctx, mkid_chan *ch, uint64_t *words, int64_t words_cap, int32_t *n_words) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, ch && words && words_cap > 0, "chan_detect_pending: NULL argument");
+    MKID_REQUIRE(ctx, ch->pending.valid, "chan_detect_pending: no mkid_chan_process(detect = 2) call is waiting for its detection");
+    if (!n_words) MKID_REQUIRE(ctx, mkid_is_device_ptr(words), "asynchronous call (n_words == NULL): words must be device memory");
+    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
+    const mkid_chan::Pending pd = ch->pending;
+    ch->pending.valid = false;
+    int64_t need = 0;
+    int rc = detect_and_fetch(ctx, ch, ch->phase_set[pd.set], ch->mask_set[pd.set], pd.rows, pd.T, pd.t_abs0, words, words_cap, n_words, &need);
+    if (rc) return rc;
+    if (need) return mkid_fail(ctx, MKID_EINVAL, "word buffer too small: need %lld per board, have %lld (the words beyond the capacity are lost)",
+                               (long long)need, (long long)words_cap);
+    return MKID_OK;
+}
+
 extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq, int64_t n, int32_t detect,
                                  uint64_t *words, int64_t words_cap, int32_t *n_words, int16_t *phase_out) {
     if (!ctx) return MKID_EINVAL;
@@ -1180,8 +1248,9 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     MKID_REQUIRE(ctx, n >= d.H, "n must be at least the history length (59392 samples) per call");
     MKID_REQUIRE(ctx, ch->fir_set, "FIR taps not set (mkid_chan_set_fir)");
     for (int b = 0; b < d.n_boards; ++b) MKID_REQUIRE(ctx, ch->board_set[b], "a board is not configured (mkid_chan_set_board)");
-    if (detect) MKID_REQUIRE(ctx, words && words_cap > 0, "detect requested but no word buffer");
-    if (detect && !n_words) MKID_REQUIRE(ctx, mkid_is_device_ptr(words) && mkid_is_device_ptr(iq) && !phase_out,
+    MKID_REQUIRE(ctx, detect >= 0 && detect <= 2, "detect must be 0, 1 or 2 (2 = mask only, detection by mkid_chan_detect_pending)");
+    if (detect == 1) MKID_REQUIRE(ctx, words && words_cap > 0, "detect requested but no word buffer");
+    if (detect == 1 && !n_words) MKID_REQUIRE(ctx, mkid_is_device_ptr(words) && mkid_is_device_ptr(iq) && !phase_out,
                                          "asynchronous call (n_words == NULL): iq and words must be device memory, no phase_out");
     MKID_CUDA(ctx, cudaSetDevice(ctx->device));
     const int B = d.n_boards;
@@ -1198,14 +1267,16 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
         MKID_CUDA(ctx, cudaMemcpyAsync(ch->in_dev, iq, (size_t)B * n * 4, cudaMemcpyHostToDevice, ctx->stream));
         in_dev = ch->in_dev;
     }
-    cap = ch->phase_rows * NCH * 2 * B;
-    if (ch->phase_rows < (size_t)rows) {
-        if ((rc = ensure(ctx, (void **)&ch->phase_buf, &cap, (size_t)B * rows * NCH * 2))) return rc;
-        ch->phase_rows = (size_t)rows;
+    const int set = ch->alternate ? (int)(ch->n_calls & 1) : 0;
+    cap = ch->phase_rows_set[set] * NCH * 2 * B;
+    if (ch->phase_rows_set[set] < (size_t)rows) {
+        if ((rc = ensure(ctx, (void **)&ch->phase_set[set], &cap, (size_t)B * rows * NCH * 2))) return rc;
+        ch->phase_rows_set[set] = (size_t)rows;
     }
+    int16_t *const phase_buf = ch->phase_set[set];
     // K4: equal chunks of rows, one CTA per SM in a single wave
     WsParams w;
-    w.d = d; w.in = in_dev; w.edge = d.hist; w.n = n; w.f0_abs = 2 * ch->t_consumed; w.phase = ch->phase_buf; w.phase_f32 = ch->f32_out; w.rows = rows;
+    w.d = d; w.in = in_dev; w.edge = d.hist; w.n = n; w.f0_abs = 2 * ch->t_consumed; w.phase = phase_buf; w.phase_f32 = ch->f32_out; w.rows = rows;
     {
         int64_t chunks = std::max<int64_t>(1, (int64_t)ctx->num_sms / B);
         while (chunks > 1 && rows / chunks < 128) chunks = (chunks + 1) / 2;
@@ -1217,13 +1288,13 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     w.mask = nullptr; w.halo = nullptr;
     if (detect) {       // K5c fused into K4: the candidate mask is produced while the phase is in registers
         const int64_t n_groups = (rows + 31) >> 5;
-        cap = ch->mask_bytes;
-        if ((rc = ensure(ctx, (void **)&ch->mask, &cap, (size_t)B * n_groups * NCH * 4))) return rc;
-        ch->mask_bytes = cap;
+        cap = ch->mask_bytes_set[set];
+        if ((rc = ensure(ctx, (void **)&ch->mask_set[set], &cap, (size_t)B * n_groups * NCH * 4))) return rc;
+        ch->mask_bytes_set[set] = cap;
         cap = ch->halo_bytes;
         if ((rc = ensure(ctx, (void **)&ch->halo, &cap, (size_t)B * w.chunks_per_board * 32 * NCH * 2))) return rc;
         ch->halo_bytes = cap;
-        w.mask = ch->mask; w.halo = ch->halo;
+        w.mask = ch->mask_set[set]; w.halo = ch->halo;
     }
     g_timer.report();
     g_timer.mark(ctx->stream, "start");
@@ -1249,37 +1320,16 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     g_timer.mark(ctx->stream, "channelize");
     if (phase_out) {
         for (int b = 0; b < B; ++b)
-            MKID_CUDA(ctx, cudaMemcpyAsync(phase_out + (size_t)b * T * NCH, ch->phase_buf + ((size_t)b * rows + PRE_ROWS) * NCH,
+            MKID_CUDA(ctx, cudaMemcpyAsync(phase_out + (size_t)b * T * NCH, phase_buf + ((size_t)b * rows + PRE_ROWS) * NCH,
                                            (size_t)T * NCH * 2, cudaMemcpyDefault, ctx->stream));
     }
     const int64_t t_abs0 = ch->t_consumed - PRE_ROWS;
     int64_t overflow_need = 0;
-    if (detect) {
-        uint64_t *wdev;
-        if (mkid_is_device_ptr(words)) wdev = words;
-        else {
-            cap = ch->words_bytes;
-            if ((rc = ensure(ctx, (void **)&ch->words_dev, &cap, (size_t)B * words_cap * 8))) return rc;
-            ch->words_bytes = cap;
-            wdev = ch->words_dev;
-        }
-        if ((rc = run_detect(ctx, ch, ch->phase_buf, rows, RES_LO, RES_LO + T, t_abs0, wdev, words_cap, true))) return rc;
-        if (n_words) {
-        MKID_CUDA(ctx, cudaMemcpyAsync(n_words, ch->n_words_dev, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        int64_t mx = 0;
-        for (int b = 0; b < B; ++b) mx = std::max<int64_t>(mx, n_words[b]);
-        if (wdev != words) {
-            const int64_t ncopy = std::min<int64_t>(mx, words_cap);
-            for (int b = 0; b < B; ++b)
-                if (n_words[b] > 0)
-                    MKID_CUDA(ctx, cudaMemcpyAsync(words + (size_t)b * words_cap, wdev + (size_t)b * words_cap,
-                                                   (size_t)std::min<int64_t>(n_words[b], ncopy) * 8, cudaMemcpyDeviceToHost,
-                                                   ctx->stream));
-            MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        }
-        overflow_need = mx > words_cap ? mx : 0;
-        }
+    ch->pending = mkid_chan::Pending();
+    if (detect == 2) {              // detection deferred to mkid_chan_detect_pending (possibly on another context's stream)
+        ch->pending.valid = true; ch->pending.set = set; ch->pending.rows = rows; ch->pending.T = T; ch->pending.t_abs0 = t_abs0;
+    } else if (detect) {
+        if ((rc = detect_and_fetch(ctx, ch, phase_buf, ch->mask_set[set], rows, T, t_abs0, words, words_cap, n_words, &overflow_need))) return rc;
     }
     // history <- last H samples of this call (n >= H)
     update_history_kernel<<<dim3(32, B), 256, 0, ctx->stream>>>(d.hist, d.H, in_dev, n, B);
@@ -1348,7 +1398,7 @@ extern "C" int mkid_chan_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *pha
     if (t_next) MKID_CUDA(ctx, cudaMemcpyAsync(d.t_next, t_next, (size_t)B * NCH * 8, cudaMemcpyDefault, ctx->stream));
     void *w_dev;
     if ((rc = mkid_stage_out(ctx, words, (size_t)B * words_cap * 8, SCR_OUT0, false, &w_dev))) return rc;
-    if ((rc = run_detect(ctx, ch, (const int16_t *)ph_dev, rows, d.M, rows - d.W - 1, t_abs0, (uint64_t *)w_dev, words_cap, false))) return rc;
+    if ((rc = run_detect(ctx, ch, (const int16_t *)ph_dev, rows, d.M, rows - d.W - 1, t_abs0, (uint64_t *)w_dev, words_cap, nullptr))) return rc;
     MKID_CUDA(ctx, cudaMemcpyAsync(n_words, ch->n_words_dev, (size_t)B * 4, cudaMemcpyDeviceToHost, ctx->stream));
     if (t_next) MKID_CUDA(ctx, cudaMemcpyAsync(t_next, d.t_next, (size_t)B * NCH * 8, cudaMemcpyDefault, ctx->stream));
     MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -151,3 +151,14 @@ extern "C" int mkid_stream_wait_ctx(mkid_ctx *ctx, void *ext_stream) {
     MKID_CUDA(ctx, cudaEventDestroy(ev));
     return MKID_OK;
 }
+
+// the context's stream waits for event `slot` of ANOTHER context (recorded there with mkid_event_record): two contexts on
+// one GPU form a two-stage pipeline (channelizer kernel of batch k + 1 under the detection / decode of batch k)
+extern "C" int mkid_stream_wait_event(mkid_ctx *ctx, mkid_ctx *owner, int32_t slot) {
+    if (!ctx) return MKID_EINVAL;
+    MKID_REQUIRE(ctx, owner && slot >= 0 && slot < MKID_NUM_EVENTS, "stream_wait_event: bad argument");
+    MKID_REQUIRE(ctx, owner->device == ctx->device, "stream_wait_event: both contexts must be on the same device");
+    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
+    MKID_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, owner->events[slot], 0));
+    return MKID_OK;
+}

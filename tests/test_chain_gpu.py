@@ -183,3 +183,40 @@ def test_stress_config_shapes(ctx):
     assert per_pix[:30 * npix].sum() == 0 and per_pix[40 * npix:].sum() == 0
     assert per_pix[30 * npix:40 * npix].sum() > 1000
     iq.free()
+
+
+def test_pipelined_chain_equals_the_single_stream_chain(ctx):
+    """ReadoutChain(pipelined=True): detection / decode / merged list of batch k on a second context under the channelizer
+    kernel of batch k + 1 (mkid_chan_process(detect=2) + mkid_chan_detect_pending + mkid_stream_wait_event).  Same photon
+    words, per-pixel products and merged lists as the single-stream chain, batch by batch."""
+    from mkids_sdr_b200 import _lib
+    from mkids_sdr_b200.chain import ReadoutChain
+    from mkids_sdr_b200.channelizer import synth_adc
+    n, nb = 2 ** 19, 5
+    outs = []
+    for pipelined in (False, True):
+        chain, boards = ReadoutChain.synthetic(2, 2 ** 16, 40, seed0=11, threshold=-2500, holdoff=100, ctx=ctx, exptime=4,
+                                               n_bins=4096, want_merged=True, pipelined=pipelined)
+        tb = np.stack([bd['tone_bins'] for bd in boards])
+        iq = ctx.alloc(2 * nb * n * 4)
+        synth_adc(2, nb * n, tb, n_lut=2 ** 16, pulse_rate=4000., seed=21, out=iq, ctx=ctx)
+        full = iq.download(np.int16).reshape(2, nb * n, 2)
+        batches = [ctx.to_device(np.ascontiguousarray(full[:, k * n:(k + 1) * n])) for k in range(nb)]
+        per_batch = []
+        for k in range(nb):
+            chain.process_async(batches[k], n=n)
+            if k in (1, nb - 1):                       # look at two of the batches (a sync in between is allowed)
+                nw = chain.sync_state()
+                words = chain._words_dev.download(np.uint64).reshape(2, -1)
+                offs = chain.merged_offsets_dev.download(np.int32, _lib.MERGE_MAX_SEC * 2 + 1)
+                merged = chain.merged_words_dev.download(np.uint64, int(offs[-1]))
+                per_batch.append((nw.copy(), [words[b, :nw[b]].copy() for b in range(2)], offs, merged))
+        outs.append((per_batch, chain.dec.counts_raw().copy(), chain.dec.hist().copy()))
+        for bf in batches:
+            bf.free()
+        iq.free()
+    (pa, ca, ha), (pb, cb, hb) = outs
+    assert ca.sum() > 300 and np.array_equal(ca, cb) and np.array_equal(ha, hb)
+    for (nwa, wa, oa, ma), (nwb, wb, ob, mb) in zip(pa, pb):
+        assert np.array_equal(nwa, nwb) and np.array_equal(oa, ob) and np.array_equal(ma, mb)
+        assert all(np.array_equal(x, y) for x, y in zip(wa, wb))
