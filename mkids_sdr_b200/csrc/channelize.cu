@@ -210,6 +210,26 @@ __device__ __forceinline__ void mk_mbar_wait_sleep(uint64_t *bar, uint32_t parit
         "}\n" ::"r"(mk_smem_u32(bar)), "r"(parity), "r"(1000000u) : "memory");
 }
 
+// Hand-over between the roles.  Default: hardware named barriers (bar.arrive by the 256 producer threads, bar.sync by the
+// 256 consumer threads, ids 1..12): a waiting warp is descheduled by the barrier unit and costs no issue slots, where the
+// mbarrier polling loops (try_wait / branch / yield) took a third of all executed instructions.  -DK4_MBAR_HANDOVER keeps
+// the mbarrier form.  The TMA stages (adc_full / dds_full) are transaction barriers and stay mbarriers.
+#ifndef K4_MBAR_HANDOVER
+struct HandOver { int id; };
+__device__ __forceinline__ void ho_arrive(HandOver h) { asm volatile("bar.arrive %0, %1;" ::"r"(h.id), "r"(2 * NCH) : "memory"); }
+__device__ __forceinline__ void ho_wait(HandOver h, uint32_t) { asm volatile("bar.sync %0, %1;" ::"r"(h.id), "r"(2 * NCH) : "memory"); }
+#define HO_U_FULL(buf) HandOver{1 + (buf)}
+#define HO_X_DONE(buf) HandOver{1 + WS_NBUF + (buf)}
+#define HO_U_FREE(buf) HandOver{1 + 2 * WS_NBUF + (buf)}
+#else
+typedef uint64_t *HandOver;
+__device__ __forceinline__ void ho_arrive(HandOver h) { mk_mbar_arrive(h); }
+__device__ __forceinline__ void ho_wait(HandOver h, uint32_t parity) { mk_mbar_wait_sleep(h, parity); }
+#define HO_U_FULL(buf) (&u_full[buf])
+#define HO_X_DONE(buf) (&x_done[buf])
+#define HO_U_FREE(buf) (&u_free[buf])
+#endif
+
 template <bool F32>
 __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -253,7 +273,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
         const int g = tid >> 8, lt = tid & 255, j = lt & 15;
         for (int kb = g; kb < n_blocks; kb += 2) {
             const int buf = kb % WS_NBUF;
-            mk_mbar_wait_sleep(&u_full[buf], (uint32_t)((kb / WS_NBUF) & 1));
+            ho_wait(HO_U_FULL(buf), (uint32_t)((kb / WS_NBUF) & 1));
             float2 *reg = s_u + buf * 16 * FFT_STRIDE + (lt >> 4) * FFT_STRIDE;
             float2 v[16];
 #pragma unroll
@@ -280,7 +300,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
             for (int k1 = 0; k1 < 4; ++k1)
 #pragma unroll
                 for (int k2 = 0; k2 < 4; ++k2) reg[j + 16 * (4 * k1 + k2)] = v[4 * k2 + k1];
-            mk_mbar_arrive(&x_done[buf]);
+            ho_arrive(HO_X_DONE(buf));
         }
         return;
     }
@@ -316,7 +336,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
         for (int blk = 0; blk < n_blocks; ++blk) {
             const int buf = blk % WS_NBUF;
             if (blk >= WS_NBUF) {
-                mk_mbar_wait_sleep(&u_free[buf], (uint32_t)((blk / WS_NBUF - 1) & 1));   // CHAN has gathered block blk - 4
+                ho_wait(HO_U_FREE(buf), (uint32_t)((blk / WS_NBUF - 1) & 1));   // CHAN has gathered block blk - 4
                 // u_free(blk - 4) follows x_done(blk - 4), which follows u_full(blk - 4): EVERY PFB thread has finished
                 // block blk - 4, so its ADC stage can be refilled (6 stages: block blk + 2 goes there) without a barrier
                 if (k == 0 && blk + 2 < n_blocks) arm_adc(blk + 2);
@@ -337,7 +357,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
                 ub[(2 * i) * FFT_STRIDE] = cadd(u0, u1);                      // even bins
                 ub[(2 * i + 1) * FFT_STRIDE] = cmul(csub(u0, u1), w512);      // odd bins
             }
-            mk_mbar_arrive(&u_full[buf]);
+            ho_arrive(HO_U_FULL(buf));
         }
         return;
     }
@@ -387,7 +407,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
 #pragma unroll
     for (int m = 0; m < 16; ++m) acc[m] = make_float2(0.f, 0.f);
 
-    auto channel_stage = [&](auto RBc, const float2 *xbuf, const uint32_t *dds_c, uint64_t *free_bar) {
+    auto channel_stage = [&](auto RBc, const float2 *xbuf, const uint32_t *dds_c, HandOver free_bar) {
         constexpr int RB = decltype(RBc)::value;
         constexpr int A0 = RB / 2;                                       // slot of output m = 0
         // gather the bin, remove the half-frame hop phase of odd bins ((-1)^(bin*(f_abs+1)); f_abs of
@@ -405,7 +425,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
             y[i].x = zz.x * dvi.x + zz.y * dvi.y;
             y[i].y = zz.y * dvi.x - zz.x * dvi.y;
         }
-        mk_mbar_arrive(free_bar);                                // the bins of this block are in registers: the buffer may be refilled
+        ho_arrive(free_bar);                                      // the bins of this block are in registers: the buffer may be refilled
         // output t = fb/2 + m uses frames 2t+1-25+k, k = 0..25: frame fb+i carries tap k = i - 2m + 24
 #pragma unroll
         for (int k = 0; k < FIRT; ++k) {
@@ -478,13 +498,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
     // copies in sequence, so that the accumulators never move between registers.
     auto one_block = [&](auto RBc, int kb) {
         const int buf = kb % WS_NBUF;
-        mk_mbar_wait_sleep(&x_done[buf], (uint32_t)((kb / WS_NBUF) & 1));
+        ho_wait(HO_X_DONE(buf), (uint32_t)((kb / WS_NBUF) & 1));
         // x_done(kb) follows u_full(kb), which follows u_free(kb - 4): EVERY CHAN thread has read the DDS values of block
         // kb - 4, so that stage can be refilled (5 stages: block kb + 1 goes there) without a barrier
         if (c == 0 && kb >= WS_NBUF && kb + 1 < n_blocks) arm_dds(kb + 1);
         const int st = kb % WS_DDS_STAGES;
         mk_mbar_wait_sleep(&dds_full[st], (uint32_t)((kb / WS_DDS_STAGES) & 1));
-        channel_stage(RBc, s_u + buf * 16 * FFT_STRIDE, s_dds + st * FB * NCH + c, &u_free[buf]);
+        channel_stage(RBc, s_u + buf * 16 * FFT_STRIDE, s_dds + st * FB * NCH + c, HO_U_FREE(buf));
         rl += 4;
     };
     for (int kb = 0; kb < n_blocks; kb += 4) {
