@@ -306,38 +306,53 @@ def main():
     n_pix = leg.n_pix
 
     # ---------------------------------------------------------------- end to end with host buffers
-    pin_iq = torch.empty((B, n, 2), dtype=torch.int16).pin_memory()
-    pin_iq.copy_(leg.iq.cpu())
+    # Two host formats of the same samples: the 12-bit packed stream (3 bytes per complex sample; the ADC is 12 bit and the
+    # synthetic input is clipped to it, so the photon words are identical: tests/test_chain_gpu.py) is the headline `e2e`,
+    # the int16 pairs (4 bytes per sample) are reported next to it as `e2e_int16`.
     cap = chain.chan.words_capacity(n)
     pin_words = torch.empty((B, cap), dtype=torch.int64).pin_memory()
     pin_counts = torch.empty(exptime * n_pix, dtype=torch.int32).pin_memory()
     words_np = pin_words.numpy().view(np.uint64)
+    k_e2e = max(min(args.steps // 2, 25), 1)
 
-    def e2e_steps(k):
+    def e2e_run(pin_iq, fmt):
         """k batches from pinned host memory through ReadoutChain.process_stream: H2D of every batch (double buffered
         on a second stream, overlapping the previous batch's kernels), D2H of the photon words, word counts and
         per-pixel counts after every batch."""
-        nw = 0
-        for nwk in chain.process_stream((pin_iq for _ in range(k)), n, words_host=words_np, counts_host=pin_counts):
-            nw += int(nwk.sum())
-        return nw
-    k_e2e = max(min(args.steps // 2, 25), 1)
-    e2e_steps(1)
-    barrier()
-    t0 = time.time()
-    nw = e2e_steps(k_e2e)
-    reducer.allreduce(leg.products, leg.n_counts + leg.n_hist)
-    barrier()
-    e2e_ms = (time.time() - t0) * 1e3
-    el = torch.tensor([e2e_ms], dtype=torch.float64, device='cuda')
-    if dist is not None:
-        dist.all_reduce(el, op=dist.ReduceOp.MAX)
-    e2e_step_ms = float(el[0]) / k_e2e
-    e2e_value = world * B * n / (e2e_step_ms * 1e-3) / 1e6
-    words_per_step = nw / k_e2e
+        def steps(k):
+            nw = 0
+            for nwk in chain.process_stream((pin_iq for _ in range(k)), n, words_host=words_np, counts_host=pin_counts,
+                                            adc_format=fmt):
+                nw += int(nwk.sum())
+            return nw
+        steps(1)
+        barrier()
+        t0 = time.time()
+        nw = steps(k_e2e)
+        reducer.allreduce(leg.products, leg.n_counts + leg.n_hist)
+        barrier()
+        el = torch.tensor([(time.time() - t0) * 1e3], dtype=torch.float64, device='cuda')
+        if dist is not None:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        step_ms = float(el[0]) / k_e2e
+        return step_ms, world * B * n / (step_ms * 1e-3) / 1e6, nw / k_e2e
+
+    pin_iq = torch.empty((B, n, 2), dtype=torch.int16).pin_memory()
+    pin_iq.copy_(leg.iq.cpu())
+    e2e16_step_ms, e2e16_value, words_per_step = e2e_run(pin_iq, 'i16')
+    del pin_iq
+    packed_dev = ctx.alloc(B * n * 3)
+    n_clipped = ctx.adc_pack12(leg.iq, B * n, packed_dev)
+    pin_p12 = torch.empty((B, 3 * n), dtype=torch.uint8).pin_memory()
+    ctx._check(ctx.lib.mkid_memcpy(ctx.h, _lib.ptr(pin_p12), _lib.ptr(packed_dev), B * n * 3))
+    ctx.sync()
+    packed_dev.free()
+    e2e_step_ms, e2e_value, words_p12 = e2e_run(pin_p12, 'p12')
+    assert n_clipped == 0, n_clipped        # the packed stream holds the same samples
+    del pin_p12
     if rank == 0:
         sampler.stop_flag = True
-    del pin_iq, pin_words, pin_counts
+    del pin_words, pin_counts
     fir_int = np.array(chain.fir_int)
     leg.free()
     stage('end-to-end done')
@@ -403,9 +418,14 @@ def main():
                            'bytes': res['reduce_bytes'], 'ms': res['reduce_ms'],
                            'bus_GB/s': (2.0 * (world - 1) / world * res['reduce_bytes'] / (res['reduce_ms'] * 1e-3) / 1e9) if world > 1 and res['reduce_ms'] > 0 else None,
                            'share_of_timed_region': res['reduce_ms'] / max(res['dev_ms'], 1e-9)},
-            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(B * n * 4),
+            'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(B * n * 3),
                     'd2h_bytes_per_step': int(B * cap * 8 + exptime * n_pix * 4 + B * 4), 'ms_per_step': e2e_step_ms, 'steps': k_e2e,
-                    'api': 'ReadoutChain.process_stream (upload of batch k+1 overlaps the kernels of batch k)', 'numa': numa},
+                    'adc_format': 'p12: 12-bit packed I/Q, 3 bytes per complex sample on the host link (the ADC is 12 bit; lossless, '
+                                  'photon words identical to the int16 format), expanded by adc_unpack12_kernel in front of K4',
+                    'api': "ReadoutChain.process_stream(adc_format='p12') (upload of batch k+1 overlaps the kernels of batch k)", 'numa': numa},
+            'e2e_int16': {'value': e2e16_value, 'unit': UNIT, 'h2d_bytes_per_step': int(B * n * 4),
+                          'd2h_bytes_per_step': int(B * cap * 8 + exptime * n_pix * 4 + B * 4), 'ms_per_step': e2e16_step_ms, 'steps': k_e2e,
+                          'adc_format': 'i16: int16 I/Q pairs, 4 bytes per complex sample', 'api': 'ReadoutChain.process_stream'},
             'gpu_launches': res['launches'],
             'photon_words_per_step': words_per_step,
             'clocks': sampler.summary()}

@@ -281,6 +281,14 @@ int  mkid_chan_detect_pending(mkid_ctx *ctx, mkid_chan *ch, uint64_t *words, int
 int  mkid_chan_overflowed(mkid_ctx *ctx, mkid_chan *ch, int32_t *flag, int32_t clear);
 int  mkid_chan_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase, int64_t rows, int64_t t_abs0,
                       int64_t *t_next, uint64_t *words, int64_t words_cap, int32_t *n_words);
+/* 12-bit packed ADC stream.  The ADC of the readout is 12 bit (the firmware data plane the channelizer models, SURVEY.md
+ * section 3: ADC 512 MS/s -> FFT-512); a complex sample can travel over the host link as 3 bytes instead of an int16
+ * pair: little-endian 24-bit group I[11:0] | Q[11:0] << 12, two's complement, four samples = three 32-bit words.
+ * mkid_adc_unpack12 expands n_samples (a multiple of 4) packed samples into the int16 [n][2] layout mkid_chan_process
+ * reads; mkid_adc_pack12 is the inverse (values outside [-2048, 2047] are clipped and counted in *n_clipped, which
+ * synchronises when non-NULL).  Device pointers, asynchronous on the context stream. */
+int  mkid_adc_unpack12(mkid_ctx *ctx, const void *packed, int64_t n_samples, int16_t *iq);
+int  mkid_adc_pack12(mkid_ctx *ctx, const int16_t *iq, int64_t n_samples, void *packed, int64_t *n_clipped);
 /* synthetic ADC stream for tests and benchmarks (replaces the ROACH ADC): per board a comb of
  * n_tones tones at fine bins tone_bin[] (f = bin*fs/n_lut), amplitude tone_amp[], phase tone_phase[],
  * each phase-modulated by exponential pulses (rate per second, decay tau_us, depth uniform in

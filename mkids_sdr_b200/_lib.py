@@ -139,6 +139,8 @@ _SIGNATURES = {
                                c_void_p, c_void_p]),
     'mkid_pack_dram': (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     'mkid_sincos_cr': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    'mkid_adc_unpack12': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p]),
+    'mkid_adc_pack12': (c_int32, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     'mkid_synth_adc': (c_int32, [c_void_p, POINTER(SynthParams), c_int32, c_void_p, c_void_p, c_void_p, c_int64,
                                  c_int64, c_void_p]),
 }
@@ -301,6 +303,17 @@ class Context:
 
     def flush_l2(self):
         self._check(self.lib.mkid_flush_l2(self.h))
+
+    def adc_unpack12(self, packed_dev, n_samples, iq_dev):
+        """12-bit packed ADC samples (3 bytes per complex sample) -> int16 [n][2]; device buffers, asynchronous."""
+        self._check(self.lib.mkid_adc_unpack12(self.h, ptr(packed_dev), int(n_samples), ptr(iq_dev)))
+
+    def adc_pack12(self, iq_dev, n_samples, packed_dev, count_clipped=True):
+        """int16 [n][2] -> 12-bit packed; returns the number of values that did not fit 12 bits (clipped)."""
+        n_bad = ctypes.c_int64(0)
+        self._check(self.lib.mkid_adc_pack12(self.h, ptr(iq_dev), int(n_samples), ptr(packed_dev),
+                                             ctypes.byref(n_bad) if count_clipped else None))
+        return int(n_bad.value)
 
     def alloc(self, nbytes):
         return DeviceBuffer(self, nbytes)

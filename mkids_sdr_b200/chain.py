@@ -141,15 +141,22 @@ class ReadoutChain:
         self._k += 1
         self._sec_cur = 1 - self._sec_cur
 
-    def process_stream(self, batches, n, words_host=None, counts_host=None):
-        """Pipelined end-to-end path for a stream of HOST batches (pinned int16 [n_boards][n][2] arrays): the upload
-        of batch k+1 (second stream, double buffered) overlaps the processing of batch k.  After every batch the
+    def process_stream(self, batches, n, words_host=None, counts_host=None, adc_format='i16'):
+        """Pipelined end-to-end path for a stream of HOST batches (pinned arrays): the upload of batch k+1 (second
+        stream, double buffered) overlaps the processing of batch k.  adc_format 'i16': int16 [n_boards][n][2]
+        (4 bytes per complex sample); 'p12': the 12-bit packed stream of mkid_adc_unpack12, uint8 [n_boards][3 n]
+        (3 bytes per sample over the host link, expanded on the GPU in front of the channelizer).  After every batch the
         photon words (whole per-board capacity, words_host u64 [n_boards][cap]), the per-(second,pixel) counts
         (counts_host) and the word counts are copied back; yields the word counts of each batch."""
         c = self.ctx
-        nbytes = self.n_boards * n * 4
+        if adc_format not in ('i16', 'p12'):
+            raise ValueError("adc_format must be 'i16' or 'p12'")
+        p12 = adc_format == 'p12'
+        nbytes = self.n_boards * n * (3 if p12 else 4)
         if getattr(self, '_iq_dev', None) is None or self._iq_dev[0].nbytes < nbytes:
             self._iq_dev = [c.alloc(nbytes), c.alloc(nbytes)]
+        if p12 and (getattr(self, '_iq_exp', None) is None or self._iq_exp.nbytes < self.n_boards * n * 4):
+            self._iq_exp = c.alloc(self.n_boards * n * 4)        # one buffer: unpack and channelizer share the stream
         cap = self.chan.words_capacity(n)
         nw_host = np.zeros(self.n_boards, dtype=np.int32)
         it = iter(batches)
@@ -163,8 +170,13 @@ class ReadoutChain:
             if nxt is not None:
                 c.upload_async(self._iq_dev[cur ^ 1], nxt, nbytes, cur ^ 1)      # waits for that buffer's consumer
             c.upload_wait(cur)
-            self.process_async(self._iq_dev[cur], n=n)
-            c.upload_consumed(cur)
+            if p12:
+                c.adc_unpack12(self._iq_dev[cur], self.n_boards * n, self._iq_exp)
+                c.upload_consumed(cur)
+                self.process_async(self._iq_exp, n=n)
+            else:
+                self.process_async(self._iq_dev[cur], n=n)
+                c.upload_consumed(cur)
             self.join()
             c._check(c.lib.mkid_memcpy(c.h, _lib.ptr(nw_host), self.chan.n_words_dev(), nw_host.nbytes))
             if words_host is not None:

@@ -947,6 +947,71 @@ __global__ void __launch_bounds__(256) synth_adc_kernel(uint32_t *out, int64_t n
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// 12-bit packed ADC stream.  The ROACH ADC delivers 12-bit I and Q; on the host link (PCIe: the bound of the end-to-end
+// path) a complex sample travels as 3 bytes instead of the 4 of the int16 pair: little-endian 24-bit group
+// I[11:0] | Q[11:0] << 12 (two's complement).  One CTA step = 1024 samples: 768 words staged through shared memory with
+// coalesced loads, every thread expands 4 samples (3 words, stride 3: conflict-free) into one 16-byte store.
+constexpr int P12_THREADS = 256;
+__device__ __forceinline__ uint32_t p12_expand(uint32_t s) {          // 24-bit group -> int16 I | int16 Q << 16
+    const uint32_t i16 = (uint32_t)(((int32_t)(s << 20)) >> 20) & 0xFFFFu;
+    const uint32_t q16 = (uint32_t)(((int32_t)(s << 8)) >> 20) << 16;
+    return i16 | q16;
+}
+__global__ void __launch_bounds__(P12_THREADS) adc_unpack12_kernel(const uint32_t *__restrict__ packed, uint4 *__restrict__ out,
+                                                                    int64_t n_quads) {
+    __shared__ uint32_t s_w[3 * P12_THREADS];
+    const int tid = threadIdx.x;
+    const int64_t n_tiles = (n_quads + P12_THREADS - 1) / P12_THREADS;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t q0 = tile * P12_THREADS;
+        const int64_t w0 = 3 * q0, w_end = 3 * n_quads;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int64_t w = w0 + k * P12_THREADS + tid;
+            s_w[k * P12_THREADS + tid] = w < w_end ? packed[w] : 0u;
+        }
+        __syncthreads();
+        const uint32_t a = s_w[3 * tid], b = s_w[3 * tid + 1], c = s_w[3 * tid + 2];
+        __syncthreads();
+        if (q0 + tid < n_quads)
+            out[q0 + tid] = make_uint4(p12_expand(a & 0xFFFFFFu), p12_expand((a >> 24) | ((b & 0xFFFFu) << 8)),
+                                       p12_expand((b >> 16) | ((c & 0xFFu) << 16)), p12_expand(c >> 8));
+    }
+}
+// the inverse (tests, input preparation): *bad counts the samples outside [-2048, 2047] (they are stored clipped)
+__global__ void __launch_bounds__(P12_THREADS) adc_pack12_kernel(const uint4 *__restrict__ iq, uint32_t *__restrict__ packed,
+                                                                  int64_t n_quads, unsigned long long *bad) {
+    __shared__ uint32_t s_w[3 * P12_THREADS];
+    const int tid = threadIdx.x;
+    const int64_t n_tiles = (n_quads + P12_THREADS - 1) / P12_THREADS;
+    int n_bad = 0;
+    auto group = [&](uint32_t v) -> uint32_t {
+        int i = (int16_t)(v & 0xFFFFu), q = (int16_t)(v >> 16);
+        const int ic = max(-2048, min(2047, i)), qc = max(-2048, min(2047, q));
+        n_bad += (ic != i) + (qc != q);
+        return ((uint32_t)ic & 0xFFFu) | (((uint32_t)qc & 0xFFFu) << 12);
+    };
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t q0 = tile * P12_THREADS;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (q0 + tid < n_quads) v = iq[q0 + tid];
+        const uint32_t g0 = group(v.x), g1 = group(v.y), g2 = group(v.z), g3 = group(v.w);
+        s_w[3 * tid] = g0 | (g1 << 24);
+        s_w[3 * tid + 1] = (g1 >> 8) | (g2 << 16);
+        s_w[3 * tid + 2] = (g2 >> 16) | (g3 << 8);
+        __syncthreads();
+        const int64_t w0 = 3 * q0, w_end = 3 * n_quads;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int64_t w = w0 + k * P12_THREADS + tid;
+            if (w < w_end) packed[w] = s_w[k * P12_THREADS + tid];
+        }
+        __syncthreads();
+    }
+    if (n_bad) atomicAdd(bad, (unsigned long long)n_bad);
+}
+
 int ensure(mkid_ctx *ctx, void **p, size_t *cap, size_t bytes) {
     if (*cap >= bytes && *p) return MKID_OK;
     if (*p) { MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); MKID_CUDA(ctx, cudaFree(*p)); *p = nullptr; *cap = 0; }
@@ -1464,4 +1529,38 @@ extern "C" int mkid_synth_adc(mkid_ctx *ctx, const mkid_synth_params *prm, int32
         MKID_CHECK_LAUNCH(ctx);
     }
     return mkid_stage_out_finish(ctx, out, (size_t)n_boards * n * 4, o_dev);
+}
+
+extern "C" int mkid_adc_unpack12(mkid_ctx *ctx, const void *packed, int64_t n_samples, int16_t *iq) {
+    MKID_REQUIRE(ctx, packed && iq && n_samples > 0 && n_samples % 4 == 0, "adc_unpack12: NULL argument or n_samples not a multiple of 4");
+    MKID_REQUIRE(ctx, mkid_is_device_ptr(packed) && mkid_is_device_ptr(iq), "adc_unpack12: device pointers required (use mkid_upload_async / mkid_memcpy for the host side)");
+    MKID_REQUIRE(ctx, ((uintptr_t)packed & 3) == 0 && ((uintptr_t)iq & 15) == 0, "adc_unpack12: packed must be 4-byte and iq 16-byte aligned");
+    const int64_t n_quads = n_samples / 4;
+    const int64_t tiles = (n_quads + P12_THREADS - 1) / P12_THREADS;
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)ctx->num_sms * 8);
+    adc_unpack12_kernel<<<grid, P12_THREADS, 0, ctx->stream>>>((const uint32_t *)packed, (uint4 *)iq, n_quads);
+    MKID_CHECK_LAUNCH(ctx);
+    return MKID_OK;
+}
+
+extern "C" int mkid_adc_pack12(mkid_ctx *ctx, const int16_t *iq, int64_t n_samples, void *packed, int64_t *n_clipped) {
+    MKID_REQUIRE(ctx, packed && iq && n_samples > 0 && n_samples % 4 == 0, "adc_pack12: NULL argument or n_samples not a multiple of 4");
+    MKID_REQUIRE(ctx, mkid_is_device_ptr(packed) && mkid_is_device_ptr(iq), "adc_pack12: device pointers required");
+    MKID_REQUIRE(ctx, ((uintptr_t)packed & 3) == 0 && ((uintptr_t)iq & 15) == 0, "adc_pack12: packed must be 4-byte and iq 16-byte aligned");
+    int rc;
+    unsigned long long *bad;
+    if ((rc = mkid_scratch(ctx, SCR_AUX5, 8, (void **)&bad))) return rc;
+    MKID_CUDA(ctx, cudaMemsetAsync(bad, 0, 8, ctx->stream));
+    const int64_t n_quads = n_samples / 4;
+    const int64_t tiles = (n_quads + P12_THREADS - 1) / P12_THREADS;
+    const int grid = (int)std::min<int64_t>(tiles, (int64_t)ctx->num_sms * 8);
+    adc_pack12_kernel<<<grid, P12_THREADS, 0, ctx->stream>>>((const uint4 *)iq, (uint32_t *)packed, n_quads, bad);
+    MKID_CHECK_LAUNCH(ctx);
+    if (n_clipped) {
+        unsigned long long h = 0;
+        MKID_CUDA(ctx, cudaMemcpyAsync(&h, bad, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        *n_clipped = (int64_t)h;
+    }
+    return MKID_OK;
 }

@@ -40,6 +40,9 @@ Model choices the reference does not determine (stated, and identical in the CUD
     rad, truncation toward zero as castBin 'Truncate') ; baseline v = sum/M.
   * timestamp = absolute output index mod 1e6 (us), words ordered by (time, channel), one
     all-ones word at every second boundary.
+  * host-link format of the ADC stream (no counterpart in the reference: its ADC feeds the FPGA directly): either
+    int16 [n][2] or, for a 12-bit ADC, 3 bytes per complex sample = little-endian 24-bit group
+    I[11:0] | Q[11:0] << 12, two's complement (adc_pack12 / adc_unpack12 below).
 """
 import numpy as np
 
@@ -242,3 +245,28 @@ def synth_board(n, tone_bins_fine, N_lut, amps=None, seed=42, pulse_rate=1000.0,
     iq[:, 0] = np.clip(np.rint(x.real), -2047, 2047)
     iq[:, 1] = np.clip(np.rint(x.imag), -2047, 2047)
     return iq, pulses
+
+
+def adc_pack12(iq):
+    """int16 [..., n, 2] (values in [-2048, 2047]) -> uint8 [..., 3 n]: 24-bit little-endian groups I | Q << 12."""
+    iq = np.asarray(iq).astype(np.int64)
+    if iq.min() < -2048 or iq.max() > 2047:
+        raise ValueError('sample does not fit 12 bits')
+    g = (iq[..., 0] & 0xFFF) | ((iq[..., 1] & 0xFFF) << 12)
+    out = np.empty(g.shape + (3,), dtype=np.uint8)
+    out[..., 0] = g & 0xFF
+    out[..., 1] = (g >> 8) & 0xFF
+    out[..., 2] = (g >> 16) & 0xFF
+    return out.reshape(g.shape[:-1] + (3 * g.shape[-1],))
+
+
+def adc_unpack12(packed):
+    """uint8 [..., 3 n] -> int16 [..., n, 2] (sign-extended 12-bit I and Q)."""
+    b = np.asarray(packed, dtype=np.uint8).astype(np.int64)
+    b = b.reshape(b.shape[:-1] + (b.shape[-1] // 3, 3))
+    g = b[..., 0] | (b[..., 1] << 8) | (b[..., 2] << 16)
+    i = g & 0xFFF
+    q = (g >> 12) & 0xFFF
+    i = np.where(i >= 2048, i - 4096, i)
+    q = np.where(q >= 2048, q - 4096, q)
+    return np.stack([i, q], axis=-1).astype(np.int16)

@@ -161,6 +161,68 @@ def test_process_stream_equals_process(ctx):
     assert sum(len(w) for w in res[0][0][0]) > 20
 
 
+def test_adc_pack12_roundtrip_and_layout(ctx):
+    """12-bit packed ADC stream: the GPU expansion equals the oracle's bit layout, the GPU packer is its inverse, values
+    outside 12 bits are clipped and counted; ragged tail (n not a multiple of the 1024-sample tile)."""
+    rng = np.random.default_rng(5)
+    for n in (4, 1020, 4096 + 8, 3 * 1024 * 40 + 12):
+        iq = rng.integers(-2048, 2048, size=(n, 2)).astype(np.int16)
+        iq[0] = (-2048, 2047)
+        iq[-1] = (2047, -2048)
+        want = oc.adc_pack12(iq)
+        assert np.array_equal(oc.adc_unpack12(want), iq)
+        d_iq, d_pk = ctx.to_device(iq), ctx.alloc(3 * n)
+        assert ctx.adc_pack12(d_iq, n, d_pk) == 0
+        assert np.array_equal(d_pk.download(np.uint8, 3 * n), want)
+        d_out = ctx.alloc(4 * n)
+        ctx.adc_unpack12(ctx.to_device(want), n, d_out)
+        assert np.array_equal(d_out.download(np.int16, 2 * n).reshape(n, 2), iq)
+    big = np.array([[3000, -5], [7, -2049], [1, 1], [0, 0]], dtype=np.int16)
+    d_pk = ctx.alloc(12)
+    assert ctx.adc_pack12(ctx.to_device(big), 4, d_pk) == 2
+    d_out = ctx.alloc(16)
+    ctx.adc_unpack12(d_pk, 4, d_out)
+    assert np.array_equal(d_out.download(np.int16, 8).reshape(4, 2), np.clip(big, -2048, 2047))
+    from mkids_sdr_b200 import _lib
+    with pytest.raises(_lib.MkidError):
+        ctx.adc_unpack12(d_pk, 6, d_out)                 # not a multiple of 4 samples
+
+
+def test_process_stream_packed12_equals_int16(ctx):
+    """process_stream over the 12-bit packed host format (3 bytes per sample over PCIe, expanded on the GPU) gives the
+    words, counts and histogram of the int16 format bit for bit (the synthetic ADC is clipped to 12 bits)."""
+    from mkids_sdr_b200.chain import ReadoutChain
+    from mkids_sdr_b200.channelizer import synth_adc
+    B, n_lut, n = 2, 2 ** 16, 2 ** 19
+    res = []
+    for fmt in ('i16', 'p12'):
+        chain, boards = ReadoutChain.synthetic(B, n_lut, 40, seed0=11, threshold=-2400, holdoff=100, ctx=ctx, exptime=3,
+                                               n_bins=16)
+        tb = np.stack([bd['tone_bins'] for bd in boards])
+        batches, keep = [], []
+        for k in range(3):
+            a = synth_adc(B, n, tb, n_lut=n_lut, pulse_rate=4000., seed=30 + k, ctx=ctx)
+            pb = ctx.pinned(B * n * (3 if fmt == 'p12' else 4))
+            if fmt == 'p12':
+                v = pb.view(np.uint8).reshape(B, 3 * n)
+                v[:] = oc.adc_pack12(a)
+            else:
+                v = pb.view(np.int16).reshape(B, n, 2)
+                v[:] = a
+            batches.append(v); keep.append(pb)
+        cap = chain.chan.words_capacity(n)
+        wh = np.zeros((B, cap), dtype=np.uint64)
+        got = []
+        for nw in chain.process_stream(iter(batches), n, words_host=wh, adc_format=fmt):
+            got.append([wh[b, :nw[b]].copy() for b in range(B)])
+        res.append((got, chain.dec.counts_raw(), chain.dec.hist()))
+    for k in range(3):
+        for b in range(B):
+            assert np.array_equal(res[0][0][k][b], res[1][0][k][b])
+    assert np.array_equal(res[0][1], res[1][1]) and np.array_equal(res[0][2], res[1][2])
+    assert sum(len(w) for w in res[0][0][0]) > 20
+
+
 def test_stress_config_shapes(ctx):
     """BASELINE config 4 (20 000 resonators over 10 feedlines = 80 board streams of 250 channels, per-pixel 4096-bin
     histograms [20 000][4096]): one GPU's share of an 8-GPU run (10 boards, roach ids 30..39) at a short batch, checked

@@ -490,3 +490,17 @@ def test_lut_oracle_matches_reference_run_at_full_size(golden_dir):
     assert hashlib.sha256(np.asarray(I).astype('<i2').tobytes()).hexdigest() == g['sha256_I']
     assert hashlib.sha256(np.asarray(Q).astype('<i2').tobytes()).hexdigest() == g['sha256_Q']
     assert [int(v) for v in I[:8]] == g['I_first'] and int(np.asarray(I).sum()) == g['I_sum']
+
+
+def test_adc_pack12_known_answer():
+    """Host-link format of a 12-bit ADC stream (oracle/channelizer.py header): I = 0x123, Q = -2 (0xFFE) -> group 0xFFE123,
+    bytes 23 E1 FF; four samples are three little-endian 32-bit words."""
+    from oracle import channelizer as oc
+    iq = np.array([[0x123, -2], [-2048, 2047], [0, -1], [5, 6]], dtype=np.int16)
+    pk = oc.adc_pack12(iq)
+    assert pk.dtype == np.uint8 and pk.shape == (12,)
+    assert pk[:3].tolist() == [0x23, 0xE1, 0xFF]
+    assert pk[3:6].tolist() == [0x00, 0xF8, 0x7F]                 # I = 0x800, Q = 0x7FF -> 0x7FF800
+    assert np.array_equal(oc.adc_unpack12(pk), iq)
+    with pytest.raises(ValueError):
+        oc.adc_pack12(np.array([[2048, 0]], dtype=np.int16))
