@@ -141,6 +141,10 @@ __device__ __forceinline__ double ref_arg(double f, double t, double fs, double 
     return __dadd_rn(__ddiv_rn(__dmul_rn(w, t), fs), phi);
 }
 
+__device__ __forceinline__ double ref_arg_w(double w, double t, double fs, double phi) {       // w = RN(2 pi f)
+    return __dadd_rn(__ddiv_rn(__dmul_rn(w, t), fs), phi);
+}
+
 struct CombParams {
     const double *freq, *amp, *phase;    // [batch][T]
     long long *kbin;                     // [batch][T] spectral line index in [0, N) (written by comb_prep_kernel)
@@ -550,23 +554,82 @@ __global__ void __launch_bounds__(128) comb_fixup_kernel(CombParams p) {
 // cos hit 0 and +-1 often (~1 % of the samples are of either kind, thousands in a channel whose residual is a multiple
 // of a high power of two): they are first collected in a shared-memory list and then evaluated by all threads of the
 // CTA, not in divergent branches.
+// Fast bulk evaluation (round 2).  For a residual on the fs2/size grid, f = k fs2/size, the argument is
+//     A = 2 pi (k t)/size + ph + dl,     dl = the rounding of the reference's own expression (a few 1e-12 rad),
+// so sin A = sin(theta_j + ph + dl) with j = k t mod size: theta_j comes from a table of size entries (sincospi, shared
+// by all channels), ph from ONE sincos per channel, and dl -- computed in extended precision from the reference's A
+// itself: dl = ((A - hi) - ph) - lo with hi + lo = (k t)(2 pi / size) as a double-double -- enters to first order
+// (dl^2 / 2 < 1e-16 is enforced; a sample that violates it, e.g. an off-grid residual, takes the library sincos).  Error
+// of the bulk value <= 6e-16 = 2e-11 LSB after scaling, far inside the 1e-9 LSB flag distance of the exact path, which is
+// unchanged; about 25 instead of about 110 fp64 operations per sample.
+__device__ __forceinline__ int dds_swz(int j) { return j ^ ((j >> 3) & 7) ^ ((j >> 6) & 7) ^ ((j >> 9) & 7); }
+__global__ void dds_table_kernel(double2 *tab, int size) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= size) return;
+    double sn, cs;
+    sincospi(2.0 * (double)j / (double)size, &sn, &cs);          // size is a power of two: the argument is exact
+    tab[dds_swz(j)] = make_double2(sn, cs);
+}
+struct DdsFast {
+    const double2 *tab; int mask; double c_hi, c_lo, sph, cph, ph, w, fs2, rfs; int k; bool on;
+    __device__ __forceinline__ void init(const double2 *table, int size, double f, double phi, double fs) {
+        tab = table; mask = size - 1; ph = phi; fs2 = fs; rfs = __ddiv_rn(1.0, fs);
+        c_hi = 6.283185307179586 / (double)size; c_lo = 2.4492935982947064e-16 / (double)size;   // 2 pi = hi + lo
+        w = __dmul_rn(6.283185307179586, f);
+        const double kf = rint(f * (double)size / fs);
+        on = table != nullptr && fabs(phi) < 64.0 && fabs(kf) <= (double)size;      // |k t| < 2^31
+        k = on ? (int)kf : 0;
+        sincos(phi, &sph, &cph);
+    }
+    // sin and cos of the reference's argument ((2 pi f) t) / fs2 + ph for the integer sample index t
+    __device__ __forceinline__ void eval(int t, double *sn, double *cs) const {
+        if (on) {
+            // A exactly as ref_arg: the correctly rounded quotient x / fs2 from the reciprocal (q0 = x r faithful, one
+            // exact-residual correction: Markstein's theorem, r = RN(1 / fs2))
+            const double x = __dmul_rn(w, (double)t);
+            const double q0 = __dmul_rn(x, rfs);
+            const double q = __fma_rn(__fma_rn(-q0, fs2, x), rfs, q0);
+            const double A = __dadd_rn(q, ph);
+            const int kt = k * t;
+            const double y = (double)kt;
+            const double p_hi = __dmul_rn(y, c_hi);
+            const double p_lo = __fma_rn(y, c_hi, -p_hi) + y * c_lo;
+            const double dl = ((A - p_hi) - ph) - p_lo;
+            const double2 e = __ldg(&tab[dds_swz(kt & mask)]);
+            const double S0 = fma(e.x, cph, e.y * sph), C0 = fma(e.y, cph, -(e.x * sph));
+            if (fabs(dl) < 1e-8) { *sn = fma(dl, C0, S0); *cs = fma(-dl, S0, C0); return; }
+        }
+        sincos(ref_arg_w(w, (double)t, fs2, ph), sn, cs);
+    }
+};
+
 __global__ void __launch_bounds__(256) dds_lut_kernel(const double *resid, const double *phase, double fs2, int size,
-                                                      int offset, int16_t *I_dds, int16_t *Q_dds, double *scales) {
-    extern __shared__ double s_dyn[];            // I[size] | Q[size] | list[2 * size] (uint16: t | isI << 15)
+                                                      int offset, const double2 *g_tab, int cpc, int16_t *I_dds, int16_t *Q_dds,
+                                                      double *scales) {
+    extern __shared__ double s_dyn[];            // I[size] | Q[size] | list[2 * size] (uint16: t | isI << 15) | exact bits[2 * size]
     __shared__ double s_red[8];
     __shared__ unsigned long long s_max;
     __shared__ unsigned s_n;
     double *sI = s_dyn, *sQ = s_dyn + size;
     unsigned short *list = reinterpret_cast<unsigned short *>(s_dyn + 2 * size);
-    const int m = blockIdx.x, b = blockIdx.y, tid = threadIdx.x;
+    // bit e of s_exact: the staged value of entry e (t | isI << 15 -> bit t + isI * size) is already the correctly rounded
+    // one (a candidate for the maximum, evaluated in the first exact round): the quantiser uses it as it is
+    unsigned *s_exact = reinterpret_cast<unsigned *>(list + 2 * size);
+    const int b = blockIdx.y, tid = threadIdx.x;
+    for (int ci = 0; ci < cpc; ++ci) {
+    const int m = blockIdx.x * cpc + ci;
     const double f = resid[(size_t)b * 256 + m], ph = phase[(size_t)b * 256 + m];
+    DdsFast fast;
+    fast.init(g_tab, size, f, ph, fs2);
     if (tid == 0) { s_max = 0ull; s_n = 0u; }
+    for (int i = tid; i < (2 * size + 31) / 32; i += 256) s_exact[i] = 0u;
+    __syncthreads();                              // the previous channel's lists are done
     double mx = 0.0;
     for (int t = tid; t < size; t += 256) {
         double s, c;
-        sincos(ref_arg(f, (double)t, fs2, ph), &s, &c);
+        fast.eval(t, &s, &c);
         sQ[t] = s;                                // amplitude 1., accumulated onto 0. : exact
-        if (offset != 0) c = cos(ref_arg(f, (double)(t + offset), fs2, ph));
+        if (offset != 0) { double s2; fast.eval(t + offset, &s2, &c); }
         sI[t] = c;
         mx = fmax(mx, fmax(fabs(c), fabs(s)));
     }
@@ -587,10 +650,12 @@ __global__ void __launch_bounds__(256) dds_lut_kernel(const double *resid, const
         const int e = list[i], t = e & 0x7fff, isI = e >> 15;
         const double v = sin_or_cos_cr(ref_arg(f, (double)(isI ? t + offset : t), fs2, ph), isI);
         (isI ? sI : sQ)[t] = v;
+        atomicOr(&s_exact[(t + isI * size) >> 5], 1u << ((t + isI * size) & 31));
         atomicMax(&s_max, (unsigned long long)__double_as_longlong(fabs(v)));
     }
     __syncthreads();
     mx = __longlong_as_double((long long)s_max);
+    __syncthreads();                              // everybody has read s_max / s_n
     if (tid == 0) { if (scales) scales[(size_t)b * 256 + m] = mx; s_n = 0u; }
     __syncthreads();
     // channel-major tables [b][m][t] (whole lines per warp); dds_interleave_kernel scatters them to the reference's layout
@@ -601,10 +666,17 @@ __global__ void __launch_bounds__(256) dds_lut_kernel(const double *resid, const
     for (int t = tid; t < size; t += 256) {
         const int dst = t;
         const double vi = sI[t] * rs, vq = sQ[t] * rs;
-        if (fabs(vi - rint(vi)) < 1e-9) list[atomicAdd(&s_n, 1u)] = (unsigned short)(t | 0x8000);
-        else Io[dst] = (int16_t)__double2int_rz(vi);
-        if (fabs(vq - rint(vq)) < 1e-9) list[atomicAdd(&s_n, 1u)] = (unsigned short)t;
-        else Qo[dst] = (int16_t)__double2int_rz(vq);
+        // (a flagged sample that rounds to 0 truncates to 0 from either side: no exact evaluation)
+        const double ri = rint(vi), rq = rint(vq);
+        const unsigned eq = (unsigned)t, ei = (unsigned)(t + size);         // bit indices of the Q and I sample
+        if (fabs(vi - ri) < 1e-9 && ri != 0.0) {
+            if ((s_exact[ei >> 5] >> (ei & 31)) & 1u) Io[dst] = (int16_t)__double2int_rz(__ddiv_rn(__dmul_rn(sI[t], 32767.0), mx));
+            else list[atomicAdd(&s_n, 1u)] = (unsigned short)(t | 0x8000);
+        } else Io[dst] = (int16_t)__double2int_rz(vi);
+        if (fabs(vq - rq) < 1e-9 && rq != 0.0) {
+            if ((s_exact[eq >> 5] >> (eq & 31)) & 1u) Qo[dst] = (int16_t)__double2int_rz(__ddiv_rn(__dmul_rn(sQ[t], 32767.0), mx));
+            else list[atomicAdd(&s_n, 1u)] = (unsigned short)t;
+        } else Qo[dst] = (int16_t)__double2int_rz(vq);
     }
     __syncthreads();
     for (unsigned i = tid; i < s_n; i += 256) {
@@ -612,6 +684,8 @@ __global__ void __launch_bounds__(256) dds_lut_kernel(const double *resid, const
         const int dst = t;
         const double x = sin_or_cos_cr(ref_arg(f, (double)(isI ? t + offset : t), fs2, ph), isI);
         (isI ? Io : Qo)[dst] = (int16_t)__double2int_rz(__ddiv_rn(__dmul_rn(x, 32767.0), mx));
+    }
+    __syncthreads();                              // the lists and s_n are reused by the next channel
     }
 }
 
@@ -847,13 +921,24 @@ extern "C" int mkid_dds_lut(mkid_ctx *ctx, const double *resid_hz, const double 
     void *dI, *dQ;
     if ((rc = mkid_stage_out(ctx, I_dds, (size_t)batch * n_lut * 2, SCR_OUT0, false, &dI))) return rc;
     if ((rc = mkid_stage_out(ctx, Q_dds, (size_t)batch * n_lut * 2, SCR_OUT1, false, &dQ))) return rc;
-    const size_t smem = (size_t)size * 20;                        // I, Q (fp64) and the list of samples for the exact path
+    size_t smem = (size_t)size * 20 + (size_t)((2 * size + 31) / 32) * 4;      // I, Q (fp64), the list of samples for the exact path, their bit map
     MKID_REQUIRE(ctx, smem <= 200 * 1024 && size <= 32768, "dds_lut: table too long for shared memory");
+    // fast bulk path: sin / cos of the size grid angles from a shared-memory table (power-of-two sizes that fit)
+    bool fast = size >= 64 && (size & (size - 1)) == 0;
+    if (const char *e = getenv("MKID_DDS_SLOW")) fast = fast && atoi(e) == 0;      // experiment switch: library sincos for every sample
+    double2 *d_tab = nullptr;
+    if (fast) {
+        if ((rc = mkid_scratch(ctx, SCR_AUX2, (size_t)size * 16, (void **)&d_tab))) return rc;
+        dds_table_kernel<<<(size + 255) / 256, 256, 0, ctx->stream>>>(d_tab, size);
+        MKID_CHECK_LAUNCH(ctx);
+    }
     MKID_CUDA(ctx, cudaFuncSetAttribute(dds_lut_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int16_t *cmI, *cmQ;                                           // channel-major tables, interleaved by a second kernel
     if ((rc = mkid_scratch(ctx, SCR_AUX0, (size_t)batch * n_lut * 2, (void **)&cmI))) return rc;
     if ((rc = mkid_scratch(ctx, SCR_AUX1, (size_t)batch * n_lut * 2, (void **)&cmQ))) return rc;
-    dds_lut_kernel<<<dim3(256, batch), 256, smem, ctx->stream>>>(d_res, d_ph, fs2, size, offset, cmI, cmQ, d_sc);
+    int cpc = 1;                                                  // channels per CTA (experiment switch; no gain measured)
+    if (const char *e = getenv("MKID_DDS_CPC")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) cpc = v; }
+    dds_lut_kernel<<<dim3(256 / cpc, batch), 256, smem, ctx->stream>>>(d_res, d_ph, fs2, size, offset, d_tab, cpc, cmI, cmQ, d_sc);
     MKID_CHECK_LAUNCH(ctx);
     const int half = size / 2;
     dds_interleave_kernel<<<dim3(8 * ((half + 31) / 32), batch), 256, 0, ctx->stream>>>(
