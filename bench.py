@@ -225,7 +225,8 @@ def workload_config(n, hist_bins):
             'boards_per_gpu': BOARDS_PER_GPU, 'samples_per_board_per_step': n, 'n_lut': N_LUT, 'fir': 'matched_30us',
             'pulse_rate_hz': 1000, 'hist_bins': hist_bins, 'hist_field': 'peak',
             'l2': 'inputs (%.0f MiB per GPU per step) are larger than the 126 MB L2' % (BOARDS_PER_GPU * n * 4 / 2 ** 20),
-            'sharding': 'boards per GPU, no data-path collective; ONE NCCL all-reduce of the per-pixel products per job'}
+            'sharding': 'boards per GPU, no data-path collective; ONE NCCL all-reduce of the per-pixel products per job',
+            'streams': 'two contexts per GPU: detection / decode / merged list of batch k under the channelizer kernel of batch k + 1'}
 
 
 def main():
@@ -238,6 +239,7 @@ def main():
     ap.add_argument('--hist-bins', type=int, default=4096)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-extras', action='store_true', help='skip the strong-scaling / stress / decode / LUT side measurements')
+    ap.add_argument('--single-stream', action='store_true', help='headline leg on ONE stream (no overlap of the detection tail with the next channelizer kernel)')
     ap.add_argument('--stress', action='store_true', help='run the config-5 stress leg at any GPU count (default: 8 GPUs only)')
     args = ap.parse_args()
 
@@ -294,8 +296,11 @@ def main():
 
     exptime = 16
     # ---------------------------------------------------------------- headline: weak scaling, 8 boards per GPU
+    # two contexts (streams) per GPU: resolve / emit / decode / merged list of batch k run under the channelizer kernel of
+    # batch k + 1 (measured on one GPU: 1.42 -> 1.31 ms per step; the kernel itself stretches from 1.266 to 1.293 ms because
+    # the two compete for SMs when both become ready)
     leg = ChainLeg(torch, ctx, reducer, B, n, N_LUT, N_ACTIVE, 253, B * world, B * rank, 42 + 8 * rank, 1000 + rank,
-                   args.hist_bins, exptime)
+                   args.hist_bins, exptime, pipelined=not args.single_stream)
     stage('chain configured, thresholds derived, input synthesised')
     sampler = ClockSampler(local_rank)
     if rank == 0:
