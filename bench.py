@@ -468,7 +468,7 @@ def stress_leg(torch, ctx, reducer, dist, rank, world, barrier, peak):
     n = 1 << 23
     steps = 8
     leg = ChainLeg(torch, ctx, reducer, Bs, n, N_LUT, 250, 250, 80, Bs * rank, 100 + Bs * rank, 2000 + rank, 4096, 4,
-                   want_merged=False)
+                   want_merged=False, pipelined=True)
     r = leg.timed(steps, 3, barrier, world, dist)
     # checksum across ranks: the reduced histogram must be identical everywhere and hold every binned word
     cs = torch.stack([leg.products[leg.n_counts:].sum(dtype=torch.int64), leg.products[:leg.n_counts].sum(dtype=torch.int64)])
