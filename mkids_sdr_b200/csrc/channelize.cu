@@ -1363,7 +1363,13 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     WsParams w;
     w.d = d; w.in = in_dev; w.edge = d.hist; w.n = n; w.f0_abs = 2 * ch->t_consumed; w.phase = phase_buf; w.phase_f32 = ch->f32_out; w.rows = rows;
     {
-        int64_t chunks = std::max<int64_t>(1, (int64_t)ctx->num_sms / B);
+        // two-context pipeline: leave 4 SMs to the detection / decode kernels of the previous batch, which run on the other
+        // context's stream at the same time (with 8 boards 144 of 148 SMs are taken either way; with one board per GPU the
+        // kernel would otherwise fill every SM and the tail of the previous batch would queue behind it: measured per
+        // step, 1 / 2 / 4 boards: 0.276 -> 0.216, 0.432 -> 0.374, 0.747 -> 0.677 ms; 8 or 12 free SMs are no better)
+        int reserve = ch->alternate ? 4 : 0;
+        if (const char *e = getenv("MKID_K4_RESERVE")) reserve = std::max(0, std::min(atoi(e), ctx->num_sms - 8));   // experiment switch
+        int64_t chunks = std::max<int64_t>(1, (int64_t)(ctx->num_sms - reserve) / B);
         while (chunks > 1 && rows / chunks < 128) chunks = (chunks + 1) / 2;
         int64_t rpc = (rows + chunks - 1) / chunks;
         rpc = std::max<int64_t>(32, (rpc + 31) / 32 * 32);
