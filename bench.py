@@ -372,7 +372,8 @@ def main():
                 # batch k + 1 (the latency-bound tail is what limits the step once a GPU has only a board or two)
                 sl = ChainLeg(torch, ctx, reducer, Bs, n, N_LUT, N_ACTIVE, 253, 8, Bs * rank, 42 + Bs * rank, 1000 + rank,
                               args.hist_bins, exptime, pipelined=True)
-                r = sl.timed(max(args.steps // 2, 5), 3, barrier, 1, dist)       # world = 1: total work is the 8 boards
+                # >= 100 batches per job (6.5 s of data per board): the one reduce and the barriers are per job, not per batch
+                r = sl.timed(max(args.steps, 100), 3, barrier, 1, dist)       # world = 1: total work is the 8 boards
                 extras['strong_scaling'] = {'value': 8 * n / (r['step_ms'] * 1e-3) / 1e6, 'unit': UNIT, 'ms_per_step': r['step_ms'],
                                             'boards_total': 8, 'boards_per_gpu': Bs, 'n_gpus': world, 'k4_ms_per_launch': r['k4_ms'],
                                             'reduce_ms': r['reduce_ms'], 'scaling': 'strong', 'streams': 'pipelined over two contexts per GPU',
@@ -466,7 +467,7 @@ def stress_leg(torch, ctx, reducer, dist, rank, world, barrier, peak):
     summed over the GPUs by ONE NCCL all-reduce (mkid_hist_allreduce) per job."""
     Bs = 80 // world
     n = 1 << 23
-    steps = 8
+    steps = 32                       # batches of 16 ms per job: the reduce is once per job (0.5 s of data)
     leg = ChainLeg(torch, ctx, reducer, Bs, n, N_LUT, 250, 250, 80, Bs * rank, 100 + Bs * rank, 2000 + rank, 4096, 4,
                    want_merged=False, pipelined=True)
     r = leg.timed(steps, 3, barrier, world, dist)
