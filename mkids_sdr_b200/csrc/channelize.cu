@@ -148,11 +148,11 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
 // K4, warp-specialised form (the default).  One CTA per SM, 1024 threads in four roles that work on DIFFERENT blocks of
 // 8 frames at the same time, so that the shared-memory-bound FFT and the FP32-bound PFB / channel stages overlap
 // instead of alternating behind block-wide barriers (setmaxnreg gives every role the registers it needs):
-//   FFT0 / FFT1  threads 0..255 / 256..511 (56 regs): group g transforms the blocks kb = g (mod 2) in place: 16
+//   FFT0 / FFT1  threads 0..255 / 256..511 (64 regs): group g transforms the blocks kb = g (mod 2) in place: 16
 //         FFT-256 per block, 16 lanes each, two radix-16 passes; a half-warp needs only __syncwarp.
 //   PFB   threads 512..767 (40 regs): thread k = branches k, k+256: sliding register window over the ADC blocks that
 //         arrive by 1-D TMA bulk copies, first radix-2 stage, 16 STS.64 into exchange buffer k mod 4.
-//   CHAN  threads 768..1023 (96 regs): thread c = channel c: gather its bin from exchange buffer kb mod 4, DDS mix,
+//   CHAN  threads 768..1023 (88 regs): thread c = channel c: gather its bin from exchange buffer kb mod 4, DDS mix,
 //         transposed-form 26-tap FIR, centre, atan2, Fix16_13 store, candidate mask.  The role with the longest
 //         dependent chains has the highest warp ids (the issue arbiter prefers them).
 // Hand-over by mbarriers (256 arrivals each): u_full[buf] PFB -> FFT, x_done[buf] FFT -> CHAN, u_free[buf] CHAN -> PFB.
@@ -160,6 +160,17 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
 // chain u_full -> x_done -> u_free proves that every thread of the role has consumed it (see the comments at arm_adc / arm_dds).
 // Every chunk is a regular chunk: the samples in front of the call come from `edge` = [input history | first 2048
 // samples of the call], which is all zeros in front of the start of the stream (frames before time 0 contribute +-0).
+#ifndef K4_REGS_FFT
+#define K4_REGS_FFT 64
+#endif
+#ifndef K4_REGS_PFB
+#define K4_REGS_PFB 40
+#endif
+#ifndef K4_REGS_CHAN
+#define K4_REGS_CHAN 88
+#endif
+#define K4_STR2(x) #x
+#define K4_STR(x) K4_STR2(x)
 constexpr int WS_THREADS = 1024;
 constexpr int WS_NBUF = 4;
 constexpr int WS_ADC_STAGES = 6, WS_DDS_STAGES = 5;       // 8 KiB each; with the exchange buffers 227 KiB of shared memory
@@ -269,7 +280,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
 
     if (tid < 2 * NCH) {
         // =============================== FFT groups ===============================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " K4_STR(K4_REGS_FFT) ";");
         const int g = tid >> 8, lt = tid & 255, j = lt & 15;
         for (int kb = g; kb < n_blocks; kb += 2) {
             const int buf = kb % WS_NBUF;
@@ -307,7 +318,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
 
     if (tid < 3 * NCH) {
         // =============================== PFB: polyphase filter + first radix-2 stage ===============================
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 " K4_STR(K4_REGS_PFB) ";");
         if (n_blocks == 0) return;
         const int k = tid - 2 * NCH;                                  // branches k and k + 256
         float hA[PTAPS], hB[PTAPS];
@@ -363,7 +374,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
     }
 
     // =============================== CHAN: thread = channel ===============================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 " K4_STR(K4_REGS_CHAN) ";");
     if (n_blocks == 0) return;
     const int c = tid - 3 * NCH;                                  // channel
     const int bin = d.bins[board * NCH + c];
