@@ -193,16 +193,19 @@ __global__ void comb_prep_kernel(CombParams p, int batch, double2 *tw, double2 *
         if (kk < 0) kk += p.N;
         p.kbin[i] = kk;
     }
-    if (i < batch) {
+    if (i < batch * 32) {
         // The reference rounds 2*pi*f, the product with t, the division by fs and the sum with phi: four roundings of an
         // argument of up to 2 pi N rad, each below 2^-53 relative, independent from tone to tone.  The bulk IFFT has none
         // of them (its own error is ~1e-15 of the scale), so reference - bulk of one sample is a sum of T terms
         // a_n * (argument error): rms below 2.2e-16 * 2 pi N * sqrt(sum a_n^2) (twice the rms of four uniform roundings
         // at the LARGEST argument).  Candidates for the max and samples near a truncation boundary are taken within
-        // 8 of these sigmas and re-evaluated in the reference's order.
+        // 8 of these sigmas and re-evaluated in the reference's order.  (One warp per LUT set: a single thread walking
+        // the amplitudes made this 3 us kernel take 23 us.)
+        const int bset = i >> 5, lane = i & 31;
         double ss = 0.0;
-        for (int n = 0; n < p.T; ++n) { const double a = p.amp[(size_t)i * p.T + n]; ss += a * a; }
-        p.sigma[i] = 2.2e-16 * 6.283185307179586 * (double)p.N * sqrt(ss);
+        for (int n = lane; n < p.T; n += 32) { const double a = p.amp[(size_t)bset * p.T + n]; ss += a * a; }
+        for (int d = 16; d > 0; d >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, d);
+        if (lane == 0) p.sigma[bset] = 2.2e-16 * 6.283185307179586 * (double)p.N * sqrt(ss);
     }
 }
 
@@ -843,7 +846,7 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
     if ((rc = mkid_scratch(ctx, SCR_AUX2, ((size_t)N1 + TB) * 16 + (size_t)batch * (N2 + 2) * 8, (void **)&d_tw))) return rc;
     p.tw = d_tw; p.tone = d_tw + N1; p.sigma = (double *)(d_tw + N1 + TB); p.eps = p.sigma + batch; p.row_max = p.eps + batch;
     {
-        const int n_prep = (int)std::max<size_t>((size_t)N1, TB);      // (N1 - 4) / 3 table entries, TB tones
+        const int n_prep = (int)std::max<size_t>(std::max<size_t>((size_t)N1, TB), (size_t)batch * 32);      // (N1 - 4) / 3 table entries, TB tones, a warp per set
         comb_prep_kernel<<<(n_prep + 255) / 256, 256, 0, ctx->stream>>>(p, batch, d_tw, d_tw + N1);
         MKID_CHECK_LAUNCH(ctx);
     }
