@@ -114,6 +114,51 @@ def test_full_chain_against_float64_oracle(ctx):
     ch.close()
 
 
+@pytest.mark.parametrize('fir,M,L,W,centers,thr', [
+    ('HammingFilter_250kHz', 8, 40, 16, True, -2200),
+    ('BlackmanFilter_250kHz', 32, 1000, 32, False, -2500),
+    ('RectFilter_250kHz', 4, 32, 8, True, -3000),
+    ('matched_30us', 20, 64, 60, True, -2500),
+])
+def test_parameter_sweep_against_float64_oracle(ctx, fir, M, L, W, centers, thr):
+    """Other FIR tap files of the reference (LUT/*.txt), baseline lengths, hold-offs, peak windows (incl. the limits
+    M = 4 / 32, L = 32, W = 60) and IQ centres: phase within 1e-5 rad of the float64 model, emission bit-exact on the GPU's
+    own rows (two consecutive calls: the streaming state is carried), every trigger that differs from the model's explained."""
+    cfg, ks = board_config(n_tones=24, seed=5, M=M, L=L, W=W, thr=thr, fir=fir, centers=centers)
+    n = 2 ** 20
+    iq = _synth(ctx, ks[None, :], n, cfg.N_lut, seed=13, pulse_rate=5000.)
+    ch = make_gpu_channelizer([cfg], ctx)
+    T = n // 512
+    half = n // 2
+    f32 = ctx.alloc((half // 512) * 256 * 4)
+    ch.set_f32_phase_out(f32)
+    w1, r1 = ch.process(iq[:, :half].copy(), want_phase=True)
+    ph_gpu = f32.download(np.float32).reshape(half // 512, 256).astype(np.float64)
+    ch.set_f32_phase_out(None)
+    w2, r2 = ch.process(iq[:, half:].copy(), want_phase=True)
+    raw_gpu = np.concatenate([r1[0], r2[0]])
+    w_gpu = np.concatenate([w1[0], w2[0]])
+    ph_ref, raw_ref, w = oc.channelize_phase(iq[0], cfg, return_w=True)
+    act = ~cfg.zero_ch
+    amp = np.hypot(w.real - 8.0 * cfg.centers_i, w.imag - 8.0 * cfg.centers_q)
+    ok = amp[64:half // 512, act] > 2.0
+    d = np.abs(np.angle(np.exp(1j * (ph_gpu - ph_ref[:half // 512])))[64:, act])
+    assert d[ok].max() <= 1e-5, d[ok].max()
+    dq = (raw_gpu.astype(np.int64) - raw_ref.astype(np.int64))[64:, act]
+    dq = (dq + 25736) % 51472 - 25736
+    assert np.abs(dq).max() <= 1 and (dq != 0).mean() < 0.01
+    # emission: bit-exact on the GPU's own rows (the two calls together resolve the rows the single stream does) ...
+    own = oc.detect_emit(raw_gpu, cfg, 0, np.zeros(256, np.int64), T - 64 - cfg.M)
+    assert np.array_equal(w_gpu, np.array(own, dtype=np.uint64)), (len(w_gpu), len(own))
+    # ... and against the model end to end
+    r = compare_words_with_model(w_gpu, raw_gpu, raw_ref, cfg, T)
+    print('\n[%s M=%d L=%d W=%d] %d oracle words, %d GPU words, %d triggers differ (%d marginal, %d shadow), %d common words differ'
+          % (fir, M, L, W, r['n_ref'], r['n_gpu'], r['only'], r['marginal'], r['shadow'], r['word_diff']))
+    assert r['n_ref'] > 20 and not r['unexplained'], r
+    assert r['only'] <= max(2, 0.01 * r['n_ref']) and r['word_diff'] <= max(2, 0.01 * r['common'])
+    ch.close()
+
+
 def test_word_buffer_overflow_keeps_the_stream_consistent(ctx):
     """A word buffer that is too small is an error, but the call completes: hold-off times, input history and time are
     those of a finished call, so the NEXT call gives exactly what it gives after an undisturbed one; asynchronous calls
