@@ -359,6 +359,17 @@ def main():
         sampler.stop_flag = True
     del pin_words, pin_counts
     fir_int = np.array(chain.fir_int)
+    # the channelizer kernel by itself (same launch: K4 + fused candidate mask, nothing else on the GPU): inside the
+    # two-stream step its duration includes the moments it shares SMs with the detection tail of the previous batch
+    k4_alone_ms = None
+    try:
+        chain.join(); ctx.sync()
+        for _ in range(12):
+            ctx._check(ctx.lib.mkid_chan_process(ctx.h, chain.chan.h, _lib.ptr(leg.iq), int(n), 2, None, 0, None, None))
+        ctx.sync()
+        k4_alone_ms = chain.chan.kernel_ms_sum(10) / 10
+    except Exception:
+        k4_alone_ms = None
     leg.free()
     stage('end-to-end done')
 
@@ -416,6 +427,8 @@ def main():
             'roofline': {'bound': 'hbm', 'kernel': 'channelize_ws_kernel', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
                          'kernel_ms_per_launch': res['k4_ms'], 'kernel_share_of_step': res['k4_ms'] / res['step_ms'],
+                         'kernel_ms_alone': k4_alone_ms,
+                         'frac_alone': (BYTES_PER_SAMPLE * B * n / (k4_alone_ms * 1e-3) / 1e9 / peak) if k4_alone_ms else None,
                          'note': 'algorithmic 4 B per complex ADC sample; the kernel is bound by the FP32 pipe / issue slots / shared '
                                  'memory together, not by HBM (111 FP32 lane operations per sample: FP32 roof = 0.20 of the HBM roof, '
                                  'see DESIGN.md)'},
