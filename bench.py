@@ -703,7 +703,7 @@ def decode_side_bench(ctx, peak):
 
 def lut_side_bench(ctx):
     """BASELINE config 1: 256 tones, 2^19-sample int16 I/Q comb + DDS LUT + DRAM image."""
-    from mkids_sdr_b200 import lut
+    from mkids_sdr_b200 import _lib, lut
     N, T = 2 ** 19, 256
     k = np.sort(np.random.default_rng(0).choice(np.arange(-N // 2 + 1, N // 2), T, replace=False))
     f = (k % N) * FS / N
@@ -733,27 +733,39 @@ def lut_side_bench(ctx):
     # everything left in HBM
     res = FS / N
     resid = np.rint((f - np.rint(f * 512 / FS) * FS / 512) / res) * res      # select_bins (ROACH_Setup.py:534-550)
+    ctx2 = _lib.Context(ctx.device)                  # second stream: the DDS tables do not depend on the comb
     for batch in (1, 64):
         ff = np.tile(f, (batch, 1)); aa = np.tile(amps, (batch, 1)); rr = np.tile(resid, (batch, 1))
+        zz = np.zeros_like(rr)
         bufs = [ctx.alloc(batch * N * 2) for _ in range(4)]
         img = ctx.alloc(batch * N * 8)
 
         def one():
             lut.comb_lut(ff, FS, N, aa, ctx=ctx, out_I=bufs[0], out_Q=bufs[1])
-            lut.dds_lut(rr, np.zeros_like(rr), FS, N, ctx=ctx, out_I=bufs[2], out_Q=bufs[3])
+            lut.dds_lut(rr, zz, FS, N, ctx=ctx, out_I=bufs[2], out_Q=bufs[3])
             lut.pack_dram(bufs[0], bufs[1], bufs[2], bufs[3], ctx=ctx, n=batch * N, out=img)
-        one()
-        ctx.sync()
-        t0 = time.time()
-        reps = 5
-        for _ in range(reps):
-            one()
-        ctx.sync()
-        dt = (time.time() - t0) / reps
-        out['full_set_batch%d_device' % batch] = {'luts_per_s': batch / dt, 'ms_per_call': dt * 1e3,
-                                                  'GB/s_written': batch * N * 16 / dt / 1e9}
+
+        def one_two_streams():
+            # the 256 DDS tables of every set on the second context while the first one synthesises the comb; the DRAM
+            # image waits for both
+            lut.dds_lut(rr, zz, FS, N, ctx=ctx2, out_I=bufs[2], out_Q=bufs[3], want_scales=False)
+            ctx2.record(50)
+            lut.comb_lut(ff, FS, N, aa, ctx=ctx, out_I=bufs[0], out_Q=bufs[1])
+            ctx.wait_event(ctx2, 50)
+            lut.pack_dram(bufs[0], bufs[1], bufs[2], bufs[3], ctx=ctx, n=batch * N, out=img)
+        for name, fn in (('full_set_batch%d_device' % batch, one), ('full_set_batch%d_device_two_streams' % batch, one_two_streams)):
+            fn()
+            ctx.sync(); ctx2.sync()
+            t0 = time.time()
+            reps = 5
+            for _ in range(reps):
+                fn()
+            ctx.sync(); ctx2.sync()
+            dt = (time.time() - t0) / reps
+            out[name] = {'luts_per_s': batch / dt, 'ms_per_call': dt * 1e3, 'GB/s_written': batch * N * 16 / dt / 1e9}
         for v in bufs + [img]:
             v.free()
+    ctx2.close()
     out['workload'] = ('256 tones, 2^19-sample int16 I/Q comb (freqCombLUT incl. seed-1000 phases, scale, exact quantisation); '
                        'full_set = comb + 256 DDS tables + DRAM image (16 B per sample written)')
     return out

@@ -41,9 +41,11 @@ def comb_lut(freqs, sample_rate, n_samples, amplitudes, phases=None, echo='yes',
     return I, Q, scale, ph
 
 
-def dds_lut(residuals, phases, sample_rate, n_lut, ch_shift=CH_SHIFT, offset=0, ctx=None, out_I=None, out_Q=None):
+def dds_lut(residuals, phases, sample_rate, n_lut, ch_shift=CH_SHIFT, offset=0, ctx=None, out_I=None, out_Q=None,
+            want_scales=True):
     """Batched define_DDS_LUT tables.  residuals/phases [batch][256] -> (I_dds, Q_dds int16 [batch][n_lut], scales).
-    out_I / out_Q: optional device buffers (int16 [batch][n_lut]) that receive the tables instead of host arrays."""
+    out_I / out_Q: optional device buffers (int16 [batch][n_lut]) that receive the tables instead of host arrays.
+    want_scales=False (device outputs only): the call does not synchronise and returns no scales."""
     ctx = ctx or _lib.default_context()
     r = np.ascontiguousarray(np.atleast_2d(np.asarray(residuals, dtype=np.float64)))
     batch = r.shape[0]
@@ -51,7 +53,7 @@ def dds_lut(residuals, phases, sample_rate, n_lut, ch_shift=CH_SHIFT, offset=0, 
     assert r.shape[1] == 256
     I = out_I if out_I is not None else np.empty((batch, n_lut), dtype=np.int16)
     Q = out_Q if out_Q is not None else np.empty((batch, n_lut), dtype=np.int16)
-    sc = np.empty((batch, 256), dtype=np.float64)
+    sc = np.empty((batch, 256), dtype=np.float64) if want_scales else None
     ctx._check(ctx.lib.mkid_dds_lut(ctx.h, _lib.ptr(r), _lib.ptr(p), float(sample_rate), int(n_lut), int(ch_shift), int(offset), batch,
                                     _lib.ptr(I), _lib.ptr(Q), _lib.ptr(sc)))
     return I, Q, sc
