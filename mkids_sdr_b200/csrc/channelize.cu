@@ -169,6 +169,15 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
 #ifndef K4_REGS_CHAN
 #define K4_REGS_CHAN 88
 #endif
+// Experiment switch -DK4_CHAN_MIX=0: the FFT group that transformed a block also gathers every channel's bin from it, mixes
+// it with the DDS value (thread = channel) and leaves y[frame][channel] in the block's exchange buffer, so that the channel
+// role starts from eight coalesced loads.  Output bit-identical, 70 instructions less in the channel role per block -- and
+// 1.25 -> 1.49 ms: the two group-wide barriers and the longer FFT stage stretch the time a block holds its exchange
+// buffer beyond what 4 buffers cover (the pipeline is bound by the latency of a block through the roles, not by the
+// instruction count of the busiest role).  Default: gather and mix in the channel role.
+#ifndef K4_CHAN_MIX
+#define K4_CHAN_MIX 1
+#endif
 #define K4_STR2(x) #x
 #define K4_STR(x) K4_STR2(x)
 constexpr int WS_THREADS = 1024;
@@ -282,6 +291,23 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
         // =============================== FFT groups ===============================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 " K4_STR(K4_REGS_FFT) ";");
         const int g = tid >> 8, lt = tid & 255, j = lt & 15;
+#if !K4_CHAN_MIX
+        // gather / mix stage of this group's blocks: thread lt = channel lt
+        const int bin_c = d.bins[board * NCH + lt];
+        const int par_c = bin_c & 1;
+        const int zoff_c = par_c * FFT_STRIDE + (bin_c >> 1);
+        const int ld_mask_f = d.Ld - 1;
+        const uint32_t *dds_blk_f = d.dds + (size_t)board * d.Ld * NCH;
+        const int dds_row0_f = (int)((p.f0_abs + fb_first) & ld_mask_f);
+        auto arm_dds_f = [&](int kb) {                            // elected thread: block kb -> stage kb mod 5
+            const int st = kb % WS_DDS_STAGES;
+            const int row = (dds_row0_f + kb * FB) & ld_mask_f;
+            mk_mbar_expect_tx(&dds_full[st], FB * NCH * 4);
+            mk_bulk_g2s(s_dds + st * FB * NCH, dds_blk_f + (size_t)row * NCH, FB * NCH * 4, &dds_full[st]);
+        };
+        if (tid == 0)
+            for (int b0 = 0; b0 < WS_DDS_STAGES && b0 < n_blocks; ++b0) arm_dds_f(b0);
+#endif
         for (int kb = g; kb < n_blocks; kb += 2) {
             const int buf = kb % WS_NBUF;
             ho_wait(HO_U_FULL(buf), (uint32_t)((kb / WS_NBUF) & 1));
@@ -311,6 +337,35 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
             for (int k1 = 0; k1 < 4; ++k1)
 #pragma unroll
                 for (int k2 = 0; k2 < 4; ++k2) reg[j + 16 * (4 * k1 + k2)] = v[4 * k2 + k1];
+#if !K4_CHAN_MIX
+            // every spectrum of the block is in place: gather this channel's bin of the 8 frames, remove the half-frame hop
+            // phase of odd bins ((-1)^(bin*(f_abs+1)); f_abs of frame i has the parity of i), mix with conj(dds)
+            asm volatile("bar.sync %0, %1;" ::"r"(13 + g), "r"(NCH) : "memory");
+            {
+                const float2 *zsrc = s_u + buf * 16 * FFT_STRIDE + zoff_c;
+                float2 z[FB], y[FB];
+#pragma unroll
+                for (int i = 0; i < FB; ++i) z[i] = zsrc[(2 * i) * FFT_STRIDE];
+                const int st = kb % WS_DDS_STAGES;
+                mk_mbar_wait_sleep(&dds_full[st], (uint32_t)((kb / WS_DDS_STAGES) & 1));
+                const uint32_t *dds_c = s_dds + st * FB * NCH + lt;
+#pragma unroll
+                for (int i = 0; i < FB; ++i) {
+                    const float2 dvi = unpack(dds_c[i * NCH]);      // zeroed channels hold (0, 0): y = +-0, w = +0 as in the model
+                    float2 zz = z[i];
+                    if ((i & 1) == 0 && par_c) { zz.x = -zz.x; zz.y = -zz.y; }     // even i: f_abs + 1 odd
+                    y[i].x = zz.x * dvi.x + zz.y * dvi.y;
+                    y[i].y = zz.y * dvi.x - zz.x * dvi.y;
+                }
+                // all gathers of the group are done (and its DDS values read): the mixed samples replace the spectra,
+                // y[frame][channel] at the start of the buffer; the DDS stage is re-armed five blocks ahead
+                asm volatile("bar.sync %0, %1;" ::"r"(13 + g), "r"(NCH) : "memory");
+                if (lt == 0 && kb + WS_DDS_STAGES < n_blocks) arm_dds_f(kb + WS_DDS_STAGES);
+                float2 *ydst = s_u + buf * 16 * FFT_STRIDE + lt;
+#pragma unroll
+                for (int i = 0; i < FB; ++i) ydst[i * NCH] = y[i];
+            }
+#endif
             ho_arrive(HO_X_DONE(buf));
         }
         return;
@@ -398,8 +453,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
         mk_mbar_expect_tx(&dds_full[st], FB * NCH * 4);
         mk_bulk_g2s(s_dds + st * FB * NCH, dds_blk + (size_t)row * NCH, FB * NCH * 4, &dds_full[st]);
     };
+#if K4_CHAN_MIX
     if (c == 0)
         for (int b0 = 0; b0 < WS_DDS_STAGES && b0 < n_blocks; ++b0) arm_dds(b0);
+#endif
     // ---- state in chunk-relative rows (32-bit): row r = row0 + rl
     const int n_rows = (int)(row1 - row0);
     const int rl_start = (int)(r_start - row0);                       // <= 0: first computed row
@@ -424,6 +481,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
         // gather the bin, remove the half-frame hop phase of odd bins ((-1)^(bin*(f_abs+1)); f_abs of
         // frame i has the parity of i because block starts and call starts are even), mix with conj(dds)
         float2 y[FB];
+#if K4_CHAN_MIX
         const float2 *zsrc = xbuf + zoff;
         float2 z[FB];
 #pragma unroll
@@ -436,6 +494,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
             y[i].x = zz.x * dvi.x + zz.y * dvi.y;
             y[i].y = zz.y * dvi.x - zz.x * dvi.y;
         }
+#else
+        // the FFT group has left the mixed samples y[frame][channel] in the buffer: coalesced, conflict-free loads
+#pragma unroll
+        for (int i = 0; i < FB; ++i) y[i] = xbuf[i * NCH + c];
+#endif
         ho_arrive(free_bar);                                      // the bins of this block are in registers: the buffer may be refilled
         // output t = fb/2 + m uses frames 2t+1-25+k, k = 0..25: frame fb+i carries tap k = i - 2m + 24
 #pragma unroll
@@ -512,9 +575,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
         ho_wait(HO_X_DONE(buf), (uint32_t)((kb / WS_NBUF) & 1));
         // x_done(kb) follows u_full(kb), which follows u_free(kb - 4): EVERY CHAN thread has read the DDS values of block
         // kb - 4, so that stage can be refilled (5 stages: block kb + 1 goes there) without a barrier
-        if (c == 0 && kb >= WS_NBUF && kb + 1 < n_blocks) arm_dds(kb + 1);
         const int st = kb % WS_DDS_STAGES;
+#if K4_CHAN_MIX
+        if (c == 0 && kb >= WS_NBUF && kb + 1 < n_blocks) arm_dds(kb + 1);
         mk_mbar_wait_sleep(&dds_full[st], (uint32_t)((kb / WS_DDS_STAGES) & 1));
+#endif
         channel_stage(RBc, s_u + buf * 16 * FFT_STRIDE, s_dds + st * FB * NCH + c, HO_U_FREE(buf));
         rl += 4;
     };
