@@ -181,8 +181,36 @@ __device__ __forceinline__ float atan2_fast(float y, float x) {
 #define K4_STR2(x) #x
 #define K4_STR(x) K4_STR2(x)
 constexpr int WS_THREADS = 1024;
-constexpr int WS_NBUF = 4;
-constexpr int WS_ADC_STAGES = 6, WS_DDS_STAGES = 5;       // 8 KiB each; with the exchange buffers 227 KiB of shared memory
+// Experiment switch -DK4_DDS_LDG=1: the channel role reads its DDS words straight from the L2-resident table (8 coalesced
+// 4-byte loads per block and thread, prefetched one block ahead in registers) instead of through TMA stages, so that the
+// 40 KiB of stages can become a FIFTH exchange buffer.  Measured (bit-identical output): the loads alone cost 1.25 -> 1.37 ms
+// at 4 buffers, with 5 buffers (and the ADC refill only one block ahead) 1.41 ms.  The number of exchange buffers does
+// matter -- 3 buffers: 1.35 ms, 4 buffers: 1.25 ms -- but a fifth one does not fit next to the TMA stages (226 of 227 KiB).
+#ifndef K4_DDS_LDG
+#define K4_DDS_LDG 0
+#endif
+#ifndef K4_NBUF
+#define K4_NBUF (K4_DDS_LDG ? 5 : 4)
+#endif
+#ifndef K4_ADC_STAGES
+#define K4_ADC_STAGES 6
+#endif
+#if K4_DDS_LDG
+constexpr int WS_NBUF = K4_NBUF;
+constexpr int WS_ADC_STAGES = K4_ADC_STAGES, WS_DDS_STAGES = 0;       // 8 KiB each; with the exchange buffers 220 KiB of shared memory
+#else
+#ifndef K4_DDS_STAGES
+#define K4_DDS_STAGES 5
+#endif
+constexpr int WS_NBUF = K4_NBUF;
+constexpr int WS_ADC_STAGES = K4_ADC_STAGES, WS_DDS_STAGES = K4_DDS_STAGES;       // 8 KiB each; with the exchange buffers 227 KiB of shared memory
+static_assert(K4_DDS_STAGES == K4_NBUF + 1, "the DDS stage of block kb + 1 is refilled at x_done(kb): NBUF + 1 stages");
+#endif
+constexpr int WS_ADC_AHEAD = WS_ADC_STAGES - WS_NBUF;     // blocks the ADC stage refill runs ahead of the PFB role
+static_assert(WS_ADC_AHEAD >= 1 && 3 * WS_NBUF + 1 <= 16, "stage / barrier budget");
+#if !K4_CHAN_MIX && K4_DDS_LDG
+#error "the K4_CHAN_MIX=0 experiment needs the DDS stages (-DK4_DDS_LDG=0)"
+#endif
 
 struct WsParams {
     ChanDev d;
@@ -403,9 +431,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
             const int buf = blk % WS_NBUF;
             if (blk >= WS_NBUF) {
                 ho_wait(HO_U_FREE(buf), (uint32_t)((blk / WS_NBUF - 1) & 1));   // CHAN has gathered block blk - 4
-                // u_free(blk - 4) follows x_done(blk - 4), which follows u_full(blk - 4): EVERY PFB thread has finished
-                // block blk - 4, so its ADC stage can be refilled (6 stages: block blk + 2 goes there) without a barrier
-                if (k == 0 && blk + 2 < n_blocks) arm_adc(blk + 2);
+                // u_free(blk - NBUF) follows x_done(blk - NBUF), which follows u_full(blk - NBUF): EVERY PFB thread has
+                // finished block blk - NBUF, so its ADC stage can be refilled (block blk + STAGES - NBUF goes there) without
+                // a barrier
+                if (k == 0 && blk + WS_ADC_AHEAD < n_blocks) arm_adc(blk + WS_ADC_AHEAD);
             }
             const int st = blk % WS_ADC_STAGES;
             mk_mbar_wait_sleep(&adc_full[st], (uint32_t)((blk / WS_ADC_STAGES) & 1));
@@ -447,6 +476,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
     const int ld_mask = d.Ld - 1;                               // Ld is a power of two
     const uint32_t *dds_blk = d.dds + (size_t)board * d.Ld * NCH;
     const int dds_row0 = (int)((p.f0_abs + fb_first) & ld_mask);   // f_abs mod Ld of the first frame of block 0
+#if K4_DDS_LDG
+    // DDS words of a block: frames kb*8 .. kb*8+7 of this channel (the rows of a block never wrap: block starts are
+    // multiples of 8 frames), from the L2-resident table
+    auto load_dds = [&](int kb, uint32_t (&dst)[FB]) {
+        const uint32_t *src = dds_blk + (size_t)((dds_row0 + kb * FB) & ld_mask) * NCH + c;
+#pragma unroll
+        for (int i = 0; i < FB; ++i) dst[i] = __ldg(src + i * NCH);
+    };
+    uint32_t ddsA[FB], ddsB[FB];
+    load_dds(0, ddsA);
+#else
     auto arm_dds = [&](int kb) {                                  // elected thread: block kb -> stage kb mod 5
         const int st = kb % WS_DDS_STAGES;
         const int row = (dds_row0 + kb * FB) & ld_mask;
@@ -456,6 +496,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
 #if K4_CHAN_MIX
     if (c == 0)
         for (int b0 = 0; b0 < WS_DDS_STAGES && b0 < n_blocks; ++b0) arm_dds(b0);
+#endif
 #endif
     // ---- state in chunk-relative rows (32-bit): row r = row0 + rl
     const int n_rows = (int)(row1 - row0);
@@ -475,7 +516,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
 #pragma unroll
     for (int m = 0; m < 16; ++m) acc[m] = make_float2(0.f, 0.f);
 
-    auto channel_stage = [&](auto RBc, const float2 *xbuf, const uint32_t *dds_c, HandOver free_bar) {
+    auto channel_stage = [&](auto RBc, const float2 *xbuf, auto dds_at, HandOver free_bar) {
         constexpr int RB = decltype(RBc)::value;
         constexpr int A0 = RB / 2;                                       // slot of output m = 0
         // gather the bin, remove the half-frame hop phase of odd bins ((-1)^(bin*(f_abs+1)); f_abs of
@@ -488,7 +529,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
         for (int i = 0; i < FB; ++i) z[i] = zsrc[(2 * i) * FFT_STRIDE];
 #pragma unroll
         for (int i = 0; i < FB; ++i) {
-            const float2 dvi = unpack(dds_c[i * NCH]);          // zeroed channels hold (0, 0): y = +-0, w = +0 as in the model
+            const float2 dvi = unpack(dds_at(i));               // zeroed channels hold (0, 0): y = +-0, w = +0 as in the model
             float2 zz = z[i];
             if ((i & 1) == 0 && par) { zz.x = -zz.x; zz.y = -zz.y; }         // even i: f_abs + 1 odd
             y[i].x = zz.x * dvi.x + zz.y * dvi.y;
@@ -570,6 +611,24 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
 
     // The ring phase of block kb is 8 * (kb mod 4) (fb_first is a multiple of 32 frames): four statically addressed
     // copies in sequence, so that the accumulators never move between registers.
+#if K4_DDS_LDG
+    auto one_block = [&](auto RBc, int kb, uint32_t (&cur)[FB], uint32_t (&nxt)[FB]) {
+        const int buf = kb % WS_NBUF;
+        if (kb + 1 < n_blocks) load_dds(kb + 1, nxt);            // in flight while this block is awaited and gathered
+        ho_wait(HO_X_DONE(buf), (uint32_t)((kb / WS_NBUF) & 1));
+        channel_stage(RBc, s_u + buf * 16 * FFT_STRIDE, [&](int i) { return cur[i]; }, HO_U_FREE(buf));
+        rl += 4;
+    };
+    for (int kb = 0; kb < n_blocks; kb += 4) {
+        one_block(std::integral_constant<int, 0>{}, kb, ddsA, ddsB);
+        if (kb + 1 >= n_blocks) break;
+        one_block(std::integral_constant<int, 8>{}, kb + 1, ddsB, ddsA);
+        if (kb + 2 >= n_blocks) break;
+        one_block(std::integral_constant<int, 16>{}, kb + 2, ddsA, ddsB);
+        if (kb + 3 >= n_blocks) break;
+        one_block(std::integral_constant<int, 24>{}, kb + 3, ddsB, ddsA);
+    }
+#else
     auto one_block = [&](auto RBc, int kb) {
         const int buf = kb % WS_NBUF;
         ho_wait(HO_X_DONE(buf), (uint32_t)((kb / WS_NBUF) & 1));
@@ -580,7 +639,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
         if (c == 0 && kb >= WS_NBUF && kb + 1 < n_blocks) arm_dds(kb + 1);
         mk_mbar_wait_sleep(&dds_full[st], (uint32_t)((kb / WS_DDS_STAGES) & 1));
 #endif
-        channel_stage(RBc, s_u + buf * 16 * FFT_STRIDE, s_dds + st * FB * NCH + c, HO_U_FREE(buf));
+        const uint32_t *dds_c = s_dds + st * FB * NCH + c;
+        channel_stage(RBc, s_u + buf * 16 * FFT_STRIDE, [&](int i) { return dds_c[i * NCH]; }, HO_U_FREE(buf));
         rl += 4;
     };
     for (int kb = 0; kb < n_blocks; kb += 4) {
@@ -592,6 +652,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
         if (kb + 3 >= n_blocks) break;
         one_block(std::integral_constant<int, 24>{}, kb + 3);
     }
+#endif
 }
 
 // edge[b] = [history (H samples) | first 2048 samples of this call]
