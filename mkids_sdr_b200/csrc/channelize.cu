@@ -1438,6 +1438,19 @@ int detect_and_fetch(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase_buf, con
 }
 }  // namespace
 
+namespace {
+// one thread that holds its stream for `ns` nanoseconds (two-context pipeline: lets the channelizer kernel of the next batch
+// take its SMs before the detection tail of this batch spreads over them)
+__global__ void delay_kernel(unsigned ns) {
+    unsigned long long t0, t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    do {
+        __nanosleep(1000);
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    } while (t - t0 < ns);
+}
+}  // namespace
+
 extern "C" int mkid_chan_set_pipelined(mkid_ctx *ctx, mkid_chan *ch, int32_t on) {
     if (!ctx) return MKID_EINVAL;
     MKID_REQUIRE(ctx, ch, "chan_set_pipelined: NULL");
@@ -1454,6 +1467,17 @@ extern "C" int mkid_chan_detect_pending(mkid_ctx *ctx, mkid_chan *ch, uint64_t *
     const mkid_chan::Pending pd = ch->pending;
     ch->pending.valid = false;
     int64_t need = 0;
+    if (ch->alternate) {
+        // Two-context pipeline.  This call's first kernel (resolve) becomes ready when the channelizer kernel of the batch
+        // ends, 13 us before the next channelizer kernel is launched (edge / history copies), and spreads over every SM: the
+        // next K4 then waits for SMs (1.25 -> 1.29 ms with 8 boards).  Holding the tail back for 20 us lets K4 take its 144
+        // SMs first and confines the tail to the 4 free ones -- which it can afford with 1 or 2 boards per GPU (per step
+        // 0.214 -> 0.200 and 0.372 -> 0.356 ms) but not with 4 or 8 (0.671 -> 0.729, 1.305 -> 1.339 ms: there the tail on 4
+        // SMs takes longer than K4).  MKID_TAIL_DELAY_US overrides.
+        int delay_us = ch->d.n_boards <= 2 ? 20 : 0;
+        if (const char *e = getenv("MKID_TAIL_DELAY_US")) delay_us = atoi(e);
+        if (delay_us > 0) { delay_kernel<<<1, 1, 0, ctx->stream>>>((unsigned)delay_us * 1000u); MKID_CHECK_LAUNCH(ctx); }
+    }
     int rc = detect_and_fetch(ctx, ch, ch->phase_set[pd.set], ch->mask_set[pd.set], pd.rows, pd.T, pd.t_abs0, words, words_cap, n_words, &need);
     if (rc) return rc;
     if (need) return mkid_fail(ctx, MKID_EINVAL, "word buffer too small: need %lld per board, have %lld (the words beyond the capacity are lost)",
