@@ -47,6 +47,9 @@ struct ChanDev {                         // device-resident configuration + stat
     uint32_t *hist;       // [B][H + 2048] input history (packed int16 I,Q), then the first 2048 samples of the current call
     int64_t *t_next;      // [B][256]
     int H;
+    // board b: the half-frame hop sign of odd bins, (-1)^(bin (f + 1)), is folded into the DDS rows with even index (always,
+    // unless a table holds -32768 where it would have to be negated: then the kernel applies the sign itself)
+    unsigned char fold[64];
 };
 
 }  // namespace
@@ -278,7 +281,8 @@ __device__ __forceinline__ void ho_wait(HandOver h, uint32_t parity) { mk_mbar_w
 #define HO_U_FREE(buf) (&u_free[buf])
 #endif
 
-template <bool F32>
+// FOLD: every board's DDS rows carry the hop sign of odd bins (ChanDev::fold): the channel role has no sign code at all
+template <bool F32, bool FOLD>
 __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     float2 *s_u = reinterpret_cast<float2 *>(smem_raw);                           // [4][16][FFT_STRIDE]
@@ -381,7 +385,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
                 for (int i = 0; i < FB; ++i) {
                     const float2 dvi = unpack(dds_c[i * NCH]);      // zeroed channels hold (0, 0): y = +-0, w = +0 as in the model
                     float2 zz = z[i];
-                    if ((i & 1) == 0 && par_c) { zz.x = -zz.x; zz.y = -zz.y; }     // even i: f_abs + 1 odd
+                    if ((i & 1) == 0 && par_c && !d.fold[board]) { zz.x = -zz.x; zz.y = -zz.y; }     // even i: f_abs + 1 odd
                     y[i].x = zz.x * dvi.x + zz.y * dvi.y;
                     y[i].y = zz.y * dvi.x - zz.x * dvi.y;
                 }
@@ -464,6 +468,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
     const int bin = d.bins[board * NCH + c];
     const int par = bin & 1;
     const int zoff = par * FFT_STRIDE + (bin >> 1);                // + 2*i*FFT_STRIDE per frame, + buffer base
+    const bool hop_folded = d.fold[board] != 0;
     const float cen_i = d.cen_i[board * NCH + c], cen_q = d.cen_q[board * NCH + c];
     int16_t *phase = p.phase + (size_t)board * p.rows * NCH + c;
     // fused candidate mask (K5c): bit (r & 31) of mask[r >> 5][c] iff M*raw[r] - sum_{k=1..M} raw[r-k] < M*thr
@@ -527,13 +532,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
         float2 z[FB];
 #pragma unroll
         for (int i = 0; i < FB; ++i) z[i] = zsrc[(2 * i) * FFT_STRIDE];
+        if (FOLD) {                                             // (compile time) the sign of odd bins is in the DDS rows
 #pragma unroll
-        for (int i = 0; i < FB; ++i) {
-            const float2 dvi = unpack(dds_at(i));               // zeroed channels hold (0, 0): y = +-0, w = +0 as in the model
-            float2 zz = z[i];
-            if ((i & 1) == 0 && par) { zz.x = -zz.x; zz.y = -zz.y; }         // even i: f_abs + 1 odd
-            y[i].x = zz.x * dvi.x + zz.y * dvi.y;
-            y[i].y = zz.y * dvi.x - zz.x * dvi.y;
+            for (int i = 0; i < FB; ++i) {
+                const float2 dvi = unpack(dds_at(i));           // zeroed channels hold (0, 0): y = +-0, w = +0 as in the model
+                y[i].x = z[i].x * dvi.x + z[i].y * dvi.y;
+                y[i].y = z[i].y * dvi.x - z[i].x * dvi.y;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < FB; ++i) {
+                const float2 dvi = unpack(dds_at(i));
+                float2 zz = z[i];
+                if ((i & 1) == 0 && par && !hop_folded) { zz.x = -zz.x; zz.y = -zz.y; }         // even i: f_abs + 1 odd
+                y[i].x = zz.x * dvi.x + zz.y * dvi.y;
+                y[i].y = zz.y * dvi.x - zz.x * dvi.y;
+            }
         }
 #else
         // the FFT group has left the mixed samples y[frame][channel] in the buffer: coalesced, conflict-free loads
@@ -1001,14 +1015,22 @@ __global__ void update_history_kernel(uint32_t *hist, int H, const uint32_t *in,
         h[i] = x[n - H + i];
 }
 
-__global__ void pack_dds_kernel(const int16_t *I, const int16_t *Q, int n_lut, const float *gain, uint32_t *out) {
+// fold: the rows with even t of odd-bin channels are negated (the hop sign (-1)^(bin (f + 1)) of frame f = t mod Ld);
+// *unfoldable is set if a value that would have to be negated is -32768 (the caller then repacks without folding)
+__global__ void pack_dds_kernel(const int16_t *I, const int16_t *Q, int n_lut, const float *gain, const int16_t *bins, int fold,
+                                uint32_t *out, int *unfoldable) {
     // out[t][m] = lut[(t/2)*512 + 2*((m+154)%256) + (t&1)]   (define_DDS_LUT layout, ROACH_Setup.py:526-530)
     const int Ld = n_lut / 256;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= Ld * NCH) return;
     const int t = idx / NCH, m = idx % NCH;
     const int src = (t >> 1) * 512 + 2 * ((m + 154) & 255) + (t & 1);
-    out[idx] = gain[m] != 0.f ? ((uint32_t)(uint16_t)I[src] | ((uint32_t)(uint16_t)Q[src] << 16)) : 0u;
+    int vi = I[src], vq = Q[src];
+    if (fold && (t & 1) == 0 && (bins[m] & 1) && gain[m] != 0.f) {
+        if (vi == -32768 || vq == -32768) *unfoldable = 1;
+        vi = -vi; vq = -vq;
+    }
+    out[idx] = gain[m] != 0.f ? ((uint32_t)(uint16_t)(int16_t)vi | ((uint32_t)(uint16_t)(int16_t)vq << 16)) : 0u;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1374,10 +1396,20 @@ extern "C" int mkid_chan_set_board(mkid_ctx *ctx, mkid_chan *ch, int32_t board, 
     MKID_CUDA(ctx, cudaMemcpyAsync(tmp, I_dds, (size_t)d.n_lut * 2, cudaMemcpyDefault, ctx->stream));
     MKID_CUDA(ctx, cudaMemcpyAsync(tmp + d.n_lut, Q_dds, (size_t)d.n_lut * 2, cudaMemcpyDefault, ctx->stream));
     const int total = d.Ld * NCH;
-    pack_dds_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(tmp, tmp + d.n_lut, d.n_lut, d.gain + (size_t)board * NCH,
-                                                                 d.dds + (size_t)board * d.Ld * NCH);
-    MKID_CHECK_LAUNCH(ctx);
-    MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int *unf = nullptr;
+    if ((rc = mkid_scratch(ctx, SCR_AUX2, 16, (void **)&unf))) return rc;
+    for (int fold = 1; fold >= 0; --fold) {          // folded hop sign; once more without it if a -32768 stands in the way
+        MKID_CUDA(ctx, cudaMemsetAsync(unf, 0, 4, ctx->stream));
+        pack_dds_kernel<<<(total + 255) / 256, 256, 0, ctx->stream>>>(tmp, tmp + d.n_lut, d.n_lut, d.gain + (size_t)board * NCH,
+                                                                     d.bins + (size_t)board * NCH, fold,
+                                                                     d.dds + (size_t)board * d.Ld * NCH, unf);
+        MKID_CHECK_LAUNCH(ctx);
+        int h_unf = 0;
+        MKID_CUDA(ctx, cudaMemcpyAsync(&h_unf, unf, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        d.fold[board] = (unsigned char)(fold && !h_unf);
+        if (!h_unf) break;
+    }
     ch->board_set[board] = true;
     return MKID_OK;
 }
@@ -1559,13 +1591,16 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
         edge_head_kernel<<<dim3(8, B), 256, 0, ctx->stream>>>(d.hist, d.H, in_dev, n);
         MKID_CHECK_LAUNCH(ctx);
         MKID_CUDA(ctx, cudaEventRecord(evp[0], ctx->stream));
-        if (ch->f32_out) {
-            MKID_CUDA(ctx, cudaFuncSetAttribute(channelize_ws_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            channelize_ws_kernel<true><<<dim3(w.chunks_per_board, B), WS_THREADS, smem, ctx->stream>>>(w);
-        } else {
-            MKID_CUDA(ctx, cudaFuncSetAttribute(channelize_ws_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            channelize_ws_kernel<false><<<dim3(w.chunks_per_board, B), WS_THREADS, smem, ctx->stream>>>(w);
-        }
+        bool all_fold = true;
+        for (int b = 0; b < B; ++b) all_fold = all_fold && d.fold[b];
+        auto launch = [&](auto kern) -> cudaError_t {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            kern<<<dim3(w.chunks_per_board, B), WS_THREADS, smem, ctx->stream>>>(w);
+            return cudaSuccess;
+        };
+        if (ch->f32_out) MKID_CUDA(ctx, all_fold ? launch(channelize_ws_kernel<true, true>) : launch(channelize_ws_kernel<true, false>));
+        else MKID_CUDA(ctx, all_fold ? launch(channelize_ws_kernel<false, true>) : launch(channelize_ws_kernel<false, false>));
         MKID_CHECK_LAUNCH(ctx);
     }
     MKID_CUDA(ctx, cudaEventRecord(evp[1], ctx->stream));

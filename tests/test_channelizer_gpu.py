@@ -159,6 +159,35 @@ def test_parameter_sweep_against_float64_oracle(ctx, fir, M, L, W, centers, thr)
     ch.close()
 
 
+def test_dds_table_with_minus_32768_uses_the_unfolded_kernel(ctx):
+    """The hop sign of odd bins is folded into the packed DDS rows (they are negated) unless a table holds -32768, which
+    cannot be negated in int16: that board is packed as it is and the kernel variant that applies the sign itself runs.  A
+    two-board channelizer with one such board: both boards within tolerance of the float64 model, which takes the tables
+    as they are; the clean board's rows are bit-identical to a run without the odd board."""
+    cfg_a, ks_a = board_config(n_tones=24, seed=3)
+    cfg_b, ks_b = board_config(n_tones=24, seed=4)
+    rng = np.random.default_rng(0)
+    pos = rng.choice(cfg_b.I_dds.size, 4000, replace=False)
+    cfg_b.I_dds = cfg_b.I_dds.copy(); cfg_b.Q_dds = cfg_b.Q_dds.copy()
+    cfg_b.I_dds[pos[:2000]] = -32768
+    cfg_b.Q_dds[pos[2000:]] = -32768
+    n = 2 ** 19
+    iq = _synth(ctx, np.stack([ks_a, ks_b]), n, cfg_a.N_lut, n_boards=2)
+    ch = make_gpu_channelizer([cfg_a, cfg_b], ctx)
+    _, raw = ch.process(iq, detect=False, want_phase=True)
+    ch.close()
+    for b, cfg in enumerate((cfg_a, cfg_b)):
+        _, raw_ref = oc.channelize_phase(iq[b], cfg)
+        act = ~cfg.zero_ch
+        dq = (raw[b].astype(np.int64) - raw_ref.astype(np.int64))[64:, act]
+        dq = (dq + 25736) % 51472 - 25736
+        assert np.abs(dq).max() <= 1 and (dq != 0).mean() < 0.01, (b, np.abs(dq).max(), (dq != 0).mean())
+    ch1 = make_gpu_channelizer([cfg_a], ctx)
+    _, raw1 = ch1.process(iq[:1].copy(), detect=False, want_phase=True)
+    ch1.close()
+    assert np.array_equal(raw1[0], raw[0])
+
+
 def test_word_buffer_overflow_keeps_the_stream_consistent(ctx):
     """A word buffer that is too small is an error, but the call completes: hold-off times, input history and time are
     those of a finished call, so the NEXT call gives exactly what it gives after an undisturbed one; asynchronous calls
