@@ -715,9 +715,12 @@ __global__ void __launch_bounds__(256) candidates_kernel(const int16_t *__restri
 // trips) and reduce it to one "word is non-zero" bit per (channel, word).  Lane 0 of warp w then walks the non-zero
 // words of channel w only: the per-trigger chain "next candidate at or after the end of the dead time" runs at
 // shared-memory latency and skips the dead time in one step.
-constexpr int RES_CH = 8;                             // channels per CTA (= warps)
-constexpr int RES_TW = 512;                           // mask words (x 32 rows) per tile
-__global__ void __launch_bounds__(256) resolve_kernel(const uint32_t *__restrict__ mask, int64_t rows, int64_t r_lo,
+// Two shapes.  RES_TW = 512 / 256 threads (a warp per channel, 4 tiles per 2^16 rows: the shortest latency when the kernel
+// has the GPU to itself) and RES_TW = 128 / 64 threads (four resolver lanes per warp, 8 KiB of tiles: 28 CTAs per SM instead
+// of 7, the better throughput when the kernel is confined to the few SMs the channelizer kernel of the next batch leaves).
+constexpr int RES_CH = 8;                             // channels per CTA
+template <int RES_TW>                                 // mask words (x 32 rows) per tile; RES_TW / 2 threads
+__global__ void __launch_bounds__(RES_TW / 2) resolve_kernel(const uint32_t *__restrict__ mask, int64_t rows, int64_t r_lo,
                                                       int64_t r_hi, int64_t t_abs0, int L, int Lw, int n_win,
                                                       int64_t *t_next, uint32_t *acc, uint32_t *win_cnt) {
     __shared__ __align__(16) uint32_t tile[2][RES_TW][RES_CH];
@@ -732,7 +735,7 @@ __global__ void __launch_bounds__(256) resolve_kernel(const uint32_t *__restrict
     const int n_tiles = (g_hi - g_lo + RES_TW - 1) / RES_TW;
     auto prefetch = [&](int k) {                       // tile k -> buffer k & 1: RES_TW rows of 2 x 16 B
         const int g0 = g_lo + k * RES_TW;
-        for (int i = tid; i < RES_TW * 2; i += 256) {
+        for (int i = tid; i < RES_TW * 2; i += RES_TW / 2) {
             const int u = i >> 1, q = i & 1;
             if (g0 + u < g_hi) {
                 const uint32_t dst = mk_smem_u32(&tile[k & 1][u][q * 4]);
@@ -744,9 +747,11 @@ __global__ void __launch_bounds__(256) resolve_kernel(const uint32_t *__restrict
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
     };
-    // resolver lanes: lane 0 of warp w owns channel c0 + w.  Rows are 32-bit inside a call.
-    const bool resolver = lane == 0;
-    const int cl = warp;                               // channel inside the CTA (resolver lanes)
+    // resolver lanes: 8 per CTA, spread evenly over its warps (lane 0 of each of 8 warps, or lanes 0, 8, 16, 24 of 2 warps);
+    // each owns channel c0 + cl.  Rows are 32-bit inside a call.
+    constexpr int RES_WARPS = RES_TW / 64, RES_STEP = 4 * RES_WARPS;
+    const bool resolver = (lane % RES_STEP) == 0;
+    const int cl = warp * (RES_CH / RES_WARPS) + lane / RES_STEP;      // channel inside the CTA (resolver lanes)
     const int c = c0 + cl;
     const int rlo = (int)r_lo, rhi = (int)r_hi;
     int64_t tn = 0;
@@ -1240,8 +1245,13 @@ int run_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase_dev, int64_t r
         MKID_CHECK_LAUNCH(ctx);
     }
     g_timer.mark(ctx->stream, "memsets");
-    resolve_kernel<<<dim3(NCH / RES_CH, B), 256, 0, ctx->stream>>>(mask, rows, r_lo, r_hi, t_abs0, d.L, d.Lw, n_win,
-                                                             d.t_next, ch->acc, ch->win_cnt);
+    // (two-context pipeline: this call runs beside the next channelizer kernel, on the few SMs it leaves)
+    if (ch->alternate && have_mask)
+        resolve_kernel<128><<<dim3(NCH / RES_CH, B), 64, 0, ctx->stream>>>(mask, rows, r_lo, r_hi, t_abs0, d.L, d.Lw, n_win,
+                                                                     d.t_next, ch->acc, ch->win_cnt);
+    else
+        resolve_kernel<512><<<dim3(NCH / RES_CH, B), 256, 0, ctx->stream>>>(mask, rows, r_lo, r_hi, t_abs0, d.L, d.Lw, n_win,
+                                                                      d.t_next, ch->acc, ch->win_cnt);
     MKID_CHECK_LAUNCH(ctx);
     g_timer.mark(ctx->stream, "resolve");
     scan_kernel<<<B, 256, 0, ctx->stream>>>(ch->win_cnt, n_win, r_lo, r_hi, t_abs0, d.Lw, ch->n_words_dev, words_cap, ch->n_words_dev + B);
@@ -1501,12 +1511,13 @@ extern "C" int mkid_chan_detect_pending(mkid_ctx *ctx, mkid_chan *ch, uint64_t *
     int64_t need = 0;
     if (ch->alternate) {
         // Two-context pipeline.  This call's first kernel (resolve) becomes ready when the channelizer kernel of the batch
-        // ends, 13 us before the next channelizer kernel is launched (edge / history copies), and spreads over every SM: the
-        // next K4 then waits for SMs (1.25 -> 1.29 ms with 8 boards).  Holding the tail back for 20 us lets K4 take its 144
-        // SMs first and confines the tail to the 4 free ones -- which it can afford with 1 or 2 boards per GPU (per step
-        // 0.214 -> 0.200 and 0.372 -> 0.356 ms) but not with 4 or 8 (0.671 -> 0.729, 1.305 -> 1.339 ms: there the tail on 4
-        // SMs takes longer than K4).  MKID_TAIL_DELAY_US overrides.
-        int delay_us = ch->d.n_boards <= 2 ? 20 : 0;
+        // ends, 13 us before the next channelizer kernel is launched (edge / history copies), and would spread over every SM:
+        // the next K4 then waits for SMs (1.24 -> 1.28 ms with 8 boards).  Holding the tail back for 20 us lets K4 take its
+        // 144 SMs first and confines the tail to the 4 free ones, where it needs 1.16 ms per batch of 8 boards at 1000
+        // triggers per second and channel (resolve in its small-tile shape 0.1 ms, emit 0.9 ms: one 32-byte sector per phase
+        // sample of a trigger) -- less than K4's 1.24 ms.  Per step, 1 / 2 / 4 / 8 boards: 0.214 -> 0.200, 0.372 -> 0.356,
+        // 0.677 -> 0.648, 1.296 -> 1.256 ms.  MKID_TAIL_DELAY_US overrides (0: the tail starts at once).
+        int delay_us = 20;
         if (const char *e = getenv("MKID_TAIL_DELAY_US")) delay_us = atoi(e);
         if (delay_us > 0) { delay_kernel<<<1, 1, 0, ctx->stream>>>((unsigned)delay_us * 1000u); MKID_CHECK_LAUNCH(ctx); }
     }
