@@ -1483,7 +1483,13 @@ int detect_and_fetch(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase_buf, con
 namespace {
 // one thread that holds its stream for `ns` nanoseconds (two-context pipeline: lets the channelizer kernel of the next batch
 // take its SMs before the detection tail of this batch spreads over them)
-__global__ void delay_kernel(unsigned ns) {
+__global__ void delay_kernel(unsigned ns, const int32_t *n_words_prev, int n_boards, int limit_per_board) {
+    // confined to the few SMs K4 leaves, the tail needs about 0.2 ms + 12 us per 1000 photon words: beyond `limit` words per
+    // board in the previous batch it would outlast the channelizer kernel, and starting at once (on all SMs, delaying K4 by
+    // some 35 us) is the better deal
+    long long total = 0;
+    for (int b = 0; b < n_boards; ++b) total += n_words_prev[b];
+    if (total > (long long)limit_per_board * n_boards) return;
     unsigned long long t0, t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     do {
@@ -1516,10 +1522,18 @@ extern "C" int mkid_chan_detect_pending(mkid_ctx *ctx, mkid_chan *ch, uint64_t *
         // 144 SMs first and confines the tail to the 4 free ones, where it needs 1.16 ms per batch of 8 boards at 1000
         // triggers per second and channel (resolve in its small-tile shape 0.1 ms, emit 0.9 ms: one 32-byte sector per phase
         // sample of a trigger) -- less than K4's 1.24 ms.  Per step, 1 / 2 / 4 / 8 boards: 0.214 -> 0.200, 0.372 -> 0.356,
-        // 0.677 -> 0.648, 1.296 -> 1.256 ms.  MKID_TAIL_DELAY_US overrides (0: the tail starts at once).
+        // 0.677 -> 0.648, 1.296 -> 1.256 ms.  MKID_TAIL_DELAY_US overrides (0: the tail starts at once).  The delay kernel skips
+        // the wait when the previous batch emitted more words than the confined tail can handle in K4's time.
         int delay_us = 20;
         if (const char *e = getenv("MKID_TAIL_DELAY_US")) delay_us = atoi(e);
-        if (delay_us > 0) { delay_kernel<<<1, 1, 0, ctx->stream>>>((unsigned)delay_us * 1000u); MKID_CHECK_LAUNCH(ctx); }
+        // words per board and batch up to which the confined tail fits under K4: K4 takes 4.6 ps per sample, the confined
+        // tail 12 ns per word (+ 0.2 ms per batch of 8 boards): about n / 3000 words per board for n samples per board
+        int limit = (int)std::min<int64_t>(pd.T * 512 / 3000, 1 << 30);
+        if (const char *e = getenv("MKID_TAIL_DELAY_LIMIT")) limit = atoi(e);
+        if (delay_us > 0) {
+            delay_kernel<<<1, 1, 0, ctx->stream>>>((unsigned)delay_us * 1000u, ch->n_words_dev, ch->d.n_boards, limit);
+            MKID_CHECK_LAUNCH(ctx);
+        }
     }
     int rc = detect_and_fetch(ctx, ch, ch->phase_set[pd.set], ch->mask_set[pd.set], pd.rows, pd.T, pd.t_abs0, words, words_cap, n_words, &need);
     if (rc) return rc;

@@ -16,7 +16,7 @@ for pipelined in (False, True):
     chain.derive_thresholds(boards)
     tb = np.stack([bd['tone_bins'] for bd in boards])
     iq = torch.empty((B, n, 2), dtype=torch.int16, device='cuda')
-    synth_adc(B, n, tb, n_lut=N_LUT, pulse_rate=1000.0, seed=1000, out=iq, ctx=ctx)
+    synth_adc(B, n, tb, n_lut=N_LUT, pulse_rate=float(os.environ.get('PROBE_RATE', '1000')), seed=1000, out=iq, ctx=ctx)
     ctx.sync()
     for _ in range(5):
         chain.process_async(iq, n=n)
