@@ -77,6 +77,7 @@ struct mkid_chan {
     static constexpr int EV_RING = 64;   // K4 start/stop event pairs of the last EV_RING process calls
     cudaEvent_t ev_k4[2 * EV_RING] = {};
     int64_t n_calls = 0;
+    int64_t n_calls_edge = 0;            // parity = the edge buffer the next call reads
 };
 
 namespace {
@@ -669,11 +670,22 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
 #endif
 }
 
-// edge[b] = [history (H samples) | first 2048 samples of this call]
-__global__ void edge_head_kernel(uint32_t *edge, int H, const uint32_t *in, int64_t n) {
+// edge[b] = [history (H samples) | first 2048 samples of this call].  Two edge buffers alternate from call to call: ONE
+// small kernel in front of the channelizer kernel copies the head of this call's input behind the history of `cur` (left
+// there by the previous call) and the last H samples of this call's input into the history of `nxt` (for the next call),
+// so that nothing stands between two channelizer launches but this copy (it was a head copy before and a history copy
+// after K4: 13 us during which the detection tail of the previous batch spread over the SMs).
+__global__ void edge_prep_kernel(uint32_t *cur, uint32_t *nxt, int H, const uint32_t *in, int64_t n) {
     const int board = blockIdx.y;
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < 2048) edge[(size_t)board * (H + 2048) + H + i] = in[(size_t)board * n + i];
+    const uint32_t *x = in + (size_t)board * n;
+    if (blockIdx.x < 8) {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x;
+        if (i < 2048) cur[(size_t)board * (H + 2048) + H + i] = x[i];
+    } else {
+        uint32_t *h = nxt + (size_t)board * (H + 2048);
+        for (int64_t i = (int64_t)(blockIdx.x - 8) * blockDim.x + threadIdx.x; i < H; i += (int64_t)(gridDim.x - 8) * blockDim.x)
+            h[i] = x[n - H + i];
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1009,16 +1021,6 @@ __global__ void __launch_bounds__(256) emit_warp_kernel(const int16_t *__restric
     }
 }
 
-// history <- last H samples of [history | new input]
-__global__ void update_history_kernel(uint32_t *hist, int H, const uint32_t *in, int64_t n, int n_boards) {
-    const int board = blockIdx.y;
-    uint32_t *h = hist + (size_t)board * (H + 2048);
-    const uint32_t *x = in + (size_t)board * n;
-    // out-of-place is required when n < H (shift): use a two-phase grid-stride that reads before writing
-    // only when n >= H (pure copy); the n < H case is handled on the host by a staging buffer.
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < H; i += (int64_t)gridDim.x * blockDim.x)
-        h[i] = x[n - H + i];
-}
 
 // fold: the rows with even t of odd-bin channels are negated (the hop sign (-1)^(bin (f + 1)) of frame f = t mod Ld);
 // *unfoldable is set if a value that would have to be negated is -32768 (the caller then repacks without folding)
@@ -1305,7 +1307,7 @@ extern "C" int mkid_chan_create(mkid_ctx *ctx, const mkid_chan_params *prm, mkid
     bad |= A((void **)&d.cen_i, (size_t)B * NCH * 4);
     bad |= A((void **)&d.cen_q, (size_t)B * NCH * 4);
     bad |= A((void **)&d.thr, (size_t)B * NCH * 4);
-    bad |= A((void **)&d.hist, (size_t)B * (d.H + 2048) * 4);
+    bad |= A((void **)&d.hist, (size_t)2 * B * (d.H + 2048) * 4);       // two edge buffers: call k reads k & 1 and prepares the other
     bad |= A((void **)&d.t_next, (size_t)B * NCH * 8);
     bad |= A((void **)&ch->n_words_dev, (size_t)(B + 1) * 4);          // [B] word counts + the sticky overflow flag
     if (bad) { mkid_chan_destroy(ctx, ch); return mkid_fail(ctx, MKID_ENOMEM, "chan_create: device allocation failed"); }
@@ -1436,7 +1438,7 @@ extern "C" int mkid_chan_reset(mkid_ctx *ctx, mkid_chan *ch) {
     if (!ctx) return MKID_EINVAL;
     MKID_REQUIRE(ctx, ch, "chan_reset: NULL");
     ChanDev &d = ch->d;
-    MKID_CUDA(ctx, cudaMemsetAsync(d.hist, 0, (size_t)d.n_boards * (d.H + 2048) * 4, ctx->stream));
+    MKID_CUDA(ctx, cudaMemsetAsync(d.hist, 0, (size_t)2 * d.n_boards * (d.H + 2048) * 4, ctx->stream));
     MKID_CUDA(ctx, cudaMemsetAsync(d.t_next, 0, (size_t)d.n_boards * NCH * 8, ctx->stream));
     MKID_CUDA(ctx, cudaMemsetAsync(ch->n_words_dev, 0, (size_t)(d.n_boards + 1) * 4, ctx->stream));
     ch->t_consumed = 0;
@@ -1579,7 +1581,10 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     int16_t *const phase_buf = ch->phase_set[set];
     // K4: equal chunks of rows, one CTA per SM in a single wave
     WsParams w;
-    w.d = d; w.in = in_dev; w.edge = d.hist; w.n = n; w.f0_abs = 2 * ch->t_consumed; w.phase = phase_buf; w.phase_f32 = ch->f32_out; w.rows = rows;
+    uint32_t *const edge_cur = d.hist + (size_t)((ch->n_calls_edge) & 1) * B * (d.H + 2048);
+    uint32_t *const edge_nxt = d.hist + (size_t)((ch->n_calls_edge + 1) & 1) * B * (d.H + 2048);
+    ch->n_calls_edge++;
+    w.d = d; w.in = in_dev; w.edge = edge_cur; w.n = n; w.f0_abs = 2 * ch->t_consumed; w.phase = phase_buf; w.phase_f32 = ch->f32_out; w.rows = rows;
     {
         // two-context pipeline: leave 4 SMs to the detection / decode kernels of the previous batch, which run on the other
         // context's stream at the same time (with 8 boards 144 of 148 SMs are taken either way; with one board per GPU the
@@ -1613,7 +1618,7 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     {
         const size_t smem = (size_t)(WS_NBUF * 16 * FFT_STRIDE + 256) * sizeof(float2) + (size_t)(WS_ADC_STAGES + WS_DDS_STAGES) * FB * NCH * 4;
         // edge buffer <- first 2048 samples of this call (behind the history of the previous ones)
-        edge_head_kernel<<<dim3(8, B), 256, 0, ctx->stream>>>(d.hist, d.H, in_dev, n);
+        edge_prep_kernel<<<dim3(8 + 32, B), 256, 0, ctx->stream>>>(edge_cur, edge_nxt, d.H, in_dev, n);
         MKID_CHECK_LAUNCH(ctx);
         MKID_CUDA(ctx, cudaEventRecord(evp[0], ctx->stream));
         bool all_fold = true;
@@ -1643,9 +1648,6 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     } else if (detect) {
         if ((rc = detect_and_fetch(ctx, ch, phase_buf, ch->mask_set[set], rows, T, t_abs0, words, words_cap, n_words, &overflow_need))) return rc;
     }
-    // history <- last H samples of this call (n >= H)
-    update_history_kernel<<<dim3(32, B), 256, 0, ctx->stream>>>(d.hist, d.H, in_dev, n, B);
-    MKID_CHECK_LAUNCH(ctx);
     ch->t_consumed += T;
     if (!mkid_is_device_ptr(iq) || phase_out) MKID_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     // reported only now: the streaming state (hold-off times, input history, time) is that of a completed call, the
