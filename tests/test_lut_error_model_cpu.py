@@ -14,7 +14,7 @@ FS = 512e6
 
 def test_flag_distance_covers_reference_rounding():
     src = open(os.path.join(os.path.dirname(__file__), '..', 'mkids_sdr_b200', 'csrc', 'lut.cu')).read()
-    m = re.search(r'p\.sigma\[i\] = ([0-9.e-]+) \* 6\.283185307179586 \* \(double\)p\.N \* sqrt\(ss\);', src)
+    m = re.search(r'p\.sigma\[\w+\] = ([0-9.e-]+) \* 6\.283185307179586 \* \(double\)p\.N \* sqrt\(ss\);', src)
     assert m, 'sigma model not found in lut.cu'
     coeff = float(m.group(1))
     assert re.search(r'p\.eps\[b\] = fmax\(1e-7, 8\.0 \* p\.sigma\[b\] \* 32767\.0 / sc\);', src)
