@@ -1522,8 +1522,8 @@ extern "C" int mkid_chan_detect_pending(mkid_ctx *ctx, mkid_chan *ch, uint64_t *
         // ends, 13 us before the next channelizer kernel is launched (edge / history copies), and would spread over every SM:
         // the next K4 then waits for SMs (1.24 -> 1.28 ms with 8 boards).  Holding the tail back for 20 us lets K4 take its
         // 144 SMs first and confines the tail to the 4 free ones, where it needs 1.16 ms per batch of 8 boards at 1000
-        // triggers per second and channel (resolve in its small-tile shape 0.1 ms, emit 0.9 ms: one 32-byte sector per phase
-        // sample of a trigger) -- less than K4's 1.24 ms.  Per step, 1 / 2 / 4 / 8 boards: 0.214 -> 0.200, 0.372 -> 0.356,
+        // triggers per second and channel (resolve in its small-tile shape 0.1 ms, emit 0.9 ms: 1024 per-window CTAs) -- less
+        // than K4's 1.24 ms.  Per step, 1 / 2 / 4 / 8 boards: 0.214 -> 0.200, 0.372 -> 0.356,
         // 0.677 -> 0.648, 1.296 -> 1.256 ms.  MKID_TAIL_DELAY_US overrides (0: the tail starts at once).  The delay kernel skips
         // the wait when the previous batch emitted more words than the confined tail can handle in K4's time.
         int delay_us = 20;
