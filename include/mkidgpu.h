@@ -272,6 +272,11 @@ int  mkid_chan_n_words_dev(mkid_ctx *ctx, mkid_chan *ch, const int32_t **out);
  * (with the candidate mask) only; mkid_chan_detect_pending then runs resolve / scan / emit for THAT call, on the stream of
  * the context it is given -- which may be a second context, ordered by mkid_event_record / mkid_stream_wait_event: the
  * detection of batch k then runs under the channelizer kernel of batch k + 1 (mkids_sdr_b200/chain.py does this).
+ * With the switch on, the channelizer kernel leaves 4 SMs free ((SMs - 4) / n_boards chunks per board) and
+ * mkid_chan_detect_pending (i) holds its kernels back by 20 us (a one-thread kernel; MKID_TAIL_DELAY_US overrides) so that
+ * the channelizer kernel of the next batch takes its SMs first -- unless the previous batch emitted more than about n / 3000
+ * photon words per board, which the tail could not handle on the free SMs in the channelizer's time (decided on the device) --
+ * and (ii) uses the small-tile shape of the hold-off resolver (more CTAs per SM).  Results are identical in every mode.
  * words / words_cap / n_words as in mkid_chan_process. */
 int  mkid_chan_set_pipelined(mkid_ctx *ctx, mkid_chan *ch, int32_t on);
 int  mkid_chan_detect_pending(mkid_ctx *ctx, mkid_chan *ch, uint64_t *words, int64_t words_cap, int32_t *n_words);
