@@ -964,6 +964,9 @@ __global__ void __launch_bounds__(256) emit_warp_kernel(const int16_t *__restric
     const int n = s_n;
     if (c == 0) win_off[(size_t)board * (n_win + 1) + wi] = 0u;     // (every thread of the CTA has read it)
     uint64_t *out = words + (size_t)board * words_cap;
+    // Phase A, a warp per photon word (two per round): the lanes fetch the baseline rows and the peak window and reduce them
+    // to what the word needs -- baseline sum, minimum and its position, the parabola's two neighbours -- in shared memory.
+    __shared__ int s_S[NCH + 2], s_vmin[NCH + 2], s_y1[NCH + 2], s_y3[NCH + 2];
     for (int i0 = warp; i0 < n; i0 += 16) {
         uint32_t key[2];
         int vb[2], vw[2], ve[2];
@@ -984,41 +987,50 @@ __global__ void __launch_bounds__(256) emit_warp_kernel(const int16_t *__restric
         }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
-            if (!live[u]) continue;                         // (warp-uniform)
-            const uint32_t k = key[u];
-            int rank = 0;
-            for (int q = lane; q < n; q += 32) rank += s_keys[q] < k;
-            rank = __reduce_add_sync(0xffffffffu, rank);
-            const int ch = (int)(k & 0x1FFu) - 1;
-            if (ch < 0) {                                   // the end-of-second word
-                if (lane == 0 && (int64_t)off + rank < words_cap) out[off + rank] = ~0ull;
-                continue;
-            }
+            if (!live[u] || (key[u] & 0x1FFu) == 0u) continue;          // (warp-uniform; channel field 0 = the end-of-second word)
             const int S = __reduce_add_sync(0xffffffffu, vb[u]);
             // minimum of the window, first occurrence: (value, index) packed
             unsigned mk = lane < W ? ((unsigned)(vw[u] + 32768) << 5) | (unsigned)lane : 0xFFFFFFFFu;
             mk = __reduce_min_sync(0xffffffffu, mk);
-            const int j = (int)(mk & 31u), vmin = (int)(mk >> 5) - 32768;
+            const int j = (int)(mk & 31u);
             const int w_prev = __shfl_sync(0xffffffffu, vw[u], (j + 31) & 31), w_next = __shfl_sync(0xffffffffu, vw[u], (j + 1) & 31);
             const int b_first = __shfl_sync(0xffffffffu, vb[u], 0), e_last = __shfl_sync(0xffffffffu, ve[u], 0);
             if (lane == 0) {
-                const double y1 = (double)(j >= 1 ? w_prev : b_first), y2 = (double)vmin, y3 = (double)(j + 1 < W ? w_next : e_last);
-                const double den = __dsub_rn(__dadd_rn(y3, y1), __dmul_rn(2.0, y2));
-                double y4 = y2;
-                if (den != 0.0) {
-                    const double dy = __dsub_rn(y3, y1);
-                    y4 = __dsub_rn(y2, __ddiv_rn(__dmul_rn(0.125, __dmul_rn(dy, dy)), den));
-                }
-                const int peak = (__double2int_rz(__dmul_rn(y4, 0.0625)) + 2048) & 0xFFF;
-                const int p1 = (vmin / 16 + 2048) & 0xFFF;
-                const int base = (S / (16 * M) + 2048) & 0xFFF;
-                const int64_t t = t_abs0 + w_lo + (int64_t)(k >> 9);
-                const uint32_t ts = (uint32_t)(t % SEC_US);
-                const uint64_t word = ((uint64_t)ch << 56) | ((uint64_t)peak << 44) | ((uint64_t)p1 << 32) | ((uint64_t)base << 20) | ts;
-                if ((int64_t)off + rank < words_cap) out[off + rank] = word;
+                const int i = i0 + 8 * u;
+                s_S[i] = S; s_vmin[i] = (int)(mk >> 5) - 32768;
+                s_y1[i] = j >= 1 ? w_prev : b_first; s_y3[i] = j + 1 < W ? w_next : e_last;
             }
         }
     }
+    __syncthreads();
+    // Phase B, a thread per photon word: rank among the keys of the window, the parabola in float64, the word.  (One lane
+    // of every warp did this for its words one after the other before: the longest serial piece of the kernel.)
+    auto finish = [&](int i) {
+        const uint32_t k = s_keys[i];
+        int rank = 0;
+        for (int q = 0; q < n; ++q) rank += s_keys[q] < k;
+        const int ch = (int)(k & 0x1FFu) - 1;
+        uint64_t word = ~0ull;                              // (channel field 0) the end-of-second word
+        if (ch >= 0) {
+            const int vmin = s_vmin[i], S = s_S[i];
+            const double y1 = (double)s_y1[i], y2 = (double)vmin, y3 = (double)s_y3[i];
+            const double den = __dsub_rn(__dadd_rn(y3, y1), __dmul_rn(2.0, y2));
+            double y4 = y2;
+            if (den != 0.0) {
+                const double dy = __dsub_rn(y3, y1);
+                y4 = __dsub_rn(y2, __ddiv_rn(__dmul_rn(0.125, __dmul_rn(dy, dy)), den));
+            }
+            const int peak = (__double2int_rz(__dmul_rn(y4, 0.0625)) + 2048) & 0xFFF;
+            const int p1 = (vmin / 16 + 2048) & 0xFFF;
+            const int base = (S / (16 * M) + 2048) & 0xFFF;
+            const int64_t t = t_abs0 + w_lo + (int64_t)(k >> 9);
+            const uint32_t ts = (uint32_t)(t % SEC_US);
+            word = ((uint64_t)ch << 56) | ((uint64_t)peak << 44) | ((uint64_t)p1 << 32) | ((uint64_t)base << 20) | ts;
+        }
+        if ((int64_t)off + rank < words_cap) out[off + rank] = word;
+    };
+    if (c < n) finish(c);
+    if (c == 0 && n > NCH) finish(NCH);                     // 256 triggers + the end-of-second word: one entry more than threads
 }
 
 
