@@ -409,8 +409,8 @@ int mkid_dashboard_image(mkid_ctx *ctx, const uint32_t *counts_raw, int32_t n_pi
  * Q[t] = sum a_n sin(2 pi f_n t/fs + phi_n), scale = fudge * max(|I|,|Q|) (fudge 1.1 for echo='yes',
  * 1.0 for 'no'; scale_override > 0 replaces it: keep-old / custom scale, :456-459),
  * out = int(v*32767/scale) truncated toward zero.  Every f_n must be a multiple of
- * sample_rate/n_samples (define_DAC_LUT snaps to that grid, :498); the check runs on the GPU with the synthesis, so an
- * off-grid tone returns MKID_EINVAL after the call's work and leaves I / Q of the whole call undefined.  random_phase != 0 draws
+ * sample_rate/n_samples (define_DAC_LUT snaps to that grid, :498): an off-grid tone returns MKID_EINVAL (the message
+ * names the set and the tone) before any work is queued, I / Q / phase / scale_out are left untouched.  random_phase != 0 draws
  * phi_n = numpy.random.seed(1000); uniform(0, 2 pi) per tone (:426-429) and returns them in phase.
  * All arrays are [batch][n_tones] / [batch][n_samples]; freq/amp/phase/scale_out are host pointers. */
 int mkid_random_phases(uint32_t seed, int32_t n, double *out);

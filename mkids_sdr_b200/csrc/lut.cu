@@ -792,8 +792,16 @@ extern "C" int mkid_comb_lut(mkid_ctx *ctx, const double *freq_hz, const double 
     int N1 = 1024;                         // largest power of four <= min(1024, N/2)
     while (N1 * 2 > N) N1 /= 4;
     const int N2 = N / N1;
-    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t TB = (size_t)batch * n_tones;
+    // every tone must sit on the fs/N grid (define_DAC_LUT snaps to it, :498): checked here, in the arithmetic of the device
+    // check in comb_prep_kernel, BEFORE any work is queued, so that a bad call leaves the caller's I / Q untouched
+    for (size_t i = 0; i < TB; ++i) {
+        const double k = freq_hz[i] * (double)N / sample_rate;
+        if (!(fabs(k - rint(k)) < 1e-6))
+            return mkid_fail(ctx, MKID_EINVAL, "comb_lut: tone frequency is not a multiple of sampleRate/n_samples (set %d, tone %d: %.17g Hz)",
+                             (int)(i / n_tones), (int)(i % n_tones), freq_hz[i]);
+    }
+    MKID_CUDA(ctx, cudaSetDevice(ctx->device));
     // one host block in the device layout freq | amp | phase: a single upload (the spectral lines are derived on the GPU)
     std::vector<double> hmeta(TB * 3);
     double *ph = hmeta.data() + 2 * TB;

@@ -293,6 +293,28 @@ class QuickLookWriter:
         return self.written
 
 
+def QuickLook(decoder, pixel_adr, tstart, tend):
+    """pulses.QuickLook (ReadoutControls/lib/pulses.py:210-236) without the HDF5 file and the plot: image[i][j] = sum
+    over the seconds tstart <= k < tend of the length of pixel beamimage[i][j]'s photon list of second k (the lists
+    PacketMaster stores hold at most max_events - 1 photons, PacketMaster.c:373-380), then the sky is taken off as the
+    median of the image.  Returns what the reference hands to imshow: float32 [rows][cols]."""
+    c = decoder.ctx
+    adr = np.ascontiguousarray(pixel_adr, dtype=np.int32)
+    rows, cols = adr.shape
+    tstart, tend = int(tstart), int(tend)
+    if not (0 <= tstart and tend <= decoder.exptime):
+        raise IndexError('QuickLook: seconds [%d, %d) outside the exposure of %d s' % (tstart, tend, decoder.exptime))
+    image = np.zeros((rows, cols), np.float64)
+    if tend - tstart == 1:
+        image = decoder.quicklook_image(tstart, adr).astype(np.float64)
+    elif tend > tstart:                          # (make_image's sum over [t_i, t_f) is the same sum of per-second images)
+        flipped = np.empty((rows, cols), np.float64)
+        c._check(c.lib.mkid_dashboard_image(c.h, _lib.ptr(decoder.counts_dev), decoder.n_pix, _lib.ptr(adr), rows, cols,
+                                            tstart, tend, decoder.max_events, None, None, _lib.ptr(flipped), _lib.ptr(image)))
+        c.sync()
+    return np.float32(image - np.median(image))
+
+
 class Dashboard:
     """Headless twin of the image part of ArconsDashboard (make_image, ArconsDashboard.py:633-723) fed straight from a
     PhotonDecoder: attributes image_time, int_time, sky_subtraction, skyrate, taking_sky, skytime, skycount,

@@ -179,6 +179,17 @@ def quicklook_image(counts_sec, pixel_adr):
     return np.asarray(counts_sec)[np.asarray(pixel_adr)].astype(np.uint16)
 
 
+def quicklook_skysub(counts, pixel_adr, tstart, tend):
+    """pulses.QuickLook (ReadoutControls/lib/pulses.py:210-236): image[i][j] += len(photons[k]) for k in
+    xrange(tstart, tend) of the pixel the beammap names at [i][j] (the stored list of a second holds photon_counts
+    entries, i.e. the capped count), skysub = float32(image - median(image)).  counts: capped [sec][pixel]."""
+    adr = np.asarray(pixel_adr)
+    image = np.zeros(adr.shape)
+    for k in range(tstart, tend):
+        image += np.asarray(counts[k])[adr]
+    return np.float32(image - np.median(image))
+
+
 # ---------------------------------------------------------------- histograms
 def pixel_field_hist(streams, npix_per_roach, exptime, field='peak', bin_lut=None, n_bins=4096,
                      max_events=None):

@@ -445,3 +445,11 @@ def test_quicklook_files_and_beammap_parse(ctx, tmp_path):
         assert np.array_equal(img, odec.quicklook_image(ref['counts'][s], adr))
         assert open(f).read().split('\n')[0].endswith(' ')               # "%d " after every value
     assert ref['counts'].max() == 2499
+    # pulses.QuickLook (lib/pulses.py:210-236): photons per pixel over a span of seconds, median sky taken off
+    from mkids_sdr_b200.decode import QuickLook
+    for t0, t1 in ((0, 3), (1, 3), (0, 1), (2, 3), (1, 1)):
+        got = QuickLook(dec, adr, t0, t1)
+        want = odec.quicklook_skysub(ref['counts'], adr, t0, t1)
+        assert got.dtype == np.float32 and got.shape == (rows, cols) and np.array_equal(got, want), (t0, t1)
+    with pytest.raises(IndexError):
+        QuickLook(dec, adr, 0, secs + 1)

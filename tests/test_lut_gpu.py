@@ -121,7 +121,7 @@ def test_comb_lut_rejects_off_grid_tone(ctx):
     N = 2 ** 12
     good = np.array([3.0, 17.0, 900.0]) * FS / N
     bad = good.copy(); bad[1] += 0.3 * FS / N
-    with pytest.raises(MkidError, match='not a multiple'):
+    with pytest.raises(MkidError, match=r'not a multiple.*set 1, tone 1'):       # found on the host, before any GPU work
         lut.comb_lut([good, bad], FS, N, [1.0, 0.5, 0.25], ctx=ctx)
     I, Q, sc, ph = lut.comb_lut(good, FS, N, [1.0, 0.5, 0.25], ctx=ctx)
     Io, Qo, so, _ = olut.freq_comb_lut('yes', list(good), FS, FS / N, [1.0, 0.5, 0.25])
