@@ -38,6 +38,26 @@ constexpr int DEC_MAX_LS = 4;                      // local seconds kept per ran
 constexpr int DEC_ROW = 264;                       // u32 per row: 256 channels | - | corrupt EOS | words | start
 constexpr int DEC_SMEM_HIST = 4096;                // smem-privatised histogram entries per CTA
 
+// Partitioned histogram (HIST == 3): a per-pixel histogram too large for shared memory ([253][4096] u32 = 4 MB per roach)
+// costs one L2 reduction per word when it is built in place (198 G reductions per second on this GPU: 20 % of the HBM
+// roof).  Instead the relative pass writes a 16-bit key (pixel inside its tile << 12 | bin) per word into the bucket of
+// the word's (roach, pixel tile) - staged per warp in shared memory and stored in whole 64-byte runs - and
+// part_hist_kernel, one CTA per bucket, builds the tile's histogram in shared memory from 2 bytes per word.
+constexpr int PART_RING = 64;                      // staged keys per (warp, tile)
+constexpr int PART_FLUSH = 32;                     // keys per store: 64 bytes
+constexpr int PART_CHUNK = 128;                    // keys a warp reserves per reduction on the bucket's cursor
+constexpr int PART_TILES = 32;                     // at most one tile per lane
+constexpr unsigned PART_EMPTY = 0xFFFFu;           // padding key (pixel-in-tile 15 does not exist: at most 8 pixels per tile)
+constexpr int PART_ROW = PART_RING * 2 + 16;         // bytes per staging ring (16-byte aligned halves); the rings of the 32 tiles fill
+                                                   // at the same pace: without the skew the lanes of an append would aim at one bank
+constexpr int PART_SMEM_WARP = PART_TILES * PART_ROW + PART_TILES * 4;
+struct PartParams {
+    uint16_t *keys;        // [n_roaches * n_tiles][cap]
+    uint32_t *cursor;      // [n_roaches * n_tiles] keys reserved so far (whole chunks; beyond cap: not stored)
+    uint32_t cap;          // keys per bucket, a multiple of PART_CHUNK
+    int n_tiles, tp;       // tiles per roach, pixels per tile
+};
+
 struct DecRange {
     long long start;       // flat: first word (relative to words); wire: first half-bundle chunk
     int n_words;           // words in the range
@@ -69,6 +89,7 @@ struct DecParams {
     uint32_t *counts;          // [exptime][n_pix]
     uint32_t *hist;            // [n_pix][n_bins] or nullptr
     unsigned long long *stats; // 5 x u64: eos, corrupt eos, non-pixel, ignored, valid
+    PartParams part;           // HIST == 3
 };
 
 __device__ __forceinline__ uint32_t bswap32(uint32_t x) { return __byte_perm(x, 0, 0x0123); }
@@ -94,7 +115,8 @@ template <bool WIRE, int HIST, bool NEED_LO, bool ABS>
 struct RangeDecoder {
     static constexpr int J = WIRE ? 4 : 2;
     static constexpr int G = 32 * J;                   // words per group
-    static constexpr int R = WIRE ? (NEED_LO ? 2 : 6) : (NEED_LO ? 4 : 8);   // ring depth: 16-24 registers per lane in flight
+    // ring depth: 16-24 registers per lane in flight (the partitioning variant needs registers of its own)
+    static constexpr int R = HIST == 3 ? (WIRE ? (NEED_LO ? 2 : 3) : (NEED_LO ? 2 : 4)) : (WIRE ? (NEED_LO ? 2 : 6) : (NEED_LO ? 4 : 8));
     // position of (lane, j) inside a group: flat = lane-contiguous 32/64-bit loads, wire = one 128-bit load per lane
     __device__ __forceinline__ int idx_of(int j) const { return WIRE ? 4 * lane + j : 32 * j + lane; }
 
@@ -120,6 +142,13 @@ struct RangeDecoder {
     unsigned n_bad;                                    // per lane, current second
     unsigned st_eos, st_bad, st_nonpix, st_valid;      // ABS: per lane totals
     unsigned long long st_ign;
+    // HIST == 3: this warp's staging rings [PART_TILES][PART_RING] u16 and append counters [PART_TILES] (shared
+    // addresses), pixels per tile and 65536 / that, rounded up; lane t keeps the state of tile t: keys flushed so far, position
+    // and keys left in the chunk reserved in the bucket, bucket full (the keys go straight to the histogram then)
+    uint32_t ring_s, tcnt_s, tp_n, tp_inv;
+    uint32_t pt_flushed, pt_left, pt_next;             // pt_next: position of the chunk reserved ahead
+    uint16_t *pt_ptr;                                  // where the next run goes
+    bool pt_direct;
 
     __device__ __forceinline__ RangeDecoder(const DecParams &p_) : p(p_) {}
 
@@ -131,10 +160,85 @@ struct RangeDecoder {
             const uint32_t f = ((f_hi ? hi : lo) >> f_sh) & 0xFFFu;
             const uint32_t b = use_lut ? s_lut[f] : f;
             if ((int)b < n_bins) {
-                if (HIST == 2 && own_roach) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_s + (adr * n_bins + b) * 4) : "memory");
+                if (HIST == 3) {
+                    const uint32_t t = (adr * tp_inv) >> 16, pit = adr - t * tp_n;      // adr / tp, exact for adr < 256, tp <= 8
+                    uint32_t pos;
+                    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(pos) : "r"(tcnt_s + t * 4) : "memory");
+                    asm volatile("st.shared.u16 [%0], %1;" ::"r"(ring_s + t * PART_ROW + (pos & (PART_RING - 1)) * 2),
+                                 "h"((unsigned short)((pit << 12) | b)) : "memory");
+                } else if (HIST == 2 && own_roach) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hist_s + (adr * n_bins + b) * 4) : "memory");
                 else atomicAdd(&hist_r[adr * n_bins + b], 1u);
             }
         }
+    }
+
+    // HIST == 3.  Lane t owns tile t: when 32 keys of the tile are staged they leave as one 64-byte run (four 16-byte
+    // stores) into the chunk the lane holds in the bucket of (roach, t).  The chunk after it is reserved ahead (the
+    // reduction on the bucket's cursor returns while this chunk fills).  A bucket that is full - a tile that takes more
+    // than four times its share of the roach's words - sends the keys to the histogram directly instead.  (A first form
+    // flushed tile by tile with the whole warp, state passed by shuffles: 128 instructions per word, issue-bound.)
+    __device__ __forceinline__ void part_flush_own() {
+        if (pt_left == 0 && !pt_direct) {
+            if (pt_next > p.part.cap - PART_CHUNK) pt_direct = true;
+            else {
+                const int bucket = roach * p.part.n_tiles + lane;
+                pt_ptr = p.part.keys + (size_t)bucket * p.part.cap + pt_next;
+                pt_left = PART_CHUNK;
+                pt_next = atomicAdd(&p.part.cursor[bucket], (uint32_t)PART_CHUNK);
+            }
+        }
+        const uint32_t src = ring_s + lane * PART_ROW + (pt_flushed & (uint32_t)PART_FLUSH) * 2;      // this half of the ring
+        if (!pt_direct) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 v;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src + 16 * q) : "memory");
+                reinterpret_cast<uint4 *>(pt_ptr)[q] = v;
+            }
+            pt_ptr += PART_FLUSH; pt_left -= PART_FLUSH;
+        } else {
+            const uint32_t pix0 = (uint32_t)lane * tp_n;
+#pragma unroll 1
+            for (int q = 0; q < PART_FLUSH / 2; ++q) {
+                uint32_t w;
+                asm volatile("ld.shared.u32 %0, [%1];" : "=r"(w) : "r"(src + 4 * q) : "memory");
+                const uint32_t k0 = w & 0xFFFFu, k1 = w >> 16;
+                if (k0 != PART_EMPTY) atomicAdd(&hist_r[(pix0 + (k0 >> 12)) * n_bins + (k0 & 0xFFFu)], 1u);
+                if (k1 != PART_EMPTY) atomicAdd(&hist_r[(pix0 + (k1 >> 12)) * n_bins + (k1 & 0xFFFu)], 1u);
+            }
+        }
+        pt_flushed += PART_FLUSH;
+    }
+    // after every bin() of the warp (each lane appends at most one key per call: a ring never holds more than 31 + 32)
+    __device__ __forceinline__ void part_check() {
+        __syncwarp();
+        uint32_t c;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c) : "r"(tcnt_s + lane * 4) : "memory");
+        if (c - pt_flushed >= (uint32_t)PART_FLUSH) part_flush_own();
+        __syncwarp();
+    }
+    // end of a range: the keys still staged leave padded to a whole run, the rest of the chunk and the chunk reserved ahead
+    // are padded as well, so that a bucket is whole chunks of keys and padding up to its cursor
+    __device__ __forceinline__ void part_drain() {
+        __syncwarp();
+        uint32_t c;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(c) : "r"(tcnt_s + lane * 4) : "memory");
+        const uint32_t pend = c - pt_flushed;
+        if (pend > 0) {
+            for (uint32_t k = pend; k < (uint32_t)PART_FLUSH; ++k)
+                asm volatile("st.shared.u16 [%0], %1;" ::"r"(ring_s + lane * PART_ROW + ((pt_flushed + k) & (PART_RING - 1)) * 2),
+                             "h"((unsigned short)PART_EMPTY) : "memory");
+            part_flush_own();
+        }
+        const uint4 pad = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+        for (uint32_t k = 0; k < pt_left; k += 8) *reinterpret_cast<uint4 *>(pt_ptr + k) = pad;
+        if (pt_next <= p.part.cap - PART_CHUNK) {
+            uint16_t *spare = p.part.keys + (size_t)(roach * p.part.n_tiles + lane) * p.part.cap + pt_next;
+            for (uint32_t k = 0; k < (uint32_t)PART_CHUNK; k += 8) *reinterpret_cast<uint4 *>(spare + k) = pad;
+        }
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(tcnt_s + lane * 4), "r"(0u) : "memory");
+        pt_flushed = 0; pt_left = 0; pt_direct = false; pt_next = 0xFFFFFFFFu;
+        __syncwarp();
     }
 
     // the second that ends with the word at position pe (or with the range: pe = n_words - 1, closed = false)
@@ -209,6 +313,7 @@ struct RangeDecoder {
             for (int j = 0; j < J; ++j) {
                 const int idx = idx_of(j);
                 if (((valid >> j) & 1u) && idx >= done && idx < pe) bin(hi[j], lo[j]);
+                if (HIST == 3) part_check();
             }
             if (pe == 0x7fffffff) return;
 #pragma unroll
@@ -276,6 +381,7 @@ struct RangeDecoder {
             const uint32_t lo = NEED_LO ? g.lo[j] : 0u;
             if (WIRE) bin(bswap32(g.hi[j]), bswap32(lo));
             else bin(g.hi[j], lo);
+            if (HIST == 3) part_check();
         }
     }
 
@@ -305,6 +411,11 @@ struct RangeDecoder {
         w_wire = p.wire; wire_chunk0 = rg.start;
         sec = 0; row_start = 0; eos_total = 0; count_only = false; stop = false; resume = -1;
         n_bad = 0;
+        if (HIST == 3) {
+            pt_flushed = 0; pt_left = 0; pt_direct = false; pt_ptr = nullptr;
+            pt_next = 0xFFFFFFFFu;
+            if (lane < p.part.n_tiles && n_words > 0) pt_next = atomicAdd(&p.part.cursor[roach * p.part.n_tiles + lane], (uint32_t)PART_CHUNK);
+        }
         int lo_bound = 0;
         if (ABS) {
             const DecRangeOut ro = p.rout[r];
@@ -338,6 +449,7 @@ struct RangeDecoder {
 #pragma unroll 1
             while (go) go = ring_round<true>(ring, pos, force);
         }
+        if (HIST == 3) part_drain();
         if (!ABS) {
             int n_ls = DEC_MAX_LS;
             if (!count_only) { flush(n_words - 1, false); n_ls = sec + 1; }
@@ -357,6 +469,7 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_stream_ke
     __shared__ __align__(16) uint32_t s_cnt[DEC_WARPS][256];
     __shared__ uint32_t s_hist[HIST == 2 ? DEC_SMEM_HIST : 1];
     __shared__ uint16_t s_lut[HIST ? 4096 : 1];
+    extern __shared__ __align__(16) unsigned char s_part[];      // HIST == 3: [DEC_WARPS][PART_SMEM_WARP]
     if (ABS && *p.flag == 0) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const bool use_lut = HIST != 0 && p.bin_lut != nullptr;
@@ -365,6 +478,8 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_stream_ke
     for (int i = tid; i < DEC_WARPS * 256; i += DEC_THREADS) (&s_cnt[0][0])[i] = 0;
     if (HIST == 2)
         for (int i = tid; i < DEC_SMEM_HIST; i += DEC_THREADS) s_hist[i] = 0;
+    if (HIST == 3)
+        for (int i = tid; i < DEC_WARPS * PART_SMEM_WARP / 4; i += DEC_THREADS) reinterpret_cast<uint32_t *>(s_part)[i] = 0u;
     __syncthreads();
 
     int r = blockIdx.x * DEC_WARPS + warp;
@@ -372,6 +487,11 @@ __global__ void __launch_bounds__(DEC_THREADS, DEC_CTAS_PER_SM) decode_stream_ke
     RangeDecoder<WIRE, HIST, NEED_LO, ABS> d(p);
     d.cnt = s_cnt[warp]; d.cnt_s = mk_smem_u32(s_cnt[warp]); d.hist_s = mk_smem_u32(s_hist); d.s_lut = s_lut; d.lane = lane;
     d.npix = p.npix_per_roach; d.n_bins = p.n_bins;
+    if (HIST == 3) {
+        d.ring_s = mk_smem_u32(s_part + warp * PART_SMEM_WARP);
+        d.tcnt_s = d.ring_s + PART_TILES * PART_ROW;
+        d.tp_n = (uint32_t)p.part.tp; d.tp_inv = (65536u + d.tp_n - 1) / d.tp_n;
+    }
     d.use_lut = use_lut;
     d.f_hi = p.field_shift >= 32; d.f_sh = p.field_shift & 31;
     d.st_eos = d.st_bad = d.st_nonpix = d.st_valid = 0; d.st_ign = 0;
@@ -516,6 +636,47 @@ __global__ void __launch_bounds__(256) decode_commit_kernel(DecParams p) {
     }
     __syncthreads();
     if (tid < 5 && s_st[tid]) atomicAdd(&p.stats[tid], s_st[tid]);
+}
+
+// HIST == 3, second step: one CTA per (roach, pixel tile) reads the tile's keys (2 bytes per word, whole chunks up to the
+// cursor, padding skipped), builds the tile's [pixels][bins] histogram in shared memory and adds it to the global one: the
+// tile is contiguous there and no other CTA touches it, so plain coalesced read-modify-writes do.  The cursor is cleared for
+// the next call.
+__global__ void __launch_bounds__(1024, 1) part_hist_kernel(PartParams q, uint32_t *hist, int npix_per_roach, int n_bins) {
+    extern __shared__ __align__(16) uint32_t s_h[];
+    const int bucket = blockIdx.x, roach = bucket / q.n_tiles, tile = bucket % q.n_tiles, tid = threadIdx.x;
+    const int pix0 = tile * q.tp, np = min(q.tp, npix_per_roach - pix0);
+    const uint32_t n = min(q.cursor[bucket], q.cap);
+    const int cells = np * n_bins;
+    for (int i = tid; i < cells; i += 1024) s_h[i] = 0u;
+    __syncthreads();
+    if (tid == 0) q.cursor[bucket] = 0u;
+    if (n == 0 || np <= 0) return;
+    const uint4 *src = reinterpret_cast<const uint4 *>(q.keys + (size_t)bucket * q.cap);
+    const uint32_t hs = mk_smem_u32(s_h), n16 = n / 8;
+    auto add2 = [&](uint32_t v) {
+        const uint32_t k0 = v & 0xFFFFu, k1 = v >> 16;
+        if (k0 != PART_EMPTY) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hs + ((k0 >> 12) * n_bins + (k0 & 0xFFFu)) * 4) : "memory");
+        if (k1 != PART_EMPTY) asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(hs + ((k1 >> 12) * n_bins + (k1 & 0xFFFu)) * 4) : "memory");
+    };
+    uint32_t i = tid;
+    for (; i + 3 * 1024 < n16; i += 4 * 1024) {          // four 16-byte loads in flight per thread
+        const uint4 a = ld_stream_u4(src + i), b = ld_stream_u4(src + i + 1024), c = ld_stream_u4(src + i + 2048), d = ld_stream_u4(src + i + 3072);
+        add2(a.x); add2(a.y); add2(a.z); add2(a.w);
+        add2(b.x); add2(b.y); add2(b.z); add2(b.w);
+        add2(c.x); add2(c.y); add2(c.z); add2(c.w);
+        add2(d.x); add2(d.y); add2(d.z); add2(d.w);
+    }
+    for (; i < n16; i += 1024) {
+        const uint4 a = ld_stream_u4(src + i);
+        add2(a.x); add2(a.y); add2(a.z); add2(a.w);
+    }
+    __syncthreads();
+    uint32_t *g = hist + ((size_t)roach * npix_per_roach + pix0) * n_bins;
+    for (int j = tid; j < cells; j += 1024) {
+        const uint32_t v = s_h[j];
+        if (v) g[j] += v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1357,19 +1518,64 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
 
         const bool smem_hist = want_hist && (int64_t)cfg->npix_per_roach * cfg->n_bins <= DEC_SMEM_HIST;
         const int grid = (int)std::min<int64_t>((n_ranges + DEC_WARPS - 1) / DEC_WARPS, (int64_t)ctx->num_sms * DEC_CTAS_PER_SM);
-        const int hist_mode = !want_hist ? 0 : smem_hist ? 2 : 1;
         const bool need_lo = want_hist && cfg->hist_field_shift < 32;
+        // A histogram too large for shared memory can be built from partitioned 16-bit keys (HIST == 3, PartParams) instead
+        // of in place: MKID_DEC_PART=1.  Bit-identical (tests/test_decode_gpu.py::test_partitioned_histogram_forms), but off
+        // by default: on 1.6e8 words x [2024][4096] the key pass takes 0.69 ms (86 instructions per word, issue- and
+        // scoreboard-bound) + 0.21 ms for the tiles against 0.97 ms in place.
+        bool part = false;
+        p.part = PartParams{nullptr, nullptr, 0u, 0, 0};
+        if (want_hist && !smem_hist && cfg->n_bins <= 4096) {
+            const int64_t unit = wire_fmt ? DEC_BUNDLE : 1;
+            std::vector<int64_t> w_roach(cfg->n_roaches, 0), r_roach(cfg->n_roaches, 0);
+            for (int i = 0; i < n_seg; ++i) w_roach[seg_roach[i]] += seg_len[i] * unit;
+            const DecRange *hr = (const DecRange *)ctx->dec_ranges_host.data();
+            for (int k = 0; k < n_ranges; ++k) r_roach[hr[k].roach]++;
+            const char *e = getenv("MKID_DEC_PART");
+            part = e && atoi(e) != 0;
+            const int tp = (cfg->npix_per_roach + PART_TILES - 1) / PART_TILES;                // <= 8 pixels per tile
+            const int n_tiles = (cfg->npix_per_roach + tp - 1) / tp;
+            // a bucket holds four times the tile's share of the roach's words (a tile that takes more sends the surplus to
+            // the histogram directly) plus what the ranges of the roach can leave unused in their last chunks
+            int64_t cap = 0;
+            for (int q = 0; q < cfg->n_roaches; ++q) {
+                const int64_t share = n_tiles <= 4 ? w_roach[q] : std::min<int64_t>(w_roach[q], 4 * ((w_roach[q] + n_tiles - 1) / n_tiles));
+                cap = std::max<int64_t>(cap, share + r_roach[q] * (2 * PART_CHUNK + PART_FLUSH));
+            }
+            cap = (cap + PART_CHUNK - 1) / PART_CHUNK * PART_CHUNK + PART_CHUNK;
+            if (cap >= ((int64_t)1 << 31)) part = false;
+            if (part) {
+                const size_t n_buckets = (size_t)cfg->n_roaches * n_tiles;
+                char *pbuf;
+                if ((rc = mkid_scratch(ctx, SCR_AUX1, n_buckets * 4 + 256 + n_buckets * (size_t)cap * 2, (void **)&pbuf))) return rc;
+                p.part.cursor = (uint32_t *)pbuf;
+                p.part.keys = (uint16_t *)(pbuf + (n_buckets * 4 + 255) / 256 * 256);
+                p.part.cap = (uint32_t)cap; p.part.n_tiles = n_tiles; p.part.tp = tp;
+                MKID_CUDA(ctx, cudaMemsetAsync(p.part.cursor, 0, n_buckets * 4, ctx->stream));
+            }
+        }
+        const int hist_mode = !want_hist ? 0 : smem_hist ? 2 : part ? 3 : 1;
+        constexpr size_t part_smem = (size_t)DEC_WARPS * PART_SMEM_WARP;
         auto launch = [&](auto kern) { kern<<<grid, DEC_THREADS, 0, ctx->stream>>>(p); };
+        auto launch_part = [&](auto kern) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)part_smem);
+            kern<<<grid, DEC_THREADS, part_smem, ctx->stream>>>(p);
+        };
         auto stream_pass = [&](auto abs_tag) {
             constexpr bool ABS = decltype(abs_tag)::value;       // (the absolute pass is rare: one variant per mode)
             constexpr bool LO_ALWAYS = ABS;
+            if (!ABS && hist_mode == 3) {                        // (the absolute pass of the partitioned form reduces in place)
+                if (wire_fmt) { if (need_lo) launch_part(decode_stream_kernel<true, 3, true, false>); else launch_part(decode_stream_kernel<true, 3, false, false>); }
+                else { if (need_lo) launch_part(decode_stream_kernel<false, 3, true, false>); else launch_part(decode_stream_kernel<false, 3, false, false>); }
+                return;
+            }
             if (wire_fmt) {
                 if (hist_mode == 0) launch(decode_stream_kernel<true, 0, LO_ALWAYS, ABS>);
-                else if (hist_mode == 1) { if (need_lo || LO_ALWAYS) launch(decode_stream_kernel<true, 1, true, ABS>); else launch(decode_stream_kernel<true, 1, LO_ALWAYS, ABS>); }
+                else if (hist_mode == 1 || hist_mode == 3) { if (need_lo || LO_ALWAYS) launch(decode_stream_kernel<true, 1, true, ABS>); else launch(decode_stream_kernel<true, 1, LO_ALWAYS, ABS>); }
                 else { if (need_lo || LO_ALWAYS) launch(decode_stream_kernel<true, 2, true, ABS>); else launch(decode_stream_kernel<true, 2, LO_ALWAYS, ABS>); }
             } else {
                 if (hist_mode == 0) launch(decode_stream_kernel<false, 0, LO_ALWAYS, ABS>);
-                else if (hist_mode == 1) { if (need_lo || LO_ALWAYS) launch(decode_stream_kernel<false, 1, true, ABS>); else launch(decode_stream_kernel<false, 1, LO_ALWAYS, ABS>); }
+                else if (hist_mode == 1 || hist_mode == 3) { if (need_lo || LO_ALWAYS) launch(decode_stream_kernel<false, 1, true, ABS>); else launch(decode_stream_kernel<false, 1, LO_ALWAYS, ABS>); }
                 else { if (need_lo || LO_ALWAYS) launch(decode_stream_kernel<false, 2, true, ABS>); else launch(decode_stream_kernel<false, 2, LO_ALWAYS, ABS>); }
             }
         };
@@ -1384,6 +1590,14 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
         mark(0);
         stream_pass(std::false_type{});                      // relative pass: every word is read here, once
         MKID_CHECK_LAUNCH(ctx);
+        static cudaEvent_t ev_part = nullptr;            // (timing switch only)
+        if (hist_mode == 3) {
+            if (timing) { if (!ev_part) cudaEventCreate(&ev_part); cudaEventRecord(ev_part, ctx->stream); }
+            const size_t hsm = (size_t)p.part.tp * cfg->n_bins * 4;
+            MKID_CUDA(ctx, cudaFuncSetAttribute(part_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+            part_hist_kernel<<<cfg->n_roaches * p.part.n_tiles, 1024, hsm, ctx->stream>>>(p.part, p.hist, cfg->npix_per_roach, cfg->n_bins);
+            MKID_CHECK_LAUNCH(ctx);
+        }
         mark(1);
         const int cgrid = (n_ranges + DEC_COMMIT_RANGES - 1) / DEC_COMMIT_RANGES;
         if (wire_fmt) decode_commit_kernel<true><<<cgrid, 256, 0, ctx->stream>>>(p);
@@ -1399,6 +1613,12 @@ int decode_common(mkid_ctx *ctx, const uint64_t *words, const uint32_t *wire, in
             for (int i = 0; i < 3; ++i) cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]);
             fprintf(stderr, "[mkid decode timing] ranges %d | stream %.1f us  commit %.1f us  absolute %.1f us\n", n_ranges,
                     t[0] * 1e3f, t[1] * 1e3f, t[2] * 1e3f);
+            if (hist_mode == 3) {
+                float tp1 = 0.f;
+                cudaEventElapsedTime(&tp1, ev[0], ev_part);
+                fprintf(stderr, "[mkid decode timing] partitioned histogram: keys %.1f us, tiles %.1f us (%d buckets of <= %u keys)\n", tp1 * 1e3f,
+                        (t[0] - tp1) * 1e3f, cfg->n_roaches * p.part.n_tiles, p.part.cap);
+            }
         }
         if (lists) {
             // the list product needs every range resolved by its rows: more than DEC_MAX_LS seconds inside one range

@@ -67,7 +67,7 @@ def test_decode_words_ragged(ctx, field, n_bins):
     assert list(dec.sec) == [secs + 1] * R
 
 
-def test_decode_many_eos_and_empty(ctx):
+def test_decode_many_eos_and_empty(ctx, n_bins=16):
     from mkids_sdr_b200.decode import PhotonDecoder
     R, npix, secs, cap = 2, 5, 50, 2500
     rng = np.random.default_rng(2)
@@ -76,9 +76,9 @@ def test_decode_many_eos_and_empty(ctx):
     st0[rng.random(st0.size) < 0.15] = np.uint64(0xFFFFFFFFFFFFFFFF)
     st1 = np.zeros(0, dtype=np.uint64)                # empty stream
     streams = [st0, st1]
-    dec = PhotonDecoder(R, npix, secs, cap, 'peak', 16, ctx=ctx)
+    dec = PhotonDecoder(R, npix, secs, cap, 'peak', n_bins, ctx=ctx)
     dec.feed_streams(streams)
-    _check(dec, streams, npix, secs, cap, 'peak', None, 16)
+    _check(dec, streams, npix, secs, cap, 'peak', None, n_bins)
 
 
 def test_decode_piecewise_equals_whole(ctx):
@@ -136,6 +136,51 @@ def test_decode_words_dev_segments(ctx, scale):
     sec_out = sec_a.download(np.int32, R)
     assert list(sec_out) == [int(((s >> np.uint64(56)) == 255).sum()) for s in streams]
     assert ref['n_ignored'] > 0 and ref['n_corrupt_eos'] > 0
+
+
+@pytest.mark.parametrize('which', ['ragged_peak', 'ragged_base', 'ragged_lut', 'dense_eos', 'piecewise', 'dev_segments',
+                                   'wire', 'uniform_253x4096'])
+def test_partitioned_histogram_forms(ctx, monkeypatch, which):
+    """The histogram built from partitioned 16-bit keys (decode.cu HIST == 3, the MKID_DEC_PART=1 form of a histogram too
+    large for shared memory) forced on the inputs of the other tests: hot pixel whose tile overflows its bucket (the surplus
+    goes to the histogram directly), low-half field, bin LUT with out-of-range classes, dense / corrupt end-of-second words
+    and an empty stream, unaligned pieces with carried seconds, device-resident segment lengths, seconds beyond exptime
+    (taken back by the commit kernel), the wire format; and that MKID_DEC_PART=0 gives the same on a plain input."""
+    from mkids_sdr_b200 import synth
+    from mkids_sdr_b200.decode import PhotonDecoder
+    monkeypatch.setenv('MKID_DEC_PART', '1')
+    if which == 'ragged_peak':
+        test_decode_words_ragged(ctx, 'peak', 4096)
+    elif which == 'ragged_base':
+        test_decode_words_ragged(ctx, 'base', 4096)
+    elif which == 'ragged_lut':
+        R, npix, secs, cap = 3, 37, 4, 300
+        streams = _ragged_streams(22, R, npix, secs, 30000)
+        lut = np.arange(4096) * 311 // 4096                       # 311 classes, those >= 300 are out of range
+        dec = PhotonDecoder(R, npix, secs, cap, 'p1', 300, lut, ctx=ctx)
+        dec.feed_streams(streams)
+        _check(dec, streams, npix, secs, cap, 'p1', lut, 300)
+    elif which == 'dense_eos':
+        test_decode_many_eos_and_empty(ctx, 1024)
+    elif which == 'piecewise':
+        test_decode_piecewise_equals_whole(ctx)
+    elif which == 'dev_segments':
+        test_decode_words_dev_segments(ctx, 40)
+    elif which == 'wire':
+        test_decode_wire_bundles(ctx)
+    else:
+        R, npix, secs = 8, 253, 3
+        streams, _ = synth.photon_streams(4 * 10 ** 6, R, npix, secs, seed=31, n_hot=3, hot_rate=3000)
+        hists = []
+        for mode in ('1', '0'):
+            monkeypatch.setenv('MKID_DEC_PART', mode)
+            dec = PhotonDecoder(R, npix, secs, 2500, 'peak', 4096, ctx=ctx)
+            dec.feed_streams(streams)
+            hists.append(dec.hist())
+            assert np.array_equal(dec.counts_raw(), odec.packetmaster_bin(streams, npix, secs)['raw_counts'])
+        assert np.array_equal(hists[0], hists[1])
+        assert np.array_equal(hists[0], odec.pixel_field_hist(streams, npix, secs, 'peak'))
+        assert int(hists[0].sum()) > 3 * 10 ** 6
 
 
 def test_decode_wire_bundles(ctx):
