@@ -62,6 +62,7 @@ struct mkid_chan {
     // so that the detection of batch k (on another stream) can run under the channelizer kernel of batch k + 1
     int16_t *phase_set[2] = {nullptr, nullptr}; size_t phase_rows_set[2] = {0, 0};
     uint32_t *mask_set[2] = {nullptr, nullptr}; size_t mask_bytes_set[2] = {0, 0};
+    int mask_head_rpc[2] = {0, 0};       // rows per chunk of the K4 call that left the set's mask with deferred chunk heads (else 0)
     bool alternate = false;
     struct Pending { bool valid = false; int set = 0; int64_t rows = 0, T = 0, t_abs0 = 0; } pending;
     uint32_t *acc = nullptr; size_t acc_bytes = 0;
@@ -229,6 +230,8 @@ struct WsParams {
     int chunks_per_board;
     uint32_t *mask;          // [B][ceil(rows/32)][256] candidate bits, or nullptr
     int16_t *halo;           // [B][chunks][32][256]
+    int head_deferred;       // chunks > 0 start at their own first row: the candidate bits of their first M rows are left
+                             // to mask_head_kernel (which finds the baseline rows in the neighbour chunk's output)
 };
 
 #ifdef K4_WARP_ARRIVE
@@ -311,7 +314,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
     const int64_t row1 = min(row0 + (int64_t)p.rows_per_chunk, p.rows);
     // rows [row0,row1) are stored; rows from r_start on are computed (the M rows in front of the chunk feed the
     // rolling baseline of the trigger); row r is local output t = r - PRE_ROWS
-    const int64_t r_start = p.mask ? (row0 - M > 0 ? row0 - M : 0) : row0;
+    const bool own_head = p.mask && !(p.head_deferred && blockIdx.x > 0);       // this chunk recomputes its M baseline rows
+    const int64_t r_start = own_head ? (row0 - M > 0 ? row0 - M : 0) : row0;
     const int64_t tl0 = r_start - PRE_ROWS, tl1 = row1 - PRE_ROWS;
     // first frame block: floor to a multiple of 32 frames, so that block 0 is in ring phase 0 of the FIR accumulators
     const int64_t fb_first = ((2 * tl0 - 24) >> 5) << 5;
@@ -474,7 +478,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
     int16_t *phase = p.phase + (size_t)board * p.rows * NCH + c;
     // fused candidate mask (K5c): bit (r & 31) of mask[r >> 5][c] iff M*raw[r] - sum_{k=1..M} raw[r-k] < M*thr
     const int thM = M * d.thr[board * NCH + c];
-    const int64_t r_eval0 = row0 > RES_LO ? row0 : RES_LO;
+    const int64_t r_eval0 = (p.mask && !own_head) ? row0 + M : (row0 > RES_LO ? row0 : RES_LO);
     int16_t *halo = p.halo ? p.halo + (((size_t)board * p.chunks_per_board + blockIdx.x) * 32) * NCH + c : nullptr;
     uint32_t *mk = p.mask ? p.mask + (size_t)board * ((p.rows + 31) >> 5) * NCH + c : nullptr;
     int S = 0;
@@ -686,6 +690,31 @@ __global__ void edge_prep_kernel(uint32_t *cur, uint32_t *nxt, int H, const uint
         for (int64_t i = (int64_t)(blockIdx.x - 8) * blockDim.x + threadIdx.x; i < H; i += (int64_t)(gridDim.x - 8) * blockDim.x)
             h[i] = x[n - H + i];
     }
+}
+
+// Candidate bits of the first M rows of every chunk > 0 of a channelizer call (head_deferred): their rolling baseline is the
+// last M rows of the NEIGHBOUR chunk, which that chunk's CTA was still computing while K4 ran.  K4 used to recompute those M
+// rows itself in front of every chunk (M of 456 + M rows with one board per GPU); now it leaves the low M bits of the
+// chunk's first mask word clear and this kernel fills them from the stored rows - the same integer arithmetic on the same
+// int16 values.  Thread = channel, block = (chunk, board); runs in front of the resolver.
+__global__ void __launch_bounds__(NCH) mask_head_kernel(const int16_t *__restrict__ phase, int64_t rows, int rpc, int M,
+                                                        const int32_t *__restrict__ thr, uint32_t *mask) {
+    const int board = blockIdx.y, c = threadIdx.x;
+    const int64_t row0 = (int64_t)(blockIdx.x + 1) * rpc;
+    if (row0 >= rows) return;
+    const int16_t *ph = phase + (size_t)board * rows * NCH + c;
+    const int thM = M * thr[board * NCH + c];
+    int S = 0;
+    for (int k = 1; k <= M; ++k) S += ph[(row0 - k) * NCH];
+    const int n = (int)min((int64_t)M, rows - row0);
+    uint32_t bits = 0;
+    for (int i = 0; i < n; ++i) {
+        const int raw = ph[(row0 + i) * NCH];
+        if (M * raw - S < thM) bits |= 1u << i;
+        S += raw - ph[(row0 + i - M) * NCH];
+    }
+    uint32_t *w = mask + ((size_t)board * ((rows + 31) >> 5) + (row0 >> 5)) * NCH + c;
+    *w = (M >= 32 ? 0u : *w & ~((1u << M) - 1u)) | bits;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1258,6 +1287,16 @@ int run_detect(mkid_ctx *ctx, mkid_chan *ch, const int16_t *phase_dev, int64_t r
         candidates_kernel<<<gc, 256, 0, ctx->stream>>>(phase_dev, rows, d.M, d.thr, ch->mask_set[0]);
         MKID_CHECK_LAUNCH(ctx);
     }
+    if (have_mask) {
+        for (int q = 0; q < 2; ++q) {
+            const int rpc = ch->mask_head_rpc[q];
+            if (mask_ready != ch->mask_set[q] || rpc <= 0 || rows <= rpc) continue;
+            mask_head_kernel<<<dim3((unsigned)((rows - 1) / rpc), B), NCH, 0, ctx->stream>>>(phase_dev, rows, rpc, d.M, d.thr, ch->mask_set[q]);
+            MKID_CHECK_LAUNCH(ctx);
+            ch->mask_head_rpc[q] = 0;                     // (done: a second detection of the same rows must not redo it)
+            break;
+        }
+    }
     g_timer.mark(ctx->stream, "memsets");
     // (two-context pipeline: this call runs beside the next channelizer kernel, on the few SMs it leaves)
     if (ch->alternate && have_mask)
@@ -1611,7 +1650,7 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
         w.rows_per_chunk = (int)rpc;
         w.chunks_per_board = (int)((rows + rpc - 1) / rpc);
     }
-    w.mask = nullptr; w.halo = nullptr;
+    w.mask = nullptr; w.halo = nullptr; w.head_deferred = 0;
     if (detect) {       // K5c fused into K4: the candidate mask is produced while the phase is in registers
         const int64_t n_groups = (rows + 31) >> 5;
         cap = ch->mask_bytes_set[set];
@@ -1621,6 +1660,9 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
         if ((rc = ensure(ctx, (void **)&ch->halo, &cap, (size_t)B * w.chunks_per_board * 32 * NCH * 2))) return rc;
         ch->halo_bytes = cap;
         w.mask = ch->mask_set[set]; w.halo = ch->halo;
+        static const bool head_off = getenv("MKID_K4_HEAD") && atoi(getenv("MKID_K4_HEAD")) == 0;      // experiment switch
+        w.head_deferred = (!head_off && w.chunks_per_board > 1) ? 1 : 0;
+        ch->mask_head_rpc[set] = w.head_deferred ? w.rows_per_chunk : 0;
     }
     g_timer.report();
     g_timer.mark(ctx->stream, "start");
