@@ -44,7 +44,7 @@ struct ChanDev {                         // device-resident configuration + stat
     float *gain;          // [B][256] 0 (zeroed FIR) or 1 (kept for reporting; the kernel uses the zeroed DDS entries)
     float *cen_i, *cen_q; // [B][256] 8*I_c, 8*Q_c
     int32_t *thr;         // [B][256]
-    uint32_t *hist;       // [B][H + 2048] input history (packed int16 I,Q), then the first 2048 samples of the current call
+    uint32_t *hist;       // 2 x [B][H + 2048] input history (packed int16 I,Q; the 2048 behind it are unused), alternating per call
     int64_t *t_next;      // [B][256]
     int H;
     // board b: the half-frame hop sign of odd bins, (-1)^(bin (f + 1)), is folded into the DDS rows with even index (always,
@@ -220,7 +220,8 @@ static_assert(WS_ADC_AHEAD >= 1 && 3 * WS_NBUF + 1 <= 16, "stage / barrier budge
 struct WsParams {
     ChanDev d;
     const uint32_t *in;      // [B][n] packed samples of this call
-    const uint32_t *edge;    // [B][H + 2048]: history, then a copy of the first 2048 samples of the call
+    const uint32_t *edge;    // [B][H + 2048]: the last H samples in front of this call (left there by the previous one)
+    uint32_t *edge_next;     // the same for the NEXT call: the PFB role of every chunk copies its slice of this call's last H samples
     int64_t n;
     int64_t f0_abs;          // absolute frame index of local frame 0 (always even)
     int16_t *phase;          // [B][rows][256]
@@ -411,14 +412,23 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
     if (tid < 3 * NCH) {
         // =============================== PFB: polyphase filter + first radix-2 stage ===============================
         asm volatile("setmaxnreg.dec.sync.aligned.u32 " K4_STR(K4_REGS_PFB) ";");
-        if (n_blocks == 0) return;
         const int k = tid - 2 * NCH;                                  // branches k and k + 256
+        // the input history of the NEXT call (its last H samples), a slice per chunk, once this role has nothing else to do:
+        // it was a kernel of its own between two channelizer launches (6.6 us of a 1.25 ms step)
+        auto save_history = [&]() {
+            const int n16 = d.H / 4, per = (n16 + (int)gridDim.x - 1) / (int)gridDim.x;
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.in + (size_t)board * p.n + (p.n - d.H));
+            uint4 *dst = reinterpret_cast<uint4 *>(p.edge_next + (size_t)board * (d.H + 2048));
+            const int i1 = min(n16, ((int)blockIdx.x + 1) * per);
+            for (int i = (int)blockIdx.x * per + k; i < i1; i += NCH) dst[i] = src[i];
+        };
+        if (n_blocks == 0) { save_history(); return; }
         float hA[PTAPS], hB[PTAPS];
 #pragma unroll
         for (int q = 0; q < PTAPS; ++q) { hA[q] = d.window[NFFT * q + k]; hB[q] = d.window[NFFT * q + HOP + k]; }
         const float2 w512 = d.tw512[k];
         const uint32_t *in = p.in + (size_t)board * p.n;
-        const uint32_t *edge = p.edge + (size_t)board * (d.H + 2048) + d.H;   // edge[idx] valid for -H <= idx < 2048
+        const uint32_t *edge = p.edge + (size_t)board * (d.H + 2048) + d.H;   // edge[idx] valid for -H <= idx < 0
         auto arm_adc = [&](int blk) {                                 // elected thread: block blk -> stage blk mod 6
             const int st = blk % WS_ADC_STAGES;
             const int64_t s0 = HOP * (fb_first + (int64_t)blk * FB);
@@ -463,6 +473,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
             }
             ho_arrive(HO_U_FULL(buf));
         }
+        save_history();
         return;
     }
 
@@ -674,23 +685,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) channelize_ws_kernel(WsParams p
 #endif
 }
 
-// edge[b] = [history (H samples) | first 2048 samples of this call].  Two edge buffers alternate from call to call: ONE
-// small kernel in front of the channelizer kernel copies the head of this call's input behind the history of `cur` (left
-// there by the previous call) and the last H samples of this call's input into the history of `nxt` (for the next call),
-// so that nothing stands between two channelizer launches but this copy (it was a head copy before and a history copy
-// after K4: 13 us during which the detection tail of the previous batch spread over the SMs).
-__global__ void edge_prep_kernel(uint32_t *cur, uint32_t *nxt, int H, const uint32_t *in, int64_t n) {
-    const int board = blockIdx.y;
-    const uint32_t *x = in + (size_t)board * n;
-    if (blockIdx.x < 8) {
-        const int i = blockIdx.x * blockDim.x + threadIdx.x;
-        if (i < 2048) cur[(size_t)board * (H + 2048) + H + i] = x[i];
-    } else {
-        uint32_t *h = nxt + (size_t)board * (H + 2048);
-        for (int64_t i = (int64_t)(blockIdx.x - 8) * blockDim.x + threadIdx.x; i < H; i += (int64_t)(gridDim.x - 8) * blockDim.x)
-            h[i] = x[n - H + i];
-    }
-}
+// edge[b] = [history (H samples) | 2048 unused].  Two edge buffers alternate from call to call: call k reads buffer k & 1 (the H
+// samples in front of it) and its PFB roles leave the last H samples of its own input in the other one.  Blocks of 8 frames
+// start at multiples of 2048 samples, so no TMA copy straddles the start of the call.  (Round 1 copied history after K4 and
+// the head of the call in front of it; later one edge_prep kernel in front of K4 did both; now nothing stands between two
+// channelizer launches.)
 
 // Candidate bits of the first M rows of every chunk > 0 of a channelizer call (head_deferred): their rolling baseline is the
 // last M rows of the NEIGHBOUR chunk, which that chunk's CTA was still computing while K4 ran.  K4 used to recompute those M
@@ -1635,7 +1634,7 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     uint32_t *const edge_cur = d.hist + (size_t)((ch->n_calls_edge) & 1) * B * (d.H + 2048);
     uint32_t *const edge_nxt = d.hist + (size_t)((ch->n_calls_edge + 1) & 1) * B * (d.H + 2048);
     ch->n_calls_edge++;
-    w.d = d; w.in = in_dev; w.edge = edge_cur; w.n = n; w.f0_abs = 2 * ch->t_consumed; w.phase = phase_buf; w.phase_f32 = ch->f32_out; w.rows = rows;
+    w.d = d; w.in = in_dev; w.edge = edge_cur; w.edge_next = edge_nxt; w.n = n; w.f0_abs = 2 * ch->t_consumed; w.phase = phase_buf; w.phase_f32 = ch->f32_out; w.rows = rows;
     {
         // two-context pipeline: leave 4 SMs to the detection / decode kernels of the previous batch, which run on the other
         // context's stream at the same time (with 8 boards 144 of 148 SMs are taken either way; with one board per GPU the
@@ -1671,9 +1670,6 @@ extern "C" int mkid_chan_process(mkid_ctx *ctx, mkid_chan *ch, const int16_t *iq
     ch->n_calls++;
     {
         const size_t smem = (size_t)(WS_NBUF * 16 * FFT_STRIDE + 256) * sizeof(float2) + (size_t)(WS_ADC_STAGES + WS_DDS_STAGES) * FB * NCH * 4;
-        // edge buffer <- first 2048 samples of this call (behind the history of the previous ones)
-        edge_prep_kernel<<<dim3(8 + 32, B), 256, 0, ctx->stream>>>(edge_cur, edge_nxt, d.H, in_dev, n);
-        MKID_CHECK_LAUNCH(ctx);
         MKID_CUDA(ctx, cudaEventRecord(evp[0], ctx->stream));
         bool all_fold = true;
         for (int b = 0; b < B; ++b) all_fold = all_fold && d.fold[b];
