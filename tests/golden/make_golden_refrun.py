@@ -493,7 +493,70 @@ def run_contsnapshot_loop():
     return out
 
 
+def function_source(path, name):
+    """A module-level function of a Python-2 file as Python-3 text (print statements, xrange)."""
+    lines = open(path).read().expandtabs(8).splitlines()
+    i0 = next(i for i, l in enumerate(lines) if re.match(r'^def %s\(' % name, l))
+    i1 = next((i for i in range(i0 + 1, len(lines)) if re.match(r'^\S', lines[i])), len(lines))
+    out = []
+    for line in lines[i0:i1]:
+        m = re.match(r'^(\s*)print\s+(.*)$', line)
+        if m and not m.group(2).startswith('('):
+            line = '%sprint(%s)' % (m.group(1), m.group(2))
+        out.append(line.replace('xrange', 'range'))
+    return '\n'.join(out) + '\n'
+
+
+def run_pulses_quicklook():
+    """QuickLook of ReadoutControls/lib/pulses.py:210-236 executed on a stand-in for the observation file: a 32 x 32
+    beammap of dataset names and, per pixel, one photon list per second whose length is what PacketMaster stored (the
+    capped count).  The image handed to imshow is the golden output."""
+    path = os.path.join(ref, 'DataReadout', 'ReadoutControls', 'lib', 'pulses.py')
+    rng = numpy.random.default_rng(23)
+    secs, npix = 6, 1024
+    counts = numpy.minimum(rng.poisson(rng.uniform(5, 400, npix), (secs, npix)), 2499).astype(numpy.int64)
+    counts[:, 77] = 2499                                   # a pixel at the cap
+    adr = rng.permutation(npix).reshape(32, 32)
+    names = [['/r%d/p%d/' % (a // 256, a % 256) for a in row] for row in adr]
+
+    class Node:
+        def __init__(self, value):
+            self.value = value
+
+        def read(self):
+            return self.value
+
+    class H5:
+        def __init__(self):
+            self.root = self
+            self.beammap = self
+            self.beamimage = Node(names)
+
+        def _f_getChild(self, name):
+            r, p_ = re.match(r'/r(\d+)/p(\d+)/', name).groups()
+            pix = int(r) * 256 + int(p_)
+            return Node([numpy.zeros(int(c), dtype=numpy.uint64) for c in counts[:, pix]])
+
+        def close(self):
+            pass
+
+    shown = []
+    plt = mock.MagicMock()
+    plt.figure.return_value.add_subplot.return_value.imshow.side_effect = lambda img, **k: shown.append(numpy.array(img))
+    ns = dict(np=numpy, openFile=lambda *a, **k: H5(), plt=plt)
+    exec(compile(function_source(path, 'QuickLook'), 'pulses.py:QuickLook', 'exec'), ns)
+    out = dict(ql_counts=counts, ql_adr=adr.astype(numpy.int32))
+    for i, (t0, t1) in enumerate(((0, 6), (2, 5), (3, 4))):
+        ns['QuickLook']('obs.h5', t0, t1)
+        out['ql_span_%d' % i] = numpy.array([t0, t1])
+        out['ql_skysub_%d' % i] = shown[-1]
+    return out
+
+
 if __name__ == '__main__':
+    ql = run_pulses_quicklook()
+    numpy.savez_compressed(os.path.join(here, 'quicklook_golden.npz'), **ql)
+    print('wrote quicklook_golden.npz:', {k: numpy.asarray(v).shape for k, v in ql.items()})
     out = {}
     out.update(run_setup_dac())
     out.update(run_pulses())

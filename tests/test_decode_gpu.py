@@ -183,6 +183,23 @@ def test_partitioned_histogram_forms(ctx, monkeypatch, which):
         assert int(hists[0].sum()) > 3 * 10 ** 6
 
 
+def test_quicklook_matches_reference_run(ctx, golden_dir):
+    """decode.QuickLook on the GPU against pulses.QuickLook itself (lib/pulses.py:210-236, run by
+    tests/golden/make_golden_refrun.py on a stand-in observation file): the decoder's count array is loaded with the
+    golden per-second counts, the preview must be the image the reference handed to imshow."""
+    from mkids_sdr_b200 import _lib
+    from mkids_sdr_b200.decode import PhotonDecoder, QuickLook
+    g = np.load(os.path.join(golden_dir, 'quicklook_golden.npz'))
+    counts = np.ascontiguousarray(g['ql_counts'], dtype=np.uint32)
+    secs, n_pix = counts.shape
+    dec = PhotonDecoder(8, n_pix // 8, secs, 2500, None, 1, ctx=ctx)
+    ctx._check(ctx.lib.mkid_memcpy(ctx.h, _lib.ptr(dec.counts_dev), _lib.ptr(counts), counts.nbytes))
+    ctx.sync()
+    for i in range(3):
+        t0, t1 = (int(v) for v in g['ql_span_%d' % i])
+        assert np.array_equal(QuickLook(dec, g['ql_adr'], t0, t1), g['ql_skysub_%d' % i]), (t0, t1)
+
+
 def test_decode_wire_bundles(ctx):
     from mkids_sdr_b200 import synth
     from mkids_sdr_b200.decode import PhotonDecoder

@@ -36,3 +36,14 @@ def test_quicklook_skysub_oracle():
     image = counts[1:4].sum(axis=0)[adr].astype(np.float64)
     assert out.dtype == np.float32 and np.array_equal(out, np.float32(image - np.median(image)))
     assert np.array_equal(odec.quicklook_skysub(counts, adr, 2, 2), np.zeros((3, 4), np.float32))
+
+
+def test_quicklook_oracle_matches_reference_run():
+    """oracle.decode.quicklook_skysub against pulses.QuickLook itself (lib/pulses.py:210-236), executed on a stand-in
+    observation file by tests/golden/make_golden_refrun.py::run_pulses_quicklook."""
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'quicklook_golden.npz'))
+    for i in range(3):
+        t0, t1 = (int(v) for v in g['ql_span_%d' % i])
+        want = g['ql_skysub_%d' % i]
+        got = odec.quicklook_skysub(g['ql_counts'], g['ql_adr'], t0, t1)
+        assert want.dtype == np.float32 and got.dtype == np.float32 and np.array_equal(got, want), (t0, t1)
